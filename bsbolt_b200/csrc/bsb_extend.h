@@ -1,0 +1,283 @@
+// bsb_extend.h -- chain -> alignment regions for one read (north_star stage 5).
+//
+//   global_core()        <- bwa_gen_cigar2 part 1       (bwa.c:199-249)  score (and CIGAR) between fixed end points
+//   chain_to_regions()   <- mem_chain2aln               (bwamem.c:636-790)
+//   patch_regions()      <- mem_patch_reg               (bwamem.c:410-439)
+//   sort_dedup_patch()   <- mem_sort_dedup_patch        (bwamem.c:441-493)
+#pragma once
+#include "bsb_ksw.h"
+#include "bsb_chain.h"
+
+namespace bsb {
+
+BSB_HD int cal_max_gap(const Opt &opt, int qlen)
+{
+    int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
+    int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+    int l = l_del > l_ins ? l_del : l_ins;
+    l = l > 1 ? l : 1;
+    return l < opt.w << 1 ? l : opt.w << 1;
+}
+
+struct DpScratch {        // per-thread DP scratch in HBM
+    int32_t *eh;          // 2*(max_q+1)
+    uint8_t *z;           // traceback, z_cap bytes
+    long z_cap;
+    int max_q;
+};
+
+// Global alignment of query[0,l_query) against reference [rb,re) (doubled coordinates).
+// Returns false when the reference rejects the request (bwa.c:212, 215). When `cig` is null only
+// the score is produced (this is what region patching needs).
+BSB_HD bool global_core(const Opt &opt, const IndexView &ix, int w_, int l_query, const uint8_t *query,
+                        int64_t rb, int64_t re, int *score, CigarBuf *cig, DpScratch &dp, int *err)
+{
+    const int64_t l_pac = ix.l_pac;
+    if (cig) cig->n = 0;
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;
+    // bns_get_seq clamps to [0, 2*l_pac); a clamped fetch has the wrong length and is rejected
+    if (re > (l_pac << 1) || rb < 0) return false;
+    int64_t rlen = re - rb;
+    QrySeq q; RefSeq t;
+    if (rb >= l_pac) { // reverse both so that gaps are left-aligned on the forward strand
+        q.base = query + (l_query - 1); q.dir = -1;
+        t.pac = ix.pac; t.l_pac = l_pac; t.start = re - 1; t.dir = -1;
+    } else {
+        q.base = query; q.dir = 1;
+        t.pac = ix.pac; t.l_pac = l_pac; t.start = rb; t.dir = 1;
+    }
+    if (l_query == rlen && w_ == 0) {
+        if (cig) cig->push(0, l_query);
+        int sc = 0;
+        for (int i = 0; i < l_query; ++i) sc += opt.mat[t(i) * 5 + q(i)];
+        *score = sc;
+    } else {
+        int w, max_gap, max_ins, max_del, min_w;
+        max_ins = (int)((double)(((l_query + 1) >> 1) * opt.mat[0] - opt.o_ins) / opt.e_ins + 1.);
+        max_del = (int)((double)(((l_query + 1) >> 1) * opt.mat[0] - opt.o_del) / opt.e_del + 1.);
+        max_gap = max_ins > max_del ? max_ins : max_del;
+        max_gap = max_gap > 1 ? max_gap : 1;
+        w = (max_gap + iabs((int)rlen - l_query) + 1) >> 1;
+        w = w < w_ ? w : w_;
+        min_w = iabs((int)rlen - l_query) + 3;
+        w = w > min_w ? w : min_w;
+        if (l_query > dp.max_q) { *err = ERR_SCRATCH_OVERFLOW; return false; }
+        if (cig) {
+            long n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
+            if (n_col * rlen > dp.z_cap) { *err = ERR_SCRATCH_OVERFLOW; return false; }
+        }
+        *score = nw_global(l_query, q, (int)rlen, t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, dp.eh, dp.z, cig, err);
+    }
+    return true;
+}
+
+BSB_HD void alnreg_clear(AlnReg &a)
+{
+    a.rb = a.re = 0; a.qb = a.qe = 0; a.rid = 0; a.score = a.truesc = a.sub = a.alt_sc = a.csub = a.sub_n = 0;
+    a.w = a.seedcov = a.secondary = a.secondary_all = a.seedlen0 = a.n_comp = a.is_alt = 0;
+    a.frac_rep = 0; a.hash = 0;
+}
+
+struct RegList { AlnReg *a; int n, cap; };
+
+// Extends the seeds of one chain (longest first) and appends the regions to av.
+// cs: the chain's seeds (contiguous); srt: scratch u64[c.n]
+BSB_HD void chain_to_regions(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query,
+                             const Chain &c, const Seed *cs, uint64_t *srt, RegList &av, DpScratch &dp, int *err)
+{
+    int i, k, max_off[2], aw[2];
+    const int64_t l_pac = ix.l_pac;
+    int64_t rmax[2], tmp, max = 0;
+    if (c.n == 0) return;
+    rmax[0] = l_pac << 1; rmax[1] = 0;
+    for (i = 0; i < c.n; ++i) {
+        const Seed &t = cs[i];
+        int64_t b = t.rbeg - (t.qbeg + cal_max_gap(opt, t.qbeg));
+        int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + cal_max_gap(opt, l_query - t.qbeg - t.len));
+        rmax[0] = rmax[0] < b ? rmax[0] : b;
+        rmax[1] = rmax[1] > e ? rmax[1] : e;
+        if (t.len > max) max = t.len;
+    }
+    rmax[0] = rmax[0] > 0 ? rmax[0] : 0;
+    rmax[1] = rmax[1] < l_pac << 1 ? rmax[1] : l_pac << 1;
+    if (rmax[0] < l_pac && l_pac < rmax[1]) {
+        if (cs[0].rbeg < l_pac) rmax[1] = l_pac;
+        else rmax[0] = l_pac;
+    }
+    fetch_window(ix, &rmax[0], cs[0].rbeg, &rmax[1]);
+    if (l_query > dp.max_q) { *err = ERR_SCRATCH_OVERFLOW; return; }
+
+    for (i = 0; i < c.n; ++i) srt[i] = (uint64_t)cs[i].score << 32 | (uint32_t)i;
+    introsort((long)c.n, srt, LtU64());
+
+    for (k = c.n - 1; k >= 0; --k) {
+        const Seed &s = cs[(uint32_t)srt[k]];
+        for (i = 0; i < av.n; ++i) { // already covered by an earlier extension?
+            const AlnReg &p = av.a[i];
+            int64_t rd;
+            int qd, w, max_gap;
+            if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+            if (s.len - p.seedlen0 > .1 * l_query) continue;
+            qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
+            max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+            w = max_gap < p.w ? max_gap : p.w;
+            if (qd - rd < w && rd - qd < w) break;
+            qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+            max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+            w = max_gap < p.w ? max_gap : p.w;
+            if (qd - rd < w && rd - qd < w) break;
+        }
+        if (i < av.n) {
+            for (i = k + 1; i < c.n; ++i) { // an overlapping, non-colinear longer seed forces an extension
+                if (srt[i] == 0) continue;
+                const Seed &t = cs[(uint32_t)srt[i]];
+                if (t.len < s.len * .95) continue;
+                if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+                if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+            }
+            if (i == c.n) { srt[k] = 0; continue; }
+        }
+        if (av.n >= av.cap) { *err = ERR_SCRATCH_OVERFLOW; return; }
+        AlnReg &a = av.a[av.n++];
+        alnreg_clear(a);
+        a.w = aw[0] = aw[1] = opt.w;
+        a.score = a.truesc = -1;
+        a.rid = c.rid;
+
+        if (s.qbeg) { // left extension over the reversed prefix
+            QrySeq qs = {query + (s.qbeg - 1), -1};
+            RefSeq rs = {ix.pac, l_pac, s.rbeg - 1, -1};
+            tmp = s.rbeg - rmax[0];
+            ExtResult x = {0, 0, 0, 0, 0, 0};
+            for (i = 0; i < 2; ++i) {
+                int prev = a.score;
+                aw[0] = opt.w << i;
+                x = sw_extend(s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0], opt.pen_clip5, opt.zdrop, s.len * opt.a, dp.eh);
+                a.score = x.score; max_off[0] = x.max_off;
+                if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
+            }
+            if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip5) {
+                a.qb = s.qbeg - x.qle; a.rb = s.rbeg - x.tle;
+                a.truesc = a.score;
+            } else {
+                a.qb = 0; a.rb = s.rbeg - x.gtle;
+                a.truesc = x.gscore;
+            }
+        } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+
+        if (s.qbeg + s.len != l_query) { // right extension
+            int qe = s.qbeg + s.len, sc0 = a.score;
+            int64_t re = s.rbeg + s.len - rmax[0];
+            QrySeq qs = {query + qe, 1};
+            RefSeq rs = {ix.pac, l_pac, rmax[0] + re, 1};
+            ExtResult x = {0, 0, 0, 0, 0, 0};
+            for (i = 0; i < 2; ++i) {
+                int prev = a.score;
+                aw[1] = opt.w << i;
+                x = sw_extend(l_query - qe, qs, (int)(rmax[1] - rmax[0] - re), rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, dp.eh);
+                a.score = x.score; max_off[1] = x.max_off;
+                if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
+            }
+            if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip3) {
+                a.qe = qe + x.qle; a.re = rmax[0] + re + x.tle;
+                a.truesc += a.score - sc0;
+            } else {
+                a.qe = l_query; a.re = rmax[0] + re + x.gtle;
+                a.truesc += x.gscore - sc0;
+            }
+        } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+
+        a.seedcov = 0;
+        for (i = 0; i < c.n; ++i) {
+            const Seed &t = cs[i];
+            if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+        }
+        a.w = aw[0] > aw[1] ? aw[0] : aw[1];
+        a.seedlen0 = s.len;
+        a.frac_rep = c.frac_rep;
+    }
+}
+
+// Can regions a (left) and b (right) be one alignment? Returns the merged score or 0.
+BSB_HD int patch_regions(const Opt &opt, const IndexView &ix, const uint8_t *query, const AlnReg &a, const AlnReg &b, int *_w, DpScratch &dp, int *err)
+{
+    int w, score = 0, q_s, r_s;
+    double r;
+    if (query == nullptr) return 0;
+    if (a.rb < ix.l_pac && b.rb >= ix.l_pac) return 0;
+    if (a.qb >= b.qb || a.qe >= b.qe || a.re >= b.re) return 0;
+    w = (int)((a.re - b.rb) - (a.qe - b.qb));
+    w = w > 0 ? w : -w;
+    r = (double)(a.re - b.rb) / (b.re - a.rb) - (double)(a.qe - b.qb) / (b.qe - a.qb);
+    r = r > 0. ? r : -r;
+    if (a.re < b.rb || a.qe < b.qb) {
+        if (w > opt.w << 1 || r >= 0.05f) return 0;
+    } else if (w > opt.w << 2 || r >= 0.05f * 2) return 0;
+    w += a.w + b.w;
+    w = w < opt.w << 2 ? w : opt.w << 2;
+    if (!global_core(opt, ix, w, b.qe - a.qb, query + a.qb, a.rb, b.re, &score, nullptr, dp, err)) return 0;
+    q_s = (int)((double)(b.qe - a.qb) / ((b.qe - b.qb) + (a.qe - a.qb)) * (b.score + a.score) + .499);
+    r_s = (int)((double)(b.re - a.rb) / ((b.re - b.rb) + (a.re - a.rb)) * (b.score + a.score) + .499);
+    if ((double)score / (q_s > r_s ? q_s : r_s) < 0.90f) return 0;
+    *_w = w;
+    return score;
+}
+
+struct LtRegRe { BSB_HD bool operator()(const AlnReg &a, const AlnReg &b) const { return a.re < b.re; } };
+struct LtRegScore {
+    BSB_HD bool operator()(const AlnReg &a, const AlnReg &b) const
+    { return a.score > b.score || (a.score == b.score && (a.rb < b.rb || (a.rb == b.rb && a.qb < b.qb))); }
+};
+
+// query == nullptr disables patching (mate-rescue call site, bwamem_pair.c:175)
+BSB_HD int sort_dedup_patch(const Opt &opt, const IndexView &ix, const uint8_t *query, int n, AlnReg *a, DpScratch &dp, int *err)
+{
+    int m, i, j;
+    if (n <= 1) return n;
+    introsort((long)n, a, LtRegRe());
+    for (i = 0; i < n; ++i) a[i].n_comp = 1;
+    for (i = 1; i < n; ++i) {
+        AlnReg &p = a[i];
+        if (p.rid != a[i - 1].rid || p.rb >= a[i - 1].re + opt.max_chain_gap) continue;
+        for (j = i - 1; j >= 0 && p.rid == a[j].rid && p.rb < a[j].re + opt.max_chain_gap; --j) {
+            AlnReg &q = a[j];
+            int64_t orr, oq, mr, mq;
+            int score, w;
+            if (q.qe == q.qb) continue;
+            orr = q.re - p.rb;
+            oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+            mr = q.re - q.rb < p.re - p.rb ? q.re - q.rb : p.re - p.rb;
+            mq = q.qe - q.qb < p.qe - p.qb ? q.qe - q.qb : p.qe - p.qb;
+            if (orr > opt.mask_level_redun * mr && oq > opt.mask_level_redun * mq) {
+                if (p.score < q.score) { p.qe = p.qb; break; }
+                else q.qe = q.qb;
+            } else if (q.rb < p.rb && (score = patch_regions(opt, ix, query, q, p, &w, dp, err)) > 0) {
+                p.n_comp += q.n_comp + 1;
+                p.seedcov = p.seedcov > q.seedcov ? p.seedcov : q.seedcov;
+                p.sub = p.sub > q.sub ? p.sub : q.sub;
+                p.csub = p.csub > q.csub ? p.csub : q.csub;
+                p.qb = q.qb; p.rb = q.rb;
+                p.truesc = p.score = score;
+                p.w = w;
+                q.qb = q.qe;
+            }
+        }
+    }
+    for (i = 0, m = 0; i < n; ++i)
+        if (a[i].qe > a[i].qb) {
+            if (m != i) a[m++] = a[i];
+            else ++m;
+        }
+    n = m;
+    introsort((long)n, a, LtRegScore());
+    for (i = 1; i < n; ++i)
+        if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+    for (i = 1, m = 1; i < n; ++i)
+        if (a[i].qe > a[i].qb) {
+            if (m != i) a[m++] = a[i];
+            else ++m;
+        }
+    return m;
+}
+
+} // namespace bsb

@@ -1,0 +1,242 @@
+// bsb_index.h -- the HBM-resident index view and the FM-index / reference-fetch primitives.
+//
+// Layout in HBM (identical to the reference's on-disk/in-RAM layout):
+//   bwt   : one 64-byte block per 128 BWT symbols = 4 x u64 cumulative A/C/G/T counts followed by
+//           8 x u32 packed symbols (symbol i of a word at bits 30-2*(i&15))   (bwt.h:72-78)
+//   sa    : SA sampled every `sa_intv` ranks, u64 entries, sa[0] = -1               (bwt.c:61-84)
+//   pac   : converted reference, 2 bit/base, forward strands only: watson(C->T) contigs then
+//           crick(G->A) contigs; opac: the same coordinates, unconverted bases    (bntseq.c:239-361)
+// A block is 64-byte aligned, so one occ query is exactly two 32-byte sectors.
+#pragma once
+#include "bsb_hd.h"
+
+namespace bsb {
+
+struct IndexView {
+    const uint32_t *bwt;
+    const uint64_t *sa;
+    const uint8_t *pac, *opac;
+    const Ann *anns;
+    uint64_t primary, L2[5], seq_len;
+    int64_t l_pac, crick_l;
+    int32_t n_seqs, sa_intv;
+    // optional result-preserving denser SA (values are independent of the sampling rate)
+    const uint32_t *sa32;   // when non-null: SA sampled every sa32_intv ranks, 32-bit entries (seq_len < 2^32)
+    int32_t sa32_intv, pad_;
+};
+
+// ---- occurrence counting -------------------------------------------------------------------
+
+// per-symbol match mask of one packed word: bit 2j set iff symbol j (from the LSB pair) == c
+BSB_HD uint32_t sym_eq_mask(uint32_t w, int c)
+{
+    uint32_t x = w ^ (0x55555555u * (uint32_t)c); // equal symbols become 00
+    return ~(x | (x >> 1)) & 0x55555555u;
+}
+
+BSB_HD int popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+struct OccBlock { uint64_t cnt[4]; uint32_t w[8]; };
+
+BSB_HD void load_block(const uint32_t *bwt, uint64_t blk, OccBlock &b)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 *p = reinterpret_cast<const uint4 *>(bwt + (blk << 4));
+    uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+    b.cnt[0] = (uint64_t)v0.y << 32 | v0.x; b.cnt[1] = (uint64_t)v0.w << 32 | v0.z;
+    b.cnt[2] = (uint64_t)v1.y << 32 | v1.x; b.cnt[3] = (uint64_t)v1.w << 32 | v1.z;
+    b.w[0] = v2.x; b.w[1] = v2.y; b.w[2] = v2.z; b.w[3] = v2.w;
+    b.w[4] = v3.x; b.w[5] = v3.y; b.w[6] = v3.z; b.w[7] = v3.w;
+#else
+    const uint32_t *p = bwt + (blk << 4);
+    for (int i = 0; i < 4; ++i) b.cnt[i] = (uint64_t)p[2 * i + 1] << 32 | p[2 * i];
+    for (int i = 0; i < 8; ++i) b.w[i] = p[8 + i];
+#endif
+}
+
+// counts of A,C,G,T in BWT[block_start .. block_start + r] (r in [0,127]), added to the block's
+// cumulative counts. Restates bwt_occ4 (bwt.c:169-186) with popcounts instead of the byte table.
+BSB_HD void block_occ4(const OccBlock &b, int r, uint64_t cnt[4])
+{
+    int nfull = r >> 4;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i <= nfull) {
+            uint32_t keep = 0x55555555u;
+            if (i == nfull) keep &= ~((1u << ((~r & 15) << 1)) - 1u);
+            uint32_t w = b.w[i];
+            uint32_t hi = (w >> 1) & 0x55555555u, lo = w & 0x55555555u;
+            c0 += popc32(~hi & ~lo & keep);
+            c1 += popc32(~hi & lo & keep);
+            c2 += popc32(hi & ~lo & keep);
+            c3 += popc32(hi & lo & keep);
+        }
+    }
+    cnt[0] = b.cnt[0] + c0; cnt[1] = b.cnt[1] + c1; cnt[2] = b.cnt[2] + c2; cnt[3] = b.cnt[3] + c3;
+}
+
+BSB_HD void occ4(const IndexView &ix, uint64_t k, uint64_t cnt[4])
+{
+    if (k == (uint64_t)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
+    k -= (k >= ix.primary);
+    OccBlock b;
+    load_block(ix.bwt, k >> 7, b);
+    block_occ4(b, (int)(k & 127), cnt);
+}
+
+// bwt_2occ4 (bwt.c:189-220): one block load when k and l fall into the same block.
+BSB_HD void occ4_pair(const IndexView &ix, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4])
+{
+    uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
+    if ((_l >> 7) != (_k >> 7) || k == (uint64_t)-1 || l == (uint64_t)-1) {
+        occ4(ix, k, ck);
+        occ4(ix, l, cl);
+    } else {
+        OccBlock b;
+        load_block(ix.bwt, _k >> 7, b);
+        block_occ4(b, (int)(_k & 127), ck);
+        block_occ4(b, (int)(_l & 127), cl);
+    }
+}
+
+// bwt_extend (bwt.c:262-275)
+BSB_HD void fm_extend(const IndexView &ix, const Intv &ik, Intv ok[4], int is_back)
+{
+    uint64_t tk[4], tl[4];
+    uint64_t xa = is_back ? ik.x0 : ik.x1; // x[!is_back]
+    uint64_t xb = is_back ? ik.x1 : ik.x0; // x[is_back]
+    occ4_pair(ix, xa - 1, xa - 1 + ik.x2, tk, tl);
+    uint64_t na[4], sz[4], nb[4];
+    for (int i = 0; i < 4; ++i) {
+        na[i] = ix.L2[i] + 1 + tk[i];
+        sz[i] = tl[i] - tk[i];
+    }
+    nb[3] = xb + (xa <= ix.primary && xa + ik.x2 - 1 >= ix.primary);
+    nb[2] = nb[3] + sz[3];
+    nb[1] = nb[2] + sz[2];
+    nb[0] = nb[1] + sz[1];
+    for (int i = 0; i < 4; ++i) {
+        if (is_back) { ok[i].x0 = na[i]; ok[i].x1 = nb[i]; }
+        else { ok[i].x1 = na[i]; ok[i].x0 = nb[i]; }
+        ok[i].x2 = sz[i];
+    }
+}
+
+BSB_HD void fm_set_intv(const IndexView &ix, int c, Intv &ik)
+{
+    ik.x0 = ix.L2[c] + 1;
+    ik.x2 = ix.L2[c + 1] - ix.L2[c];
+    ik.x1 = ix.L2[3 - c] + 1;
+    ik.info = 0;
+}
+
+// ---- suffix-array lookup -------------------------------------------------------------------
+
+// one LF step: bwt_invPsi (bwt.c:53-59) with the symbol fetch and the rank sharing one block load
+BSB_HD uint64_t fm_lf(const IndexView &ix, uint64_t k)
+{
+    if (k == ix.primary) return 0;
+    uint64_t x = k - (k > ix.primary);
+    OccBlock b;
+    load_block(ix.bwt, x >> 7, b);
+    int r = (int)(x & 127);
+    int c = (b.w[r >> 4] >> ((~r & 15) << 1)) & 3;
+    // rank of c in BWT[0..x]
+    uint32_t n = 0;
+    int nfull = r >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i <= nfull) {
+            uint32_t m = sym_eq_mask(b.w[i], c);
+            if (i == nfull) m &= ~((1u << ((~r & 15) << 1)) - 1u);
+            n += popc32(m);
+        }
+    }
+    return ix.L2[c] + b.cnt[c] + n;
+}
+
+// bwt_sa (bwt.c:86-96)
+BSB_HD uint64_t fm_sa(const IndexView &ix, uint64_t k)
+{
+    uint64_t steps = 0;
+    if (ix.sa32) {
+        uint64_t mask = (uint64_t)ix.sa32_intv - 1;
+        while (k & mask) { ++steps; k = fm_lf(ix, k); }
+        uint64_t j = k / (uint64_t)ix.sa32_intv;
+        uint64_t v = j == 0 ? (uint64_t)-1 : (uint64_t)ix.sa32[j];
+        return steps + v;
+    }
+    uint64_t mask = (uint64_t)ix.sa_intv - 1;
+    while (k & mask) { ++steps; k = fm_lf(ix, k); }
+    return steps + ix.sa[k / (uint64_t)ix.sa_intv];
+}
+
+// ---- reference coordinates & sequence --------------------------------------------------------
+
+BSB_HD int pac_get(const uint8_t *pac, int64_t l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }
+
+// base at doubled coordinate p in [0, 2*l_pac): reverse half is the reverse complement (bntseq.c:413-434)
+BSB_HD int ref_base(const uint8_t *pac, int64_t l_pac, int64_t p)
+{
+    return p < l_pac ? pac_get(pac, p) : 3 - pac_get(pac, (l_pac << 1) - 1 - p);
+}
+
+BSB_HD int64_t depos(int64_t l_pac, int64_t pos, int *is_rev)
+{
+    return (*is_rev = (pos >= l_pac)) ? (l_pac << 1) - 1 - pos : pos;
+}
+
+// bns_pos2rid (bntseq.c:364-378)
+BSB_HD int pos2rid(const IndexView &ix, int64_t pos_f)
+{
+    if (pos_f >= ix.l_pac) return -1;
+    int left = 0, mid = 0, right = ix.n_seqs;
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (pos_f >= ix.anns[mid].offset) {
+            if (mid == ix.n_seqs - 1) break;
+            if (pos_f < ix.anns[mid + 1].offset) break;
+            left = mid + 1;
+        } else right = mid;
+    }
+    return mid;
+}
+
+// bns_intv2rid (bntseq.c:380-388)
+BSB_HD int intv2rid(const IndexView &ix, int64_t rb, int64_t re)
+{
+    int is_rev;
+    if (rb < ix.l_pac && re > ix.l_pac) return -2;
+    int rid_b = pos2rid(ix, depos(ix.l_pac, rb, &is_rev));
+    int rid_e = rb < re ? pos2rid(ix, depos(ix.l_pac, re - 1, &is_rev)) : rid_b;
+    return rid_b == rid_e ? rid_b : -1;
+}
+
+// bns_fetch_seq (bntseq.c:436-461) without materialising the sequence: clamps [beg,end) to the
+// contig (and strand) that contains mid and returns its id. Bases are then read with ref_base().
+BSB_HD int fetch_window(const IndexView &ix, int64_t *beg, int64_t mid, int64_t *end)
+{
+    if (*end < *beg) tswap(*beg, *end);
+    int is_rev;
+    int rid = pos2rid(ix, depos(ix.l_pac, mid, &is_rev));
+    int64_t far_beg = ix.anns[rid].offset;
+    int64_t far_end = far_beg + ix.anns[rid].len;
+    if (is_rev) {
+        int64_t tmp = far_beg;
+        far_beg = (ix.l_pac << 1) - far_end;
+        far_end = (ix.l_pac << 1) - tmp;
+    }
+    *beg = *beg > far_beg ? *beg : far_beg;
+    *end = *end < far_end ? *end : far_end;
+    return rid;
+}
+
+} // namespace bsb

@@ -1,0 +1,755 @@
+// host_mem.cpp -- see host_mem.h
+#include "host_mem.h"
+#include "bsb_hd.h"
+#include <ctype.h>
+#include <getopt.h>
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#include <time.h>
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+
+namespace bsb {
+
+// ------------------------------------------------------------------------------------------------
+// options
+// ------------------------------------------------------------------------------------------------
+void fill_scmat(int a, int b, int8_t mat[25])
+{
+    int i, j, k;
+    for (i = k = 0; i < 4; ++i) {
+        for (j = 0; j < 4; ++j) mat[k++] = (int8_t)(i == j ? a : -b);
+        mat[k++] = -1;
+    }
+    for (j = 0; j < 5; ++j) mat[k++] = -1;
+}
+
+void opt_init(Opt &o)
+{
+    memset(&o, 0, sizeof(Opt));
+    o.a = 1; o.b = 4;
+    o.o_del = o.o_ins = 6;
+    o.e_del = o.e_ins = 1;
+    o.w = 100;
+    o.T = 30;
+    o.zdrop = 100;
+    o.pen_unpaired = 17;
+    o.pen_clip5 = o.pen_clip3 = 5;
+    o.max_mem_intv = 20;
+    o.min_seed_len = 19;
+    o.split_width = 10;
+    o.max_occ = 500;
+    o.max_chain_gap = 10000;
+    o.max_ins = 10000;
+    o.mask_level = 0.50f;
+    o.drop_ratio = 0.50f;
+    o.XA_drop_ratio = 0.95f;
+    o.split_factor = 1.5f;
+    o.chunk_size = 10000000;
+    o.n_threads = 1;
+    o.max_XA_hits = 5;
+    o.max_XA_hits_alt = 200;
+    o.max_matesw = 50;
+    o.mask_level_redun = 0.95f;
+    o.min_chain_weight = 0;
+    o.max_chain_extend = 1 << 30;
+    o.mapQ_coef_len = 50; o.mapQ_coef_fac = (int)log(o.mapQ_coef_len);
+    o.undirectional = 0;
+    o.ch_conversion_threshold = 5;
+    o.ch_conversion_proportion = 0.5f;
+    o.substitution_proportion = 0.1f;
+    fill_scmat(o.a, o.b, o.mat);
+}
+
+static std::string unescape(const std::string &s)
+{   // bwa_escape (bwa.c:555-571)
+    std::string q;
+    for (size_t i = 0; i < s.size(); ++i) {
+        if (s[i] == '\\') {
+            ++i;
+            if (i >= s.size()) break;
+            if (s[i] == 't') q.push_back('\t');
+            else if (s[i] == 'n') q.push_back('\n');
+            else if (s[i] == 'r') q.push_back('\r');
+            else if (s[i] == '\\') q.push_back('\\');
+        } else q.push_back(s[i]);
+    }
+    return q;
+}
+
+static void insert_header(MemArgs &ma, const std::string &s)
+{   // bwa_insert_header (bwa.c:603-616)
+    if (s.empty() || s[0] != '@') return;
+    if (ma.have_hdr) { ma.hdr_line.push_back('\n'); ma.hdr_line += unescape(s); }
+    else { ma.hdr_line = unescape(s); ma.have_hdr = true; }
+}
+
+static void parse_two(const char *arg, int *a, int *b)
+{
+    char *p;
+    *a = *b = (int)strtol(arg, &p, 10);
+    if (*p != 0 && ispunct((unsigned char)*p) && isdigit((unsigned char)p[1])) *b = (int)strtol(p + 1, &p, 10);
+}
+
+static std::mutex g_getopt_mutex;
+
+int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err)
+{
+    std::lock_guard<std::mutex> lock(g_getopt_mutex);
+    Opt &opt = ma.opt;
+    Opt opt0;
+    opt_init(opt);
+    memset(&opt0, 0, sizeof(Opt));
+    memset(ma.pes0, 0, sizeof(ma.pes0));
+    for (int i = 0; i < 4; ++i) ma.pes0[i].failed = 1;
+    std::string rg_line;
+    const char *mode = nullptr;
+    int c;
+    optind = 1; opterr = 0;
+    while ((c = getopt(argc, argv, "51qpaMCSPVYjuzk:c:v:s:r:t:R:A:B:O:E:U:w:L:d:T:Q:D:m:I:N:o:f:W:x:G:h:Z:y:K:X:H:l:n:e:")) >= 0) {
+        if (c == 'k') opt.min_seed_len = atoi(optarg), opt0.min_seed_len = 1;
+        else if (c == '1') ma.no_mt_io = true;
+        else if (c == 'x') mode = optarg;
+        else if (c == 'w') opt.w = atoi(optarg), opt0.w = 1;
+        else if (c == 'A') opt.a = atoi(optarg), opt0.a = 1;
+        else if (c == 'B') opt.b = atoi(optarg), opt0.b = 1;
+        else if (c == 'T') opt.T = atoi(optarg), opt0.T = 1;
+        else if (c == 'U') opt.pen_unpaired = atoi(optarg), opt0.pen_unpaired = 1;
+        else if (c == 't') opt.n_threads = atoi(optarg), opt.n_threads = opt.n_threads > 1 ? opt.n_threads : 1;
+        else if (c == 'P') opt.flag |= F_NOPAIRING;
+        else if (c == 'a') opt.flag |= F_ALL;
+        else if (c == 'p') opt.flag |= F_PE | F_SMARTPE;
+        else if (c == 'M') opt.flag |= F_NO_MULTI;
+        else if (c == 'S') opt.flag |= F_NO_RESCUE;
+        else if (c == 'Y') opt.flag |= F_SOFTCLIP;
+        else if (c == 'V') opt.flag |= F_REF_HDR;
+        else if (c == '5') opt.flag |= F_PRIMARY5 | F_KEEP_SUPP_MAPQ;
+        else if (c == 'q') opt.flag |= F_KEEP_SUPP_MAPQ;
+        else if (c == 'u') opt.flag |= F_XB;
+        else if (c == 'z') opt.undirectional = 1;
+        else if (c == 'e') opt.substitution_proportion = (float)atof(optarg);
+        else if (c == 'c') opt.max_occ = atoi(optarg), opt0.max_occ = 1;
+        else if (c == 'd') opt.zdrop = atoi(optarg), opt0.zdrop = 1;
+        else if (c == 'v') ma.verbose = atoi(optarg);
+        else if (c == 'j') ma.ignore_alt = true;
+        else if (c == 'r') opt.split_factor = (float)atof(optarg), opt0.split_factor = 1.f;
+        else if (c == 'D') opt.drop_ratio = (float)atof(optarg), opt0.drop_ratio = 1.f;
+        else if (c == 'm') opt.max_matesw = atoi(optarg), opt0.max_matesw = 1;
+        else if (c == 's') opt.split_width = atoi(optarg), opt0.split_width = 1;
+        else if (c == 'G') opt.max_chain_gap = atoi(optarg), opt0.max_chain_gap = 1;
+        else if (c == 'N') opt.max_chain_extend = atoi(optarg), opt0.max_chain_extend = 1;
+        else if (c == 'o' || c == 'f') ma.out_path = optarg;
+        else if (c == 'W') opt.min_chain_weight = atoi(optarg), opt0.min_chain_weight = 1;
+        else if (c == 'y') opt.max_mem_intv = (uint64_t)atol(optarg), opt0.max_mem_intv = 1;
+        else if (c == 'C') ma.copy_comment = true;
+        else if (c == 'K') ma.fixed_chunk_size = atoi(optarg);
+        else if (c == 'X') opt.mask_level = (float)atof(optarg);
+        else if (c == 'Z') opt.XA_drop_ratio = (float)atof(optarg);
+        else if (c == 'l') opt.ch_conversion_proportion = (float)atof(optarg);
+        else if (c == 'n') opt.ch_conversion_threshold = atoi(optarg);
+        else if (c == 'h') { opt0.max_XA_hits = opt0.max_XA_hits_alt = 1; parse_two(optarg, &opt.max_XA_hits, &opt.max_XA_hits_alt); }
+        else if (c == 'Q') {
+            opt0.mapQ_coef_len = 1;
+            opt.mapQ_coef_len = (float)atoi(optarg);
+            opt.mapQ_coef_fac = opt.mapQ_coef_len > 0 ? (int)log(opt.mapQ_coef_len) : 0;
+        }
+        else if (c == 'O') { opt0.o_del = opt0.o_ins = 1; parse_two(optarg, &opt.o_del, &opt.o_ins); }
+        else if (c == 'E') { opt0.e_del = opt0.e_ins = 1; parse_two(optarg, &opt.e_del, &opt.e_ins); }
+        else if (c == 'L') { opt0.pen_clip5 = opt0.pen_clip3 = 1; parse_two(optarg, &opt.pen_clip5, &opt.pen_clip3); }
+        else if (c == 'R') {
+            std::string s = optarg; // bwa_set_rg (bwa.c:573-601)
+            if (s.compare(0, 3, "@RG") != 0) { err = "[E::bwa_set_rg] the read group line is not started with @RG"; return 1; }
+            if (s.find('\t') != std::string::npos) { err = "[E::bwa_set_rg] the read group line contained literal <tab> characters -- replace with escaped tabs: \\t"; return 1; }
+            rg_line = unescape(s);
+            size_t p = rg_line.find("\tID:");
+            if (p == std::string::npos) { err = "[E::bwa_set_rg] no ID within the read group line"; return 1; }
+            p += 4;
+            size_t q = p;
+            while (q < rg_line.size() && rg_line[q] != '\t' && rg_line[q] != '\n') ++q;
+            if (q - p + 1 > 256) { err = "[E::bwa_set_rg] @RG:ID is longer than 255 characters"; return 1; }
+            ma.rg_id = rg_line.substr(p, q - p);
+        }
+        else if (c == 'H') {
+            if (optarg[0] != '@') {
+                FILE *fp;
+                if ((fp = fopen(optarg, "r")) != nullptr) {
+                    std::vector<char> buf(0x10000);
+                    while (fgets(buf.data(), 0xffff, fp)) {
+                        size_t l = strlen(buf.data());
+                        if (l && buf[l - 1] == '\n') buf[l - 1] = 0;
+                        insert_header(ma, buf.data());
+                    }
+                    fclose(fp);
+                }
+            } else insert_header(ma, optarg);
+        }
+        else if (c == 'I') {
+            char *p;
+            PeStat *pes = ma.pes0;
+            ma.have_pes0 = true;
+            pes[1].failed = 0;
+            pes[1].avg = strtod(optarg, &p);
+            pes[1].std = pes[1].avg * .1;
+            if (*p != 0 && ispunct((unsigned char)*p) && isdigit((unsigned char)p[1])) pes[1].std = strtod(p + 1, &p);
+            pes[1].high = (int)(pes[1].avg + 4. * pes[1].std + .499);
+            pes[1].low = (int)(pes[1].avg - 4. * pes[1].std + .499);
+            if (pes[1].low < 1) pes[1].low = 1;
+            if (*p != 0 && ispunct((unsigned char)*p) && isdigit((unsigned char)p[1])) pes[1].high = (int)(strtod(p + 1, &p) + .499);
+            if (*p != 0 && ispunct((unsigned char)*p) && isdigit((unsigned char)p[1])) pes[1].low = (int)(strtod(p + 1, &p) + .499);
+        }
+        else { err = "[E::main_mem] unrecognized option"; return 1; }
+    }
+    if (!rg_line.empty()) insert_header(ma, rg_line);
+    if (opt.n_threads < 1) opt.n_threads = 1;
+    if (optind + 1 >= argc || optind + 3 < argc) {
+        err = "Usage: bwa mem [options] <idxbase> <in1.fq> [in2.fq]";
+        return 1;
+    }
+    if (mode) {
+        std::string m = mode;
+        if (m == "intractg") {
+            if (!opt0.o_del) opt.o_del = 16;
+            if (!opt0.o_ins) opt.o_ins = 16;
+            if (!opt0.b) opt.b = 9;
+            if (!opt0.pen_clip5) opt.pen_clip5 = 5;
+            if (!opt0.pen_clip3) opt.pen_clip3 = 5;
+        } else if (m == "pacbio" || m == "pbref" || m == "ont2d") {
+            if (!opt0.o_del) opt.o_del = 1;
+            if (!opt0.e_del) opt.e_del = 1;
+            if (!opt0.o_ins) opt.o_ins = 1;
+            if (!opt0.e_ins) opt.e_ins = 1;
+            if (!opt0.b) opt.b = 1;
+            if (opt0.split_factor == 0.) opt.split_factor = 10.;
+            if (m == "ont2d") {
+                if (!opt0.min_chain_weight) opt.min_chain_weight = 20;
+                if (!opt0.min_seed_len) opt.min_seed_len = 14;
+            } else {
+                if (!opt0.min_chain_weight) opt.min_chain_weight = 40;
+                if (!opt0.min_seed_len) opt.min_seed_len = 17;
+            }
+            if (!opt0.pen_clip5) opt.pen_clip5 = 0;
+            if (!opt0.pen_clip3) opt.pen_clip3 = 0;
+        } else { err = std::string("[E::main_mem] unknown read type '") + mode + "'"; return 1; }
+    } else if (opt0.a) { // update_a (fastmap.c:78-92)
+        if (!opt0.b) opt.b *= opt.a;
+        if (!opt0.T) opt.T *= opt.a;
+        if (!opt0.o_del) opt.o_del *= opt.a;
+        if (!opt0.e_del) opt.e_del *= opt.a;
+        if (!opt0.o_ins) opt.o_ins *= opt.a;
+        if (!opt0.e_ins) opt.e_ins *= opt.a;
+        if (!opt0.zdrop) opt.zdrop *= opt.a;
+        if (!opt0.pen_clip5) opt.pen_clip5 *= opt.a;
+        if (!opt0.pen_clip3) opt.pen_clip3 *= opt.a;
+        if (!opt0.pen_unpaired) opt.pen_unpaired *= opt.a;
+    }
+    fill_scmat(opt.a, opt.b, opt.mat);
+    ma.idxbase = argv[optind];
+    ma.fq1 = argv[optind + 1];
+    if (optind + 2 < argc) {
+        if (opt.flag & F_PE) {
+            if (ma.verbose >= 2) fprintf(stderr, "[W::%s] when '-p' is in use, the second query file is ignored.\n", "main_mem");
+        } else {
+            ma.fq2 = argv[optind + 2];
+            opt.flag |= F_PE;
+        }
+    }
+    if (opt.flag & F_SMARTPE) { err = "[E::main_mem] smart pairing (-p) is not supported by the B200 aligner"; return 1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SAM text
+// ------------------------------------------------------------------------------------------------
+std::string sam_header(const HostIndex &idx, const MemArgs &ma)
+{
+    std::string h;
+    int n_SQ = 0;
+    if (ma.have_hdr) {
+        size_t p = 0;
+        while ((p = ma.hdr_line.find("@SQ\t", p)) != std::string::npos) {
+            if (p == 0 || ma.hdr_line[p - 1] == '\n') ++n_SQ;
+            p += 4;
+        }
+    }
+    if (n_SQ == 0) {
+        for (const HostContig &c : idx.contigs) {
+            if (c.is_crick) continue;
+            h += "@SQ\tSN:" + c.name + "\tLN:" + std::to_string(c.len);
+            if (c.is_alt && !ma.ignore_alt) h += "\tAH:*";
+            h += '\n';
+        }
+    }
+    if (ma.have_hdr) { h += ma.hdr_line; h += '\n'; }
+    if (!ma.pg_line.empty()) { h += ma.pg_line; h += '\n'; }
+    return h;
+}
+
+static inline void put_int(std::string &s, long v)
+{
+    char buf[24]; int l = 0; unsigned long x = v < 0 ? (unsigned long)(-v) : (unsigned long)v;
+    do { buf[l++] = (char)('0' + x % 10); x /= 10; } while (x);
+    if (v < 0) buf[l++] = '-';
+    while (l) s.push_back(buf[--l]);
+}
+
+static void put_cigar(std::string &s, int n, const uint32_t *cig, const char *ops, int clip_as)
+{
+    for (int i = 0; i < n; ++i) {
+        int c = cig[i] & 0xf;
+        if (clip_as >= 0 && (c == 3 || c == 4)) c = clip_as;
+        put_int(s, cig[i] >> 4);
+        s.push_back(ops[c]);
+    }
+}
+
+static int get_rlen(int n_cigar, const uint32_t *cigar)
+{
+    int l = 0;
+    for (int k = 0; k < n_cigar; ++k) { int op = cigar[k] & 0xf; if (op == 0 || op == 2) l += cigar[k] >> 4; }
+    return l;
+}
+
+static std::string format_xa(const MemArgs &ma, const HostIndex &idx, const AlnOut &p, const uint8_t *arena)
+{   // text built by mem_gen_alt (bwamem_extra.c:126-145)
+    std::string s;
+    const XaOut *xa = reinterpret_cast<const XaOut *>(arena + p.xa_off);
+    for (int i = 0; i < p.xa_n; ++i) {
+        const XaOut &t = xa[i];
+        s += idx.contigs[t.rid].name;
+        s.push_back(',');
+        s.push_back("+-"[t.is_rev]);
+        put_int(s, t.pos + 1);
+        s.push_back(',');
+        put_cigar(s, t.n_cigar, reinterpret_cast<const uint32_t *>(arena + t.cigar_off), "MIDSHN", -1);
+        s.push_back(',');
+        put_int(s, t.NM);
+        if (ma.opt.flag & F_XB) { s.push_back(','); put_int(s, t.score); }
+        s.push_back(';');
+    }
+    return s;
+}
+
+static int count_alts(const std::string &tag, int is_crick)
+{   // countAlts (bs_helpers.cpp:9-16)
+    char strand = is_crick ? '+' : '-';
+    return tag.find(strand) != std::string::npos ? 1 : 0;
+}
+
+static const unsigned char kNt4[256] = {
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 5, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+
+struct MateView { bool present; int64_t pos; int rid, is_rev, n_cigar, rlen, ch_meth, ch_unmeth; };
+
+static void format_one(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int ei, const AlnOut *list, int n, int which,
+                       const MateView &mate, const uint8_t *arena, std::string &str, EntryStats &st)
+{
+    const Opt &opt = ma.opt;
+    AlnOut p = list[which];
+    MateView m = mate;
+    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(arena + p.cigar_off);
+    std::string xa = p.xa_n > 0 ? format_xa(ma, idx, p, arena) : std::string();
+    int is_mate_crick = 0, is_crick = 0, bs_conflict = 0, reverse = 0;
+    double ch_meth = 0, ch_unmeth = 0;
+    if (p.rid >= 0) {
+        is_crick = idx.contigs[p.rid].is_crick;
+        reverse = p.is_rev ? 1 : 0;
+        ch_meth += p.ch_meth; ch_unmeth += p.ch_unmeth;
+        if (p.xa_n > 0) bs_conflict = count_alts(xa, is_crick);
+        if (is_crick) {
+            p.is_rev = 1;
+            if (m.present && m.rid >= 0) {
+                ch_unmeth += m.ch_unmeth; ch_meth += m.ch_meth;
+                is_mate_crick = idx.contigs[m.rid].is_crick;
+                m.is_rev = is_mate_crick ? 1 : 0;
+                if (is_crick != is_mate_crick) bs_conflict = 1;
+            }
+        } else {
+            p.is_rev = 0;
+            if (m.present && m.rid >= 0) m.is_rev = is_mate_crick ? 1 : 0;
+        }
+    }
+    if (bs_conflict) { p.score = 0; p.mapq = 0; }
+    p.flag |= p.rid < 0 ? 0x4 : 0;
+    p.flag |= m.present && m.rid < 0 ? 0x8 : 0;
+    if (p.rid < 0 && m.present && m.rid >= 0) { p.rid = m.rid; p.pos = m.pos; p.n_cigar = 0; }
+    if (m.present && m.rid < 0 && p.rid >= 0) { m.rid = p.rid; m.pos = p.pos; m.n_cigar = 0; m.rlen = 0; }
+    p.flag |= p.is_rev ? 0x10 : 0;
+    p.flag |= m.present && m.is_rev ? 0x20 : 0;
+
+    const int l_seq = b.len(ei);
+    const char *bases = b.bases.data() + b.seq_off[ei];
+    const char *qual = b.qual.data() + b.seq_off[ei];
+    const bool has_qual = b.has_qual[ei] != 0;
+    str.append(b.names.data() + b.name_off[ei], b.name_off[ei + 1] - b.name_off[ei]);
+    str.push_back('\t');
+    put_int(str, (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0));
+    str.push_back('\t');
+    const bool hard = !(opt.flag & F_SOFTCLIP) && !p.is_alt;
+    if (p.rid >= 0) {
+        str += idx.contigs[p.rid].name; str.push_back('\t');
+        put_int(str, p.pos + 1); str.push_back('\t');
+        put_int(str, p.mapq); str.push_back('\t');
+        if (p.n_cigar) put_cigar(str, p.n_cigar, cigar, "MIDSH", hard ? (which ? 4 : 3) : -1);
+        else str.push_back('*');
+    } else str += "*\t0\t0\t*";
+    str.push_back('\t');
+    if (m.present && m.rid >= 0) {
+        if (p.rid == m.rid) str.push_back('=');
+        else str += idx.contigs[m.rid].name;
+        str.push_back('\t');
+        put_int(str, m.pos + 1); str.push_back('\t');
+        if (p.rid == m.rid) {
+            int64_t p0 = p.pos, p1 = m.pos;
+            if (p0 > p1) p0 += get_rlen(p.n_cigar, cigar) - 1;
+            else p1 += m.rlen - 1;
+            if (m.n_cigar == 0 || p.n_cigar == 0) str.push_back('0');
+            else put_int(str, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
+        } else str.push_back('0');
+    } else str += "*\t0\t0";
+    str.push_back('\t');
+    if (p.flag & 0x100) {
+        str += "*\t*";
+    } else {
+        int qb = 0, qe = l_seq;
+        if (p.n_cigar && which && hard) {
+            int c0 = cigar[0] & 0xf, c1 = cigar[p.n_cigar - 1] & 0xf;
+            if (!reverse) {
+                if (c0 == 4 || c0 == 3) qb += cigar[0] >> 4;
+                if (c1 == 4 || c1 == 3) qe -= cigar[p.n_cigar - 1] >> 4;
+            } else {
+                if (c0 == 4 || c0 == 3) qe -= cigar[0] >> 4;
+                if (c1 == 4 || c1 == 3) qb += cigar[p.n_cigar - 1] >> 4;
+            }
+        }
+        if (!reverse) {
+            for (int i = qb; i < qe; ++i) str.push_back("ACGTN"[kNt4[(unsigned char)bases[i]]]);
+            str.push_back('\t');
+            if (has_qual) str.append(qual + qb, qe - qb);
+            else str.push_back('*');
+        } else {
+            for (int i = qe - 1; i >= qb; --i) str.push_back("TGCAN"[kNt4[(unsigned char)bases[i]]]);
+            str.push_back('\t');
+            if (has_qual) for (int i = qe - 1; i >= qb; --i) str.push_back(qual[i]);
+            else str.push_back('*');
+        }
+    }
+    if (p.n_cigar) {
+        str += "\tNM:i:"; put_int(str, p.NM);
+        str += "\tMD:Z:"; str.append(reinterpret_cast<const char *>(arena + p.md_off), p.md_len);
+        if (ch_unmeth + ch_meth >= opt.ch_conversion_threshold) {
+            double prop = ch_meth / (ch_unmeth + ch_meth);
+            str += "\tXC:i:";
+            str.push_back(prop < opt.ch_conversion_proportion ? '0' : '1');
+        }
+    }
+    if (p.score >= 0) { str += "\tAS:i:"; put_int(str, p.score); }
+    if (p.sub >= 0) { str += "\tXS:i:"; put_int(str, p.sub); }
+    if (!ma.rg_id.empty()) { str += "\tRG:Z:"; str += ma.rg_id; }
+    if (p.rid >= 0) {
+        const int pattern = b.pattern[ei];
+        str += "\tYS:Z:";
+        if (is_crick) {
+            if (pattern) { str += "C_G2A"; st.mapped = 1; }
+            else { str += "C_C2T"; st.mapped = 2; }
+            str += "\tXG:Z:GA";
+        } else {
+            if (pattern) { str += "W_G2A"; st.mapped = 3; }
+            else { str += "W_C2T"; st.mapped = 4; }
+            str += "\tXG:Z:CT";
+        }
+    }
+    if (bs_conflict) str += "\tYC:i:1";
+    if (!(p.flag & 0x100)) {
+        int i;
+        for (i = 0; i < n; ++i)
+            if (i != which && !(list[i].flag & 0x100)) break;
+        if (i < n) {
+            str += "\tSA:Z:";
+            for (i = 0; i < n; ++i) {
+                const AlnOut &r = list[i];
+                if (i == which || (r.flag & 0x100)) continue;
+                str += idx.contigs[r.rid].name; str.push_back(',');
+                put_int(str, r.pos + 1); str.push_back(',');
+                str.push_back("+-"[r.is_rev]); str.push_back(',');
+                put_cigar(str, r.n_cigar, reinterpret_cast<const uint32_t *>(arena + r.cigar_off), "MIDSH", -1);
+                str.push_back(','); put_int(str, r.mapq);
+                str.push_back(','); put_int(str, r.NM);
+                str.push_back(';');
+            }
+        }
+        if (p.alt_sc > 0) {
+            char buf[64];
+            snprintf(buf, sizeof buf, "\tpa:f:%.3f", (double)p.score / p.alt_sc);
+            str += buf;
+        }
+    }
+    if (p.xa_n > 0) {
+        str += (opt.flag & F_XB) ? "\tXB:Z:" : "\tXA:Z:";
+        str += xa;
+    }
+    if (b.cmt_off[ei + 1] > b.cmt_off[ei]) {
+        str.push_back('\t');
+        str.append(b.comments.data() + b.cmt_off[ei], b.cmt_off[ei + 1] - b.cmt_off[ei]);
+    }
+    if ((opt.flag & F_REF_HDR) && p.rid >= 0 && !idx.contigs[p.rid].anno.empty()) {
+        str += "\tXR:Z:";
+        for (char ch : idx.contigs[p.rid].anno) str.push_back(ch == '\t' ? ' ' : ch);
+    }
+    st.alignment_score += p.score;
+    st.bs_conflict = bs_conflict;
+    st.crick = is_crick;
+    if (m.present) st.paired = 1;
+    str.push_back('\n');
+}
+
+void format_entry(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int i, const BatchResult &res,
+                  std::string &sam, EntryStats &st)
+{
+    const ReadOut &ro = res.reads[i];
+    const uint8_t *arena = res.arena.data();
+    const AlnOut *list = reinterpret_cast<const AlnOut *>(arena + ro.aln_off);
+    MateView mv;
+    mv.present = (ma.opt.flag & F_PE) != 0;
+    mv.pos = ro.h_pos; mv.rid = ro.h_rid; mv.is_rev = ro.h_is_rev; mv.n_cigar = ro.h_n_cigar; mv.rlen = ro.h_rlen;
+    mv.ch_meth = ro.h_ch_meth; mv.ch_unmeth = ro.h_ch_unmeth;
+    sam.clear();
+    st = EntryStats();
+    for (int k = 0; k < ro.n_aln; ++k) format_one(ma, idx, b, i, list, ro.n_aln, k, mv, arena, sam, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// read-group arbiter
+// ------------------------------------------------------------------------------------------------
+void MapStats::add(const MapStats &o)
+{
+    reads += o.reads; alignments += o.alignments; wc2t += o.wc2t; wg2a += o.wg2a; cc2t += o.cc2t; cg2a += o.cg2a;
+    unaligned += o.unaligned; bs_ambiguous += o.bs_ambiguous;
+}
+
+static void set_unmapped(const ReadBatch &b, int i, const EntryStats &st, std::string &sam)
+{   // samSorter::setUnmapped (bs_sorter.cpp:51-82)
+    sam.clear();
+    sam.append(b.names.data() + b.name_off[i], b.name_off[i + 1] - b.name_off[i]);
+    sam.push_back('\t');
+    if (st.paired) sam += b.first[i] ? "77\t" : "141\t";
+    else sam += "4\t";
+    sam += "*\t0\t0\t*\t*\t0\t0\t";
+    const char *bases = b.bases.data() + b.seq_off[i];
+    int l = b.len(i);
+    for (int k = 0; k < l; ++k) sam.push_back("ACGTN"[kNt4[(unsigned char)bases[k]]]);
+    sam.push_back('\t');
+    if (b.has_qual[i]) sam.append(b.qual.data() + b.seq_off[i], l);
+    sam += "\tAS:i:0\tYS:Z:WC\n";
+}
+
+void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st, std::string &out, MapStats &ms)
+{
+    if (b.n == 0) return;
+    std::vector<int> g[2];
+    long score[2] = {0, 0};
+    auto same_name = [&](int i, int j) {
+        uint32_t li = b.name_off[i + 1] - b.name_off[i], lj = b.name_off[j + 1] - b.name_off[j];
+        return li == lj && memcmp(b.names.data() + b.name_off[i], b.names.data() + b.name_off[j], li) == 0;
+    };
+    auto update = [&](int i) {
+        ++ms.alignments;
+        if (st[i].bs_conflict) ++ms.bs_ambiguous;
+        switch (st[i].mapped) {
+            case 0: ++ms.unaligned; break;
+            case 1: ++ms.cg2a; break;
+            case 2: ++ms.cc2t; break;
+            case 3: ++ms.wg2a; break;
+            case 4: ++ms.wc2t; break;
+        }
+    };
+    auto flush = [&]() {
+        int pick = score[0] > score[1] ? 0 : score[0] < score[1] ? 1 : 2;
+        ++ms.reads;
+        if (pick == 1) {
+            for (int i : g[1]) { update(i); out += sam[i]; }
+        } else {
+            for (int i : g[0]) {
+                if (pick == 2) {
+                    if (st[i].mapped) set_unmapped(b, i, st[i], sam[i]);
+                    st[i].mapped = 0;
+                    st[i].bs_conflict = 1;
+                }
+                update(i);
+                out += sam[i];
+            }
+        }
+        g[0].clear(); g[1].clear(); score[0] = score[1] = 0;
+    };
+    auto bank = [&](int i) { int k = b.read_group[i] ? 1 : 0; score[k] += st[i].alignment_score; g[k].push_back(i); };
+    int cur = 0;
+    bank(0);
+    for (int i = 1; i < b.n; ++i) {
+        if (same_name(i, cur)) bank(i);
+        else { flush(); cur = i; bank(i); }
+    }
+    flush();
+}
+
+// ------------------------------------------------------------------------------------------------
+// insert size statistics + math tables
+// ------------------------------------------------------------------------------------------------
+void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::vector<int64_t> &isz, PeStat pes[4], int verbose)
+{
+    (void)opt;
+    std::vector<uint64_t> isize[4];
+    memset(pes, 0, 4 * sizeof(PeStat));
+    for (size_t i = 0; i < dir.size(); ++i)
+        if (dir[i] >= 0) isize[dir[i]].push_back((uint64_t)isz[i]);
+    if (verbose >= 3)
+        fprintf(stderr, "[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", "mem_pestat",
+                (long)isize[0].size(), (long)isize[1].size(), (long)isize[2].size(), (long)isize[3].size());
+    for (int d = 0; d < 4; ++d) {
+        PeStat *r = &pes[d];
+        std::vector<uint64_t> &q = isize[d];
+        int p25, p50, p75, x;
+        size_t n = q.size(), i;
+        if (n < 10) {
+            if (verbose >= 3) fprintf(stderr, "[M::%s] skip orientation %c%c as there are not enough pairs\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
+            r->failed = 1;
+            continue;
+        } else if (verbose >= 3) fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
+        std::sort(q.begin(), q.end());
+        p25 = (int)q[(int)(.25 * n + .499)];
+        p50 = (int)q[(int)(.50 * n + .499)];
+        p75 = (int)q[(int)(.75 * n + .499)];
+        r->low = (int)(p25 - 2.0 * (p75 - p25) + .499);
+        if (r->low < 1) r->low = 1;
+        r->high = (int)(p75 + 2.0 * (p75 - p25) + .499);
+        if (verbose >= 3) {
+            fprintf(stderr, "[M::%s] (25, 50, 75) percentile: (%d, %d, %d)\n", "mem_pestat", p25, p50, p75);
+            fprintf(stderr, "[M::%s] low and high boundaries for computing mean and std.dev: (%d, %d)\n", "mem_pestat", r->low, r->high);
+        }
+        for (i = 0, x = 0, r->avg = 0; i < n; ++i)
+            if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) r->avg += q[i], ++x;
+        r->avg /= x;
+        for (i = 0, r->std = 0; i < n; ++i)
+            if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) r->std += (q[i] - r->avg) * (q[i] - r->avg);
+        r->std = sqrt(r->std / x);
+        if (verbose >= 3) fprintf(stderr, "[M::%s] mean and std.dev: (%.2f, %.2f)\n", "mem_pestat", r->avg, r->std);
+        r->low = (int)(p25 - 3.0 * (p75 - p25) + .499);
+        r->high = (int)(p75 + 3.0 * (p75 - p25) + .499);
+        if (r->low > r->avg - 4.0 * r->std) r->low = (int)(r->avg - 4.0 * r->std + .499);
+        if (r->high < r->avg + 4.0 * r->std) r->high = (int)(r->avg + 4.0 * r->std + .499);
+        if (r->low < 1) r->low = 1;
+        if (verbose >= 3) fprintf(stderr, "[M::%s] low and high boundaries for proper pairs: (%d, %d)\n", "mem_pestat", r->low, r->high);
+    }
+    size_t max = 0;
+    for (int d = 0; d < 4; ++d) max = max > isize[d].size() ? max : isize[d].size();
+    for (int d = 0; d < 4; ++d)
+        if (pes[d].failed == 0 && isize[d].size() < max * 0.05) {
+            pes[d].failed = 1;
+            if (verbose >= 3) fprintf(stderr, "[M::%s] skip orientation %c%c\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
+        }
+}
+
+void build_log_table(std::vector<double> &t, int n)
+{
+    t.resize(n);
+    for (int i = 0; i < n; ++i) t[i] = log((double)i); // integer arguments are converted to double by the C call
+}
+
+void build_pair_table(const Opt &opt, const PeStat pes[4], std::vector<double> &t, int off[4])
+{
+    t.clear();
+    for (int d = 0; d < 4; ++d) {
+        off[d] = (int)t.size();
+        if (pes[d].failed || pes[d].high < pes[d].low) continue;
+        for (int64_t dist = pes[d].low; dist <= pes[d].high; ++dist) {
+            double ns = (dist - pes[d].avg) / pes[d].std;
+            t.push_back(.721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt.a);
+        }
+    }
+    if (t.empty()) t.push_back(0.);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the run
+// ------------------------------------------------------------------------------------------------
+static double now_sec()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+template <class F>
+static void parallel_for(int n_threads, int n, F f)
+{
+    if (n_threads <= 1 || n < 256) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::vector<std::thread> th;
+    int chunk = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        int lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([=]() { for (int i = lo; i < hi; ++i) f(i); });
+    }
+    for (auto &x : th) x.join();
+}
+
+int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary)
+{
+    double t0 = now_sec();
+    FastxReader r1(ma.fq1);
+    std::unique_ptr<FastxReader> r2;
+    if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2));
+    std::string hdr = sam_header(idx, ma);
+    fwrite(hdr.data(), 1, hdr.size(), out);
+    int64_t n_processed = 0;
+    RunSummary sum;
+    ReadBatch batch;
+    BatchResult res;
+    std::vector<std::string> sam;
+    std::vector<EntryStats> st;
+    std::string text;
+    int host_threads = (int)std::thread::hardware_concurrency();
+    if (host_threads < 1) host_threads = 1;
+    if (host_threads > 32) host_threads = 32;
+    while (read_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.copy_comment, ma.opt.undirectional, ma.opt.substitution_proportion, batch)) {
+        if (ma.verbose >= 3) fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", batch.n, (long)batch.n_bases);
+        double ta = now_sec();
+        aligner.align(ma.opt, batch, n_processed, ma.have_pes0 ? ma.pes0 : nullptr, res);
+        double tb = now_sec();
+        sum.sec_align += tb - ta;
+        if (ma.verbose >= 3) fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", batch.n, tb - ta);
+        n_processed += batch.n;
+        sam.resize(batch.n); st.resize(batch.n);
+        parallel_for(host_threads, batch.n, [&](int i) { format_entry(ma, idx, batch, i, res, sam[i], st[i]); });
+        text.clear();
+        MapStats ms;
+        sam_sort_batch(batch, sam, st, text, ms);
+        fwrite(text.data(), 1, text.size(), out);
+        fprintf(log, "BSStat TotalReads: %ld\n", ms.reads);
+        fprintf(log, "BSStat TotalAlignments: %ld\n", ms.alignments);
+        fprintf(log, "BSStat W_C2T: %ld\n", ms.wc2t);
+        fprintf(log, "BSStat W_G2A: %ld\n", ms.wg2a);
+        fprintf(log, "BSStat C_C2T: %ld\n", ms.cc2t);
+        fprintf(log, "BSStat C_G2A: %ld\n", ms.cg2a);
+        fprintf(log, "BSStat Unaligned: %ld\n", ms.unaligned);
+        fprintf(log, "BSStat BSAmbiguous: %ld\n", ms.bs_ambiguous);
+        sum.stats.add(ms);
+        ++sum.n_batches;
+        sum.n_entries += batch.n;
+    }
+    fflush(out);
+    sum.sec_total = now_sec() - t0;
+    if (summary) *summary = sum;
+    return 0;
+}
+
+} // namespace bsb

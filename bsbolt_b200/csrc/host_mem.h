@@ -1,0 +1,84 @@
+// host_mem.h -- host side of `bwa mem` as BSBolt runs it: option parsing, SAM header, SAM text
+// assembly, the bisulfite read-group arbiter and the batch loop. The GPU work sits behind the
+// BatchAligner interface (the seam is the reference's mem_process_seqs, bwamem.c:1319).
+//   parse_mem_args()  <- main_mem option loop + update_a       (fastmap.c:78-317)
+//   sam_header()      <- bwa_print_sam_hdr                      (bwa.c:530-553)
+//   format_entry()    <- mem_aln2sam                            (bwamem.c:829-1053)
+//   SamSorter         <- samSorter + wrapper                    (bs_sorter.cpp, bs_sorter_wrapper.cpp)
+//   estimate_pestat() <- mem_pestat from per-pair candidates    (bwamem_pair.c:46-109)
+//   run_mem()         <- main_mem + process() pipeline          (fastmap.c:10-76, 319-363)
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "bsb_types.h"
+#include "host_index.h"
+#include "host_reads.h"
+
+namespace bsb {
+
+struct MemArgs {
+    Opt opt;
+    bool copy_comment = false, ignore_alt = false, no_mt_io = false;
+    int fixed_chunk_size = -1;
+    int verbose = 3;
+    std::string hdr_line; bool have_hdr = false;
+    std::string rg_id;
+    bool have_pes0 = false;
+    PeStat pes0[4];
+    std::string idxbase, fq1, fq2, out_path;
+    std::string pg_line;         // "@PG\tID:bwa\tPN:bwa\tVN:...\tCL:..."
+    int64_t actual_chunk_size() const { return fixed_chunk_size > 0 ? fixed_chunk_size : (int64_t)opt.chunk_size * opt.n_threads; }
+};
+
+void opt_init(Opt &o);                              // mem_opt_init (bwamem.c:50-88)
+void fill_scmat(int a, int b, int8_t mat[25]);      // bwa_fill_scmat (bwa.c:169-178)
+// argv as given to `bwa mem` (argv[0] == "mem"). Returns 0 on success, 1 on usage error (message in err).
+int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err);
+
+struct BatchResult {
+    std::vector<ReadOut> reads;
+    std::vector<uint8_t> arena;
+    PeStat pes[4];
+    // hot-path accounting for the benchmark (device-side event timings in ms; optional)
+    double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0;
+};
+
+class BatchAligner {
+public:
+    virtual ~BatchAligner() {}
+    // Aligns one batch. n_processed is the number of bseq entries in all earlier batches.
+    // Throws std::runtime_error on device errors or scratch overflow (never truncates silently).
+    virtual void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out) = 0;
+};
+
+struct EntryStats { int alignment_score = 0, mapped = 0, bs_conflict = 0, crick = 0, paired = 0; };
+
+std::string sam_header(const HostIndex &idx, const MemArgs &ma);
+void format_entry(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int i, const BatchResult &res,
+                  std::string &sam, EntryStats &st);
+
+struct MapStats {
+    long reads = 0, alignments = 0, wc2t = 0, wg2a = 0, cc2t = 0, cg2a = 0, unaligned = 0, bs_ambiguous = 0;
+    void add(const MapStats &o);
+};
+
+// Arbitrates between the two conversion-pattern groups of each read name and appends the chosen
+// SAM text to `out`, in input order. One instance per batch, like the reference.
+void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st,
+                    std::string &out, MapStats &stats);
+
+// Insert-size distribution from the per-pair candidates (dir in [0,4) or -1, insert size).
+void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::vector<int64_t> &isize, PeStat pes[4], int verbose);
+
+// glibc-evaluated tables shipped to the device (see MathTab in bsb_final.h)
+void build_log_table(std::vector<double> &t, int n);
+void build_pair_table(const Opt &opt, const PeStat pes[4], std::vector<double> &t, int off[4]);
+
+struct RunSummary { MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0; };
+
+// The whole `bwa mem` run. SAM goes to `out`, log/BSStat lines to `log`.
+int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary);
+
+} // namespace bsb

@@ -1,0 +1,193 @@
+// host_reads.cpp -- see host_reads.h
+#include "host_reads.h"
+#include <ctype.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdexcept>
+
+namespace bsb {
+
+enum { SEP_SPACE = 0, SEP_LINE = 2 };
+static const int kBuf = 1 << 20;
+
+FastxReader::FastxReader(const std::string &path) : buf_(kBuf)
+{
+    fp_ = path == "-" ? gzdopen(0, "r") : gzopen(path.c_str(), "r");
+    if (!fp_) throw std::runtime_error("[E::main_mem] fail to open file `" + path + "'.");
+    gzbuffer(fp_, 1 << 20);
+}
+
+FastxReader::~FastxReader() { if (fp_) gzclose(fp_); }
+
+int FastxReader::getc_()
+{
+    if (is_eof_ && begin_ >= end_) return -1;
+    if (begin_ >= end_) {
+        begin_ = 0;
+        end_ = gzread(fp_, buf_.data(), kBuf);
+        if (end_ <= 0) { end_ = 0; is_eof_ = true; return -1; }
+    }
+    return (int)buf_[begin_++];
+}
+
+int FastxReader::get_until(int delim, std::string &s, int *dret, bool append)
+{
+    bool gotany = false;
+    if (dret) *dret = 0;
+    if (!append) s.clear();
+    for (;;) {
+        int i;
+        if (begin_ >= end_) {
+            if (!is_eof_) {
+                begin_ = 0;
+                end_ = gzread(fp_, buf_.data(), kBuf);
+                if (end_ <= 0) { end_ = 0; is_eof_ = true; break; }
+            } else break;
+        }
+        if (delim == SEP_LINE) {
+            const unsigned char *p = (const unsigned char *)memchr(buf_.data() + begin_, '\n', end_ - begin_);
+            i = p ? (int)(p - buf_.data()) : end_;
+        } else {
+            for (i = begin_; i < end_; ++i) if (isspace(buf_[i])) break;
+        }
+        gotany = true;
+        s.append((const char *)buf_.data() + begin_, i - begin_);
+        begin_ = i + 1;
+        if (i < end_) { if (dret) *dret = buf_[i]; break; }
+    }
+    if (!gotany && eof()) return -1;
+    if (delim == SEP_LINE && s.size() > 1 && s.back() == '\r') s.pop_back();
+    return (int)s.size();
+}
+
+int FastxReader::next(FastxRecord &r)
+{
+    int c;
+    if (last_char_ == 0) {
+        while ((c = getc_()) != -1 && c != '>' && c != '@') {}
+        if (c == -1) return -1;
+        last_char_ = c;
+    }
+    r.comment.clear(); r.seq.clear(); r.qual.clear();
+    if (get_until(SEP_SPACE, r.name, &c, false) < 0) return -1;
+    if (c != '\n') get_until(SEP_LINE, r.comment, nullptr, false);
+    while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+        if (c == '\n') continue;
+        r.seq.push_back((char)c);
+        get_until(SEP_LINE, r.seq, nullptr, true);
+    }
+    if (c == '>' || c == '@') last_char_ = c;
+    if (c != '+') return (int)r.seq.size();
+    while ((c = getc_()) != -1 && c != '\n') {}
+    if (c == -1) return -2;
+    while (get_until(SEP_LINE, r.qual, nullptr, true) >= 0 && r.qual.size() < r.seq.size()) {}
+    last_char_ = 0;
+    if (r.seq.size() != r.qual.size()) return -2;
+    return (int)r.seq.size();
+}
+
+void ReadBatch::clear()
+{
+    n = 0; n_bases = 0;
+    seq_off.assign(1, 0); name_off.assign(1, 0); cmt_off.assign(1, 0);
+    bases.clear(); qual.clear(); has_qual.clear(); names.clear(); comments.clear();
+    first.clear(); read_group.clear(); pattern.clear();
+}
+
+void ReadBatch::add(const FastxRecord &r, bool keep_comment, int first_, int read_group_, int pattern_)
+{
+    // l_seq = strlen(seq): an embedded NUL would end the read in the reference as well
+    size_t l = strnlen(r.seq.data(), r.seq.size());
+    bases.insert(bases.end(), r.seq.begin(), r.seq.begin() + l);
+    bool hq = !r.qual.empty();
+    if (hq) { qual.insert(qual.end(), r.qual.begin(), r.qual.begin() + l); }
+    else qual.insert(qual.end(), l, '*');
+    has_qual.push_back(hq);
+    seq_off.push_back((uint32_t)bases.size());
+    names.insert(names.end(), r.name.begin(), r.name.end());
+    name_off.push_back((uint32_t)names.size());
+    if (keep_comment) comments.insert(comments.end(), r.comment.begin(), r.comment.end());
+    cmt_off.push_back((uint32_t)comments.size());
+    first.push_back((uint8_t)first_); read_group.push_back((uint8_t)read_group_); pattern.push_back((uint8_t)pattern_);
+    n_bases += (int64_t)l;
+    ++n;
+}
+
+static int count_base(const std::string &s, char b)
+{
+    float c = 0;
+    size_t l = strnlen(s.data(), s.size());
+    for (size_t i = 0; i < l; ++i) if (s[i] == b) ++c;
+    return (int)c;
+}
+
+int assess_conversion(const std::string &s1, const std::string &s2, int paired_end, float substitution_proportion)
+{
+    float observed = (float)strnlen(s1.data(), s1.size());
+    float c_count = (float)count_base(s1, 'C');
+    float g_count = (float)count_base(s1, 'G');
+    if (paired_end) {
+        observed += (float)strnlen(s2.data(), s2.size());
+        g_count += (float)count_base(s2, 'C');
+        c_count += (float)count_base(s2, 'G');
+    }
+    float c_prop = c_count / observed;
+    float g_prop = g_count / observed;
+    float diff = c_prop - g_prop;
+    if (diff < 0) diff = (float)(diff * -1.0);
+    if (c_prop > substitution_proportion && g_prop > substitution_proportion) return 2;
+    else if (c_prop == g_prop) return 2;
+    else if (diff < 0.02) return 2;
+    else if (c_prop < g_prop) return 0;
+    else return 1;
+}
+
+static void trim_readno(std::string &s)
+{
+    size_t l = s.size();
+    if (l > 2 && s[l - 2] == '/' && isdigit((unsigned char)s[l - 1])) s.resize(l - 2);
+}
+
+bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,
+                float substitution_proportion, ReadBatch &b)
+{
+    b.clear();
+    FastxRecord k1, k2;
+    int64_t size = 0;
+    while (r1->next(k1) >= 0) {
+        if (r2 && r2->next(k2) < 0) {
+            fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", "bseq_read");
+            break;
+        }
+        trim_readno(k1.name);
+        int pattern = 0, compare_reads = 0;
+        if (undirectional) {
+            int un_type = r2 ? assess_conversion(k1.seq, k2.seq, 1, substitution_proportion)
+                             : assess_conversion(k1.seq, k1.seq, 0, substitution_proportion);
+            if (un_type == 2) compare_reads = 1;
+            else pattern = un_type;
+        }
+        b.add(k1, keep_comment, 0, 0, pattern);
+        size += b.len(b.n - 1);
+        if (r2) {
+            trim_readno(k2.name);
+            b.add(k2, keep_comment, 1, 0, pattern ? 0 : 1);
+            size += b.len(b.n - 1);
+        }
+        if (compare_reads) {
+            b.add(k1, keep_comment, 0, 1, 1);
+            size += b.len(b.n - 1);
+            if (r2) {
+                b.add(k2, keep_comment, 1, 1, 0);
+                size += b.len(b.n - 1);
+            }
+        }
+        if (size >= chunk_size && (b.n & 1) == 0) break;
+    }
+    if (size == 0) {
+        if (r2 && r2->next(k2) >= 0) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", "bseq_read");
+    }
+    return b.n > 0;
+}
+
+} // namespace bsb

@@ -1,0 +1,59 @@
+// host_reads.h -- FASTQ/FASTA (optionally gzip) reader and the batcher that cuts the input into the
+// same batches as the reference, including the bisulfite conversion-pattern bookkeeping.
+//   FastxReader::next()  <- kseq_read              (kseq.h:175-217)
+//   assess_conversion()  <- assessConversion       (bs_helpers.cpp:41-62)
+//   read_batch()         <- bseq_read, kseq2bseq1  (bwa.c:44-145)
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+namespace bsb {
+
+struct FastxRecord { std::string name, comment, seq, qual; };
+
+class FastxReader {
+public:
+    explicit FastxReader(const std::string &path);
+    ~FastxReader();
+    // >=0 sequence length, -1 end of file, -2 truncated quality
+    int next(FastxRecord &r);
+private:
+    int getc_();
+    int get_until(int delim, std::string &s, int *dret, bool append);
+    bool eof() const { return is_eof_ && begin_ >= end_; }
+    gzFile fp_;
+    std::vector<unsigned char> buf_;
+    int begin_ = 0, end_ = 0;
+    bool is_eof_ = false;
+    int last_char_ = 0;
+};
+
+// One batch of bseq entries (a read aligned under both conversion patterns appears twice).
+struct ReadBatch {
+    int n = 0;
+    std::vector<uint32_t> seq_off;   // n+1 offsets into bases/qual
+    std::vector<char> bases;         // ASCII as read from the file (unconverted)
+    std::vector<char> qual;          // same offsets as bases; valid iff has_qual
+    std::vector<uint8_t> has_qual;
+    std::vector<uint32_t> name_off;  // n+1
+    std::vector<char> names;
+    std::vector<uint32_t> cmt_off;   // n+1 (empty ranges unless -C)
+    std::vector<char> comments;
+    std::vector<uint8_t> first, read_group, pattern;
+    int64_t n_bases = 0;
+
+    void clear();
+    void add(const FastxRecord &r, bool keep_comment, int first, int read_group, int pattern);
+    int len(int i) const { return (int)(seq_off[i + 1] - seq_off[i]); }
+    std::string name(int i) const { return std::string(names.data() + name_off[i], name_off[i + 1] - name_off[i]); }
+};
+
+int assess_conversion(const std::string &s1, const std::string &s2, int paired_end, float substitution_proportion);
+
+// Fills `b` with the next batch. Returns false when no read could be read (end of input).
+bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,
+                float substitution_proportion, ReadBatch &b);
+
+} // namespace bsb

@@ -1,0 +1,149 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// Runs the kernel bodies of bsbolt_b200/csrc/bsb_stages.h in plain CPU loops so that the alignment
+// logic can be unit-tested against the reference (oracle/_ref) in the GPU-less build container.
+// The product path is kernels.cu/pipeline.cu; it has no CPU execution mode.
+//
+// Usage: hostsim mem [bwa-mem options] <idxbase> <in1.fq> [in2.fq]   (SAM on stdout)
+#include <stdio.h>
+#include <string.h>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+#include "../../bsbolt_b200/csrc/bsb_stages.h"
+#include "../../bsbolt_b200/csrc/host_mem.h"
+
+using namespace bsb;
+
+class HostSimAligner : public BatchAligner {
+public:
+    explicit HostSimAligner(const HostIndex &idx) : idx_(idx), ix_(idx.host_view()) { build_log_table(log_tab_, 65536); }
+
+    void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out) override
+    {
+        const int n = b.n;
+        const bool pe = (opt.flag & F_PE) != 0;
+        int max_len = 0;
+        for (int i = 0; i < n; ++i) max_len = std::max(max_len, b.len(i));
+        BatchDev B;
+        memset(&B, 0, sizeof B);
+        B.n = n; B.is_pe = pe; B.n_processed = n_processed;
+        B.bases = b.bases.data(); B.seq_off = b.seq_off.data(); B.pattern = b.pattern.data();
+        std::vector<uint8_t> seq(b.bases.size() + 1), oseq(b.bases.size() + 1);
+        B.seq = seq.data(); B.oseq = oseq.data();
+        B.intv_cap = std::max(256, 2 * max_len);
+        std::vector<Intv> intv((size_t)n * B.intv_cap), sc((size_t)3 * B.intv_cap);
+        std::vector<int32_t> n_intv(n), l_rep(n), n_seed(n), n_chain(n), n_regs(n), err(n, 0);
+        B.intv = intv.data(); B.n_intv = n_intv.data(); B.l_rep = l_rep.data(); B.n_seed = n_seed.data();
+        B.n_chain = n_chain.data(); B.n_regs = n_regs.data(); B.err = err.data();
+        for (int r = 0; r < n; ++r)
+            for (uint32_t i = b.seq_off[r]; i < b.seq_off[r + 1]; ++i) stage_convert_base(B, r, i);
+        SeedScratch ss = {sc.data(), sc.data() + B.intv_cap, sc.data() + 2 * B.intv_cap};
+        for (int r = 0; r < n; ++r) stage_seed(opt, ix_, B, r, ss);
+        std::vector<uint32_t> seed_off(n + 1, 0);
+        for (int r = 0; r < n; ++r) seed_off[r + 1] = seed_off[r] + (uint32_t)n_seed[r];
+        const size_t S = seed_off[n];
+        B.seed_off = seed_off.data();
+        std::vector<Seed> seeds(S + 1), cseeds(S + 1);
+        std::vector<int32_t> next(S + 1), tmp(S + 1);
+        std::vector<Chain> pool(S + 1), chains(S + 1);
+        std::vector<uint64_t> srt(S + 1);
+        std::vector<AlnReg> regs(S + 1);
+        std::vector<BtNode> nodes(S / 4 + 2 * (size_t)n + 4);
+        B.seeds = seeds.data(); B.cseeds = cseeds.data(); B.next = next.data(); B.tmp = tmp.data();
+        B.chain_pool = pool.data(); B.chains = chains.data(); B.srt = srt.data(); B.regs = regs.data(); B.nodes = nodes.data();
+        for (int r = 0; r < n; ++r)
+            for (uint32_t g = seed_off[r]; g < seed_off[r + 1]; ++g) stage_sa(opt, ix_, B, r, g);
+        for (int r = 0; r < n; ++r) stage_chain(opt, ix_, B, r);
+        // DP scratch
+        const int max_q = max_len + 8;
+        std::vector<int32_t> eh(2 * (size_t)(max_q + 1));
+        const long z_cap = (long)(max_q) * (long)(max_q + 2 * (4 * opt.w) + 64);
+        std::vector<uint8_t> z(z_cap);
+        DpScratch dp = {eh.data(), z.data(), z_cap, max_q};
+        for (int r = 0; r < n; ++r) stage_extend(opt, ix_, B, r, dp);
+        int max_regs = 0;
+        for (int r = 0; r < n; ++r) max_regs = std::max(max_regs, n_regs[r]);
+        // pairing statistics
+        std::vector<double> pair_tab;
+        if (pe) {
+            std::vector<int8_t> dir(n / 2);
+            std::vector<int64_t> isz(n / 2);
+            B.pe_dir = dir.data(); B.pe_isize = isz.data();
+            if (pes0) memcpy(B.pes, pes0, sizeof B.pes);
+            else {
+                for (int p = 0; p < n / 2; ++p) stage_pestat(opt, ix_, B, p);
+                estimate_pestat(opt, dir, isz, B.pes, 3);
+            }
+            memcpy(out.pes, B.pes, sizeof B.pes);
+        }
+        build_pair_table(opt, B.pes, pair_tab, B.mt.pair_off);
+        B.mt.pair_tab = pair_tab.data();
+        B.mt.log_tab = log_tab_.data(); B.mt.n_log = (int)log_tab_.size();
+        // finalisation scratch
+        FinalWS ws;
+        ws.dp = dp;
+        const int reg_cap = max_regs + 4 * opt.max_matesw + 8;
+        std::vector<uint32_t> cigar(2 * max_q + 16);
+        std::vector<char> md(8 * max_q + 64), xb(4 * max_q + 64);
+        std::vector<int32_t> cnt(reg_cap), zz(reg_cap);
+        std::vector<int8_t> has_alt(reg_cap);
+        std::vector<Pair64> pv(2 * reg_cap), pu((size_t)reg_cap * reg_cap + 16);
+        ws.cigar = cigar.data(); ws.cigar_cap = (int)cigar.size();
+        ws.md = md.data(); ws.md_cap = (int)md.size(); ws.xb = xb.data(); ws.xb_cap = (int)xb.size();
+        ws.cnt = cnt.data(); ws.has_alt = has_alt.data(); ws.z = zz.data();
+        ws.pv = pv.data(); ws.pu = pu.data(); ws.pair_cap = 2 * reg_cap;
+        ws.reg_cap = reg_cap;
+        const int sw_cap = max_q + 32, sw_b = 1 << 16;
+        std::vector<int32_t> swbuf(4 * (size_t)sw_cap);
+        std::vector<uint64_t> swb(sw_b);
+        ws.sw.H0 = swbuf.data(); ws.sw.H1 = swbuf.data() + sw_cap; ws.sw.E = swbuf.data() + 2 * sw_cap; ws.sw.Hmax = swbuf.data() + 3 * sw_cap;
+        ws.sw.b = swb.data(); ws.sw.cap = sw_cap; ws.sw.cap_b = sw_b;
+        std::vector<uint8_t> rev(max_q);
+        ws.rev = rev.data();
+        std::vector<AlnReg> wregs(2 * (size_t)(reg_cap + opt.max_matesw));
+        // outputs
+        out.reads.assign(n, ReadOut());
+        size_t arena_cap = (size_t)n * 1024 + (1 << 20);
+        for (;;) {
+            out.arena.assign(arena_cap, 0);
+            unsigned long long used = 8; // offset 0 is reserved as "null"
+            B.out = out.reads.data();
+            B.arena.base = out.arena.data(); B.arena.used = &used; B.arena.cap = arena_cap;
+            std::vector<AlnReg> regs_backup = regs; // finalisation mutates regions; keep a copy for an arena retry
+            if (pe) for (int p = 0; p < n / 2; ++p) stage_final_pe(opt, ix_, B, p, ws, wregs.data());
+            else for (int r = 0; r < n; ++r) stage_final_se(opt, ix_, B, r, ws);
+            bool ovf = false;
+            for (int r = 0; r < n; ++r) if (out.reads[r].err == ERR_ARENA_OVERFLOW) ovf = true;
+            if (!ovf) { out.arena.resize(used); break; }
+            regs = regs_backup; B.regs = regs.data();
+            arena_cap *= 2;
+        }
+        for (int r = 0; r < n; ++r)
+            if (out.reads[r].err) throw std::runtime_error("hostsim: read " + b.name(r) + " failed with error code " + std::to_string(out.reads[r].err));
+    }
+private:
+    const HostIndex &idx_;
+    IndexView ix_;
+    std::vector<double> log_tab_;
+};
+
+int main(int argc, char **argv)
+{
+    if (argc < 2 || strcmp(argv[1], "mem") != 0) { fprintf(stderr, "usage: hostsim mem [options] <idxbase> <in1.fq> [in2.fq]\n"); return 1; }
+    try {
+        MemArgs ma;
+        std::string err;
+        if (parse_mem_args(argc - 1, argv + 1, ma, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        ma.pg_line = "@PG\tID:bwa\tPN:bwa\tVN:hostsim";
+        HostIndex idx;
+        idx.load(ma.idxbase);
+        if (ma.ignore_alt) for (auto &a : idx.anns) a.is_alt = 0;
+        HostSimAligner al(idx);
+        RunSummary sum;
+        return run_mem(ma, idx, al, stdout, stderr, &sum);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 2;
+    }
+}
