@@ -1,0 +1,407 @@
+// bsb_cuda.cu -- the sm_100a kernels and the per-batch device pipeline (the product hot path).
+//
+// One CudaAligner owns one GPU: the index stays resident in HBM for the life of the object, every
+// batch flows  H2D -> K1 convert -> K2 seed -> scan -> K3 SA -> K4 chain -> K5 extend
+//              [-> pair candidates -> host insert-size stats -> tables H2D] -> K6/7/8 finalise -> D2H.
+// There is no CPU execution path in this file: if CUDA is unavailable construction throws.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no contraction: MAPQ/pairing
+// doubles must round exactly like the reference's x86-64 SSE2 arithmetic).
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "bsb_stages.h"
+#include "bsb_cuda.h"
+
+namespace bsb {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("[E::bsbolt_b200] CUDA error: ") + cudaGetErrorString(e_) + " (" #x ") at " __FILE__ ":" + std::to_string(__LINE__)); } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr; size_t cap = 0;
+    void ensure(size_t n)
+    {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t c = n + n / 4 + 64;
+        CK(cudaMalloc((void **)&p, c * sizeof(T)));
+        cap = c;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DevBuf() { release(); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels: thin launch shells around the stage bodies of bsb_stages.h
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int owner_of(const uint32_t *off, int n, uint32_t g)
+{   // largest r with off[r] <= g   (off is non-decreasing, off[n] > g)
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_convert(BatchDev B, uint32_t n_bases)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bases) return;
+    int r = owner_of(B.seq_off, B.n, i);
+    stage_convert_base(B, r, i);
+}
+
+__global__ void __launch_bounds__(64) k_seed(Opt opt, IndexView ix, BatchDev B, Intv *scratch)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    Intv *base = scratch + (size_t)w * 3 * B.intv_cap;
+    SeedScratch sc = {base, base + B.intv_cap, base + 2 * (size_t)B.intv_cap};
+    for (int r = w; r < B.n; r += nw) stage_seed(opt, ix, B, r, sc);
+}
+
+__global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
+{
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_seeds) return;
+    int r = owner_of(B.seed_off, B.n, g);
+    stage_sa(opt, ix, B, r, g);
+}
+
+__global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < B.n) stage_chain(opt, ix, B, r);
+}
+
+__global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    DpScratch dp = {eh + (size_t)w * 2 * (max_q + 1), nullptr, 0, max_q};
+    for (int r = w; r < B.n; r += nw) stage_extend(opt, ix, B, r, dp);
+}
+
+__global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < (B.n >> 1)) stage_pestat(opt, ix, B, p);
+}
+
+struct FinalLayout {       // byte offsets inside one worker's scratch block
+    size_t eh, z, cigar, md, xb, cnt, has_alt, zz, pv, pu, sw, swb, rev, wregs, total;
+    long z_cap; int max_q, cigar_cap, md_cap, xb_cap, reg_cap, pair_cap, sw_cap, sw_b, wreg_stride;
+};
+
+__device__ __forceinline__ void make_ws(const FinalLayout &L, uint8_t *blk, FinalWS &ws, AlnReg *&wregs)
+{
+    ws.dp.eh = (int32_t *)(blk + L.eh); ws.dp.z = blk + L.z; ws.dp.z_cap = L.z_cap; ws.dp.max_q = L.max_q;
+    ws.cigar = (uint32_t *)(blk + L.cigar); ws.cigar_cap = L.cigar_cap;
+    ws.md = (char *)(blk + L.md); ws.md_cap = L.md_cap;
+    ws.xb = (char *)(blk + L.xb); ws.xb_cap = L.xb_cap;
+    ws.cnt = (int32_t *)(blk + L.cnt); ws.has_alt = (int8_t *)(blk + L.has_alt); ws.z = (int32_t *)(blk + L.zz);
+    ws.pv = (Pair64 *)(blk + L.pv); ws.pu = (Pair64 *)(blk + L.pu); ws.pair_cap = L.pair_cap; ws.reg_cap = L.reg_cap;
+    int32_t *sw = (int32_t *)(blk + L.sw);
+    ws.sw.H0 = sw; ws.sw.H1 = sw + L.sw_cap; ws.sw.E = sw + 2 * L.sw_cap; ws.sw.Hmax = sw + 3 * L.sw_cap;
+    ws.sw.b = (uint64_t *)(blk + L.swb); ws.sw.cap = L.sw_cap; ws.sw.cap_b = L.sw_b;
+    ws.rev = blk + L.rev;
+    wregs = (AlnReg *)(blk + L.wregs);
+}
+
+__global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    FinalWS ws; AlnReg *wregs;
+    make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
+    for (int r = w; r < B.n; r += nw) stage_final_se(opt, ix, B, r, ws, wregs);
+}
+
+__global__ void __launch_bounds__(32) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    FinalWS ws; AlnReg *wregs;
+    make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
+    for (int p = w; p < (B.n >> 1); p += nw) stage_final_pe(opt, ix, B, p, ws, wregs);
+}
+
+__global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
+{
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, a[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CudaAligner
+// ------------------------------------------------------------------------------------------------
+struct CudaAligner::Impl {
+    int device = 0, n_sm = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[12];
+    // resident index
+    DevBuf<uint32_t> d_bwt; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
+    IndexView ix;
+    // batch buffers
+    DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
+    DevBuf<Intv> d_intv, d_seed_scratch;
+    DevBuf<int32_t> d_n_intv, d_l_rep, d_n_seed, d_n_chain, d_n_regs, d_err, d_misc;
+    DevBuf<uint32_t> d_seed_off;
+    DevBuf<uint8_t> d_cub;
+    DevBuf<Seed> d_seeds, d_cseeds; DevBuf<int32_t> d_next, d_tmp; DevBuf<Chain> d_pool, d_chains;
+    DevBuf<uint64_t> d_srt; DevBuf<AlnReg> d_regs; DevBuf<BtNode> d_nodes;
+    DevBuf<int32_t> d_eh;
+    DevBuf<int8_t> d_pe_dir; DevBuf<int64_t> d_pe_isize;
+    DevBuf<double> d_log, d_pair;
+    DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch;
+    DevBuf<unsigned long long> d_used;
+    std::vector<double> log_tab;
+    size_t arena_cap = 0;
+    int intv_cap_hint = 0;
+    long launches = 0;
+};
+
+CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
+{
+    Impl &m = *im_;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw std::runtime_error(std::string("[E::bsbolt_b200] no CUDA device available (") + cudaGetErrorString(e) + "); this aligner has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::runtime_error("[E::bsbolt_b200] invalid CUDA device index " + std::to_string(device));
+    m.device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    m.n_sm = prop.multiProcessorCount;
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+    CK(cudaStreamCreateWithFlags(&m.st, cudaStreamNonBlocking));
+    for (auto &ev : m.ev) CK(cudaEventCreate(&ev));
+    // index -> HBM (reference layout, see bsb_index.h)
+    m.d_bwt.ensure(idx.bwt.size()); CK(cudaMemcpy(m.d_bwt.p, idx.bwt.data(), idx.bwt.size() * 4, cudaMemcpyHostToDevice));
+    m.d_sa.ensure(idx.sa.size()); CK(cudaMemcpy(m.d_sa.p, idx.sa.data(), idx.sa.size() * 8, cudaMemcpyHostToDevice));
+    m.d_pac.ensure(idx.pac.size()); CK(cudaMemcpy(m.d_pac.p, idx.pac.data(), idx.pac.size(), cudaMemcpyHostToDevice));
+    m.d_opac.ensure(idx.opac.size()); CK(cudaMemcpy(m.d_opac.p, idx.opac.data(), idx.opac.size(), cudaMemcpyHostToDevice));
+    m.d_anns.ensure(idx.anns.size()); CK(cudaMemcpy(m.d_anns.p, idx.anns.data(), idx.anns.size() * sizeof(Ann), cudaMemcpyHostToDevice));
+    m.ix = idx.host_view();
+    m.ix.bwt = m.d_bwt.p; m.ix.sa = m.d_sa.p; m.ix.pac = m.d_pac.p; m.ix.opac = m.d_opac.p; m.ix.anns = m.d_anns.p;
+    build_log_table(m.log_tab, 65536);
+    m.d_log.ensure(m.log_tab.size());
+    CK(cudaMemcpy(m.d_log.p, m.log_tab.data(), m.log_tab.size() * 8, cudaMemcpyHostToDevice));
+    m.d_used.ensure(1); m.d_misc.ensure(16);
+}
+
+CudaAligner::~CudaAligner()
+{
+    if (!im_) return;
+    cudaSetDevice(im_->device);
+    for (auto &ev : im_->ev) cudaEventDestroy(ev);
+    if (im_->st) cudaStreamDestroy(im_->st);
+    delete im_;
+}
+
+long CudaAligner::kernel_launches() const { return im_->launches; }
+int CudaAligner::device() const { return im_->device; }
+size_t CudaAligner::index_bytes() const
+{
+    const Impl &m = *im_;
+    return m.d_bwt.cap * 4 + m.d_sa.cap * 8 + m.d_pac.cap + m.d_opac.cap;
+}
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out)
+{
+    Impl &m = *im_;
+    CK(cudaSetDevice(m.device));
+    cudaStream_t st = m.st;
+    const Opt opt = opt_in;
+    const int n = b.n;
+    const bool pe = (opt.flag & F_PE) != 0;
+    if (pe && (n & 1)) throw std::runtime_error("[E::bsbolt_b200] paired-end batch with an odd number of reads");
+    const size_t nb = b.bases.size();
+    int max_len = 0;
+    for (int i = 0; i < n; ++i) max_len = std::max(max_len, b.len(i));
+    if (max_len > 700) throw std::runtime_error("[E::bsbolt_b200] reads longer than 700 bp need mem_seed_sw (bwamem.c:575-619), which this build does not implement");
+    for (int k = 0; k < 8; ++k) out.ms_stage[k] = 0;
+
+    // ---- H2D ----
+    CK(cudaEventRecord(m.ev[0], st));
+    m.d_bases.ensure(nb + 16); m.d_seq.ensure(nb + 16); m.d_oseq.ensure(nb + 16);
+    m.d_seq_off.ensure(n + 1); m.d_pattern.ensure(n + 1);
+    CK(cudaMemcpyAsync(m.d_bases.p, b.bases.data(), nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m.d_seq_off.p, b.seq_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m.d_pattern.p, b.pattern.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(m.ev[1], st));
+
+    BatchDev B;
+    memset(&B, 0, sizeof B);
+    B.n = n; B.is_pe = pe; B.n_processed = n_processed;
+    B.bases = m.d_bases.p; B.seq_off = m.d_seq_off.p; B.pattern = m.d_pattern.p; B.seq = m.d_seq.p; B.oseq = m.d_oseq.p;
+    m.d_n_intv.ensure(n + 1); m.d_l_rep.ensure(n + 1); m.d_n_seed.ensure(n + 1); m.d_n_chain.ensure(n + 1); m.d_n_regs.ensure(n + 1);
+    m.d_err.ensure(n + 1); m.d_seed_off.ensure(n + 2);
+    B.n_intv = m.d_n_intv.p; B.l_rep = m.d_l_rep.p; B.n_seed = m.d_n_seed.p; B.n_chain = m.d_n_chain.p; B.n_regs = m.d_n_regs.p;
+    B.err = m.d_err.p;
+
+    // ---- K1 ----
+    if (nb) { k_convert<<<cdiv(nb, 256), 256, 0, st>>>(B, (uint32_t)nb); ++m.launches; }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(m.ev[2], st));
+
+    // ---- K2 (retry with a larger interval capacity on overflow) ----
+    B.intv_cap = std::max(std::max(256, 2 * max_len), m.intv_cap_hint);
+    const int seed_block = 64;
+    const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)m.n_sm * 16 * seed_block);
+    for (;;) {
+        m.d_intv.ensure((size_t)n * B.intv_cap);
+        m.d_seed_scratch.ensure((size_t)seed_workers * 3 * B.intv_cap);
+        B.intv = m.d_intv.p;
+        CK(cudaMemsetAsync(m.d_err.p, 0, (size_t)(n + 1) * 4, st));
+        CK(cudaMemsetAsync(m.d_n_seed.p, 0, (size_t)(n + 1) * 4, st));
+        CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
+        k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p); ++m.launches;
+        CK(cudaGetLastError());
+        k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p); ++m.launches;
+        int32_t max_err = 0;
+        CK(cudaMemcpyAsync(&max_err, m.d_misc.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (max_err == 0) break;
+        if (max_err != ERR_INTV_OVERFLOW) throw std::runtime_error("[E::bsbolt_b200] seeding failed with error code " + std::to_string(max_err));
+        B.intv_cap *= 2;
+        m.intv_cap_hint = B.intv_cap;
+        if (B.intv_cap > (1 << 20)) throw std::runtime_error("[E::bsbolt_b200] interval list overflow");
+    }
+    CK(cudaEventRecord(m.ev[3], st));
+
+    // ---- seed offsets ----
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t *)m.d_n_seed.p, (uint32_t *)m.d_seed_off.p, n + 1, st);
+    m.d_cub.ensure(cub_bytes + 16);
+    cub::DeviceScan::ExclusiveSum(m.d_cub.p, cub_bytes, (const int32_t *)m.d_n_seed.p, (uint32_t *)m.d_seed_off.p, n + 1, st); ++m.launches;
+    uint32_t S = 0;
+    CK(cudaMemcpyAsync(&S, m.d_seed_off.p + n, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    B.seed_off = m.d_seed_off.p;
+    m.d_seeds.ensure(S + 1); m.d_cseeds.ensure(S + 1); m.d_next.ensure(S + 1); m.d_tmp.ensure(S + 1);
+    m.d_pool.ensure(S + 1); m.d_chains.ensure(S + 1); m.d_srt.ensure(S + 1); m.d_regs.ensure(S + 1);
+    m.d_nodes.ensure(S / 4 + 2 * (size_t)n + 4);
+    B.seeds = m.d_seeds.p; B.cseeds = m.d_cseeds.p; B.next = m.d_next.p; B.tmp = m.d_tmp.p;
+    B.chain_pool = m.d_pool.p; B.chains = m.d_chains.p; B.srt = m.d_srt.p; B.regs = m.d_regs.p; B.nodes = m.d_nodes.p;
+
+    // ---- K3 ----
+    if (S) { k_sa<<<cdiv(S, 128), 128, 0, st>>>(opt, m.ix, B, S); ++m.launches; }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(m.ev[4], st));
+    // ---- K4 ----
+    k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, m.ix, B); ++m.launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(m.ev[5], st));
+    // ---- K5 ----
+    const int max_q = max_len + 8;
+    const int ext_block = 64;
+    const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)m.n_sm * 16 * ext_block);
+    m.d_eh.ensure((size_t)ext_workers * 2 * (max_q + 1));
+    k_extend<<<ext_workers / ext_block, ext_block, 0, st>>>(opt, m.ix, B, m.d_eh.p, max_q); ++m.launches;
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
+    k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_n_regs.p, n, m.d_misc.p); ++m.launches;
+    k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p + 1); ++m.launches;
+    int32_t h_misc[2] = {0, 0};
+    CK(cudaMemcpyAsync(h_misc, m.d_misc.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(m.ev[6], st));
+    CK(cudaStreamSynchronize(st));
+    if (h_misc[1]) throw std::runtime_error("[E::bsbolt_b200] chaining/extension failed with error code " + std::to_string(h_misc[1]));
+    const int max_regs = h_misc[0];
+
+    // ---- insert-size statistics (host, per batch) ----
+    std::vector<double> pair_tab;
+    if (pe) {
+        if (pes0) memcpy(B.pes, pes0, sizeof B.pes);
+        else {
+            const int np = n >> 1;
+            m.d_pe_dir.ensure(np + 1); m.d_pe_isize.ensure(np + 1);
+            B.pe_dir = m.d_pe_dir.p; B.pe_isize = m.d_pe_isize.p;
+            k_pestat<<<cdiv(np, 128), 128, 0, st>>>(opt, m.ix, B); ++m.launches;
+            CK(cudaGetLastError());
+            std::vector<int8_t> dir(np); std::vector<int64_t> isz(np);
+            CK(cudaMemcpyAsync(dir.data(), m.d_pe_dir.p, np, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(isz.data(), m.d_pe_isize.p, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            estimate_pestat(opt, dir, isz, B.pes, verbose);
+        }
+        memcpy(out.pes, B.pes, sizeof B.pes);
+    }
+    build_pair_table(opt, B.pes, pair_tab, B.mt.pair_off);
+    m.d_pair.ensure(pair_tab.size());
+    CK(cudaMemcpyAsync(m.d_pair.p, pair_tab.data(), pair_tab.size() * 8, cudaMemcpyHostToDevice, st));
+    B.mt.pair_tab = m.d_pair.p; B.mt.log_tab = m.d_log.p; B.mt.n_log = (int)m.log_tab.size();
+    CK(cudaEventRecord(m.ev[7], st));
+
+    // ---- K6/K7/K8 ----
+    FinalLayout L;
+    memset(&L, 0, sizeof L);
+    L.max_q = max_q;
+    L.reg_cap = max_regs + 4 * opt.max_matesw + 8;
+    L.z_cap = (long)max_q * (long)(max_q + 2 * (4 * opt.w) + 64);
+    L.cigar_cap = 2 * max_q + 16; L.md_cap = 8 * max_q + 64; L.xb_cap = 4 * max_q + 64;
+    L.pair_cap = 16384; L.sw_cap = max_q + 32; L.sw_b = 1 << 14; L.wreg_stride = L.reg_cap + opt.max_matesw;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+    L.eh = take((size_t)2 * (max_q + 1) * 4); L.z = take((size_t)L.z_cap); L.cigar = take((size_t)L.cigar_cap * 4);
+    L.md = take(L.md_cap); L.xb = take(L.xb_cap); L.cnt = take((size_t)L.reg_cap * 4); L.has_alt = take(L.reg_cap);
+    L.zz = take((size_t)L.reg_cap * 4); L.pv = take((size_t)L.pair_cap * 16); L.pu = take((size_t)L.pair_cap * 16);
+    L.sw = take((size_t)4 * L.sw_cap * 4); L.swb = take((size_t)L.sw_b * 8); L.rev = take(max_q);
+    L.wregs = take((size_t)2 * L.wreg_stride * sizeof(AlnReg));
+    L.total = o;
+    const int fin_block = 32;
+    const int items = pe ? n >> 1 : n;
+    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)m.n_sm * 8 * fin_block);
+    m.d_final_scratch.ensure((size_t)fin_workers * L.total);
+    m.d_out.ensure(n + 1);
+    B.out = m.d_out.p;
+    if (m.arena_cap == 0) m.arena_cap = (size_t)n * 640 + (1 << 20);
+    unsigned long long used = 0;
+    out.reads.resize(n);
+    for (;;) {
+        m.d_arena.ensure(m.arena_cap);
+        unsigned long long init = 8; // offset 0 = "null"
+        CK(cudaMemcpyAsync(m.d_used.p, &init, 8, cudaMemcpyHostToDevice, st));
+        B.arena.base = m.d_arena.p; B.arena.used = m.d_used.p; B.arena.cap = m.arena_cap;
+        if (items) {
+            if (pe) k_final_pe<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            ++m.launches;
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(m.ev[8], st));
+        CK(cudaMemcpyAsync(&used, m.d_used.p, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out.reads.data(), m.d_out.p, (size_t)n * sizeof(ReadOut), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (used <= m.arena_cap) break;
+        m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
+    }
+    // ---- D2H ----
+    out.arena.resize((size_t)used);
+    CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(m.ev[9], st));
+    CK(cudaStreamSynchronize(st));
+    for (int r = 0; r < n; ++r)
+        if (out.reads[r].err)
+            throw std::runtime_error("[E::bsbolt_b200] read '" + b.name(r) + "' failed on the device with error code " + std::to_string(out.reads[r].err));
+    float ms;
+    for (int k = 0; k < 9; ++k) { CK(cudaEventElapsedTime(&ms, m.ev[k], m.ev[k + 1])); if (k < 8) out.ms_stage[k] = ms; else out.ms_d2h = ms; }
+    out.ms_h2d = out.ms_stage[0];
+    CK(cudaEventElapsedTime(&ms, m.ev[1], m.ev[8]));
+    out.ms_kernels = ms;
+    out.n_seeds = S;
+    out.h2d_bytes = nb + (size_t)(n + 1) * 4 + (size_t)n;
+    out.d2h_bytes = (size_t)used + (size_t)n * sizeof(ReadOut);
+}
+
+} // namespace bsb

@@ -316,12 +316,19 @@ BSB_HD void reg_to_aln(const Opt &opt, const IndexView &ix, const MathTab &mt, i
     } while (++i < 3 && score < ar->truesc - opt.a);
     if (!ok) { if (!*err) *err = ERR_NO_MD; aln_unmapped(a); return; }
     StrBuf md = {ws.md, 0, ws.md_cap, false}, xb = {ws.xb, 0, ws.xb_cap, false};
-    if (!bs_md_xb(ix, cig.n, cig.a, qe - qb, oquery, rb, re, md, xb, &a.NM, &a.mc)) { *err = ERR_NO_MD; aln_unmapped(a); return; }
-    const char tag[7] = "\tXB:Z:";
-    for (int j = 0; j < 6; ++j) md.putc_(tag[j]);
-    for (int j = 0; j < xb.n; ++j) md.putc_(xb.s[j]);
-    if (md.ovf || xb.ovf) *err = ERR_SCRATCH_OVERFLOW;
-    a.md_len = md.n;
+    if (bs_md_xb(ix, cig.n, cig.a, qe - qb, oquery, rb, re, md, xb, &a.NM, &a.mc)) {
+        const char tag[7] = "\tXB:Z:";
+        for (int j = 0; j < 6; ++j) md.putc_(tag[j]);
+        for (int j = 0; j < xb.n; ++j) md.putc_(xb.s[j]);
+        if (md.ovf || xb.ovf) *err = ERR_SCRATCH_OVERFLOW;
+        a.md_len = md.n;
+    } else {
+        // The +-2 flank of the unconverted reference bridges the strand boundary: the reference returns
+        // the CIGAR without MD/XB and leaves NM = -1, which its 22-bit field prints as 4194303; the MD
+        // text it then reads is whatever follows the CIGAR in memory (empty in practice) (bwa.c:266).
+        a.NM = 0x3fffff; a.md_len = 0;
+        a.mc.cg_meth = a.mc.cg_unmeth = a.mc.ch_meth = a.mc.ch_unmeth = 0;
+    }
     pos = depos(ix.l_pac, rb < ix.l_pac ? rb : re - 1, &is_rev);
     a.is_rev = is_rev;
     int n_cigar = cig.n;

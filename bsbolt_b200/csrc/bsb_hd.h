@@ -8,7 +8,7 @@
 #include "bsb_types.h"
 
 #if defined(__CUDACC__)
-#define BSB_HD __host__ __device__ __forceinline__
+#define BSB_HD __host__ __device__ inline
 #define BSB_HDN __host__ __device__ __noinline__
 #else
 #define BSB_HD inline
@@ -82,7 +82,7 @@ BSB_HD void introsort(long n, T *a, Lt lt)
         return;
     }
     struct Frame { T *l, *r; int depth; };
-    Frame stack[64 * 2 + 2];
+    Frame stack[48]; // only ranges of >16 elements are pushed and the smaller side is processed first: depth <= log2(n/16)
     Frame *top = stack;
     int d;
     for (d = 2; (1ul << d) < (unsigned long)n; ++d) {}

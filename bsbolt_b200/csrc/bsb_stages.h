@@ -187,8 +187,10 @@ BSB_HD void stage_pestat(const Opt &opt, const IndexView &ix, const BatchDev &B,
     B.pe_dir[p] = (int8_t)d; B.pe_isize[p] = is;
 }
 
-// K6+K8 (single-end): mark primary, CIGAR, bisulfite tags, XA -> records
-BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int r, FinalWS &ws)
+// K6+K8 (single-end): mark primary, CIGAR, bisulfite tags, XA -> records.
+// Works on a private copy of the regions (wregs) so that a batch can be re-finalised after an
+// arena overflow: mark_primary's hash tie-break depends on the incoming order.
+BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int r, FinalWS &ws, AlnReg *wregs)
 {
     ReadOut &ro = B.out[r];
     ro.aln_off = 0; ro.n_aln = 0; ro.h_pos = -1; ro.h_rid = -1; ro.h_is_rev = 0; ro.h_n_cigar = 0; ro.h_rlen = 0;
@@ -197,12 +199,13 @@ BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int
     int err = 0;
     const int n = B.n_regs[r];
     if (n > ws.reg_cap) { ro.err = ERR_SCRATCH_OVERFLOW; return; }
-    AlnReg *regs = B.regs + B.seed_off[r];
-    mark_primary(opt, n, regs, B.n_processed + r, ws.z);
+    const AlnReg *src = B.regs + B.seed_off[r];
+    for (int j = 0; j < n; ++j) wregs[j] = src[j];
+    mark_primary(opt, n, wregs, B.n_processed + r, ws.z);
     ReadCtx rc;
     rc.l_seq = (int)(B.seq_off[r + 1] - B.seq_off[r]);
     rc.seq = B.seq + B.seq_off[r]; rc.oseq = B.oseq + B.seq_off[r];
-    rc.regs = regs; rc.n_regs = n;
+    rc.regs = wregs; rc.n_regs = n;
     emit_read(opt, ix, B.mt, rc, 0, ws, B.arena, ro, &err);
     ro.err = err;
 }

@@ -726,6 +726,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
         aligner.align(ma.opt, batch, n_processed, ma.have_pes0 ? ma.pes0 : nullptr, res);
         double tb = now_sec();
         sum.sec_align += tb - ta;
+        sum.add_timing(res);
         if (ma.verbose >= 3) fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", batch.n, tb - ta);
         n_processed += batch.n;
         sam.resize(batch.n); st.resize(batch.n);

@@ -41,8 +41,10 @@ struct BatchResult {
     std::vector<ReadOut> reads;
     std::vector<uint8_t> arena;
     PeStat pes[4];
-    // hot-path accounting for the benchmark (device-side event timings in ms; optional)
-    double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0;
+    // hot-path accounting for the benchmark (CUDA-event timings in ms on the aligner's stream)
+    // ms_stage: 0 H2D, 1 convert, 2 seed, 3 scan+SA lookup, 4 chain, 5 extend, 6 pair stats, 7 finalise
+    double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
 class BatchAligner {
@@ -76,7 +78,17 @@ void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::
 void build_log_table(std::vector<double> &t, int n);
 void build_pair_table(const Opt &opt, const PeStat pes[4], std::vector<double> &t, int off[4]);
 
-struct RunSummary { MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0; };
+struct RunSummary {
+    MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0;
+    double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
+    void add_timing(const BatchResult &r)
+    {
+        ms_h2d += r.ms_h2d; ms_kernels += r.ms_kernels; ms_d2h += r.ms_d2h;
+        for (int k = 0; k < 8; ++k) ms_stage[k] += r.ms_stage[k];
+        n_seeds += r.n_seeds; h2d_bytes += r.h2d_bytes; d2h_bytes += r.d2h_bytes;
+    }
+};
 
 // The whole `bwa mem` run. SAM goes to `out`, log/BSStat lines to `log`.
 int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary);

@@ -1,0 +1,79 @@
+/* bsbolt_b200.h -- C ABI of the B200-native bisulfite aligner (libbsbolt_b200.so).
+ *
+ * Drop-in boundary for the `bsbolt Align` hot path. The reference reaches its aligner through a
+ * process boundary (`bwa mem` argv + pipes, bsbolt/Align/AlignReads.py:43-87); in-process the seam
+ * is main_mem / mem_process_seqs. Each entry point below names the reference interface it replaces
+ * (paths relative to bsbolt/External/BWA/ of NuttyLogic/BSBolt v1.6.0).
+ *
+ * Plain C types only: pointers, sizes, ints. All functions are safe to call from any one thread at
+ * a time per bsb_index_t. On failure functions return NULL / non-zero and bsb_last_error() holds
+ * the message. There is no CPU fallback: without a CUDA device bsb_index_load fails.
+ */
+#ifndef BSBOLT_B200_H
+#define BSBOLT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsb_index bsb_index_t; /* index files of `bsbolt Index` resident in one GPU's HBM */
+typedef struct bsb_batch bsb_batch_t; /* one batch of reads (reference: bseq1_t[] of one kt_pipeline step) */
+
+typedef struct {
+    /* BSStat counters, summed over batches (bs_sorter_wrapper.cpp:13-23) */
+    int64_t total_reads, total_alignments, w_c2t, w_g2a, c_c2t, c_g2a, unaligned, bs_ambiguous;
+    int64_t n_batches, n_entries;   /* batches processed; bseq entries (reads x conversion patterns) */
+    double sec_total, sec_align;    /* host wall clock: whole run; inside the batch aligner */
+    /* CUDA-event sums over batches, milliseconds, on the aligner's stream:
+       stage 0 H2D, 1 convert, 2 SMEM seeding, 3 scan + SA lookup, 4 chaining, 5 extension,
+       6 pair statistics (incl. host round trip), 7 finalisation (CIGAR/MD/XB/pairing) */
+    double ms_h2d, ms_kernels, ms_d2h, ms_stage[8];
+    int64_t n_seeds, h2d_bytes, d2h_bytes, kernel_launches;
+} bsb_run_stats_t;
+
+typedef struct {
+    const char *name;     /* NUL-terminated; "/1" "/2" suffixes are trimmed like bwa.c:28-32 */
+    const char *comment;  /* may be NULL */
+    const char *seq;      /* ASCII bases as in the FASTQ (unconverted) */
+    const char *qual;     /* may be NULL */
+} bsb_read_t;
+
+const char *bsb_version(void);
+const char *bsb_last_error(void);
+int bsb_device_count(void);                       /* number of CUDA devices, 0 if none */
+
+/* replaces bwa_idx_load(hint, BWA_IDX_ALL) (bwa.c:407-443): reads <idxbase>.bwt .sa .ann .amb .pac .opac
+ * and uploads them to HBM of `device` */
+bsb_index_t *bsb_index_load(const char *idxbase, int device);
+void bsb_index_free(bsb_index_t *idx);
+int64_t bsb_index_hbm_bytes(const bsb_index_t *idx);
+int bsb_index_n_contigs(const bsb_index_t *idx);  /* includes the hidden crick copies */
+
+/* replaces main_mem (fastmap.c:95-363): argv is exactly what BSBolt passes after the program name,
+ * i.e. argv[0] == "mem", options, <idxbase> <in1.fq> [in2.fq]. SAM goes to out_fd, the log and the
+ * `BSStat ...` lines go to log_fd. idx may be NULL (the index named in argv is loaded on device
+ * `device` and freed at the end). Returns 0 on success. */
+int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, int log_fd, bsb_run_stats_t *stats);
+
+/* replaces bseq_read (bwa.c:73-145) for reads already in host memory: builds the bseq entries of one
+ * batch (conversion-pattern assessment, undirectional duplication). r2 may be NULL (single end).
+ * opt_argc/opt_argv: `bwa mem` options only (argv[0] == "mem", no positional arguments). */
+bsb_batch_t *bsb_batch_create(bsb_index_t *idx, int opt_argc, char **opt_argv, int n, const bsb_read_t *r1, const bsb_read_t *r2);
+/* replaces mem_process_seqs (bwamem.c:1319-1348): H2D, the eight kernels, D2H.
+ * n_processed = bseq entries of all earlier batches (fastmap.c:59). */
+int bsb_batch_align(bsb_batch_t *b, int64_t n_processed, bsb_run_stats_t *stats);
+/* replaces step 2 of process() + samSorter (fastmap.c:61-73, bs_sorter.cpp): SAM text of the batch in
+ * input order after the conversion-group arbitration; the buffer is owned by the batch. */
+int bsb_batch_sam(bsb_batch_t *b, const char **sam, size_t *len, bsb_run_stats_t *stats);
+int bsb_batch_n_entries(const bsb_batch_t *b);
+void bsb_batch_free(bsb_batch_t *b);
+
+/* SAM header as printed by bwa_print_sam_hdr (bwa.c:530-553); buffer valid until the next call on this thread */
+const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -32,14 +32,21 @@ public:
         std::vector<uint8_t> seq(b.bases.size() + 1), oseq(b.bases.size() + 1);
         B.seq = seq.data(); B.oseq = oseq.data();
         B.intv_cap = std::max(256, 2 * max_len);
-        std::vector<Intv> intv((size_t)n * B.intv_cap), sc((size_t)3 * B.intv_cap);
+        std::vector<Intv> intv, sc;
         std::vector<int32_t> n_intv(n), l_rep(n), n_seed(n), n_chain(n), n_regs(n), err(n, 0);
-        B.intv = intv.data(); B.n_intv = n_intv.data(); B.l_rep = l_rep.data(); B.n_seed = n_seed.data();
+        B.n_intv = n_intv.data(); B.l_rep = l_rep.data(); B.n_seed = n_seed.data();
         B.n_chain = n_chain.data(); B.n_regs = n_regs.data(); B.err = err.data();
         for (int r = 0; r < n; ++r)
             for (uint32_t i = b.seq_off[r]; i < b.seq_off[r + 1]; ++i) stage_convert_base(B, r, i);
-        SeedScratch ss = {sc.data(), sc.data() + B.intv_cap, sc.data() + 2 * B.intv_cap};
-        for (int r = 0; r < n; ++r) stage_seed(opt, ix_, B, r, ss);
+        for (;;) { // an interval-list overflow is retried with twice the capacity, never truncated
+            intv.assign((size_t)n * B.intv_cap, Intv()); sc.assign((size_t)3 * B.intv_cap, Intv());
+            B.intv = intv.data();
+            SeedScratch ss = {sc.data(), sc.data() + B.intv_cap, sc.data() + 2 * B.intv_cap};
+            bool ovf = false;
+            for (int r = 0; r < n; ++r) { err[r] = 0; stage_seed(opt, ix_, B, r, ss); if (err[r] == ERR_INTV_OVERFLOW) ovf = true; }
+            if (!ovf) break;
+            B.intv_cap *= 2;
+        }
         std::vector<uint32_t> seed_off(n + 1, 0);
         for (int r = 0; r < n; ++r) seed_off[r + 1] = seed_off[r] + (uint32_t)n_seed[r];
         const size_t S = seed_off[n];
@@ -88,11 +95,12 @@ public:
         std::vector<char> md(8 * max_q + 64), xb(4 * max_q + 64);
         std::vector<int32_t> cnt(reg_cap), zz(reg_cap);
         std::vector<int8_t> has_alt(reg_cap);
-        std::vector<Pair64> pv(2 * reg_cap), pu((size_t)reg_cap * reg_cap + 16);
+        const int pair_cap = 16384;
+        std::vector<Pair64> pv(pair_cap), pu(pair_cap);
         ws.cigar = cigar.data(); ws.cigar_cap = (int)cigar.size();
         ws.md = md.data(); ws.md_cap = (int)md.size(); ws.xb = xb.data(); ws.xb_cap = (int)xb.size();
         ws.cnt = cnt.data(); ws.has_alt = has_alt.data(); ws.z = zz.data();
-        ws.pv = pv.data(); ws.pu = pu.data(); ws.pair_cap = 2 * reg_cap;
+        ws.pv = pv.data(); ws.pu = pu.data(); ws.pair_cap = pair_cap;
         ws.reg_cap = reg_cap;
         const int sw_cap = max_q + 32, sw_b = 1 << 16;
         std::vector<int32_t> swbuf(4 * (size_t)sw_cap);
@@ -110,13 +118,11 @@ public:
             unsigned long long used = 8; // offset 0 is reserved as "null"
             B.out = out.reads.data();
             B.arena.base = out.arena.data(); B.arena.used = &used; B.arena.cap = arena_cap;
-            std::vector<AlnReg> regs_backup = regs; // finalisation mutates regions; keep a copy for an arena retry
             if (pe) for (int p = 0; p < n / 2; ++p) stage_final_pe(opt, ix_, B, p, ws, wregs.data());
-            else for (int r = 0; r < n; ++r) stage_final_se(opt, ix_, B, r, ws);
+            else for (int r = 0; r < n; ++r) stage_final_se(opt, ix_, B, r, ws, wregs.data());
             bool ovf = false;
             for (int r = 0; r < n; ++r) if (out.reads[r].err == ERR_ARENA_OVERFLOW) ovf = true;
             if (!ovf) { out.arena.resize(used); break; }
-            regs = regs_backup; B.regs = regs.data();
             arena_cap *= 2;
         }
         for (int r = 0; r < n; ++r)

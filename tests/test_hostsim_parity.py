@@ -1,0 +1,37 @@
+"""CPU-side unit tests of the kernel bodies (bsbolt_b200/csrc/bsb_*.h) through tests/hostsim, against
+the committed golden SAM of the reference aligner. The same bodies are what the sm_100a kernels run; the
+GPU tests (test_gpu_parity.py) repeat these comparisons through the C ABI on the device."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT, first_diff, strip_pg
+
+HOSTSIM = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
+CASES = ['se100', 'se100_un', 'se50_clip', 'pe150', 'pe150_un', 'pe150_un_sp0', 'pe150_opts']
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_kernel_bodies_match_reference_sam(built, golden, case):
+    p = subprocess.run([HOSTSIM] + golden.argv(case), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    mine, want = strip_pg(p.stdout), golden.sam(case)
+    assert mine == want, first_diff(want, mine)
+    stats = {}
+    for l in p.stderr.split('\n'):
+        if l.startswith('BSStat '):
+            k, v = l[7:].split(': ')
+            stats[k] = stats.get(k, 0) + int(v)
+    assert stats == golden.cases[case]['bsstat']
+
+
+def test_reference_binary_reproduces_golden(built, golden):
+    """Pins oracle/_ref (the compiled reference) to the committed vectors."""
+    bwa = os.path.join(ROOT, 'oracle', '_ref', 'bwa')
+    if not os.path.exists(bwa):
+        pytest.skip('oracle/_ref/bwa not built (no /root/reference and no prebuilt copy)')
+    for case in ('se100', 'pe150_un'):
+        p = subprocess.run([bwa] + golden.argv(case), capture_output=True, text=True)
+        assert p.returncode == 0
+        assert strip_pg(p.stdout) == golden.sam(case)
