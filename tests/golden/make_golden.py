@@ -20,7 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.path.join(ROOT, 'oracle', '_ref')
-WORK = os.path.join(ROOT, '.work', 'golden')
+WORK = os.path.join(os.environ.get('BSB_WORK', '/tmp/bsb_work'), 'golden')
 LAUNCHER_ARGS = ('-Y -A 1 -B 4 -D 0.5 -E 1,1 -L 30,30 -T 10 -U 17 -W 0 -c 500 -d 100 -k 19 -m 50 -r 1.5 -t 1 -w 100 -y 20 '
                  '-O 6,6 -h 100,200 -e 0.1 -l 0.5 -n 5 -Z 0.95').split()
 
