@@ -32,7 +32,7 @@ class Read(C.Structure):
 
 EXPORTS = ('bsb_version', 'bsb_last_error', 'bsb_device_count', 'bsb_index_load', 'bsb_index_free',
            'bsb_index_hbm_bytes', 'bsb_index_n_contigs', 'bsb_mem_main', 'bsb_batch_create', 'bsb_batch_align',
-           'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header')
+           'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header', 'bsb_index_build')
 
 
 def lib():
@@ -62,6 +62,7 @@ def lib():
     L.bsb_batch_free.argtypes = [C.c_void_p]
     L.bsb_sam_header.restype = C.c_char_p
     L.bsb_sam_header.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
+    L.bsb_index_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -98,6 +99,14 @@ class Index:
             self.close()
         except Exception:
             pass
+
+
+def index_build(fasta, prefix, device=0):
+    """GPU replacement of `bwa index -a bwtsw` (writes <prefix>.pac .opac .ann .amb .bwt .sa). Returns device ms."""
+    ms = C.c_double()
+    if lib().bsb_index_build(str(fasta).encode(), str(prefix).encode(), int(device), C.byref(ms)):
+        raise RuntimeError(last_error())
+    return ms.value
 
 
 def mem_main(argv, index=None, device=0, out_fd=1, log_fd=2):

@@ -9,6 +9,7 @@
 #include <vector>
 #include <cuda_runtime_api.h>
 #include "bsb_cuda.h"
+#include "bsb_index_build.h"
 
 using namespace bsb;
 
@@ -208,6 +209,16 @@ const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv)
         g_hdr = sam_header(idx->host, ma);
         return g_hdr.c_str();
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
+int bsb_index_build(const char *fasta, const char *prefix, int device, double *device_ms)
+{
+    try {
+        IndexBuildStats st;
+        index_build(fasta, prefix, device, &st);
+        if (device_ms) *device_ms = st.ms_device;
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return 1; }
 }
 
 } // extern "C"

@@ -70,6 +70,12 @@ int bsb_batch_sam(bsb_batch_t *b, const char **sam, size_t *len, bsb_run_stats_t
 int bsb_batch_n_entries(const bsb_batch_t *b);
 void bsb_batch_free(bsb_batch_t *b);
 
+/* replaces `bwa index -a bwtsw <fasta>` as run by `bsbolt Index` (bwa_idx_build, bwtindex.c:256-321;
+ * bns_fasta2bntseq, bntseq.c:296-361): writes <prefix>.pac .opac .ann .amb .bwt .sa byte-identical to the
+ * reference for references below 2^31 bases; the suffix array is built on the GPU. device_ms (optional)
+ * receives the device time. */
+int bsb_index_build(const char *fasta, const char *prefix, int device, double *device_ms);
+
 /* SAM header as printed by bwa_print_sam_hdr (bwa.c:530-553); buffer valid until the next call on this thread */
 const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv);
 

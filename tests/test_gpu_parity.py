@@ -160,3 +160,14 @@ def test_round_trip_properties(index, golden, tmp_path):
                 n = ''
         assert r[5] == '*' or clen == len(r[9])
     assert hit >= 3900
+
+
+def test_index_build_byte_identical(built, golden, tmp_path):
+    """GPU index builder (bsb_index_build) vs the files the reference's `bwa index` wrote for the same genome."""
+    import hashlib
+    from bsbolt_b200 import index_db
+    ref, ms = index_db.build_database(os.path.join(golden.dir, 'genome.fa'), str(tmp_path / 'db'))
+    for ext in ('pac', 'opac', 'ann', 'amb', 'bwt', 'sa'):
+        got = hashlib.md5(open(f'{ref}.{ext}', 'rb').read()).hexdigest()
+        assert got == golden.manifest['md5'][f'db/BSB_ref.fa.{ext}'], f'.{ext} differs from the reference index'
+    assert ms > 0
