@@ -17,6 +17,10 @@ for _a, _b in zip(b'ACGTN', b'TGCAN'):
     _COMP[_a] = _b
 
 
+def _cname(i, n):
+    return 'chr%0*d' % (len(str(n)), i + 1)
+
+
 def make_genome(path, contig_lens, seed=20240517, n_frac=0.005, n_dups=4, dup_len=5000):
     """i.i.d. ACGT contigs with a few N runs and duplicated segments (so XA/YC/MAPQ-0 paths fire)."""
     rng = np.random.default_rng(seed)
@@ -40,7 +44,7 @@ def make_genome(path, contig_lens, seed=20240517, n_frac=0.005, n_dups=4, dup_le
         contigs[b][pb:pb + dup_len] = contigs[a][pa:pa + dup_len]
     with open(path, 'wb') as f:
         for i, s in enumerate(contigs):
-            f.write(b'>chr%d\n' % (i + 1))
+            f.write(b'>' + _cname(i, len(contigs)).encode() + b'\n')
             n = len(s)
             full = (n // 60) * 60
             if full:
@@ -50,7 +54,7 @@ def make_genome(path, contig_lens, seed=20240517, n_frac=0.005, n_dups=4, dup_le
                 f.write(block.tobytes())
             if n > full:
                 f.write(s[full:].tobytes() + b'\n')
-    return [f'chr{i + 1}' for i in range(len(contigs))], contigs
+    return [_cname(i, len(contigs)) for i in range(len(contigs))], contigs
 
 
 def read_fasta(path):
@@ -71,7 +75,7 @@ def read_fasta(path):
 
 def simulate_reads(names, contigs, out_prefix, n_pairs, read_len=150, paired=True, undirectional=False, seed=7,
                    insert_mean=50, insert_sd=50, mut_rate=0.005, indel_frac=0.2, seq_err=0.001,
-                   cpg_meth=0.8, ch_meth=0.02, corrupt_frac=0.0, chunk=200000, first_id=0):
+                   cpg_meth=0.8, ch_meth=0.02, corrupt_frac=0.0, chunk=200000, first_id=0, truth=True):
     """Writes <out_prefix>_1.fq (and _2.fq). Returns the file paths."""
     rng = np.random.default_rng(seed)
     lens = np.array([len(c) for c in contigs], dtype=np.int64)
@@ -84,8 +88,11 @@ def simulate_reads(names, contigs, out_prefix, n_pairs, read_len=150, paired=Tru
     done = 0
     rid = first_id
     acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    fast_names = None
+    if not truth and len({len(x) for x in names}) == 1:
+        fast_names = np.array([np.frombuffer(x.encode(), dtype=np.uint8) for x in names])
     while done < n_pairs:
-        n = int(min(chunk, n_pairs - done))
+        n = int(min(chunk, (n_pairs - done) * 1.03 + 64))  # a few candidates are rejected (N-rich, contig end)
         frag = (2 * L + np.clip(rng.normal(insert_mean, insert_sd, size=n), -L + 10, 400).astype(np.int64)) if paired else np.full(n, L, dtype=np.int64)
         ci = rng.choice(len(contigs), size=n, p=lens / lens.sum())
         ok_len = lens[ci] > frag + 2
@@ -152,17 +159,40 @@ def simulate_reads(names, contigs, out_prefix, n_pairs, read_len=150, paired=Tru
             sub = (rng.random(r2.shape) < 0.15) & rows[:, None]
             r2[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
         has_n = ((r1 == ord('N')).mean(axis=1) > 0.05) | (paired & ((r2 == ord('N')).mean(axis=1) > 0.05))
-        good = np.nonzero(ok_len & ~has_n)[0]
-        for j in good:
-            c = names[ci[j]]
-            tag1 = ('W' if watson[j] else 'C') + ('G2A' if swap[j] else 'C2T')
-            s0, e0 = int(start[j]), int(start[j] + frag[j])
-            files[0].write(b'@%d_%s/1\n' % (rid, c.encode()) + r1[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), s0, e0, L, tag1.encode()) + qual + b'\n')
-            if paired:
-                tag2 = ('W' if watson[j] else 'C') + ('C2T' if swap[j] else 'G2A')
-                files[1].write(b'@%d_%s/2\n' % (rid, c.encode()) + r2[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), s0, e0, L, tag2.encode()) + qual + b'\n')
-            rid += 1
-        done += n
+        good = np.nonzero(ok_len & ~has_n)[0][:n_pairs - done]
+        if fast_names is not None:
+            # vectorised writer: fixed-width records "@<10-digit id>_<contig>/1\n<seq>\n+\n<qual>\n"
+            g = len(good)
+            ids = rid + np.arange(g, dtype=np.int64)
+            digits = ((ids[:, None] // (10 ** np.arange(9, -1, -1, dtype=np.int64))[None, :]) % 10 + 48).astype(np.uint8)
+            cn = fast_names[ci[good]]
+            w = cn.shape[1]
+            rec_len = 1 + 10 + 1 + w + 3 + L + 3 + L + 1
+            for k, (fh, mat) in enumerate(zip(files, (r1, r2) if paired else (r1,))):
+                rec = np.empty((g, rec_len), dtype=np.uint8)
+                o = 0
+                rec[:, o] = ord('@'); o += 1
+                rec[:, o:o + 10] = digits; o += 10
+                rec[:, o] = ord('_'); o += 1
+                rec[:, o:o + w] = cn; o += w
+                rec[:, o:o + 3] = np.frombuffer(b'/%d\n' % (k + 1), dtype=np.uint8); o += 3
+                rec[:, o:o + L] = mat[good]; o += L
+                rec[:, o:o + 3] = np.frombuffer(b'\n+\n', dtype=np.uint8); o += 3
+                rec[:, o:o + L] = np.frombuffer(qual, dtype=np.uint8); o += L
+                rec[:, o] = 10
+                fh.write(rec.tobytes())
+            rid += g
+        else:
+            for j in good:
+                c = names[ci[j]]
+                tag1 = ('W' if watson[j] else 'C') + ('G2A' if swap[j] else 'C2T')
+                s0, e0 = int(start[j]), int(start[j] + frag[j])
+                files[0].write(b'@%d_%s/1\n' % (rid, c.encode()) + r1[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), s0, e0, L, tag1.encode()) + qual + b'\n')
+                if paired:
+                    tag2 = ('W' if watson[j] else 'C') + ('C2T' if swap[j] else 'G2A')
+                    files[1].write(b'@%d_%s/2\n' % (rid, c.encode()) + r2[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), s0, e0, L, tag2.encode()) + qual + b'\n')
+                rid += 1
+        done += len(good)
     for f in files:
         f.close()
     return paths, rid - first_id
