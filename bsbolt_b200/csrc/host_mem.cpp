@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <time.h>
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -702,6 +704,54 @@ static void parallel_for(int n_threads, int n, F f)
     for (auto &x : th) x.join();
 }
 
+namespace {
+// bounded single-producer/single-consumer hand-off between the pipeline stages
+template <class T>
+class Channel {
+public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    void push(T v)
+    {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+        q_.push_back(std::move(v));
+        cv_.notify_all();
+    }
+    bool pop(T &v)
+    {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        cv_.notify_all();
+        return true;
+    }
+    void close()
+    {
+        std::lock_guard<std::mutex> l(m_);
+        closed_ = true;
+        cv_.notify_all();
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
+
+struct Job {
+    ReadBatch batch;
+    BatchResult res;
+    int64_t n_processed = 0;
+    double sec_align = 0;
+};
+} // namespace
+
+// Three overlapped stages, like the reference's kt_pipeline (fastmap.c:352) but with the GPU in the
+// middle: [read + convert-pattern bookkeeping] -> [device batch] -> [SAM text + arbiter + write].
+// Each stage handles batches strictly in input order, so output order and n_processed are unchanged.
 int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary)
 {
     double t0 = now_sec();
@@ -710,46 +760,88 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2));
     std::string hdr = sam_header(idx, ma);
     fwrite(hdr.data(), 1, hdr.size(), out);
-    int64_t n_processed = 0;
     RunSummary sum;
-    ReadBatch batch;
-    BatchResult res;
-    std::vector<std::string> sam;
-    std::vector<EntryStats> st;
-    std::string text;
     int host_threads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
-    while (read_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.copy_comment, ma.opt.undirectional, ma.opt.substitution_proportion, batch)) {
-        if (ma.verbose >= 3) fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", batch.n, (long)batch.n_bases);
-        double ta = now_sec();
-        aligner.align(ma.opt, batch, n_processed, ma.have_pes0 ? ma.pes0 : nullptr, res);
-        double tb = now_sec();
-        sum.sec_align += tb - ta;
-        sum.add_timing(res);
-        if (ma.verbose >= 3) fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", batch.n, tb - ta);
-        n_processed += batch.n;
-        sam.resize(batch.n); st.resize(batch.n);
-        parallel_for(host_threads, batch.n, [&](int i) { format_entry(ma, idx, batch, i, res, sam[i], st[i]); });
-        text.clear();
-        MapStats ms;
-        sam_sort_batch(batch, sam, st, text, ms);
-        fwrite(text.data(), 1, text.size(), out);
-        fprintf(log, "BSStat TotalReads: %ld\n", ms.reads);
-        fprintf(log, "BSStat TotalAlignments: %ld\n", ms.alignments);
-        fprintf(log, "BSStat W_C2T: %ld\n", ms.wc2t);
-        fprintf(log, "BSStat W_G2A: %ld\n", ms.wg2a);
-        fprintf(log, "BSStat C_C2T: %ld\n", ms.cc2t);
-        fprintf(log, "BSStat C_G2A: %ld\n", ms.cg2a);
-        fprintf(log, "BSStat Unaligned: %ld\n", ms.unaligned);
-        fprintf(log, "BSStat BSAmbiguous: %ld\n", ms.bs_ambiguous);
-        sum.stats.add(ms);
-        ++sum.n_batches;
-        sum.n_entries += batch.n;
+    Channel<std::unique_ptr<Job>> q_read(2), q_done(2);
+    std::string fail;
+    std::mutex fail_m;
+    auto set_fail = [&](const std::string &w) { std::lock_guard<std::mutex> l(fail_m); if (fail.empty()) fail = w; };
+    std::mutex log_m;
+
+    std::thread t_read([&] {
+        try {
+            int64_t n_processed = 0;
+            for (;;) {
+                std::unique_ptr<Job> j(new Job);
+                if (!read_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.copy_comment, ma.opt.undirectional, ma.opt.substitution_proportion, j->batch)) break;
+                if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", j->batch.n, (long)j->batch.n_bases); }
+                j->n_processed = n_processed;
+                n_processed += j->batch.n;
+                q_read.push(std::move(j));
+                { std::lock_guard<std::mutex> l(fail_m); if (!fail.empty()) break; }
+            }
+        } catch (const std::exception &e) { set_fail(e.what()); }
+        q_read.close();
+    });
+    std::thread t_gpu([&] {
+        try {
+            std::unique_ptr<Job> j;
+            while (q_read.pop(j)) {
+                double ta = now_sec();
+                aligner.align(ma.opt, j->batch, j->n_processed, ma.have_pes0 ? ma.pes0 : nullptr, j->res);
+                j->sec_align = now_sec() - ta;
+                if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", j->batch.n, j->sec_align); }
+                q_done.push(std::move(j));
+            }
+        } catch (const std::exception &e) {
+            set_fail(e.what());
+            std::unique_ptr<Job> j;
+            while (q_read.pop(j)) {} // drain so that the reader can finish
+        }
+        q_done.close();
+    });
+    {
+        std::vector<std::string> sam;
+        std::vector<EntryStats> st;
+        std::string text;
+        std::unique_ptr<Job> j;
+        while (q_done.pop(j)) {
+            try {
+                const ReadBatch &batch = j->batch;
+                sum.sec_align += j->sec_align;
+                sum.add_timing(j->res);
+                sam.resize(batch.n); st.resize(batch.n);
+                parallel_for(host_threads, batch.n, [&](int i) { format_entry(ma, idx, batch, i, j->res, sam[i], st[i]); });
+                text.clear();
+                MapStats ms;
+                sam_sort_batch(batch, sam, st, text, ms);
+                fwrite(text.data(), 1, text.size(), out);
+                {
+                    std::lock_guard<std::mutex> l(log_m);
+                    fprintf(log, "BSStat TotalReads: %ld\n", ms.reads);
+                    fprintf(log, "BSStat TotalAlignments: %ld\n", ms.alignments);
+                    fprintf(log, "BSStat W_C2T: %ld\n", ms.wc2t);
+                    fprintf(log, "BSStat W_G2A: %ld\n", ms.wg2a);
+                    fprintf(log, "BSStat C_C2T: %ld\n", ms.cc2t);
+                    fprintf(log, "BSStat C_G2A: %ld\n", ms.cg2a);
+                    fprintf(log, "BSStat Unaligned: %ld\n", ms.unaligned);
+                    fprintf(log, "BSStat BSAmbiguous: %ld\n", ms.bs_ambiguous);
+                }
+                sum.stats.add(ms);
+                ++sum.n_batches;
+                sum.n_entries += batch.n;
+            } catch (const std::exception &e) { set_fail(e.what()); }
+        }
     }
+    t_gpu.join();
+    t_read.join();
     fflush(out);
     sum.sec_total = now_sec() - t0;
     if (summary) *summary = sum;
+    if (!fail.empty()) throw std::runtime_error(fail);
     return 0;
 }
 
