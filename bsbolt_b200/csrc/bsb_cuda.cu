@@ -10,12 +10,14 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
 #include "bsb_stages.h"
+#include "bsb_warp.cuh"
 #include "bsb_cuda.h"
 
 namespace bsb {
@@ -88,6 +90,19 @@ __global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B
     for (int r = w; r < B.n; r += nw) stage_extend(opt, ix, B, r, dp);
 }
 
+// K5, warp per read: rows of the banded extension across the lanes, (h,e) rows + query in shared memory
+__global__ void __launch_bounds__(128) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int wib = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    uint8_t *mine = smem + (size_t)wib * smem_per_warp;
+    WarpDp S;
+    S.H = (int32_t *)mine; S.E = S.H + (max_q + 1); S.qs = (uint8_t *)(S.E + (max_q + 1));
+    DpScratch dp = {eh + (size_t)gw * 2 * (max_q + 1), nullptr, 0, max_q};
+    for (int r = gw; r < B.n; r += nw) stage_extend_warp(opt, ix, B, r, S, dp);
+}
+
 __global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,6 +145,25 @@ __global__ void __launch_bounds__(32) k_final_pe(Opt opt, IndexView ix, BatchDev
     for (int p = w; p < (B.n >> 1); p += nw) stage_final_pe(opt, ix, B, p, ws, wregs);
 }
 
+// Index-load time: expands the reference's SA sample (every sa_intv-th rank) into the full suffix array in
+// HBM. SA values do not depend on the sampling rate, so lookups become one 4-byte load
+// instead of ~31 dependent 64-byte LF steps. One thread per sample walks LF until the next sampled rank.
+__global__ void k_dense_sa(IndexView ix, uint64_t n_sa, uint32_t *sa32)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sa) return;
+    uint64_t k = j * (uint64_t)ix.sa_intv;
+    uint64_t v = j == 0 ? ix.seq_len : ix.sa[j];
+    sa32[k] = j == 0 ? 0xffffffffu : (uint32_t)v;
+    const uint64_t mask = (uint64_t)ix.sa_intv - 1;
+    for (;;) {
+        k = fm_lf(ix, k);
+        --v;
+        if ((k & mask) == 0) break;
+        sa32[k] = (uint32_t)v;
+    }
+}
+
 __global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
 {
     int m = 0;
@@ -146,7 +180,7 @@ struct CudaAligner::Impl {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[12];
     // resident index
-    DevBuf<uint32_t> d_bwt; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
+    DevBuf<uint32_t> d_bwt, d_sa32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
     IndexView ix;
     // batch buffers
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
@@ -191,6 +225,15 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     m.d_anns.ensure(idx.anns.size()); CK(cudaMemcpy(m.d_anns.p, idx.anns.data(), idx.anns.size() * sizeof(Ann), cudaMemcpyHostToDevice));
     m.ix = idx.host_view();
     m.ix.bwt = m.d_bwt.p; m.ix.sa = m.d_sa.p; m.ix.pac = m.d_pac.p; m.ix.opac = m.d_opac.p; m.ix.anns = m.d_anns.p;
+    m.ix.sa32 = nullptr; m.ix.sa32_intv = 0;
+    if (idx.seq_len + 1 < (1ull << 32) && !getenv("BSB_SAMPLED_SA")) { // full SA resident in HBM (4 B/rank)
+        m.d_sa32.ensure(idx.seq_len + 1);
+        k_dense_sa<<<(unsigned)((idx.n_sa + 127) / 128), 128>>>(m.ix, idx.n_sa, m.d_sa32.p);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        m.ix.sa32 = m.d_sa32.p; m.ix.sa32_intv = 1;
+        ++m.launches;
+    }
     build_log_table(m.log_tab, 65536);
     m.d_log.ensure(m.log_tab.size());
     CK(cudaMemcpy(m.d_log.p, m.log_tab.data(), m.log_tab.size() * 8, cudaMemcpyHostToDevice));
@@ -211,7 +254,7 @@ int CudaAligner::device() const { return im_->device; }
 size_t CudaAligner::index_bytes() const
 {
     const Impl &m = *im_;
-    return m.d_bwt.cap * 4 + m.d_sa.cap * 8 + m.d_pac.cap + m.d_opac.cap;
+    return m.d_bwt.cap * 4 + m.d_sa.cap * 8 + m.d_sa32.cap * 4 + m.d_pac.cap + m.d_opac.cap;
 }
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -304,10 +347,18 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaEventRecord(m.ev[5], st));
     // ---- K5 ----
     const int max_q = max_len + 8;
-    const int ext_block = 64;
-    const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)m.n_sm * 16 * ext_block);
-    m.d_eh.ensure((size_t)ext_workers * 2 * (max_q + 1));
-    k_extend<<<ext_workers / ext_block, ext_block, 0, st>>>(opt, m.ix, B, m.d_eh.p, max_q); ++m.launches;
+    if (getenv("BSB_EXTEND_V1")) {
+        const int ext_block = 64;
+        const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)m.n_sm * 16 * ext_block);
+        m.d_eh.ensure((size_t)ext_workers * 2 * (max_q + 1));
+        k_extend<<<ext_workers / ext_block, ext_block, 0, st>>>(opt, m.ix, B, m.d_eh.p, max_q); ++m.launches;
+    } else {
+        const int wpb = 4;
+        const int smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 15) & ~15;
+        const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)m.n_sm * 8);
+        m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
+        k_extend_warp<<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp); ++m.launches;
+    }
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
     k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_n_regs.p, n, m.d_misc.p); ++m.launches;

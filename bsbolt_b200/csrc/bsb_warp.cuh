@@ -1,0 +1,299 @@
+// bsb_warp.cuh -- warp-cooperative kernels bodies (device only).
+//
+// The v1 kernels ran one read per thread; ncu showed 4-7 of 32 lanes active per issued instruction
+// (profiles/r01_ncu_v1_thread_per_read.md). Here one WARP owns one read: the control logic is executed
+// uniformly by all 32 lanes (no divergence), the dynamic programming rows are spread across the lanes.
+//
+// sw_extend_warp() is ksw_extend2 (ksw.c:380-479) row by row, exactly: the (h,e) row persists in shared
+// memory with its stale cells, the band [beg,end) evolves per row from the zero cells, the row maximum takes
+// the LAST column holding it, z-drop and the to-end score are evaluated per row. Inside a row
+//     M(j)   = H(i-1,j-1) ? H(i-1,j-1) + s(i,j) : 0           (previous row only)
+//     E(i,j)                                                   (previous row only)
+//     F(i,j) = max_{j'<j} ( max(M(j') - oe_ins, 0) - (j-1-j') * e_ins )      F(i,beg) = 0
+// so F is an exclusive max-scan of g(j') = max(M(j')-oe_ins,0) + j'*e_ins: five shuffle steps per 32 cells.
+#pragma once
+#include "bsb_stages.h"
+
+namespace bsb {
+
+#define FULLMASK 0xffffffffu
+#define NEG_BIG (-0x3fffffff)
+
+struct WarpDp {            // per-warp shared memory
+    int32_t *H, *E;        // max_q + 1 each
+    uint8_t *qs;           // query of the current extension, in extension order
+};
+
+__device__ __forceinline__ int warp_max(int v)
+{
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULLMASK, v, o));
+    return v;
+}
+
+template <class T>
+__device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, const T &target, const int8_t *mat,
+                                    int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
+                                    const WarpDp &S)
+{
+    const int lane = threadIdx.x & 31;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int32_t *H = S.H, *E = S.E;
+    uint8_t *qs = S.qs;
+    // first row + query staging
+    const int H1 = h0 > oe_ins ? h0 - oe_ins : 0;
+    for (int j = lane; j <= qlen; j += 32) {
+        int v = 0;
+        if (j == 0) v = h0;
+        else { v = H1 - (j - 1) * e_ins; if (v < 0) v = 0; }
+        H[j] = v; E[j] = 0;
+        if (j < qlen) qs[j] = (uint8_t)query(j);
+    }
+    int i, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off, beg, end;
+    for (i = 0, max = 0; i < 25; ++i) max = max > mat[i] ? max : mat[i];
+    max_ins = (int)((double)(qlen * max + end_bonus - o_ins) / e_ins + 1.);
+    max_ins = max_ins > 1 ? max_ins : 1;
+    w = w < max_ins ? w : max_ins;
+    max_del = (int)((double)(qlen * max + end_bonus - o_del) / e_del + 1.);
+    max_del = max_del > 1 ? max_del : 1;
+    w = w < max_del ? w : max_del;
+    max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+    beg = 0; end = qlen;
+    __syncwarp();
+    for (i = 0; i < tlen; ++i) {
+        const int8_t *row = mat + target(i) * 5;
+        if (beg < i - w) beg = i - w;
+        if (end > i + w + 1) end = i + w + 1;
+        if (end > qlen) end = qlen;
+        int h1;
+        if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
+        else h1 = 0;
+        int carry_g = NEG_BIG, carry_h = h1;       // running F source, H(i, j-1) entering the chunk
+        int best = -1;                              // (h << 12 | j) maximum of the row
+        int first_nz = -1, last_nz = -1;            // non-zero cells of the updated row in [beg,end)
+        for (int c0 = beg; c0 < end; c0 += 32) {
+            const int j = c0 + lane;
+            const bool act = j < end;
+            int Hj = 0, Ej = 0, M = 0;
+            if (act) { Hj = H[j]; Ej = E[j]; M = Hj ? Hj + row[qs[j]] : 0; }
+            int tI = M - oe_ins; tI = tI > 0 ? tI : 0;
+            int g = act ? tI + j * e_ins : NEG_BIG;
+            int incl = g;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(FULLMASK, incl, d);
+                if (lane >= d) incl = incl > v ? incl : v;
+            }
+            int excl = __shfl_up_sync(FULLMASK, incl, 1);
+            if (lane == 0) excl = NEG_BIG;
+            excl = excl > carry_g ? excl : carry_g;
+            int f = (j == beg) ? 0 : excl - (j - 1) * e_ins;
+            int h = M > Ej ? M : Ej;
+            h = h > f ? h : f;
+            int tD = M - oe_del; tD = tD > 0 ? tD : 0;
+            int e2 = Ej - e_del; e2 = e2 > tD ? e2 : tD;
+            int hprev = __shfl_up_sync(FULLMASK, h, 1);
+            if (lane == 0) hprev = carry_h;
+            if (act) { H[j] = hprev; E[j] = e2; }
+            int key = act ? (h << 12 | j) : -1;
+            key = warp_max(key);
+            best = best > key ? best : key;
+            unsigned nz = __ballot_sync(FULLMASK, act && (hprev != 0 || e2 != 0));
+            if (nz) {
+                if (first_nz < 0) first_nz = c0 + __ffs(nz) - 1;
+                last_nz = c0 + 31 - __clz(nz);
+            }
+            const int n_act = end - c0 < 32 ? end - c0 : 32;
+            const int chunk_max = __shfl_sync(FULLMASK, incl, 31); // inactive lanes hold NEG_BIG
+            carry_g = carry_g > chunk_max ? carry_g : chunk_max;
+            carry_h = __shfl_sync(FULLMASK, h, n_act - 1);
+        }
+        h1 = carry_h;
+        if (lane == 0) { H[end] = h1; E[end] = 0; }
+        int m = 0, mj = -1;
+        if (best >= 0) { m = best >> 12; mj = best & 0xfff; }
+        if (end == qlen) {
+            max_ie = gscore > h1 ? max_ie : i;
+            gscore = gscore > h1 ? gscore : h1;
+        }
+        if (m == 0) break;
+        if (m > max) {
+            max = m; max_i = i; max_j = mj;
+            max_off = max_off > iabs(mj - i) ? max_off : iabs(mj - i);
+        } else if (zdrop > 0) {
+            if (i - max_i > mj - max_j) {
+                if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break;
+            } else {
+                if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break;
+            }
+        }
+        // next band: drop leading/trailing cells whose h and e are both zero
+        int nb = first_nz >= 0 ? first_nz : end;
+        int jl;
+        if (h1 != 0) jl = end;
+        else if (last_nz >= 0 && last_nz >= nb) jl = last_nz;
+        else jl = nb - 1;
+        beg = nb;
+        end = jl + 2 < qlen ? jl + 2 : qlen;
+        __syncwarp();
+    }
+    ExtResult r;
+    r.score = max; r.qle = max_j + 1; r.tle = max_i + 1; r.gtle = max_ie + 1; r.gscore = gscore; r.max_off = max_off;
+    return r;
+}
+
+// mem_chain2aln, warp-uniform: every lane executes the same control flow on the same values; lane 0 alone
+// writes to HBM; the two extensions per seed run across the lanes.
+__device__ void chain_to_regions_warp(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query,
+                                      const Chain &c, const Seed *cs, uint64_t *srt, RegList &av, const WarpDp &S, DpScratch &dp, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    int i, k, max_off[2], aw[2];
+    const int64_t l_pac = ix.l_pac;
+    int64_t rmax[2], tmp;
+    if (c.n == 0) return;
+    rmax[0] = l_pac << 1; rmax[1] = 0;
+    for (i = 0; i < c.n; ++i) {
+        const Seed &t = cs[i];
+        int64_t b = t.rbeg - (t.qbeg + cal_max_gap(opt, t.qbeg));
+        int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + cal_max_gap(opt, l_query - t.qbeg - t.len));
+        rmax[0] = rmax[0] < b ? rmax[0] : b;
+        rmax[1] = rmax[1] > e ? rmax[1] : e;
+    }
+    rmax[0] = rmax[0] > 0 ? rmax[0] : 0;
+    rmax[1] = rmax[1] < l_pac << 1 ? rmax[1] : l_pac << 1;
+    if (rmax[0] < l_pac && l_pac < rmax[1]) {
+        if (cs[0].rbeg < l_pac) rmax[1] = l_pac;
+        else rmax[0] = l_pac;
+    }
+    fetch_window(ix, &rmax[0], cs[0].rbeg, &rmax[1]);
+    if (l_query > dp.max_q) { *err = ERR_SCRATCH_OVERFLOW; return; }
+    if (lane == 0) {
+        for (i = 0; i < c.n; ++i) srt[i] = (uint64_t)cs[i].score << 32 | (uint32_t)i;
+        introsort((long)c.n, srt, LtU64());
+    }
+    __syncwarp();
+    for (k = c.n - 1; k >= 0; --k) {
+        const Seed s = cs[(uint32_t)srt[k]];
+        for (i = 0; i < av.n; ++i) {
+            const AlnReg &p = av.a[i];
+            int64_t rd;
+            int qd, w, max_gap;
+            if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+            if (s.len - p.seedlen0 > .1 * l_query) continue;
+            qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
+            max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+            w = max_gap < p.w ? max_gap : p.w;
+            if (qd - rd < w && rd - qd < w) break;
+            qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+            max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
+            w = max_gap < p.w ? max_gap : p.w;
+            if (qd - rd < w && rd - qd < w) break;
+        }
+        if (i < av.n) {
+            for (i = k + 1; i < c.n; ++i) {
+                if (srt[i] == 0) continue;
+                const Seed &t = cs[(uint32_t)srt[i]];
+                if (t.len < s.len * .95) continue;
+                if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+                if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+            }
+            if (i == c.n) {
+                __syncwarp();
+                if (lane == 0) srt[k] = 0;
+                __syncwarp();
+                continue;
+            }
+        }
+        if (av.n >= av.cap) { *err = ERR_SCRATCH_OVERFLOW; return; }
+        AlnReg a;
+        alnreg_clear(a);
+        a.w = aw[0] = aw[1] = opt.w;
+        a.score = a.truesc = -1;
+        a.rid = c.rid;
+        if (s.qbeg) {
+            QrySeq qs = {query + (s.qbeg - 1), -1};
+            RefSeq rs = {ix.pac, l_pac, s.rbeg - 1, -1};
+            tmp = s.rbeg - rmax[0];
+            ExtResult x = {0, 0, 0, 0, 0, 0};
+            for (i = 0; i < 2; ++i) {
+                int prev = a.score;
+                aw[0] = opt.w << i;
+                x = sw_extend_warp(s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0], opt.pen_clip5, opt.zdrop, s.len * opt.a, S);
+                a.score = x.score; max_off[0] = x.max_off;
+                if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
+            }
+            if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip5) {
+                a.qb = s.qbeg - x.qle; a.rb = s.rbeg - x.tle;
+                a.truesc = a.score;
+            } else {
+                a.qb = 0; a.rb = s.rbeg - x.gtle;
+                a.truesc = x.gscore;
+            }
+        } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+        if (s.qbeg + s.len != l_query) {
+            int qe = s.qbeg + s.len, sc0 = a.score;
+            int64_t re = s.rbeg + s.len - rmax[0];
+            QrySeq qs = {query + qe, 1};
+            RefSeq rs = {ix.pac, l_pac, rmax[0] + re, 1};
+            ExtResult x = {0, 0, 0, 0, 0, 0};
+            for (i = 0; i < 2; ++i) {
+                int prev = a.score;
+                aw[1] = opt.w << i;
+                x = sw_extend_warp(l_query - qe, qs, (int)(rmax[1] - rmax[0] - re), rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, S);
+                a.score = x.score; max_off[1] = x.max_off;
+                if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
+            }
+            if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip3) {
+                a.qe = qe + x.qle; a.re = rmax[0] + re + x.tle;
+                a.truesc += a.score - sc0;
+            } else {
+                a.qe = l_query; a.re = rmax[0] + re + x.gtle;
+                a.truesc += x.gscore - sc0;
+            }
+        } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+        a.seedcov = 0;
+        for (i = 0; i < c.n; ++i) {
+            const Seed &t = cs[i];
+            if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+        }
+        a.w = aw[0] > aw[1] ? aw[0] : aw[1];
+        a.seedlen0 = s.len;
+        a.frac_rep = c.frac_rep;
+        __syncwarp();
+        if (lane == 0) av.a[av.n] = a;
+        ++av.n;
+        __syncwarp();
+    }
+}
+
+// K5, one warp per read
+__device__ void stage_extend_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const WarpDp &S, DpScratch &dp)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t so = B.seed_off[r];
+    const int ns = (int)(B.seed_off[r + 1] - so);
+    if (ns == 0 || B.err[r]) { if (lane == 0) B.n_regs[r] = 0; return; }
+    const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+    const uint8_t *seq = B.seq + B.seq_off[r];
+    RegList av = {B.regs + so, 0, ns};
+    int err = 0;
+    const int nc = B.n_chain[r];
+    for (int i = 0; i < nc; ++i) {
+        const Chain c = B.chains[so + i];
+        chain_to_regions_warp(opt, ix, len, seq, c, B.cseeds + so + c.head, B.srt + so, av, S, dp, &err);
+        if (err) break;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (!err) {
+            av.n = sort_dedup_patch(opt, ix, seq, av.n, av.a, dp, &err);
+            for (int i = 0; i < av.n; ++i)
+                if (av.a[i].rid >= 0 && ix.anns[av.a[i].rid].is_alt) av.a[i].is_alt = 1;
+        }
+        if (err) { B.err[r] = err; B.n_regs[r] = 0; }
+        else B.n_regs[r] = av.n;
+    }
+    __syncwarp();
+}
+
+} // namespace bsb
