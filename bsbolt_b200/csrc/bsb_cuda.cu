@@ -69,6 +69,19 @@ __global__ void __launch_bounds__(64) k_seed(Opt opt, IndexView ix, BatchDev B, 
     for (int r = w; r < B.n; r += nw) stage_seed(opt, ix, B, r, sc);
 }
 
+// K2, state-machine form: lane = read, the warp reconverges at the single FM-index extension site
+__global__ void __launch_bounds__(64) k_seed_sm(Opt opt, IndexView ix, BatchDev B, Intv *scratch)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    Intv *base = scratch + (size_t)w * 3 * B.intv_cap;
+    SeedScratch sc = {base, base + B.intv_cap, base + 2 * (size_t)B.intv_cap};
+    const int first = w & ~31;
+    for (int r0 = first; r0 < B.n; r0 += nw) {   // all 32 lanes of a warp iterate together
+        const int r = r0 + (w & 31);
+        stage_seed(opt, ix, B, r, sc, true, r < B.n);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
 {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,7 +321,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemsetAsync(m.d_err.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_n_seed.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
-        k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p); ++m.launches;
+        if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
+        else k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
+        ++m.launches;
         CK(cudaGetLastError());
         k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p); ++m.launches;
         int32_t max_err = 0;

@@ -10,6 +10,7 @@
 //   per worker: scratch blocks (interval lists, DP rows, traceback, strings)
 #pragma once
 #include "bsb_smem.h"
+#include "bsb_smem_sm.h"
 #include "bsb_chain.h"
 #include "bsb_extend.h"
 #include "bsb_final.h"
@@ -73,17 +74,20 @@ BSB_HD void stage_convert_base(const BatchDev &B, int r, uint32_t i)
     B.seq[i] = code == 5 ? 4 : code; // mem_align1_core maps through nst_nt4_table where '-' is 5; any code > 3 is "ambiguous"
 }
 
-// K2: SMEM seeding for read r
-BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const SeedScratch &sc)
+// K2: SMEM seeding for read r. use_sm selects the converged state-machine form (all lanes of a warp call
+// together, `active` false for lanes without a read); both forms produce the same interval list.
+BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const SeedScratch &sc, bool use_sm = false, bool active = true)
 {
-    const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
-    const uint8_t *seq = B.seq + B.seq_off[r];
-    IntvList mem = {B.intv + (size_t)r * B.intv_cap, 0, B.intv_cap};
+    const int len = active ? (int)(B.seq_off[r + 1] - B.seq_off[r]) : 0;
+    const uint8_t *seq = active ? B.seq + B.seq_off[r] : nullptr;
+    IntvList mem = {active ? B.intv + (size_t)r * B.intv_cap : nullptr, 0, B.intv_cap};
     IntvList mem1 = {sc.mem1, 0, B.intv_cap}, t0 = {sc.t0, 0, B.intv_cap}, t1 = {sc.t1, 0, B.intv_cap};
     int err = 0;
-    B.n_intv[r] = 0; B.l_rep[r] = 0; B.n_seed[r] = 0;
-    if (len < opt.min_seed_len) return;
-    collect_intv(opt, ix, len, seq, mem, mem1, t0, t1, &err);
+    if (active) { B.n_intv[r] = 0; B.l_rep[r] = 0; B.n_seed[r] = 0; }
+    const bool work = active && len >= opt.min_seed_len;
+    if (use_sm) collect_intv_sm(opt, ix, len, seq, mem, mem1, t0, t1, &err, work);
+    else if (work) collect_intv(opt, ix, len, seq, mem, mem1, t0, t1, &err);
+    if (!work) return;
     if (err) { B.err[r] = err; return; }
     int b = 0, e = 0, l_rep = 0, total = 0;
     for (int i = 0; i < mem.n; ++i) { // frac_rep bookkeeping + seed count (bwamem.c:269-283)

@@ -6,6 +6,7 @@
 //
 // Usage: hostsim mem [bwa-mem options] <idxbase> <in1.fq> [in2.fq]   (SAM on stdout)
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <memory>
 #include <stdexcept>
@@ -43,7 +44,8 @@ public:
             B.intv = intv.data();
             SeedScratch ss = {sc.data(), sc.data() + B.intv_cap, sc.data() + 2 * B.intv_cap};
             bool ovf = false;
-            for (int r = 0; r < n; ++r) { err[r] = 0; stage_seed(opt, ix_, B, r, ss); if (err[r] == ERR_INTV_OVERFLOW) ovf = true; }
+            const bool use_sm = getenv("BSB_HOSTSIM_SEED_SM") != nullptr;
+            for (int r = 0; r < n; ++r) { err[r] = 0; stage_seed(opt, ix_, B, r, ss, use_sm, true); if (err[r] == ERR_INTV_OVERFLOW) ovf = true; }
             if (!ovf) break;
             B.intv_cap *= 2;
         }
