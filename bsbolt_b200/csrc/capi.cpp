@@ -42,6 +42,7 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     for (int k = 0; k < 8; ++k) s->ms_stage[k] = sum.ms_stage[k];
     s->n_seeds = (int64_t)sum.n_seeds; s->h2d_bytes = (int64_t)sum.h2d_bytes; s->d2h_bytes = (int64_t)sum.d2h_bytes;
     s->kernel_launches = al ? al->kernel_launches() : 0;
+    s->sec_read = sum.sec_read; s->sec_format = sum.sec_format; s->sec_write = sum.sec_write;
 }
 
 extern "C" {

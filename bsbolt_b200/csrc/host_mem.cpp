@@ -765,19 +765,24 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
-    Channel<std::unique_ptr<Job>> q_read(2), q_done(2);
+    Channel<std::unique_ptr<Job>> q_read(2), q_done(2), q_free(8);
+    for (int k = 0; k < 5; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
     std::string fail;
     std::mutex fail_m;
     auto set_fail = [&](const std::string &w) { std::lock_guard<std::mutex> l(fail_m); if (fail.empty()) fail = w; };
     std::mutex log_m;
 
+    double sec_read = 0;
     std::thread t_read([&] {
         try {
             int64_t n_processed = 0;
             for (;;) {
-                std::unique_ptr<Job> j(new Job);
+                std::unique_ptr<Job> j;
+                if (!q_free.pop(j)) break;
+                double tr = now_sec();
                 if (!read_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.copy_comment, ma.opt.undirectional, ma.opt.substitution_proportion, j->batch)) break;
                 if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", j->batch.n, (long)j->batch.n_bases); }
+                sec_read += now_sec() - tr;
                 j->n_processed = n_processed;
                 n_processed += j->batch.n;
                 q_read.push(std::move(j));
@@ -813,12 +818,15 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 const ReadBatch &batch = j->batch;
                 sum.sec_align += j->sec_align;
                 sum.add_timing(j->res);
+                double tf = now_sec();
                 sam.resize(batch.n); st.resize(batch.n);
                 parallel_for(host_threads, batch.n, [&](int i) { format_entry(ma, idx, batch, i, j->res, sam[i], st[i]); });
                 text.clear();
                 MapStats ms;
                 sam_sort_batch(batch, sam, st, text, ms);
+                double tw = now_sec();
                 fwrite(text.data(), 1, text.size(), out);
+                sum.sec_format += tw - tf; sum.sec_write += now_sec() - tw;
                 {
                     std::lock_guard<std::mutex> l(log_m);
                     fprintf(log, "BSStat TotalReads: %ld\n", ms.reads);
@@ -834,11 +842,14 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 ++sum.n_batches;
                 sum.n_entries += batch.n;
             } catch (const std::exception &e) { set_fail(e.what()); }
+            q_free.push(std::move(j));
         }
     }
+    q_free.close();
     t_gpu.join();
     t_read.join();
     fflush(out);
+    sum.sec_read = sec_read;
     sum.sec_total = now_sec() - t0;
     if (summary) *summary = sum;
     if (!fail.empty()) throw std::runtime_error(fail);

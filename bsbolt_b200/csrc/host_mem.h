@@ -80,6 +80,7 @@ void build_pair_table(const Opt &opt, const PeStat pes[4], std::vector<double> &
 
 struct RunSummary {
     MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0;
+    double sec_read = 0, sec_format = 0, sec_write = 0; // busy time of the reader / formatter / output stages
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
     void add_timing(const BatchResult &r)

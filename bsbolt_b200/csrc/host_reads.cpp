@@ -3,21 +3,100 @@
 #include <ctype.h>
 #include <string.h>
 #include <stdio.h>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 
 namespace bsb {
 
 enum { SEP_SPACE = 0, SEP_LINE = 2 };
 static const int kBuf = 1 << 20;
 
+// Parsing (and gunzip) of each input file runs on its own thread; records reach the batcher in blocks.
+struct FastxReader::Prefetch {
+    struct Block { std::vector<FastxRecord> rec; int n = 0; int status = 0; };
+    static const int kBlock = 4096;
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::unique_ptr<Block>> ready, spare;
+    std::unique_ptr<Block> cur;
+    int pos = 0;
+    bool done = false, stop = false;
+    std::thread th;
+};
+
 FastxReader::FastxReader(const std::string &path) : buf_(kBuf)
 {
     fp_ = path == "-" ? gzdopen(0, "r") : gzopen(path.c_str(), "r");
     if (!fp_) throw std::runtime_error("[E::main_mem] fail to open file `" + path + "'.");
     gzbuffer(fp_, 1 << 20);
+    pf_ = new Prefetch;
+    pf_->th = std::thread([this] { pump(); });
 }
 
-FastxReader::~FastxReader() { if (fp_) gzclose(fp_); }
+FastxReader::~FastxReader()
+{
+    if (pf_) {
+        { std::lock_guard<std::mutex> l(pf_->m); pf_->stop = true; }
+        pf_->cv.notify_all();
+        if (pf_->th.joinable()) pf_->th.join();
+        delete pf_;
+    }
+    if (fp_) gzclose(fp_);
+}
+
+void FastxReader::pump()
+{
+    Prefetch &P = *pf_;
+    for (;;) {
+        std::unique_ptr<Prefetch::Block> b;
+        {
+            std::unique_lock<std::mutex> l(P.m);
+            P.cv.wait(l, [&] { return P.stop || P.ready.size() < 8; });
+            if (P.stop) return;
+            if (!P.spare.empty()) { b = std::move(P.spare.front()); P.spare.pop_front(); }
+        }
+        if (!b) { b.reset(new Prefetch::Block); b->rec.resize(Prefetch::kBlock); }
+        b->n = 0; b->status = 0;
+        while (b->n < Prefetch::kBlock) {
+            int r = next_raw(b->rec[b->n]);
+            if (r < 0) { b->status = r; break; }
+            ++b->n;
+        }
+        bool last = b->status < 0;
+        {
+            std::lock_guard<std::mutex> l(P.m);
+            P.ready.push_back(std::move(b));
+            if (last) P.done = true;
+        }
+        P.cv.notify_all();
+        if (last) return;
+    }
+}
+
+int FastxReader::next(FastxRecord &r)
+{
+    Prefetch &P = *pf_;
+    for (;;) {
+        if (P.cur && P.pos < P.cur->n) {
+            FastxRecord &s = P.cur->rec[P.pos++];
+            r.name.swap(s.name); r.comment.swap(s.comment); r.seq.swap(s.seq); r.qual.swap(s.qual);
+            return (int)r.seq.size();
+        }
+        if (P.cur && P.cur->status < 0) return P.cur->status;
+        std::unique_lock<std::mutex> l(P.m);
+        if (P.cur) { P.spare.push_back(std::move(P.cur)); P.cv.notify_all(); }
+        P.cv.wait(l, [&] { return !P.ready.empty() || P.done; });
+        if (P.ready.empty()) return -1;
+        P.cur = std::move(P.ready.front());
+        P.ready.pop_front();
+        P.pos = 0;
+        P.cv.notify_all();
+    }
+}
 
 int FastxReader::getc_()
 {
@@ -60,7 +139,7 @@ int FastxReader::get_until(int delim, std::string &s, int *dret, bool append)
     return (int)s.size();
 }
 
-int FastxReader::next(FastxRecord &r)
+int FastxReader::next_raw(FastxRecord &r)
 {
     int c;
     if (last_char_ == 0) {
@@ -97,20 +176,34 @@ void ReadBatch::clear()
 void ReadBatch::add(const FastxRecord &r, bool keep_comment, int first_, int read_group_, int pattern_)
 {
     // l_seq = strlen(seq): an embedded NUL would end the read in the reference as well
-    size_t l = strnlen(r.seq.data(), r.seq.size());
-    bases.insert(bases.end(), r.seq.begin(), r.seq.begin() + l);
-    bool hq = !r.qual.empty();
-    if (hq) { qual.insert(qual.end(), r.qual.begin(), r.qual.begin() + l); }
-    else qual.insert(qual.end(), l, '*');
+    const size_t l = strnlen(r.seq.data(), r.seq.size());
+    const size_t o = bases.size();
+    if (bases.capacity() < o + l) { bases.reserve((o + l) * 2 + (1 << 20)); qual.reserve((o + l) * 2 + (1 << 20)); }
+    bases.resize(o + l); qual.resize(o + l);
+    memcpy(bases.data() + o, r.seq.data(), l);
+    const bool hq = !r.qual.empty();
+    if (hq) memcpy(qual.data() + o, r.qual.data(), l);
+    else memset(qual.data() + o, '*', l);
     has_qual.push_back(hq);
-    seq_off.push_back((uint32_t)bases.size());
-    names.insert(names.end(), r.name.begin(), r.name.end());
+    seq_off.push_back((uint32_t)(o + l));
+    const size_t no = names.size();
+    if (names.capacity() < no + r.name.size()) names.reserve((no + r.name.size()) * 2 + (1 << 16));
+    names.resize(no + r.name.size());
+    memcpy(names.data() + no, r.name.data(), r.name.size());
     name_off.push_back((uint32_t)names.size());
     if (keep_comment) comments.insert(comments.end(), r.comment.begin(), r.comment.end());
     cmt_off.push_back((uint32_t)comments.size());
     first.push_back((uint8_t)first_); read_group.push_back((uint8_t)read_group_); pattern.push_back((uint8_t)pattern_);
     n_bases += (int64_t)l;
     ++n;
+}
+
+void ReadBatch::reserve_like(const ReadBatch &o)
+{
+    bases.reserve(o.bases.size() + (o.bases.size() >> 3)); qual.reserve(o.qual.size() + (o.qual.size() >> 3));
+    names.reserve(o.names.size() + (o.names.size() >> 3));
+    size_t k = (size_t)o.n + (o.n >> 3) + 16;
+    seq_off.reserve(k); name_off.reserve(k); cmt_off.reserve(k); has_qual.reserve(k); first.reserve(k); read_group.reserve(k); pattern.reserve(k);
 }
 
 static int count_base(const std::string &s, char b)

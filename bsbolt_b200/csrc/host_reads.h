@@ -20,6 +20,10 @@ public:
     // >=0 sequence length, -1 end of file, -2 truncated quality
     int next(FastxRecord &r);
 private:
+    int next_raw(FastxRecord &r);
+    void pump();               // parser thread body
+    struct Prefetch;           // blocks of parsed records handed over from the parser thread
+    Prefetch *pf_ = nullptr;
     int getc_();
     int get_until(int delim, std::string &s, int *dret, bool append);
     bool eof() const { return is_eof_ && begin_ >= end_; }
@@ -45,6 +49,7 @@ struct ReadBatch {
     int64_t n_bases = 0;
 
     void clear();
+    void reserve_like(const ReadBatch &o);   // pre-size for a batch about as large as o
     void add(const FastxRecord &r, bool keep_comment, int first, int read_group, int pattern);
     int len(int i) const { return (int)(seq_off[i + 1] - seq_off[i]); }
     std::string name(int i) const { return std::string(names.data() + name_off[i], name_off[i + 1] - name_off[i]); }

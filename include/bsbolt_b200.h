@@ -31,6 +31,7 @@ typedef struct {
        6 pair statistics (incl. host round trip), 7 finalisation (CIGAR/MD/XB/pairing) */
     double ms_h2d, ms_kernels, ms_d2h, ms_stage[8];
     int64_t n_seeds, h2d_bytes, d2h_bytes, kernel_launches;
+    double sec_read, sec_format, sec_write; /* busy time of the host stages: FASTQ batching, SAM text, output */
 } bsb_run_stats_t;
 
 typedef struct {
