@@ -130,6 +130,30 @@ BSB_HD void fm_extend(const IndexView &ix, const Intv &ik, Intv ok[4], int is_ba
     }
 }
 
+BSB_HD uint64_t sel4(int c, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3)
+{
+    return c == 0 ? a0 : c == 1 ? a1 : c == 2 ? a2 : a3;
+}
+
+// fm_extend() when only the interval of symbol c is wanted; no indexable temporaries, so everything stays
+// in registers on the device
+BSB_HD Intv fm_extend_sel(const IndexView &ix, const Intv &ik, int c, int is_back)
+{
+    uint64_t tk[4], tl[4];
+    const uint64_t xa = is_back ? ik.x0 : ik.x1, xb = is_back ? ik.x1 : ik.x0;
+    occ4_pair(ix, xa - 1, xa - 1 + ik.x2, tk, tl);
+    const uint64_t s0 = tl[0] - tk[0], s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
+    const uint64_t n3 = xb + (xa <= ix.primary && xa + ik.x2 - 1 >= ix.primary);
+    const uint64_t n2 = n3 + s3, n1 = n2 + s2, n0 = n1 + s1;
+    const uint64_t na = sel4(c, ix.L2[0] + 1 + tk[0], ix.L2[1] + 1 + tk[1], ix.L2[2] + 1 + tk[2], ix.L2[3] + 1 + tk[3]);
+    const uint64_t nb = sel4(c, n0, n1, n2, n3);
+    Intv o;
+    if (is_back) { o.x0 = na; o.x1 = nb; } else { o.x1 = na; o.x0 = nb; }
+    o.x2 = sel4(c, s0, s1, s2, s3);
+    o.info = 0;
+    return o;
+}
+
 BSB_HD void fm_set_intv(const IndexView &ix, int c, Intv &ik)
 {
     ik.x0 = ix.L2[c] + 1;
