@@ -301,6 +301,7 @@ def main():
                          'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms},
             'cpu_baseline': cpu,
             'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st['ms_stage'])},
+            'final_split_ms_per_step': {'select': st['ms_select'] / n_batches, 'tasks': st['ms_tasks'] / n_batches, 'n_tasks': st['n_tasks'] // n_batches},
             'host_busy_s': {'read': st['sec_read'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_thread': st['sec_align']},
             'setup_s': {'simulate': t_sim, 'index_build_or_wait': t_index}, 'index_hbm_bytes': idx.hbm_bytes}
     print(json.dumps(line))

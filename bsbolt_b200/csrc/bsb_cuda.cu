@@ -122,17 +122,15 @@ __global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
     if (p < (B.n >> 1)) stage_pestat(opt, ix, B, p);
 }
 
-struct FinalLayout {       // byte offsets inside one worker's scratch block
-    size_t eh, z, cigar, md, xb, cnt, has_alt, zz, pv, pu, sw, swb, rev, wregs, total;
-    long z_cap; int max_q, cigar_cap, md_cap, xb_cap, reg_cap, pair_cap, sw_cap, sw_b, wreg_stride;
+struct FinalLayout {       // byte offsets inside one worker's scratch block (selection / pairing kernel)
+    size_t eh, cnt, has_alt, zz, pv, pu, sw, swb, rev, wregs, total;
+    int max_q, reg_cap, pair_cap, sw_cap, sw_b, wreg_stride;
 };
 
 __device__ __forceinline__ void make_ws(const FinalLayout &L, uint8_t *blk, FinalWS &ws, AlnReg *&wregs)
 {
-    ws.dp.eh = (int32_t *)(blk + L.eh); ws.dp.z = blk + L.z; ws.dp.z_cap = L.z_cap; ws.dp.max_q = L.max_q;
-    ws.cigar = (uint32_t *)(blk + L.cigar); ws.cigar_cap = L.cigar_cap;
-    ws.md = (char *)(blk + L.md); ws.md_cap = L.md_cap;
-    ws.xb = (char *)(blk + L.xb); ws.xb_cap = L.xb_cap;
+    ws.dp.eh = (int32_t *)(blk + L.eh); ws.dp.z = nullptr; ws.dp.z_cap = 0; ws.dp.max_q = L.max_q;
+    ws.cigar = nullptr; ws.cigar_cap = 0; ws.md = nullptr; ws.md_cap = 0; ws.xb = nullptr; ws.xb_cap = 0;
     ws.cnt = (int32_t *)(blk + L.cnt); ws.has_alt = (int8_t *)(blk + L.has_alt); ws.z = (int32_t *)(blk + L.zz);
     ws.pv = (Pair64 *)(blk + L.pv); ws.pu = (Pair64 *)(blk + L.pu); ws.pair_cap = L.pair_cap; ws.reg_cap = L.reg_cap;
     int32_t *sw = (int32_t *)(blk + L.sw);
@@ -140,6 +138,23 @@ __device__ __forceinline__ void make_ws(const FinalLayout &L, uint8_t *blk, Fina
     ws.sw.b = (uint64_t *)(blk + L.swb); ws.sw.cap = L.sw_cap; ws.sw.cap_b = L.sw_b;
     ws.rev = blk + L.rev;
     wregs = (AlnReg *)(blk + L.wregs);
+}
+
+// K6 + K8b: one warp per queued alignment
+__global__ void __launch_bounds__(128) k_tasks(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint8_t *zbuf, long z_cap, int max_q, int smem_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int wib = threadIdx.x >> 5;
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    uint8_t *mine = smem + (size_t)wib * smem_per_warp;
+    WarpTask S;
+    S.H = (int32_t *)mine; S.E = S.H + (max_q + 1);
+    S.cigar = (uint32_t *)(S.E + (max_q + 1)); S.cigar_cap = 2 * max_q + 16;
+    S.md = (char *)(S.cigar + S.cigar_cap); S.md_cap = 8 * max_q + 64;
+    S.xb = S.md + S.md_cap; S.xb_cap = 4 * max_q + 64;
+    S.qs = (uint8_t *)(S.xb + S.xb_cap);
+    uint8_t *z = zbuf + (size_t)gw * z_cap;
+    for (unsigned int k = gw; k < n_tasks; k += nw) stage_task_warp(opt, ix, B, k, S, z, z_cap, max_q);
 }
 
 __global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
@@ -191,7 +206,7 @@ __global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
 struct CudaAligner::Impl {
     int device = 0, n_sm = 0;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[12];
+    cudaEvent_t ev[12];   // 0..9 stage boundaries, 10 = selection kernel done
     // resident index
     DevBuf<uint32_t> d_bwt, d_sa32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
     IndexView ix;
@@ -206,7 +221,9 @@ struct CudaAligner::Impl {
     DevBuf<int32_t> d_eh;
     DevBuf<int8_t> d_pe_dir; DevBuf<int64_t> d_pe_isize;
     DevBuf<double> d_log, d_pair;
-    DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch;
+    DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
+    DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
+    size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
     std::vector<double> log_tab;
     size_t arena_cap = 0;
@@ -250,7 +267,7 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     build_log_table(m.log_tab, 65536);
     m.d_log.ensure(m.log_tab.size());
     CK(cudaMemcpy(m.d_log.p, m.log_tab.data(), m.log_tab.size() * 8, cudaMemcpyHostToDevice));
-    m.d_used.ensure(1); m.d_misc.ensure(16);
+    m.d_used.ensure(1); m.d_misc.ensure(16); m.d_ntasks.ensure(1);
 }
 
 CudaAligner::~CudaAligner()
@@ -414,34 +431,54 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     memset(&L, 0, sizeof L);
     L.max_q = max_q;
     L.reg_cap = max_regs + 4 * opt.max_matesw + 8;
-    L.z_cap = (long)max_q * (long)(max_q + 2 * (4 * opt.w) + 64);
-    L.cigar_cap = 2 * max_q + 16; L.md_cap = 8 * max_q + 64; L.xb_cap = 4 * max_q + 64;
-    L.pair_cap = 16384; L.sw_cap = max_q + 32; L.sw_b = 1 << 14; L.wreg_stride = L.reg_cap + opt.max_matesw;
+    L.pair_cap = 4096; L.sw_cap = max_q + 32; L.sw_b = 1 << 14; L.wreg_stride = L.reg_cap + opt.max_matesw;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    L.eh = take((size_t)2 * (max_q + 1) * 4); L.z = take((size_t)L.z_cap); L.cigar = take((size_t)L.cigar_cap * 4);
-    L.md = take(L.md_cap); L.xb = take(L.xb_cap); L.cnt = take((size_t)L.reg_cap * 4); L.has_alt = take(L.reg_cap);
+    L.eh = take((size_t)2 * (max_q + 1) * 4);
+    L.cnt = take((size_t)L.reg_cap * 4); L.has_alt = take(L.reg_cap);
     L.zz = take((size_t)L.reg_cap * 4); L.pv = take((size_t)L.pair_cap * 16); L.pu = take((size_t)L.pair_cap * 16);
     L.sw = take((size_t)4 * L.sw_cap * 4); L.swb = take((size_t)L.sw_b * 8); L.rev = take(max_q);
     L.wregs = take((size_t)2 * L.wreg_stride * sizeof(AlnReg));
     L.total = o;
     const int fin_block = 32;
     const int items = pe ? n >> 1 : n;
-    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)m.n_sm * 8 * fin_block);
+    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)m.n_sm * 16 * fin_block);
     m.d_final_scratch.ensure((size_t)fin_workers * L.total);
     m.d_out.ensure(n + 1);
     B.out = m.d_out.p;
     if (m.arena_cap == 0) m.arena_cap = (size_t)n * 640 + (1 << 20);
+    if (m.task_cap == 0) m.task_cap = (size_t)n + (size_t)n / 2 + 4096;
+    // task kernel geometry
+    const int tk_wpb = 4;
+    const int tk_blocks = m.n_sm * 8;
+    const long z_cap = (long)max_q * (long)(max_q + 2 * (4 * opt.w) + 64);
+    const int tk_smem_per_warp = (2 * (max_q + 1) * 4 + (2 * max_q + 16) * 4 + (8 * max_q + 64) + (4 * max_q + 64) + max_q + 31) & ~15;
+    m.d_zbuf.ensure((size_t)tk_blocks * tk_wpb * z_cap);
+    if (tk_wpb * tk_smem_per_warp > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, tk_wpb * tk_smem_per_warp));
     unsigned long long used = 0;
+    unsigned int n_tasks = 0;
     out.reads.resize(n);
     for (;;) {
         m.d_arena.ensure(m.arena_cap);
+        m.d_tasks.ensure(m.task_cap);
         unsigned long long init = 8; // offset 0 = "null"
         CK(cudaMemcpyAsync(m.d_used.p, &init, 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(m.d_ntasks.p, 0, 4, st));
         B.arena.base = m.d_arena.p; B.arena.used = m.d_used.p; B.arena.cap = m.arena_cap;
+        B.tasks.a = m.d_tasks.p; B.tasks.n = m.d_ntasks.p; B.tasks.cap = (unsigned int)m.task_cap;
         if (items) {
             if (pe) k_final_pe<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
             else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            ++m.launches;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&n_tasks, m.d_ntasks.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(m.ev[10], st));
+        CK(cudaStreamSynchronize(st));
+        if (n_tasks > m.task_cap) { m.task_cap = (size_t)n_tasks + (size_t)n_tasks / 4 + 4096; continue; }
+        if (n_tasks) {
+            k_tasks<<<tk_blocks, tk_wpb * 32, tk_wpb * tk_smem_per_warp, st>>>(opt, m.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, tk_smem_per_warp);
             ++m.launches;
         }
         CK(cudaGetLastError());
@@ -463,6 +500,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     float ms;
     for (int k = 0; k < 9; ++k) { CK(cudaEventElapsedTime(&ms, m.ev[k], m.ev[k + 1])); if (k < 8) out.ms_stage[k] = ms; else out.ms_d2h = ms; }
     out.ms_h2d = out.ms_stage[0];
+    CK(cudaEventElapsedTime(&ms, m.ev[7], m.ev[10])); out.ms_select = ms;
+    CK(cudaEventElapsedTime(&ms, m.ev[10], m.ev[8])); out.ms_tasks = ms;
+    out.n_tasks = n_tasks;
     CK(cudaEventElapsedTime(&ms, m.ev[1], m.ev[8]));
     out.ms_kernels = ms;
     out.n_seeds = S;

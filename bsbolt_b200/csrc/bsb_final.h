@@ -3,7 +3,8 @@
 //   mark_primary()     <- mem_mark_primary_se(_core)      (bwamem.c:497-562)
 //   approx_mapq()      <- mem_approx_mapq_se              (bwamem.c:1059-1083)
 //   bs_md_xb()         <- bwa_gen_cigar2 part 2 + getMethylationContext (bwa.c:180-196, 250-343)
-//   reg_to_aln()       <- mem_reg2aln + infer_bw          (bwamem.c:796-803, 1197-1272)
+//   aln_head()/align_body()/aln_finish() <- mem_reg2aln + infer_bw (bwamem.c:796-803, 1197-1272), split into the
+//                         part decided per region and the base-level part that runs as a deferred AlnTask
 //   emit_read()        <- mem_reg2sam + mem_gen_alt       (bwamem.c:1110-1155, bwamem_extra.c:91-152)
 //   mate_rescue()      <- mem_matesw                      (bwamem_pair.c:111-180)
 //   pair_hits()        <- mem_pair                        (bwamem_pair.c:182-243)
@@ -276,8 +277,26 @@ BSB_HD int infer_bw(int l1, int l2, int score, int a, int q, int r)
     return w;
 }
 
-struct AlnTmp {             // mem_aln_t while it still lives in scratch
+struct TaskList {
+    AlnTask *a; unsigned int *n; unsigned int cap;
+    BSB_HD void push(const AlnTask &t, int *err)
+    {
+#if defined(__CUDA_ARCH__)
+        unsigned int k = atomicAdd(n, 1u);
+#else
+        unsigned int k = (*n)++;
+#endif
+        if (k < cap) a[k] = t; else *err = ERR_ARENA_OVERFLOW; // the counter keeps counting: exact size for the retry
+    }
+};
+
+struct AlnTmp {             // the part of mem_aln_t that does not need the base-level alignment
     int64_t pos; int rid, flag, is_rev, is_alt, mapq, NM, n_cigar, score, sub, alt_sc, md_len;
+    MethCounts mc;
+};
+
+struct AlnBody {            // the part that does: produced by align_body() / the warp kernel
+    int64_t pos; int rid, is_rev, NM, n_cigar, md_len;
     MethCounts mc;
 };
 
@@ -288,51 +307,53 @@ BSB_HD void aln_unmapped(AlnTmp &a)
     a.mc.cg_meth = a.mc.cg_unmeth = a.mc.ch_meth = a.mc.ch_unmeth = 0;
 }
 
-// Result: `a`, CIGAR in ws.cigar[0..n_cigar), "MD\tXB:Z:xb" text in ws.md[0..md_len).
-BSB_HD void reg_to_aln(const Opt &opt, const IndexView &ix, const MathTab &mt, int l_query, const uint8_t *query,
-                       const uint8_t *oquery, const AlnReg *ar, FinalWS &ws, AlnTmp &a, int *err)
+// mem_reg2aln, first half: everything that follows from the region record alone
+BSB_HD bool aln_head(const Opt &opt, const MathTab &mt, const AlnReg *ar, AlnTmp &a, int *err)
 {
     aln_unmapped(a);
-    if (ar == nullptr || ar->rb < 0 || ar->re < 0) return;
+    if (ar == nullptr || ar->rb < 0 || ar->re < 0) return false;
     a.flag = 0;
-    int qb = ar->qb, qe = ar->qe, w2, tmp, score = 0, last_sc = -(1 << 30), i, is_rev;
-    int64_t rb = ar->rb, re = ar->re, pos;
     a.mapq = ar->secondary < 0 ? approx_mapq(opt, mt, *ar, err) : 0;
     if (ar->secondary >= 0) a.flag |= 0x100;
-    tmp = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_del, opt.e_del);
-    w2 = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_ins, opt.e_ins);
+    a.rid = ar->rid;
+    a.score = ar->score; a.sub = ar->sub > ar->csub ? ar->sub : ar->csub;
+    a.is_alt = ar->is_alt; a.alt_sc = ar->alt_sc;
+    return true;
+}
+
+BSB_HD int band_for_task(const Opt &opt, const AlnTask &t)
+{   // infer_bw x2 + clamp (bwamem.c:1219-1223)
+    int tmp = infer_bw(t.qe - t.qb, (int)(t.re - t.rb), t.truesc, opt.a, opt.o_del, opt.e_del);
+    int w2 = infer_bw(t.qe - t.qb, (int)(t.re - t.rb), t.truesc, opt.a, opt.o_ins, opt.e_ins);
     w2 = w2 > tmp ? w2 : tmp;
-    if (w2 > opt.w) w2 = w2 < ar->w ? w2 : ar->w;
-    CigarBuf cig = {ws.cigar, 0, ws.cigar_cap - 2};
-    i = 0;
-    bool ok;
-    do {
-        w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
-        ok = global_core(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cig, ws.dp, err);
-        if (!ok) break;
-        if (score == last_sc || w2 == opt.w << 2) break;
-        last_sc = score;
-        w2 <<= 1;
-    } while (++i < 3 && score < ar->truesc - opt.a);
-    if (!ok) { if (!*err) *err = ERR_NO_MD; aln_unmapped(a); return; }
-    StrBuf md = {ws.md, 0, ws.md_cap, false}, xb = {ws.xb, 0, ws.xb_cap, false};
-    if (bs_md_xb(ix, cig.n, cig.a, qe - qb, oquery, rb, re, md, xb, &a.NM, &a.mc)) {
+    if (w2 > opt.w) w2 = w2 < t.w ? w2 : t.w;
+    return w2;
+}
+
+// mem_reg2aln after the CIGAR is known: bisulfite MD/XB/NM, strand, position, deletion squeeze, soft clips.
+// cig holds the CIGAR of the global alignment (room for two more operations).
+BSB_HD void aln_finish(const IndexView &ix, const AlnTask &t, int l_query, const uint8_t *oquery,
+                       uint32_t *c, int n_cig, StrBuf &md, StrBuf &xb, AlnBody &b, int *err)
+{
+    const int qb = t.qb, qe = t.qe;
+    const int64_t rb = t.rb, re = t.re;
+    int is_rev;
+    if (bs_md_xb(ix, n_cig, c, qe - qb, oquery, rb, re, md, xb, &b.NM, &b.mc)) {
         const char tag[7] = "\tXB:Z:";
         for (int j = 0; j < 6; ++j) md.putc_(tag[j]);
         for (int j = 0; j < xb.n; ++j) md.putc_(xb.s[j]);
         if (md.ovf || xb.ovf) *err = ERR_SCRATCH_OVERFLOW;
-        a.md_len = md.n;
+        b.md_len = md.n;
     } else {
         // The +-2 flank of the unconverted reference bridges the strand boundary: the reference returns
         // the CIGAR without MD/XB and leaves NM = -1, which its 22-bit field prints as 4194303; the MD
         // text it then reads is whatever follows the CIGAR in memory (empty in practice) (bwa.c:266).
-        a.NM = 0x3fffff; a.md_len = 0;
-        a.mc.cg_meth = a.mc.cg_unmeth = a.mc.ch_meth = a.mc.ch_unmeth = 0;
+        b.NM = 0x3fffff; b.md_len = 0;
+        b.mc.cg_meth = b.mc.cg_unmeth = b.mc.ch_meth = b.mc.ch_unmeth = 0;
     }
-    pos = depos(ix.l_pac, rb < ix.l_pac ? rb : re - 1, &is_rev);
-    a.is_rev = is_rev;
-    int n_cigar = cig.n;
-    uint32_t *c = ws.cigar;
+    int64_t pos = depos(ix.l_pac, rb < ix.l_pac ? rb : re - 1, &is_rev);
+    b.is_rev = is_rev;
+    int n_cigar = n_cig;
     if (n_cigar > 0) { // squeeze out a leading or trailing deletion
         if ((c[0] & 0xf) == 2) {
             pos += c[0] >> 4;
@@ -350,33 +371,30 @@ BSB_HD void reg_to_aln(const Opt &opt, const IndexView &ix, const MathTab &mt, i
         }
         if (clip3) c[n_cigar++] = (uint32_t)clip3 << 4 | 3;
     }
-    a.n_cigar = n_cigar;
-    a.rid = pos2rid(ix, pos);
-    a.pos = pos - ix.anns[a.rid].offset;
-    a.score = ar->score; a.sub = ar->sub > ar->csub ? ar->sub : ar->csub;
-    a.is_alt = ar->is_alt; a.alt_sc = ar->alt_sc;
+    b.n_cigar = n_cigar;
+    b.rid = pos2rid(ix, pos);
+    b.pos = pos - ix.anns[b.rid].offset;
 }
 
-// copies the scratch record into the arena
-BSB_HD void aln_store(const AlnTmp &t, const FinalWS &ws, Arena &ar, AlnOut &o, int *err)
+// mem_reg2aln, second half (scalar form): up to three global alignments with a doubling band, then aln_finish
+BSB_HD bool align_body(const Opt &opt, const IndexView &ix, const AlnTask &t, int l_query, const uint8_t *query,
+                       const uint8_t *oquery, FinalWS &ws, AlnBody &b, int *err)
 {
-    o.pos = t.pos; o.rid = t.rid; o.flag = t.flag; o.is_rev = t.is_rev; o.is_alt = t.is_alt; o.mapq = t.mapq; o.NM = t.NM;
-    o.n_cigar = t.n_cigar; o.md_len = t.md_len;
-    o.ch_meth = t.mc.ch_meth; o.ch_unmeth = t.mc.ch_unmeth; o.cg_meth = t.mc.cg_meth; o.cg_unmeth = t.mc.cg_unmeth;
-    o.score = t.score; o.sub = t.sub; o.alt_sc = t.alt_sc;
-    o.xa_off = 0; o.xa_n = 0; o.cigar_off = 0; o.md_off = 0;
-    if (t.n_cigar > 0) {
-        o.cigar_off = ar.alloc((uint32_t)t.n_cigar * 4u, err);
-        if (*err == ERR_ARENA_OVERFLOW) { o.n_cigar = 0; o.md_len = 0; return; }
-        uint32_t *d = reinterpret_cast<uint32_t *>(ar.base + o.cigar_off);
-        for (int j = 0; j < t.n_cigar; ++j) d[j] = ws.cigar[j];
-    }
-    if (t.md_len > 0) {
-        o.md_off = ar.alloc((uint32_t)t.md_len, err);
-        if (*err == ERR_ARENA_OVERFLOW) { o.md_len = 0; return; }
-        char *d = reinterpret_cast<char *>(ar.base + o.md_off);
-        for (int j = 0; j < t.md_len; ++j) d[j] = ws.md[j];
-    }
+    int w2 = band_for_task(opt, t), score = 0, last_sc = -(1 << 30), i = 0;
+    CigarBuf cig = {ws.cigar, 0, ws.cigar_cap - 2};
+    bool ok;
+    do {
+        w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+        ok = global_core(opt, ix, w2, t.qe - t.qb, query + t.qb, t.rb, t.re, &score, &cig, ws.dp, err);
+        if (!ok) break;
+        if (score == last_sc || w2 == opt.w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++i < 3 && score < t.truesc - opt.a);
+    if (!ok) { if (!*err) *err = ERR_NO_MD; return false; }
+    StrBuf md = {ws.md, 0, ws.md_cap, false}, xb = {ws.xb, 0, ws.xb_cap, false};
+    aln_finish(ix, t, l_query, oquery, ws.cigar, cig.n, md, xb, b, err);
+    return true;
 }
 
 BSB_HD int get_rlen(int n_cigar, const uint32_t *cigar)
@@ -386,10 +404,62 @@ BSB_HD int get_rlen(int n_cigar, const uint32_t *cigar)
     return l;
 }
 
-BSB_HD void mate_from(const AlnTmp &t, const uint32_t *cigar, ReadOut &dst)
+// Writes a finished body (CIGAR in `cigar`, text in `md`) to its record(s) in the arena.
+// lane-0 / single-thread code. `reads` is the ReadOut array of the batch.
+BSB_HD void task_store(const IndexView &ix, const AlnTask &t, const AlnBody &b, const uint32_t *cigar, const char *md,
+                       Arena &ar, ReadOut *reads, int *err)
 {
-    dst.h_pos = t.pos; dst.h_rid = t.rid; dst.h_is_rev = t.is_rev; dst.h_n_cigar = t.n_cigar;
-    dst.h_rlen = get_rlen(t.n_cigar, cigar); dst.h_ch_meth = t.mc.ch_meth; dst.h_ch_unmeth = t.mc.ch_unmeth;
+    uint32_t cig_off = 0, md_off = 0;
+    if (b.n_cigar > 0) {
+        cig_off = ar.alloc((uint32_t)b.n_cigar * 4u, err);
+        if (*err == ERR_ARENA_OVERFLOW) return;
+        uint32_t *d = reinterpret_cast<uint32_t *>(ar.base + cig_off);
+        for (int j = 0; j < b.n_cigar; ++j) d[j] = cigar[j];
+    }
+    if (t.kind == 0) {
+        if (b.md_len > 0) {
+            md_off = ar.alloc((uint32_t)b.md_len, err);
+            if (*err == ERR_ARENA_OVERFLOW) return;
+            char *d = reinterpret_cast<char *>(ar.base + md_off);
+            for (int j = 0; j < b.md_len; ++j) d[j] = md[j];
+        }
+        AlnOut &o = *reinterpret_cast<AlnOut *>(ar.base + t.target_off);
+        o.pos = b.pos; o.rid = b.rid; o.is_rev = b.is_rev; o.NM = b.NM; o.n_cigar = b.n_cigar; o.cigar_off = cig_off;
+        o.md_off = md_off; o.md_len = b.md_len;
+        o.ch_meth = b.mc.ch_meth; o.ch_unmeth = b.mc.ch_unmeth; o.cg_meth = b.mc.cg_meth; o.cg_unmeth = b.mc.cg_unmeth;
+    } else {
+        XaOut &x = *reinterpret_cast<XaOut *>(ar.base + t.target_off);
+        x.pos = b.pos; x.rid = b.rid; x.NM = b.NM; x.n_cigar = b.n_cigar; x.cigar_off = cig_off;
+        x.is_rev = ix.anns[b.rid].is_crick ? 1 : 0;
+    }
+    if (t.mate_read >= 0) {
+        ReadOut &dst = reads[t.mate_read];
+        dst.h_pos = b.pos; dst.h_rid = b.rid; dst.h_is_rev = b.is_rev; dst.h_n_cigar = b.n_cigar;
+        dst.h_rlen = get_rlen(b.n_cigar, cigar); dst.h_ch_meth = b.mc.ch_meth; dst.h_ch_unmeth = b.mc.ch_unmeth;
+    }
+}
+
+// header part of a record into the arena; the body fields are completed by the task
+BSB_HD void aln_store(const AlnTmp &t, AlnOut &o)
+{
+    o.pos = t.pos; o.rid = t.rid; o.flag = t.flag; o.is_rev = t.is_rev; o.is_alt = t.is_alt; o.mapq = t.mapq; o.NM = t.NM;
+    o.n_cigar = 0; o.md_len = 0;
+    o.ch_meth = o.ch_unmeth = o.cg_meth = o.cg_unmeth = 0;
+    o.score = t.score; o.sub = t.sub; o.alt_sc = t.alt_sc;
+    o.xa_off = 0; o.xa_n = 0; o.cigar_off = 0; o.md_off = 0;
+}
+
+BSB_HD void mate_unmapped(ReadOut &dst)
+{
+    dst.h_pos = -1; dst.h_rid = -1; dst.h_is_rev = 0; dst.h_n_cigar = 0; dst.h_rlen = 0; dst.h_ch_meth = dst.h_ch_unmeth = 0;
+}
+
+BSB_HD void push_task(TaskList &tl, const AlnReg &ar, int read, int kind, uint32_t target_off, int mate_read, int *err)
+{
+    AlnTask t;
+    t.rb = ar.rb; t.re = ar.re; t.qb = ar.qb; t.qe = ar.qe; t.truesc = ar.truesc; t.w = ar.w;
+    t.read = read; t.kind = kind; t.target_off = target_off; t.mate_read = mate_read;
+    tl.push(t, err);
 }
 
 // ---- XA + record emission ------------------------------------------------------------------------
@@ -402,8 +472,8 @@ BSB_HD int xa_pri_idx(double XA_drop_ratio, const AlnReg *a, int i)
 }
 
 struct ReadCtx {           // everything the finalisation of one read needs
+    int read;              // bseq entry index
     int l_seq;
-    const uint8_t *seq, *oseq;
     AlnReg *regs; int n_regs;
 };
 
@@ -416,10 +486,10 @@ BSB_HD void xa_prepare(const Opt &opt, const ReadCtx &rc, FinalWS &ws)
     }
 }
 
-// XA entries of region k (mem_gen_alt): one global alignment per listed secondary hit
-BSB_HD void xa_emit(const Opt &opt, const IndexView &ix, const MathTab &mt, const ReadCtx &rc, int k,
-                    FinalWS &ws, Arena &ar, AlnOut &o, int *err)
+// XA entries of region k (mem_gen_alt): one global alignment task per listed secondary hit
+BSB_HD void xa_emit(const Opt &opt, const ReadCtx &rc, int k, FinalWS &ws, Arena &ar, TaskList &tl, uint32_t aln_off, int *err)
 {
+    AlnOut &o = *reinterpret_cast<AlnOut *>(ar.base + aln_off);
     o.xa_n = 0; o.xa_off = 0;
     if (opt.flag & F_ALL) return;
     int cnt = ws.cnt[k];
@@ -431,26 +501,21 @@ BSB_HD void xa_emit(const Opt &opt, const IndexView &ix, const MathTab &mt, cons
     int n = 0;
     for (int i = 0; i < rc.n_regs; ++i) {
         if (xa_pri_idx((double)opt.XA_drop_ratio, rc.regs, i) != k) continue;
-        AlnTmp t;
-        reg_to_aln(opt, ix, mt, rc.l_seq, rc.seq, rc.oseq, &rc.regs[i], ws, t, err);
-        XaOut &x = xa[n++];
-        x.pos = t.pos; x.rid = t.rid; x.NM = t.NM; x.score = t.score; x.n_cigar = t.n_cigar;
-        x.is_rev = t.rid >= 0 ? (ix.anns[t.rid].is_crick ? 1 : 0) : 0;
-        x.cigar_off = 0;
-        if (t.n_cigar > 0) {
-            x.cigar_off = ar.alloc((uint32_t)t.n_cigar * 4u, err);
-            if (*err == ERR_ARENA_OVERFLOW) { x.n_cigar = 0; continue; }
-            uint32_t *d = reinterpret_cast<uint32_t *>(ar.base + x.cigar_off);
-            for (int j = 0; j < t.n_cigar; ++j) d[j] = ws.cigar[j];
-        }
+        const AlnReg &r = rc.regs[i];
+        XaOut &x = xa[n];
+        x.pos = -1; x.rid = r.rid; x.NM = 0; x.score = r.score; x.n_cigar = 0; x.is_rev = 0; x.cigar_off = 0;
+        push_task(tl, r, rc.read, 1, off + (uint32_t)n * (uint32_t)sizeof(XaOut), -1, err);
+        ++n;
     }
     o.xa_off = off; o.xa_n = n;
 }
 
-// mem_reg2sam: choose the regions that become SAM lines and build their records
-BSB_HD void emit_read(const Opt &opt, const IndexView &ix, const MathTab &mt, const ReadCtx &rc, int extra_flag,
-                      FinalWS &ws, Arena &ar, ReadOut &ro, int *err)
+// mem_reg2sam: choose the regions that become SAM lines; mate_read >= 0: the first record doubles as the
+// mate record of that entry (h[] of the no-pairing branch of mem_sam_pe)
+BSB_HD void emit_read(const Opt &opt, const MathTab &mt, const ReadCtx &rc, int extra_flag, int mate_read,
+                      FinalWS &ws, Arena &ar, TaskList &tl, ReadOut *reads, int *err)
 {
+    ReadOut &ro = reads[rc.read];
     const AlnReg *a = rc.regs;
     int n_out = 0;
     for (int k = 0; k < rc.n_regs; ++k) {
@@ -470,24 +535,28 @@ BSB_HD void emit_read(const Opt &opt, const IndexView &ix, const MathTab &mt, co
         AlnTmp t;
         aln_unmapped(t);
         t.flag |= extra_flag;
-        aln_store(t, ws, ar, out[0], err);
+        aln_store(t, out[0]);
         ro.n_aln = 1;
+        if (mate_read >= 0) mate_unmapped(reads[mate_read]);
         return;
     }
-    int l = 0;
+    int l = 0, mapq0 = 0;
     for (int k = 0; k < rc.n_regs; ++k) {
         const AlnReg &p = a[k];
         if (p.score < opt.T) continue;
         if (p.secondary >= 0 && (p.is_alt || !(opt.flag & F_ALL))) continue;
         if (p.secondary >= 0 && p.secondary < 0x7fffffff && p.score < a[p.secondary].score * opt.drop_ratio) continue;
         AlnTmp t;
-        reg_to_aln(opt, ix, mt, rc.l_seq, rc.seq, rc.oseq, &p, ws, t, err);
+        aln_head(opt, mt, &p, t, err);
         t.flag |= extra_flag;
         if (p.secondary >= 0) t.sub = -1;
         if (l && p.secondary < 0) t.flag |= (opt.flag & F_NO_MULTI) ? 0x10000 : 0x800;
-        if (!(opt.flag & F_KEEP_SUPP_MAPQ) && l && !p.is_alt && t.mapq > out[0].mapq) t.mapq = out[0].mapq;
-        aln_store(t, ws, ar, out[l], err);
-        xa_emit(opt, ix, mt, rc, k, ws, ar, out[l], err);
+        if (l == 0) mapq0 = t.mapq;
+        if (!(opt.flag & F_KEEP_SUPP_MAPQ) && l && !p.is_alt && t.mapq > mapq0) t.mapq = mapq0;
+        aln_store(t, out[l]);
+        const uint32_t off = ro.aln_off + (uint32_t)l * (uint32_t)sizeof(AlnOut);
+        push_task(tl, p, rc.read, 0, off, l == 0 ? mate_read : -1, err);
+        xa_emit(opt, rc, k, ws, ar, tl, off, err);
         ++l;
     }
     ro.n_aln = l;
@@ -664,15 +733,15 @@ BSB_HD int pair_hits(const Opt &opt, const IndexView &ix, const MathTab &mt, con
 }
 
 // mem_sam_pe. regs0/regs1 are the two ends' region lists (capacity cap0/cap1; rescue may append).
-BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt, const PeStat pes[4], uint64_t id,
-                          int l0, const uint8_t *seq0, const uint8_t *oseq0, RegList &r0,
-                          int l1, const uint8_t *seq1, const uint8_t *oseq1, RegList &r1,
-                          FinalWS &ws, Arena &ar, ReadOut &o0, ReadOut &o1, int *err)
+// `first` is the bseq index of read 1 of the pair (read 2 is first+1); alignments are queued in `tl`.
+BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt, const PeStat pes[4], uint64_t id, int first,
+                          int l0, const uint8_t *seq0, RegList &r0, int l1, const uint8_t *seq1, RegList &r1,
+                          FinalWS &ws, Arena &ar, TaskList &tl, ReadOut *reads, int *err)
 {
     RegList *a[2] = {&r0, &r1};
     const int ls[2] = {l0, l1};
-    const uint8_t *seqs[2] = {seq0, seq1}, *oseqs[2] = {oseq0, oseq1};
-    ReadOut *ro[2] = {&o0, &o1};
+    const uint8_t *seqs[2] = {seq0, seq1};
+    ReadOut *ro[2] = {&reads[first], &reads[first + 1]};
     int i, j, z[2] = {0, 0}, o, subo = 0, n_sub = 0, extra_flag = 1, n_pri[2];
 
     if (!(opt.flag & F_NO_RESCUE)) {
@@ -696,7 +765,7 @@ BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt
     n_pri[0] = mark_primary(opt, a[0]->n, a[0]->a, (int64_t)(id << 1 | 0), ws.z);
     n_pri[1] = mark_primary(opt, a[1]->n, a[1]->a, (int64_t)(id << 1 | 1), ws.z);
     ReadCtx rc[2];
-    for (i = 0; i < 2; ++i) { rc[i].l_seq = ls[i]; rc[i].seq = seqs[i]; rc[i].oseq = oseqs[i]; rc[i].regs = a[i]->a; rc[i].n_regs = a[i]->n; }
+    for (i = 0; i < 2; ++i) { rc[i].read = first + i; rc[i].l_seq = ls[i]; rc[i].regs = a[i]->a; rc[i].n_regs = a[i]->n; }
 
     bool paired = false;
     if (!(opt.flag & F_NOPAIRING) && n_pri[0] && n_pri[1] &&
@@ -752,19 +821,21 @@ BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt
                 AlnOut *out = reinterpret_cast<AlnOut *>(ar.base + ro[i]->aln_off);
                 if (!(opt.flag & F_ALL)) xa_prepare(opt, rc[i], ws);
                 AlnTmp h;
-                reg_to_aln(opt, ix, mt, ls[i], seqs[i], oseqs[i], &a[i]->a[z[i]], ws, h, err);
+                aln_head(opt, mt, &a[i]->a[z[i]], h, err);
                 h.mapq = q_se[i];
                 h.flag |= 0x40 << i | extra_flag;
-                mate_from(h, ws.cigar, *ro[!i]);
-                aln_store(h, ws, ar, out[0], err);
-                xa_emit(opt, ix, mt, rc[i], z[i], ws, ar, out[0], err);
+                aln_store(h, out[0]);
+                push_task(tl, a[i]->a[z[i]], first + i, 0, ro[i]->aln_off, first + (i ^ 1), err); // also h[i], the mate record of the other end
+                xa_emit(opt, rc[i], z[i], ws, ar, tl, ro[i]->aln_off, err);
                 ro[i]->n_aln = 1;
                 if (has_alt_hit) {
                     AlnTmp g;
-                    reg_to_aln(opt, ix, mt, ls[i], seqs[i], oseqs[i], &a[i]->a[n_pri[i]], ws, g, err);
+                    aln_head(opt, mt, &a[i]->a[n_pri[i]], g, err);
                     g.flag |= 0x800 | 0x40 << i | extra_flag;
-                    aln_store(g, ws, ar, out[1], err);
-                    xa_emit(opt, ix, mt, rc[i], n_pri[i], ws, ar, out[1], err);
+                    aln_store(g, out[1]);
+                    const uint32_t off = ro[i]->aln_off + (uint32_t)sizeof(AlnOut);
+                    push_task(tl, a[i]->a[n_pri[i]], first + i, 0, off, -1, err);
+                    xa_emit(opt, rc[i], n_pri[i], ws, ar, tl, off, err);
                     ro[i]->n_aln = 2;
                 }
             }
@@ -780,18 +851,16 @@ BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt
             if (a[i]->a[0].score >= opt.T) which = 0;
             else if (n_pri[i] < a[i]->n && a[i]->a[n_pri[i]].score >= opt.T) which = n_pri[i];
         }
-        AlnTmp h;
-        reg_to_aln(opt, ix, mt, ls[i], seqs[i], oseqs[i], which >= 0 ? &a[i]->a[which] : nullptr, ws, h, err);
-        mate_from(h, ws.cigar, *ro[!i]);
-        h_rid[i] = h.rid;
+        // h[i] is the first record emit_read() produces for this end (or unmapped); its rid is the region's
+        h_rid[i] = which >= 0 && a[i]->a[which].rb >= 0 && a[i]->a[which].re >= 0 ? a[i]->a[which].rid : -1;
     }
     if (!(opt.flag & F_NOPAIRING) && h_rid[0] == h_rid[1] && h_rid[0] >= 0) {
         int64_t dist;
         int d = infer_dir(ix.l_pac, a[0]->a[0].rb, a[1]->a[0].rb, &dist);
         if (!pes[d].failed && dist >= pes[d].low && dist <= pes[d].high) extra_flag |= 2;
     }
-    emit_read(opt, ix, mt, rc[0], 0x41 | extra_flag, ws, ar, *ro[0], err);
-    emit_read(opt, ix, mt, rc[1], 0x81 | extra_flag, ws, ar, *ro[1], err);
+    emit_read(opt, mt, rc[0], 0x41 | extra_flag, first + 1, ws, ar, tl, reads, err);
+    emit_read(opt, mt, rc[1], 0x81 | extra_flag, first, ws, ar, tl, reads, err);
 }
 
 } // namespace bsb

@@ -47,6 +47,7 @@ struct BatchDev {
     // output
     ReadOut *out;
     Arena arena;
+    TaskList tasks;
 };
 
 struct SeedScratch { Intv *mem1, *t0, *t1; };
@@ -191,14 +192,19 @@ BSB_HD void stage_pestat(const Opt &opt, const IndexView &ix, const BatchDev &B,
     B.pe_dir[p] = (int8_t)d; B.pe_isize[p] = is;
 }
 
-// K6+K8 (single-end): mark primary, CIGAR, bisulfite tags, XA -> records.
+BSB_HD void readout_init(ReadOut &ro, int err)
+{
+    ro.aln_off = 0; ro.n_aln = 0; ro.h_pos = -1; ro.h_rid = -1; ro.h_is_rev = 0; ro.h_n_cigar = 0; ro.h_rlen = 0;
+    ro.h_ch_meth = ro.h_ch_unmeth = 0; ro.err = err; ro.pad_ = 0;
+}
+
+// K8a (single-end): mark primary, choose the records, MAPQ/flags, XA lists; queues the alignments (AlnTask).
 // Works on a private copy of the regions (wregs) so that a batch can be re-finalised after an
 // arena overflow: mark_primary's hash tie-break depends on the incoming order.
 BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int r, FinalWS &ws, AlnReg *wregs)
 {
     ReadOut &ro = B.out[r];
-    ro.aln_off = 0; ro.n_aln = 0; ro.h_pos = -1; ro.h_rid = -1; ro.h_is_rev = 0; ro.h_n_cigar = 0; ro.h_rlen = 0;
-    ro.h_ch_meth = ro.h_ch_unmeth = 0; ro.err = B.err[r]; ro.pad_ = 0;
+    readout_init(ro, B.err[r]);
     if (ro.err) return;
     int err = 0;
     const int n = B.n_regs[r];
@@ -207,39 +213,49 @@ BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int
     for (int j = 0; j < n; ++j) wregs[j] = src[j];
     mark_primary(opt, n, wregs, B.n_processed + r, ws.z);
     ReadCtx rc;
+    rc.read = r;
     rc.l_seq = (int)(B.seq_off[r + 1] - B.seq_off[r]);
-    rc.seq = B.seq + B.seq_off[r]; rc.oseq = B.oseq + B.seq_off[r];
     rc.regs = wregs; rc.n_regs = n;
-    emit_read(opt, ix, B.mt, rc, 0, ws, B.arena, ro, &err);
+    emit_read(opt, B.mt, rc, 0, -1, ws, B.arena, B.tasks, B.out, &err);
     ro.err = err;
 }
 
-// K7+K6+K8 (paired-end). wregs: per-worker scratch of 2*(reg_cap + max_matesw) regions
+// K7 + K8a (paired-end): mate rescue, pairing, record selection. wregs: per-worker scratch of
+// 2*(reg_cap + max_matesw) regions
 BSB_HD void stage_final_pe(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs)
 {
     const int r0 = p << 1, r1 = r0 | 1;
-    ReadOut *ro[2] = {&B.out[r0], &B.out[r1]};
-    for (int i = 0; i < 2; ++i) {
-        ro[i]->aln_off = 0; ro[i]->n_aln = 0; ro[i]->h_pos = -1; ro[i]->h_rid = -1; ro[i]->h_is_rev = 0; ro[i]->h_n_cigar = 0;
-        ro[i]->h_rlen = 0; ro[i]->h_ch_meth = ro[i]->h_ch_unmeth = 0; ro[i]->pad_ = 0;
-        ro[i]->err = B.err[r0] ? B.err[r0] : B.err[r1];
-    }
-    if (ro[0]->err) return;
+    const int e0 = B.err[r0] ? B.err[r0] : B.err[r1];
+    readout_init(B.out[r0], e0); readout_init(B.out[r1], e0);
+    if (e0) return;
     const int stride = ws.reg_cap + opt.max_matesw;
     RegList rl[2];
     for (int i = 0; i < 2; ++i) {
         int r = r0 | i, n = B.n_regs[r];
         rl[i].a = wregs + (size_t)i * stride; rl[i].cap = ws.reg_cap; rl[i].n = n;
-        if (n > ws.reg_cap) { ro[0]->err = ro[1]->err = ERR_SCRATCH_OVERFLOW; return; }
+        if (n > ws.reg_cap) { B.out[r0].err = B.out[r1].err = ERR_SCRATCH_OVERFLOW; return; }
         const AlnReg *src = B.regs + B.seed_off[r];
         for (int j = 0; j < n; ++j) rl[i].a[j] = src[j];
     }
     int err = 0;
-    finalize_pair(opt, ix, B.mt, B.pes, (uint64_t)((B.n_processed >> 1) + p),
-                  (int)(B.seq_off[r0 + 1] - B.seq_off[r0]), B.seq + B.seq_off[r0], B.oseq + B.seq_off[r0], rl[0],
-                  (int)(B.seq_off[r1 + 1] - B.seq_off[r1]), B.seq + B.seq_off[r1], B.oseq + B.seq_off[r1], rl[1],
-                  ws, B.arena, *ro[0], *ro[1], &err);
-    ro[0]->err = ro[1]->err = err;
+    finalize_pair(opt, ix, B.mt, B.pes, (uint64_t)((B.n_processed >> 1) + p), r0,
+                  (int)(B.seq_off[r0 + 1] - B.seq_off[r0]), B.seq + B.seq_off[r0], rl[0],
+                  (int)(B.seq_off[r1 + 1] - B.seq_off[r1]), B.seq + B.seq_off[r1], rl[1],
+                  ws, B.arena, B.tasks, B.out, &err);
+    if (err) B.out[r0].err = B.out[r1].err = err;
+}
+
+// K6 + K8b (scalar form): one queued alignment -> CIGAR, NM, MD/XB, position, written to its record(s)
+BSB_HD void stage_task(const Opt &opt, const IndexView &ix, BatchDev &B, unsigned int k, FinalWS &ws)
+{
+    const AlnTask t = B.tasks.a[k];
+    const int r = t.read;
+    const int l = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+    AlnBody b;
+    int err = 0;
+    if (align_body(opt, ix, t, l, B.seq + B.seq_off[r], B.oseq + B.seq_off[r], ws, b, &err))
+        task_store(ix, t, b, ws.cigar, ws.md, B.arena, B.out, &err);
+    if (err) B.out[r].err = err;
 }
 
 } // namespace bsb

@@ -105,6 +105,19 @@ struct ReadOut {        // per bseq entry
     int32_t pad_;
 };
 
+// Deferred alignment work: the finalisation kernel decides WHICH regions become records (flags, MAPQ,
+// pairing); the CIGAR / NM / MD / XB of each chosen region is then produced by a separate, warp-cooperative
+// kernel from this task list.
+struct AlnTask {
+    int64_t rb, re;      // reference span (doubled coordinates)
+    int32_t qb, qe;      // query span
+    int32_t truesc, w;   // local score of the region and the band it was found with (band inference)
+    int32_t read;        // bseq entry (query bases)
+    int32_t kind;        // 0: complete an AlnOut, 1: complete an XaOut
+    uint32_t target_off; // arena offset of that record
+    int32_t mate_read;   // >= 0: this alignment is also the "mate" record of that entry (h[] in mem_sam_pe)
+};
+
 // contig table entry (bntann1_t subset, bntseq.h:40-48)
 struct Ann {
     int64_t offset;

@@ -296,4 +296,186 @@ __device__ void stage_extend_warp(const Opt &opt, const IndexView &ix, const Bat
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6: banded global alignment + traceback, one warp per queued alignment (AlnTask).
+//
+// nw_global_warp() is ksw_global2 (ksw.c:504-606) row by row with the columns across the lanes: M and E
+// come from the previous row, F(i,j) = max( -inf - (j-beg)*e_ins, max_{j'<j} (M(j') - oe_ins - (j-1-j')*e_ins) )
+// is an exclusive max-scan, and each lane derives its own three direction bits with the reference's tie
+// rules (m >= e, h >= f, e > t, f > t). The direction matrix goes to HBM (coalesced rows), the backtrack
+// walks it on lane 0.
+// ---------------------------------------------------------------------------------------------
+struct WarpTask {          // per-warp shared memory of the task kernel
+    int32_t *H, *E;        // max_q + 1 each
+    uint8_t *qs;           // max_q
+    uint32_t *cigar; int cigar_cap;
+    char *md; int md_cap;
+    char *xb; int xb_cap;
+};
+
+template <class Q, class T>
+__device__ int nw_global_warp(int qlen, const Q &query, int tlen, const T &target, const int8_t *mat,
+                              int o_del, int e_del, int o_ins, int e_ins, int w, const WarpTask &S, uint8_t *z, CigarBuf *cig, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    int32_t *H = S.H, *E = S.E;
+    uint8_t *qs = S.qs;
+    for (int j = lane; j <= qlen; j += 32) {
+        int h;
+        if (j == 0) h = 0;
+        else if (j <= w) h = -(o_ins + e_ins * j);
+        else h = BSB_MINUS_INF;
+        H[j] = h; E[j] = BSB_MINUS_INF;
+        if (j < qlen) qs[j] = (uint8_t)query(j);
+    }
+    __syncwarp();
+    for (int i = 0; i < tlen; ++i) {
+        const int8_t *row = mat + target(i) * 5;
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        int carry_h = beg == 0 ? -(o_del + e_del * (i + 1)) : BSB_MINUS_INF;
+        int carry_g = BSB_MINUS_INF + (beg - 1) * e_ins;   // the "-inf" F entering column beg, in scan coordinates
+        uint8_t *zi = z + (long)i * n_col;
+        for (int c0 = beg; c0 < end; c0 += 32) {
+            const int j = c0 + lane;
+            const bool act = j < end;
+            int m = 0, e = 0;
+            if (act) { m = H[j] + row[qs[j]]; e = E[j]; }
+            int g = act ? m - oe_ins + j * e_ins : BSB_MINUS_INF * 2 + 1;
+            int incl = g;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(FULLMASK, incl, d);
+                if (lane >= d) incl = incl > v ? incl : v;
+            }
+            int excl = __shfl_up_sync(FULLMASK, incl, 1);
+            if (lane == 0) excl = carry_g;
+            else excl = excl > carry_g ? excl : carry_g;
+            const int f = excl - (j - 1) * e_ins;
+            uint8_t d = m >= e ? 0 : 1;
+            int h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            int t = m - oe_del;
+            int e2 = e - e_del;
+            d |= e2 > t ? 1 << 2 : 0;
+            e2 = e2 > t ? e2 : t;
+            t = m - oe_ins;
+            const int f2 = f - e_ins;
+            d |= f2 > t ? 2 << 4 : 0;
+            int hprev = __shfl_up_sync(FULLMASK, h, 1);
+            if (lane == 0) hprev = carry_h;
+            if (act) { H[j] = hprev; E[j] = e2; zi[j - beg] = d; }
+            const int n_act = end - c0 < 32 ? end - c0 : 32;
+            const int chunk_max = __shfl_sync(FULLMASK, incl, n_act - 1);
+            carry_g = carry_g > chunk_max ? carry_g : chunk_max;
+            carry_h = __shfl_sync(FULLMASK, h, n_act - 1);
+        }
+        if (lane == 0) { H[end] = carry_h; E[end] = BSB_MINUS_INF; }
+        __syncwarp();
+    }
+    const int score = H[qlen];
+    int n_cig = 0, bad = 0;
+    if (lane == 0) {
+        cig->n = 0;
+        int which = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+        bool ok = true;
+        while (i >= 0 && k >= 0) {
+            which = z[(long)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+            if (which == 0) { ok &= cig->push(0, 1); --i; --k; }
+            else if (which == 1) { ok &= cig->push(2, 1); --i; }
+            else { ok &= cig->push(1, 1); --k; }
+        }
+        if (i >= 0) ok &= cig->push(2, i + 1);
+        if (k >= 0) ok &= cig->push(1, k + 1);
+        for (i = 0; i < cig->n >> 1; ++i) tswap(cig->a[i], cig->a[cig->n - 1 - i]);
+        n_cig = cig->n; bad = ok ? 0 : 1;
+    }
+    n_cig = __shfl_sync(FULLMASK, n_cig, 0);
+    bad = __shfl_sync(FULLMASK, bad, 0);
+    cig->n = n_cig;
+    if (bad) *err = ERR_CIGAR_OVERFLOW;
+    __syncwarp();
+    return score;
+}
+
+// bwa_gen_cigar2 part 1 (bwa.c:199-249), warp form; all lanes pass identical arguments
+__device__ bool global_core_warp(const Opt &opt, const IndexView &ix, int w_, int l_query, const uint8_t *query,
+                                 int64_t rb, int64_t re, int *score, CigarBuf *cig, const WarpTask &S, uint8_t *z, long z_cap, int max_q, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t l_pac = ix.l_pac;
+    cig->n = 0;
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;
+    if (re > (l_pac << 1) || rb < 0) return false;
+    const int64_t rlen = re - rb;
+    QrySeq q; RefSeq t;
+    if (rb >= l_pac) {
+        q.base = query + (l_query - 1); q.dir = -1;
+        t.pac = ix.pac; t.l_pac = l_pac; t.start = re - 1; t.dir = -1;
+    } else {
+        q.base = query; q.dir = 1;
+        t.pac = ix.pac; t.l_pac = l_pac; t.start = rb; t.dir = 1;
+    }
+    if (l_query == rlen && w_ == 0) {
+        if (lane == 0) { cig->a[0] = (uint32_t)l_query << 4; }
+        cig->n = 1;
+        int sc = 0;
+        for (int i = lane; i < l_query; i += 32) sc += opt.mat[t(i) * 5 + q(i)];
+        for (int o = 16; o; o >>= 1) sc += __shfl_xor_sync(FULLMASK, sc, o);
+        *score = sc;
+        __syncwarp();
+    } else {
+        int w, max_gap, max_ins, max_del, min_w;
+        max_ins = (int)((double)(((l_query + 1) >> 1) * opt.mat[0] - opt.o_ins) / opt.e_ins + 1.);
+        max_del = (int)((double)(((l_query + 1) >> 1) * opt.mat[0] - opt.o_del) / opt.e_del + 1.);
+        max_gap = max_ins > max_del ? max_ins : max_del;
+        max_gap = max_gap > 1 ? max_gap : 1;
+        w = (max_gap + iabs((int)rlen - l_query) + 1) >> 1;
+        w = w < w_ ? w : w_;
+        min_w = iabs((int)rlen - l_query) + 3;
+        w = w > min_w ? w : min_w;
+        if (l_query > max_q) { *err = ERR_SCRATCH_OVERFLOW; return false; }
+        long n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
+        if (n_col * rlen > z_cap) { *err = ERR_SCRATCH_OVERFLOW; return false; }
+        *score = nw_global_warp(l_query, q, (int)rlen, t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, S, z, cig, err);
+    }
+    return true;
+}
+
+// One queued alignment on one warp: CIGAR by the lanes together, bisulfite MD/XB + record write by lane 0
+__device__ void stage_task_warp(const Opt &opt, const IndexView &ix, BatchDev &B, unsigned int k, const WarpTask &S, uint8_t *z, long z_cap, int max_q)
+{
+    const int lane = threadIdx.x & 31;
+    const AlnTask t = B.tasks.a[k];
+    const int r = t.read;
+    const int l = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+    const uint8_t *query = B.seq + B.seq_off[r], *oquery = B.oseq + B.seq_off[r];
+    int err = 0;
+    int w2 = band_for_task(opt, t), score = 0, last_sc = -(1 << 30), i = 0;
+    CigarBuf cig = {S.cigar, 0, S.cigar_cap - 2};
+    bool ok;
+    do {
+        w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+        ok = global_core_warp(opt, ix, w2, t.qe - t.qb, query + t.qb, t.rb, t.re, &score, &cig, S, z, z_cap, max_q, &err);
+        if (!ok) break;
+        if (score == last_sc || w2 == opt.w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++i < 3 && score < t.truesc - opt.a);
+    if (lane == 0) {
+        if (!ok) { if (!err) err = ERR_NO_MD; }
+        else {
+            AlnBody b;
+            StrBuf md = {S.md, 0, S.md_cap, false}, xb = {S.xb, 0, S.xb_cap, false};
+            aln_finish(ix, t, l, oquery, S.cigar, cig.n, md, xb, b, &err);
+            task_store(ix, t, b, S.cigar, S.md, B.arena, B.out, &err);
+        }
+        if (err) B.out[r].err = err;
+    }
+    __syncwarp();
+}
+
 } // namespace bsb

@@ -43,6 +43,7 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     s->n_seeds = (int64_t)sum.n_seeds; s->h2d_bytes = (int64_t)sum.h2d_bytes; s->d2h_bytes = (int64_t)sum.d2h_bytes;
     s->kernel_launches = al ? al->kernel_launches() : 0;
     s->sec_read = sum.sec_read; s->sec_format = sum.sec_format; s->sec_write = sum.sec_write;
+    s->ms_select = sum.ms_select; s->ms_tasks = sum.ms_tasks; s->n_tasks = (int64_t)sum.n_tasks;
 }
 
 extern "C" {

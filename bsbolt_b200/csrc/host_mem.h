@@ -45,6 +45,7 @@ struct BatchResult {
     // ms_stage: 0 H2D, 1 convert, 2 seed, 3 scan+SA lookup, 4 chain, 5 extend, 6 pair stats, 7 finalise
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
+    double ms_select = 0, ms_tasks = 0; uint64_t n_tasks = 0;   // split of stage 7: record selection / alignment tasks
 };
 
 class BatchAligner {
@@ -82,9 +83,11 @@ struct RunSummary {
     MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0;
     double sec_read = 0, sec_format = 0, sec_write = 0; // busy time of the reader / formatter / output stages
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
+    uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0, n_tasks = 0;
+    double ms_select = 0, ms_tasks = 0;
     void add_timing(const BatchResult &r)
     {
+        ms_select += r.ms_select; ms_tasks += r.ms_tasks; n_tasks += r.n_tasks;
         ms_h2d += r.ms_h2d; ms_kernels += r.ms_kernels; ms_d2h += r.ms_d2h;
         for (int k = 0; k < 8; ++k) ms_stage[k] += r.ms_stage[k];
         n_seeds += r.n_seeds; h2d_bytes += r.h2d_bytes; d2h_bytes += r.d2h_bytes;

@@ -32,6 +32,8 @@ typedef struct {
     double ms_h2d, ms_kernels, ms_d2h, ms_stage[8];
     int64_t n_seeds, h2d_bytes, d2h_bytes, kernel_launches;
     double sec_read, sec_format, sec_write; /* busy time of the host stages: FASTQ batching, SAM text, output */
+    double ms_select, ms_tasks;             /* stage 7 split: record selection/pairing kernel, alignment-task kernel */
+    int64_t n_tasks;                        /* global alignments queued (records + XA entries) */
 } bsb_run_stats_t;
 
 typedef struct {

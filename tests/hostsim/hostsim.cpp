@@ -115,16 +115,23 @@ public:
         // outputs
         out.reads.assign(n, ReadOut());
         size_t arena_cap = (size_t)n * 1024 + (1 << 20);
+        size_t task_cap = (size_t)n * 2 + 1024;
+        std::vector<AlnTask> tasks;
         for (;;) {
             out.arena.assign(arena_cap, 0);
+            tasks.assign(task_cap, AlnTask());
             unsigned long long used = 8; // offset 0 is reserved as "null"
+            unsigned int n_tasks = 0;
             B.out = out.reads.data();
             B.arena.base = out.arena.data(); B.arena.used = &used; B.arena.cap = arena_cap;
+            B.tasks.a = tasks.data(); B.tasks.n = &n_tasks; B.tasks.cap = (unsigned int)task_cap;
             if (pe) for (int p = 0; p < n / 2; ++p) stage_final_pe(opt, ix_, B, p, ws, wregs.data());
             else for (int r = 0; r < n; ++r) stage_final_se(opt, ix_, B, r, ws, wregs.data());
-            bool ovf = false;
+            if (n_tasks <= task_cap) for (unsigned int k = 0; k < n_tasks; ++k) stage_task(opt, ix_, B, k, ws);
+            bool ovf = n_tasks > task_cap || used > arena_cap;
             for (int r = 0; r < n; ++r) if (out.reads[r].err == ERR_ARENA_OVERFLOW) ovf = true;
             if (!ovf) { out.arena.resize(used); break; }
+            if (n_tasks > task_cap) task_cap = (size_t)n_tasks + 1024;
             arena_cap *= 2;
         }
         for (int r = 0; r < n; ++r)
