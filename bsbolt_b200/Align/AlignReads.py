@@ -59,6 +59,10 @@ class BisulfiteAlignmentAndProcessing:
         if not argv or argv[0] != 'mem':
             raise BisulfiteAlignmentError('alignment_commands must be [bwa, "mem", ...]')
         sys.stdout.flush()
+        if isinstance(self.device, (list, tuple)) and len(self.device) > 1:
+            return self._align_multi_gpu(argv)
+        if isinstance(self.device, (list, tuple)):
+            self.device = self.device[0]
         with tempfile.TemporaryFile(mode='w+') as log:
             if self.output_to_stdout:
                 rc, stats = _native.mem_main(argv, index=self.index, device=self.device, out_fd=1, log_fd=log.fileno())
@@ -78,3 +82,39 @@ class BisulfiteAlignmentAndProcessing:
         if rc:
             print(rc, file=sys.stderr)
             raise BisulfiteAlignmentError(_native.last_error())
+
+    def _consume_log(self, lines):
+        for alignment_info in lines:
+            if alignment_info[0:7] == 'BSStat ':
+                category, count = alignment_info.replace('BSStat ', '').split(': ')
+                self.mapping_statistics[category] += int(count)
+                print(alignment_info.replace('BSStat ', '').strip(), file=sys.stderr)
+            else:
+                print(alignment_info.strip(), file=sys.stderr)
+
+    def _align_multi_gpu(self, argv):
+        """One worker process per GPU; batch b is aligned on GPU b mod G; parts merged in input order."""
+        import subprocess
+        from bsbolt_b200.shard import merge_shards
+        devices = list(self.device)
+        with tempfile.TemporaryDirectory() as d:
+            procs = []
+            for i, dev in enumerate(devices):
+                cmd = [sys.executable, '-m', 'bsbolt_b200._shard_worker', str(dev), str(i), str(len(devices)),
+                       f'{d}/p{i}.sam', f'{d}/p{i}.idx', f'{d}/p{i}.log', '--'] + argv
+                procs.append(subprocess.Popen(cmd))
+            rcs = [p.wait() for p in procs]
+            for i in range(len(devices)):
+                self._consume_log(open(f'{d}/p{i}.log'))
+            if any(rcs):
+                raise BisulfiteAlignmentError(f'shard worker failed: {rcs}')
+            sams, parts = [f'{d}/p{i}.sam' for i in range(len(devices))], [f'{d}/p{i}.idx' for i in range(len(devices))]
+            if self.output_to_stdout:
+                merge_shards(sams, parts, sys.stdout.buffer)
+                sys.stdout.buffer.flush()
+            else:
+                from bsbolt_b200.Utils.BamOutput import sam_to_bam
+                with open(f'{d}/merged.sam', 'wb') as o:
+                    merge_shards(sams, parts, o)
+                with open(f'{d}/merged.sam') as f:
+                    sam_to_bam(f, f'{self.output}.bam', self.output_threads)

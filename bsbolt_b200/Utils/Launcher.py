@@ -90,7 +90,7 @@ def launch_alignment(arguments):
     bwa_cmd = build_alignment_command(arguments)
     if arguments.O is None and not arguments.OS:
         raise FileNotFoundError("-O and -OS arguments empty, please specify output path")
-    return align_bisulfite(bwa_cmd, arguments.O, arguments.OT, arguments.OS, device=getattr(arguments, 'GPU', 0))
+    return align_bisulfite(bwa_cmd, arguments.O, arguments.OT, arguments.OS, device=getattr(arguments, 'GPU', [0]))
 
 
 bsb_launch = {'Align': launch_alignment}

@@ -57,7 +57,8 @@ ALIGN_FLAGS = [
 # extensions of this build (not in the reference parser)
 EXTRA_FLAGS = [
     ('-K', dict(type=int, default=None, help='process INT input bases in each batch regardless of -t (bwa mem -K; reproducible batches)')),
-    ('-GPU', dict(type=int, default=0, help='CUDA device to align on [0]')),
+    ('-GPU', dict(type=lambda x: [int(v) for v in str(x).split(',')], default=[0],
+                  help='CUDA device(s) to align on, comma separated; with several devices batch b runs on device b mod G [0]')),
 ]
 
 parser = argparse.ArgumentParser(description='bsbolt_b200: GPU drop-in for the bsbolt Align module',

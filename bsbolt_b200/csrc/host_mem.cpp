@@ -260,6 +260,10 @@ int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err)
         }
     }
     if (opt.flag & F_SMARTPE) { err = "[E::main_mem] smart pairing (-p) is not supported by the B200 aligner"; return 1; }
+    if (const char *e = getenv("BSB_SHARD_COUNT")) ma.shard_count = atoi(e) > 1 ? atoi(e) : 1;
+    if (const char *e = getenv("BSB_SHARD_INDEX")) ma.shard_index = atoi(e);
+    if (const char *e = getenv("BSB_SHARD_PARTS")) ma.shard_parts = e;
+    if (ma.shard_index < 0 || ma.shard_index >= ma.shard_count) { err = "[E::main_mem] BSB_SHARD_INDEX out of range"; return 1; }
     return 0;
 }
 
@@ -745,6 +749,7 @@ struct Job {
     ReadBatch batch;
     BatchResult res;
     int64_t n_processed = 0;
+    long batch_id = 0;
     double sec_align = 0;
 };
 } // namespace
@@ -759,7 +764,15 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     std::unique_ptr<FastxReader> r2;
     if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2));
     std::string hdr = sam_header(idx, ma);
-    fwrite(hdr.data(), 1, hdr.size(), out);
+    const int shard_count = ma.shard_count > 1 ? ma.shard_count : 1, shard_index = ma.shard_index;
+    size_t out_bytes = 0;
+    if (shard_index == 0) { fwrite(hdr.data(), 1, hdr.size(), out); out_bytes += hdr.size(); }
+    FILE *parts = nullptr;
+    if (shard_count > 1 && !ma.shard_parts.empty()) {
+        parts = fopen(ma.shard_parts.c_str(), "w");
+        if (!parts) throw std::runtime_error("[E::run_mem] cannot write " + ma.shard_parts);
+        if (shard_index == 0) fprintf(parts, "-1\t0\t%zu\n", hdr.size());
+    }
     RunSummary sum;
     int host_threads = (int)std::thread::hardware_concurrency();
     if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
@@ -776,6 +789,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     std::thread t_read([&] {
         try {
             int64_t n_processed = 0;
+            long batch_id = 0;
             for (;;) {
                 std::unique_ptr<Job> j;
                 if (!q_free.pop(j)) break;
@@ -784,7 +798,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", j->batch.n, (long)j->batch.n_bases); }
                 sec_read += now_sec() - tr;
                 j->n_processed = n_processed;
+                j->batch_id = batch_id++;
                 n_processed += j->batch.n;
+                if (j->batch_id % shard_count != shard_index) { q_free.push(std::move(j)); continue; } // another GPU's batch
                 q_read.push(std::move(j));
                 { std::lock_guard<std::mutex> l(fail_m); if (!fail.empty()) break; }
             }
@@ -826,6 +842,8 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 sam_sort_batch(batch, sam, st, text, ms);
                 double tw = now_sec();
                 fwrite(text.data(), 1, text.size(), out);
+                if (parts) fprintf(parts, "%ld\t%zu\t%zu\n", j->batch_id, out_bytes, text.size());
+                out_bytes += text.size();
                 sum.sec_format += tw - tf; sum.sec_write += now_sec() - tw;
                 {
                     std::lock_guard<std::mutex> l(log_m);
@@ -849,6 +867,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     t_gpu.join();
     t_read.join();
     fflush(out);
+    if (parts) fclose(parts);
     sum.sec_read = sec_read;
     sum.sec_total = now_sec() - t0;
     if (summary) *summary = sum;

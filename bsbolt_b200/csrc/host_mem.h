@@ -29,6 +29,10 @@ struct MemArgs {
     PeStat pes0[4];
     std::string idxbase, fq1, fq2, out_path;
     std::string pg_line;         // "@PG\tID:bwa\tPN:bwa\tVN:...\tCL:..."
+    // multi-GPU: this process aligns batches b with b % shard_count == shard_index; every shard
+    // scans the whole input so that batch boundaries and n_processed are those of a single run
+    int shard_index = 0, shard_count = 1;
+    std::string shard_parts;     // sidecar listing (batch id, byte offset, length) of this shard's SAM output
     int64_t actual_chunk_size() const { return fixed_chunk_size > 0 ? fixed_chunk_size : (int64_t)opt.chunk_size * opt.n_threads; }
 };
 

@@ -171,3 +171,42 @@ def test_index_build_byte_identical(built, golden, tmp_path):
         got = hashlib.md5(open(f'{ref}.{ext}', 'rb').read()).hexdigest()
         assert got == golden.manifest['md5'][f'db/BSB_ref.fa.{ext}'], f'.{ext} differs from the reference index'
     assert ms > 0
+
+
+def test_cli_drop_in_single_and_two_shards(built, golden, tmp_path):
+    """`python -m bsbolt_b200 Align ... -OS` (the reference's CLI surface) on one device and as two batch shards
+    (-GPU 0,0: two worker processes on the same device) -- both must print the reference's SAM."""
+    import sys
+    db = os.path.dirname(golden.idxbase)
+    c = golden.cases['pe150']
+    fq = [os.path.join(golden.dir, f) for f in c['fq']]
+    want = golden.sam('pe150')
+    for gpu in ('0', '0,0'):
+        cmd = [sys.executable, '-m', 'bsbolt_b200', 'Align', '-F1', fq[0], '-F2', fq[1], '-DB', db, '-OS', '-K', '200000', '-GPU', gpu]
+        p = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert strip_pg(p.stdout) == want, first_diff(want, strip_pg(p.stdout))
+        assert 'Total Reads: 1954' in p.stderr
+
+
+def test_bam_output(built, golden, tmp_path):
+    """-O writes <prefix>.bam: BGZF container, BAM magic, every SAM record present."""
+    import gzip
+    import struct
+    import sys
+    db = os.path.dirname(golden.idxbase)
+    c = golden.cases['se100']
+    cmd = [sys.executable, '-m', 'bsbolt_b200', 'Align', '-F1', os.path.join(golden.dir, c['fq'][0]), '-DB', db, '-O', str(tmp_path / 'out'), '-K', '100000']
+    p = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    raw = gzip.open(tmp_path / 'out.bam', 'rb').read()   # BGZF is a series of gzip members
+    assert raw[:4] == b'BAM\x01'
+    l_text, = struct.unpack('<i', raw[4:8])
+    off = 8 + l_text
+    n_ref, = struct.unpack('<i', raw[off:off + 4]); off += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack('<i', raw[off:off + 4]); off += 4 + l_name + 4
+    n = 0
+    while off < len(raw):
+        bs, = struct.unpack('<i', raw[off:off + 4]); off += 4 + bs; n += 1
+    assert n_ref == 6 and n == c['n_records']

@@ -1,0 +1,88 @@
+"""Host-side mirror of the reference interface: CLI flags, argv construction, exceptions, BAM encoder,
+shard merge. No GPU."""
+import gzip
+import io
+import os
+import struct
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+REF = '/root/reference'
+
+
+def test_align_flags_match_reference_parser():
+    from bsbolt_b200.Utils.Parser import ALIGN_FLAGS, parser
+    flags = [f for f, _ in ALIGN_FLAGS]
+    expected = ['-F1', '-F2', '-UN', '-O', '-OS', '-DB', '-CP', '-CT', '-SP', '-t', '-k', '-w', '-d', '-r', '-y', '-c', '-D', '-W', '-m',
+                '-S', '-P', '-A', '-B', '-INDEL', '-E', '-L', '-U', '-p', '-R', '-H', '-j', '-T', '-XA', '-DR', '-M', '-I', '-OT']
+    assert flags == expected
+    if os.path.exists(os.path.join(REF, 'bsbolt', 'Utils', 'Parser.py')):
+        src = open(os.path.join(REF, 'bsbolt', 'Utils', 'Parser.py')).read()
+        import re
+        ref_flags = re.findall(r"align_parser\.add_argument\('(-\w+)'", src)
+        assert ref_flags == expected
+    a = parser.parse_args(['Align', '-F1', 'a.fq', '-DB', 'db', '-OS'])
+    assert (a.t, a.k, a.T, a.L, a.XA, a.DR, a.INDEL, a.U) == (1, 19, 10, '30,30', '100,200', 0.95, '6,6', 17)
+
+
+def test_argv_equals_reference_launcher(tmp_path):
+    """build_alignment_command() produces the argv the reference's launch_alignment() would exec."""
+    from bsbolt_b200.Utils.Launcher import build_alignment_command
+    from bsbolt_b200.Utils.Parser import parser
+    db = tmp_path / 'db'
+    db.mkdir()
+    (db / 'BSB_ref.fa').write_text('>x\nA\n'); (db / 'BSB_ref.fa.opac').write_text('')
+    (tmp_path / 'r1.fq').write_text(''); (tmp_path / 'r2.fq').write_text('')
+    a = parser.parse_args(['Align', '-F1', str(tmp_path / 'r1.fq'), '-F2', str(tmp_path / 'r2.fq'), '-DB', str(db), '-OS', '-UN', '-t', '4', '-M'])
+    cmd = build_alignment_command(a)
+    assert cmd[1:] == ['mem', '-Y', '-z', '-M', '-A', '1', '-B', '4', '-D', '0.5', '-E', '1,1', '-L', '30,30', '-T', '10', '-U', '17', '-W', '0',
+                       '-c', '500', '-d', '100', '-k', '19', '-m', '50', '-r', '1.5', '-t', '4', '-w', '100', '-y', '20', '-O', '6,6',
+                       '-h', '100,200', '-e', '0.1', '-l', '0.5', '-n', '5', '-Z', '0.95', f'{db}/BSB_ref.fa', str(tmp_path / 'r1.fq'), str(tmp_path / 'r2.fq')]
+
+
+def test_api_surface():
+    from bsbolt_b200.Align.AlignReads import (AlignmentCompressionError, BisulfiteAlignmentAndProcessing,
+                                              BisulfiteAlignmentError)
+    b = BisulfiteAlignmentAndProcessing(['bwa', 'mem', 'x'], output='o', output_threads=2, output_to_stdout=True)
+    assert sorted(b.mapping_statistics) == sorted(['TotalReads', 'TotalAlignments', 'BSAmbiguous', 'C_C2T', 'C_G2A', 'W_C2T', 'W_G2A', 'Unaligned'])
+    assert issubclass(BisulfiteAlignmentError, Exception) and issubclass(AlignmentCompressionError, Exception)
+    with pytest.raises(BisulfiteAlignmentError):
+        BisulfiteAlignmentAndProcessing(['bwa', 'index'], output_to_stdout=True).align_reads()
+
+
+def test_bam_encoder_round_trip(golden, tmp_path):
+    from bsbolt_b200.Utils.BamOutput import sam_to_bam
+    sam = golden.sam('pe150')
+    out = tmp_path / 'x.bam'
+    sam_to_bam(io.StringIO(sam), str(out), threads=2)
+    raw = gzip.open(out, 'rb').read()
+    assert raw[:4] == b'BAM\x01'
+    l_text, = struct.unpack('<i', raw[4:8])
+    assert raw[8:8 + l_text].decode() == ''.join(l + '\n' for l in sam.split('\n') if l.startswith('@'))
+    off = 8 + l_text
+    n_ref, = struct.unpack('<i', raw[off:off + 4]); off += 4
+    names = []
+    for _ in range(n_ref):
+        l_name, = struct.unpack('<i', raw[off:off + 4]); off += 4
+        names.append(raw[off:off + l_name - 1].decode()); off += l_name + 4
+    recs = [l.split('\t') for l in sam.split('\n') if l and not l.startswith('@')]
+    for r in recs:
+        bs, = struct.unpack('<i', raw[off:off + 4])
+        rid, pos, l_rn, mapq, _bin, n_cig, flag, l_seq, nrid, npos, tlen = struct.unpack('<iiBBHHHIiii', raw[off + 4:off + 36])
+        assert (names[rid] if rid >= 0 else '*') == r[2] and pos + 1 == int(r[3]) and mapq == int(r[4]) and flag == int(r[1])
+        assert raw[off + 36:off + 36 + l_rn - 1].decode() == r[0] and tlen == int(r[8]) and l_seq == (0 if r[9] == '*' else len(r[9]))
+        off += 4 + bs
+    assert off == len(raw)
+    assert open(out, 'rb').read()[-28:] == bytes.fromhex('1f8b08040000000000ff0600424302001b0003000000000000000000')
+
+
+def test_merge_shards(tmp_path):
+    from bsbolt_b200.shard import merge_shards
+    (tmp_path / 'a.sam').write_bytes(b'HDR\nb0\nb2\n'); (tmp_path / 'a.idx').write_text('-1\t0\t4\n0\t4\t3\n2\t7\t3\n')
+    (tmp_path / 'b.sam').write_bytes(b'b1\nb3\n'); (tmp_path / 'b.idx').write_text('1\t0\t3\n3\t3\t3\n')
+    out = io.BytesIO()
+    assert merge_shards([str(tmp_path / 'a.sam'), str(tmp_path / 'b.sam')], [str(tmp_path / 'a.idx'), str(tmp_path / 'b.idx')], out) == 5
+    assert out.getvalue() == b'HDR\nb0\nb1\nb2\nb3\n'
