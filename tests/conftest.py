@@ -31,6 +31,15 @@ def golden(tmp_path_factory):
     for f in os.listdir(GOLDEN):
         if f.endswith('.fq.gz') or f == 'genome.fa.gz':
             _gunzip(os.path.join(GOLDEN, f), d / f[:-3])
+    # the database directory of `bsbolt Index` also holds the FASTA it indexed (one line per contig)
+    with open(d / 'genome.fa') as f, open(d / 'db' / 'BSB_ref.fa', 'w') as o:
+        first = True
+        for line in f:
+            if line.startswith('>'):
+                o.write(('' if first else '\n') + line.split()[0] + '\n'); first = False
+            else:
+                o.write(line.strip())
+        o.write('\n')
     man = json.load(open(os.path.join(GOLDEN, 'golden.json')))
 
     class G:
