@@ -82,6 +82,43 @@ __global__ void __launch_bounds__(64) k_seed_sm(Opt opt, IndexView ix, BatchDev 
     }
 }
 
+// K2, dynamic form: every lane runs the seeding state machine of one read and, the moment that read is done,
+// pulls the next read from a global counter -- the warp never waits for its slowest read (the static form had
+// 9 of 32 lanes at the extension site on average, profiles/r01_ncu_seed_sm.md)
+__global__ void __launch_bounds__(64, 16) k_seed_dyn(Opt opt, IndexView ix, BatchDev B, Intv *scratch, int *next_read)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    Intv *base = scratch + (size_t)w * 3 * B.intv_cap;
+    SeedMachine sm;
+    sm.sub = SeedMachine::FINISHED; sm.err = 0; sm.mem_n = 0; sm.mem_a = nullptr;
+    int r = -1;
+    bool exhausted = false;
+    for (;;) {
+        bool need = false;
+        while (!need && !exhausted) {
+            if (sm.sub == SeedMachine::FINISHED) {
+                if (r >= 0) { // close the read that just finished
+                    if (!sm.err) introsort((long)sm.mem_n, sm.mem_a, LtIntvInfo());
+                    seed_finish(opt, B, r, sm.mem_a, sm.mem_n, sm.err);
+                }
+                r = atomicAdd(next_read, 1);
+                if (r >= B.n) { exhausted = true; r = -1; break; }
+                const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+                B.n_intv[r] = 0; B.l_rep[r] = 0; B.n_seed[r] = 0;
+                if (len < opt.min_seed_len) { r = -1; continue; }
+                sm.init(opt, len, B.seq + B.seq_off[r], B.intv + (size_t)r * B.intv_cap, base, base + B.intv_cap, base + 2 * (size_t)B.intv_cap, B.intv_cap);
+            }
+            need = sm.advance(ix);
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, need)) break;
+        if (need) {
+            const Intv o = fm_extend_sel(ix, sm.req, sm.req_c, sm.req_back);
+            sm.consume(o);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
 {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,7 +376,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemsetAsync(m.d_n_seed.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
         if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
-        else k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
+        else if (getenv("BSB_SEED_V2")) k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
+        else k_seed_dyn<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p, m.d_misc.p + 8);
         ++m.launches;
         CK(cudaGetLastError());
         k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p); ++m.launches;

@@ -61,26 +61,36 @@ BSB_HD void load_block(const uint32_t *bwt, uint64_t blk, OccBlock &b)
 #endif
 }
 
+BSB_HD int popc64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
 // counts of A,C,G,T in BWT[block_start .. block_start + r] (r in [0,127]), added to the block's
-// cumulative counts. Restates bwt_occ4 (bwt.c:169-186) with popcounts instead of the byte table.
+// cumulative counts. Restates bwt_occ4 (bwt.c:169-186) with popcounts instead of the byte table:
+// two packed words at a time, C/G/T by popcount, A as the remainder.
 BSB_HD void block_occ4(const OccBlock &b, int r, uint64_t cnt[4])
 {
-    int nfull = r >> 4;
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const int nsym = r + 1;                 // symbols to count
+    uint32_t c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i <= nfull) {
-            uint32_t keep = 0x55555555u;
-            if (i == nfull) keep &= ~((1u << ((~r & 15) << 1)) - 1u);
-            uint32_t w = b.w[i];
-            uint32_t hi = (w >> 1) & 0x55555555u, lo = w & 0x55555555u;
-            c0 += popc32(~hi & ~lo & keep);
-            c1 += popc32(~hi & lo & keep);
-            c2 += popc32(hi & ~lo & keep);
-            c3 += popc32(hi & lo & keep);
-        }
+    for (int i = 0; i < 4; ++i) {
+        // symbols 32*i .. 32*i+31: word 2i holds the first 16 (high half of the 64-bit view)
+        uint64_t w = (uint64_t)b.w[2 * i] << 32 | b.w[2 * i + 1];
+        int k = nsym - 32 * i;              // how many of these 32 symbols are wanted
+        k = k < 0 ? 0 : k > 32 ? 32 : k;
+        uint64_t keep = k == 0 ? 0ull : (~0ull << ((32 - k) << 1));
+        keep &= 0x5555555555555555ull;
+        uint64_t hi = (w >> 1), lo = w;
+        c1 += popc64(~hi & lo & keep);
+        c2 += popc64(hi & ~lo & keep);
+        c3 += popc64(hi & lo & keep);
     }
-    cnt[0] = b.cnt[0] + c0; cnt[1] = b.cnt[1] + c1; cnt[2] = b.cnt[2] + c2; cnt[3] = b.cnt[3] + c3;
+    cnt[0] = b.cnt[0] + (uint32_t)nsym - c1 - c2 - c3; cnt[1] = b.cnt[1] + c1; cnt[2] = b.cnt[2] + c2; cnt[3] = b.cnt[3] + c3;
 }
 
 BSB_HD void occ4(const IndexView &ix, uint64_t k, uint64_t cnt[4])
@@ -92,19 +102,19 @@ BSB_HD void occ4(const IndexView &ix, uint64_t k, uint64_t cnt[4])
     block_occ4(b, (int)(k & 127), cnt);
 }
 
-// bwt_2occ4 (bwt.c:189-220): one block load when k and l fall into the same block.
+// bwt_2occ4 (bwt.c:189-220). Branch-free on the device: both blocks are always fetched (the second fetch
+// hits the same line when k and l share a block), so the lanes of a warp never split here.
 BSB_HD void occ4_pair(const IndexView &ix, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4])
 {
-    uint64_t _k = k - (k >= ix.primary), _l = l - (l >= ix.primary);
-    if ((_l >> 7) != (_k >> 7) || k == (uint64_t)-1 || l == (uint64_t)-1) {
-        occ4(ix, k, ck);
-        occ4(ix, l, cl);
-    } else {
-        OccBlock b;
-        load_block(ix.bwt, _k >> 7, b);
-        block_occ4(b, (int)(_k & 127), ck);
-        block_occ4(b, (int)(_l & 127), cl);
-    }
+    const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
+    const uint64_t _k = kz ? 0 : k - (k >= ix.primary), _l = lz ? 0 : l - (l >= ix.primary);
+    OccBlock bk, bl;
+    load_block(ix.bwt, _k >> 7, bk);
+    load_block(ix.bwt, _l >> 7, bl);
+    block_occ4(bk, (int)(_k & 127), ck);
+    block_occ4(bl, (int)(_l & 127), cl);
+    if (kz) ck[0] = ck[1] = ck[2] = ck[3] = 0;
+    if (lz) cl[0] = cl[1] = cl[2] = cl[3] = 0;
 }
 
 // bwt_extend (bwt.c:262-275)

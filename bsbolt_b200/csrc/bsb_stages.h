@@ -75,6 +75,25 @@ BSB_HD void stage_convert_base(const BatchDev &B, int r, uint32_t i)
     B.seq[i] = code == 5 ? 4 : code; // mem_align1_core maps through nst_nt4_table where '-' is 5; any code > 3 is "ambiguous"
 }
 
+// tail of K2 for one read: frac_rep bookkeeping + seed count (bwamem.c:269-283) from the sorted interval list
+BSB_HD void seed_finish(const Opt &opt, const BatchDev &B, int r, const Intv *mem, int n, int err)
+{
+    if (err) { B.err[r] = err; return; }
+    int b = 0, e = 0, l_rep = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+        const Intv &p = mem[i];
+        int sb = (int)(p.info >> 32), se = (int)(uint32_t)p.info;
+        int64_t step = p.x2 > (uint64_t)opt.max_occ ? (int64_t)(p.x2 / opt.max_occ) : 1;
+        int64_t cnt = ((int64_t)p.x2 + step - 1) / step;
+        total += (int)(cnt < opt.max_occ ? cnt : opt.max_occ);
+        if (p.x2 <= (uint64_t)opt.max_occ) continue;
+        if (sb > e) { l_rep += e - b; b = sb; e = se; }
+        else e = e > se ? e : se;
+    }
+    l_rep += e - b;
+    B.n_intv[r] = n; B.l_rep[r] = l_rep; B.n_seed[r] = total;
+}
+
 // K2: SMEM seeding for read r. use_sm selects the converged state-machine form (all lanes of a warp call
 // together, `active` false for lanes without a read); both forms produce the same interval list.
 BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const SeedScratch &sc, bool use_sm = false, bool active = true)
@@ -89,20 +108,7 @@ BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, i
     if (use_sm) collect_intv_sm(opt, ix, len, seq, mem, mem1, t0, t1, &err, work);
     else if (work) collect_intv(opt, ix, len, seq, mem, mem1, t0, t1, &err);
     if (!work) return;
-    if (err) { B.err[r] = err; return; }
-    int b = 0, e = 0, l_rep = 0, total = 0;
-    for (int i = 0; i < mem.n; ++i) { // frac_rep bookkeeping + seed count (bwamem.c:269-283)
-        const Intv &p = mem.a[i];
-        int sb = (int)(p.info >> 32), se = (int)(uint32_t)p.info;
-        int64_t step = p.x2 > (uint64_t)opt.max_occ ? (int64_t)(p.x2 / opt.max_occ) : 1;
-        int64_t cnt = ((int64_t)p.x2 + step - 1) / step;
-        total += (int)(cnt < opt.max_occ ? cnt : opt.max_occ);
-        if (p.x2 <= (uint64_t)opt.max_occ) continue;
-        if (sb > e) { l_rep += e - b; b = sb; e = se; }
-        else e = e > se ? e : se;
-    }
-    l_rep += e - b;
-    B.n_intv[r] = mem.n; B.l_rep[r] = l_rep; B.n_seed[r] = total;
+    seed_finish(opt, B, r, mem.a, mem.n, err);
 }
 
 // K3: one suffix-array lookup. g = global seed slot, r = owning read (seed_off[r] <= g < seed_off[r+1])
