@@ -238,6 +238,28 @@ __global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
 }
 
 // ------------------------------------------------------------------------------------------------
+// page-locked host buffers for everything that crosses PCIe (installed once, at library load)
+// ------------------------------------------------------------------------------------------------
+static void *pinned_alloc(size_t n)
+{
+    // 64-byte header remembers how the block was obtained so that release() matches
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) == cudaSuccess && p) { *(uint64_t *)p = 0x50494e4e45445f5full; return (uint8_t *)p + 64; }
+    cudaGetLastError();
+    p = malloc(n + 64);
+    if (!p) throw std::bad_alloc();
+    *(uint64_t *)p = 0;
+    return (uint8_t *)p + 64;
+}
+static void pinned_release(void *q)
+{
+    uint8_t *p = (uint8_t *)q - 64;
+    if (*(uint64_t *)p == 0x50494e4e45445f5full) cudaFreeHost(p); else free(p);
+}
+struct InstallPinnedHooks { InstallPinnedHooks() { g_host_alloc.alloc = pinned_alloc; g_host_alloc.release = pinned_release; } };
+static InstallPinnedHooks g_install_pinned_hooks;
+
+// ------------------------------------------------------------------------------------------------
 // CudaAligner
 // ------------------------------------------------------------------------------------------------
 struct CudaAligner::Impl {
@@ -401,6 +423,14 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemcpyAsync(&S, m.d_seed_off.p + n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     B.seed_off = m.d_seed_off.p;
+    if (getenv("BSB_DEBUG_STATS")) { // distribution of per-read seed counts (load-balance diagnostics)
+        std::vector<int32_t> ns(n);
+        CK(cudaMemcpy(ns.data(), m.d_n_seed.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        std::sort(ns.begin(), ns.end());
+        long big = 0; for (int v : ns) if (v > 1000) ++big;
+        fprintf(stderr, "[D::seeds] reads %d total %u mean %.1f p50 %d p90 %d p99 %d p99.9 %d max %d; >1000 seeds: %ld reads\n", n, S,
+                (double)S / std::max(n, 1), ns[n / 2], ns[(size_t)n * 9 / 10], ns[(size_t)n * 99 / 100], ns[(size_t)n * 999 / 1000], ns[n - 1], big);
+    }
     m.d_seeds.ensure(S + 1); m.d_cseeds.ensure(S + 1); m.d_next.ensure(S + 1); m.d_tmp.ensure(S + 1);
     m.d_pool.ensure(S + 1); m.d_chains.ensure(S + 1); m.d_srt.ensure(S + 1); m.d_regs.ensure(S + 1);
     m.d_nodes.ensure(S / 4 + 2 * (size_t)n + 4);
@@ -439,6 +469,14 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaStreamSynchronize(st));
     if (h_misc[1]) throw std::runtime_error("[E::bsbolt_b200] chaining/extension failed with error code " + std::to_string(h_misc[1]));
     const int max_regs = h_misc[0];
+    if (getenv("BSB_DEBUG_STATS")) {
+        std::vector<int32_t> nr(n), nc(n);
+        CK(cudaMemcpy(nr.data(), m.d_n_regs.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(nc.data(), m.d_n_chain.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        std::sort(nr.begin(), nr.end()); std::sort(nc.begin(), nc.end());
+        fprintf(stderr, "[D::regs] p50 %d p99 %d p99.9 %d max %d | chains p50 %d p99 %d p99.9 %d max %d\n", nr[n / 2], nr[(size_t)n * 99 / 100],
+                nr[(size_t)n * 999 / 1000], nr[n - 1], nc[n / 2], nc[(size_t)n * 99 / 100], nc[(size_t)n * 999 / 1000], nc[n - 1]);
+    }
 
     // ---- insert-size statistics (host, per batch) ----
     std::vector<double> pair_tab;
@@ -528,7 +566,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
     }
     // ---- D2H ----
-    out.arena.resize((size_t)used);
+    out.arena.resize_uninit((size_t)used);
     CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(m.ev[9], st));
     CK(cudaStreamSynchronize(st));

@@ -559,8 +559,11 @@ static void set_unmapped(const ReadBatch &b, int i, const EntryStats &st, std::s
     sam += "\tAS:i:0\tYS:Z:WC\n";
 }
 
-void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st, std::string &out, MapStats &ms)
+// Decision pass of the arbiter: which entries are printed (in input order), with BS-ambiguous groups rewritten
+// as unmapped. Serial and cheap -- no SAM text is copied here.
+static void sam_sort_plan(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st, std::vector<int> &emit, MapStats &ms)
 {
+    emit.clear();
     if (b.n == 0) return;
     std::vector<int> g[2];
     long score[2] = {0, 0};
@@ -583,7 +586,7 @@ void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vect
         int pick = score[0] > score[1] ? 0 : score[0] < score[1] ? 1 : 2;
         ++ms.reads;
         if (pick == 1) {
-            for (int i : g[1]) { update(i); out += sam[i]; }
+            for (int i : g[1]) { update(i); emit.push_back(i); }
         } else {
             for (int i : g[0]) {
                 if (pick == 2) {
@@ -592,7 +595,7 @@ void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vect
                     st[i].bs_conflict = 1;
                 }
                 update(i);
-                out += sam[i];
+                emit.push_back(i);
             }
         }
         g[0].clear(); g[1].clear(); score[0] = score[1] = 0;
@@ -605,6 +608,13 @@ void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vect
         else { flush(); cur = i; bank(i); }
     }
     flush();
+}
+
+void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st, std::string &out, MapStats &ms)
+{
+    std::vector<int> emit;
+    sam_sort_plan(b, sam, st, emit, ms);
+    for (int i : emit) out += sam[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,7 +640,16 @@ void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::
             r->failed = 1;
             continue;
         } else if (verbose >= 3) fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
-        std::sort(q.begin(), q.end());
+        { // insert sizes are bounded by max_ins: counting sort when the range is small, else a comparison sort
+            uint64_t mx = 0;
+            for (uint64_t v : q) mx = v > mx ? v : mx;
+            if (mx < (1u << 20)) {
+                std::vector<uint32_t> cnt(mx + 1, 0);
+                for (uint64_t v : q) ++cnt[v];
+                size_t k = 0;
+                for (uint64_t v = 0; v <= mx; ++v) for (uint32_t c = cnt[v]; c; --c) q[k++] = v;
+            } else std::sort(q.begin(), q.end());
+        }
         p25 = (int)q[(int)(.25 * n + .499)];
         p50 = (int)q[(int)(.50 * n + .499)];
         p75 = (int)q[(int)(.75 * n + .499)];
@@ -827,7 +846,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     {
         std::vector<std::string> sam;
         std::vector<EntryStats> st;
-        std::string text;
+        std::vector<int> emit;
+        std::vector<size_t> offs;
+        RawBuf text;
         std::unique_ptr<Job> j;
         while (q_done.pop(j)) {
             try {
@@ -837,13 +858,19 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 double tf = now_sec();
                 sam.resize(batch.n); st.resize(batch.n);
                 parallel_for(host_threads, batch.n, [&](int i) { format_entry(ma, idx, batch, i, j->res, sam[i], st[i]); });
-                text.clear();
                 MapStats ms;
-                sam_sort_batch(batch, sam, st, text, ms);
+                sam_sort_plan(batch, sam, st, emit, ms);
+                const int ne = (int)emit.size();
+                offs.resize((size_t)ne + 1);
+                size_t total = 0;
+                for (int k = 0; k < ne; ++k) { offs[k] = total; total += sam[emit[k]].size(); }
+                offs[ne] = total;
+                text.resize_uninit(total);
+                parallel_for(host_threads, ne, [&](int k) { memcpy(text.data() + offs[k], sam[emit[k]].data(), sam[emit[k]].size()); });
                 double tw = now_sec();
-                fwrite(text.data(), 1, text.size(), out);
-                if (parts) fprintf(parts, "%ld\t%zu\t%zu\n", j->batch_id, out_bytes, text.size());
-                out_bytes += text.size();
+                fwrite(text.data(), 1, total, out);
+                if (parts) fprintf(parts, "%ld\t%zu\t%zu\n", j->batch_id, out_bytes, total);
+                out_bytes += total;
                 sum.sec_format += tw - tf; sum.sec_write += now_sec() - tw;
                 {
                     std::lock_guard<std::mutex> l(log_m);

@@ -43,7 +43,7 @@ int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err);
 
 struct BatchResult {
     std::vector<ReadOut> reads;
-    std::vector<uint8_t> arena;
+    RawBuf arena;
     PeStat pes[4];
     // hot-path accounting for the benchmark (CUDA-event timings in ms on the aligner's stream)
     // ms_stage: 0 H2D, 1 convert, 2 seed, 3 scan+SA lookup, 4 chain, 5 extend, 6 pair stats, 7 finalise

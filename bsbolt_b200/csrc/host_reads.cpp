@@ -10,7 +10,11 @@
 #include <stdexcept>
 #include <thread>
 
+#include <stdlib.h>
+
 namespace bsb {
+
+HostAllocHooks g_host_alloc = {malloc, free};
 
 enum { SEP_SPACE = 0, SEP_LINE = 2 };
 static const int kBuf = 1 << 20;
@@ -22,6 +26,7 @@ struct FastxReader::Prefetch {
     std::mutex m;
     std::condition_variable cv;
     std::deque<std::unique_ptr<Block>> ready, spare;
+    std::vector<std::unique_ptr<Block>> held;   // consumed blocks whose records a batch still points into
     std::unique_ptr<Block> cur;
     int pos = 0;
     bool done = false, stop = false;
@@ -55,7 +60,7 @@ void FastxReader::pump()
         std::unique_ptr<Prefetch::Block> b;
         {
             std::unique_lock<std::mutex> l(P.m);
-            P.cv.wait(l, [&] { return P.stop || P.ready.size() < 8; });
+            P.cv.wait(l, [&] { return P.stop || P.ready.size() < 96; });
             if (P.stop) return;
             if (!P.spare.empty()) { b = std::move(P.spare.front()); P.spare.pop_front(); }
         }
@@ -96,6 +101,33 @@ int FastxReader::next(FastxRecord &r)
         P.pos = 0;
         P.cv.notify_all();
     }
+}
+
+FastxRecord *FastxReader::next_ptr()
+{
+    Prefetch &P = *pf_;
+    for (;;) {
+        if (P.cur && P.pos < P.cur->n) return &P.cur->rec[P.pos++];
+        if (P.cur && P.cur->status < 0) return nullptr;
+        if (P.cur) P.held.push_back(std::move(P.cur));
+        std::unique_lock<std::mutex> l(P.m);
+        P.cv.wait(l, [&] { return !P.ready.empty() || P.done; });
+        if (P.ready.empty()) return nullptr;
+        P.cur = std::move(P.ready.front());
+        P.ready.pop_front();
+        P.pos = 0;
+        P.cv.notify_all();
+    }
+}
+
+void FastxReader::release_held()
+{
+    Prefetch &P = *pf_;
+    if (P.held.empty()) return;
+    std::lock_guard<std::mutex> l(P.m);
+    for (auto &b : P.held) P.spare.push_back(std::move(b));
+    P.held.clear();
+    P.cv.notify_all();
 }
 
 int FastxReader::getc_()
@@ -241,45 +273,91 @@ static void trim_readno(std::string &s)
     if (l > 2 && s[l - 2] == '/' && isdigit((unsigned char)s[l - 1])) s.resize(l - 2);
 }
 
+void ReadBatch::fill(const std::vector<Entry> &e, bool keep_comment, int n_threads)
+{
+    clear();
+    const size_t m = e.size();
+    seq_off.resize(m + 1); name_off.resize(m + 1); cmt_off.resize(m + 1);
+    has_qual.resize(m); first.resize(m); read_group.resize(m); pattern.resize(m);
+    uint32_t so = 0, no = 0, co = 0;
+    for (size_t i = 0; i < m; ++i) {
+        seq_off[i] = so; name_off[i] = no; cmt_off[i] = co;
+        so += e[i].len; no += (uint32_t)e[i].rec->name.size();
+        if (keep_comment) co += (uint32_t)e[i].rec->comment.size();
+    }
+    seq_off[m] = so; name_off[m] = no; cmt_off[m] = co;
+    bases.resize(so); qual.resize(so); names.resize(no); comments.resize(co);
+    n = (int)m; n_bases = so;
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const FastxRecord &r = *e[i].rec;
+            const size_t l = e[i].len;
+            memcpy(bases.data() + seq_off[i], r.seq.data(), l);
+            const bool hq = !r.qual.empty();
+            if (hq) memcpy(qual.data() + seq_off[i], r.qual.data(), l);
+            else memset(qual.data() + seq_off[i], '*', l);
+            has_qual[i] = hq;
+            memcpy(names.data() + name_off[i], r.name.data(), r.name.size());
+            if (keep_comment) memcpy(comments.data() + cmt_off[i], r.comment.data(), r.comment.size());
+            first[i] = e[i].first; read_group[i] = e[i].read_group; pattern[i] = e[i].pattern;
+        }
+    };
+    if (n_threads <= 1 || m < 4096) { work(0, m); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (m + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        size_t lo = t * chunk, hi = lo + chunk < m ? lo + chunk : m;
+        if (lo >= hi) break;
+        th.emplace_back(work, lo, hi);
+    }
+    for (auto &x : th) x.join();
+}
+
 bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,
                 float substitution_proportion, ReadBatch &b)
 {
-    b.clear();
-    FastxRecord k1, k2;
+    // phase 1 (serial, no copying): walk the parsers' record blocks, apply the reference's batching rule
+    static thread_local std::vector<ReadBatch::Entry> ents;
+    ents.clear();
     int64_t size = 0;
-    while (r1->next(k1) >= 0) {
-        if (r2 && r2->next(k2) < 0) {
+    auto push = [&](FastxRecord *k, int first, int rg, int pattern) {
+        uint32_t l = (uint32_t)strnlen(k->seq.data(), k->seq.size());
+        ents.push_back(ReadBatch::Entry{k, l, (uint8_t)first, (uint8_t)rg, (uint8_t)pattern});
+        size += l;
+    };
+    FastxRecord *k1, *k2 = nullptr;
+    while ((k1 = r1->next_ptr()) != nullptr) {
+        if (r2 && (k2 = r2->next_ptr()) == nullptr) {
             fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", "bseq_read");
             break;
         }
-        trim_readno(k1.name);
+        trim_readno(k1->name);
         int pattern = 0, compare_reads = 0;
         if (undirectional) {
-            int un_type = r2 ? assess_conversion(k1.seq, k2.seq, 1, substitution_proportion)
-                             : assess_conversion(k1.seq, k1.seq, 0, substitution_proportion);
+            int un_type = r2 ? assess_conversion(k1->seq, k2->seq, 1, substitution_proportion)
+                             : assess_conversion(k1->seq, k1->seq, 0, substitution_proportion);
             if (un_type == 2) compare_reads = 1;
             else pattern = un_type;
         }
-        b.add(k1, keep_comment, 0, 0, pattern);
-        size += b.len(b.n - 1);
-        if (r2) {
-            trim_readno(k2.name);
-            b.add(k2, keep_comment, 1, 0, pattern ? 0 : 1);
-            size += b.len(b.n - 1);
-        }
+        push(k1, 0, 0, pattern);
+        if (r2) { trim_readno(k2->name); push(k2, 1, 0, pattern ? 0 : 1); }
         if (compare_reads) {
-            b.add(k1, keep_comment, 0, 1, 1);
-            size += b.len(b.n - 1);
-            if (r2) {
-                b.add(k2, keep_comment, 1, 1, 0);
-                size += b.len(b.n - 1);
-            }
+            push(k1, 0, 1, 1);
+            if (r2) push(k2, 1, 1, 0);
         }
-        if (size >= chunk_size && (b.n & 1) == 0) break;
+        if (size >= chunk_size && (ents.size() & 1) == 0) break;
     }
-    if (size == 0) {
-        if (r2 && r2->next(k2) >= 0) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", "bseq_read");
+    if (size == 0 && ents.empty()) {
+        if (r2 && r1->next_ptr() == nullptr && r2->next_ptr() != nullptr) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", "bseq_read");
     }
+    // phase 2 (parallel): copy into the flat batch arrays
+    int nt = (int)std::thread::hardware_concurrency() / 2;
+    if (const char *e = getenv("BSB_HOST_THREADS")) nt = atoi(e) / 2;
+    if (nt < 1) nt = 1;
+    if (nt > 8) nt = 8;
+    b.fill(ents, keep_comment, nt);
+    r1->release_held();
+    if (r2) r2->release_held();
     return b.n > 0;
 }
 

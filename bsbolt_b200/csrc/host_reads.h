@@ -5,11 +5,65 @@
 //   read_batch()         <- bseq_read, kseq2bseq1  (bwa.c:44-145)
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include <zlib.h>
 
 namespace bsb {
+
+// Host buffers that cross PCIe are allocated through these hooks: malloc/free by default, page-locked memory
+// once the CUDA library installs its allocator (bsb_cuda.cu). Set once, before any buffer exists.
+struct HostAllocHooks { void *(*alloc)(size_t); void (*release)(void *); };
+extern HostAllocHooks g_host_alloc;
+
+// growable byte buffer without value-initialisation (a 100 MB std::vector::resize costs ~10 ms of memset)
+class RawBuf {
+public:
+    RawBuf() {}
+    ~RawBuf() { if (p_) g_host_alloc.release(p_); }
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    size_t size() const { return n_; }
+    void resize_uninit(size_t n)
+    {
+        if (n > cap_) {
+            size_t c = n + n / 4 + 4096;
+            uint8_t *q = (uint8_t *)g_host_alloc.alloc(c);
+            if (p_) g_host_alloc.release(p_);     // contents are not preserved: callers refill the buffer
+            p_ = q; cap_ = c;
+        }
+        n_ = n;
+    }
+private:
+    uint8_t *p_ = nullptr; size_t n_ = 0, cap_ = 0;
+};
+
+// std::vector<char>-like, hook-allocated (page-locked in the product), contents preserved on growth
+class PinVec {
+public:
+    PinVec() {}
+    ~PinVec() { if (p_) g_host_alloc.release(p_); }
+    PinVec(const PinVec &) = delete;
+    PinVec &operator=(const PinVec &) = delete;
+    char *data() { return p_; }
+    const char *data() const { return p_; }
+    size_t size() const { return n_; }
+    size_t capacity() const { return cap_; }
+    void clear() { n_ = 0; }
+    void reserve(size_t c)
+    {
+        if (c <= cap_) return;
+        char *q = (char *)g_host_alloc.alloc(c);
+        if (p_) { memcpy(q, p_, n_); g_host_alloc.release(p_); }
+        p_ = q; cap_ = c;
+    }
+    void resize(size_t n) { if (n > cap_) reserve(n + n / 2 + 4096); n_ = n; }
+private:
+    char *p_ = nullptr; size_t n_ = 0, cap_ = 0;
+};
 
 struct FastxRecord { std::string name, comment, seq, qual; };
 
@@ -19,6 +73,10 @@ public:
     ~FastxReader();
     // >=0 sequence length, -1 end of file, -2 truncated quality
     int next(FastxRecord &r);
+    // zero-copy form for the batcher: the next record inside the parser's block (nullptr at end of input). The
+    // pointer stays valid until release_held().
+    FastxRecord *next_ptr();
+    void release_held();
 private:
     int next_raw(FastxRecord &r);
     void pump();               // parser thread body
@@ -38,7 +96,7 @@ private:
 struct ReadBatch {
     int n = 0;
     std::vector<uint32_t> seq_off;   // n+1 offsets into bases/qual
-    std::vector<char> bases;         // ASCII as read from the file (unconverted)
+    PinVec bases;                    // ASCII as read from the file (unconverted); uploaded to the device
     std::vector<char> qual;          // same offsets as bases; valid iff has_qual
     std::vector<uint8_t> has_qual;
     std::vector<uint32_t> name_off;  // n+1
@@ -50,6 +108,8 @@ struct ReadBatch {
 
     void clear();
     void reserve_like(const ReadBatch &o);   // pre-size for a batch about as large as o
+    struct Entry { const FastxRecord *rec; uint32_t len; uint8_t first, read_group, pattern; };
+    void fill(const std::vector<Entry> &e, bool keep_comment, int n_threads);   // bulk, multi-threaded add()
     void add(const FastxRecord &r, bool keep_comment, int first, int read_group, int pattern);
     int len(int i) const { return (int)(seq_off[i + 1] - seq_off[i]); }
     std::string name(int i) const { return std::string(names.data() + name_off[i], name_off[i + 1] - name_off[i]); }

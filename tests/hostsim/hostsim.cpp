@@ -118,7 +118,8 @@ public:
         size_t task_cap = (size_t)n * 2 + 1024;
         std::vector<AlnTask> tasks;
         for (;;) {
-            out.arena.assign(arena_cap, 0);
+            out.arena.resize_uninit(arena_cap);
+            memset(out.arena.data(), 0, arena_cap);
             tasks.assign(task_cap, AlnTask());
             unsigned long long used = 8; // offset 0 is reserved as "null"
             unsigned int n_tasks = 0;
@@ -130,7 +131,7 @@ public:
             if (n_tasks <= task_cap) for (unsigned int k = 0; k < n_tasks; ++k) stage_task(opt, ix_, B, k, ws);
             bool ovf = n_tasks > task_cap || used > arena_cap;
             for (int r = 0; r < n; ++r) if (out.reads[r].err == ERR_ARENA_OVERFLOW) ovf = true;
-            if (!ovf) { out.arena.resize(used); break; }
+            if (!ovf) break;
             if (n_tasks > task_cap) task_cap = (size_t)n_tasks + 1024;
             arena_cap *= 2;
         }
