@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -240,21 +241,49 @@ __global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
 // ------------------------------------------------------------------------------------------------
 // page-locked host buffers for everything that crosses PCIe (installed once, at library load)
 // ------------------------------------------------------------------------------------------------
+// Page-locking is expensive (~0.3 ms/MB), so released blocks go to a process-wide pool and are handed out
+// again: the second run of a process (and every recycled batch) reuses the blocks of the first.
+struct PinnedPool {
+    std::mutex m;
+    std::vector<std::pair<uint8_t *, size_t>> free_blocks;   // (block incl. 64-byte header, payload capacity)
+};
+static PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool; return *p; }
+
 static void *pinned_alloc(size_t n)
 {
-    // 64-byte header remembers how the block was obtained so that release() matches
+    {
+        PinnedPool &P = pinned_pool();
+        std::lock_guard<std::mutex> l(P.m);
+        int best = -1;
+        for (int i = 0; i < (int)P.free_blocks.size(); ++i)
+            if (P.free_blocks[i].second >= n && P.free_blocks[i].second <= 2 * n + (1 << 20) &&
+                (best < 0 || P.free_blocks[i].second < P.free_blocks[best].second)) best = i;
+        if (best >= 0) {
+            uint8_t *p = P.free_blocks[best].first;
+            P.free_blocks.erase(P.free_blocks.begin() + best);
+            return p + 64;
+        }
+    }
+    // 64-byte header: how the block was obtained + its capacity
     void *p = nullptr;
-    if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) == cudaSuccess && p) { *(uint64_t *)p = 0x50494e4e45445f5full; return (uint8_t *)p + 64; }
+    if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) == cudaSuccess && p) {
+        ((uint64_t *)p)[0] = 0x50494e4e45445f5full; ((uint64_t *)p)[1] = n;
+        return (uint8_t *)p + 64;
+    }
     cudaGetLastError();
     p = malloc(n + 64);
     if (!p) throw std::bad_alloc();
-    *(uint64_t *)p = 0;
+    ((uint64_t *)p)[0] = 0; ((uint64_t *)p)[1] = n;
     return (uint8_t *)p + 64;
 }
 static void pinned_release(void *q)
 {
     uint8_t *p = (uint8_t *)q - 64;
-    if (*(uint64_t *)p == 0x50494e4e45445f5full) cudaFreeHost(p); else free(p);
+    if (((uint64_t *)p)[0] == 0x50494e4e45445f5full) {
+        PinnedPool &P = pinned_pool();
+        std::lock_guard<std::mutex> l(P.m);
+        P.free_blocks.emplace_back(p, (size_t)((uint64_t *)p)[1]);
+    } else free(p);
 }
 struct InstallPinnedHooks { InstallPinnedHooks() { g_host_alloc.alloc = pinned_alloc; g_host_alloc.release = pinned_release; } };
 static InstallPinnedHooks g_install_pinned_hooks;

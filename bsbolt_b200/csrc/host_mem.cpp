@@ -848,7 +848,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
         std::vector<EntryStats> st;
         std::vector<int> emit;
         std::vector<size_t> offs;
-        RawBuf text;
+        RawBuf text(false);   // SAM text never crosses PCIe: ordinary memory
         std::unique_ptr<Job> j;
         while (q_done.pop(j)) {
             try {

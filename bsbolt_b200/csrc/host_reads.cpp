@@ -351,10 +351,10 @@ bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_
         if (r2 && r1->next_ptr() == nullptr && r2->next_ptr() != nullptr) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", "bseq_read");
     }
     // phase 2 (parallel): copy into the flat batch arrays
-    int nt = (int)std::thread::hardware_concurrency() / 2;
-    if (const char *e = getenv("BSB_HOST_THREADS")) nt = atoi(e) / 2;
+    int nt = (int)std::thread::hardware_concurrency() / 4;
+    if (const char *e = getenv("BSB_HOST_THREADS")) nt = atoi(e) / 4;
     if (nt < 1) nt = 1;
-    if (nt > 8) nt = 8;
+    if (nt > 4) nt = 4;
     b.fill(ents, keep_comment, nt);
     r1->release_held();
     if (r2) r2->release_held();

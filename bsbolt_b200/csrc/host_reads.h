@@ -5,6 +5,7 @@
 //   read_batch()         <- bseq_read, kseq2bseq1  (bwa.c:44-145)
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -20,8 +21,8 @@ extern HostAllocHooks g_host_alloc;
 // growable byte buffer without value-initialisation (a 100 MB std::vector::resize costs ~10 ms of memset)
 class RawBuf {
 public:
-    RawBuf() {}
-    ~RawBuf() { if (p_) g_host_alloc.release(p_); }
+    explicit RawBuf(bool transfer_buffer = true) : hooks_(transfer_buffer) {}
+    ~RawBuf() { if (p_) rel(p_); }
     RawBuf(const RawBuf &) = delete;
     RawBuf &operator=(const RawBuf &) = delete;
     uint8_t *data() { return p_; }
@@ -31,14 +32,16 @@ public:
     {
         if (n > cap_) {
             size_t c = n + n / 4 + 4096;
-            uint8_t *q = (uint8_t *)g_host_alloc.alloc(c);
-            if (p_) g_host_alloc.release(p_);     // contents are not preserved: callers refill the buffer
-            p_ = q; cap_ = c;
+            if (p_) rel(p_);                      // contents are not preserved: callers refill the buffer
+            p_ = (uint8_t *)(hooks_ ? g_host_alloc.alloc(c) : malloc(c));
+            cap_ = c;
         }
         n_ = n;
     }
 private:
+    void rel(void *p) { if (hooks_) g_host_alloc.release(p); else free(p); }
     uint8_t *p_ = nullptr; size_t n_ = 0, cap_ = 0;
+    bool hooks_;
 };
 
 // std::vector<char>-like, hook-allocated (page-locked in the product), contents preserved on growth
