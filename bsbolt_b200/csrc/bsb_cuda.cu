@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -251,6 +252,9 @@ static PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool; return
 
 static void *pinned_alloc(size_t n)
 {
+    // coarse size classes so that buffers of "about the same" size are interchangeable
+    if (n > (16u << 20)) n = (n + (32u << 20) - 1) / (32u << 20) * (32u << 20);
+    else if (n > (1u << 20)) n = (n + (4u << 20) - 1) / (4u << 20) * (4u << 20);
     {
         PinnedPool &P = pinned_pool();
         std::lock_guard<std::mutex> l(P.m);
@@ -391,6 +395,11 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     for (int i = 0; i < n; ++i) max_len = std::max(max_len, b.len(i));
     if (max_len > 700) throw std::runtime_error("[E::bsbolt_b200] reads longer than 700 bp need mem_seed_sw (bwamem.c:575-619), which this build does not implement");
     for (int k = 0; k < 8; ++k) out.ms_stage[k] = 0;
+    const bool dbg = getenv("BSB_DEBUG_TIMELINE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto T = [&](const char *tag) {
+        if (dbg) fprintf(stderr, "[D::timeline] %-14s %8.2f ms\n", tag, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
 
     // ---- H2D ----
     CK(cudaEventRecord(m.ev[0], st));
@@ -400,6 +409,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemcpyAsync(m.d_seq_off.p, b.seq_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m.d_pattern.p, b.pattern.data(), (size_t)n, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(m.ev[1], st));
+    T("h2d_enq");
 
     BatchDev B;
     memset(&B, 0, sizeof B);
@@ -442,6 +452,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         if (B.intv_cap > (1 << 20)) throw std::runtime_error("[E::bsbolt_b200] interval list overflow");
     }
     CK(cudaEventRecord(m.ev[3], st));
+    T("seed_done");
 
     // ---- seed offsets ----
     size_t cub_bytes = 0;
@@ -452,6 +463,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemcpyAsync(&S, m.d_seed_off.p + n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     B.seed_off = m.d_seed_off.p;
+    T("scan_done");
     if (getenv("BSB_DEBUG_STATS")) { // distribution of per-read seed counts (load-balance diagnostics)
         std::vector<int32_t> ns(n);
         CK(cudaMemcpy(ns.data(), m.d_n_seed.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -496,6 +508,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemcpyAsync(h_misc, m.d_misc.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(m.ev[6], st));
     CK(cudaStreamSynchronize(st));
+    T("extend_done");
     if (h_misc[1]) throw std::runtime_error("[E::bsbolt_b200] chaining/extension failed with error code " + std::to_string(h_misc[1]));
     const int max_regs = h_misc[0];
     if (getenv("BSB_DEBUG_STATS")) {
@@ -530,6 +543,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemcpyAsync(m.d_pair.p, pair_tab.data(), pair_tab.size() * 8, cudaMemcpyHostToDevice, st));
     B.mt.pair_tab = m.d_pair.p; B.mt.log_tab = m.d_log.p; B.mt.n_log = (int)m.log_tab.size();
     CK(cudaEventRecord(m.ev[7], st));
+    T("pestat_done");
 
     // ---- K6/K7/K8 ----
     FinalLayout L;
@@ -564,6 +578,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     unsigned long long used = 0;
     unsigned int n_tasks = 0;
     out.reads.resize(n);
+    T("final_setup");
     for (;;) {
         m.d_arena.ensure(m.arena_cap);
         m.d_tasks.ensure(m.task_cap);
@@ -581,6 +596,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemcpyAsync(&n_tasks, m.d_ntasks.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(m.ev[10], st));
         CK(cudaStreamSynchronize(st));
+        T("select_done");
         if (n_tasks > m.task_cap) { m.task_cap = (size_t)n_tasks + (size_t)n_tasks / 4 + 4096; continue; }
         if (n_tasks) {
             k_tasks<<<tk_blocks, tk_wpb * 32, tk_wpb * tk_smem_per_warp, st>>>(opt, m.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, tk_smem_per_warp);
@@ -591,6 +607,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemcpyAsync(&used, m.d_used.p, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out.reads.data(), m.d_out.p, (size_t)n * sizeof(ReadOut), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        T("tasks_done");
         if (used <= m.arena_cap) break;
         m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
     }
@@ -599,6 +616,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(m.ev[9], st));
     CK(cudaStreamSynchronize(st));
+    T("d2h_done");
     for (int r = 0; r < n; ++r)
         if (out.reads[r].err)
             throw std::runtime_error("[E::bsbolt_b200] read '" + b.name(r) + "' failed on the device with error code " + std::to_string(out.reads[r].err));

@@ -798,7 +798,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
     Channel<std::unique_ptr<Job>> q_read(2), q_done(2), q_free(8);
-    for (int k = 0; k < 5; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
+    for (int k = 0; k < 4; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
     std::string fail;
     std::mutex fail_m;
     auto set_fail = [&](const std::string &w) { std::lock_guard<std::mutex> l(fail_m); if (fail.empty()) fail = w; };

@@ -42,7 +42,7 @@ void fill_scmat(int a, int b, int8_t mat[25]);      // bwa_fill_scmat (bwa.c:169
 int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err);
 
 struct BatchResult {
-    std::vector<ReadOut> reads;
+    PinArray<ReadOut> reads;
     RawBuf arena;
     PeStat pes[4];
     // hot-path accounting for the benchmark (CUDA-event timings in ms on the aligner's stream)

@@ -44,6 +44,21 @@ private:
     bool hooks_;
 };
 
+// fixed-type array over a RawBuf (contents undefined after resize)
+template <class T>
+class PinArray {
+public:
+    T *data() { return reinterpret_cast<T *>(buf_.data()); }
+    const T *data() const { return reinterpret_cast<const T *>(buf_.data()); }
+    T &operator[](size_t i) { return data()[i]; }
+    const T &operator[](size_t i) const { return data()[i]; }
+    size_t size() const { return n_; }
+    void resize(size_t n) { buf_.resize_uninit(n * sizeof(T)); n_ = n; }
+    void assign(size_t n, const T &v) { resize(n); for (size_t i = 0; i < n; ++i) data()[i] = v; }
+private:
+    RawBuf buf_; size_t n_ = 0;
+};
+
 // std::vector<char>-like, hook-allocated (page-locked in the product), contents preserved on growth
 class PinVec {
 public:
