@@ -119,11 +119,11 @@ def head_records(src, dst, n):
             o.write(line)
 
 
-def reference_cpu_run(bwa, argv_tail, n_reads, threads):
+def reference_cpu_run(bwa, argv_tail, n_reads, threads, sam_out=os.devnull):
     """Times the reference aligner; the clock starts when the first batch has been read (index load excluded)."""
     cmd = [bwa, 'mem'] + LAUNCHER_ARGS + ['-t', str(threads)] + argv_tail
     t_first = None
-    with open(os.devnull, 'w') as null:
+    with open(sam_out, 'w') as null:
         p = subprocess.Popen(cmd, stdout=null, stderr=subprocess.PIPE, text=True)
         for line in p.stderr:
             if t_first is None and line.startswith('[M::process] read'):
@@ -133,6 +133,21 @@ def reference_cpu_run(bwa, argv_tail, n_reads, threads):
     if p.returncode != 0 or t_first is None:
         raise RuntimeError('reference aligner failed')
     return n_reads / (t_end - t_first), t_end - t_first
+
+
+def compare_sam(ref_path, my_path):
+    """record-by-record identity of two SAM files (headers: all but @PG, whose CL differs by construction)"""
+    n = same = 0
+    hdr_same = True
+    with open(ref_path) as fa, open(my_path) as fb:
+        la = [l for l in fa if not l.startswith('@PG')]
+        lb = [l for l in fb if not l.startswith('@PG')]
+    ha = [l for l in la if l.startswith('@')]; hb = [l for l in lb if l.startswith('@')]
+    hdr_same = ha == hb
+    ra = la[len(ha):]; rb = lb[len(hb):]
+    n = max(len(ra), len(rb))
+    same = sum(1 for x, y in zip(ra, rb) if x == y)
+    return {'sam_records': n, 'identical': same, 'identical_frac': same / n if n else None, 'header_identical': hdr_same}
 
 
 def main():
@@ -279,17 +294,25 @@ def main():
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = SEED_BYTES_PER_READ * reads_per_launch / (seed_ms / 1000) / 1e9
     cpu = None
+    parity = None
     if os.path.exists(bwa) and world == 1:
         sp = min(a.cpu_sample_pairs, a.batch_pairs)
         s1 = os.path.join(work, 'cpu_s1.fq'); s2 = os.path.join(work, 'cpu_s2.fq')
+        ref_sam = os.path.join(work, 'cpu_ref.sam'); my_sam = os.path.join(work, 'cpu_mine.sam')
         for src, dst in ((f1, s1), (f2, s2)):
             head_records(src, dst, sp)
         try:
-            r, sec = reference_cpu_run(bwa, ['-K', str(K_bases), db, s1, s2], 2 * sp, cores)
+            r, sec = reference_cpu_run(bwa, ['-K', str(K_bases), db, s1, s2], 2 * sp, cores, sam_out=ref_sam)
             cpu = {'value': r, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference',
                    'sample': f'first {sp} pairs of the timed reads, oracle/_ref/bwa mem -t {cores}, {sec:.1f} s, clock from first batch read to exit'}
+            # the same sample through the product (untimed): record-level identity with the reference's SAM
+            fd = os.open(my_sam, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            rc, _ = _native.mem_main(argv_common + [db, s1, s2], index=idx, out_fd=fd, log_fd=null)
+            os.close(fd)
+            if rc == 0:
+                parity = compare_sam(ref_sam, my_sam)
         except Exception as e:  # noqa
-            cpu = {'value': None, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference', 'sample': f'failed: {e}'}
+            cpu = cpu or {'value': None, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference', 'sample': f'failed: {e}'}
     line = {'metric': 'paired-end 150bp WGBS reads aligned/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': a.gpus, 'steps': n_batches,
             'warmup': W, 'ms_per_step': ms_kernels / n_batches, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'int32', 'data': 'synthetic', 'config': config, 'clocks': clocks,
@@ -299,7 +322,7 @@ def main():
             'roofline': {'bound': 'hbm', 'kernel': 'k_seed (SMEM seeding)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms},
-            'cpu_baseline': cpu,
+            'cpu_baseline': cpu, 'parity_vs_reference': parity,
             'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st['ms_stage'])},
             'final_split_ms_per_step': {'select': st['ms_select'] / n_batches, 'tasks': st['ms_tasks'] / n_batches, 'n_tasks': st['n_tasks'] // n_batches},
             'host_busy_s': {'read': st['sec_read'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_thread': st['sec_align']},
