@@ -121,6 +121,119 @@ __global__ void __launch_bounds__(64, 16) k_seed_dyn(Opt opt, IndexView ix, Batc
     }
 }
 
+// ---- K2, two-item form (bsb_seed3.h) ---------------------------------------------------------
+// 4-bit packed copy of the converted reads, 16 bases per 64-bit word; read r starts at word (seq_off[r] >> 4) + r
+// (a closed form that never overlaps: ceil(len/16) <= (len >> 4) + 1). A lane keeps one word in registers.
+__global__ void k_pack4(BatchDev B, uint64_t *seq4, uint32_t n_words)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    int lo = 0, hi = B.n;                       // largest r with start(r) <= w
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((B.seq_off[mid] >> 4) + (uint32_t)mid <= w) lo = mid; else hi = mid;
+    }
+    const uint32_t beg = B.seq_off[lo], len = B.seq_off[lo + 1] - beg;
+    const uint32_t k = w - ((beg >> 4) + (uint32_t)lo);
+    if (k * 16 >= len) return;                  // padding word between two reads
+    uint64_t v = 0;
+    const uint32_t m = min(16u, len - k * 16);
+    for (uint32_t t = 0; t < m; ++t) v |= (uint64_t)(B.seq[beg + k * 16 + t] & 15) << (t << 2);
+    seq4[w] = v;
+}
+
+struct BasesPacked {
+    const uint64_t *w; uint64_t cur; int widx;
+    __device__ __forceinline__ int get(int i)
+    {
+        const int wi = i >> 4;
+        if (wi != widx) { cur = __ldg(w + wi); widx = wi; }
+        return (int)(cur >> ((i & 15) << 2)) & 15;
+    }
+};
+
+// interval list of one lane: the first `scap` ranks in shared memory (12 bytes per entry, 40-bit coordinates,
+// lane-interleaved so that lanes at the same rank hit different banks), the rest in an HBM spill area
+constexpr int SEED3_BLOCK = 64;
+struct ListSmem {
+    uint32_t *s; uint4 *g; int scap, total;
+    __device__ __forceinline__ int cap() const { return total; }
+    __device__ __forceinline__ void get(int p, uint64_t &x0, uint64_t &x2, int &end) const
+    {
+        if (p < scap) {
+            const uint32_t *e = s + p * 3 * SEED3_BLOCK;
+            const uint32_t a = e[0], b = e[SEED3_BLOCK], m = e[2 * SEED3_BLOCK];
+            x0 = (uint64_t)(m & 0xff) << 32 | a; x2 = (uint64_t)((m >> 8) & 0xff) << 32 | b; end = (int)(m >> 16);
+        } else {
+            const uint4 v = g[p - scap];
+            x0 = (uint64_t)(v.z & 0xff) << 32 | v.x; x2 = (uint64_t)((v.z >> 8) & 0xff) << 32 | v.y; end = (int)(v.z >> 16);
+        }
+    }
+    __device__ __forceinline__ void set(int p, uint64_t x0, uint64_t x2, int end)
+    {
+        const uint32_t m = (uint32_t)(x0 >> 32) & 0xff | ((uint32_t)(x2 >> 32) & 0xff) << 8 | (uint32_t)end << 16;
+        if (p < scap) {
+            uint32_t *e = s + p * 3 * SEED3_BLOCK;
+            e[0] = (uint32_t)x0; e[SEED3_BLOCK] = (uint32_t)x2; e[2 * SEED3_BLOCK] = m;
+        } else g[p - scap] = make_uint4((uint32_t)x0, (uint32_t)x2, m, 0);
+    }
+};
+
+// Every lane runs one work item (item < n: passes 1+2 of read `item`; item >= n: pass 3 of read item - n) and pulls
+// the next from a global counter the moment it finishes; all lanes of the warp meet at the single extension site.
+__global__ void __launch_bounds__(SEED3_BLOCK, 12) k_seed3(Opt opt, IndexView ix, BatchDev B, const uint64_t *seq4, uint4 *spill, int scap, int ltotal,
+                                                            int *next_item, int32_t *cnt_a, int32_t *cnt_b)
+{
+    extern __shared__ uint32_t sm_list[];
+    Seeder3<BasesPacked, ListSmem> sm;
+    sm.L.s = sm_list + threadIdx.x; sm.L.scap = scap; sm.L.total = ltotal;
+    sm.L.g = spill + (size_t)(blockIdx.x * SEED3_BLOCK + threadIdx.x) * (size_t)(ltotal > scap ? ltotal - scap : 0);
+    sm.st = Seeder3<BasesPacked, ListSmem>::DONE; sm.err = 0; sm.n_out = 0;
+    int item = -1;
+    bool exhausted = false;
+    for (;;) {
+        bool need = false;
+        while (!need && !exhausted) {
+            if (sm.done()) {
+                if (item >= 0) {   // close the item that just finished
+                    const int r = item < B.n ? item : item - B.n;
+                    (item < B.n ? cnt_a : cnt_b)[r] = sm.n_out;
+                    if (sm.err) B.err[r] = sm.err;
+                }
+                item = atomicAdd(next_item, 1);
+                if (item >= 2 * B.n) { exhausted = true; item = -1; break; }
+                const int r = item < B.n ? item : item - B.n;
+                const uint32_t beg = B.seq_off[r];
+                const int len = (int)(B.seq_off[r + 1] - beg);
+                if (len < opt.min_seed_len) { item = -1; continue; }
+                sm.q.w = seq4 + (beg >> 4) + r; sm.q.widx = -1;
+                sm.init(opt, len, B.intv + (size_t)r * B.intv_cap, B.intv_cap, item >= B.n);
+            }
+            need = sm.advance(ix);
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, need)) break;
+        if (need) {
+            uint64_t xa, xb, s, na, nb, sz;
+            sm.request(xa, xb, s);
+            fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
+            sm.consume(na, nb, sz);
+        }
+    }
+}
+
+// merges the two parts of every read's interval list, sorts it, and runs the tail of the stage (bwamem.c:269-283)
+__global__ void k_seed3_finish(Opt opt, BatchDev B, const int32_t *cnt_a, const int32_t *cnt_b)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n) return;
+    if (B.err[r]) return;
+    Intv *mem = B.intv + (size_t)r * B.intv_cap;
+    const int n = seed3_merge_sort(mem, B.intv_cap, cnt_a[r], cnt_b[r]);
+    if (n < 0) { B.err[r] = ERR_INTV_OVERFLOW; return; }
+    seed_finish(opt, B, r, mem, n, 0);
+}
+
 __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
 {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,6 +418,7 @@ struct CudaAligner::Impl {
     // batch buffers
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
     DevBuf<Intv> d_intv, d_seed_scratch;
+    DevBuf<uint64_t> d_seq4; DevBuf<uint4> d_spill; DevBuf<int32_t> d_cnt_ab;
     DevBuf<int32_t> d_n_intv, d_l_rep, d_n_seed, d_n_chain, d_n_regs, d_err, d_misc;
     DevBuf<uint32_t> d_seed_off;
     DevBuf<uint8_t> d_cub;
@@ -429,17 +543,35 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     B.intv_cap = std::max(std::max(256, 2 * max_len), m.intv_cap_hint);
     const int seed_block = 64;
     const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)m.n_sm * 16 * seed_block);
+    const bool seed_old = getenv("BSB_SEED_V1") || getenv("BSB_SEED_V2") || getenv("BSB_SEED_DYN");
+    const int s3_scap = 24, s3_total = max_len + 1, s3_blocks = m.n_sm * 12;
+    const uint32_t n_words = (uint32_t)(nb >> 4) + (uint32_t)n + 1;
+    if (!seed_old && n) {
+        m.d_seq4.ensure(n_words + 1);
+        m.d_spill.ensure((size_t)s3_blocks * SEED3_BLOCK * (size_t)std::max(s3_total - s3_scap, 0) + 1);
+        m.d_cnt_ab.ensure(2 * (size_t)n + 2);
+        k_pack4<<<cdiv(n_words, 256), 256, 0, st>>>(B, m.d_seq4.p, n_words); ++m.launches;
+        CK(cudaGetLastError());
+    }
     for (;;) {
         m.d_intv.ensure((size_t)n * B.intv_cap);
-        m.d_seed_scratch.ensure((size_t)seed_workers * 3 * B.intv_cap);
         B.intv = m.d_intv.p;
         CK(cudaMemsetAsync(m.d_err.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_n_seed.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
-        if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
-        else if (getenv("BSB_SEED_V2")) k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
-        else k_seed_dyn<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p, m.d_misc.p + 8);
-        ++m.launches;
+        if (seed_old) {
+            m.d_seed_scratch.ensure((size_t)seed_workers * 3 * B.intv_cap);
+            if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
+            else if (getenv("BSB_SEED_V2")) k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
+            else k_seed_dyn<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p, m.d_misc.p + 8);
+            ++m.launches;
+        } else if (n) {
+            CK(cudaMemsetAsync(m.d_cnt_ab.p, 0, 2 * (size_t)n * 4, st));
+            k_seed3<<<s3_blocks, SEED3_BLOCK, (size_t)SEED3_BLOCK * s3_scap * 12, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_scap, s3_total,
+                                                                                       m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n);
+            k_seed3_finish<<<cdiv(n, 128), 128, 0, st>>>(opt, B, m.d_cnt_ab.p, m.d_cnt_ab.p + n);
+            m.launches += 2;
+        }
         CK(cudaGetLastError());
         k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p); ++m.launches;
         int32_t max_err = 0;

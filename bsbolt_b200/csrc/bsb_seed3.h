@@ -1,0 +1,249 @@
+// bsb_seed3.h -- SMEM seeding, third form: two independent work items per read, one in-place interval list.
+//
+// Same results as collect_intv() (bsb_smem.h), i.e. mem_collect_intv (bwamem.c:118-166) over bwt_smem1a
+// (bwt.c:289-351) and bwt_seed_strategy1 (bwt.c:358-379); what changed is how the work is laid out:
+//
+//  * item A of a read = pass 1 (all SMEMs) followed by pass 2 (re-seeding inside long, rare SMEMs);
+//    item B = pass 3 (forward-only "LAST-like" seeds). Pass 3 reads nothing the other passes write, so the two
+//    items run on different lanes and the list is merged and sorted afterwards (seed3_finish). Interval records
+//    with equal `info` describe the same substring of the read and are therefore identical, so ANY sort by
+//    `info` gives the list the reference's introsort gives.
+//  * the reverse-strand coordinate x[1] of an interval is only needed while it is extended FORWARD. Nothing
+//    downstream reads it (mem_chain uses x[0], x[2], info), and the backward sweep of bwt_smem1a extends
+//    backward only -- so list entries are (x0, size, end) and the backward sweep rewrites ONE list in place:
+//    an entry consumed at rank j produces at most one entry at rank <= j. The forward sweep pushes entries in
+//    increasing length; the backward sweep walks them from the top down, so nothing is ever reversed.
+//  * every FM-index extension of a lane happens at one call site (the caller's), the lanes of a warp meet
+//    there; between extensions a lane touches only its list (shared memory on the device), its base window
+//    and registers.
+#pragma once
+#include "bsb_index.h"
+
+namespace bsb {
+
+// the extension both sweeps use: interval (xa = the coordinate on the strand being extended, xb = the other one,
+// s = size) by symbol c. Returns the new xa-side start, the new xb-side start and the new size.
+// Restates bwt_extend (bwt.c:262-275) for one output symbol.
+BSB_HD void fm_extend_one(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_t s, int c, uint64_t &na, uint64_t &nb, uint64_t &sz)
+{
+    uint64_t tk[4], tl[4];
+    occ4_pair(ix, xa - 1, xa - 1 + s, tk, tl);
+    const uint64_t s0 = tl[0] - tk[0], s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
+    const uint64_t n3 = xb + (xa <= ix.primary && xa + s - 1 >= ix.primary);
+    const uint64_t n2 = n3 + s3, n1 = n2 + s2, n0 = n1 + s1;
+    na = sel4(c, ix.L2[0] + 1 + tk[0], ix.L2[1] + 1 + tk[1], ix.L2[2] + 1 + tk[2], ix.L2[3] + 1 + tk[3]);
+    nb = sel4(c, n0, n1, n2, n3);
+    sz = sel4(c, s0, s1, s2, s3);
+}
+
+// Bases: int get(int i) -> code 0..3, >3 ambiguous.   List: void get(int p, uint64_t &x0, uint64_t &x2, int &end),
+// void set(int p, uint64_t x0, uint64_t x2, int end), int cap().
+template <class Bases, class List>
+struct Seeder3 {
+    enum St { NEXT, FWD, BWD_ROW, BWD_CELL, SMEM_END, P3, W_FWD, W_BWD, W_P3, DONE };
+    Bases q; List L;
+    Intv *out; int out_cap;          // this read's slice of the interval array: item A fills from the front, item B from the back
+    int len, min_seed_len, split_len, split_width, max_mem_intv;
+    int st, pass, x, i, min_intv, ret, c, err;
+    uint64_t k0, k1, ks; int k_end;  // the interval being extended forward (x0, x1, size) and the end it reaches
+    int nf, pn, j, cn; uint64_t last_x2;   // list: nf entries after the forward sweep; current row = ranks nf-1 .. nf-pn
+    uint64_t e0, e2; int e_end;      // the list entry whose backward extension is in flight
+    int m1_any, m1_start;            // bwt_smem1a's "mem->n == 0 || i + 1 < last start" test, without the list
+    int k2, old_n, n_out;
+
+    BSB_HD void init(const Opt &o, int len_, Intv *out_, int out_cap_, bool item_b)
+    {
+        len = len_; out = out_; out_cap = out_cap_; n_out = 0; err = 0;
+        min_seed_len = o.min_seed_len; split_width = o.split_width;
+        split_len = (int)(o.min_seed_len * o.split_factor + .499);
+        max_mem_intv = (int)o.max_mem_intv;
+        x = 0; i = -1; k2 = 0; old_n = 0;
+        if (item_b) { pass = 3; st = max_mem_intv > 0 ? P3 : DONE; }
+        else { pass = 1; st = NEXT; }
+    }
+    BSB_HD bool done() const { return st == DONE; }
+    BSB_HD bool is_back() const { return st == W_BWD; }
+
+    BSB_HD void emit(uint64_t x0, uint64_t x2, int start, int end)
+    {
+        if (n_out >= out_cap) { err = ERR_INTV_OVERFLOW; return; }
+        Intv v; v.x0 = x0; v.x1 = 0; v.x2 = x2; v.info = (uint64_t)(uint32_t)start << 32 | (uint32_t)end;
+        out[pass == 3 ? out_cap - 1 - n_out : n_out] = v;
+        ++n_out;
+    }
+    BSB_HD void emit_if_new(uint64_t x0, uint64_t x2, int start, int end)
+    {   // bwt.c:334-338 / 343-344 and the length filter of bwamem.c:130-133
+        if (m1_any && start >= m1_start) return;
+        m1_any = 1; m1_start = start;
+        if (end - start >= min_seed_len) emit(x0, x2, start, end);
+    }
+    BSB_HD void push_fwd()
+    {
+        if (nf >= L.cap()) { err = ERR_INTV_OVERFLOW; return; }
+        L.set(nf, k0, ks, k_end); ++nf; ret = k_end;
+    }
+    BSB_HD void begin_bwd() { pn = nf; i = x - 1; st = BWD_ROW; }
+    BSB_HD void start_smem(const IndexView &ix, int x_, int min_intv_)
+    {   // head of bwt_smem1a; caller guarantees q[x_] < 4
+        x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_;
+        m1_any = 0; m1_start = 0; nf = 0; ret = x + 1;
+        const int b = q.get(x);
+        k0 = ix.L2[b] + 1; ks = ix.L2[b + 1] - ix.L2[b]; k1 = ix.L2[3 - b] + 1; k_end = x + 1;
+        i = x + 1;
+        st = FWD;
+    }
+
+    // Runs until this lane needs an FM-index extension (true; operands via request()) or has finished (false).
+    BSB_HD bool advance(const IndexView &ix)
+    {
+        for (;;) {
+            switch (st) {
+            case NEXT:
+                if (pass == 1) {
+                    while (x < len && q.get(x) > 3) ++x;
+                    if (x >= len) { pass = 2; old_n = n_out; k2 = 0; break; }
+                    start_smem(ix, x, 1);
+                } else {
+                    bool started = false;
+                    while (k2 < old_n) {
+                        const uint64_t info = out[k2].info, occ = out[k2].x2;
+                        const int start = (int)(info >> 32), end = (int32_t)info;
+                        if (end - start < split_len || occ > (uint64_t)split_width) { ++k2; continue; }
+                        const int xm = (start + end) >> 1;
+                        if (q.get(xm) > 3) { ++k2; continue; }      // bwt_smem1a returns at once on an ambiguous base
+                        start_smem(ix, xm, (int)(occ + 1));
+                        started = true;
+                        break;
+                    }
+                    if (!started) st = DONE;
+                }
+                break;
+            case FWD:
+                if (i < len) {
+                    const int b = q.get(i);
+                    if (b < 4) { c = 3 - b; st = W_FWD; return true; }
+                }
+                push_fwd(); begin_bwd();       // read end or ambiguous base: record the interval, turn around
+                break;
+            case BWD_ROW:
+                if (i >= 0) c = q.get(i);
+                if (i < 0 || c > 3) {          // nothing can be extended: only the longest entry can be a new SMEM
+                    L.get(nf - 1, e0, e2, e_end);
+                    emit_if_new(e0, e2, i + 1, e_end);
+                    st = SMEM_END;
+                } else { j = 0; cn = 0; st = BWD_CELL; }
+                break;
+            case BWD_CELL:
+                if (j >= pn) {
+                    if (cn == 0) st = SMEM_END;
+                    else { pn = cn; --i; st = BWD_ROW; }
+                } else { L.get(nf - 1 - j, e0, e2, e_end); st = W_BWD; return true; }
+                break;
+            case SMEM_END:
+                if (pass == 1) x = ret; else ++k2;
+                st = NEXT;
+                break;
+            case P3:
+                if (i < 0) {                   // next start
+                    while (x < len && q.get(x) > 3) ++x;
+                    if (x >= len) { st = DONE; break; }
+                    const int b = q.get(x);
+                    k0 = ix.L2[b] + 1; ks = ix.L2[b + 1] - ix.L2[b]; k1 = ix.L2[3 - b] + 1;
+                    i = x + 1;
+                }
+                if (i >= len) { x = len; i = -1; break; }          // bwt_seed_strategy1 returns len
+                {
+                    const int b = q.get(i);
+                    if (b < 4) { c = 3 - b; st = W_P3; return true; }
+                }
+                x = i + 1; i = -1;                                  // ambiguous base: restart behind it
+                break;
+            default:
+                return false;
+            }
+        }
+    }
+
+    BSB_HD void request(uint64_t &xa, uint64_t &xb, uint64_t &s) const
+    {
+        if (st == W_BWD) { xa = e0; xb = 0; s = e2; } else { xa = k1; xb = k0; s = ks; }
+    }
+
+    BSB_HD void consume(uint64_t na, uint64_t nb, uint64_t sz)
+    {
+        if (st == W_FWD) {
+            if (sz != ks) {
+                push_fwd();
+                if (sz < (uint64_t)min_intv) { begin_bwd(); return; }
+            }
+            k1 = na; k0 = nb; ks = sz; k_end = i + 1;
+            ++i;
+            st = FWD;
+        } else if (st == W_BWD) {
+            if (sz < (uint64_t)min_intv) {
+                if (cn == 0) emit_if_new(e0, e2, i + 1, e_end);
+            } else if (cn == 0 || sz != last_x2) {
+                L.set(nf - 1 - cn, na, sz, e_end); ++cn; last_x2 = sz;
+            }
+            ++j;
+            st = BWD_CELL;
+        } else { // W_P3
+            if (sz < (uint64_t)max_mem_intv && i - x >= min_seed_len) {
+                if (sz > 0) emit(nb, sz, x, i + 1);
+                x = i + 1; i = -1;
+            } else { k1 = na; k0 = nb; ks = sz; ++i; }
+            st = P3;
+        }
+    }
+};
+
+// Merges the two items of a read (front part n_a, back part n_b of `mem`), sorts by info, and runs the tail of
+// the seeding stage. Returns the list length or -1 when the two parts collided (capacity too small).
+BSB_HD int seed3_merge_sort(Intv *mem, int cap, int n_a, int n_b)
+{
+    if (n_a + 2 * n_b > cap) return -1;                                // also keeps the copy below clear of its own source
+    for (int k = 0; k < n_b; ++k) mem[n_a + k] = mem[cap - 1 - k];
+    const int n = n_a + n_b;
+    for (int a = 1; a < n; ++a) {
+        const Intv v = mem[a];
+        int b = a;
+        while (b > 0 && mem[b - 1].info > v.info) { mem[b] = mem[b - 1]; --b; }
+        mem[b] = v;
+    }
+    return n;
+}
+
+// Plain-memory adapters (CPU unit harness; the device kernel has its own shared-memory list, bsb_cuda.cu)
+struct BasesBytes { const uint8_t *p; BSB_HD int get(int i) const { return p[i]; } };
+struct ListPlain {
+    uint64_t *a0, *a2; int *ae; int n;
+    BSB_HD int cap() const { return n; }
+    BSB_HD void get(int p, uint64_t &x0, uint64_t &x2, int &end) const { x0 = a0[p]; x2 = a2[p]; end = ae[p]; }
+    BSB_HD void set(int p, uint64_t x0, uint64_t x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
+};
+
+// collect_intv() through the two work items, one after the other (what the kernel does on two lanes)
+template <class Bases, class List>
+BSB_HD int collect_intv_v3(const Opt &opt, const IndexView &ix, int len, Bases q, List L, Intv *mem, int cap, int *err)
+{
+    int n_part[2] = {0, 0};
+    for (int item = 0; item < 2; ++item) {
+        Seeder3<Bases, List> sm;
+        sm.q = q; sm.L = L;
+        sm.init(opt, len, mem, cap, item == 1);
+        while (sm.advance(ix)) {
+            uint64_t xa, xb, s, na, nb, sz;
+            sm.request(xa, xb, s);
+            fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
+            sm.consume(na, nb, sz);
+        }
+        if (sm.err) *err = sm.err;
+        n_part[item] = sm.n_out;
+    }
+    if (*err) return 0;
+    const int n = seed3_merge_sort(mem, cap, n_part[0], n_part[1]);
+    if (n < 0) { *err = ERR_INTV_OVERFLOW; return 0; }
+    return n;
+}
+
+} // namespace bsb

@@ -11,6 +11,7 @@
 #pragma once
 #include "bsb_smem.h"
 #include "bsb_smem_sm.h"
+#include "bsb_seed3.h"
 #include "bsb_chain.h"
 #include "bsb_extend.h"
 #include "bsb_final.h"
@@ -96,7 +97,7 @@ BSB_HD void seed_finish(const Opt &opt, const BatchDev &B, int r, const Intv *me
 
 // K2: SMEM seeding for read r. use_sm selects the converged state-machine form (all lanes of a warp call
 // together, `active` false for lanes without a read); both forms produce the same interval list.
-BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const SeedScratch &sc, bool use_sm = false, bool active = true)
+BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const SeedScratch &sc, bool use_sm = false, bool active = true, bool use_v3 = false)
 {
     const int len = active ? (int)(B.seq_off[r + 1] - B.seq_off[r]) : 0;
     const uint8_t *seq = active ? B.seq + B.seq_off[r] : nullptr;
@@ -105,7 +106,13 @@ BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, i
     int err = 0;
     if (active) { B.n_intv[r] = 0; B.l_rep[r] = 0; B.n_seed[r] = 0; }
     const bool work = active && len >= opt.min_seed_len;
-    if (use_sm) collect_intv_sm(opt, ix, len, seq, mem, mem1, t0, t1, &err, work);
+    if (use_v3) {   // the product's seeding form (k_seed3), driven sequentially: list storage borrowed from the scratch lists
+        if (work) {
+            ListPlain L = {(uint64_t *)sc.t0, (uint64_t *)sc.t1, (int *)sc.mem1, B.intv_cap};
+            BasesBytes q = {seq};
+            mem.n = collect_intv_v3(opt, ix, len, q, L, mem.a, mem.cap, &err);
+        }
+    } else if (use_sm) collect_intv_sm(opt, ix, len, seq, mem, mem1, t0, t1, &err, work);
     else if (work) collect_intv(opt, ix, len, seq, mem, mem1, t0, t1, &err);
     if (!work) return;
     seed_finish(opt, B, r, mem.a, mem.n, err);

@@ -45,7 +45,8 @@ public:
             SeedScratch ss = {sc.data(), sc.data() + B.intv_cap, sc.data() + 2 * B.intv_cap};
             bool ovf = false;
             const bool use_sm = getenv("BSB_HOSTSIM_SEED_SM") != nullptr;
-            for (int r = 0; r < n; ++r) { err[r] = 0; stage_seed(opt, ix_, B, r, ss, use_sm, true); if (err[r] == ERR_INTV_OVERFLOW) ovf = true; }
+            const bool use_v3 = getenv("BSB_HOSTSIM_SEED_V3") != nullptr;
+            for (int r = 0; r < n; ++r) { err[r] = 0; stage_seed(opt, ix_, B, r, ss, use_sm, true, use_v3); if (err[r] == ERR_INTV_OVERFLOW) ovf = true; }
             if (!ovf) break;
             B.intv_cap *= 2;
         }

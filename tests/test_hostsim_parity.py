@@ -12,9 +12,14 @@ HOSTSIM = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
 CASES = ['se100', 'se100_un', 'se50_clip', 'pe150', 'pe150_un', 'pe150_un_sp0', 'pe150_opts']
 
 
+@pytest.mark.parametrize('seeding', ['nested', 'two_item'])
 @pytest.mark.parametrize('case', CASES)
-def test_kernel_bodies_match_reference_sam(built, golden, case):
-    p = subprocess.run([HOSTSIM] + golden.argv(case), capture_output=True, text=True)
+def test_kernel_bodies_match_reference_sam(built, golden, case, seeding):
+    """`two_item` = the seeding form the product kernel runs (bsb_seed3.h); `nested` = the direct restatement."""
+    env = dict(os.environ)
+    if seeding == 'two_item':
+        env['BSB_HOSTSIM_SEED_V3'] = '1'
+    p = subprocess.run([HOSTSIM] + golden.argv(case), capture_output=True, text=True, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     mine, want = strip_pg(p.stdout), golden.sam(case)
     assert mine == want, first_diff(want, mine)
