@@ -142,96 +142,173 @@ __global__ void k_pack4(BatchDev B, uint64_t *seq4, uint32_t n_words)
     seq4[w] = v;
 }
 
+// One 64-bit word (16 bases) of the read in registers, the word the sweep will need next already in flight:
+// a lane that stalls on a load inside the divergent part of the machine stalls the other 31 lanes with it.
 struct BasesPacked {
-    const uint64_t *w; uint64_t cur; int widx;
+    const uint64_t *w; uint64_t cur, nxt; int widx, nidx, nwords;
+    __device__ __forceinline__ void open(const uint64_t *words, int len) { w = words; nwords = (len + 15) >> 4; widx = -1; nidx = -1; cur = nxt = 0; }
     __device__ __forceinline__ int get(int i)
     {
         const int wi = i >> 4;
-        if (wi != widx) { cur = __ldg(w + wi); widx = wi; }
+        if (wi != widx) {
+            cur = wi == nidx ? nxt : __ldg(w + wi);
+            nidx = wi + (wi < widx ? -1 : 1);
+            widx = wi;
+            if (nidx >= 0 && nidx < nwords) nxt = __ldg(w + nidx); else nidx = -1;
+        }
         return (int)(cur >> ((i & 15) << 2)) & 15;
     }
 };
 
-// interval list of one lane: the first `scap` ranks in shared memory (12 bytes per entry, 40-bit coordinates,
-// lane-interleaved so that lanes at the same rank hit different banks), the rest in an HBM spill area
+// Interval list of one lane (bsb_seed3.h). Entries are 12 bytes (40-bit coordinates). Shared memory holds a ring of the
+// SCAP most recently pushed ranks, lane-interleaved so that lanes at the same rank hit different banks; a push beyond
+// SCAP first moves the rank it overwrites to the lane's HBM spill row. The backward sweep lives at the top of the
+// list (ranks nf-1 downwards, shrinking row by row), i.e. in the ring; only its first rows reach into the spill row.
 constexpr int SEED3_BLOCK = 64;
-struct ListSmem {
-    uint32_t *s; uint4 *g; int scap, total;
+template <int SCAP>
+struct ListRing {
+    uint32_t *s; uint4 *g; int total;
     __device__ __forceinline__ int cap() const { return total; }
-    __device__ __forceinline__ void get(int p, uint64_t &x0, uint64_t &x2, int &end) const
+    __device__ __forceinline__ static uint32_t pack(uint64_t x0, uint64_t x2, int end)
     {
-        if (p < scap) {
-            const uint32_t *e = s + p * 3 * SEED3_BLOCK;
-            const uint32_t a = e[0], b = e[SEED3_BLOCK], m = e[2 * SEED3_BLOCK];
-            x0 = (uint64_t)(m & 0xff) << 32 | a; x2 = (uint64_t)((m >> 8) & 0xff) << 32 | b; end = (int)(m >> 16);
+        return ((uint32_t)(x0 >> 32) & 0xff) | ((uint32_t)(x2 >> 32) & 0xff) << 8 | (uint32_t)end << 16;
+    }
+    __device__ __forceinline__ static void unpack(uint32_t a, uint32_t b, uint32_t m, uint64_t &x0, uint64_t &x2, int &end)
+    {
+        x0 = (uint64_t)(m & 0xff) << 32 | a; x2 = (uint64_t)((m >> 8) & 0xff) << 32 | b; end = (int)(m >> 16);
+    }
+    __device__ __forceinline__ void push(int p, uint64_t x0, uint64_t x2, int end)
+    {
+        uint32_t *e = s + (p & (SCAP - 1)) * 3 * SEED3_BLOCK;
+        if (p >= SCAP) g[p - SCAP] = make_uint4(e[0], e[SEED3_BLOCK], e[2 * SEED3_BLOCK], 0);
+        e[0] = (uint32_t)x0; e[SEED3_BLOCK] = (uint32_t)x2; e[2 * SEED3_BLOCK] = pack(x0, x2, end);
+    }
+    __device__ __forceinline__ void get(int p, int nf, uint64_t &x0, uint64_t &x2, int &end) const
+    {
+        if (p + SCAP >= nf) {
+            const uint32_t *e = s + (p & (SCAP - 1)) * 3 * SEED3_BLOCK;
+            unpack(e[0], e[SEED3_BLOCK], e[2 * SEED3_BLOCK], x0, x2, end);
         } else {
-            const uint4 v = g[p - scap];
-            x0 = (uint64_t)(v.z & 0xff) << 32 | v.x; x2 = (uint64_t)((v.z >> 8) & 0xff) << 32 | v.y; end = (int)(v.z >> 16);
+            const uint4 v = g[p];
+            unpack(v.x, v.y, v.z, x0, x2, end);
         }
     }
-    __device__ __forceinline__ void set(int p, uint64_t x0, uint64_t x2, int end)
+    __device__ __forceinline__ void set(int p, int nf, uint64_t x0, uint64_t x2, int end)
     {
-        const uint32_t m = (uint32_t)(x0 >> 32) & 0xff | ((uint32_t)(x2 >> 32) & 0xff) << 8 | (uint32_t)end << 16;
-        if (p < scap) {
-            uint32_t *e = s + p * 3 * SEED3_BLOCK;
-            e[0] = (uint32_t)x0; e[SEED3_BLOCK] = (uint32_t)x2; e[2 * SEED3_BLOCK] = m;
-        } else g[p - scap] = make_uint4((uint32_t)x0, (uint32_t)x2, m, 0);
+        if (p + SCAP >= nf) {
+            uint32_t *e = s + (p & (SCAP - 1)) * 3 * SEED3_BLOCK;
+            e[0] = (uint32_t)x0; e[SEED3_BLOCK] = (uint32_t)x2; e[2 * SEED3_BLOCK] = pack(x0, x2, end);
+        } else g[p] = make_uint4((uint32_t)x0, (uint32_t)x2, pack(x0, x2, end), 0);
     }
 };
 
-// Every lane runs one work item (item < n: passes 1+2 of read `item`; item >= n: pass 3 of read item - n) and pulls
-// the next from a global counter the moment it finishes; all lanes of the warp meet at the single extension site.
-__global__ void __launch_bounds__(SEED3_BLOCK, 12) k_seed3(Opt opt, IndexView ix, BatchDev B, const uint64_t *seq4, uint4 *spill, int scap, int ltotal,
+// Every lane runs one work item (item < n: passes 1+2 of read `item`; item >= n: pass 3 of read item - n). The warp
+// draws items 32 at a time from a global counter and hands them to its lanes as they finish; all lanes meet at the
+// single extension site.
+template <int SCAP, int MINB>
+__global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView ix, BatchDev B, const uint64_t *seq4, uint4 *spill, int ltotal,
                                                             int *next_item, int32_t *cnt_a, int32_t *cnt_b)
 {
     extern __shared__ uint32_t sm_list[];
-    Seeder3<BasesPacked, ListSmem> sm;
-    sm.L.s = sm_list + threadIdx.x; sm.L.scap = scap; sm.L.total = ltotal;
-    sm.L.g = spill + (size_t)(blockIdx.x * SEED3_BLOCK + threadIdx.x) * (size_t)(ltotal > scap ? ltotal - scap : 0);
-    sm.st = Seeder3<BasesPacked, ListSmem>::DONE; sm.err = 0; sm.n_out = 0;
-    int item = -1;
-    bool exhausted = false;
+    typedef Seeder3<BasesPacked, ListRing<SCAP>> Machine;
+    Machine sm;
+    sm.L.s = sm_list + threadIdx.x; sm.L.total = ltotal;
+    sm.L.g = spill + (size_t)(blockIdx.x * SEED3_BLOCK + threadIdx.x) * (size_t)ltotal;
+    sm.st = Machine::DONE; sm.err = 0; sm.n_out = 0;
+    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    const int n_items = 2 * B.n;
+    int item = -1, pool_next = 0, pool_end = 0;   // the warp's drawn items [pool_next, pool_end): same values in all lanes
+    bool dry = false;                              // the global counter has run out
     for (;;) {
-        bool need = false;
-        while (!need && !exhausted) {
-            if (sm.done()) {
-                if (item >= 0) {   // close the item that just finished
-                    const int r = item < B.n ? item : item - B.n;
-                    (item < B.n ? cnt_a : cnt_b)[r] = sm.n_out;
-                    if (sm.err) B.err[r] = sm.err;
-                }
-                item = atomicAdd(next_item, 1);
-                if (item >= 2 * B.n) { exhausted = true; item = -1; break; }
+        // ---- converged: close finished items, hand out new ones ----
+        const bool idle = sm.done();
+        if (idle && item >= 0) {
+            const int r = item < B.n ? item : item - B.n;
+            (item < B.n ? cnt_a : cnt_b)[r] = sm.n_out;
+            if (sm.err) B.err[r] = sm.err;
+            item = -1;
+        }
+        unsigned want = __ballot_sync(0xffffffffu, idle);
+        while (want) {
+            if (pool_next == pool_end) {
+                if (dry) break;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(next_item, 32);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                pool_next = min(base, n_items); pool_end = min(base + 32, n_items);
+                if (pool_next == pool_end) { dry = true; break; }
+            }
+            const int rank = __popc(want & lt_mask);
+            const bool take = idle && item < 0 && pool_next + rank < pool_end;
+            if (take) {
+                item = pool_next + rank;
+                sm.n_out = 0; sm.err = 0;
                 const int r = item < B.n ? item : item - B.n;
                 const uint32_t beg = B.seq_off[r];
                 const int len = (int)(B.seq_off[r + 1] - beg);
-                if (len < opt.min_seed_len) { item = -1; continue; }
-                sm.q.w = seq4 + (beg >> 4) + r; sm.q.widx = -1;
-                sm.init(opt, len, B.intv + (size_t)r * B.intv_cap, B.intv_cap, item >= B.n);
+                if (len >= opt.min_seed_len) {
+                    sm.q.open(seq4 + (beg >> 4) + r, len);
+                    sm.init(opt, len, B.intv + (size_t)r * B.intv_cap, B.intv_cap, item >= B.n);
+                }   // else: nothing to seed; the lane stays idle, closes the empty item and draws again next round
             }
-            need = sm.advance(ix);
+            const unsigned took = __ballot_sync(0xffffffffu, take);
+            pool_next += __popc(took);
+            want &= ~took;
         }
+        // ---- divergent: every lane runs its machine up to its next extension ----
+        const bool need = !sm.done() && sm.advance(opt, ix);
         __syncwarp();
-        if (!__any_sync(0xffffffffu, need)) break;
+        const unsigned busy = __ballot_sync(0xffffffffu, need || item >= 0);
+        if (!busy) break;
         if (need) {
             uint64_t xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
             fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
-            sm.consume(na, nb, sz);
+            sm.consume(opt, na, nb, sz);
         }
     }
 }
 
-// merges the two parts of every read's interval list, sorts it, and runs the tail of the stage (bwamem.c:269-283)
-__global__ void k_seed3_finish(Opt opt, BatchDev B, const int32_t *cnt_a, const int32_t *cnt_b)
+// One warp per read: merges the two parts of the read's interval list (front: item A, back: item B), sorts it by
+// `info` (rank by counting, one entry per lane) and runs the tail of the stage (bwamem.c:269-283).
+__global__ void __launch_bounds__(128) k_seed3_finish(Opt opt, BatchDev B, const int32_t *cnt_a, const int32_t *cnt_b)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
     if (r >= B.n) return;
     if (B.err[r]) return;
     Intv *mem = B.intv + (size_t)r * B.intv_cap;
-    const int n = seed3_merge_sort(mem, B.intv_cap, cnt_a[r], cnt_b[r]);
-    if (n < 0) { B.err[r] = ERR_INTV_OVERFLOW; return; }
-    seed_finish(opt, B, r, mem, n, 0);
+    const int na = cnt_a[r], nb = cnt_b[r], n = na + nb;
+    if (na + 2 * nb > B.intv_cap) { if (lane == 0) B.err[r] = ERR_INTV_OVERFLOW; return; }
+    if (n > 32) {   // long lists: the serial form
+        if (lane == 0) {
+            const int m = seed3_merge_sort(mem, B.intv_cap, na, nb);
+            seed_finish(opt, B, r, mem, m, 0);
+        }
+        return;
+    }
+    Intv v; v.x0 = v.x1 = v.x2 = 0; v.info = ~0ull;
+    if ((int)lane < n) v = mem[(int)lane < na ? (int)lane : B.intv_cap - 1 - ((int)lane - na)];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+        const uint64_t o = __shfl_sync(0xffffffffu, v.info, k);
+        rank += (o < v.info) || (o == v.info && k < (int)lane);
+    }
+    __syncwarp();
+    int cnt = 0; bool rep = false;
+    if ((int)lane < n) {
+        mem[rank] = v;
+        const int64_t step = v.x2 > (uint64_t)opt.max_occ ? (int64_t)(v.x2 / opt.max_occ) : 1;
+        const int64_t c = ((int64_t)v.x2 + step - 1) / step;
+        cnt = (int)(c < opt.max_occ ? c : opt.max_occ);
+        rep = v.x2 > (uint64_t)opt.max_occ;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const unsigned any_rep = __ballot_sync(0xffffffffu, rep);
+    if (any_rep) {   // repetitive intervals present: l_rep needs the sorted order (rare)
+        __syncwarp();
+        if (lane == 0) seed_finish(opt, B, r, mem, n, 0);
+    } else if (lane == 0) { B.n_intv[r] = n; B.l_rep[r] = 0; B.n_seed[r] = cnt; }
 }
 
 __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
@@ -544,11 +621,12 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const int seed_block = 64;
     const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)m.n_sm * 16 * seed_block);
     const bool seed_old = getenv("BSB_SEED_V1") || getenv("BSB_SEED_V2") || getenv("BSB_SEED_DYN");
-    const int s3_scap = 24, s3_total = max_len + 1, s3_blocks = m.n_sm * 12;
+    auto env_int = [](const char *k, int d) { const char *v = getenv(k); return v ? atoi(v) : d; };
+    const int s3_scap = env_int("BSB_S3_SCAP", 16), s3_total = max_len + 1, s3_bps = env_int("BSB_S3_BPS", 10), s3_blocks = m.n_sm * s3_bps;
     const uint32_t n_words = (uint32_t)(nb >> 4) + (uint32_t)n + 1;
     if (!seed_old && n) {
         m.d_seq4.ensure(n_words + 1);
-        m.d_spill.ensure((size_t)s3_blocks * SEED3_BLOCK * (size_t)std::max(s3_total - s3_scap, 0) + 1);
+        m.d_spill.ensure((size_t)s3_blocks * SEED3_BLOCK * (size_t)s3_total + 1);
         m.d_cnt_ab.ensure(2 * (size_t)n + 2);
         k_pack4<<<cdiv(n_words, 256), 256, 0, st>>>(B, m.d_seq4.p, n_words); ++m.launches;
         CK(cudaGetLastError());
@@ -567,9 +645,12 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
             ++m.launches;
         } else if (n) {
             CK(cudaMemsetAsync(m.d_cnt_ab.p, 0, 2 * (size_t)n * 4, st));
-            k_seed3<<<s3_blocks, SEED3_BLOCK, (size_t)SEED3_BLOCK * s3_scap * 12, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_scap, s3_total,
-                                                                                       m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n);
-            k_seed3_finish<<<cdiv(n, 128), 128, 0, st>>>(opt, B, m.d_cnt_ab.p, m.d_cnt_ab.p + n);
+            const size_t s3_smem = (size_t)SEED3_BLOCK * s3_scap * 12;
+#define BSB_S3_LAUNCH(SC, MB) k_seed3<SC, MB><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
+            if (s3_bps > 10) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 12); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 12); else BSB_S3_LAUNCH(16, 12); }
+            else { if (s3_scap == 8) BSB_S3_LAUNCH(8, 10); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 10); else BSB_S3_LAUNCH(16, 10); }
+#undef BSB_S3_LAUNCH
+            k_seed3_finish<<<cdiv((size_t)n * 32, 128), 128, 0, st>>>(opt, B, m.d_cnt_ab.p, m.d_cnt_ab.p + n);
             m.launches += 2;
         }
         CK(cudaGetLastError());

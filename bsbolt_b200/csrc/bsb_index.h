@@ -48,12 +48,11 @@ struct OccBlock { uint64_t cnt[4]; uint32_t w[8]; };
 BSB_HD void load_block(const uint32_t *bwt, uint64_t blk, OccBlock &b)
 {
 #if defined(__CUDA_ARCH__)
-    const uint4 *p = reinterpret_cast<const uint4 *>(bwt + (blk << 4));
-    uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
-    b.cnt[0] = (uint64_t)v0.y << 32 | v0.x; b.cnt[1] = (uint64_t)v0.w << 32 | v0.z;
-    b.cnt[2] = (uint64_t)v1.y << 32 | v1.x; b.cnt[3] = (uint64_t)v1.w << 32 | v1.z;
-    b.w[0] = v2.x; b.w[1] = v2.y; b.w[2] = v2.z; b.w[3] = v2.w;
-    b.w[4] = v3.x; b.w[5] = v3.y; b.w[6] = v3.z; b.w[7] = v3.w;
+    // two 256-bit loads (LDG.E.256, sm_100): header and packed symbols, each one 32-byte sector
+    const uint32_t *p = bwt + (blk << 4);
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(b.cnt[0]), "=l"(b.cnt[1]), "=l"(b.cnt[2]), "=l"(b.cnt[3]) : "l"(p));
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7]) : "l"(p + 8));
 #else
     const uint32_t *p = bwt + (blk << 4);
     for (int i = 0; i < 4; ++i) b.cnt[i] = (uint64_t)p[2 * i + 1] << 32 | p[2 * i];

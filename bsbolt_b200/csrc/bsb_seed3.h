@@ -21,44 +21,75 @@
 
 namespace bsb {
 
-// the extension both sweeps use: interval (xa = the coordinate on the strand being extended, xb = the other one,
-// s = size) by symbol c. Returns the new xa-side start, the new xb-side start and the new size.
-// Restates bwt_extend (bwt.c:262-275) for one output symbol.
-BSB_HD void fm_extend_one(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_t s, int c, uint64_t &na, uint64_t &nb, uint64_t &sz)
+// Counts, inside one occ block, of the symbols == c (E) and > c (G) among BWT[block start .. block start + r],
+// added to the block's cumulative counts. Same numbers bwt_occ4 (bwt.c:169-186) would give, but only the two
+// sums an extension by ONE symbol needs, computed branch-free from the two bit planes of the packed words.
+BSB_HD void block_occ_eg(const OccBlock &b, int r, int c, uint64_t &E, uint64_t &G)
 {
-    uint64_t tk[4], tl[4];
-    occ4_pair(ix, xa - 1, xa - 1 + s, tk, tl);
-    const uint64_t s0 = tl[0] - tk[0], s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
-    const uint64_t n3 = xb + (xa <= ix.primary && xa + s - 1 >= ix.primary);
-    const uint64_t n2 = n3 + s3, n1 = n2 + s2, n0 = n1 + s1;
-    na = sel4(c, ix.L2[0] + 1 + tk[0], ix.L2[1] + 1 + tk[1], ix.L2[2] + 1 + tk[2], ix.L2[3] + 1 + tk[3]);
-    nb = sel4(c, n0, n1, n2, n3);
-    sz = sel4(c, s0, s1, s2, s3);
+    const int nsym = r + 1;
+    const uint64_t MH = (c & 2) ? ~0ull : 0ull, ML = (c & 1) ? ~0ull : 0ull;
+    uint32_t e = 0, g = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t w = (uint64_t)b.w[2 * i] << 32 | b.w[2 * i + 1];
+        int k = nsym - 32 * i;
+        k = k < 0 ? 0 : k > 32 ? 32 : k;
+        uint64_t keep = k == 0 ? 0ull : (~0ull << ((32 - k) << 1));
+        keep &= 0x5555555555555555ull;
+        const uint64_t hi = w >> 1, lo = w;
+        const uint64_t same_hi = ~(hi ^ MH);
+        e += popc64(same_hi & ~(lo ^ ML) & keep);
+        g += popc64(((hi & ~MH) | (same_hi & lo & ~ML)) & keep);
+    }
+    uint64_t he = b.cnt[3], hg = 0;
+    he = c == 2 ? b.cnt[2] : he; he = c == 1 ? b.cnt[1] : he; he = c == 0 ? b.cnt[0] : he;
+    hg += c < 3 ? b.cnt[3] : 0; hg += c < 2 ? b.cnt[2] : 0; hg += c < 1 ? b.cnt[1] : 0;
+    E = he + e; G = hg + g;
 }
 
-// Bases: int get(int i) -> code 0..3, >3 ambiguous.   List: void get(int p, uint64_t &x0, uint64_t &x2, int &end),
-// void set(int p, uint64_t x0, uint64_t x2, int end), int cap().
+// the extension both sweeps use: interval (xa = the coordinate on the strand being extended, xb = the other one,
+// s = size) by symbol c. Returns the new xa-side start, the new xb-side start and the new size.
+// Restates bwt_extend (bwt.c:262-275) for one output symbol: with E(p) = occ(c, p) and G(p) = sum of occ(j, p), j > c,
+//   na = L2[c] + 1 + E(k),  size = E(l) - E(k),  nb = xb + [sentinel inside] + G(l) - G(k)     (k = xa - 1, l = k + s)
+BSB_HD void fm_extend_one(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_t s, int c, uint64_t &na, uint64_t &nb, uint64_t &sz)
+{
+    const uint64_t k = xa - 1, l = xa - 1 + s;
+    const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
+    const uint64_t _k = kz ? 0 : k - (k >= ix.primary), _l = lz ? 0 : l - (l >= ix.primary);
+    OccBlock bk, bl;
+    load_block(ix.bwt, _k >> 7, bk);
+    load_block(ix.bwt, _l >> 7, bl);
+    uint64_t ek, gk, el, gl;
+    block_occ_eg(bk, (int)(_k & 127), c, ek, gk);
+    block_occ_eg(bl, (int)(_l & 127), c, el, gl);
+    if (kz) ek = gk = 0;
+    if (lz) el = gl = 0;
+    na = ix.L2[c] + 1 + ek;
+    sz = el - ek;
+    nb = xb + (xa <= ix.primary && xa + s - 1 >= ix.primary) + (gl - gk);
+}
+
+// Bases: int get(int i) -> code 0..3, >3 ambiguous.
+// List: push(p, x0, x2, end) appends rank p during the forward sweep; get(p, nf, ...) / set(p, nf, ...) read and rewrite
+// rank p once the forward sweep has ended with nf entries (the device list keeps the top ranks in shared memory); cap().
 template <class Bases, class List>
 struct Seeder3 {
     enum St { NEXT, FWD, BWD_ROW, BWD_CELL, SMEM_END, P3, W_FWD, W_BWD, W_P3, DONE };
     Bases q; List L;
     Intv *out; int out_cap;          // this read's slice of the interval array: item A fills from the front, item B from the back
-    int len, min_seed_len, split_len, split_width, max_mem_intv;
+    int len;
     int st, pass, x, i, min_intv, ret, c, err;
-    uint64_t k0, k1, ks; int k_end;  // the interval being extended forward (x0, x1, size) and the end it reaches
+    uint64_t k0, k1, ks;             // the interval being extended forward (x0, x1, size); it ends at query position i
     int nf, pn, j, cn; uint64_t last_x2;   // list: nf entries after the forward sweep; current row = ranks nf-1 .. nf-pn
     uint64_t e0, e2; int e_end;      // the list entry whose backward extension is in flight
-    int m1_any, m1_start;            // bwt_smem1a's "mem->n == 0 || i + 1 < last start" test, without the list
+    int m1_start;                    // bwt_smem1a's "mem->n == 0 || i + 1 < last start" test, without the list (INT_MAX: none yet)
     int k2, old_n, n_out;
 
     BSB_HD void init(const Opt &o, int len_, Intv *out_, int out_cap_, bool item_b)
     {
         len = len_; out = out_; out_cap = out_cap_; n_out = 0; err = 0;
-        min_seed_len = o.min_seed_len; split_width = o.split_width;
-        split_len = (int)(o.min_seed_len * o.split_factor + .499);
-        max_mem_intv = (int)o.max_mem_intv;
         x = 0; i = -1; k2 = 0; old_n = 0;
-        if (item_b) { pass = 3; st = max_mem_intv > 0 ? P3 : DONE; }
+        if (item_b) { pass = 3; st = o.max_mem_intv > 0 ? P3 : DONE; }
         else { pass = 1; st = NEXT; }
     }
     BSB_HD bool done() const { return st == DONE; }
@@ -71,30 +102,30 @@ struct Seeder3 {
         out[pass == 3 ? out_cap - 1 - n_out : n_out] = v;
         ++n_out;
     }
-    BSB_HD void emit_if_new(uint64_t x0, uint64_t x2, int start, int end)
+    BSB_HD void emit_if_new(const Opt &o, uint64_t x0, uint64_t x2, int start, int end)
     {   // bwt.c:334-338 / 343-344 and the length filter of bwamem.c:130-133
-        if (m1_any && start >= m1_start) return;
-        m1_any = 1; m1_start = start;
-        if (end - start >= min_seed_len) emit(x0, x2, start, end);
+        if (start >= m1_start) return;
+        m1_start = start;
+        if (end - start >= o.min_seed_len) emit(x0, x2, start, end);
     }
     BSB_HD void push_fwd()
     {
         if (nf >= L.cap()) { err = ERR_INTV_OVERFLOW; return; }
-        L.set(nf, k0, ks, k_end); ++nf; ret = k_end;
+        L.push(nf, k0, ks, i); ++nf; ret = i;
     }
     BSB_HD void begin_bwd() { pn = nf; i = x - 1; st = BWD_ROW; }
     BSB_HD void start_smem(const IndexView &ix, int x_, int min_intv_)
     {   // head of bwt_smem1a; caller guarantees q[x_] < 4
         x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_;
-        m1_any = 0; m1_start = 0; nf = 0; ret = x + 1;
+        m1_start = 0x7fffffff; nf = 0; ret = x + 1;
         const int b = q.get(x);
-        k0 = ix.L2[b] + 1; ks = ix.L2[b + 1] - ix.L2[b]; k1 = ix.L2[3 - b] + 1; k_end = x + 1;
+        k0 = ix.L2[b] + 1; ks = ix.L2[b + 1] - ix.L2[b]; k1 = ix.L2[3 - b] + 1;
         i = x + 1;
         st = FWD;
     }
 
     // Runs until this lane needs an FM-index extension (true; operands via request()) or has finished (false).
-    BSB_HD bool advance(const IndexView &ix)
+    BSB_HD bool advance(const Opt &o, const IndexView &ix)
     {
         for (;;) {
             switch (st) {
@@ -105,10 +136,11 @@ struct Seeder3 {
                     start_smem(ix, x, 1);
                 } else {
                     bool started = false;
+                    const int split_len = (int)(o.min_seed_len * o.split_factor + .499);
                     while (k2 < old_n) {
                         const uint64_t info = out[k2].info, occ = out[k2].x2;
                         const int start = (int)(info >> 32), end = (int32_t)info;
-                        if (end - start < split_len || occ > (uint64_t)split_width) { ++k2; continue; }
+                        if (end - start < split_len || occ > (uint64_t)o.split_width) { ++k2; continue; }
                         const int xm = (start + end) >> 1;
                         if (q.get(xm) > 3) { ++k2; continue; }      // bwt_smem1a returns at once on an ambiguous base
                         start_smem(ix, xm, (int)(occ + 1));
@@ -128,8 +160,8 @@ struct Seeder3 {
             case BWD_ROW:
                 if (i >= 0) c = q.get(i);
                 if (i < 0 || c > 3) {          // nothing can be extended: only the longest entry can be a new SMEM
-                    L.get(nf - 1, e0, e2, e_end);
-                    emit_if_new(e0, e2, i + 1, e_end);
+                    L.get(nf - 1, nf, e0, e2, e_end);
+                    emit_if_new(o, e0, e2, i + 1, e_end);
                     st = SMEM_END;
                 } else { j = 0; cn = 0; st = BWD_CELL; }
                 break;
@@ -137,7 +169,7 @@ struct Seeder3 {
                 if (j >= pn) {
                     if (cn == 0) st = SMEM_END;
                     else { pn = cn; --i; st = BWD_ROW; }
-                } else { L.get(nf - 1 - j, e0, e2, e_end); st = W_BWD; return true; }
+                } else { L.get(nf - 1 - j, nf, e0, e2, e_end); st = W_BWD; return true; }
                 break;
             case SMEM_END:
                 if (pass == 1) x = ret; else ++k2;
@@ -169,26 +201,26 @@ struct Seeder3 {
         if (st == W_BWD) { xa = e0; xb = 0; s = e2; } else { xa = k1; xb = k0; s = ks; }
     }
 
-    BSB_HD void consume(uint64_t na, uint64_t nb, uint64_t sz)
+    BSB_HD void consume(const Opt &o, uint64_t na, uint64_t nb, uint64_t sz)
     {
         if (st == W_FWD) {
             if (sz != ks) {
                 push_fwd();
                 if (sz < (uint64_t)min_intv) { begin_bwd(); return; }
             }
-            k1 = na; k0 = nb; ks = sz; k_end = i + 1;
+            k1 = na; k0 = nb; ks = sz;
             ++i;
             st = FWD;
         } else if (st == W_BWD) {
             if (sz < (uint64_t)min_intv) {
-                if (cn == 0) emit_if_new(e0, e2, i + 1, e_end);
+                if (cn == 0) emit_if_new(o, e0, e2, i + 1, e_end);
             } else if (cn == 0 || sz != last_x2) {
-                L.set(nf - 1 - cn, na, sz, e_end); ++cn; last_x2 = sz;
+                L.set(nf - 1 - cn, nf, na, sz, e_end); ++cn; last_x2 = sz;
             }
             ++j;
             st = BWD_CELL;
         } else { // W_P3
-            if (sz < (uint64_t)max_mem_intv && i - x >= min_seed_len) {
+            if (sz < o.max_mem_intv && i - x >= o.min_seed_len) {
                 if (sz > 0) emit(nb, sz, x, i + 1);
                 x = i + 1; i = -1;
             } else { k1 = na; k0 = nb; ks = sz; ++i; }
@@ -218,8 +250,9 @@ struct BasesBytes { const uint8_t *p; BSB_HD int get(int i) const { return p[i];
 struct ListPlain {
     uint64_t *a0, *a2; int *ae; int n;
     BSB_HD int cap() const { return n; }
-    BSB_HD void get(int p, uint64_t &x0, uint64_t &x2, int &end) const { x0 = a0[p]; x2 = a2[p]; end = ae[p]; }
-    BSB_HD void set(int p, uint64_t x0, uint64_t x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
+    BSB_HD void get(int p, int, uint64_t &x0, uint64_t &x2, int &end) const { x0 = a0[p]; x2 = a2[p]; end = ae[p]; }
+    BSB_HD void set(int p, int, uint64_t x0, uint64_t x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
+    BSB_HD void push(int p, uint64_t x0, uint64_t x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
 };
 
 // collect_intv() through the two work items, one after the other (what the kernel does on two lanes)
@@ -231,11 +264,11 @@ BSB_HD int collect_intv_v3(const Opt &opt, const IndexView &ix, int len, Bases q
         Seeder3<Bases, List> sm;
         sm.q = q; sm.L = L;
         sm.init(opt, len, mem, cap, item == 1);
-        while (sm.advance(ix)) {
+        while (sm.advance(opt, ix)) {
             uint64_t xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
             fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
-            sm.consume(na, nb, sz);
+            sm.consume(opt, na, nb, sz);
         }
         if (sm.err) *err = sm.err;
         n_part[item] = sm.n_out;
