@@ -205,7 +205,7 @@ struct ListRing {
 // Every lane runs one work item (item < n: passes 1+2 of read `item`; item >= n: pass 3 of read item - n). The warp
 // draws items 32 at a time from a global counter and hands them to its lanes as they finish; all lanes meet at the
 // single extension site.
-template <int SCAP, int MINB>
+template <int SCAP, int MINB, bool COMPACT>
 __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView ix, BatchDev B, const uint64_t *seq4, uint4 *spill, int ltotal,
                                                             int *next_item, int32_t *cnt_a, int32_t *cnt_b)
 {
@@ -263,10 +263,22 @@ __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView 
         if (need) {
             uint64_t xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
-            fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
+            if (COMPACT) fm_extend_one32(ix, xa, xb, s, sm.c, na, nb, sz);
+            else fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
             sm.consume(opt, na, nb, sz);
         }
     }
+}
+
+// index-load time: the sector-sized occ blocks (bsb_index.h) from the reference-layout BWT
+__global__ void k_make_occ32(const uint32_t *bwt, uint64_t n_blocks32, uint32_t *occ32)
+{
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks32) return;
+    uint32_t o[8];
+    occ32_make_block(bwt, b, o);
+    uint4 *dst = reinterpret_cast<uint4 *>(occ32 + b * 8);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]); dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 // One warp per read: merges the two parts of the read's interval list (front: item A, back: item B), sorts it by
@@ -490,7 +502,7 @@ struct CudaAligner::Impl {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[12];   // 0..9 stage boundaries, 10 = selection kernel done
     // resident index
-    DevBuf<uint32_t> d_bwt, d_sa32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
+    DevBuf<uint32_t> d_bwt, d_sa32, d_occ32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
     IndexView ix;
     // batch buffers
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
@@ -538,7 +550,16 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     m.d_anns.ensure(idx.anns.size()); CK(cudaMemcpy(m.d_anns.p, idx.anns.data(), idx.anns.size() * sizeof(Ann), cudaMemcpyHostToDevice));
     m.ix = idx.host_view();
     m.ix.bwt = m.d_bwt.p; m.ix.sa = m.d_sa.p; m.ix.pac = m.d_pac.p; m.ix.opac = m.d_opac.p; m.ix.anns = m.d_anns.p;
-    m.ix.sa32 = nullptr; m.ix.sa32_intv = 0;
+    m.ix.sa32 = nullptr; m.ix.sa32_intv = 0; m.ix.occ32 = nullptr;
+    if (idx.seq_len + 1 < (1ull << 32) && !getenv("BSB_REF_BLOCKS")) {   // sector-sized occ blocks for seeding
+        const uint64_t nb32 = (uint64_t)(idx.bwt.size() / 16) * 2;
+        m.d_occ32.ensure(nb32 * 8);
+        k_make_occ32<<<(unsigned)((nb32 + 255) / 256), 256>>>(m.d_bwt.p, nb32, m.d_occ32.p);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        m.ix.occ32 = m.d_occ32.p;
+        ++m.launches;
+    }
     if (idx.seq_len + 1 < (1ull << 32) && !getenv("BSB_SAMPLED_SA")) { // full SA resident in HBM (4 B/rank)
         m.d_sa32.ensure(idx.seq_len + 1);
         k_dense_sa<<<(unsigned)((idx.n_sa + 127) / 128), 128>>>(m.ix, idx.n_sa, m.d_sa32.p);
@@ -567,7 +588,7 @@ int CudaAligner::device() const { return im_->device; }
 size_t CudaAligner::index_bytes() const
 {
     const Impl &m = *im_;
-    return m.d_bwt.cap * 4 + m.d_sa.cap * 8 + m.d_sa32.cap * 4 + m.d_pac.cap + m.d_opac.cap;
+    return m.d_bwt.cap * 4 + m.d_occ32.cap * 4 + m.d_sa.cap * 8 + m.d_sa32.cap * 4 + m.d_pac.cap + m.d_opac.cap;
 }
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -622,7 +643,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)m.n_sm * 16 * seed_block);
     const bool seed_old = getenv("BSB_SEED_V1") || getenv("BSB_SEED_V2") || getenv("BSB_SEED_DYN");
     auto env_int = [](const char *k, int d) { const char *v = getenv(k); return v ? atoi(v) : d; };
-    const int s3_scap = env_int("BSB_S3_SCAP", 16), s3_total = max_len + 1, s3_bps = env_int("BSB_S3_BPS", 10), s3_blocks = m.n_sm * s3_bps;
+    const int s3_scap = m.ix.occ32 ? env_int("BSB_S3_SCAP", 16) : 16, s3_total = max_len + 1, s3_bps = env_int("BSB_S3_BPS", m.ix.occ32 ? 12 : 10), s3_blocks = m.n_sm * s3_bps;
     const uint32_t n_words = (uint32_t)(nb >> 4) + (uint32_t)n + 1;
     if (!seed_old && n) {
         m.d_seq4.ensure(n_words + 1);
@@ -646,9 +667,10 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         } else if (n) {
             CK(cudaMemsetAsync(m.d_cnt_ab.p, 0, 2 * (size_t)n * 4, st));
             const size_t s3_smem = (size_t)SEED3_BLOCK * s3_scap * 12;
-#define BSB_S3_LAUNCH(SC, MB) k_seed3<SC, MB><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
-            if (s3_bps > 10) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 12); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 12); else BSB_S3_LAUNCH(16, 12); }
-            else { if (s3_scap == 8) BSB_S3_LAUNCH(8, 10); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 10); else BSB_S3_LAUNCH(16, 10); }
+#define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
+            if (!m.ix.occ32) BSB_S3_LAUNCH(16, 10, false);       // >= 2^32-symbol index: reference block layout
+            else if (s3_bps > 10) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 12, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 12, true); else BSB_S3_LAUNCH(16, 12, true); }
+            else { if (s3_scap == 8) BSB_S3_LAUNCH(8, 10, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 10, true); else BSB_S3_LAUNCH(16, 10, true); }
 #undef BSB_S3_LAUNCH
             k_seed3_finish<<<cdiv((size_t)n * 32, 128), 128, 0, st>>>(opt, B, m.d_cnt_ab.p, m.d_cnt_ab.p + n);
             m.launches += 2;

@@ -23,6 +23,9 @@ struct IndexView {
     // optional result-preserving denser SA (values are independent of the sampling rate)
     const uint32_t *sa32;   // when non-null: SA sampled every sa32_intv ranks, 32-bit entries (seq_len < 2^32)
     int32_t sa32_intv, pad_;
+    // optional sector-sized occ blocks (seq_len < 2^32): one 32-byte block per 64 BWT symbols = 4 x u32 cumulative
+    // counts + 4 packed words, so that one rank query is ONE 32-byte sector and one 256-bit load (occ32_* below)
+    const uint32_t *occ32;
 };
 
 // ---- occurrence counting -------------------------------------------------------------------
@@ -169,6 +172,87 @@ BSB_HD void fm_set_intv(const IndexView &ix, int c, Intv &ik)
     ik.x2 = ix.L2[c + 1] - ix.L2[c];
     ik.x1 = ix.L2[3 - c] + 1;
     ik.info = 0;
+}
+
+// ---- sector-sized occ blocks -----------------------------------------------------------------
+// Same BWT, same counts as the reference blocks (bwt.h:72-78), re-cut at index load: block b32 covers symbols
+// [64*b32, 64*b32 + 64); its counts are the reference block's, plus the first 64 symbols of that block for odd b32.
+BSB_HD void occ32_make_block(const uint32_t *bwt, uint64_t b32, uint32_t out[8])
+{
+    const uint32_t *p = bwt + ((b32 >> 1) << 4);
+    uint64_t cnt[4];
+    for (int j = 0; j < 4; ++j) cnt[j] = (uint64_t)p[2 * j + 1] << 32 | p[2 * j];
+    const int half = (int)(b32 & 1);
+    if (half)
+        for (int i = 0; i < 4; ++i)
+            for (int c = 0; c < 4; ++c) cnt[c] += (uint64_t)popc32(sym_eq_mask(p[8 + i], c));
+    for (int j = 0; j < 4; ++j) out[j] = (uint32_t)cnt[j];
+    for (int i = 0; i < 4; ++i) out[4 + i] = p[8 + 4 * half + i];
+}
+
+struct Occ32 { uint32_t cnt[4], w[4]; };
+
+BSB_HD void occ32_load(const uint32_t *occ32, uint64_t blk, Occ32 &b)
+{
+    const uint32_t *p = occ32 + (blk << 3);
+#if defined(__CUDA_ARCH__)
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(b.cnt[0]), "=r"(b.cnt[1]), "=r"(b.cnt[2]), "=r"(b.cnt[3]), "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]) : "l"(p));
+#else
+    for (int i = 0; i < 4; ++i) { b.cnt[i] = p[i]; b.w[i] = p[4 + i]; }
+#endif
+}
+
+// mask of the first k (0..16) symbols of a packed word, at the low bit of each symbol
+BSB_HD uint32_t occ32_keep(int k)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(0u, 0x55555555u, (unsigned)(2 * k));
+#else
+    return k == 0 ? 0u : 0x55555555u << (32 - 2 * k);
+#endif
+}
+
+// E = occ(c, p), G = sum of occ(j, p) over j > c, for the position p = 64*blk + r of block b. With P1/P2/P3 = number
+// of symbols >= 1 / >= 2 / >= 3 among the first r+1 of the block: symbols >= t form the sequence (r+1, P1, P2, P3, 0).
+BSB_HD void occ32_eg(const Occ32 &b, int r, int c, uint32_t &E, uint32_t &G)
+{
+    const int nsym = r + 1;
+    uint32_t a[4], h[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int k = nsym - 16 * i;
+        k = k < 0 ? 0 : k > 16 ? 16 : k;
+        const uint32_t keep = occ32_keep(k), hi = b.w[i] >> 1, lo = b.w[i];
+        a[i] = (hi | lo) & keep; h[i] = hi & keep; d[i] = hi & lo & keep;
+    }
+    const uint32_t P1 = popc32(a[0] | a[1] << 1) + popc32(a[2] | a[3] << 1);
+    const uint32_t P2 = popc32(h[0] | h[1] << 1) + popc32(h[2] | h[3] << 1);
+    const uint32_t P3 = popc32(d[0] | d[1] << 1) + popc32(d[2] | d[3] << 1);
+    uint32_t ge_c = (uint32_t)nsym, ge_c1 = P1, he = b.cnt[0], hg = b.cnt[1] + b.cnt[2] + b.cnt[3];
+    if (c >= 1) { ge_c = P1; ge_c1 = P2; he = b.cnt[1]; hg = b.cnt[2] + b.cnt[3]; }
+    if (c >= 2) { ge_c = P2; ge_c1 = P3; he = b.cnt[2]; hg = b.cnt[3]; }
+    if (c >= 3) { ge_c = P3; ge_c1 = 0; he = b.cnt[3]; hg = 0; }
+    E = he + ge_c - ge_c1; G = hg + ge_c1;
+}
+
+// fm_extend_one (bsb_seed3.h) over the sector-sized blocks; all coordinates < 2^32
+BSB_HD void fm_extend_one32(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_t s, int c, uint64_t &na, uint64_t &nb, uint64_t &sz)
+{
+    const uint64_t k = xa - 1, l = xa - 1 + s;
+    const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
+    const uint64_t _k = kz ? 0 : k - (k >= ix.primary), _l = lz ? 0 : l - (l >= ix.primary);
+    Occ32 bk, bl;
+    occ32_load(ix.occ32, _k >> 6, bk);
+    occ32_load(ix.occ32, _l >> 6, bl);
+    uint32_t ek, gk, el, gl;
+    occ32_eg(bk, (int)(_k & 63), c, ek, gk);
+    occ32_eg(bl, (int)(_l & 63), c, el, gl);
+    if (kz) ek = gk = 0;
+    if (lz) el = gl = 0;
+    na = ix.L2[c] + 1 + ek;
+    sz = (uint64_t)(el - ek);
+    nb = xb + (xa <= ix.primary && xa + s - 1 >= ix.primary) + (uint64_t)(gl - gk);
 }
 
 // ---- suffix-array lookup -------------------------------------------------------------------

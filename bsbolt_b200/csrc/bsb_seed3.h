@@ -267,7 +267,8 @@ BSB_HD int collect_intv_v3(const Opt &opt, const IndexView &ix, int len, Bases q
         while (sm.advance(opt, ix)) {
             uint64_t xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
-            fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
+            if (ix.occ32) fm_extend_one32(ix, xa, xb, s, sm.c, na, nb, sz);
+            else fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
             sm.consume(opt, na, nb, sz);
         }
         if (sm.err) *err = sm.err;

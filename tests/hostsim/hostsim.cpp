@@ -18,7 +18,16 @@ using namespace bsb;
 
 class HostSimAligner : public BatchAligner {
 public:
-    explicit HostSimAligner(const HostIndex &idx) : idx_(idx), ix_(idx.host_view()) { build_log_table(log_tab_, 65536); }
+    explicit HostSimAligner(const HostIndex &idx) : idx_(idx), ix_(idx.host_view())
+    {
+        build_log_table(log_tab_, 65536);
+        if (getenv("BSB_HOSTSIM_SEED_V3") && !getenv("BSB_HOSTSIM_REF_BLOCKS") && idx.seq_len + 1 < (1ull << 32)) {
+            const uint64_t nb32 = (uint64_t)(idx.bwt.size() / 16) * 2;   // the product's sector-sized occ blocks
+            occ32_.resize(nb32 * 8);
+            for (uint64_t b = 0; b < nb32; ++b) occ32_make_block(idx.bwt.data(), b, occ32_.data() + b * 8);
+            ix_.occ32 = occ32_.data();
+        }
+    }
 
     void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out) override
     {
@@ -143,6 +152,7 @@ private:
     const HostIndex &idx_;
     IndexView ix_;
     std::vector<double> log_tab_;
+    std::vector<uint32_t> occ32_;
 };
 
 int main(int argc, char **argv)

@@ -72,10 +72,12 @@ def test_c2_pe150_directional_with_rescue(big, tmp_path):
 
 
 def test_c2_sampled_suffix_array_layout(big, tmp_path):
-    """BSB_SAMPLED_SA keeps the reference's SA layout (every 32nd rank, u64) and LF-walks on the device."""
+    """The configuration a >= 2^32-symbol index (C4) runs with: BSB_SAMPLED_SA keeps the reference's SA layout (every
+    32nd rank, u64, LF-walk on the device) and BSB_REF_BLOCKS seeds over the reference's 64-byte occ blocks with 64-bit
+    counts instead of the sector-sized 32-bit ones."""
     from bsbolt_b200 import simulate
     fqs, n = simulate.simulate_reads(big.names, big.contigs, str(tmp_path / 'pe'), 15000, seed=12, corrupt_frac=0.02)
-    both(big, ['-K', '100000000', '-t', '16'], fqs, tmp_path, env={'BSB_SAMPLED_SA': '1'})
+    both(big, ['-K', '100000000', '-t', '16'], fqs, tmp_path, env={'BSB_SAMPLED_SA': '1', 'BSB_REF_BLOCKS': '1'})
 
 
 def test_c5_undirectional_pe150(big, tmp_path):
