@@ -169,21 +169,25 @@ template <int SCAP>
 struct ListRing {
     uint32_t *s; uint4 *g; int total;
     __device__ __forceinline__ int cap() const { return total; }
-    __device__ __forceinline__ static uint32_t pack(uint64_t x0, uint64_t x2, int end)
+    template <class U> __device__ __forceinline__ static uint32_t pack(U x0, U x2, int end)
     {
-        return ((uint32_t)(x0 >> 32) & 0xff) | ((uint32_t)(x2 >> 32) & 0xff) << 8 | (uint32_t)end << 16;
+        uint32_t m = (uint32_t)end << 16;
+        if (sizeof(U) == 8) m |= ((uint32_t)((uint64_t)x0 >> 32) & 0xff) | ((uint32_t)((uint64_t)x2 >> 32) & 0xff) << 8;
+        return m;
     }
-    __device__ __forceinline__ static void unpack(uint32_t a, uint32_t b, uint32_t m, uint64_t &x0, uint64_t &x2, int &end)
+    template <class U> __device__ __forceinline__ static void unpack(uint32_t a, uint32_t b, uint32_t m, U &x0, U &x2, int &end)
     {
-        x0 = (uint64_t)(m & 0xff) << 32 | a; x2 = (uint64_t)((m >> 8) & 0xff) << 32 | b; end = (int)(m >> 16);
+        if (sizeof(U) == 8) { x0 = (U)((uint64_t)(m & 0xff) << 32 | a); x2 = (U)((uint64_t)((m >> 8) & 0xff) << 32 | b); }
+        else { x0 = (U)a; x2 = (U)b; }
+        end = (int)(m >> 16);
     }
-    __device__ __forceinline__ void push(int p, uint64_t x0, uint64_t x2, int end)
+    template <class U> __device__ __forceinline__ void push(int p, U x0, U x2, int end)
     {
         uint32_t *e = s + (p & (SCAP - 1)) * 3 * SEED3_BLOCK;
         if (p >= SCAP) g[p - SCAP] = make_uint4(e[0], e[SEED3_BLOCK], e[2 * SEED3_BLOCK], 0);
         e[0] = (uint32_t)x0; e[SEED3_BLOCK] = (uint32_t)x2; e[2 * SEED3_BLOCK] = pack(x0, x2, end);
     }
-    __device__ __forceinline__ void get(int p, int nf, uint64_t &x0, uint64_t &x2, int &end) const
+    template <class U> __device__ __forceinline__ void get(int p, int nf, U &x0, U &x2, int &end) const
     {
         if (p + SCAP >= nf) {
             const uint32_t *e = s + (p & (SCAP - 1)) * 3 * SEED3_BLOCK;
@@ -193,7 +197,7 @@ struct ListRing {
             unpack(v.x, v.y, v.z, x0, x2, end);
         }
     }
-    __device__ __forceinline__ void set(int p, int nf, uint64_t x0, uint64_t x2, int end)
+    template <class U> __device__ __forceinline__ void set(int p, int nf, U x0, U x2, int end)
     {
         if (p + SCAP >= nf) {
             uint32_t *e = s + (p & (SCAP - 1)) * 3 * SEED3_BLOCK;
@@ -202,15 +206,19 @@ struct ListRing {
     }
 };
 
+template <bool COMPACT> struct SeedCoord { typedef uint64_t type; };
+template <> struct SeedCoord<true> { typedef uint32_t type; };
+
 // Every lane runs one work item (item < n: passes 1+2 of read `item`; item >= n: pass 3 of read item - n). The warp
 // draws items 32 at a time from a global counter and hands them to its lanes as they finish; all lanes meet at the
-// single extension site.
+// single extension site. COMPACT: sector-sized occ blocks and 32-bit coordinates (index < 2^32 symbols).
 template <int SCAP, int MINB, bool COMPACT>
 __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView ix, BatchDev B, const uint64_t *seq4, uint4 *spill, int ltotal,
-                                                            int *next_item, int32_t *cnt_a, int32_t *cnt_b)
+                                                              int *next_item, int32_t *cnt_a, int32_t *cnt_b)
 {
     extern __shared__ uint32_t sm_list[];
-    typedef Seeder3<BasesPacked, ListRing<SCAP>> Machine;
+    typedef typename SeedCoord<COMPACT>::type U;
+    typedef Seeder3<BasesPacked, ListRing<SCAP>, U> Machine;
     Machine sm;
     sm.L.s = sm_list + threadIdx.x; sm.L.total = ltotal;
     sm.L.g = spill + (size_t)(blockIdx.x * SEED3_BLOCK + threadIdx.x) * (size_t)ltotal;
@@ -219,9 +227,10 @@ __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView 
     const int n_items = 2 * B.n;
     int item = -1, pool_next = 0, pool_end = 0;   // the warp's drawn items [pool_next, pool_end): same values in all lanes
     bool dry = false;                              // the global counter has run out
+    bool need = false;                             // this lane has an extension pending
     for (;;) {
         // ---- converged: close finished items, hand out new ones ----
-        const bool idle = sm.done();
+        const bool idle = !need;
         if (idle && item >= 0) {
             const int r = item < B.n ? item : item - B.n;
             (item < B.n ? cnt_a : cnt_b)[r] = sm.n_out;
@@ -249,24 +258,23 @@ __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView 
                 if (len >= opt.min_seed_len) {
                     sm.q.open(seq4 + (beg >> 4) + r, len);
                     sm.init(opt, len, B.intv + (size_t)r * B.intv_cap, B.intv_cap, item >= B.n);
-                }   // else: nothing to seed; the lane stays idle, closes the empty item and draws again next round
+                    need = sm.advance(opt, ix);
+                }   // else: nothing to seed; the lane closes the empty item and draws again next round
             }
             const unsigned took = __ballot_sync(0xffffffffu, take);
             pool_next += __popc(took);
             want &= ~took;
         }
-        // ---- divergent: every lane runs its machine up to its next extension ----
-        const bool need = !sm.done() && sm.advance(opt, ix);
-        __syncwarp();
         const unsigned busy = __ballot_sync(0xffffffffu, need || item >= 0);
         if (!busy) break;
+        // ---- the one extension site, then every lane runs its machine up to its next extension ----
         if (need) {
-            uint64_t xa, xb, s, na, nb, sz;
+            U xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
-            if (COMPACT) fm_extend_one32(ix, xa, xb, s, sm.c, na, nb, sz);
-            else fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
-            sm.consume(opt, na, nb, sz);
+            fm_extend_any(ix, xa, xb, s, sm.c, na, nb, sz);
+            need = sm.step(opt, ix, na, nb, sz);
         }
+        __syncwarp();
     }
 }
 
@@ -282,45 +290,66 @@ __global__ void k_make_occ32(const uint32_t *bwt, uint64_t n_blocks32, uint32_t 
 }
 
 // One warp per read: merges the two parts of the read's interval list (front: item A, back: item B), sorts it by
-// `info` (rank by counting, one entry per lane) and runs the tail of the stage (bwamem.c:269-283).
+// `info` (rank by counting; up to four entries per lane, keys staged in shared memory) and runs the tail of the stage
+// (bwamem.c:269-283): seed count, and l_rep = length of the union of the repetitive intervals (a bitmap per warp).
+constexpr int FIN_MAX = 128, FIN_WORDS = 24;   // entries handled in registers; bitmap words (reads <= 768 bp)
 __global__ void __launch_bounds__(128) k_seed3_finish(Opt opt, BatchDev B, const int32_t *cnt_a, const int32_t *cnt_b)
 {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned lane = threadIdx.x & 31;
+    __shared__ uint64_t s_keys[4][FIN_MAX];
+    __shared__ uint32_t s_cov[4][FIN_WORDS];
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= B.n) return;
     if (B.err[r]) return;
     Intv *mem = B.intv + (size_t)r * B.intv_cap;
     const int na = cnt_a[r], nb = cnt_b[r], n = na + nb;
     if (na + 2 * nb > B.intv_cap) { if (lane == 0) B.err[r] = ERR_INTV_OVERFLOW; return; }
-    if (n > 32) {   // long lists: the serial form
+    const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+    if (n > FIN_MAX || len > FIN_WORDS * 32) {   // very long lists / reads: the serial form
         if (lane == 0) {
             const int m = seed3_merge_sort(mem, B.intv_cap, na, nb);
             seed_finish(opt, B, r, mem, m, 0);
         }
         return;
     }
-    Intv v; v.x0 = v.x1 = v.x2 = 0; v.info = ~0ull;
-    if ((int)lane < n) v = mem[(int)lane < na ? (int)lane : B.intv_cap - 1 - ((int)lane - na)];
-    int rank = 0;
-    for (int k = 0; k < n; ++k) {
-        const uint64_t o = __shfl_sync(0xffffffffu, v.info, k);
-        rank += (o < v.info) || (o == v.info && k < (int)lane);
+    uint64_t *keys = s_keys[wib];
+    uint32_t *cov = s_cov[wib];
+    Intv v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = lane + 32 * q;
+        if (e < n) { v[q] = mem[e < na ? e : B.intv_cap - 1 - (e - na)]; keys[e] = v[q].info; }
+    }
+    if (lane < FIN_WORDS) cov[lane] = 0;
+    __syncwarp();
+    int rank[4] = {0, 0, 0, 0};
+    for (int f = 0; f < n; ++f) {
+        const uint64_t o = keys[f];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rank[q] += (o < v[q].info) || (o == v[q].info && f < lane + 32 * q);
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (lane + 32 * q < n) {
+            mem[rank[q]] = v[q];
+            const uint64_t occ = v[q].x2;
+            if (occ > (uint64_t)opt.max_occ) {   // repetitive interval: at most max_occ of its hits, its span counts towards l_rep
+                const int64_t step = (int64_t)(occ / opt.max_occ);
+                const int64_t c = ((int64_t)occ + step - 1) / step;
+                cnt += (int)(c < opt.max_occ ? c : opt.max_occ);
+                const int sb = (int)(v[q].info >> 32), se = (int)(uint32_t)v[q].info;
+                for (int w = sb >> 5; w <= (se - 1) >> 5 && se > sb; ++w) {
+                    const int lo = max(sb - 32 * w, 0), hi = min(se - 32 * w, 32);
+                    atomicOr(&cov[w], (hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u));
+                }
+            } else cnt += (int)occ;
+        }
     }
     __syncwarp();
-    int cnt = 0; bool rep = false;
-    if ((int)lane < n) {
-        mem[rank] = v;
-        const int64_t step = v.x2 > (uint64_t)opt.max_occ ? (int64_t)(v.x2 / opt.max_occ) : 1;
-        const int64_t c = ((int64_t)v.x2 + step - 1) / step;
-        cnt = (int)(c < opt.max_occ ? c : opt.max_occ);
-        rep = v.x2 > (uint64_t)opt.max_occ;
-    }
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    const unsigned any_rep = __ballot_sync(0xffffffffu, rep);
-    if (any_rep) {   // repetitive intervals present: l_rep needs the sorted order (rare)
-        __syncwarp();
-        if (lane == 0) seed_finish(opt, B, r, mem, n, 0);
-    } else if (lane == 0) { B.n_intv[r] = n; B.l_rep[r] = 0; B.n_seed[r] = cnt; }
+    int l_rep = lane < FIN_WORDS ? __popc(cov[lane]) : 0;
+    for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); l_rep += __shfl_xor_sync(0xffffffffu, l_rep, o); }
+    if (lane == 0) { B.n_intv[r] = n; B.l_rep[r] = l_rep; B.n_seed[r] = cnt; }
 }
 
 __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
@@ -669,6 +698,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
             const size_t s3_smem = (size_t)SEED3_BLOCK * s3_scap * 12;
 #define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
             if (!m.ix.occ32) BSB_S3_LAUNCH(16, 10, false);       // >= 2^32-symbol index: reference block layout
+            else if (s3_bps > 12) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 16, true); else BSB_S3_LAUNCH(16, 16, true); }
             else if (s3_bps > 10) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 12, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 12, true); else BSB_S3_LAUNCH(16, 12, true); }
             else { if (s3_scap == 8) BSB_S3_LAUNCH(8, 10, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 10, true); else BSB_S3_LAUNCH(16, 10, true); }
 #undef BSB_S3_LAUNCH

@@ -236,12 +236,13 @@ BSB_HD void occ32_eg(const Occ32 &b, int r, int c, uint32_t &E, uint32_t &G)
     E = he + ge_c - ge_c1; G = hg + ge_c1;
 }
 
-// fm_extend_one (bsb_seed3.h) over the sector-sized blocks; all coordinates < 2^32
-BSB_HD void fm_extend_one32(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_t s, int c, uint64_t &na, uint64_t &nb, uint64_t &sz)
+// fm_extend_one (bsb_seed3.h) over the sector-sized blocks; every coordinate is < 2^32 (seq_len + 1 < 2^32)
+BSB_HD void fm_extend_one32(const IndexView &ix, uint32_t xa, uint32_t xb, uint32_t s, int c, uint32_t &na, uint32_t &nb, uint32_t &sz)
 {
-    const uint64_t k = xa - 1, l = xa - 1 + s;
-    const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
-    const uint64_t _k = kz ? 0 : k - (k >= ix.primary), _l = lz ? 0 : l - (l >= ix.primary);
+    const uint32_t primary = (uint32_t)ix.primary;
+    const uint32_t k = xa - 1, l = xa - 1 + s;
+    const bool kz = k == 0xffffffffu, lz = l == 0xffffffffu;
+    const uint32_t _k = kz ? 0 : k - (k >= primary), _l = lz ? 0 : l - (l >= primary);
     Occ32 bk, bl;
     occ32_load(ix.occ32, _k >> 6, bk);
     occ32_load(ix.occ32, _l >> 6, bl);
@@ -250,9 +251,9 @@ BSB_HD void fm_extend_one32(const IndexView &ix, uint64_t xa, uint64_t xb, uint6
     occ32_eg(bl, (int)(_l & 63), c, el, gl);
     if (kz) ek = gk = 0;
     if (lz) el = gl = 0;
-    na = ix.L2[c] + 1 + ek;
-    sz = (uint64_t)(el - ek);
-    nb = xb + (xa <= ix.primary && xa + s - 1 >= ix.primary) + (uint64_t)(gl - gk);
+    na = (uint32_t)ix.L2[c] + 1 + ek;
+    sz = el - ek;
+    nb = xb + (xa <= primary && xa + s - 1 >= primary) + (gl - gk);
 }
 
 // ---- suffix-array lookup -------------------------------------------------------------------

@@ -69,19 +69,29 @@ BSB_HD void fm_extend_one(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_
     nb = xb + (xa <= ix.primary && xa + s - 1 >= ix.primary) + (gl - gk);
 }
 
+BSB_HD void fm_extend_any(const IndexView &ix, uint64_t xa, uint64_t xb, uint64_t s, int c, uint64_t &na, uint64_t &nb, uint64_t &sz)
+{
+    fm_extend_one(ix, xa, xb, s, c, na, nb, sz);
+}
+BSB_HD void fm_extend_any(const IndexView &ix, uint32_t xa, uint32_t xb, uint32_t s, int c, uint32_t &na, uint32_t &nb, uint32_t &sz)
+{
+    fm_extend_one32(ix, xa, xb, s, c, na, nb, sz);
+}
+
 // Bases: int get(int i) -> code 0..3, >3 ambiguous.
 // List: push(p, x0, x2, end) appends rank p during the forward sweep; get(p, nf, ...) / set(p, nf, ...) read and rewrite
 // rank p once the forward sweep has ended with nf entries (the device list keeps the top ranks in shared memory); cap().
-template <class Bases, class List>
+// U: the coordinate type -- uint32_t when the BWT has fewer than 2^32 symbols (half the registers), else uint64_t.
+template <class Bases, class List, class U>
 struct Seeder3 {
     enum St { NEXT, FWD, BWD_ROW, BWD_CELL, SMEM_END, P3, W_FWD, W_BWD, W_P3, DONE };
     Bases q; List L;
     Intv *out; int out_cap;          // this read's slice of the interval array: item A fills from the front, item B from the back
     int len;
     int st, pass, x, i, min_intv, ret, c, err;
-    uint64_t k0, k1, ks;             // the interval being extended forward (x0, x1, size); it ends at query position i
-    int nf, pn, j, cn; uint64_t last_x2;   // list: nf entries after the forward sweep; current row = ranks nf-1 .. nf-pn
-    uint64_t e0, e2; int e_end;      // the list entry whose backward extension is in flight
+    U k0, k1, ks;                    // the interval being extended forward (x0, x1, size); it ends at query position i
+    int nf, pn, j, cn; U last_x2;    // list: nf entries after the forward sweep; current row = ranks nf-1 .. nf-pn
+    U e0, e2; int e_end;             // the list entry whose backward extension is in flight
     int m1_start;                    // bwt_smem1a's "mem->n == 0 || i + 1 < last start" test, without the list (INT_MAX: none yet)
     int k2, old_n, n_out;
 
@@ -93,16 +103,15 @@ struct Seeder3 {
         else { pass = 1; st = NEXT; }
     }
     BSB_HD bool done() const { return st == DONE; }
-    BSB_HD bool is_back() const { return st == W_BWD; }
 
-    BSB_HD void emit(uint64_t x0, uint64_t x2, int start, int end)
+    BSB_HD void emit(U x0, U x2, int start, int end)
     {
         if (n_out >= out_cap) { err = ERR_INTV_OVERFLOW; return; }
         Intv v; v.x0 = x0; v.x1 = 0; v.x2 = x2; v.info = (uint64_t)(uint32_t)start << 32 | (uint32_t)end;
         out[pass == 3 ? out_cap - 1 - n_out : n_out] = v;
         ++n_out;
     }
-    BSB_HD void emit_if_new(const Opt &o, uint64_t x0, uint64_t x2, int start, int end)
+    BSB_HD void emit_if_new(const Opt &o, U x0, U x2, int start, int end)
     {   // bwt.c:334-338 / 343-344 and the length filter of bwamem.c:130-133
         if (start >= m1_start) return;
         m1_start = start;
@@ -114,12 +123,15 @@ struct Seeder3 {
         L.push(nf, k0, ks, i); ++nf; ret = i;
     }
     BSB_HD void begin_bwd() { pn = nf; i = x - 1; st = BWD_ROW; }
+    BSB_HD void set_intv(const IndexView &ix, int b)
+    {
+        k0 = (U)(ix.L2[b] + 1); ks = (U)(ix.L2[b + 1] - ix.L2[b]); k1 = (U)(ix.L2[3 - b] + 1);
+    }
     BSB_HD void start_smem(const IndexView &ix, int x_, int min_intv_)
     {   // head of bwt_smem1a; caller guarantees q[x_] < 4
         x = x_; min_intv = min_intv_ < 1 ? 1 : min_intv_;
         m1_start = 0x7fffffff; nf = 0; ret = x + 1;
-        const int b = q.get(x);
-        k0 = ix.L2[b] + 1; ks = ix.L2[b + 1] - ix.L2[b]; k1 = ix.L2[3 - b] + 1;
+        set_intv(ix, q.get(x));
         i = x + 1;
         st = FWD;
     }
@@ -179,8 +191,7 @@ struct Seeder3 {
                 if (i < 0) {                   // next start
                     while (x < len && q.get(x) > 3) ++x;
                     if (x >= len) { st = DONE; break; }
-                    const int b = q.get(x);
-                    k0 = ix.L2[b] + 1; ks = ix.L2[b + 1] - ix.L2[b]; k1 = ix.L2[3 - b] + 1;
+                    set_intv(ix, q.get(x));
                     i = x + 1;
                 }
                 if (i >= len) { x = len; i = -1; break; }          // bwt_seed_strategy1 returns len
@@ -196,36 +207,52 @@ struct Seeder3 {
         }
     }
 
-    BSB_HD void request(uint64_t &xa, uint64_t &xb, uint64_t &s) const
+    // operands of the pending extension: xa = coordinate on the strand being extended, xb = the other one, s = size
+    BSB_HD void request(U &xa, U &xb, U &s) const
     {
         if (st == W_BWD) { xa = e0; xb = 0; s = e2; } else { xa = k1; xb = k0; s = ks; }
     }
 
-    BSB_HD void consume(const Opt &o, uint64_t na, uint64_t nb, uint64_t sz)
+    // Takes the result of the pending extension and runs on to the next one (true) or to the end of the item (false).
+    // The common continuations -- next base of a forward sweep, next entry or next row of the backward sweep -- are
+    // handled here in straight-line code; everything else goes through the state loop of advance().
+    BSB_HD bool step(const Opt &o, const IndexView &ix, U na, U nb, U sz)
     {
-        if (st == W_FWD) {
-            if (sz != ks) {
-                push_fwd();
-                if (sz < (uint64_t)min_intv) { begin_bwd(); return; }
-            }
-            k1 = na; k0 = nb; ks = sz;
-            ++i;
-            st = FWD;
-        } else if (st == W_BWD) {
-            if (sz < (uint64_t)min_intv) {
+        if (st == W_BWD) {
+            if (sz < (U)min_intv) {
                 if (cn == 0) emit_if_new(o, e0, e2, i + 1, e_end);
             } else if (cn == 0 || sz != last_x2) {
                 L.set(nf - 1 - cn, nf, na, sz, e_end); ++cn; last_x2 = sz;
             }
             ++j;
+            if (j >= pn && cn > 0 && i > 0) {      // row finished with survivors: next row, if its base can be matched
+                const int b = q.get(i - 1);
+                if (b < 4) { pn = cn; --i; c = b; j = 0; cn = 0; }
+            }
+            if (j < pn) { L.get(nf - 1 - j, nf, e0, e2, e_end); return true; }
             st = BWD_CELL;
-        } else { // W_P3
-            if (sz < o.max_mem_intv && i - x >= o.min_seed_len) {
+        } else {
+            bool on = true;
+            if (st == W_FWD) {
+                if (sz != ks) {
+                    push_fwd();
+                    if (sz < (U)min_intv) { begin_bwd(); on = false; }
+                }
+            } else if (sz < (U)o.max_mem_intv && i - x >= o.min_seed_len) {    // W_P3: seed found, restart behind it
                 if (sz > 0) emit(nb, sz, x, i + 1);
-                x = i + 1; i = -1;
-            } else { k1 = na; k0 = nb; ks = sz; ++i; }
-            st = P3;
+                x = i + 1; i = -1; st = P3; on = false;
+            }
+            if (on) {
+                k1 = na; k0 = nb; ks = sz;
+                ++i;
+                if (i < len) {
+                    const int b = q.get(i);
+                    if (b < 4) { c = 3 - b; return true; }
+                }
+                st = st == W_FWD ? FWD : P3;
+            }
         }
+        return advance(o, ix);
     }
 };
 
@@ -250,26 +277,26 @@ struct BasesBytes { const uint8_t *p; BSB_HD int get(int i) const { return p[i];
 struct ListPlain {
     uint64_t *a0, *a2; int *ae; int n;
     BSB_HD int cap() const { return n; }
-    BSB_HD void get(int p, int, uint64_t &x0, uint64_t &x2, int &end) const { x0 = a0[p]; x2 = a2[p]; end = ae[p]; }
-    BSB_HD void set(int p, int, uint64_t x0, uint64_t x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
-    BSB_HD void push(int p, uint64_t x0, uint64_t x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
+    template <class U> BSB_HD void get(int p, int, U &x0, U &x2, int &end) const { x0 = (U)a0[p]; x2 = (U)a2[p]; end = ae[p]; }
+    template <class U> BSB_HD void set(int p, int, U x0, U x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
+    template <class U> BSB_HD void push(int p, U x0, U x2, int end) { a0[p] = x0; a2[p] = x2; ae[p] = end; }
 };
 
 // collect_intv() through the two work items, one after the other (what the kernel does on two lanes)
-template <class Bases, class List>
+template <class U, class Bases, class List>
 BSB_HD int collect_intv_v3(const Opt &opt, const IndexView &ix, int len, Bases q, List L, Intv *mem, int cap, int *err)
 {
     int n_part[2] = {0, 0};
     for (int item = 0; item < 2; ++item) {
-        Seeder3<Bases, List> sm;
+        Seeder3<Bases, List, U> sm;
         sm.q = q; sm.L = L;
         sm.init(opt, len, mem, cap, item == 1);
-        while (sm.advance(opt, ix)) {
-            uint64_t xa, xb, s, na, nb, sz;
+        bool need = sm.advance(opt, ix);
+        while (need) {
+            U xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
-            if (ix.occ32) fm_extend_one32(ix, xa, xb, s, sm.c, na, nb, sz);
-            else fm_extend_one(ix, xa, xb, s, sm.c, na, nb, sz);
-            sm.consume(opt, na, nb, sz);
+            fm_extend_any(ix, xa, xb, s, sm.c, na, nb, sz);
+            need = sm.step(opt, ix, na, nb, sz);
         }
         if (sm.err) *err = sm.err;
         n_part[item] = sm.n_out;

@@ -110,7 +110,8 @@ BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, i
         if (work) {
             ListPlain L = {(uint64_t *)sc.t0, (uint64_t *)sc.t1, (int *)sc.mem1, B.intv_cap};
             BasesBytes q = {seq};
-            mem.n = collect_intv_v3(opt, ix, len, q, L, mem.a, mem.cap, &err);
+            mem.n = ix.occ32 ? collect_intv_v3<uint32_t>(opt, ix, len, q, L, mem.a, mem.cap, &err)
+                             : collect_intv_v3<uint64_t>(opt, ix, len, q, L, mem.a, mem.cap, &err);
         }
     } else if (use_sm) collect_intv_sm(opt, ix, len, seq, mem, mem1, t0, t1, &err, work);
     else if (work) collect_intv(opt, ix, len, seq, mem, mem1, t0, t1, &err);
