@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B
 }
 
 // K5, warp per read: rows of the banded extension across the lanes, (h,e) rows + query in shared memory
-__global__ void __launch_bounds__(128) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int wib = threadIdx.x >> 5;
@@ -410,7 +411,7 @@ __device__ __forceinline__ void make_ws(const FinalLayout &L, uint8_t *blk, Fina
     wregs = (AlnReg *)(blk + L.wregs);
 }
 
-// K6 + K8b: one warp per queued alignment
+// K6 + K8b, single-kernel form (one warp per queued alignment; lane 0 finishes the record)
 __global__ void __launch_bounds__(128) k_tasks(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint8_t *zbuf, long z_cap, int max_q, int smem_per_warp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -425,6 +426,41 @@ __global__ void __launch_bounds__(128) k_tasks(Opt opt, IndexView ix, BatchDev B
     S.qs = (uint8_t *)(S.xb + S.xb_cap);
     uint8_t *z = zbuf + (size_t)gw * z_cap;
     for (unsigned int k = gw; k < n_tasks; k += nw) stage_task_warp(opt, ix, B, k, S, z, z_cap, max_q);
+}
+
+// K6a: global alignments of the queued alignments that need one (about one in ten), warp-cooperative
+__global__ void __launch_bounds__(128) k_tasks_dp(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint8_t *zbuf, long z_cap, int max_q, int smem_per_warp,
+                                                  uint32_t *slots, int slot_cap, int32_t *n_cig)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    uint8_t *mine = smem + (size_t)wib * smem_per_warp;
+    WarpTask S;
+    S.H = (int32_t *)mine; S.E = S.H + (max_q + 1); S.qs = (uint8_t *)(S.E + (max_q + 1));
+    S.cigar = nullptr; S.cigar_cap = 0; S.md = nullptr; S.md_cap = 0; S.xb = nullptr; S.xb_cap = 0;
+    uint8_t *z = zbuf + (size_t)gw * z_cap;
+    for (unsigned int base = gw * 32; base < n_tasks; base += nw * 32) {
+        const unsigned int k = base + lane;
+        bool dp = false;
+        if (k < n_tasks) { const AlnTask t = B.tasks.a[k]; dp = !B.out[t.read].err && !task_is_trivial(opt, t); }
+        unsigned m = __ballot_sync(0xffffffffu, dp);
+        while (m) {
+            const unsigned int kk = base + (unsigned)__ffs(m) - 1;
+            m &= m - 1;
+            stage_task_dp_warp(opt, ix, B, kk, S, z, z_cap, max_q, slots + (size_t)kk * slot_cap, slot_cap, n_cig + kk);
+        }
+    }
+}
+
+// K6b + K8b: one thread per queued alignment
+__global__ void __launch_bounds__(128) k_tasks_finish(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint32_t *slots, int slot_cap, const int32_t *n_cig,
+                                                      char *text, int md_cap, int xb_cap)
+{
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    char *md = text + (size_t)w * (size_t)(md_cap + xb_cap);
+    for (unsigned int k = w; k < n_tasks; k += nw)
+        stage_task_finish(opt, ix, B, k, slots + (size_t)k * slot_cap, n_cig + k, md, md_cap, md + md_cap, xb_cap);
 }
 
 __global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
@@ -547,6 +583,7 @@ struct CudaAligner::Impl {
     DevBuf<double> d_log, d_pair;
     DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
+    DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
     std::vector<double> log_tab;
@@ -761,9 +798,12 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     } else {
         const int wpb = 4;
         const int smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 15) & ~15;
-        const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)m.n_sm * 8);
+        const int ext_bps = env_int("BSB_EXT_BPS", 5);
+        const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)m.n_sm * ext_bps);
         m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
-        k_extend_warp<<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp); ++m.launches;
+        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp);
+        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp);
+        ++m.launches;
     }
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
@@ -863,9 +903,20 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaStreamSynchronize(st));
         T("select_done");
         if (n_tasks > m.task_cap) { m.task_cap = (size_t)n_tasks + (size_t)n_tasks / 4 + 4096; continue; }
-        if (n_tasks) {
+        if (n_tasks && getenv("BSB_TASKS_V1")) {
             k_tasks<<<tk_blocks, tk_wpb * 32, tk_wpb * tk_smem_per_warp, st>>>(opt, m.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, tk_smem_per_warp);
             ++m.launches;
+        } else if (n_tasks) {
+            const int slot_cap = 2 * max_q + 16, md_cap = 8 * max_q + 64, xb_cap = 4 * max_q + 64;
+            const int dp_smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 31) & ~15;
+            const int fin_threads = m.n_sm * 8 * 128;
+            m.d_task_cigar.ensure((size_t)n_tasks * slot_cap);
+            m.d_task_ncig.ensure(n_tasks);
+            m.d_task_text.ensure((size_t)fin_threads * (md_cap + xb_cap));
+            k_tasks_dp<<<tk_blocks, tk_wpb * 32, tk_wpb * dp_smem_per_warp, st>>>(opt, m.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, dp_smem_per_warp,
+                                                                                   m.d_task_cigar.p, slot_cap, m.d_task_ncig.p);
+            k_tasks_finish<<<fin_threads / 128, 128, 0, st>>>(opt, m.ix, B, n_tasks, m.d_task_cigar.p, slot_cap, m.d_task_ncig.p, m.d_task_text.p, md_cap, xb_cap);
+            m.launches += 2;
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(m.ev[8], st));

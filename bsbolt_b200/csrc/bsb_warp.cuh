@@ -24,11 +24,7 @@ struct WarpDp {            // per-warp shared memory
     uint8_t *qs;           // query of the current extension, in extension order
 };
 
-__device__ __forceinline__ int warp_max(int v)
-{
-    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULLMASK, v, o));
-    return v;
-}
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(FULLMASK, v); }   // one REDUX.MAX
 
 template <class T>
 __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, const T &target, const int8_t *mat,
@@ -59,8 +55,10 @@ __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, con
     max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
     beg = 0; end = qlen;
     __syncwarp();
+    int tcache = 0;                                 // target bases of rows [i & ~31, +32), one per lane
     for (i = 0; i < tlen; ++i) {
-        const int8_t *row = mat + target(i) * 5;
+        if ((i & 31) == 0) tcache = i + lane < tlen ? target(i + lane) : 4;
+        const int8_t *row = mat + __shfl_sync(FULLMASK, tcache, i & 31) * 5;
         if (beg < i - w) beg = i - w;
         if (end > i + w + 1) end = i + w + 1;
         if (end > qlen) end = qlen;
@@ -443,6 +441,69 @@ __device__ bool global_core_warp(const Opt &opt, const IndexView &ix, int w_, in
         *score = nw_global_warp(l_query, q, (int)rlen, t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, S, z, cig, err);
     }
     return true;
+}
+
+// A queued alignment needs no dynamic programming when the band inferred for it is empty and both spans have the
+// same length: bwa_gen_cigar2 then returns <len>M whatever the score (bwa.c:222-230), also on the retries.
+__device__ __forceinline__ bool task_is_trivial(const Opt &opt, const AlnTask &t)
+{
+    return band_for_task(opt, t) == 0 && (int64_t)(t.qe - t.qb) == t.re - t.rb;
+}
+
+// K6a: the global alignments. Each warp scans 32 queued alignments at a time and runs the ones that need the
+// DP, one after the other, with its 32 lanes across the columns; the CIGAR goes to the task's slot in HBM.
+__device__ void stage_task_dp_warp(const Opt &opt, const IndexView &ix, BatchDev &B, unsigned int k, const WarpTask &S, uint8_t *z, long z_cap, int max_q,
+                                   uint32_t *slot, int slot_cap, int32_t *n_cig_out)
+{
+    const int lane = threadIdx.x & 31;
+    const AlnTask t = B.tasks.a[k];
+    const int r = t.read;
+    const uint8_t *query = B.seq + B.seq_off[r];
+    int err = 0;
+    int w2 = band_for_task(opt, t), score = 0, last_sc = -(1 << 30), i = 0;
+    CigarBuf cig = {slot, 0, slot_cap - 2};
+    bool ok;
+    do {
+        w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+        ok = global_core_warp(opt, ix, w2, t.qe - t.qb, query + t.qb, t.rb, t.re, &score, &cig, S, z, z_cap, max_q, &err);
+        if (!ok) break;
+        if (score == last_sc || w2 == opt.w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++i < 3 && score < t.truesc - opt.a);
+    if (lane == 0) {
+        *n_cig_out = ok ? cig.n : -1;
+        if (err) B.out[r].err = err;
+    }
+    __syncwarp();
+}
+
+// K6b + K8b: one queued alignment per THREAD once its CIGAR exists: bisulfite NM/MD/XB against the unconverted
+// reference, position, clips, and the write into the record(s) in the arena.
+__device__ void stage_task_finish(const Opt &opt, const IndexView &ix, BatchDev &B, unsigned int k, uint32_t *slot, const int32_t *n_cig_in,
+                                  char *md_buf, int md_cap, char *xb_buf, int xb_cap)
+{
+    const AlnTask t = B.tasks.a[k];
+    const int r = t.read;
+    if (B.out[r].err) return;
+    const int l = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+    const uint8_t *oquery = B.oseq + B.seq_off[r];
+    uint32_t small[4];
+    uint32_t *c = slot;
+    int n_cig, err = 0;
+    if (task_is_trivial(opt, t)) {
+        const int l_query = t.qe - t.qb;
+        const bool valid = !(l_query <= 0 || t.rb >= t.re || (t.rb < ix.l_pac && t.re > ix.l_pac)) && !(t.re > (ix.l_pac << 1) || t.rb < 0);
+        c = small; c[0] = (uint32_t)l_query << 4; n_cig = valid ? 1 : -1;
+    } else n_cig = *n_cig_in;
+    if (n_cig < 0) err = ERR_NO_MD;
+    else {
+        AlnBody b;
+        StrBuf md = {md_buf, 0, md_cap, false}, xb = {xb_buf, 0, xb_cap, false};
+        aln_finish(ix, t, l, oquery, c, n_cig, md, xb, b, &err);
+        task_store(ix, t, b, c, md_buf, B.arena, B.out, &err);
+    }
+    if (err) B.out[r].err = err;
 }
 
 // One queued alignment on one warp: CIGAR by the lanes together, bisulfite MD/XB + record write by lane 0
