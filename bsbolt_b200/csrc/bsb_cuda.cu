@@ -360,10 +360,18 @@ __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, u
     stage_sa(opt, ix, B, r, g);
 }
 
-__global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B)
+// K4: thread per read, reads visited in order of decreasing seed count so that the lanes of a warp carry similar
+// work (the per-read cost is heavy-tailed: a repetitive read has thousands of seeds) and the heavy ones start first
+__global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B, const int32_t *order)
 {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < B.n) stage_chain(opt, ix, B, r);
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B.n) stage_chain(opt, ix, B, order ? order[t] : t);
+}
+
+__global__ void k_iota(int32_t *a, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
 }
 
 __global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q)
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B
 
 // K5, warp per read: rows of the banded extension across the lanes, (h,e) rows + query in shared memory
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp)
+__global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp, const int32_t *order)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int wib = threadIdx.x >> 5;
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix
     WarpDp S;
     S.H = (int32_t *)mine; S.E = S.H + (max_q + 1); S.qs = (uint8_t *)(S.E + (max_q + 1));
     DpScratch dp = {eh + (size_t)gw * 2 * (max_q + 1), nullptr, 0, max_q};
-    for (int r = gw; r < B.n; r += nw) stage_extend_warp(opt, ix, B, r, S, dp);
+    for (int t = gw; t < B.n; t += nw) stage_extend_warp(opt, ix, B, order ? order[t] : t, S, dp);
 }
 
 __global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
@@ -471,7 +479,8 @@ __global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev
     for (int r = w; r < B.n; r += nw) stage_final_se(opt, ix, B, r, ws, wregs);
 }
 
-__global__ void __launch_bounds__(32) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
     FinalWS ws; AlnReg *wregs;
@@ -583,6 +592,7 @@ struct CudaAligner::Impl {
     DevBuf<double> d_log, d_pair;
     DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
+    DevBuf<int32_t> d_order, d_order_tmp, d_key_tmp;
     DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
@@ -785,7 +795,16 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[4], st));
     // ---- K4 ----
-    k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, m.ix, B); ++m.launches;
+    {   // reads by decreasing seed count
+        m.d_order.ensure(n + 1); m.d_order_tmp.ensure(n + 1); m.d_key_tmp.ensure(n + 1);
+        k_iota<<<cdiv(n, 256), 256, 0, st>>>(m.d_order_tmp.p, n); ++m.launches;
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const int32_t *)m.d_n_seed.p, m.d_key_tmp.p, (const int32_t *)m.d_order_tmp.p, m.d_order.p, n, 0, 32, st);
+        m.d_cub.ensure(sort_bytes + 16);
+        cub::DeviceRadixSort::SortPairsDescending(m.d_cub.p, sort_bytes, (const int32_t *)m.d_n_seed.p, m.d_key_tmp.p, (const int32_t *)m.d_order_tmp.p, m.d_order.p, n, 0, 32, st);
+        m.launches += 4;
+    }
+    k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, m.ix, B, getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p); ++m.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[5], st));
     // ---- K5 ----
@@ -799,10 +818,11 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         const int wpb = 4;
         const int smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 15) & ~15;
         const int ext_bps = env_int("BSB_EXT_BPS", 5);
+        const int32_t *ext_order = getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p;
         const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)m.n_sm * ext_bps);
         m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
-        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp);
-        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp);
+        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
+        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
         ++m.launches;
     }
     CK(cudaGetLastError());
@@ -866,7 +886,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     L.total = o;
     const int fin_block = 32;
     const int items = pe ? n >> 1 : n;
-    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)m.n_sm * 16 * fin_block);
+    const int fin_bps = env_int("BSB_FIN_BPS", 16);
+    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)m.n_sm * fin_bps * fin_block);
     m.d_final_scratch.ensure((size_t)fin_workers * L.total);
     m.d_out.ensure(n + 1);
     B.out = m.d_out.p;
@@ -893,7 +914,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         B.arena.base = m.d_arena.p; B.arena.used = m.d_used.p; B.arena.cap = m.arena_cap;
         B.tasks.a = m.d_tasks.p; B.tasks.n = m.d_ntasks.p; B.tasks.cap = (unsigned int)m.task_cap;
         if (items) {
-            if (pe) k_final_pe<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            if (pe && fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            else if (pe && fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            else if (pe) k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
             else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
             ++m.launches;
         }
