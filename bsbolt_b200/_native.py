@@ -17,7 +17,7 @@ class RunStats(C.Structure):
                 ('ms_h2d', C.c_double), ('ms_kernels', C.c_double), ('ms_d2h', C.c_double),
                 ('ms_stage', C.c_double * 8)] + \
                [(n, C.c_int64) for n in ('n_seeds', 'h2d_bytes', 'd2h_bytes', 'kernel_launches')] + \
-               [(n, C.c_double) for n in ('sec_read', 'sec_format', 'sec_write', 'ms_select', 'ms_tasks')] + [('n_tasks', C.c_int64)]
+               [(n, C.c_double) for n in ('sec_read', 'sec_format', 'sec_write', 'ms_select', 'ms_tasks')] + [('n_tasks', C.c_int64), ('sec_resident', C.c_double)]
 
     def as_dict(self):
         d = {}

@@ -571,14 +571,13 @@ static InstallPinnedHooks g_install_pinned_hooks;
 // ------------------------------------------------------------------------------------------------
 // CudaAligner
 // ------------------------------------------------------------------------------------------------
-struct CudaAligner::Impl {
-    int device = 0, n_sm = 0;
+// per-batch device state: one stream and its buffers. A CudaAligner owns several so that several batches can be in
+// flight on the GPU at once (each driven by its own host thread): the kernels of one batch fill the tails and the
+// host round trips of the other.
+struct BatchCtx {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[12];   // 0..9 stage boundaries, 10 = selection kernel done
-    // resident index
-    DevBuf<uint32_t> d_bwt, d_sa32, d_occ32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
-    IndexView ix;
-    // batch buffers
+    cudaEvent_t ev_wait = nullptr;   // blocking-sync event: the host thread sleeps instead of spinning on a core
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
     DevBuf<Intv> d_intv, d_seed_scratch;
     DevBuf<uint64_t> d_seq4; DevBuf<uint4> d_spill; DevBuf<int32_t> d_cnt_ab;
@@ -589,17 +588,52 @@ struct CudaAligner::Impl {
     DevBuf<uint64_t> d_srt; DevBuf<AlnReg> d_regs; DevBuf<BtNode> d_nodes;
     DevBuf<int32_t> d_eh;
     DevBuf<int8_t> d_pe_dir; DevBuf<int64_t> d_pe_isize;
-    DevBuf<double> d_log, d_pair;
+    DevBuf<double> d_pair;
     DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
     DevBuf<int32_t> d_order, d_order_tmp, d_key_tmp;
     DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
-    std::vector<double> log_tab;
     size_t arena_cap = 0;
     int intv_cap_hint = 0;
     long launches = 0;
+    bool ready = false;
+    void init()
+    {
+        if (ready) return;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (auto &e : ev) CK(cudaEventCreate(&e));
+        CK(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+        d_used.ensure(1); d_misc.ensure(16); d_ntasks.ensure(1);
+        ready = true;
+    }
+    ~BatchCtx()
+    {
+        if (!ready) return;
+        for (auto &e : ev) cudaEventDestroy(e);
+        if (ev_wait) cudaEventDestroy(ev_wait);
+        if (st) cudaStreamDestroy(st);
+    }
+    void wait()
+    {
+        static const bool spin = getenv("BSB_SPIN") != nullptr;
+        if (spin) { CK(cudaStreamSynchronize(st)); return; }
+        CK(cudaEventRecord(ev_wait, st));
+        CK(cudaEventSynchronize(ev_wait));
+    }
+};
+
+struct CudaAligner::Impl {
+    int device = 0, n_sm = 0;
+    // resident index
+    DevBuf<uint32_t> d_bwt, d_sa32, d_occ32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
+    IndexView ix;
+    DevBuf<double> d_log;
+    std::vector<double> log_tab;
+    long launches = 0;        // index-load kernels
+    BatchCtx ctx[CudaAligner::kSlots];
+    std::mutex init_m;
 };
 
 CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
@@ -616,8 +650,6 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     CK(cudaGetDeviceProperties(&prop, device));
     m.n_sm = prop.multiProcessorCount;
     CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
-    CK(cudaStreamCreateWithFlags(&m.st, cudaStreamNonBlocking));
-    for (auto &ev : m.ev) CK(cudaEventCreate(&ev));
     // index -> HBM (reference layout, see bsb_index.h)
     m.d_bwt.ensure(idx.bwt.size()); CK(cudaMemcpy(m.d_bwt.p, idx.bwt.data(), idx.bwt.size() * 4, cudaMemcpyHostToDevice));
     m.d_sa.ensure(idx.sa.size()); CK(cudaMemcpy(m.d_sa.p, idx.sa.data(), idx.sa.size() * 8, cudaMemcpyHostToDevice));
@@ -647,19 +679,43 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     build_log_table(m.log_tab, 65536);
     m.d_log.ensure(m.log_tab.size());
     CK(cudaMemcpy(m.d_log.p, m.log_tab.data(), m.log_tab.size() * 8, cudaMemcpyHostToDevice));
-    m.d_used.ensure(1); m.d_misc.ensure(16); m.d_ntasks.ensure(1);
 }
 
 CudaAligner::~CudaAligner()
 {
     if (!im_) return;
     cudaSetDevice(im_->device);
-    for (auto &ev : im_->ev) cudaEventDestroy(ev);
-    if (im_->st) cudaStreamDestroy(im_->st);
     delete im_;
 }
 
-long CudaAligner::kernel_launches() const { return im_->launches; }
+struct DeviceInput { DevBuf<char> bases; DevBuf<uint32_t> seq_off; DevBuf<uint8_t> pattern; };
+
+void CudaAligner::preload(ReadBatch &b)
+{
+    CK(cudaSetDevice(im_->device));
+    DeviceInput *d = new DeviceInput;
+    const size_t nb = b.bases.size();
+    d->bases.ensure(nb + 16); d->seq_off.ensure(b.n + 1); d->pattern.ensure(b.n + 1);
+    CK(cudaMemcpy(d->bases.p, b.bases.data(), nb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->seq_off.p, b.seq_off.data(), (size_t)(b.n + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->pattern.p, b.pattern.data(), (size_t)b.n, cudaMemcpyHostToDevice));
+    b.dev_input = d;
+}
+
+void CudaAligner::unload(ReadBatch &b)
+{
+    if (!b.dev_input) return;
+    cudaSetDevice(im_->device);
+    delete static_cast<DeviceInput *>(b.dev_input);
+    b.dev_input = nullptr;
+}
+
+long CudaAligner::kernel_launches() const
+{
+    long n = im_->launches;
+    for (const BatchCtx &c : im_->ctx) n += c.launches;
+    return n;
+}
 int CudaAligner::device() const { return im_->device; }
 size_t CudaAligner::index_bytes() const
 {
@@ -669,10 +725,13 @@ size_t CudaAligner::index_bytes() const
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out)
+void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot)
 {
-    Impl &m = *im_;
-    CK(cudaSetDevice(m.device));
+    Impl &I = *im_;
+    if (slot < 0 || slot >= kSlots) throw std::runtime_error("[E::bsbolt_b200] invalid batch slot");
+    CK(cudaSetDevice(I.device));
+    BatchCtx &m = I.ctx[slot];
+    { std::lock_guard<std::mutex> l(I.init_m); m.init(); }
     cudaStream_t st = m.st;
     const Opt opt = opt_in;
     const int n = b.n;
@@ -685,17 +744,22 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     for (int k = 0; k < 8; ++k) out.ms_stage[k] = 0;
     const bool dbg = getenv("BSB_DEBUG_TIMELINE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
+    static const auto t_epoch = std::chrono::steady_clock::now();
     auto T = [&](const char *tag) {
-        if (dbg) fprintf(stderr, "[D::timeline] %-14s %8.2f ms\n", tag, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        if (dbg) fprintf(stderr, "[D::timeline] slot %d %-14s %8.2f ms (abs %9.2f)\n", slot, tag, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(),
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epoch).count());
     };
 
     // ---- H2D ----
     CK(cudaEventRecord(m.ev[0], st));
     m.d_bases.ensure(nb + 16); m.d_seq.ensure(nb + 16); m.d_oseq.ensure(nb + 16);
     m.d_seq_off.ensure(n + 1); m.d_pattern.ensure(n + 1);
-    CK(cudaMemcpyAsync(m.d_bases.p, b.bases.data(), nb, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m.d_seq_off.p, b.seq_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m.d_pattern.p, b.pattern.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+    const DeviceInput *pre = static_cast<const DeviceInput *>(b.dev_input);
+    if (!pre) {
+        CK(cudaMemcpyAsync(m.d_bases.p, b.bases.data(), nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(m.d_seq_off.p, b.seq_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(m.d_pattern.p, b.pattern.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaEventRecord(m.ev[1], st));
     T("h2d_enq");
 
@@ -703,6 +767,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     memset(&B, 0, sizeof B);
     B.n = n; B.is_pe = pe; B.n_processed = n_processed;
     B.bases = m.d_bases.p; B.seq_off = m.d_seq_off.p; B.pattern = m.d_pattern.p; B.seq = m.d_seq.p; B.oseq = m.d_oseq.p;
+    if (pre) { B.bases = pre->bases.p; B.seq_off = pre->seq_off.p; B.pattern = pre->pattern.p; }
     m.d_n_intv.ensure(n + 1); m.d_l_rep.ensure(n + 1); m.d_n_seed.ensure(n + 1); m.d_n_chain.ensure(n + 1); m.d_n_regs.ensure(n + 1);
     m.d_err.ensure(n + 1); m.d_seed_off.ensure(n + 2);
     B.n_intv = m.d_n_intv.p; B.l_rep = m.d_l_rep.p; B.n_seed = m.d_n_seed.p; B.n_chain = m.d_n_chain.p; B.n_regs = m.d_n_regs.p;
@@ -716,10 +781,10 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     // ---- K2 (retry with a larger interval capacity on overflow) ----
     B.intv_cap = std::max(std::max(256, 2 * max_len), m.intv_cap_hint);
     const int seed_block = 64;
-    const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)m.n_sm * 16 * seed_block);
+    const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)I.n_sm * 16 * seed_block);
     const bool seed_old = getenv("BSB_SEED_V1") || getenv("BSB_SEED_V2") || getenv("BSB_SEED_DYN");
     auto env_int = [](const char *k, int d) { const char *v = getenv(k); return v ? atoi(v) : d; };
-    const int s3_scap = m.ix.occ32 ? env_int("BSB_S3_SCAP", 16) : 16, s3_total = max_len + 1, s3_bps = env_int("BSB_S3_BPS", m.ix.occ32 ? 12 : 10), s3_blocks = m.n_sm * s3_bps;
+    const int s3_scap = I.ix.occ32 ? env_int("BSB_S3_SCAP", 16) : 16, s3_total = max_len + 1, s3_bps = env_int("BSB_S3_BPS", I.ix.occ32 ? 12 : 10), s3_blocks = I.n_sm * s3_bps;
     const uint32_t n_words = (uint32_t)(nb >> 4) + (uint32_t)n + 1;
     if (!seed_old && n) {
         m.d_seq4.ensure(n_words + 1);
@@ -736,15 +801,15 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
         if (seed_old) {
             m.d_seed_scratch.ensure((size_t)seed_workers * 3 * B.intv_cap);
-            if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
-            else if (getenv("BSB_SEED_V2")) k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p);
-            else k_seed_dyn<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, m.ix, B, m.d_seed_scratch.p, m.d_misc.p + 8);
+            if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, I.ix, B, m.d_seed_scratch.p);
+            else if (getenv("BSB_SEED_V2")) k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, I.ix, B, m.d_seed_scratch.p);
+            else k_seed_dyn<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, I.ix, B, m.d_seed_scratch.p, m.d_misc.p + 8);
             ++m.launches;
         } else if (n) {
             CK(cudaMemsetAsync(m.d_cnt_ab.p, 0, 2 * (size_t)n * 4, st));
             const size_t s3_smem = (size_t)SEED3_BLOCK * s3_scap * 12;
-#define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, m.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
-            if (!m.ix.occ32) BSB_S3_LAUNCH(16, 10, false);       // >= 2^32-symbol index: reference block layout
+#define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, I.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
+            if (!I.ix.occ32) BSB_S3_LAUNCH(16, 10, false);       // >= 2^32-symbol index: reference block layout
             else if (s3_bps > 12) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 16, true); else BSB_S3_LAUNCH(16, 16, true); }
             else if (s3_bps > 10) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 12, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 12, true); else BSB_S3_LAUNCH(16, 12, true); }
             else { if (s3_scap == 8) BSB_S3_LAUNCH(8, 10, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 10, true); else BSB_S3_LAUNCH(16, 10, true); }
@@ -753,10 +818,10 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
             m.launches += 2;
         }
         CK(cudaGetLastError());
-        k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p); ++m.launches;
+        k_max_i32<<<I.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p); ++m.launches;
         int32_t max_err = 0;
         CK(cudaMemcpyAsync(&max_err, m.d_misc.p, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        m.wait();
         if (max_err == 0) break;
         if (max_err != ERR_INTV_OVERFLOW) throw std::runtime_error("[E::bsbolt_b200] seeding failed with error code " + std::to_string(max_err));
         B.intv_cap *= 2;
@@ -773,7 +838,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     cub::DeviceScan::ExclusiveSum(m.d_cub.p, cub_bytes, (const int32_t *)m.d_n_seed.p, (uint32_t *)m.d_seed_off.p, n + 1, st); ++m.launches;
     uint32_t S = 0;
     CK(cudaMemcpyAsync(&S, m.d_seed_off.p + n, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    m.wait();
     B.seed_off = m.d_seed_off.p;
     T("scan_done");
     if (getenv("BSB_DEBUG_STATS")) { // distribution of per-read seed counts (load-balance diagnostics)
@@ -791,7 +856,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     B.chain_pool = m.d_pool.p; B.chains = m.d_chains.p; B.srt = m.d_srt.p; B.regs = m.d_regs.p; B.nodes = m.d_nodes.p;
 
     // ---- K3 ----
-    if (S) { k_sa<<<cdiv(S, 128), 128, 0, st>>>(opt, m.ix, B, S); ++m.launches; }
+    if (S) { k_sa<<<cdiv(S, 128), 128, 0, st>>>(opt, I.ix, B, S); ++m.launches; }
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[4], st));
     // ---- K4 ----
@@ -804,35 +869,35 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         cub::DeviceRadixSort::SortPairsDescending(m.d_cub.p, sort_bytes, (const int32_t *)m.d_n_seed.p, m.d_key_tmp.p, (const int32_t *)m.d_order_tmp.p, m.d_order.p, n, 0, 32, st);
         m.launches += 4;
     }
-    k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, m.ix, B, getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p); ++m.launches;
+    k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p); ++m.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[5], st));
     // ---- K5 ----
     const int max_q = max_len + 8;
     if (getenv("BSB_EXTEND_V1")) {
         const int ext_block = 64;
-        const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)m.n_sm * 16 * ext_block);
+        const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)I.n_sm * 16 * ext_block);
         m.d_eh.ensure((size_t)ext_workers * 2 * (max_q + 1));
-        k_extend<<<ext_workers / ext_block, ext_block, 0, st>>>(opt, m.ix, B, m.d_eh.p, max_q); ++m.launches;
+        k_extend<<<ext_workers / ext_block, ext_block, 0, st>>>(opt, I.ix, B, m.d_eh.p, max_q); ++m.launches;
     } else {
         const int wpb = 4;
         const int smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 15) & ~15;
         const int ext_bps = env_int("BSB_EXT_BPS", 5);
         const int32_t *ext_order = getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p;
-        const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)m.n_sm * ext_bps);
+        const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)I.n_sm * ext_bps);
         m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
-        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
-        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, m.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
+        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
+        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
         ++m.launches;
     }
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
-    k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_n_regs.p, n, m.d_misc.p); ++m.launches;
-    k_max_i32<<<m.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p + 1); ++m.launches;
+    k_max_i32<<<I.n_sm, 256, 0, st>>>(m.d_n_regs.p, n, m.d_misc.p); ++m.launches;
+    k_max_i32<<<I.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p + 1); ++m.launches;
     int32_t h_misc[2] = {0, 0};
     CK(cudaMemcpyAsync(h_misc, m.d_misc.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(m.ev[6], st));
-    CK(cudaStreamSynchronize(st));
+    m.wait();
     T("extend_done");
     if (h_misc[1]) throw std::runtime_error("[E::bsbolt_b200] chaining/extension failed with error code " + std::to_string(h_misc[1]));
     const int max_regs = h_misc[0];
@@ -853,12 +918,12 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
             const int np = n >> 1;
             m.d_pe_dir.ensure(np + 1); m.d_pe_isize.ensure(np + 1);
             B.pe_dir = m.d_pe_dir.p; B.pe_isize = m.d_pe_isize.p;
-            k_pestat<<<cdiv(np, 128), 128, 0, st>>>(opt, m.ix, B); ++m.launches;
+            k_pestat<<<cdiv(np, 128), 128, 0, st>>>(opt, I.ix, B); ++m.launches;
             CK(cudaGetLastError());
             std::vector<int8_t> dir(np); std::vector<int64_t> isz(np);
             CK(cudaMemcpyAsync(dir.data(), m.d_pe_dir.p, np, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(isz.data(), m.d_pe_isize.p, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            m.wait();
             estimate_pestat(opt, dir, isz, B.pes, verbose);
         }
         memcpy(out.pes, B.pes, sizeof B.pes);
@@ -866,7 +931,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     build_pair_table(opt, B.pes, pair_tab, B.mt.pair_off);
     m.d_pair.ensure(pair_tab.size());
     CK(cudaMemcpyAsync(m.d_pair.p, pair_tab.data(), pair_tab.size() * 8, cudaMemcpyHostToDevice, st));
-    B.mt.pair_tab = m.d_pair.p; B.mt.log_tab = m.d_log.p; B.mt.n_log = (int)m.log_tab.size();
+    B.mt.pair_tab = m.d_pair.p; B.mt.log_tab = I.d_log.p; B.mt.n_log = (int)I.log_tab.size();
     CK(cudaEventRecord(m.ev[7], st));
     T("pestat_done");
 
@@ -887,7 +952,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const int fin_block = 32;
     const int items = pe ? n >> 1 : n;
     const int fin_bps = env_int("BSB_FIN_BPS", 16);
-    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)m.n_sm * fin_bps * fin_block);
+    const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)I.n_sm * fin_bps * fin_block);
     m.d_final_scratch.ensure((size_t)fin_workers * L.total);
     m.d_out.ensure(n + 1);
     B.out = m.d_out.p;
@@ -895,7 +960,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     if (m.task_cap == 0) m.task_cap = (size_t)n + (size_t)n / 2 + 4096;
     // task kernel geometry
     const int tk_wpb = 4;
-    const int tk_blocks = m.n_sm * 8;
+    const int tk_blocks = I.n_sm * 8;
     const long z_cap = (long)max_q * (long)(max_q + 2 * (4 * opt.w) + 64);
     const int tk_smem_per_warp = (2 * (max_q + 1) * 4 + (2 * max_q + 16) * 4 + (8 * max_q + 64) + (4 * max_q + 64) + max_q + 31) & ~15;
     m.d_zbuf.ensure((size_t)tk_blocks * tk_wpb * z_cap);
@@ -914,38 +979,38 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         B.arena.base = m.d_arena.p; B.arena.used = m.d_used.p; B.arena.cap = m.arena_cap;
         B.tasks.a = m.d_tasks.p; B.tasks.n = m.d_ntasks.p; B.tasks.cap = (unsigned int)m.task_cap;
         if (items) {
-            if (pe && fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
-            else if (pe && fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
-            else if (pe) k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
-            else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, m.ix, B, L, m.d_final_scratch.p);
+            if (pe && fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
+            else if (pe && fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
+            else if (pe) k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
+            else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
             ++m.launches;
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&n_tasks, m.d_ntasks.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(m.ev[10], st));
-        CK(cudaStreamSynchronize(st));
+        m.wait();
         T("select_done");
         if (n_tasks > m.task_cap) { m.task_cap = (size_t)n_tasks + (size_t)n_tasks / 4 + 4096; continue; }
         if (n_tasks && getenv("BSB_TASKS_V1")) {
-            k_tasks<<<tk_blocks, tk_wpb * 32, tk_wpb * tk_smem_per_warp, st>>>(opt, m.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, tk_smem_per_warp);
+            k_tasks<<<tk_blocks, tk_wpb * 32, tk_wpb * tk_smem_per_warp, st>>>(opt, I.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, tk_smem_per_warp);
             ++m.launches;
         } else if (n_tasks) {
             const int slot_cap = 2 * max_q + 16, md_cap = 8 * max_q + 64, xb_cap = 4 * max_q + 64;
             const int dp_smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 31) & ~15;
-            const int fin_threads = m.n_sm * 8 * 128;
+            const int fin_threads = I.n_sm * 8 * 128;
             m.d_task_cigar.ensure((size_t)n_tasks * slot_cap);
             m.d_task_ncig.ensure(n_tasks);
             m.d_task_text.ensure((size_t)fin_threads * (md_cap + xb_cap));
-            k_tasks_dp<<<tk_blocks, tk_wpb * 32, tk_wpb * dp_smem_per_warp, st>>>(opt, m.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, dp_smem_per_warp,
+            k_tasks_dp<<<tk_blocks, tk_wpb * 32, tk_wpb * dp_smem_per_warp, st>>>(opt, I.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, dp_smem_per_warp,
                                                                                    m.d_task_cigar.p, slot_cap, m.d_task_ncig.p);
-            k_tasks_finish<<<fin_threads / 128, 128, 0, st>>>(opt, m.ix, B, n_tasks, m.d_task_cigar.p, slot_cap, m.d_task_ncig.p, m.d_task_text.p, md_cap, xb_cap);
+            k_tasks_finish<<<fin_threads / 128, 128, 0, st>>>(opt, I.ix, B, n_tasks, m.d_task_cigar.p, slot_cap, m.d_task_ncig.p, m.d_task_text.p, md_cap, xb_cap);
             m.launches += 2;
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(m.ev[8], st));
         CK(cudaMemcpyAsync(&used, m.d_used.p, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out.reads.data(), m.d_out.p, (size_t)n * sizeof(ReadOut), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        m.wait();
         T("tasks_done");
         if (used <= m.arena_cap) break;
         m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
@@ -954,7 +1019,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     out.arena.resize_uninit((size_t)used);
     CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(m.ev[9], st));
-    CK(cudaStreamSynchronize(st));
+    m.wait();
     T("d2h_done");
     for (int r = 0; r < n; ++r)
         if (out.reads[r].err)

@@ -44,6 +44,7 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     s->kernel_launches = al ? al->kernel_launches() : 0;
     s->sec_read = sum.sec_read; s->sec_format = sum.sec_format; s->sec_write = sum.sec_write;
     s->ms_select = sum.ms_select; s->ms_tasks = sum.ms_tasks; s->n_tasks = (int64_t)sum.n_tasks;
+    s->sec_resident = sum.sec_resident;
 }
 
 extern "C" {
@@ -144,7 +145,8 @@ bsb_batch_t *bsb_batch_create(bsb_index_t *idx, int opt_argc, char **opt_argv, i
             if (r2) { k2.name = r2[i].name; k2.seq = r2[i].seq; if (r2[i].comment) k2.comment = r2[i].comment; if (r2[i].qual) k2.qual = r2[i].qual; trim(k2.name); }
             int pattern = 0, both = 0;
             if (opt.undirectional) {
-                int t = r2 ? assess_conversion(k1.seq, k2.seq, 1, opt.substitution_proportion) : assess_conversion(k1.seq, k1.seq, 0, opt.substitution_proportion);
+                int t = r2 ? assess_conversion(k1.seq.data(), k1.seq.size(), k2.seq.data(), k2.seq.size(), 1, opt.substitution_proportion)
+                           : assess_conversion(k1.seq.data(), k1.seq.size(), k1.seq.data(), k1.seq.size(), 0, opt.substitution_proportion);
                 if (t == 2) both = 1; else pattern = t;
             }
             b->reads.add(k1, b->ma.copy_comment, 0, 0, pattern);

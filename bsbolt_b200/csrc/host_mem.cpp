@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <deque>
 #include <memory>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -765,11 +766,45 @@ private:
 };
 
 struct Job {
+    BatchPlan plan;
     ReadBatch batch;
     BatchResult res;
     int64_t n_processed = 0;
     long batch_id = 0;
+    long seq = 0;              // position in this run's stream of batches (batch_id skips other shards' batches)
     double sec_align = 0;
+};
+
+// hands finished batches to the formatter in input order, whichever device slot finished first
+class OrderedDone {
+public:
+    void push(std::unique_ptr<Job> j)
+    {
+        std::lock_guard<std::mutex> l(m_);
+        const long k = j->seq;
+        ready_[k] = std::move(j);
+        cv_.notify_all();
+    }
+    bool pop(std::unique_ptr<Job> &j)
+    {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return aborted_ || ready_.count(next_) || (producers_ == 0 && ready_.empty()); });
+        if (aborted_ || !ready_.count(next_)) return false;
+        j = std::move(ready_[next_]);
+        ready_.erase(next_);
+        ++next_;
+        return true;
+    }
+    void add_producer() { std::lock_guard<std::mutex> l(m_); ++producers_; }
+    void producer_done() { std::lock_guard<std::mutex> l(m_); --producers_; cv_.notify_all(); }
+    void abort() { std::lock_guard<std::mutex> l(m_); aborted_ = true; cv_.notify_all(); }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::map<long, std::unique_ptr<Job>> ready_;
+    long next_ = 0;
+    int producers_ = 0;
+    bool aborted_ = false;
 };
 } // namespace
 
@@ -793,56 +828,110 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
         if (shard_index == 0) fprintf(parts, "-1\t0\t%zu\n", hdr.size());
     }
     RunSummary sum;
+    // formatter threads: this process's share of the cores (one process per GPU under torchrun / the shard launcher),
+    // minus the reader, the parser threads and the device threads, which must never wait for a core
     int host_threads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) host_threads /= std::max(1, atoi(e));
+    else if (ma.shard_count > 1) host_threads /= ma.shard_count;
+    host_threads -= 5;
     if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
-    Channel<std::unique_ptr<Job>> q_read(2), q_done(2), q_free(8);
-    for (int k = 0; k < 4; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
+    int n_slots = aligner.slots();
+    if (const char *e = getenv("BSB_GPU_SLOTS")) n_slots = std::max(1, std::min(n_slots, atoi(e)));
+    Channel<std::unique_ptr<Job>> q_plan(2), q_read(2), q_free(16);
+    OrderedDone q_done;
+    for (int k = 0; k < 5 + 2 * n_slots; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
     std::string fail;
     std::mutex fail_m;
     auto set_fail = [&](const std::string &w) { std::lock_guard<std::mutex> l(fail_m); if (fail.empty()) fail = w; };
     std::mutex log_m;
 
-    double sec_read = 0;
+    // BSB_RESIDENT_BENCH (measurement): read and upload every batch first, then release them to the device slots at
+    // once; sec_resident = wall time from that moment to the last batch leaving the device
+    const bool resident = getenv("BSB_RESIDENT_BENCH") != nullptr;
+    std::vector<std::unique_ptr<Job>> held;
+    double t_res0 = 0, t_res1 = 0;
+    std::mutex res_m;
+    double sec_plan = 0, sec_fill = 0;
+    // reader, first half: cut the input into the reference's batches (serial walk over the parsers' records)
     std::thread t_read([&] {
         try {
             int64_t n_processed = 0;
-            long batch_id = 0;
+            long batch_id = 0, seq = 0;
             for (;;) {
                 std::unique_ptr<Job> j;
-                if (!q_free.pop(j)) break;
+                if (resident) j.reset(new Job);
+                else if (!q_free.pop(j)) break;
                 double tr = now_sec();
-                if (!read_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.copy_comment, ma.opt.undirectional, ma.opt.substitution_proportion, j->batch)) break;
-                if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", j->batch.n, (long)j->batch.n_bases); }
-                sec_read += now_sec() - tr;
+                if (!plan_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.opt.undirectional, ma.opt.substitution_proportion, j->plan)) break;
+                sec_plan += now_sec() - tr;
+                const int n = (int)j->plan.ents.size();
                 j->n_processed = n_processed;
                 j->batch_id = batch_id++;
-                n_processed += j->batch.n;
-                if (j->batch_id % shard_count != shard_index) { q_free.push(std::move(j)); continue; } // another GPU's batch
-                q_read.push(std::move(j));
+                n_processed += n;
+                j->seq = -1;
+                if (j->batch_id % shard_count == shard_index) j->seq = seq++;   // else: another GPU's batch, only its blocks are released
+                q_plan.push(std::move(j));
                 { std::lock_guard<std::mutex> l(fail_m); if (!fail.empty()) break; }
             }
         } catch (const std::exception &e) { set_fail(e.what()); }
-        q_read.close();
+        q_plan.close();
     });
-    std::thread t_gpu([&] {
+    // reader, second half: copy the batch into its flat (page-locked) arrays while the next one is being cut
+    std::thread t_fill([&] {
         try {
+            const int nt = host_fill_threads();
             std::unique_ptr<Job> j;
-            while (q_read.pop(j)) {
-                double ta = now_sec();
-                aligner.align(ma.opt, j->batch, j->n_processed, ma.have_pes0 ? ma.pes0 : nullptr, j->res);
-                j->sec_align = now_sec() - ta;
-                if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", j->batch.n, j->sec_align); }
-                q_done.push(std::move(j));
+            while (q_plan.pop(j)) {
+                if (j->seq < 0) {
+                    r1.release_until(j->plan.mark1);
+                    if (r2) r2->release_until(j->plan.mark2);
+                    q_free.push(std::move(j));
+                    continue;
+                }
+                double tr = now_sec();
+                fill_batch(j->plan, &r1, r2.get(), ma.copy_comment, nt, j->batch);
+                sec_fill += now_sec() - tr;
+                if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", j->batch.n, (long)j->batch.n_bases); }
+                if (resident) { aligner.preload(j->batch); held.push_back(std::move(j)); continue; }
+                q_read.push(std::move(j));
+            }
+            if (resident) {
+                t_res0 = now_sec();
+                for (auto &h : held) q_read.push(std::move(h));
+                held.clear();
             }
         } catch (const std::exception &e) {
             set_fail(e.what());
             std::unique_ptr<Job> j;
-            while (q_read.pop(j)) {} // drain so that the reader can finish
+            while (q_plan.pop(j)) {}
         }
-        q_done.close();
+        q_read.close();
     });
+    // one host thread per device slot: batches are taken in input order and may finish out of order
+    std::vector<std::thread> t_gpu;
+    for (int slot = 0; slot < n_slots; ++slot) q_done.add_producer();
+    for (int slot = 0; slot < n_slots; ++slot)
+        t_gpu.emplace_back([&, slot] {
+            try {
+                std::unique_ptr<Job> j;
+                while (q_read.pop(j)) {
+                    double ta = now_sec();
+                    aligner.align(ma.opt, j->batch, j->n_processed, ma.have_pes0 ? ma.pes0 : nullptr, j->res, slot);
+                    j->sec_align = now_sec() - ta;
+                    { std::lock_guard<std::mutex> l(res_m); t_res1 = std::max(t_res1, now_sec()); }
+                    if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", j->batch.n, j->sec_align); }
+                    q_done.push(std::move(j));
+                }
+            } catch (const std::exception &e) {
+                set_fail(e.what());
+                q_done.abort();
+                std::unique_ptr<Job> j;
+                while (q_read.pop(j)) {} // drain so that the reader can finish
+            }
+            q_done.producer_done();
+        });
     {
         std::vector<std::string> sam;
         std::vector<EntryStats> st;
@@ -887,15 +976,18 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 ++sum.n_batches;
                 sum.n_entries += batch.n;
             } catch (const std::exception &e) { set_fail(e.what()); }
-            q_free.push(std::move(j));
+            if (resident) { aligner.unload(j->batch); j.reset(); }
+            else q_free.push(std::move(j));
         }
     }
     q_free.close();
-    t_gpu.join();
+    for (auto &t : t_gpu) t.join();
+    t_fill.join();
     t_read.join();
     fflush(out);
     if (parts) fclose(parts);
-    sum.sec_read = sec_read;
+    sum.sec_read = std::max(sec_plan, sec_fill);   // the slower of the reader's two overlapped halves
+    sum.sec_resident = resident ? t_res1 - t_res0 : 0;
     sum.sec_total = now_sec() - t0;
     if (summary) *summary = sum;
     if (!fail.empty()) throw std::runtime_error(fail);

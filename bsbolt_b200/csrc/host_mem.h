@@ -57,7 +57,14 @@ public:
     virtual ~BatchAligner() {}
     // Aligns one batch. n_processed is the number of bseq entries in all earlier batches.
     // Throws std::runtime_error on device errors or scratch overflow (never truncates silently).
-    virtual void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out) = 0;
+    // `slot` < slots() selects one of the aligner's independent batch contexts; calls on different slots may run
+    // concurrently from different host threads.
+    virtual void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot = 0) = 0;
+    virtual int slots() const { return 1; }
+    // Measurement aid: uploads the inputs of `b` ahead of time (b.dev_input) so that a following align() starts with
+    // its batch already resident in device memory; unload() frees them.
+    virtual void preload(ReadBatch &) {}
+    virtual void unload(ReadBatch &) {}
 };
 
 struct EntryStats { int alignment_score = 0, mapped = 0, bs_conflict = 0, crick = 0, paired = 0; };
@@ -86,6 +93,7 @@ void build_pair_table(const Opt &opt, const PeStat pes[4], std::vector<double> &
 struct RunSummary {
     MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0;
     double sec_read = 0, sec_format = 0, sec_write = 0; // busy time of the reader / formatter / output stages
+    double sec_resident = 0;  // BSB_RESIDENT_BENCH: wall time from "all batches resident on the device" to "last batch aligned"
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0, n_tasks = 0;
     double ms_select = 0, ms_tasks = 0;

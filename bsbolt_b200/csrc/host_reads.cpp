@@ -1,6 +1,7 @@
 // host_reads.cpp -- see host_reads.h
 #include "host_reads.h"
 #include <ctype.h>
+#include <algorithm>
 #include <string.h>
 #include <stdio.h>
 #include <condition_variable>
@@ -21,12 +22,19 @@ static const int kBuf = 1 << 20;
 
 // Parsing (and gunzip) of each input file runs on its own thread; records reach the batcher in blocks.
 struct FastxReader::Prefetch {
-    struct Block { std::vector<FastxRecord> rec; int n = 0; int status = 0; };
+    struct Block {
+        std::vector<FastxRecord> rec;   // general parser: the records themselves
+        std::vector<char> raw;          // fast parser: one piece of the file
+        std::vector<RecView> view;      // what the batcher reads, either way
+        int n = 0; int status = 0;
+    };
     static const int kBlock = 4096;
+    static const size_t kPiece = 8u << 20;
     std::mutex m;
     std::condition_variable cv;
     std::deque<std::unique_ptr<Block>> ready, spare;
-    std::vector<std::unique_ptr<Block>> held;   // consumed blocks whose records a batch still points into
+    std::deque<std::unique_ptr<Block>> held;    // consumed blocks whose records a batch may still point into, oldest first
+    uint64_t n_retired = 0, n_released = 0;     // blocks ever moved to `held` / ever recycled from it
     std::unique_ptr<Block> cur;
     int pos = 0;
     bool done = false, stop = false;
@@ -38,6 +46,11 @@ FastxReader::FastxReader(const std::string &path) : buf_(kBuf)
     fp_ = path == "-" ? gzdopen(0, "r") : gzopen(path.c_str(), "r");
     if (!fp_) throw std::runtime_error("[E::main_mem] fail to open file `" + path + "'.");
     gzbuffer(fp_, 1 << 20);
+    if (path != "-" && gzdirect(fp_) && !getenv("BSB_SLOW_READER")) {   // not compressed: try the fast parser
+        raw_ = fopen(path.c_str(), "rb");
+        if (raw_ && fseeko(raw_, 0, SEEK_END) != 0) { fclose(raw_); raw_ = nullptr; }   // pipes and the like
+        if (raw_) { rewind(raw_); setvbuf(raw_, nullptr, _IONBF, 0); }
+    }
     pf_ = new Prefetch;
     pf_->th = std::thread([this] { pump(); });
 }
@@ -51,6 +64,7 @@ FastxReader::~FastxReader()
         delete pf_;
     }
     if (fp_) gzclose(fp_);
+    if (raw_) fclose(raw_);
 }
 
 void FastxReader::pump()
@@ -64,12 +78,20 @@ void FastxReader::pump()
             if (P.stop) return;
             if (!P.spare.empty()) { b = std::move(P.spare.front()); P.spare.pop_front(); }
         }
-        if (!b) { b.reset(new Prefetch::Block); b->rec.resize(Prefetch::kBlock); }
+        if (!b) b.reset(new Prefetch::Block);
         b->n = 0; b->status = 0;
-        while (b->n < Prefetch::kBlock) {
-            int r = next_raw(b->rec[b->n]);
-            if (r < 0) { b->status = r; break; }
-            ++b->n;
+        if (!raw_ || !pump_fast_block(b.get())) {
+            if (b->rec.size() < (size_t)Prefetch::kBlock) b->rec.resize(Prefetch::kBlock);
+            b->view.resize(Prefetch::kBlock);
+            while (b->n < Prefetch::kBlock) {
+                FastxRecord &k = b->rec[b->n];
+                int r = next_raw(k);
+                if (r < 0) { b->status = r; break; }
+                RecView &v = b->view[b->n];
+                v.name = k.name.data(); v.name_l = (uint32_t)k.name.size(); v.cmt = k.comment.data(); v.cmt_l = (uint32_t)k.comment.size();
+                v.seq = k.seq.data(); v.seq_l = (uint32_t)k.seq.size(); v.qual = k.qual.data(); v.qual_l = (uint32_t)k.qual.size();
+                ++b->n;
+            }
         }
         bool last = b->status < 0;
         {
@@ -82,13 +104,64 @@ void FastxReader::pump()
     }
 }
 
+// Cuts one piece of the file into records. Returns false (block untouched) when the general parser has to take over:
+// raw_ is then closed and the zlib stream positioned on the first byte that was not handed out.
+bool FastxReader::pump_fast_block(void *block)
+{
+    Prefetch::Block &b = *static_cast<Prefetch::Block *>(block);
+    std::vector<char> &raw = b.raw;
+    raw.resize(carry_.size() + Prefetch::kPiece);
+    if (!carry_.empty()) memcpy(raw.data(), carry_.data(), carry_.size());
+    const size_t got = fread(raw.data() + carry_.size(), 1, Prefetch::kPiece, raw_);
+    const size_t len = carry_.size() + got;
+    const bool at_eof = got < Prefetch::kPiece;
+    carry_.clear();
+    b.view.clear();
+    const char *base = raw.data(), *end = base + len;
+    const char *p = base;
+    bool give_up = false;
+    while (p < end) {
+        const char *l0 = p, *e0, *e1, *e2, *e3;
+        if (!(e0 = (const char *)memchr(l0, '\n', end - l0))) break;
+        if (!(e1 = (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)))) break;
+        if (!(e2 = (const char *)memchr(e1 + 1, '\n', end - (e1 + 1)))) break;
+        if (!(e3 = (const char *)memchr(e2 + 1, '\n', end - (e2 + 1)))) break;
+        const char *seq = e0 + 1, *qual = e2 + 1;
+        const size_t sl = (size_t)(e1 - seq), ql = (size_t)(e3 - qual);
+        // anything but "@name[ comment]\nSEQ\n+...\nQUAL\n" with |SEQ| == |QUAL| > 0 and no carriage returns
+        if (*l0 != '@' || e0 == l0 + 1 || e1[1] != '+' || sl == 0 || sl != ql || seq[0] == '+' || seq[0] == '>' || seq[0] == '@' ||
+            e0[-1] == '\r' || e1[-1] == '\r' || e3[-1] == '\r') { give_up = true; break; }
+        const char *nm = l0 + 1, *q = nm;
+        while (q < e0 && !isspace((unsigned char)*q)) ++q;
+        if (q == nm) { give_up = true; break; }
+        RecView v;
+        v.name = nm; v.name_l = (uint32_t)(q - nm);
+        v.cmt = q < e0 ? q + 1 : e0; v.cmt_l = (uint32_t)(e0 - v.cmt);
+        v.seq = seq; v.seq_l = (uint32_t)sl; v.qual = qual; v.qual_l = (uint32_t)ql;
+        b.view.push_back(v);
+        p = e3 + 1;
+    }
+    const size_t used = (size_t)(p - base);
+    raw_off_ += (int64_t)used;
+    if (!give_up && !at_eof) carry_.assign(p, end);          // an incomplete record: finish it with the next piece
+    else if (give_up || p < end) {                            // unrecognised record, or a tail without its last newline
+        fclose(raw_); raw_ = nullptr;
+        gzseek(fp_, raw_off_, SEEK_SET);
+        begin_ = end_ = 0; is_eof_ = false; last_char_ = 0;
+        if (b.view.empty()) return false;
+    }
+    b.n = (int)b.view.size();
+    if (at_eof && !give_up && p >= end) { b.status = -1; fclose(raw_); raw_ = nullptr; gzseek(fp_, 0, SEEK_END); begin_ = end_ = 0; is_eof_ = true; }
+    return true;
+}
+
 int FastxReader::next(FastxRecord &r)
 {
     Prefetch &P = *pf_;
     for (;;) {
         if (P.cur && P.pos < P.cur->n) {
-            FastxRecord &s = P.cur->rec[P.pos++];
-            r.name.swap(s.name); r.comment.swap(s.comment); r.seq.swap(s.seq); r.qual.swap(s.qual);
+            const RecView &s = P.cur->view[P.pos++];
+            r.name.assign(s.name, s.name_l); r.comment.assign(s.cmt, s.cmt_l); r.seq.assign(s.seq, s.seq_l); r.qual.assign(s.qual, s.qual_l);
             return (int)r.seq.size();
         }
         if (P.cur && P.cur->status < 0) return P.cur->status;
@@ -103,14 +176,14 @@ int FastxReader::next(FastxRecord &r)
     }
 }
 
-FastxRecord *FastxReader::next_ptr()
+RecView *FastxReader::next_ptr()
 {
     Prefetch &P = *pf_;
     for (;;) {
-        if (P.cur && P.pos < P.cur->n) return &P.cur->rec[P.pos++];
+        if (P.cur && P.pos < P.cur->n) return &P.cur->view[P.pos++];
         if (P.cur && P.cur->status < 0) return nullptr;
-        if (P.cur) P.held.push_back(std::move(P.cur));
         std::unique_lock<std::mutex> l(P.m);
+        if (P.cur) { P.held.push_back(std::move(P.cur)); ++P.n_retired; }
         P.cv.wait(l, [&] { return !P.ready.empty() || P.done; });
         if (P.ready.empty()) return nullptr;
         P.cur = std::move(P.ready.front());
@@ -120,13 +193,21 @@ FastxRecord *FastxReader::next_ptr()
     }
 }
 
-void FastxReader::release_held()
+uint64_t FastxReader::hold_mark()
+{
+    std::lock_guard<std::mutex> l(pf_->m);
+    return pf_->n_retired;
+}
+
+void FastxReader::release_until(uint64_t mark)
 {
     Prefetch &P = *pf_;
-    if (P.held.empty()) return;
     std::lock_guard<std::mutex> l(P.m);
-    for (auto &b : P.held) P.spare.push_back(std::move(b));
-    P.held.clear();
+    while (P.n_released < mark && !P.held.empty()) {
+        P.spare.push_back(std::move(P.held.front()));
+        P.held.pop_front();
+        ++P.n_released;
+    }
     P.cv.notify_all();
 }
 
@@ -238,23 +319,23 @@ void ReadBatch::reserve_like(const ReadBatch &o)
     seq_off.reserve(k); name_off.reserve(k); cmt_off.reserve(k); has_qual.reserve(k); first.reserve(k); read_group.reserve(k); pattern.reserve(k);
 }
 
-static int count_base(const std::string &s, char b)
+static int count_base(const char *s, size_t n, char b)
 {
     float c = 0;
-    size_t l = strnlen(s.data(), s.size());
+    size_t l = strnlen(s, n);
     for (size_t i = 0; i < l; ++i) if (s[i] == b) ++c;
     return (int)c;
 }
 
-int assess_conversion(const std::string &s1, const std::string &s2, int paired_end, float substitution_proportion)
+int assess_conversion(const char *s1, size_t l1, const char *s2, size_t l2, int paired_end, float substitution_proportion)
 {
-    float observed = (float)strnlen(s1.data(), s1.size());
-    float c_count = (float)count_base(s1, 'C');
-    float g_count = (float)count_base(s1, 'G');
+    float observed = (float)strnlen(s1, l1);
+    float c_count = (float)count_base(s1, l1, 'C');
+    float g_count = (float)count_base(s1, l1, 'G');
     if (paired_end) {
-        observed += (float)strnlen(s2.data(), s2.size());
-        g_count += (float)count_base(s2, 'C');
-        c_count += (float)count_base(s2, 'G');
+        observed += (float)strnlen(s2, l2);
+        g_count += (float)count_base(s2, l2, 'C');
+        c_count += (float)count_base(s2, l2, 'G');
     }
     float c_prop = c_count / observed;
     float g_prop = g_count / observed;
@@ -267,10 +348,10 @@ int assess_conversion(const std::string &s1, const std::string &s2, int paired_e
     else return 1;
 }
 
-static void trim_readno(std::string &s)
+static void trim_readno(RecView &v)
 {
-    size_t l = s.size();
-    if (l > 2 && s[l - 2] == '/' && isdigit((unsigned char)s[l - 1])) s.resize(l - 2);
+    size_t l = v.name_l;
+    if (l > 2 && v.name[l - 2] == '/' && isdigit((unsigned char)v.name[l - 1])) v.name_l = (uint32_t)(l - 2);
 }
 
 void ReadBatch::fill(const std::vector<Entry> &e, bool keep_comment, int n_threads)
@@ -282,23 +363,23 @@ void ReadBatch::fill(const std::vector<Entry> &e, bool keep_comment, int n_threa
     uint32_t so = 0, no = 0, co = 0;
     for (size_t i = 0; i < m; ++i) {
         seq_off[i] = so; name_off[i] = no; cmt_off[i] = co;
-        so += e[i].len; no += (uint32_t)e[i].rec->name.size();
-        if (keep_comment) co += (uint32_t)e[i].rec->comment.size();
+        so += e[i].len; no += e[i].rec->name_l;
+        if (keep_comment) co += e[i].rec->cmt_l;
     }
     seq_off[m] = so; name_off[m] = no; cmt_off[m] = co;
     bases.resize(so); qual.resize(so); names.resize(no); comments.resize(co);
     n = (int)m; n_bases = so;
     auto work = [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) {
-            const FastxRecord &r = *e[i].rec;
+            const RecView &r = *e[i].rec;
             const size_t l = e[i].len;
-            memcpy(bases.data() + seq_off[i], r.seq.data(), l);
-            const bool hq = !r.qual.empty();
-            if (hq) memcpy(qual.data() + seq_off[i], r.qual.data(), l);
+            memcpy(bases.data() + seq_off[i], r.seq, l);
+            const bool hq = r.qual_l != 0;
+            if (hq) memcpy(qual.data() + seq_off[i], r.qual, l);
             else memset(qual.data() + seq_off[i], '*', l);
             has_qual[i] = hq;
-            memcpy(names.data() + name_off[i], r.name.data(), r.name.size());
-            if (keep_comment) memcpy(comments.data() + cmt_off[i], r.comment.data(), r.comment.size());
+            memcpy(names.data() + name_off[i], r.name, r.name_l);
+            if (keep_comment) memcpy(comments.data() + cmt_off[i], r.cmt, r.cmt_l);
             first[i] = e[i].first; read_group[i] = e[i].read_group; pattern[i] = e[i].pattern;
         }
     };
@@ -313,34 +394,33 @@ void ReadBatch::fill(const std::vector<Entry> &e, bool keep_comment, int n_threa
     for (auto &x : th) x.join();
 }
 
-bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,
-                float substitution_proportion, ReadBatch &b)
+bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undirectional, float substitution_proportion, BatchPlan &plan)
 {
-    // phase 1 (serial, no copying): walk the parsers' record blocks, apply the reference's batching rule
-    static thread_local std::vector<ReadBatch::Entry> ents;
+    // serial, no copying: walk the parsers' record blocks, apply the reference's batching rule (bwa.c:73-145)
+    std::vector<ReadBatch::Entry> &ents = plan.ents;
     ents.clear();
     int64_t size = 0;
-    auto push = [&](FastxRecord *k, int first, int rg, int pattern) {
-        uint32_t l = (uint32_t)strnlen(k->seq.data(), k->seq.size());
+    auto push = [&](RecView *k, int first, int rg, int pattern) {
+        uint32_t l = (uint32_t)strnlen(k->seq, k->seq_l);
         ents.push_back(ReadBatch::Entry{k, l, (uint8_t)first, (uint8_t)rg, (uint8_t)pattern});
         size += l;
     };
-    FastxRecord *k1, *k2 = nullptr;
+    RecView *k1, *k2 = nullptr;
     while ((k1 = r1->next_ptr()) != nullptr) {
         if (r2 && (k2 = r2->next_ptr()) == nullptr) {
             fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", "bseq_read");
             break;
         }
-        trim_readno(k1->name);
+        trim_readno(*k1);
         int pattern = 0, compare_reads = 0;
         if (undirectional) {
-            int un_type = r2 ? assess_conversion(k1->seq, k2->seq, 1, substitution_proportion)
-                             : assess_conversion(k1->seq, k1->seq, 0, substitution_proportion);
+            int un_type = r2 ? assess_conversion(k1->seq, k1->seq_l, k2->seq, k2->seq_l, 1, substitution_proportion)
+                             : assess_conversion(k1->seq, k1->seq_l, k1->seq, k1->seq_l, 0, substitution_proportion);
             if (un_type == 2) compare_reads = 1;
             else pattern = un_type;
         }
         push(k1, 0, 0, pattern);
-        if (r2) { trim_readno(k2->name); push(k2, 1, 0, pattern ? 0 : 1); }
+        if (r2) { trim_readno(*k2); push(k2, 1, 0, pattern ? 0 : 1); }
         if (compare_reads) {
             push(k1, 0, 1, 1);
             if (r2) push(k2, 1, 1, 0);
@@ -350,15 +430,36 @@ bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_
     if (size == 0 && ents.empty()) {
         if (r2 && r1->next_ptr() == nullptr && r2->next_ptr() != nullptr) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", "bseq_read");
     }
-    // phase 2 (parallel): copy into the flat batch arrays
-    int nt = (int)std::thread::hardware_concurrency() / 4;
-    if (const char *e = getenv("BSB_HOST_THREADS")) nt = atoi(e) / 4;
-    if (nt < 1) nt = 1;
-    if (nt > 4) nt = 4;
-    b.fill(ents, keep_comment, nt);
-    r1->release_held();
-    if (r2) r2->release_held();
-    return b.n > 0;
+    // the block each parser is standing in may also hold records of the next batch: it is not part of this mark
+    plan.mark1 = r1->hold_mark();
+    plan.mark2 = r2 ? r2->hold_mark() : 0;
+    return !ents.empty();
 }
+
+void fill_batch(const BatchPlan &plan, FastxReader *r1, FastxReader *r2, bool keep_comment, int n_threads, ReadBatch &b)
+{
+    b.fill(plan.ents, keep_comment, n_threads);
+    r1->release_until(plan.mark1);
+    if (r2) r2->release_until(plan.mark2);
+}
+
+static int fill_threads()
+{
+    int nt = (int)std::thread::hardware_concurrency() / 2;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(e));
+    if (const char *e = getenv("BSB_HOST_THREADS")) nt = atoi(e) / 2;
+    return nt < 1 ? 1 : nt > 8 ? 8 : nt;
+}
+
+bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,
+                float substitution_proportion, ReadBatch &b)
+{
+    static thread_local BatchPlan plan;
+    const bool any = plan_batch(chunk_size, r1, r2, undirectional, substitution_proportion, plan);
+    fill_batch(plan, r1, r2, keep_comment, fill_threads(), b);
+    return any && b.n > 0;
+}
+
+int host_fill_threads() { return fill_threads(); }
 
 } // namespace bsb

@@ -85,6 +85,17 @@ private:
 
 struct FastxRecord { std::string name, comment, seq, qual; };
 
+// One parsed record as the batcher sees it: spans into the parser's block (text of the file itself on the fast path)
+struct RecView {
+    const char *name, *cmt, *seq, *qual;
+    uint32_t name_l, cmt_l, seq_l, qual_l;   // qual_l == 0: no quality string
+};
+
+// Two parsers behind one interface, each on its own thread, handing blocks of records to the batcher:
+//  * fast: plain (uncompressed, seekable) files made of strict four-line FASTQ records are read in multi-megabyte
+//    pieces and cut with memchr; records are spans into the piece, nothing is copied until the batch is filled;
+//  * general: kseq semantics (kseq.h:175-217) over zlib -- gzip, stdin, FASTA, multi-line records. The fast parser
+//    hands over to it at the byte offset of the first record it does not recognise, so results never differ.
 class FastxReader {
 public:
     explicit FastxReader(const std::string &path);
@@ -93,11 +104,16 @@ public:
     int next(FastxRecord &r);
     // zero-copy form for the batcher: the next record inside the parser's block (nullptr at end of input). The
     // pointer stays valid until release_held().
-    FastxRecord *next_ptr();
-    void release_held();
+    RecView *next_ptr();
+    // Blocks the batcher has walked past stay alive until released. hold_mark() names the blocks fully consumed so
+    // far; release_until(mark) recycles them (callable from another thread than next_ptr()'s).
+    uint64_t hold_mark();
+    void release_until(uint64_t mark);
+    void release_held() { release_until(hold_mark()); }
 private:
     int next_raw(FastxRecord &r);
     void pump();               // parser thread body
+    bool pump_fast_block(void *block);
     struct Prefetch;           // blocks of parsed records handed over from the parser thread
     Prefetch *pf_ = nullptr;
     int getc_();
@@ -108,6 +124,10 @@ private:
     int begin_ = 0, end_ = 0;
     bool is_eof_ = false;
     int last_char_ = 0;
+    // fast path
+    FILE *raw_ = nullptr;      // non-null while the fast parser is active
+    int64_t raw_off_ = 0;      // file offset of the first byte not yet handed out as a record
+    std::vector<char> carry_;  // incomplete record at the end of the previous piece
 };
 
 // One batch of bseq entries (a read aligned under both conversion patterns appears twice).
@@ -123,17 +143,27 @@ struct ReadBatch {
     std::vector<char> comments;
     std::vector<uint8_t> first, read_group, pattern;
     int64_t n_bases = 0;
+    void *dev_input = nullptr;       // set by BatchAligner::preload(): the batch's inputs are already resident on the device
 
     void clear();
     void reserve_like(const ReadBatch &o);   // pre-size for a batch about as large as o
-    struct Entry { const FastxRecord *rec; uint32_t len; uint8_t first, read_group, pattern; };
+    struct Entry { const RecView *rec; uint32_t len; uint8_t first, read_group, pattern; };
     void fill(const std::vector<Entry> &e, bool keep_comment, int n_threads);   // bulk, multi-threaded add()
     void add(const FastxRecord &r, bool keep_comment, int first, int read_group, int pattern);
     int len(int i) const { return (int)(seq_off[i + 1] - seq_off[i]); }
     std::string name(int i) const { return std::string(names.data() + name_off[i], name_off[i + 1] - name_off[i]); }
 };
 
-int assess_conversion(const std::string &s1, const std::string &s2, int paired_end, float substitution_proportion);
+int assess_conversion(const char *s1, size_t l1, const char *s2, size_t l2, int paired_end, float substitution_proportion);
+
+// The two halves of read_batch(), so that cutting batch i+1 can overlap with copying batch i: plan_batch() applies the
+// reference's batching rule and records which parser records make up the batch; fill_batch() copies them into the flat
+// arrays (multi-threaded) and lets the parsers recycle the blocks.
+struct BatchPlan { std::vector<ReadBatch::Entry> ents; uint64_t mark1 = 0, mark2 = 0; };
+bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undirectional, float substitution_proportion, BatchPlan &plan);
+void fill_batch(const BatchPlan &plan, FastxReader *r1, FastxReader *r2, bool keep_comment, int n_threads, ReadBatch &b);
+
+int host_fill_threads();   // copy threads for fill_batch(): this process's share of the cores, at most 8
 
 // Fills `b` with the next batch. Returns false when no read could be read (end of input).
 bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,

@@ -34,6 +34,8 @@ typedef struct {
     double sec_read, sec_format, sec_write; /* busy time of the host stages: FASTQ batching, SAM text, output */
     double ms_select, ms_tasks;             /* stage 7 split: record selection/pairing kernel, alignment-task kernel */
     int64_t n_tasks;                        /* global alignments queued (records + XA entries) */
+    double sec_resident;                    /* BSB_RESIDENT_BENCH=1 only (measurement): wall time from "every batch's input
+                                               resident in HBM" to "last batch left the device"; 0 otherwise */
 } bsb_run_stats_t;
 
 typedef struct {

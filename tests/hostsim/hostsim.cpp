@@ -29,7 +29,7 @@ public:
         }
     }
 
-    void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out) override
+    void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int = 0) override
     {
         const int n = b.n;
         const bool pe = (opt.flag & F_PE) != 0;

@@ -86,3 +86,41 @@ def test_merge_shards(tmp_path):
     out = io.BytesIO()
     assert merge_shards([str(tmp_path / 'a.sam'), str(tmp_path / 'b.sam')], [str(tmp_path / 'a.idx'), str(tmp_path / 'b.idx')], out) == 5
     assert out.getvalue() == b'HDR\nb0\nb1\nb2\nb3\n'
+
+
+def test_reader_variants_give_identical_batches(built, golden, tmp_path):
+    """The fast plain-FASTQ parser and the general kseq-style parser (gzip, CRLF, missing final newline, a record the
+    fast parser does not recognise in the middle of the file) must cut identical reads and batches."""
+    import gzip
+    import subprocess
+    hostsim = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
+    src = open(os.path.join(golden.dir, golden.cases['se100']['fq'][0])).read().split('\n')
+    recs = [src[i:i + 4] for i in range(0, 4 * 3000, 4)]
+    plain = ''.join('\n'.join(r) + '\n' for r in recs)
+    variants = {'plain.fq': plain.encode(), 'nonl.fq': plain[:-1].encode(), 'crlf.fq': plain.replace('\n', '\r\n').encode()}
+    # record 1500 with its sequence and quality folded over two lines each: only the general parser reads that
+    folded = []
+    for k, r in enumerate(recs):
+        if k == 1500:
+            h = len(r[1]) // 2
+            folded.append('\n'.join([r[0], r[1][:h], r[1][h:], r[2], r[3][:h], r[3][h:]]) + '\n')
+        else:
+            folded.append('\n'.join(r) + '\n')
+    variants['folded.fq'] = ''.join(folded).encode()
+    outs = {}
+    for name, data in variants.items():
+        (tmp_path / name).write_bytes(data)
+    with gzip.open(tmp_path / 'plain.fq.gz', 'wb') as f:
+        f.write(plain.encode())
+    for name in list(variants) + ['plain.fq.gz']:
+        argv = [hostsim, 'mem'] + golden.manifest['launcher_args'] + ['-K', '70000', golden.idxbase, str(tmp_path / name)]
+        p = subprocess.run(argv, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-1500:]
+        outs[name] = ''.join(l + '\n' for l in p.stdout.split('\n') if l and not l.startswith('@PG'))
+    env = dict(os.environ, BSB_SLOW_READER='1')
+    p = subprocess.run([hostsim, 'mem'] + golden.manifest['launcher_args'] + ['-K', '70000', golden.idxbase, str(tmp_path / 'plain.fq')],
+                       capture_output=True, text=True, env=env)
+    want = ''.join(l + '\n' for l in p.stdout.split('\n') if l and not l.startswith('@PG'))
+    assert want.count('\n') > 1000
+    for name, got in outs.items():
+        assert got == want, name
