@@ -841,7 +841,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (const char *e = getenv("BSB_GPU_SLOTS")) n_slots = std::max(1, std::min(n_slots, atoi(e)));
     Channel<std::unique_ptr<Job>> q_plan(2), q_read(2), q_free(16);
     OrderedDone q_done;
-    for (int k = 0; k < 5 + 2 * n_slots; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
+    const int n_jobs = 5 + 2 * n_slots;
+    std::thread t_prefill;   // page-locks the transfer buffers of the other jobs while the first batches run
+    for (int k = 0; k < n_jobs; ++k) q_free.push(std::unique_ptr<Job>(new Job)); // recycled: their buffers stay mapped and sized
     std::string fail;
     std::mutex fail_m;
     auto set_fail = [&](const std::string &w) { std::lock_guard<std::mutex> l(fail_m); if (fail.empty()) fail = w; };
@@ -850,7 +852,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     // BSB_RESIDENT_BENCH (measurement): read and upload every batch first, then release them to the device slots at
     // once; sec_resident = wall time from that moment to the last batch leaving the device
     const bool resident = getenv("BSB_RESIDENT_BENCH") != nullptr;
-    std::vector<std::unique_ptr<Job>> held;
+    std::vector<std::unique_ptr<Job>> held, finished;
     double t_res0 = 0, t_res1 = 0;
     std::mutex res_m;
     double sec_plan = 0, sec_fill = 0;
@@ -942,6 +944,13 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
         while (q_done.pop(j)) {
             try {
                 const ReadBatch &batch = j->batch;
+                if (sum.n_batches == 0 && g_host_alloc.prefill && !resident && !t_prefill.joinable()) {
+                    const size_t s_bases = batch.bases.capacity(), s_arena = j->res.arena.size(), s_reads = j->res.reads.size() * sizeof(ReadOut);
+                    t_prefill = std::thread([=] {
+                        g_host_alloc.prefill(s_bases, n_jobs - 1); g_host_alloc.prefill(s_arena + s_arena / 4 + 4096, n_jobs - 1);
+                        g_host_alloc.prefill(s_reads + s_reads / 4 + 4096, n_jobs - 1);
+                    });
+                }
                 sum.sec_align += j->sec_align;
                 sum.add_timing(j->res);
                 double tf = now_sec();
@@ -976,7 +985,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 ++sum.n_batches;
                 sum.n_entries += batch.n;
             } catch (const std::exception &e) { set_fail(e.what()); }
-            if (resident) { aligner.unload(j->batch); j.reset(); }
+            if (resident) finished.push_back(std::move(j));   // device inputs are freed after the run (cudaFree synchronises the device)
             else q_free.push(std::move(j));
         }
     }
@@ -984,6 +993,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     for (auto &t : t_gpu) t.join();
     t_fill.join();
     t_read.join();
+    if (t_prefill.joinable()) t_prefill.join();
+    for (auto &h : finished) aligner.unload(h->batch);
+    finished.clear();
     fflush(out);
     if (parts) fclose(parts);
     sum.sec_read = std::max(sec_plan, sec_fill);   // the slower of the reader's two overlapped halves

@@ -15,7 +15,7 @@
 
 namespace bsb {
 
-HostAllocHooks g_host_alloc = {malloc, free};
+HostAllocHooks g_host_alloc = {malloc, free, nullptr};
 
 enum { SEP_SPACE = 0, SEP_LINE = 2 };
 static const int kBuf = 1 << 20;

@@ -15,7 +15,10 @@ namespace bsb {
 
 // Host buffers that cross PCIe are allocated through these hooks: malloc/free by default, page-locked memory
 // once the CUDA library installs its allocator (bsb_cuda.cu). Set once, before any buffer exists.
-struct HostAllocHooks { void *(*alloc)(size_t); void (*release)(void *); };
+struct HostAllocHooks {
+    void *(*alloc)(size_t); void (*release)(void *);
+    void (*prefill)(size_t bytes, int count);   // optional: make sure `count` released blocks of that size are on hand
+};
 extern HostAllocHooks g_host_alloc;
 
 // growable byte buffer without value-initialisation (a 100 MB std::vector::resize costs ~10 ms of memset)
