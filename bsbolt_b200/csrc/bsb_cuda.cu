@@ -368,6 +368,16 @@ __global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B,
     if (t < B.n) stage_chain(opt, ix, B, order ? order[t] : t);
 }
 
+// K4, one warp per read (bsb_warp.cuh)
+__global__ void __launch_bounds__(128) k_chain_warp(Opt opt, IndexView ix, BatchDev B)
+{
+    __shared__ ChainRec s_rec[4][CHAIN_MAX];
+    __shared__ int32_t s_off[4][CHAIN_MAX];
+    const int wib = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = gw; r < B.n; r += nw) stage_chain_warp(opt, ix, B, r, s_rec[wib], s_off[wib]);
+}
+
 __global__ void k_iota(int32_t *a, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -893,7 +903,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         cub::DeviceRadixSort::SortPairsDescending(m.d_cub.p, sort_bytes, (const int32_t *)m.d_n_seed.p, m.d_key_tmp.p, (const int32_t *)m.d_order_tmp.p, m.d_order.p, n, 0, 32, st);
         m.launches += 4;
     }
-    k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p); ++m.launches;
+    if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p);
+    else k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B);
+    ++m.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[5], st));
     // ---- K5 ----

@@ -139,6 +139,221 @@ __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, con
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K4, one warp per read. Chains live in the lanes (two per lane, so up to 64 per read):
+//   * the B-tree of the reference (kbtree.h, restated in bsb_chain.h) is only a map from a chain's first reference
+//     position to the chain; with DISTINCT keys "closest chain at or before x" is a predecessor query -- here one
+//     compare per lane and a warp maximum -- and the in-order traversal is the ascending order of the keys. A
+//     duplicate key (a seed that starts exactly where an existing chain starts and cannot be merged into it), whose
+//     place depends on the shape of the tree, sends the read to the serial form (stage_chain) instead;
+//   * test_and_merge (bwamem.c:194-215) runs on the lane that owns the chain; the chain weight (mem_chain_weight,
+//     bwamem.c:217-236) is accumulated as seeds are appended, in the same seed order;
+//   * mem_chain_flt (bwamem.c:331-389) runs on lane 0 over 24-byte records in shared memory -- the introsort is the
+//     order-exact restatement of bsb_hd.h, so the permutation among equal weights is the reference's.
+// ---------------------------------------------------------------------------------------------
+struct ChainRec { int32_t w, ci, beg, end, first; int8_t kept, is_alt; int16_t pad_; };
+struct LtChainRecW { __device__ bool operator()(const ChainRec &a, const ChainRec &b) const { return a.w > b.w; } };
+constexpr int CHAIN_SLOTS = 2, CHAIN_MAX = 32 * CHAIN_SLOTS;
+
+struct LaneChain {
+    int64_t pos, l_rbeg, endr;
+    int32_t rid, n, head, tail, f_qbeg, l_qbeg, l_len, wq, endq, wr;
+    int8_t is_alt; bool valid;
+};
+
+__device__ __forceinline__ int64_t warp_max_i64(int64_t v)
+{
+    for (int o = 16; o; o >>= 1) { const int64_t t = __shfl_xor_sync(FULLMASK, v, o); v = v > t ? v : t; }
+    return v;
+}
+
+// returns false when the read has to be redone by the serial form
+__device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainRec *rec, int32_t *cs_off)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t so = B.seed_off[r];
+    const int ns = (int)(B.seed_off[r + 1] - so);
+    const Seed *seeds = B.seeds + so;
+    int32_t *next = B.next + so;
+    LaneChain c[CHAIN_SLOTS];
+#pragma unroll
+    for (int q = 0; q < CHAIN_SLOTS; ++q) c[q].valid = false;
+    int n_chains = 0;
+    const int64_t l_pac = ix.l_pac;
+    for (int si = 0; si < ns; ++si) {
+        const Seed s = seeds[si];
+        if (s.rid < 0) continue;
+        // predecessor query: the chain with the largest first position <= s.rbeg
+        int64_t best = -1;
+#pragma unroll
+        for (int q = 0; q < CHAIN_SLOTS; ++q) if (c[q].valid && c[q].pos <= s.rbeg && c[q].pos > best) best = c[q].pos;
+        best = warp_max_i64(best);
+        bool merged = false;
+        if (best >= 0) {
+#pragma unroll
+            for (int q = 0; q < CHAIN_SLOTS; ++q) {
+                LaneChain &k = c[q];
+                if (!(k.valid && k.pos == best)) continue;
+                // test_and_merge
+                const int64_t qend = k.l_qbeg + k.l_len, rend = k.l_rbeg + k.l_len;
+                if (s.rid != k.rid) continue;
+                if (s.qbeg >= k.f_qbeg && s.qbeg + s.len <= qend && s.rbeg >= k.pos && s.rbeg + s.len <= rend) { merged = true; continue; }
+                if ((k.l_rbeg < l_pac || k.pos < l_pac) && s.rbeg >= l_pac) continue;
+                const int64_t x = s.qbeg - k.l_qbeg, y = s.rbeg - k.l_rbeg;
+                if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - k.l_len < opt.max_chain_gap && y - k.l_len < opt.max_chain_gap) {
+                    next[k.tail] = si; next[si] = -1;
+                    k.tail = si; ++k.n;
+                    k.l_qbeg = s.qbeg; k.l_rbeg = s.rbeg; k.l_len = s.len;
+                    if (s.qbeg >= k.endq) k.wq += s.len; else if (s.qbeg + s.len > k.endq) k.wq += s.qbeg + s.len - k.endq;
+                    k.endq = k.endq > s.qbeg + s.len ? k.endq : s.qbeg + s.len;
+                    if (s.rbeg >= k.endr) k.wr += s.len; else if (s.rbeg + s.len > k.endr) k.wr += (int)(s.rbeg + s.len - k.endr);
+                    k.endr = k.endr > s.rbeg + s.len ? k.endr : s.rbeg + s.len;
+                    merged = true;
+                }
+            }
+        }
+        if (__any_sync(FULLMASK, merged)) continue;
+        if (best == s.rbeg || n_chains >= CHAIN_MAX) return false;     // duplicate key / too many chains: serial form
+        const int ci = n_chains++;
+        if (lane == (ci & 31)) {
+#pragma unroll
+            for (int q = 0; q < CHAIN_SLOTS; ++q) {
+                if (q != ci >> 5) continue;
+                LaneChain &k = c[q];
+                k.valid = true; k.pos = s.rbeg; k.rid = s.rid; k.n = 1; k.head = k.tail = si;
+                k.f_qbeg = k.l_qbeg = s.qbeg; k.l_rbeg = s.rbeg; k.l_len = s.len;
+                k.wq = s.len; k.endq = s.qbeg + s.len; k.wr = s.len; k.endr = s.rbeg + s.len;
+                k.is_alt = (int8_t)(ix.anns[s.rid].is_alt != 0);
+                next[si] = -1;
+            }
+        }
+    }
+    // tree order = ascending first position; chains lighter than min_chain_weight are dropped before the sort
+    int w[CHAIN_SLOTS], rank[CHAIN_SLOTS];
+    bool keep[CHAIN_SLOTS];
+#pragma unroll
+    for (int q = 0; q < CHAIN_SLOTS; ++q) {
+        int v = c[q].wq < c[q].wr ? c[q].wq : c[q].wr;
+        w[q] = v < (1 << 30) ? v : (1 << 30) - 1;
+        keep[q] = c[q].valid && w[q] >= opt.min_chain_weight;
+        rank[q] = 0;
+    }
+    int n_kept = 0;
+    for (int ci = 0; ci < n_chains; ++ci) {
+        const int src = ci & 31;
+        int64_t p = 0; bool kp = false;
+#pragma unroll
+        for (int q = 0; q < CHAIN_SLOTS; ++q) if (q == ci >> 5) { p = c[q].pos; kp = keep[q]; }
+        p = __shfl_sync(FULLMASK, p, src);
+        kp = __shfl_sync(FULLMASK, (int)kp, src) != 0;
+        if (!kp) continue;
+        ++n_kept;
+#pragma unroll
+        for (int q = 0; q < CHAIN_SLOTS; ++q) rank[q] += p < c[q].pos;
+    }
+#pragma unroll
+    for (int q = 0; q < CHAIN_SLOTS; ++q)
+        if (keep[q]) {
+            ChainRec t;
+            t.w = w[q]; t.ci = lane + 32 * q; t.beg = c[q].f_qbeg; t.end = c[q].l_qbeg + c[q].l_len; t.first = -1;
+            t.kept = 0; t.is_alt = c[q].is_alt; t.pad_ = 0;
+            rec[rank[q]] = t;
+        }
+    __syncwarp();
+    // mem_chain_flt on lane 0
+    int n_out = 0;
+    if (lane == 0 && n_kept > 0) {
+        ChainRec *a = rec;
+        int n_chn = n_kept, i, k;
+        introsort((long)n_chn, a, LtChainRecW());
+        int keptl[CHAIN_MAX], nk = 0;
+        a[0].kept = 3;
+        keptl[nk++] = 0;
+        for (i = 1; i < n_chn; ++i) {
+            int large_ovlp = 0;
+            for (k = 0; k < nk; ++k) {
+                const int j = keptl[k];
+                const int b_max = a[j].beg > a[i].beg ? a[j].beg : a[i].beg;
+                const int e_min = a[j].end < a[i].end ? a[j].end : a[i].end;
+                if (e_min > b_max && (!a[j].is_alt || a[i].is_alt)) {
+                    const int li = a[i].end - a[i].beg, lj = a[j].end - a[j].beg;
+                    const int min_l = li < lj ? li : lj;
+                    if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+                        large_ovlp = 1;
+                        if (a[j].first < 0) a[j].first = i;
+                        if (a[i].w < a[j].w * opt.drop_ratio && a[j].w - a[i].w >= opt.min_seed_len << 1) break;
+                    }
+                }
+            }
+            if (k == nk) {
+                keptl[nk++] = i;
+                a[i].kept = large_ovlp ? 2 : 3;
+            }
+        }
+        for (i = 0; i < nk; ++i) {
+            ChainRec &t = a[keptl[i]];
+            if (t.first >= 0) a[t.first].kept = 1;
+        }
+        for (i = k = 0; i < n_chn; ++i) {
+            if (a[i].kept == 0 || a[i].kept == 3) continue;
+            if (++k >= opt.max_chain_extend) break;
+        }
+        for (; i < n_chn; ++i)
+            if (a[i].kept < 3) a[i].kept = 0;
+        for (i = k = 0; i < n_chn; ++i)
+            if (a[i].kept != 0) a[k++] = a[i];
+        n_out = k;
+    }
+    n_out = __shfl_sync(FULLMASK, n_out, 0);
+    __syncwarp();
+    // seed offsets of the surviving chains inside cseeds: exclusive sum of their seed counts, in output order
+    int run = 0;
+    for (int k = 0; k < n_out; ++k) {
+        const int ci = rec[k].ci, src = ci & 31;
+        int n = 0;
+#pragma unroll
+        for (int q = 0; q < CHAIN_SLOTS; ++q) if (q == ci >> 5) n = c[q].n;
+        n = __shfl_sync(FULLMASK, n, src);
+        if (lane == 0) cs_off[k] = run;
+        run += n;
+    }
+    __syncwarp();
+    // every surviving chain is written out by the lane that owns it: record + its seeds in list order
+    const float frac_rep = (float)B.l_rep[r] / (float)(int)(B.seq_off[r + 1] - B.seq_off[r]);
+    Seed *cs = B.cseeds + so;
+    for (int k = 0; k < n_out; ++k) {
+        const ChainRec t = rec[k];
+        if (lane != (t.ci & 31)) continue;
+#pragma unroll
+        for (int q = 0; q < CHAIN_SLOTS; ++q) {
+            if (q != t.ci >> 5) continue;
+            const LaneChain &k0 = c[q];
+            const int head = cs_off[k];
+            int o = head;
+            for (int j = k0.head; j >= 0; j = next[j]) cs[o++] = seeds[j];
+            Chain out;
+            out.pos = k0.pos; out.n = k0.n; out.head = head; out.tail = o - 1; out.rid = k0.rid; out.first = t.first;
+            out.w = t.w; out.kept = t.kept; out.is_alt = k0.is_alt; out.frac_rep = frac_rep;
+            B.chains[so + k] = out;
+        }
+    }
+    if (lane == 0) B.n_chain[r] = n_out;
+    __syncwarp();
+    return true;
+}
+
+__device__ void stage_chain_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainRec *rec, int32_t *cs_off)
+{
+    const int lane = threadIdx.x & 31;
+    const int ns = (int)(B.seed_off[r + 1] - B.seed_off[r]);
+    if (ns == 0 || B.err[r]) { if (lane == 0) B.n_chain[r] = 0; return; }
+    if (!chain_read_warp(opt, ix, B, r, rec, cs_off)) {
+        __syncwarp();
+        if (lane == 0) stage_chain(opt, ix, B, r);
+        __syncwarp();
+    }
+}
+
 // mem_chain2aln, warp-uniform: every lane executes the same control flow on the same values; lane 0 alone
 // writes to HBM; the two extensions per seed run across the lanes.
 __device__ void chain_to_regions_warp(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query,
