@@ -1,5 +1,7 @@
-for cfg in "" "BSB_HOST_THREADS=8" "BSB_HOST_THREADS=6" "BSB_HOST_THREADS=8 BSB_SPIN=1" "BSB_HOST_THREADS=12 BSB_SPIN=1"; do
-  env $cfg python bench.py > gpurun_out/bench_m.log 2>gpurun_out/bench_m.err
+#!/bin/bash
+# development aid: bench.py under different host/device settings, one summary line each
+for cfg in "$@"; do
+  env $cfg python bench.py --steps ${STEPS:-8} > gpurun_out/bench_m.log 2>gpurun_out/bench_m.err
   python - "$cfg" <<EOF
 import json,sys
 d=json.loads(open("gpurun_out/bench_m.log").read().strip().split("\n")[-1])
