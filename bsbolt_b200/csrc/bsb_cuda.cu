@@ -360,8 +360,7 @@ __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, u
     stage_sa(opt, ix, B, r, g);
 }
 
-// K4: thread per read, reads visited in order of decreasing seed count so that the lanes of a warp carry similar
-// work (the per-read cost is heavy-tailed: a repetitive read has thousands of seeds) and the heavy ones start first
+// K4, thread-per-read form (kept for comparison; `order` optionally permutes the reads)
 __global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B, const int32_t *order)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,18 +370,13 @@ __global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B,
 // K4, one warp per read (bsb_warp.cuh)
 __global__ void __launch_bounds__(128) k_chain_warp(Opt opt, IndexView ix, BatchDev B)
 {
-    __shared__ ChainRec s_rec[4][CHAIN_MAX];
-    __shared__ int32_t s_off[4][CHAIN_MAX];
+    __shared__ ChainSmem sm[4];
     const int wib = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int r = gw; r < B.n; r += nw) stage_chain_warp(opt, ix, B, r, s_rec[wib], s_off[wib]);
+    for (int r = gw; r < B.n; r += nw) stage_chain_warp(opt, ix, B, r, sm[wib]);
 }
 
-__global__ void k_iota(int32_t *a, int n)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = i;
-}
+
 
 __global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q)
 {
@@ -625,7 +619,6 @@ struct BatchCtx {
     DevBuf<double> d_pair;
     DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
-    DevBuf<int32_t> d_order, d_order_tmp, d_key_tmp;
     DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
@@ -894,16 +887,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[4], st));
     // ---- K4 ----
-    {   // reads by decreasing seed count
-        m.d_order.ensure(n + 1); m.d_order_tmp.ensure(n + 1); m.d_key_tmp.ensure(n + 1);
-        k_iota<<<cdiv(n, 256), 256, 0, st>>>(m.d_order_tmp.p, n); ++m.launches;
-        size_t sort_bytes = 0;
-        cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const int32_t *)m.d_n_seed.p, m.d_key_tmp.p, (const int32_t *)m.d_order_tmp.p, m.d_order.p, n, 0, 32, st);
-        m.d_cub.ensure(sort_bytes + 16);
-        cub::DeviceRadixSort::SortPairsDescending(m.d_cub.p, sort_bytes, (const int32_t *)m.d_n_seed.p, m.d_key_tmp.p, (const int32_t *)m.d_order_tmp.p, m.d_order.p, n, 0, 32, st);
-        m.launches += 4;
-    }
-    if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p);
+    if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, nullptr);
     else k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B);
     ++m.launches;
     CK(cudaGetLastError());
@@ -919,7 +903,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         const int wpb = 4;
         const int smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 15) & ~15;
         const int ext_bps = env_int("BSB_EXT_BPS", 5);
-        const int32_t *ext_order = getenv("BSB_NO_ORDER") ? nullptr : m.d_order.p;
+        const int32_t *ext_order = nullptr;
         const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)I.n_sm * ext_bps);
         m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
         if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);

@@ -161,112 +161,137 @@ struct LaneChain {
     int8_t is_alt; bool valid;
 };
 
+// maximum of non-negative 64-bit values (or -1 for "none") across the warp: two 32-bit REDUX steps
 __device__ __forceinline__ int64_t warp_max_i64(int64_t v)
 {
-    for (int o = 16; o; o >>= 1) { const int64_t t = __shfl_xor_sync(FULLMASK, v, o); v = v > t ? v : t; }
-    return v;
+    const uint64_t u = (uint64_t)(v + 1);                       // 0 = none
+    const uint32_t hi = __reduce_max_sync(FULLMASK, (uint32_t)(u >> 32));
+    const uint32_t lo = __reduce_max_sync(FULLMASK, (uint32_t)(u >> 32) == hi ? (uint32_t)u : 0u);
+    return (int64_t)((uint64_t)hi << 32 | lo) - 1;
+}
+struct LtKeyHiDesc { __device__ bool operator()(uint64_t a, uint64_t b) const { return (int32_t)(a >> 32) > (int32_t)(b >> 32); } };
+constexpr int CHAIN_STAGE = 64;   // seeds staged in shared memory at a time
+
+// test_and_merge (bwamem.c:194-215) on the lane that owns chain k; true when the seed was absorbed or appended
+__device__ __forceinline__ bool lane_chain_merge(const Opt &opt, int64_t l_pac, LaneChain &k, const Seed &s, int si, int32_t *next)
+{
+    const int64_t qend = k.l_qbeg + k.l_len, rend = k.l_rbeg + k.l_len;
+    if (s.rid != k.rid) return false;
+    if (s.qbeg >= k.f_qbeg && s.qbeg + s.len <= qend && s.rbeg >= k.pos && s.rbeg + s.len <= rend) return true;   // contained
+    if ((k.l_rbeg < l_pac || k.pos < l_pac) && s.rbeg >= l_pac) return false;                                     // other strand
+    const int64_t x = s.qbeg - k.l_qbeg, y = s.rbeg - k.l_rbeg;
+    if (!(y >= 0 && x - y <= opt.w && y - x <= opt.w && x - k.l_len < opt.max_chain_gap && y - k.l_len < opt.max_chain_gap)) return false;
+    next[k.tail] = si; next[si] = -1;
+    k.tail = si; ++k.n;
+    k.l_qbeg = s.qbeg; k.l_rbeg = s.rbeg; k.l_len = s.len;
+    // mem_chain_weight (bwamem.c:217-236), one seed at a time
+    if (s.qbeg >= k.endq) k.wq += s.len; else if (s.qbeg + s.len > k.endq) k.wq += s.qbeg + s.len - k.endq;
+    k.endq = k.endq > s.qbeg + s.len ? k.endq : s.qbeg + s.len;
+    if (s.rbeg >= k.endr) k.wr += s.len; else if (s.rbeg + s.len > k.endr) k.wr += (int)(s.rbeg + s.len - k.endr);
+    k.endr = k.endr > s.rbeg + s.len ? k.endr : s.rbeg + s.len;
+    return true;
+}
+
+__device__ __forceinline__ void lane_chain_start(const IndexView &ix, LaneChain &k, const Seed &s, int si, int32_t *next)
+{
+    k.valid = true; k.pos = s.rbeg; k.rid = s.rid; k.n = 1; k.head = k.tail = si;
+    k.f_qbeg = k.l_qbeg = s.qbeg; k.l_rbeg = s.rbeg; k.l_len = s.len;
+    k.wq = s.len; k.endq = s.qbeg + s.len; k.wr = s.len; k.endr = s.rbeg + s.len;
+    k.is_alt = (int8_t)(ix.anns[s.rid].is_alt != 0);
+    next[si] = -1;
+}
+
+__device__ __forceinline__ int lane_chain_weight(const LaneChain &k)
+{
+    const int v = k.wq < k.wr ? k.wq : k.wr;
+    return v < (1 << 30) ? v : (1 << 30) - 1;
+}
+
+__device__ __forceinline__ void lane_chain_emit(const BatchDev &B, uint32_t so, const Seed *seeds, const int32_t *next, const LaneChain &k,
+                                                const ChainRec &t, int head, int out_idx, float frac_rep)
+{
+    Seed *cs = B.cseeds + so;
+    int o = head;
+    for (int j = k.head; j >= 0; j = next[j]) cs[o++] = seeds[j];
+    Chain out;
+    out.pos = k.pos; out.n = k.n; out.head = head; out.tail = o - 1; out.rid = k.rid; out.first = t.first;
+    out.w = t.w; out.kept = t.kept; out.is_alt = k.is_alt; out.frac_rep = frac_rep;
+    B.chains[so + out_idx] = out;
 }
 
 // returns false when the read has to be redone by the serial form
-__device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainRec *rec, int32_t *cs_off)
+__device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainRec *rec, ChainRec *rec2, int32_t *cs_off,
+                                uint64_t *keys, Seed *stage)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t so = B.seed_off[r];
     const int ns = (int)(B.seed_off[r + 1] - so);
     const Seed *seeds = B.seeds + so;
     int32_t *next = B.next + so;
-    LaneChain c[CHAIN_SLOTS];
-#pragma unroll
-    for (int q = 0; q < CHAIN_SLOTS; ++q) c[q].valid = false;
+    LaneChain c0, c1;          // chain `ci` lives in lane ci & 31, in c0 when ci < 32 else c1 (two named structs: registers)
+    c0.valid = c1.valid = false;
     int n_chains = 0;
     const int64_t l_pac = ix.l_pac;
     for (int si = 0; si < ns; ++si) {
-        const Seed s = seeds[si];
+        if (si % CHAIN_STAGE == 0) {          // stage the next seeds (coalesced), then every lane reads them from shared memory
+            __syncwarp();
+            const int m = ns - si < CHAIN_STAGE ? ns - si : CHAIN_STAGE;
+            const uint2 *src = reinterpret_cast<const uint2 *>(seeds + si);
+            uint2 *dst = reinterpret_cast<uint2 *>(stage);
+            for (int t = lane; t < m * 3; t += 32) dst[t] = src[t];
+            __syncwarp();
+        }
+        const Seed s = stage[si % CHAIN_STAGE];
         if (s.rid < 0) continue;
         // predecessor query: the chain with the largest first position <= s.rbeg
         int64_t best = -1;
-#pragma unroll
-        for (int q = 0; q < CHAIN_SLOTS; ++q) if (c[q].valid && c[q].pos <= s.rbeg && c[q].pos > best) best = c[q].pos;
+        if (c0.valid && c0.pos <= s.rbeg) best = c0.pos;
+        if (c1.valid && c1.pos <= s.rbeg && c1.pos > best) best = c1.pos;
         best = warp_max_i64(best);
         bool merged = false;
         if (best >= 0) {
-#pragma unroll
-            for (int q = 0; q < CHAIN_SLOTS; ++q) {
-                LaneChain &k = c[q];
-                if (!(k.valid && k.pos == best)) continue;
-                // test_and_merge
-                const int64_t qend = k.l_qbeg + k.l_len, rend = k.l_rbeg + k.l_len;
-                if (s.rid != k.rid) continue;
-                if (s.qbeg >= k.f_qbeg && s.qbeg + s.len <= qend && s.rbeg >= k.pos && s.rbeg + s.len <= rend) { merged = true; continue; }
-                if ((k.l_rbeg < l_pac || k.pos < l_pac) && s.rbeg >= l_pac) continue;
-                const int64_t x = s.qbeg - k.l_qbeg, y = s.rbeg - k.l_rbeg;
-                if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - k.l_len < opt.max_chain_gap && y - k.l_len < opt.max_chain_gap) {
-                    next[k.tail] = si; next[si] = -1;
-                    k.tail = si; ++k.n;
-                    k.l_qbeg = s.qbeg; k.l_rbeg = s.rbeg; k.l_len = s.len;
-                    if (s.qbeg >= k.endq) k.wq += s.len; else if (s.qbeg + s.len > k.endq) k.wq += s.qbeg + s.len - k.endq;
-                    k.endq = k.endq > s.qbeg + s.len ? k.endq : s.qbeg + s.len;
-                    if (s.rbeg >= k.endr) k.wr += s.len; else if (s.rbeg + s.len > k.endr) k.wr += (int)(s.rbeg + s.len - k.endr);
-                    k.endr = k.endr > s.rbeg + s.len ? k.endr : s.rbeg + s.len;
-                    merged = true;
-                }
-            }
+            if (c0.valid && c0.pos == best) merged = lane_chain_merge(opt, l_pac, c0, s, si, next);
+            else if (c1.valid && c1.pos == best) merged = lane_chain_merge(opt, l_pac, c1, s, si, next);
         }
         if (__any_sync(FULLMASK, merged)) continue;
         if (best == s.rbeg || n_chains >= CHAIN_MAX) return false;     // duplicate key / too many chains: serial form
         const int ci = n_chains++;
         if (lane == (ci & 31)) {
-#pragma unroll
-            for (int q = 0; q < CHAIN_SLOTS; ++q) {
-                if (q != ci >> 5) continue;
-                LaneChain &k = c[q];
-                k.valid = true; k.pos = s.rbeg; k.rid = s.rid; k.n = 1; k.head = k.tail = si;
-                k.f_qbeg = k.l_qbeg = s.qbeg; k.l_rbeg = s.rbeg; k.l_len = s.len;
-                k.wq = s.len; k.endq = s.qbeg + s.len; k.wr = s.len; k.endr = s.rbeg + s.len;
-                k.is_alt = (int8_t)(ix.anns[s.rid].is_alt != 0);
-                next[si] = -1;
-            }
+            if (ci < 32) lane_chain_start(ix, c0, s, si, next);
+            else lane_chain_start(ix, c1, s, si, next);
         }
     }
     // tree order = ascending first position; chains lighter than min_chain_weight are dropped before the sort
-    int w[CHAIN_SLOTS], rank[CHAIN_SLOTS];
-    bool keep[CHAIN_SLOTS];
-#pragma unroll
-    for (int q = 0; q < CHAIN_SLOTS; ++q) {
-        int v = c[q].wq < c[q].wr ? c[q].wq : c[q].wr;
-        w[q] = v < (1 << 30) ? v : (1 << 30) - 1;
-        keep[q] = c[q].valid && w[q] >= opt.min_chain_weight;
-        rank[q] = 0;
-    }
-    int n_kept = 0;
+    const int w0 = c0.valid ? lane_chain_weight(c0) : 0, w1 = c1.valid ? lane_chain_weight(c1) : 0;
+    const bool keep0 = c0.valid && w0 >= opt.min_chain_weight, keep1 = c1.valid && w1 >= opt.min_chain_weight;
+    int rank0 = 0, rank1 = 0, n_kept = 0;
     for (int ci = 0; ci < n_chains; ++ci) {
-        const int src = ci & 31;
-        int64_t p = 0; bool kp = false;
-#pragma unroll
-        for (int q = 0; q < CHAIN_SLOTS; ++q) if (q == ci >> 5) { p = c[q].pos; kp = keep[q]; }
-        p = __shfl_sync(FULLMASK, p, src);
-        kp = __shfl_sync(FULLMASK, (int)kp, src) != 0;
+        int64_t p = ci < 32 ? c0.pos : c1.pos;
+        int kp = ci < 32 ? (int)keep0 : (int)keep1;
+        p = __shfl_sync(FULLMASK, p, ci & 31);
+        kp = __shfl_sync(FULLMASK, kp, ci & 31);
         if (!kp) continue;
         ++n_kept;
-#pragma unroll
-        for (int q = 0; q < CHAIN_SLOTS; ++q) rank[q] += p < c[q].pos;
+        rank0 += p < c0.pos; rank1 += p < c1.pos;
     }
-#pragma unroll
-    for (int q = 0; q < CHAIN_SLOTS; ++q)
-        if (keep[q]) {
-            ChainRec t;
-            t.w = w[q]; t.ci = lane + 32 * q; t.beg = c[q].f_qbeg; t.end = c[q].l_qbeg + c[q].l_len; t.first = -1;
-            t.kept = 0; t.is_alt = c[q].is_alt; t.pad_ = 0;
-            rec[rank[q]] = t;
-        }
+    if (keep0) { ChainRec t; t.w = w0; t.ci = lane; t.beg = c0.f_qbeg; t.end = c0.l_qbeg + c0.l_len; t.first = -1; t.kept = 0; t.is_alt = c0.is_alt; t.pad_ = 0; rec[rank0] = t; }
+    if (keep1) { ChainRec t; t.w = w1; t.ci = lane + 32; t.beg = c1.f_qbeg; t.end = c1.l_qbeg + c1.l_len; t.first = -1; t.kept = 0; t.is_alt = c1.is_alt; t.pad_ = 0; rec[rank1] = t; }
     __syncwarp();
     // mem_chain_flt on lane 0
     int n_out = 0;
+    // the reference sorts the chain records themselves; the permutation depends only on the weights, so 8-byte
+    // (weight, rank) keys are sorted with the same algorithm and the records are moved once, by all lanes
+    for (int t = lane; t < n_kept; t += 32) keys[t] = (uint64_t)(uint32_t)rec[t].w << 32 | (uint32_t)t;
+    __syncwarp();
+    if (lane == 0 && n_kept > 0) introsort((long)n_kept, keys, LtKeyHiDesc());
+    __syncwarp();
+    for (int t = lane; t < n_kept; t += 32) rec2[t] = rec[(uint32_t)keys[t]];
+    __syncwarp();
     if (lane == 0 && n_kept > 0) {
-        ChainRec *a = rec;
+        ChainRec *a = rec2;
         int n_chn = n_kept, i, k;
-        introsort((long)n_chn, a, LtChainRecW());
-        int keptl[CHAIN_MAX], nk = 0;
+        int32_t *keptl = cs_off;     // scratch until the offsets are computed below
+        int nk = 0;
         a[0].kept = 3;
         keptl[nk++] = 0;
         for (i = 1; i < n_chn; ++i) {
@@ -309,45 +334,34 @@ __device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const Batch
     // seed offsets of the surviving chains inside cseeds: exclusive sum of their seed counts, in output order
     int run = 0;
     for (int k = 0; k < n_out; ++k) {
-        const int ci = rec[k].ci, src = ci & 31;
-        int n = 0;
-#pragma unroll
-        for (int q = 0; q < CHAIN_SLOTS; ++q) if (q == ci >> 5) n = c[q].n;
-        n = __shfl_sync(FULLMASK, n, src);
+        const int ci = rec2[k].ci;
+        int n = ci < 32 ? c0.n : c1.n;
+        n = __shfl_sync(FULLMASK, n, ci & 31);
         if (lane == 0) cs_off[k] = run;
         run += n;
     }
     __syncwarp();
     // every surviving chain is written out by the lane that owns it: record + its seeds in list order
     const float frac_rep = (float)B.l_rep[r] / (float)(int)(B.seq_off[r + 1] - B.seq_off[r]);
-    Seed *cs = B.cseeds + so;
     for (int k = 0; k < n_out; ++k) {
-        const ChainRec t = rec[k];
+        const ChainRec t = rec2[k];
         if (lane != (t.ci & 31)) continue;
-#pragma unroll
-        for (int q = 0; q < CHAIN_SLOTS; ++q) {
-            if (q != t.ci >> 5) continue;
-            const LaneChain &k0 = c[q];
-            const int head = cs_off[k];
-            int o = head;
-            for (int j = k0.head; j >= 0; j = next[j]) cs[o++] = seeds[j];
-            Chain out;
-            out.pos = k0.pos; out.n = k0.n; out.head = head; out.tail = o - 1; out.rid = k0.rid; out.first = t.first;
-            out.w = t.w; out.kept = t.kept; out.is_alt = k0.is_alt; out.frac_rep = frac_rep;
-            B.chains[so + k] = out;
-        }
+        if (t.ci < 32) lane_chain_emit(B, so, seeds, next, c0, t, cs_off[k], k, frac_rep);
+        else lane_chain_emit(B, so, seeds, next, c1, t, cs_off[k], k, frac_rep);
     }
     if (lane == 0) B.n_chain[r] = n_out;
     __syncwarp();
     return true;
 }
 
-__device__ void stage_chain_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainRec *rec, int32_t *cs_off)
+struct ChainSmem { ChainRec rec[CHAIN_MAX], rec2[CHAIN_MAX]; uint64_t keys[CHAIN_MAX]; int32_t off[CHAIN_MAX]; Seed stage[CHAIN_STAGE]; };
+
+__device__ void stage_chain_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainSmem &S)
 {
     const int lane = threadIdx.x & 31;
     const int ns = (int)(B.seed_off[r + 1] - B.seed_off[r]);
     if (ns == 0 || B.err[r]) { if (lane == 0) B.n_chain[r] = 0; return; }
-    if (!chain_read_warp(opt, ix, B, r, rec, cs_off)) {
+    if (!chain_read_warp(opt, ix, B, r, S.rec, S.rec2, S.off, S.keys, S.stage)) {
         __syncwarp();
         if (lane == 0) stage_chain(opt, ix, B, r);
         __syncwarp();
