@@ -309,6 +309,15 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = SEED_BYTES_PER_READ * reads_per_launch / (seed_ms / 1000) / 1e9
+    traffic, layout = None, {}
+    try:   # one ncu --set full capture of the same kernel on the same workload (profiles/r01_ncu_final.md)
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r01_seed_traffic.json')))
+        traffic = t['dram_bytes_read'] + t['dram_bytes_write']
+        layout = {'counted_extensions_per_launch': t['extensions_per_launch'],
+                  'counted_bytes_reference_layout': 64 * (t['extensions_per_launch'] + t['two_block_64B']),
+                  'counted_bytes_this_layout': 32 * (t['extensions_per_launch'] + t['two_block_32B'])}
+    except Exception:
+        pass
     cpu = None
     parity = None
     if os.path.exists(bwa) and world == 1:
@@ -336,9 +345,10 @@ def main():
                     'api': 'bsb_mem_main (FASTQ files on host -> SAM text to /dev/null)', 'wall_s': wall},
             'gpu_launches': st['kernel_launches'] - launches0, 'batches_in_flight_per_gpu': 2,
             'value_one_batch_in_flight': reads_all / (ms_one / 1000),
-            'roofline': {'bound': 'hbm', 'kernel': 'k_seed (SMEM seeding)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
-                         'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms},
+            'roofline': {'bound': 'hbm', 'kernel': 'k_seed3 (+ k_pack4, k_seed3_finish: SMEM seeding stage)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
+                         'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms,
+                         'reads_per_launch': reads_per_launch, **layout},
             'cpu_baseline': cpu, 'parity_vs_reference': parity,
             'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
             'final_split_ms_per_step': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},

@@ -50,7 +50,29 @@ def lines(rep, kernel, top=40, by=1):
         print(f'{k[0]}:{k[1]:4d} inst {100 * a[1] / ti:5.1f}% samp {100 * a[0] / max(ts, 1):5.1f}% thr {a[2] / max(a[1], 1):5.1f} | {k[2]}')
 
 
+def md(rep):
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    r = list(csv.reader(out.splitlines()))
+    h = r[0]
+    names = [row[h.index('Kernel Name')].split('(')[0].replace('void ', '') for row in r[2:]]
+    print('| metric | ' + ' | '.join(names) + ' |')
+    print('|---|' + '---|' * len(names))
+    for w in WANT:
+        if w in h:
+            i = h.index(w)
+            vals = []
+            for row in r[2:]:
+                try:
+                    vals.append('%.4g' % float(row[i]))
+                except ValueError:
+                    vals.append(row[i])
+            print(f'| {w} ({r[1][i]}) | ' + ' | '.join(vals) + ' |')
+
+
 if __name__ == '__main__':
+    if '--md' in sys.argv:
+        md(sys.argv[1])
+        sys.exit(0)
     if '--lines' in sys.argv:
         k = sys.argv[sys.argv.index('--lines') + 1]
         by = 0 if '--by-samples' in sys.argv else 1
