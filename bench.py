@@ -46,7 +46,8 @@ def _simulate_step(args):
     fa, prefix, n_pairs, seed, first_id = args
     from bsbolt_b200 import simulate
     names, ctg = simulate.read_fasta(fa)
-    paths, n = simulate.simulate_reads(names, ctg, prefix, n_pairs, seed=seed, truth=False, first_id=first_id, corrupt_frac=0.0)
+    paths, n = simulate.simulate_reads(names, ctg, prefix, n_pairs, seed=seed, truth=False, first_id=first_id,
+                                       corrupt_frac=float(os.environ.get('BSB_SIM_CORRUPT', '0')), undirectional=bool(os.environ.get('BSB_SIM_UNDIRECTIONAL')))
     return paths, n
 
 

@@ -483,13 +483,33 @@ __global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev
     for (int r = w; r < B.n; r += nw) stage_final_se(opt, ix, B, r, ws, wregs);
 }
 
+// K7 + K8a, thread per pair. Pairs that need mate-rescue Smith-Waterman are not finalised here: they are queued (heavy,
+// n_heavy) for the warp-cooperative kernel below, before anything has been written for them.
 template <int MINB>
-__global__ void __launch_bounds__(32, MINB) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
+__global__ void __launch_bounds__(32, MINB) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, int32_t *heavy, int *n_heavy)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
     FinalWS ws; AlnReg *wregs;
     make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
-    for (int p = w; p < (B.n >> 1); p += nw) stage_final_pe(opt, ix, B, p, ws, wregs);
+    for (int p = w; p < (B.n >> 1); p += nw)
+        if (stage_final_pe(opt, ix, B, p, ws, wregs, heavy != nullptr)) heavy[atomicAdd(n_heavy, 1)] = p;
+}
+
+// K7 for the queued pairs: one warp per pair, rescue Smith-Waterman across the lanes (bsb_warp.cuh)
+__global__ void __launch_bounds__(128) k_final_pe_heavy(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, const int32_t *heavy, const int *n_heavy)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int wib = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    FinalWS ws; AlnReg *wregs;
+    make_ws(L, scratch + (size_t)gw * L.total, ws, wregs);
+    WarpSw sw;
+    int32_t *base = reinterpret_cast<int32_t *>(smem) + (size_t)wib * (4 * L.sw_cap + (L.sw_cap + 3) / 4);
+    sw.H0 = base; sw.H1 = base + L.sw_cap; sw.E = base + 2 * L.sw_cap; sw.Hmax = base + 3 * L.sw_cap;
+    sw.qs = reinterpret_cast<uint8_t *>(base + 4 * L.sw_cap); sw.cap = L.sw_cap;
+    sw.b = ws.sw.b; sw.cap_b = ws.sw.cap_b;
+    const int n = *n_heavy;
+    for (int k = gw; k < n; k += nw) stage_final_pe_heavy(opt, ix, B, heavy[k], ws, wregs, sw);
 }
 
 // Index-load time: expands the reference's SA sample (every sa_intv-th rank) into the full suffix array in
@@ -620,6 +640,7 @@ struct BatchCtx {
     DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
     DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
+    DevBuf<int32_t> d_heavy;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
     size_t arena_cap = 0;
@@ -973,7 +994,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const int items = pe ? n >> 1 : n;
     const int fin_bps = env_int("BSB_FIN_BPS", 16);
     const int fin_workers = (int)std::min<size_t>((size_t)cdiv(std::max(items, 1), fin_block) * fin_block, (size_t)I.n_sm * fin_bps * fin_block);
-    m.d_final_scratch.ensure((size_t)fin_workers * L.total);
+    const int heavy_blocks = I.n_sm * 4;   // 4 warps each; every warp needs one scratch block like a light worker
+    m.d_final_scratch.ensure((size_t)std::max(fin_workers, heavy_blocks * 4) * L.total);
+    if (pe) m.d_heavy.ensure((size_t)(n >> 1) + 1);
     m.d_out.ensure(n + 1);
     B.out = m.d_out.p;
     if (m.arena_cap == 0) m.arena_cap = (size_t)n * 640 + (1 << 20);
@@ -999,9 +1022,20 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         B.arena.base = m.d_arena.p; B.arena.used = m.d_used.p; B.arena.cap = m.arena_cap;
         B.tasks.a = m.d_tasks.p; B.tasks.n = m.d_ntasks.p; B.tasks.cap = (unsigned int)m.task_cap;
         if (items) {
-            if (pe && fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
-            else if (pe && fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
-            else if (pe) k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
+            if (pe) {
+                const bool coop = !getenv("BSB_RESCUE_V1");
+                int32_t *heavy = coop ? m.d_heavy.p : nullptr;
+                int *n_heavy = m.d_misc.p + 12;
+                CK(cudaMemsetAsync(n_heavy, 0, 4, st));
+                if (fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
+                else if (fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
+                else k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
+                if (coop) {
+                    const int hv_smem = 4 * (int)((4 * L.sw_cap + (L.sw_cap + 3) / 4) * 4);
+                    k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
+                    ++m.launches;
+                }
+            }
             else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);
             ++m.launches;
         }

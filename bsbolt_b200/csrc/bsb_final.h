@@ -601,8 +601,10 @@ BSB_HD int pestat_candidate(const Opt &opt, int64_t l_pac, const AlnReg *r0, int
 
 // mem_matesw: Smith-Waterman of the mate inside the window implied by region `a` and the
 // insert-size distribution. `ma` is the mate's region list (grows in place).
+// `defer` (optional): instead of running the Smith-Waterman, report that one is needed and return before anything has
+// been modified -- the pair is then finalised by the warp-cooperative kernel (k_final_pe_heavy).
 BSB_HD int mate_rescue(const Opt &opt, const IndexView &ix, const PeStat pes[4], const AlnReg &a, int l_ms, const uint8_t *ms,
-                       RegList &ma, FinalWS &ws, int *err)
+                       RegList &ma, FinalWS &ws, int *err, int *defer = nullptr)
 {
     const int64_t l_pac = ix.l_pac;
     int i, r, skip[4], n = 0;
@@ -636,6 +638,7 @@ BSB_HD int mate_rescue(const Opt &opt, const IndexView &ix, const PeStat pes[4],
         bool have_ref = false;
         if (rb < re) { rid = fetch_window(ix, &rb, (rb + re) >> 1, &re); have_ref = true; }
         if (have_ref && a.rid == rid && re - rb >= opt.min_seed_len) {
+            if (defer) { *defer = 1; return n; }
             int xtra = SW_XSUBO | SW_XSTART | (l_ms * opt.a < 250 ? SW_XBYTE : 0) | (opt.min_seed_len * opt.a);
             QrySeq q = {seq, 1};
             RefSeq t = {ix.pac, l_pac, rb, 1};
@@ -736,7 +739,7 @@ BSB_HD int pair_hits(const Opt &opt, const IndexView &ix, const MathTab &mt, con
 // `first` is the bseq index of read 1 of the pair (read 2 is first+1); alignments are queued in `tl`.
 BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt, const PeStat pes[4], uint64_t id, int first,
                           int l0, const uint8_t *seq0, RegList &r0, int l1, const uint8_t *seq1, RegList &r1,
-                          FinalWS &ws, Arena &ar, TaskList &tl, ReadOut *reads, int *err)
+                          FinalWS &ws, Arena &ar, TaskList &tl, ReadOut *reads, int *err, int *defer = nullptr)
 {
     RegList *a[2] = {&r0, &r1};
     const int ls[2] = {l0, l1};
@@ -759,8 +762,10 @@ BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt
             if (nb[i] > opt.max_matesw) nb[i] = opt.max_matesw;
         }
         for (i = 0; i < 2; ++i)
-            for (j = 0; j < nb[i]; ++j)
-                mate_rescue(opt, ix, pes, bcopy[i][j], ls[!i], seqs[!i], *a[!i], ws, err);
+            for (j = 0; j < nb[i]; ++j) {
+                mate_rescue(opt, ix, pes, bcopy[i][j], ls[!i], seqs[!i], *a[!i], ws, err, defer);
+                if (defer && *defer) return;
+            }
     }
     n_pri[0] = mark_primary(opt, a[0]->n, a[0]->a, (int64_t)(id << 1 | 0), ws.z);
     n_pri[1] = mark_primary(opt, a[1]->n, a[1]->a, (int64_t)(id << 1 | 1), ws.z);

@@ -236,27 +236,30 @@ BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int
 
 // K7 + K8a (paired-end): mate rescue, pairing, record selection. wregs: per-worker scratch of
 // 2*(reg_cap + max_matesw) regions
-BSB_HD void stage_final_pe(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs)
+// `defer` (optional): returns true, with nothing written, when the pair needs rescue Smith-Waterman (see mate_rescue)
+BSB_HD bool stage_final_pe(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs, bool defer = false)
 {
     const int r0 = p << 1, r1 = r0 | 1;
     const int e0 = B.err[r0] ? B.err[r0] : B.err[r1];
     readout_init(B.out[r0], e0); readout_init(B.out[r1], e0);
-    if (e0) return;
+    if (e0) return false;
     const int stride = ws.reg_cap + opt.max_matesw;
     RegList rl[2];
     for (int i = 0; i < 2; ++i) {
         int r = r0 | i, n = B.n_regs[r];
         rl[i].a = wregs + (size_t)i * stride; rl[i].cap = ws.reg_cap; rl[i].n = n;
-        if (n > ws.reg_cap) { B.out[r0].err = B.out[r1].err = ERR_SCRATCH_OVERFLOW; return; }
+        if (n > ws.reg_cap) { B.out[r0].err = B.out[r1].err = ERR_SCRATCH_OVERFLOW; return false; }
         const AlnReg *src = B.regs + B.seed_off[r];
         for (int j = 0; j < n; ++j) rl[i].a[j] = src[j];
     }
-    int err = 0;
+    int err = 0, deferred = 0;
     finalize_pair(opt, ix, B.mt, B.pes, (uint64_t)((B.n_processed >> 1) + p), r0,
                   (int)(B.seq_off[r0 + 1] - B.seq_off[r0]), B.seq + B.seq_off[r0], rl[0],
                   (int)(B.seq_off[r1 + 1] - B.seq_off[r1]), B.seq + B.seq_off[r1], rl[1],
-                  ws, B.arena, B.tasks, B.out, &err);
+                  ws, B.arena, B.tasks, B.out, &err, defer ? &deferred : nullptr);
+    if (deferred) return true;
     if (err) B.out[r0].err = B.out[r1].err = err;
+    return false;
 }
 
 // K6 + K8b (scalar form): one queued alignment -> CIGAR, NM, MD/XB, position, written to its record(s)

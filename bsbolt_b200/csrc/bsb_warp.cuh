@@ -768,4 +768,306 @@ __device__ void stage_task_warp(const Opt &opt, const IndexView &ix, BatchDev &B
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7, heavy pairs: mate rescue with the Smith-Waterman spread over the warp.
+//
+// sw_striped_warp() is sw_striped() (bsb_ksw.h: the cell-exact restatement of ksw_u8 / ksw_i16, ksw.c:115-339) with the
+// query positions of a row across the lanes. In the linear restatement the stripe-local F of the first sweep is a
+// SEGMENTED exclusive max-scan (segments = stripes of slen cells) of g(q) = max(h(q) - oe_ins, 0) + q * e_ins, and the
+// lazy-F repair is a plain exclusive max-scan of the same quantity over the row: a cell whose h was itself raised by F
+// cannot raise a later F (oe_ins > e_ins), so both scans read the pre-F values. E and the row maximum use the
+// first-sweep h, exactly like the reference.
+// ---------------------------------------------------------------------------------------------
+struct WarpSw {
+    int32_t *H0, *H1, *E, *Hmax;   // shared memory, cap cells each
+    uint8_t *qs;                   // shared memory, cap bytes: query codes of the current pass
+    int cap;
+    uint64_t *b; int cap_b;        // sub-optimal list (HBM)
+};
+
+template <class Q, class T>
+__device__ SwResult sw_striped_warp(int size, int qlen, const Q &query, int tlen, const T &target, const int8_t *mat,
+                                    int o_del, int e_del, int o_ins, int e_ins, int xtra, const WarpSw &ws, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    SwResult r = {0, -1, -1, -1, -1, -1, -1};
+    const int p = size == 1 ? 16 : 8;
+    const int slen = (qlen + p - 1) / p, L = slen * p;
+    int shift = 127, mdiff = 0, qmax;
+    for (int a = 0; a < 25; ++a) {
+        if (mat[a] < (int8_t)shift) shift = mat[a];
+        if (mat[a] > (int8_t)mdiff) mdiff = mat[a];
+    }
+    qmax = mdiff;
+    shift = (256 - shift) & 0xff;
+    if (L > ws.cap) { *err = ERR_SCRATCH_OVERFLOW; return r; }
+    const int minsc = (xtra & SW_XSUBO) ? xtra & 0xffff : 0x10000;
+    const int endsc = (xtra & SW_XSTOP) ? xtra & 0xffff : 0x10000;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int32_t *H0 = ws.H0, *H1 = ws.H1, *E = ws.E, *Hmax = ws.Hmax;
+    uint8_t *qs = ws.qs;
+    for (int q = lane; q < L; q += 32) { E[q] = H0[q] = Hmax[q] = 0; qs[q] = q < qlen ? (uint8_t)query(q) : (uint8_t)5; }
+    int n_b = 0, te = -1, gmax = 0, last_b_sc = 0, last_b_i = -2, tcache = 0, i;
+    __syncwarp();
+    for (i = 0; i < tlen; ++i) {
+        if ((i & 31) == 0) tcache = i + lane < tlen ? target(i + lane) : 4;
+        const int8_t *row = mat + __shfl_sync(FULLMASK, tcache, i & 31) * 5;
+        const uint64_t rowpack = (uint64_t)(uint8_t)row[0] | (uint64_t)(uint8_t)row[1] << 8 | (uint64_t)(uint8_t)row[2] << 16 |
+                                 (uint64_t)(uint8_t)row[3] << 24 | (uint64_t)(uint8_t)row[4] << 32;   // byte 5 = 0: the pad cells
+        int imax = 0;
+        int carry1 = NEG_BIG, carry1_seg = -1;   // first sweep: best g of the stripe that runs into this chunk
+        int carry2 = NEG_BIG;                    // lazy-F sweep: best g of everything before this chunk
+        for (int c0 = 0; c0 < L; c0 += 32) {
+            const int q = c0 + lane;
+            const bool act = q < L;
+            int hh = 0, e = 0, seg = -2;
+            if (act) {
+                hh = q ? H0[q - 1] : 0;
+                const int sc = (int)(int8_t)(rowpack >> (8 * qs[q]));
+                if (size == 1) { hh = hh + sc + shift; if (hh > 255) hh = 255; hh = hh - shift; if (hh < 0) hh = 0; }
+                else { hh = hh + sc; if (hh > 32767) hh = 32767; }
+                e = E[q];
+                hh = hh > e ? hh : e;
+                seg = q / slen;
+            }
+            // first sweep: F restarts at the head of every stripe
+            int t = hh - oe_ins; t = t > 0 ? t : 0;
+            const int g = act ? t + q * e_ins : NEG_BIG;
+            int incl = g;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULLMASK, incl, d);
+                const int sg = __shfl_up_sync(FULLMASK, seg, d);
+                if (lane >= d && sg == seg) incl = incl > v ? incl : v;
+            }
+            int excl = __shfl_up_sync(FULLMASK, incl, 1);
+            const int pseg = __shfl_up_sync(FULLMASK, seg, 1);
+            if (lane == 0 || pseg != seg) excl = NEG_BIG;
+            if (seg == carry1_seg && carry1 > excl) excl = carry1;
+            int f = excl - (q - 1) * e_ins; f = f > 0 ? f : 0;
+            if (!act) f = 0;
+            int h = hh > f ? hh : f;
+            const int rm = __reduce_max_sync(FULLMASK, act ? h : 0);
+            imax = imax > rm ? imax : rm;
+            int e2 = e - e_del; e2 = e2 > 0 ? e2 : 0;
+            int tD = h - oe_del; tD = tD > 0 ? tD : 0;
+            if (act) E[q] = e2 > tD ? e2 : tD;
+            // carry of the first sweep: the running maximum of the last lane's stripe
+            const int last_seg = __shfl_sync(FULLMASK, seg, 31);
+            const int last_incl = __shfl_sync(FULLMASK, incl, 31);
+            int nc1 = last_incl;
+            if (last_seg == carry1_seg && carry1 > nc1) nc1 = carry1;
+            // does the last lane's stripe start inside this chunk? then the old carry does not belong to it (handled by the test above)
+            carry1 = nc1; carry1_seg = last_seg;
+            // lazy-F repair: plain scan over the row of the first-sweep h
+            int t2 = h - oe_ins; t2 = t2 > 0 ? t2 : 0;
+            const int g2 = act ? t2 + q * e_ins : NEG_BIG;
+            int incl2 = g2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULLMASK, incl2, d);
+                if (lane >= d) incl2 = incl2 > v ? incl2 : v;
+            }
+            int excl2 = __shfl_up_sync(FULLMASK, incl2, 1);
+            if (lane == 0) excl2 = NEG_BIG;
+            excl2 = excl2 > carry2 ? excl2 : carry2;
+            int f2 = excl2 - (q - 1) * e_ins; f2 = f2 > 0 ? f2 : 0;
+            if (act) H1[q] = f2 > h ? f2 : h;
+            const int cm2 = __shfl_sync(FULLMASK, incl2, 31);
+            carry2 = carry2 > cm2 ? carry2 : cm2;
+        }
+        __syncwarp();
+        if (imax >= minsc) {
+            if (n_b == 0 || last_b_i + 1 != i) {
+                if (n_b >= ws.cap_b) { *err = ERR_SCRATCH_OVERFLOW; return r; }
+                if (lane == 0) ws.b[n_b] = (uint64_t)imax << 32 | (uint32_t)i;
+                ++n_b; last_b_sc = imax; last_b_i = i;
+            } else if (last_b_sc < imax) {
+                if (lane == 0) ws.b[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i;
+                last_b_sc = imax; last_b_i = i;
+            }
+        }
+        bool stop = false;
+        if (imax > gmax) {
+            gmax = imax; te = i;
+            for (int q = lane; q < L; q += 32) Hmax[q] = H1[q];
+            if (size == 1) { if (gmax + shift >= 255 || gmax >= endsc) stop = true; }
+            else if (gmax >= endsc) stop = true;
+        }
+        if (stop) break;
+        int32_t *S = H1; H1 = H0; H0 = S;
+        __syncwarp();
+    }
+    __syncwarp();
+    r.score = size == 1 ? (gmax + shift < 255 ? gmax : 255) : gmax;
+    r.te = te;
+    if (size != 1 || r.score != 255) {
+        // smallest query position holding the maximum of Hmax
+        int key = -1;
+        for (int q = lane; q < L; q += 32) { const int k = Hmax[q] << 12 | (4095 - q); key = key > k ? key : k; }
+        key = __reduce_max_sync(FULLMASK, key);
+        r.qe = key >= 0 ? 4095 - (key & 0xfff) : -1;
+        int s2 = -1, te2 = -1;
+        if (n_b && lane == 0) {
+            int k = (r.score + qmax - 1) / qmax;
+            const int low = te - k, high = te + k;
+            for (k = 0; k < n_b; ++k) {
+                const int e = (int32_t)ws.b[k];
+                if ((e < low || e > high) && (int)(ws.b[k] >> 32) > s2) { s2 = (int)(ws.b[k] >> 32); te2 = e; }
+            }
+        }
+        r.score2 = __shfl_sync(FULLMASK, s2, 0);
+        r.te2 = __shfl_sync(FULLMASK, te2, 0);
+    }
+    __syncwarp();
+    return r;
+}
+
+// ksw_align2 (ksw.c:343-365) on the warp: forward pass, then the reverse pass that locates the start
+template <class Q, class T>
+__device__ SwResult sw_local_warp(int qlen, const Q &query, int tlen, const T &target, const int8_t *mat,
+                                  int o_del, int e_del, int o_ins, int e_ins, int xtra, const WarpSw &ws, int *err)
+{
+    const int size = (xtra & SW_XBYTE) ? 1 : 2;
+    SwResult r = sw_striped_warp(size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, ws, err);
+    if ((xtra & SW_XSTART) == 0 || ((xtra & SW_XSUBO) && r.score < (xtra & 0xffff))) return r;
+    struct RevQ { const Q &q; int n; __device__ int operator()(int i) const { return q(n - 1 - i); } };
+    struct RevT { const T &t; int n; __device__ int operator()(int i) const { return i < n ? t(n - 1 - i) : t(i); } };
+    RevQ rq = {query, r.qe + 1};
+    RevT rt = {target, r.te + 1};
+    SwResult rr = sw_striped_warp(size, r.qe + 1, rq, tlen, rt, mat, o_del, e_del, o_ins, e_ins, SW_XSTOP | r.score, ws, err);
+    if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    return r;
+}
+
+// mem_matesw (bwamem_pair.c:111-180), warp-uniform: every lane follows the same control flow on the same values, the
+// Smith-Waterman runs across the lanes, lane 0 alone modifies the mate's region list.
+__device__ int mate_rescue_warp(const Opt &opt, const IndexView &ix, const PeStat pes[4], const AlnReg &a, int l_ms, const uint8_t *ms,
+                                RegList &ma, FinalWS &ws, const WarpSw &sw, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t l_pac = ix.l_pac;
+    int i, r, skip[4], n = 0;
+    for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+    for (i = 0; i < ma.n; ++i) {
+        int64_t dist;
+        r = infer_dir(l_pac, a.rb, ma.a[i].rb, &dist);
+        if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+    }
+    if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
+    for (r = 0; r < 4; ++r) {
+        int is_rev, is_larger, rid = -1;
+        int64_t rb, re;
+        if (skip[r]) continue;
+        is_rev = (r >> 1 != (r & 1));
+        is_larger = !(r >> 1);
+        const uint8_t *seq = ms;
+        if (is_rev) {
+            __syncwarp();
+            for (i = lane; i < l_ms; i += 32) ws.rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
+            __syncwarp();
+            seq = ws.rev;
+        }
+        if (!is_rev) {
+            rb = is_larger ? a.rb + pes[r].low : a.rb - pes[r].high;
+            re = (is_larger ? a.rb + pes[r].high : a.rb - pes[r].low) + l_ms;
+        } else {
+            rb = (is_larger ? a.rb + pes[r].low : a.rb - pes[r].high) - l_ms;
+            re = is_larger ? a.rb + pes[r].high : a.rb - pes[r].low;
+        }
+        if (rb < 0) rb = 0;
+        if (re > l_pac << 1) re = l_pac << 1;
+        bool have_ref = false;
+        if (rb < re) { rid = fetch_window(ix, &rb, (rb + re) >> 1, &re); have_ref = true; }
+        if (have_ref && a.rid == rid && re - rb >= opt.min_seed_len) {
+            int xtra = SW_XSUBO | SW_XSTART | (l_ms * opt.a < 250 ? SW_XBYTE : 0) | (opt.min_seed_len * opt.a);
+            QrySeq q = {seq, 1};
+            RefSeq t = {ix.pac, l_pac, rb, 1};
+            SwResult aln = sw_local_warp(l_ms, q, (int)(re - rb), t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, sw, err);
+            if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
+                AlnReg b;
+                alnreg_clear(b);
+                b.rid = a.rid;
+                b.is_alt = a.is_alt;
+                b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+                b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+                b.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
+                b.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
+                b.score = aln.score;
+                b.csub = aln.score2;
+                b.secondary = -1;
+                b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+                if (ma.n >= ma.cap) { *err = ERR_SCRATCH_OVERFLOW; return n; }
+                ++ma.n;
+                __syncwarp();
+                if (lane == 0) {
+                    for (i = 0; i < ma.n - 1; ++i)
+                        if (ma.a[i].score < b.score) break;
+                    int tmp = i;
+                    for (i = ma.n - 1; i > tmp; --i) ma.a[i] = ma.a[i - 1];
+                    ma.a[i] = b;
+                }
+                __syncwarp();
+            }
+            ++n;
+        }
+        if (n) {
+            int m = 0, e0 = 0;
+            __syncwarp();
+            if (lane == 0) { m = sort_dedup_patch(opt, ix, nullptr, ma.n, ma.a, ws.dp, &e0); }
+            m = __shfl_sync(FULLMASK, m, 0); e0 = __shfl_sync(FULLMASK, e0, 0);
+            ma.n = m;
+            if (e0) *err = e0;
+            __syncwarp();
+        }
+    }
+    return n;
+}
+
+// One pair that needs rescue Smith-Waterman, on one warp: the rescue block of mem_sam_pe (bwamem_pair.c:262-277) with
+// the lanes together, then the rest of the pair's finalisation on lane 0 with the rescue already done.
+__device__ void stage_final_pe_heavy(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs, const WarpSw &sw)
+{
+    const int lane = threadIdx.x & 31;
+    const int r0 = p << 1, r1 = r0 | 1;
+    const int stride = ws.reg_cap + opt.max_matesw;
+    RegList rl[2];
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 | i, n = B.n_regs[r];
+        rl[i].a = wregs + (size_t)i * stride; rl[i].cap = ws.reg_cap; rl[i].n = n;
+        const AlnReg *src = B.regs + B.seed_off[r];
+        for (int j = lane; j < n; j += 32) rl[i].a[j] = src[j];
+    }
+    __syncwarp();
+    int err = 0;
+    const int ls[2] = {(int)(B.seq_off[r0 + 1] - B.seq_off[r0]), (int)(B.seq_off[r1 + 1] - B.seq_off[r1])};
+    const uint8_t *seqs[2] = {B.seq + B.seq_off[r0], B.seq + B.seq_off[r1]};
+    AlnReg *bcopy[2]; int nb[2];
+    for (int i = 0; i < 2; ++i) {
+        nb[i] = 0;
+        bcopy[i] = rl[i].a + rl[i].cap;
+        for (int j = 0; j < rl[i].n; ++j)
+            if (rl[i].a[j].score >= rl[i].a[0].score - opt.pen_unpaired) {
+                if (nb[i] < opt.max_matesw && lane == 0) bcopy[i][nb[i]] = rl[i].a[j];
+                ++nb[i];
+            }
+        if (nb[i] > opt.max_matesw) nb[i] = opt.max_matesw;
+    }
+    __syncwarp();
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < nb[i]; ++j) {
+            const AlnReg a = bcopy[i][j];
+            mate_rescue_warp(opt, ix, B.pes, a, ls[!i], seqs[!i], rl[!i], ws, sw, &err);
+        }
+    __syncwarp();
+    if (lane == 0) {
+        Opt o2 = opt;
+        o2.flag |= F_NO_RESCUE;
+        finalize_pair(o2, ix, B.mt, B.pes, (uint64_t)((B.n_processed >> 1) + p), r0, ls[0], seqs[0], rl[0], ls[1], seqs[1], rl[1],
+                      ws, B.arena, B.tasks, B.out, &err);
+        if (err) B.out[r0].err = B.out[r1].err = err;
+    }
+    __syncwarp();
+}
+
 } // namespace bsb
