@@ -212,10 +212,16 @@ BSB_HD bool bs_md_xb(const IndexView &ix, int n_cigar, const uint32_t *cigar, in
     if (clen <= 0) return false;
     const bool rev = rb >= l_pac;
     const char *int2base = rb < l_pac ? "ACGTN" : "TGCAN";
-    // cseq'(i): flank-extended unconverted reference in the orientation of the CIGAR
-    auto cs = [&](int64_t i) -> int {
-        if (i < 0 || i >= clen) return 4;
-        return rev ? ref_base(ix.opac, l_pac, ce - 1 - i) : ref_base(ix.opac, l_pac, cb + i);
+    // cseq'(i): flank-extended unconverted reference in the orientation of the CIGAR. The window lies on one strand, so
+    // both orientations walk the forward-strand bytes of opac upwards from one start (complemented for the reverse
+    // half: ref_base(p) = 3 - pac[2 l_pac - 1 - p]) -- 32-bit index arithmetic per base instead of 64-bit.
+    const int64_t p0 = rev ? (l_pac << 1) - ce : cb;
+    const uint8_t *pbase = ix.opac + (p0 >> 2);
+    const int poff = (int)(p0 & 3), comp = rev ? 3 : 0, ncl = (int)clen;
+    auto cs = [&](int i) -> int {
+        if (i < 0 || i >= ncl) return 4;
+        const int k = poff + i;
+        return comp ^ (pbase[k >> 2] >> ((~k & 3) << 1) & 3);
     };
     auto oq = [&](int x) -> int { return rev ? oquery[l_query - 1 - x] : oquery[x]; };
     int k, x, y, u, n_mm = 0, n_gap = 0, meth_pos = 0;

@@ -558,8 +558,10 @@ __device__ int nw_global_warp(int qlen, const Q &query, int tlen, const T &targe
         if (j < qlen) qs[j] = (uint8_t)query(j);
     }
     __syncwarp();
+    int tcache = 0;                                 // target bases of rows [i & ~31, +32), one per lane
     for (int i = 0; i < tlen; ++i) {
-        const int8_t *row = mat + target(i) * 5;
+        if ((i & 31) == 0) tcache = i + lane < tlen ? target(i + lane) : 4;
+        const int8_t *row = mat + __shfl_sync(FULLMASK, tcache, i & 31) * 5;
         const int beg = i > w ? i - w : 0;
         const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
         int carry_h = beg == 0 ? -(o_del + e_del * (i + 1)) : BSB_MINUS_INF;

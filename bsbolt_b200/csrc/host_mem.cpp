@@ -439,16 +439,20 @@ static void format_one(const MemArgs &ma, const HostIndex &idx, const ReadBatch 
                 if (c1 == 4 || c1 == 3) qb += cigar[p.n_cigar - 1] >> 4;
             }
         }
+        const int nq = qe > qb ? qe - qb : 0;
+        const size_t at = str.size();
+        str.resize(at + (size_t)nq + 1 + (has_qual ? (size_t)nq : 1));   // SEQ \t QUAL in one growth, filled through a pointer
+        char *o = &str[at];
         if (!reverse) {
-            for (int i = qb; i < qe; ++i) str.push_back("ACGTN"[kNt4[(unsigned char)bases[i]]]);
-            str.push_back('\t');
-            if (has_qual) str.append(qual + qb, qe - qb);
-            else str.push_back('*');
+            for (int i = qb; i < qe; ++i) *o++ = "ACGTN"[kNt4[(unsigned char)bases[i]]];
+            *o++ = '\t';
+            if (has_qual) memcpy(o, qual + qb, (size_t)nq);
+            else *o = '*';
         } else {
-            for (int i = qe - 1; i >= qb; --i) str.push_back("TGCAN"[kNt4[(unsigned char)bases[i]]]);
-            str.push_back('\t');
-            if (has_qual) for (int i = qe - 1; i >= qb; --i) str.push_back(qual[i]);
-            else str.push_back('*');
+            for (int i = qe - 1; i >= qb; --i) *o++ = "TGCAN"[kNt4[(unsigned char)bases[i]]];
+            *o++ = '\t';
+            if (has_qual) for (int i = qe - 1; i >= qb; --i) *o++ = qual[i];
+            else *o = '*';
         }
     }
     if (p.n_cigar) {
@@ -535,6 +539,21 @@ void format_entry(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, i
     for (int k = 0; k < ro.n_aln; ++k) format_one(ma, idx, b, i, list, ro.n_aln, k, mv, arena, sam, st);
 }
 
+// the same, appended to a buffer shared by consecutive entries (the pipeline's formatter)
+static void format_entry_append(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int i, const BatchResult &res,
+                                std::string &buf, EntryStats &st)
+{
+    const ReadOut &ro = res.reads[i];
+    const uint8_t *arena = res.arena.data();
+    const AlnOut *list = reinterpret_cast<const AlnOut *>(arena + ro.aln_off);
+    MateView mv;
+    mv.present = (ma.opt.flag & F_PE) != 0;
+    mv.pos = ro.h_pos; mv.rid = ro.h_rid; mv.is_rev = ro.h_is_rev; mv.n_cigar = ro.h_n_cigar; mv.rlen = ro.h_rlen;
+    mv.ch_meth = ro.h_ch_meth; mv.ch_unmeth = ro.h_ch_unmeth;
+    st = EntryStats();
+    for (int k = 0; k < ro.n_aln; ++k) format_one(ma, idx, b, i, list, ro.n_aln, k, mv, arena, buf, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // read-group arbiter
 // ------------------------------------------------------------------------------------------------
@@ -562,9 +581,10 @@ static void set_unmapped(const ReadBatch &b, int i, const EntryStats &st, std::s
 
 // Decision pass of the arbiter: which entries are printed (in input order), with BS-ambiguous groups rewritten
 // as unmapped. Serial and cheap -- no SAM text is copied here.
-static void sam_sort_plan(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st, std::vector<int> &emit, MapStats &ms)
+static void sam_sort_plan(const ReadBatch &b, std::vector<EntryStats> &st, std::vector<int> &emit, std::vector<uint8_t> &rewrite, MapStats &ms)
 {
     emit.clear();
+    rewrite.assign(b.n, 0);
     if (b.n == 0) return;
     std::vector<int> g[2];
     long score[2] = {0, 0};
@@ -591,7 +611,7 @@ static void sam_sort_plan(const ReadBatch &b, std::vector<std::string> &sam, std
         } else {
             for (int i : g[0]) {
                 if (pick == 2) {
-                    if (st[i].mapped) set_unmapped(b, i, st[i], sam[i]);
+                    if (st[i].mapped) rewrite[i] = 1;     // printed as an unmapped record (set_unmapped)
                     st[i].mapped = 0;
                     st[i].bs_conflict = 1;
                 }
@@ -614,8 +634,12 @@ static void sam_sort_plan(const ReadBatch &b, std::vector<std::string> &sam, std
 void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vector<EntryStats> &st, std::string &out, MapStats &ms)
 {
     std::vector<int> emit;
-    sam_sort_plan(b, sam, st, emit, ms);
-    for (int i : emit) out += sam[i];
+    std::vector<uint8_t> rewrite;
+    sam_sort_plan(b, st, emit, rewrite, ms);
+    for (int i : emit) {
+        if (rewrite[i]) set_unmapped(b, i, st[i], sam[i]);
+        out += sam[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,9 +739,9 @@ static double now_sec()
 }
 
 template <class F>
-static void parallel_for(int n_threads, int n, F f)
+static void parallel_for(int n_threads, int n, F f, int serial_below = 256)
 {
-    if (n_threads <= 1 || n < 256) { for (int i = 0; i < n; ++i) f(i); return; }
+    if (n_threads <= 1 || n < serial_below) { for (int i = 0; i < n; ++i) f(i); return; }
     std::vector<std::thread> th;
     int chunk = (n + n_threads - 1) / n_threads;
     for (int t = 0; t < n_threads; ++t) {
@@ -935,10 +959,14 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
             q_done.producer_done();
         });
     {
-        std::vector<std::string> sam;
+        // SAM text: each formatter thread appends the records of a run of consecutive entries to ONE buffer, so that in
+        // the common case (every entry printed as formatted, in input order) the buffers are written out as they are
+        struct Piece { std::string buf; std::vector<size_t> end; int lo = 0, hi = 0; };
+        std::vector<Piece> pieces(host_threads);
         std::vector<EntryStats> st;
         std::vector<int> emit;
-        std::vector<size_t> offs;
+        std::vector<uint8_t> rewrite;
+        std::string tmp;
         RawBuf text(false);   // SAM text never crosses PCIe: ordinary memory
         std::unique_ptr<Job> j;
         while (q_done.pop(j)) {
@@ -954,19 +982,43 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 sum.sec_align += j->sec_align;
                 sum.add_timing(j->res);
                 double tf = now_sec();
-                sam.resize(batch.n); st.resize(batch.n);
-                parallel_for(host_threads, batch.n, [&](int i) { format_entry(ma, idx, batch, i, j->res, sam[i], st[i]); });
+                st.resize(batch.n);
+                const int nt = std::max(1, std::min(host_threads, batch.n / 256 + 1));
+                const int chunk = (batch.n + nt - 1) / nt;
+                for (int t = 0; t < nt; ++t) { pieces[t].lo = std::min(batch.n, t * chunk); pieces[t].hi = std::min(batch.n, (t + 1) * chunk); }
+                parallel_for(nt, nt, [&](int t) {
+                    Piece &pc = pieces[t];
+                    pc.buf.clear(); pc.end.resize(pc.hi - pc.lo);
+                    for (int i = pc.lo; i < pc.hi; ++i) {
+                        format_entry_append(ma, idx, batch, i, j->res, pc.buf, st[i]);
+                        pc.end[i - pc.lo] = pc.buf.size();
+                    }
+                }, 1);
                 MapStats ms;
-                sam_sort_plan(batch, sam, st, emit, ms);
-                const int ne = (int)emit.size();
-                offs.resize((size_t)ne + 1);
+                sam_sort_plan(batch, st, emit, rewrite, ms);
+                bool as_is = (int)emit.size() == batch.n;
+                for (int k = 0; as_is && k < batch.n; ++k) as_is = emit[k] == k && !rewrite[k];
                 size_t total = 0;
-                for (int k = 0; k < ne; ++k) { offs[k] = total; total += sam[emit[k]].size(); }
-                offs[ne] = total;
-                text.resize_uninit(total);
-                parallel_for(host_threads, ne, [&](int k) { memcpy(text.data() + offs[k], sam[emit[k]].data(), sam[emit[k]].size()); });
-                double tw = now_sec();
-                fwrite(text.data(), 1, total, out);
+                double tw;
+                if (as_is) {
+                    tw = now_sec();
+                    for (int t = 0; t < nt; ++t) { fwrite(pieces[t].buf.data(), 1, pieces[t].buf.size(), out); total += pieces[t].buf.size(); }
+                } else {   // some entries dropped or rewritten by the arbiter: assemble the text entry by entry
+                    tmp.clear();
+                    auto span = [&](int i, const char *&p, size_t &l) {
+                        const Piece &pc = pieces[i / chunk];
+                        const size_t b0 = i == pc.lo ? 0 : pc.end[i - pc.lo - 1];
+                        p = pc.buf.data() + b0; l = pc.end[i - pc.lo] - b0;
+                    };
+                    std::string all;
+                    for (int i : emit) {
+                        if (rewrite[i]) { set_unmapped(batch, i, st[i], tmp); all += tmp; }
+                        else { const char *p; size_t l; span(i, p, l); all.append(p, l); }
+                    }
+                    total = all.size();
+                    tw = now_sec();
+                    fwrite(all.data(), 1, total, out);
+                }
                 if (parts) fprintf(parts, "%ld\t%zu\t%zu\n", j->batch_id, out_bytes, total);
                 out_bytes += total;
                 sum.sec_format += tw - tf; sum.sec_write += now_sec() - tw;
@@ -985,7 +1037,10 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 ++sum.n_batches;
                 sum.n_entries += batch.n;
             } catch (const std::exception &e) { set_fail(e.what()); }
-            if (resident) finished.push_back(std::move(j));   // device inputs are freed after the run (cudaFree synchronises the device)
+            if (resident) {   // the page-locked host buffers go back to the pool now, for the batches still to come
+                j->res.arena.reset(); j->res.reads.reset(); j->batch.bases.reset();
+                finished.push_back(std::move(j));
+            }   // (device inputs are freed after the run: cudaFree synchronises the device)
             else q_free.push(std::move(j));
         }
     }

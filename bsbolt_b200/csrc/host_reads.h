@@ -31,6 +31,7 @@ public:
     uint8_t *data() { return p_; }
     const uint8_t *data() const { return p_; }
     size_t size() const { return n_; }
+    void reset() { if (p_) rel(p_); p_ = nullptr; n_ = cap_ = 0; }   // hand the block back (to the page-locked pool)
     void resize_uninit(size_t n)
     {
         if (n > cap_) {
@@ -58,6 +59,7 @@ public:
     size_t size() const { return n_; }
     void resize(size_t n) { buf_.resize_uninit(n * sizeof(T)); n_ = n; }
     void assign(size_t n, const T &v) { resize(n); for (size_t i = 0; i < n; ++i) data()[i] = v; }
+    void reset() { buf_.reset(); n_ = 0; }
 private:
     RawBuf buf_; size_t n_ = 0;
 };
@@ -74,6 +76,7 @@ public:
     size_t size() const { return n_; }
     size_t capacity() const { return cap_; }
     void clear() { n_ = 0; }
+    void reset() { if (p_) g_host_alloc.release(p_); p_ = nullptr; n_ = cap_ = 0; }
     void reserve(size_t c)
     {
         if (c <= cap_) return;
