@@ -120,6 +120,27 @@ void HostIndex::load(const std::string &hint)
         anns[i].offset = contigs[i].offset; anns[i].len = contigs[i].len;
         anns[i].is_alt = contigs[i].is_alt; anns[i].is_crick = contigs[i].is_crick; anns[i].pad_ = 0;
     }
+    build_sam_table();
+}
+
+void HostIndex::build_sam_table()
+{
+    const size_t n = contigs.size();
+    ctg_text.clear(); ctg_name_off.assign(n + 1, 0); ctg_anno_off.assign(n + 1, 0); ctg_is_crick.assign(n, 0); ctg_sign.assign(n, 0);
+    any_alt = false;
+    for (size_t i = 0; i < n; ++i) {
+        ctg_name_off[i] = (uint32_t)ctg_text.size();
+        ctg_text.insert(ctg_text.end(), contigs[i].name.begin(), contigs[i].name.end());
+        ctg_is_crick[i] = contigs[i].is_crick ? 1 : 0;
+        ctg_sign[i] = (uint8_t)((contigs[i].name.find('+') != std::string::npos ? 1 : 0) | (contigs[i].name.find('-') != std::string::npos ? 2 : 0));
+        if (contigs[i].is_alt) any_alt = true;
+    }
+    ctg_name_off[n] = (uint32_t)ctg_text.size();
+    for (size_t i = 0; i < n; ++i) {
+        ctg_anno_off[i] = (uint32_t)ctg_text.size();
+        ctg_text.insert(ctg_text.end(), contigs[i].anno.begin(), contigs[i].anno.end());
+    }
+    ctg_anno_off[n] = (uint32_t)ctg_text.size();
 }
 
 IndexView HostIndex::host_view() const

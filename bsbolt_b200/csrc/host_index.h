@@ -26,6 +26,10 @@ struct HostIndex {
     std::vector<HostContig> contigs;
     std::vector<Ann> anns;
     std::string prefix;
+    // contig table flattened for the SAM formatter (bsb_sam.h): names back to back, then annotations
+    std::vector<char> ctg_text; std::vector<uint32_t> ctg_name_off, ctg_anno_off; std::vector<uint8_t> ctg_is_crick, ctg_sign;
+    bool any_alt = false;
+    void build_sam_table();
 
     // throws std::runtime_error on any missing/corrupt file
     void load(const std::string &hint);

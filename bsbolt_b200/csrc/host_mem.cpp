@@ -1,6 +1,7 @@
 // host_mem.cpp -- see host_mem.h
 #include "host_mem.h"
 #include "bsb_hd.h"
+#include "bsb_sam.h"
 #include <ctype.h>
 #include <getopt.h>
 #include <math.h>
@@ -295,56 +296,20 @@ std::string sam_header(const HostIndex &idx, const MemArgs &ma)
     return h;
 }
 
-static inline void put_int(std::string &s, long v)
-{
-    char buf[24]; int l = 0; unsigned long x = v < 0 ? (unsigned long)(-v) : (unsigned long)v;
-    do { buf[l++] = (char)('0' + x % 10); x /= 10; } while (x);
-    if (v < 0) buf[l++] = '-';
-    while (l) s.push_back(buf[--l]);
-}
-
-static void put_cigar(std::string &s, int n, const uint32_t *cig, const char *ops, int clip_as)
-{
-    for (int i = 0; i < n; ++i) {
-        int c = cig[i] & 0xf;
-        if (clip_as >= 0 && (c == 3 || c == 4)) c = clip_as;
-        put_int(s, cig[i] >> 4);
-        s.push_back(ops[c]);
+// the text sink of the host formatter
+struct SamString {
+    std::string &s;
+    void ch(char c) { s.push_back(c); }
+    void mem(const char *p, size_t l) { s.append(p, l); }
+    void num(long v)
+    {
+        char buf[24]; int l = 0; unsigned long x = v < 0 ? (unsigned long)(-v) : (unsigned long)v;
+        do { buf[l++] = (char)('0' + x % 10); x /= 10; } while (x);
+        if (v < 0) buf[l++] = '-';
+        while (l) s.push_back(buf[--l]);
     }
-}
-
-static int get_rlen(int n_cigar, const uint32_t *cigar)
-{
-    int l = 0;
-    for (int k = 0; k < n_cigar; ++k) { int op = cigar[k] & 0xf; if (op == 0 || op == 2) l += cigar[k] >> 4; }
-    return l;
-}
-
-static std::string format_xa(const MemArgs &ma, const HostIndex &idx, const AlnOut &p, const uint8_t *arena)
-{   // text built by mem_gen_alt (bwamem_extra.c:126-145)
-    std::string s;
-    const XaOut *xa = reinterpret_cast<const XaOut *>(arena + p.xa_off);
-    for (int i = 0; i < p.xa_n; ++i) {
-        const XaOut &t = xa[i];
-        s += idx.contigs[t.rid].name;
-        s.push_back(',');
-        s.push_back("+-"[t.is_rev]);
-        put_int(s, t.pos + 1);
-        s.push_back(',');
-        put_cigar(s, t.n_cigar, reinterpret_cast<const uint32_t *>(arena + t.cigar_off), "MIDSHN", -1);
-        s.push_back(',');
-        put_int(s, t.NM);
-        if (ma.opt.flag & F_XB) { s.push_back(','); put_int(s, t.score); }
-        s.push_back(';');
-    }
-    return s;
-}
-
-static int count_alts(const std::string &tag, int is_crick)
-{   // countAlts (bs_helpers.cpp:9-16)
-    char strand = is_crick ? '+' : '-';
-    return tag.find(strand) != std::string::npos ? 1 : 0;
-}
+    void pa(double r) { char buf[64]; snprintf(buf, sizeof buf, "\tpa:f:%.3f", r); s += buf; }
+};
 
 static const unsigned char kNt4[256] = {
     4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
@@ -356,202 +321,46 @@ static const unsigned char kNt4[256] = {
     4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
     4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
 
-struct MateView { bool present; int64_t pos; int rid, is_rev, n_cigar, rlen, ch_meth, ch_unmeth; };
-
-static void format_one(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int ei, const AlnOut *list, int n, int which,
-                       const MateView &mate, const uint8_t *arena, std::string &str, EntryStats &st)
+// everything bsb_sam.h reads, over the host copies of one batch and its results
+SamView make_sam_view(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, const BatchResult &res)
 {
-    const Opt &opt = ma.opt;
-    AlnOut p = list[which];
-    MateView m = mate;
-    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(arena + p.cigar_off);
-    std::string xa = p.xa_n > 0 ? format_xa(ma, idx, p, arena) : std::string();
-    int is_mate_crick = 0, is_crick = 0, bs_conflict = 0, reverse = 0;
-    double ch_meth = 0, ch_unmeth = 0;
-    if (p.rid >= 0) {
-        is_crick = idx.contigs[p.rid].is_crick;
-        reverse = p.is_rev ? 1 : 0;
-        ch_meth += p.ch_meth; ch_unmeth += p.ch_unmeth;
-        if (p.xa_n > 0) bs_conflict = count_alts(xa, is_crick);
-        if (is_crick) {
-            p.is_rev = 1;
-            if (m.present && m.rid >= 0) {
-                ch_unmeth += m.ch_unmeth; ch_meth += m.ch_meth;
-                is_mate_crick = idx.contigs[m.rid].is_crick;
-                m.is_rev = is_mate_crick ? 1 : 0;
-                if (is_crick != is_mate_crick) bs_conflict = 1;
-            }
-        } else {
-            p.is_rev = 0;
-            if (m.present && m.rid >= 0) m.is_rev = is_mate_crick ? 1 : 0;
-        }
-    }
-    if (bs_conflict) { p.score = 0; p.mapq = 0; }
-    p.flag |= p.rid < 0 ? 0x4 : 0;
-    p.flag |= m.present && m.rid < 0 ? 0x8 : 0;
-    if (p.rid < 0 && m.present && m.rid >= 0) { p.rid = m.rid; p.pos = m.pos; p.n_cigar = 0; }
-    if (m.present && m.rid < 0 && p.rid >= 0) { m.rid = p.rid; m.pos = p.pos; m.n_cigar = 0; m.rlen = 0; }
-    p.flag |= p.is_rev ? 0x10 : 0;
-    p.flag |= m.present && m.is_rev ? 0x20 : 0;
+    SamView v;
+    memset(&v, 0, sizeof v);
+    v.flag = ma.opt.flag; v.ch_conversion_threshold = ma.opt.ch_conversion_threshold; v.ch_conversion_proportion = ma.opt.ch_conversion_proportion;
+    v.rg_id = ma.rg_id.data(); v.rg_len = (int)ma.rg_id.size();
+    v.names = b.names.data(); v.name_off = b.name_off.data();
+    v.bases = b.bases.data(); v.qual = b.qual.data(); v.seq_off = b.seq_off.data();
+    v.has_qual = b.has_qual.data(); v.pattern = b.pattern.data();
+    v.cmt = b.comments.data(); v.cmt_off = b.cmt_off.data();
+    v.ctg_text = idx.ctg_text.data(); v.ctg_name_off = idx.ctg_name_off.data(); v.ctg_anno_off = idx.ctg_anno_off.data();
+    v.ctg_is_crick = idx.ctg_is_crick.data(); v.ctg_sign = idx.ctg_sign.data();
+    v.arena = res.arena.data(); v.reads = res.reads.data();
+    return v;
+}
 
-    const int l_seq = b.len(ei);
-    const char *bases = b.bases.data() + b.seq_off[ei];
-    const char *qual = b.qual.data() + b.seq_off[ei];
-    const bool has_qual = b.has_qual[ei] != 0;
-    str.append(b.names.data() + b.name_off[ei], b.name_off[ei + 1] - b.name_off[ei]);
-    str.push_back('\t');
-    put_int(str, (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0));
-    str.push_back('\t');
-    const bool hard = !(opt.flag & F_SOFTCLIP) && !p.is_alt;
-    if (p.rid >= 0) {
-        str += idx.contigs[p.rid].name; str.push_back('\t');
-        put_int(str, p.pos + 1); str.push_back('\t');
-        put_int(str, p.mapq); str.push_back('\t');
-        if (p.n_cigar) put_cigar(str, p.n_cigar, cigar, "MIDSH", hard ? (which ? 4 : 3) : -1);
-        else str.push_back('*');
-    } else str += "*\t0\t0\t*";
-    str.push_back('\t');
-    if (m.present && m.rid >= 0) {
-        if (p.rid == m.rid) str.push_back('=');
-        else str += idx.contigs[m.rid].name;
-        str.push_back('\t');
-        put_int(str, m.pos + 1); str.push_back('\t');
-        if (p.rid == m.rid) {
-            int64_t p0 = p.pos, p1 = m.pos;
-            if (p0 > p1) p0 += get_rlen(p.n_cigar, cigar) - 1;
-            else p1 += m.rlen - 1;
-            if (m.n_cigar == 0 || p.n_cigar == 0) str.push_back('0');
-            else put_int(str, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
-        } else str.push_back('0');
-    } else str += "*\t0\t0";
-    str.push_back('\t');
-    if (p.flag & 0x100) {
-        str += "*\t*";
-    } else {
-        int qb = 0, qe = l_seq;
-        if (p.n_cigar && which && hard) {
-            int c0 = cigar[0] & 0xf, c1 = cigar[p.n_cigar - 1] & 0xf;
-            if (!reverse) {
-                if (c0 == 4 || c0 == 3) qb += cigar[0] >> 4;
-                if (c1 == 4 || c1 == 3) qe -= cigar[p.n_cigar - 1] >> 4;
-            } else {
-                if (c0 == 4 || c0 == 3) qe -= cigar[0] >> 4;
-                if (c1 == 4 || c1 == 3) qb += cigar[p.n_cigar - 1] >> 4;
-            }
-        }
-        const int nq = qe > qb ? qe - qb : 0;
-        const size_t at = str.size();
-        str.resize(at + (size_t)nq + 1 + (has_qual ? (size_t)nq : 1));   // SEQ \t QUAL in one growth, filled through a pointer
-        char *o = &str[at];
-        if (!reverse) {
-            for (int i = qb; i < qe; ++i) *o++ = "ACGTN"[kNt4[(unsigned char)bases[i]]];
-            *o++ = '\t';
-            if (has_qual) memcpy(o, qual + qb, (size_t)nq);
-            else *o = '*';
-        } else {
-            for (int i = qe - 1; i >= qb; --i) *o++ = "TGCAN"[kNt4[(unsigned char)bases[i]]];
-            *o++ = '\t';
-            if (has_qual) for (int i = qe - 1; i >= qb; --i) *o++ = qual[i];
-            else *o = '*';
-        }
-    }
-    if (p.n_cigar) {
-        str += "\tNM:i:"; put_int(str, p.NM);
-        str += "\tMD:Z:"; str.append(reinterpret_cast<const char *>(arena + p.md_off), p.md_len);
-        if (ch_unmeth + ch_meth >= opt.ch_conversion_threshold) {
-            double prop = ch_meth / (ch_unmeth + ch_meth);
-            str += "\tXC:i:";
-            str.push_back(prop < opt.ch_conversion_proportion ? '0' : '1');
-        }
-    }
-    if (p.score >= 0) { str += "\tAS:i:"; put_int(str, p.score); }
-    if (p.sub >= 0) { str += "\tXS:i:"; put_int(str, p.sub); }
-    if (!ma.rg_id.empty()) { str += "\tRG:Z:"; str += ma.rg_id; }
-    if (p.rid >= 0) {
-        const int pattern = b.pattern[ei];
-        str += "\tYS:Z:";
-        if (is_crick) {
-            if (pattern) { str += "C_G2A"; st.mapped = 1; }
-            else { str += "C_C2T"; st.mapped = 2; }
-            str += "\tXG:Z:GA";
-        } else {
-            if (pattern) { str += "W_G2A"; st.mapped = 3; }
-            else { str += "W_C2T"; st.mapped = 4; }
-            str += "\tXG:Z:CT";
-        }
-    }
-    if (bs_conflict) str += "\tYC:i:1";
-    if (!(p.flag & 0x100)) {
-        int i;
-        for (i = 0; i < n; ++i)
-            if (i != which && !(list[i].flag & 0x100)) break;
-        if (i < n) {
-            str += "\tSA:Z:";
-            for (i = 0; i < n; ++i) {
-                const AlnOut &r = list[i];
-                if (i == which || (r.flag & 0x100)) continue;
-                str += idx.contigs[r.rid].name; str.push_back(',');
-                put_int(str, r.pos + 1); str.push_back(',');
-                str.push_back("+-"[r.is_rev]); str.push_back(',');
-                put_cigar(str, r.n_cigar, reinterpret_cast<const uint32_t *>(arena + r.cigar_off), "MIDSH", -1);
-                str.push_back(','); put_int(str, r.mapq);
-                str.push_back(','); put_int(str, r.NM);
-                str.push_back(';');
-            }
-        }
-        if (p.alt_sc > 0) {
-            char buf[64];
-            snprintf(buf, sizeof buf, "\tpa:f:%.3f", (double)p.score / p.alt_sc);
-            str += buf;
-        }
-    }
-    if (p.xa_n > 0) {
-        str += (opt.flag & F_XB) ? "\tXB:Z:" : "\tXA:Z:";
-        str += xa;
-    }
-    if (b.cmt_off[ei + 1] > b.cmt_off[ei]) {
-        str.push_back('\t');
-        str.append(b.comments.data() + b.cmt_off[ei], b.cmt_off[ei + 1] - b.cmt_off[ei]);
-    }
-    if ((opt.flag & F_REF_HDR) && p.rid >= 0 && !idx.contigs[p.rid].anno.empty()) {
-        str += "\tXR:Z:";
-        for (char ch : idx.contigs[p.rid].anno) str.push_back(ch == '\t' ? ' ' : ch);
-    }
-    st.alignment_score += p.score;
-    st.bs_conflict = bs_conflict;
-    st.crick = is_crick;
-    if (m.present) st.paired = 1;
-    str.push_back('\n');
+static void stats_from(const SamStats &s, EntryStats &st)
+{
+    st.alignment_score = s.alignment_score; st.mapped = s.mapped; st.bs_conflict = s.bs_conflict; st.crick = s.crick; st.paired = s.paired;
 }
 
 void format_entry(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int i, const BatchResult &res,
                   std::string &sam, EntryStats &st)
 {
-    const ReadOut &ro = res.reads[i];
-    const uint8_t *arena = res.arena.data();
-    const AlnOut *list = reinterpret_cast<const AlnOut *>(arena + ro.aln_off);
-    MateView mv;
-    mv.present = (ma.opt.flag & F_PE) != 0;
-    mv.pos = ro.h_pos; mv.rid = ro.h_rid; mv.is_rev = ro.h_is_rev; mv.n_cigar = ro.h_n_cigar; mv.rlen = ro.h_rlen;
-    mv.ch_meth = ro.h_ch_meth; mv.ch_unmeth = ro.h_ch_unmeth;
     sam.clear();
-    st = EntryStats();
-    for (int k = 0; k < ro.n_aln; ++k) format_one(ma, idx, b, i, list, ro.n_aln, k, mv, arena, sam, st);
+    const SamView v = make_sam_view(ma, idx, b, res);
+    SamString o = {sam};
+    SamStats ss;
+    sam_entry(o, v, i, (ma.opt.flag & F_PE) != 0, ss);
+    stats_from(ss, st);
 }
 
 // the same, appended to a buffer shared by consecutive entries (the pipeline's formatter)
-static void format_entry_append(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int i, const BatchResult &res,
-                                std::string &buf, EntryStats &st)
+static void format_entry_append(const SamView &v, bool is_pe, int i, std::string &buf, EntryStats &st)
 {
-    const ReadOut &ro = res.reads[i];
-    const uint8_t *arena = res.arena.data();
-    const AlnOut *list = reinterpret_cast<const AlnOut *>(arena + ro.aln_off);
-    MateView mv;
-    mv.present = (ma.opt.flag & F_PE) != 0;
-    mv.pos = ro.h_pos; mv.rid = ro.h_rid; mv.is_rev = ro.h_is_rev; mv.n_cigar = ro.h_n_cigar; mv.rlen = ro.h_rlen;
-    mv.ch_meth = ro.h_ch_meth; mv.ch_unmeth = ro.h_ch_unmeth;
-    st = EntryStats();
-    for (int k = 0; k < ro.n_aln; ++k) format_one(ma, idx, b, i, list, ro.n_aln, k, mv, arena, buf, st);
+    SamString o = {buf};
+    SamStats ss;
+    sam_entry(o, v, i, is_pe, ss);
+    stats_from(ss, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -986,11 +795,13 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 const int nt = std::max(1, std::min(host_threads, batch.n / 256 + 1));
                 const int chunk = (batch.n + nt - 1) / nt;
                 for (int t = 0; t < nt; ++t) { pieces[t].lo = std::min(batch.n, t * chunk); pieces[t].hi = std::min(batch.n, (t + 1) * chunk); }
+                const SamView view = make_sam_view(ma, idx, batch, j->res);
+                const bool is_pe = (ma.opt.flag & F_PE) != 0;
                 parallel_for(nt, nt, [&](int t) {
                     Piece &pc = pieces[t];
                     pc.buf.clear(); pc.end.resize(pc.hi - pc.lo);
                     for (int i = pc.lo; i < pc.hi; ++i) {
-                        format_entry_append(ma, idx, batch, i, j->res, pc.buf, st[i]);
+                        format_entry_append(view, is_pe, i, pc.buf, st[i]);
                         pc.end[i - pc.lo] = pc.buf.size();
                     }
                 }, 1);

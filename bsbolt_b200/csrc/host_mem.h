@@ -69,6 +69,8 @@ public:
 
 struct EntryStats { int alignment_score = 0, mapped = 0, bs_conflict = 0, crick = 0, paired = 0; };
 
+struct SamView;
+SamView make_sam_view(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, const BatchResult &res);
 std::string sam_header(const HostIndex &idx, const MemArgs &ma);
 void format_entry(const MemArgs &ma, const HostIndex &idx, const ReadBatch &b, int i, const BatchResult &res,
                   std::string &sam, EntryStats &st);
