@@ -512,6 +512,27 @@ __global__ void __launch_bounds__(128) k_final_pe_heavy(Opt opt, IndexView ix, B
     for (int k = gw; k < n; k += nw) stage_final_pe_heavy(opt, ix, B, heavy[k], ws, wregs, sw);
 }
 
+// SAM text on the device (bsb_sam.h): sizes, then (after a scan) the bytes, one thread per entry
+__global__ void __launch_bounds__(128) k_sam_count(SamView v, int n, int is_pe, uint32_t *len, SamStats *stats)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SamCount o;
+    SamStats st;
+    sam_entry(o, v, i, is_pe != 0, st);
+    len[i] = (uint32_t)o.n;
+    stats[i] = st;
+}
+
+__global__ void __launch_bounds__(128) k_sam_write(SamView v, int n, int is_pe, const uint32_t *off, char *text)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SamWrite o = {text + off[i]};
+    SamStats st;
+    sam_entry(o, v, i, is_pe != 0, st);
+}
+
 // Index-load time: expands the reference's SA sample (every sa_intv-th rank) into the full suffix array in
 // HBM. SA values do not depend on the sampling rate, so lookups become one 4-byte load
 // instead of ~31 dependent 64-byte LF steps. One thread per sample walks LF until the next sampled rank.
@@ -641,6 +662,8 @@ struct BatchCtx {
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
     DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
     DevBuf<int32_t> d_heavy;
+    // device-side SAM text
+    DevBuf<char> d_names, d_qual, d_text, d_rg; DevBuf<uint32_t> d_name_off, d_text_len, d_text_off; DevBuf<uint8_t> d_has_qual; DevBuf<SamStats> d_stats;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used;
     size_t arena_cap = 0;
@@ -679,6 +702,8 @@ struct CudaAligner::Impl {
     IndexView ix;
     DevBuf<double> d_log;
     std::vector<double> log_tab;
+    DevBuf<char> d_ctg_text; DevBuf<uint32_t> d_ctg_name_off, d_ctg_anno_off; DevBuf<uint8_t> d_ctg_is_crick, d_ctg_sign;   // SAM formatter's contig table
+    bool any_alt = false;
     long launches = 0;        // index-load kernels
     BatchCtx ctx[CudaAligner::kSlots];
     std::mutex init_m;
@@ -723,6 +748,12 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
         CK(cudaDeviceSynchronize());
         m.ix.sa32 = m.d_sa32.p; m.ix.sa32_intv = 1;
         ++m.launches;
+    }
+    {   // contig table of the SAM formatter
+        auto up = [](auto &dst, const auto &src) { dst.ensure(src.size() + 1); if (!src.empty()) CK(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(src[0]), cudaMemcpyHostToDevice)); };
+        up(m.d_ctg_text, idx.ctg_text); up(m.d_ctg_name_off, idx.ctg_name_off); up(m.d_ctg_anno_off, idx.ctg_anno_off);
+        up(m.d_ctg_is_crick, idx.ctg_is_crick); up(m.d_ctg_sign, idx.ctg_sign);
+        m.any_alt = idx.any_alt;
     }
     build_log_table(m.log_tab, 65536);
     m.d_log.ensure(m.log_tab.size());
@@ -807,6 +838,14 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemcpyAsync(m.d_bases.p, b.bases.data(), nb, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(m.d_seq_off.p, b.seq_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(m.d_pattern.p, b.pattern.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    const bool dev_text = out.want_text && !I.any_alt && b.comments.empty() && !getenv("BSB_HOST_FORMAT");
+    if (dev_text) {   // what the device formatter reads besides the results: names, qualities
+        m.d_names.ensure(b.names.size() + 16); m.d_name_off.ensure(n + 2); m.d_qual.ensure(nb + 16); m.d_has_qual.ensure(n + 1);
+        CK(cudaMemcpyAsync(m.d_names.p, b.names.data(), b.names.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(m.d_name_off.p, b.name_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(m.d_qual.p, b.qual.data(), nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(m.d_has_qual.p, b.has_qual.data(), (size_t)n, cudaMemcpyHostToDevice, st));
     }
     CK(cudaEventRecord(m.ev[1], st));
     T("h2d_enq");
@@ -1069,9 +1108,46 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         if (used <= m.arena_cap) break;
         m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
     }
-    // ---- D2H ----
-    out.arena.resize_uninit((size_t)used);
-    CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
+    // ---- SAM text on the device, D2H ----
+    out.have_text = false;
+    size_t text_bytes = 0;
+    if (dev_text && n) {
+        SamView v;
+        memset(&v, 0, sizeof v);
+        v.flag = opt.flag; v.ch_conversion_threshold = opt.ch_conversion_threshold; v.ch_conversion_proportion = opt.ch_conversion_proportion;
+        m.d_rg.ensure(out.rg_id.size() + 1);
+        if (!out.rg_id.empty()) CK(cudaMemcpyAsync(m.d_rg.p, out.rg_id.data(), out.rg_id.size(), cudaMemcpyHostToDevice, st));
+        v.rg_id = m.d_rg.p; v.rg_len = (int)out.rg_id.size();
+        v.names = m.d_names.p; v.name_off = m.d_name_off.p; v.bases = B.bases; v.qual = m.d_qual.p; v.seq_off = B.seq_off;
+        v.has_qual = m.d_has_qual.p; v.pattern = B.pattern; v.cmt = nullptr; v.cmt_off = nullptr;
+        v.ctg_text = I.d_ctg_text.p; v.ctg_name_off = I.d_ctg_name_off.p; v.ctg_anno_off = I.d_ctg_anno_off.p;
+        v.ctg_is_crick = I.d_ctg_is_crick.p; v.ctg_sign = I.d_ctg_sign.p;
+        v.arena = m.d_arena.p; v.reads = m.d_out.p;
+        m.d_text_len.ensure(n + 2); m.d_text_off.ensure(n + 2); m.d_stats.ensure(n + 1);
+        CK(cudaMemsetAsync(m.d_text_len.p + n, 0, 4, st));
+        k_sam_count<<<cdiv(n, 128), 128, 0, st>>>(v, n, pe ? 1 : 0, m.d_text_len.p, m.d_stats.p);
+        size_t sb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, sb, m.d_text_len.p, m.d_text_off.p, n + 1, st);
+        m.d_cub.ensure(sb + 16);
+        cub::DeviceScan::ExclusiveSum(m.d_cub.p, sb, m.d_text_len.p, m.d_text_off.p, n + 1, st);
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, m.d_text_off.p + n, 4, cudaMemcpyDeviceToHost, st));
+        m.wait();
+        text_bytes = total;
+        m.d_text.ensure(text_bytes + 16);
+        k_sam_write<<<cdiv(n, 128), 128, 0, st>>>(v, n, pe ? 1 : 0, m.d_text_off.p, m.d_text.p);
+        m.launches += 3;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(m.ev[11], st));
+        out.text.resize_uninit(text_bytes); out.text_off.resize(n + 1); out.stats.resize(n);
+        CK(cudaMemcpyAsync(out.text.data(), m.d_text.p, text_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out.text_off.data(), m.d_text_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out.stats.data(), m.d_stats.p, (size_t)n * sizeof(SamStats), cudaMemcpyDeviceToHost, st));
+        out.have_text = true;
+    } else {
+        out.arena.resize_uninit((size_t)used);
+        CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(m.ev[9], st));
     m.wait();
     T("d2h_done");
@@ -1088,7 +1164,11 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     out.ms_kernels = ms;
     out.n_seeds = S;
     out.h2d_bytes = nb + (size_t)(n + 1) * 4 + (size_t)n;
-    out.d2h_bytes = (size_t)used + (size_t)n * sizeof(ReadOut);
+    out.d2h_bytes = (out.have_text ? text_bytes + (size_t)(n + 1) * 4 + (size_t)n * sizeof(SamStats) : (size_t)used) + (size_t)n * sizeof(ReadOut);
+    if (out.have_text) {
+        CK(cudaEventElapsedTime(&ms, m.ev[8], m.ev[11])); out.ms_text = ms;
+        out.h2d_bytes += b.names.size() + (size_t)(n + 1) * 4 + nb + (size_t)n;
+    }
 }
 
 } // namespace bsb

@@ -6,6 +6,7 @@
 // Everything the text depends on is reached through SamView: plain pointers into the batch arrays, the record arena
 // and a flattened contig table, so the same bytes serve host and device.
 #pragma once
+#include <stddef.h>
 #include "bsb_hd.h"
 
 namespace bsb {

@@ -753,6 +753,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 std::unique_ptr<Job> j;
                 while (q_read.pop(j)) {
                     double ta = now_sec();
+                    j->res.want_text = true; j->res.rg_id = ma.rg_id;   // SAM text from the device when the aligner can produce it
                     aligner.align(ma.opt, j->batch, j->n_processed, ma.have_pes0 ? ma.pes0 : nullptr, j->res, slot);
                     j->sec_align = now_sec() - ta;
                     { std::lock_guard<std::mutex> l(res_m); t_res1 = std::max(t_res1, now_sec()); }
@@ -782,16 +783,50 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
             try {
                 const ReadBatch &batch = j->batch;
                 if (sum.n_batches == 0 && g_host_alloc.prefill && !resident && !t_prefill.joinable()) {
-                    const size_t s_bases = batch.bases.capacity(), s_arena = j->res.arena.size(), s_reads = j->res.reads.size() * sizeof(ReadOut);
+                    const size_t s_bases = batch.bases.capacity(), s_names = batch.names.capacity(), s_reads = j->res.reads.size() * sizeof(ReadOut);
+                    const size_t s_arena = j->res.have_text ? j->res.text.size() : j->res.arena.size();
+                    const size_t s_off = j->res.text_off.size() * 4, s_stats = j->res.stats.size() * sizeof(SamStats);
                     t_prefill = std::thread([=] {
-                        g_host_alloc.prefill(s_bases, n_jobs - 1); g_host_alloc.prefill(s_arena + s_arena / 4 + 4096, n_jobs - 1);
+                        g_host_alloc.prefill(s_bases, 2 * (n_jobs - 1));     // bases and qualities
+                        g_host_alloc.prefill(s_names, n_jobs - 1);
+                        g_host_alloc.prefill(s_arena + s_arena / 4 + 4096, n_jobs - 1);
                         g_host_alloc.prefill(s_reads + s_reads / 4 + 4096, n_jobs - 1);
+                        if (s_off) { g_host_alloc.prefill(s_off + s_off / 4 + 4096, n_jobs - 1); g_host_alloc.prefill(s_stats + s_stats / 4 + 4096, n_jobs - 1); }
                     });
                 }
                 sum.sec_align += j->sec_align;
                 sum.add_timing(j->res);
                 double tf = now_sec();
                 st.resize(batch.n);
+                MapStats ms;
+                size_t total = 0;
+                double tw;
+                if (j->res.have_text) {
+                    // the records were formatted on the device: only the arbiter runs here
+                    const BatchResult &R = j->res;
+                    parallel_for(host_threads, batch.n, [&](int i) {
+                        const SamStats &x = R.stats[i];
+                        st[i].alignment_score = x.alignment_score; st[i].mapped = x.mapped; st[i].bs_conflict = x.bs_conflict; st[i].crick = x.crick; st[i].paired = x.paired;
+                    });
+                    sam_sort_plan(batch, st, emit, rewrite, ms);
+                    bool as_is = (int)emit.size() == batch.n;
+                    for (int k = 0; as_is && k < batch.n; ++k) as_is = emit[k] == k && !rewrite[k];
+                    const char *text = reinterpret_cast<const char *>(R.text.data());
+                    if (as_is) {
+                        tw = now_sec();
+                        total = R.text.size();
+                        fwrite(text, 1, total, out);
+                    } else {
+                        std::string all;
+                        for (int i : emit) {
+                            if (rewrite[i]) { set_unmapped(batch, i, st[i], tmp); all += tmp; }
+                            else all.append(text + R.text_off[i], R.text_off[i + 1] - R.text_off[i]);
+                        }
+                        total = all.size();
+                        tw = now_sec();
+                        fwrite(all.data(), 1, total, out);
+                    }
+                } else {
                 const int nt = std::max(1, std::min(host_threads, batch.n / 256 + 1));
                 const int chunk = (batch.n + nt - 1) / nt;
                 for (int t = 0; t < nt; ++t) { pieces[t].lo = std::min(batch.n, t * chunk); pieces[t].hi = std::min(batch.n, (t + 1) * chunk); }
@@ -805,12 +840,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                         pc.end[i - pc.lo] = pc.buf.size();
                     }
                 }, 1);
-                MapStats ms;
                 sam_sort_plan(batch, st, emit, rewrite, ms);
                 bool as_is = (int)emit.size() == batch.n;
                 for (int k = 0; as_is && k < batch.n; ++k) as_is = emit[k] == k && !rewrite[k];
-                size_t total = 0;
-                double tw;
                 if (as_is) {
                     tw = now_sec();
                     for (int t = 0; t < nt; ++t) { fwrite(pieces[t].buf.data(), 1, pieces[t].buf.size(), out); total += pieces[t].buf.size(); }
@@ -829,6 +861,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                     total = all.size();
                     tw = now_sec();
                     fwrite(all.data(), 1, total, out);
+                }
                 }
                 if (parts) fprintf(parts, "%ld\t%zu\t%zu\n", j->batch_id, out_bytes, total);
                 out_bytes += total;
@@ -849,7 +882,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 sum.n_entries += batch.n;
             } catch (const std::exception &e) { set_fail(e.what()); }
             if (resident) {   // the page-locked host buffers go back to the pool now, for the batches still to come
-                j->res.arena.reset(); j->res.reads.reset(); j->batch.bases.reset();
+                j->res.arena.reset(); j->res.reads.reset(); j->res.text.reset(); j->res.text_off.reset(); j->res.stats.reset(); j->batch.bases.reset();
                 finished.push_back(std::move(j));
             }   // (device inputs are freed after the run: cudaFree synchronises the device)
             else q_free.push(std::move(j));

@@ -8,6 +8,7 @@
 //   estimate_pestat() <- mem_pestat from per-pair candidates    (bwamem_pair.c:46-109)
 //   run_mem()         <- main_mem + process() pipeline          (fastmap.c:10-76, 319-363)
 #pragma once
+#include "bsb_sam.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -50,6 +51,13 @@ struct BatchResult {
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
     double ms_select = 0, ms_tasks = 0; uint64_t n_tasks = 0;   // split of stage 7: record selection / alignment tasks
+    // SAM text formatted on the device (bsb_sam.h): requested by the caller with want_text (+ the read-group id, if any);
+    // when have_text comes back true, `text` holds the records of all entries back to back (entry i = bytes
+    // [text_off[i], text_off[i+1])), `stats` the per-entry statistics the arbiter needs, and `arena` was not copied back.
+    bool want_text = false, have_text = false;
+    std::string rg_id;
+    RawBuf text; PinArray<uint32_t> text_off; PinArray<SamStats> stats;
+    double ms_text = 0;
 };
 
 class BatchAligner {

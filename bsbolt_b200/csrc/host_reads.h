@@ -141,10 +141,10 @@ struct ReadBatch {
     int n = 0;
     std::vector<uint32_t> seq_off;   // n+1 offsets into bases/qual
     PinVec bases;                    // ASCII as read from the file (unconverted); uploaded to the device
-    std::vector<char> qual;          // same offsets as bases; valid iff has_qual
+    PinVec qual;                     // same offsets as bases; valid iff has_qual (uploaded for the device SAM formatter)
     std::vector<uint8_t> has_qual;
     std::vector<uint32_t> name_off;  // n+1
-    std::vector<char> names;
+    PinVec names;
     std::vector<uint32_t> cmt_off;   // n+1 (empty ranges unless -C)
     std::vector<char> comments;
     std::vector<uint8_t> first, read_group, pattern;
