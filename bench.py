@@ -51,15 +51,17 @@ def _simulate_step(args):
     return paths, n
 
 
-def prepare_workload(work, genome_mb, n_steps, batch_pairs, rank, seed0=1000):
-    """Genome + per-step FASTQ pairs (rank-specific reads, shared genome)."""
+def prepare_workload(work, genome_mb, n_steps, batch_pairs, rank, seed0=1000, dist=None):
+    """Genome + per-step FASTQ pairs (rank-specific reads, shared genome written by rank 0 only)."""
     from bsbolt_b200 import simulate
     os.makedirs(work, exist_ok=True)
     fa = os.path.join(work, 'genome.fa')
-    if not os.path.exists(fa + '.done'):
+    if rank == 0 and not os.path.exists(fa + '.done'):
         n_ctg = 10
         simulate.make_genome(fa, [genome_mb * 1000000 // n_ctg] * n_ctg, seed=20240517)
         open(fa + '.done', 'w').write('ok')
+    if dist:
+        dist.barrier()
     jobs = []
     for s in range(n_steps):
         prefix = os.path.join(work, f'r{rank}_s{s}')
@@ -188,7 +190,7 @@ def main():
 
     # ---------------- workload ----------------
     t0 = time.time()
-    fa, jobs = prepare_workload(work, a.genome_mb, W + K, a.batch_pairs, rank) if (rank == 0 or True) else (None, None)
+    fa, jobs = prepare_workload(work, a.genome_mb, W + K, a.batch_pairs, rank, dist=dist)
     sim_workers = max(1, min(len(jobs), cores // max(world, 1), 8))
     sims = run_simulation(jobs, sim_workers)
     t_sim = time.time() - t0
