@@ -288,6 +288,21 @@ def main():
     _, st_res = fenced(lambda: run(f1, f2, {'BSB_RESIDENT_BENCH': '1'}))                     # value: inputs resident
     clocks = sampler.stop()
     _, st_one = fenced(lambda: run(f1, f2, {'BSB_RESIDENT_BENCH': '1', 'BSB_GPU_SLOTS': '1'}))  # clean per-kernel times
+    # the reference's default output (`-O prefix`: bwa mem | stream_bam): FASTQ files -> BAM file, on the first 4 steps' reads
+    bam_info = None
+    if world == 1:
+        nb = min(4, K) * a.batch_pairs
+        b1 = os.path.join(work, 'bam_1.fq'); b2 = os.path.join(work, 'bam_2.fq'); bam_path = os.path.join(work, 'bench_out.bam')
+        head_records(f1, b1, nb); head_records(f2, b2, nb)
+        for level in (-1, 1):
+            t = time.time()
+            rc, st_b = _native.mem_main_bam(argv_common + [db, b1, b2], bam_path, index=idx, threads=0, level=level, log_fd=null)
+            dt = time.time() - t
+            if rc:
+                raise RuntimeError(_native.last_error())
+            bam_info = bam_info or {'api': 'bsb_mem_main_bam (FASTQ files on host -> BGZF/BAM file)', 'reads': 2 * nb, 'unit': 'reads/s'}
+            bam_info['zlib_default' if level < 0 else f'zlib_level_{level}'] = {'value': 2 * nb / dt, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path)}
+        os.remove(bam_path)
     ms_resident, ms_total_wall = st_res['sec_resident'] * 1000, wall * 1000
     ms_one = st_one['sec_resident'] * 1000
     reads_all = n_reads_timed
@@ -352,7 +367,7 @@ def main():
                          'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms,
                          'reads_per_launch': reads_per_launch, **layout},
-            'cpu_baseline': cpu, 'parity_vs_reference': parity,
+            'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info,
             'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
             'final_split_ms_per_step': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},
             'stage_note': 'CUDA-event stage times of the run with ONE batch in flight (with two in flight the stages of different batches overlap)',

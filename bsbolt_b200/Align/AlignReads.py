@@ -113,8 +113,7 @@ class BisulfiteAlignmentAndProcessing:
                 merge_shards(sams, parts, sys.stdout.buffer)
                 sys.stdout.buffer.flush()
             else:
-                from bsbolt_b200.Utils.BamOutput import sam_to_bam
+                from bsbolt_b200.Utils.BamOutput import sam_file_to_bam
                 with open(f'{d}/merged.sam', 'wb') as o:
                     merge_shards(sams, parts, o)
-                with open(f'{d}/merged.sam') as f:
-                    sam_to_bam(f, f'{self.output}.bam', self.output_threads)
+                sam_file_to_bam(f'{d}/merged.sam', f'{self.output}.bam', self.output_threads)

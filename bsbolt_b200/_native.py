@@ -33,7 +33,8 @@ class Read(C.Structure):
 
 EXPORTS = ('bsb_version', 'bsb_last_error', 'bsb_device_count', 'bsb_index_load', 'bsb_index_free',
            'bsb_index_hbm_bytes', 'bsb_index_n_contigs', 'bsb_mem_main', 'bsb_batch_create', 'bsb_batch_align',
-           'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header', 'bsb_index_build')
+           'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header', 'bsb_index_build',
+           'bsb_mem_main_bam', 'bsb_stream_bam')
 
 
 def lib():
@@ -55,6 +56,9 @@ def lib():
     L.bsb_index_hbm_bytes.argtypes = [C.c_void_p]
     L.bsb_index_n_contigs.argtypes = [C.c_void_p]
     L.bsb_mem_main.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(RunStats)]
+    L.bsb_mem_main_bam.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(RunStats)]
+    L.bsb_stream_bam.restype = C.c_int64
+    L.bsb_stream_bam.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int]
     L.bsb_batch_create.restype = C.c_void_p
     L.bsb_batch_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(Read), C.POINTER(Read)]
     L.bsb_batch_align.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RunStats)]
@@ -116,6 +120,24 @@ def mem_main(argv, index=None, device=0, out_fd=1, log_fd=2):
     arr = _argv(argv)
     rc = lib().bsb_mem_main(index._h if index is not None else None, int(device), len(argv), arr, int(out_fd), int(log_fd), C.byref(st))
     return rc, st.as_dict()
+
+
+def mem_main_bam(argv, bam_path, index=None, device=0, threads=0, level=-1, log_fd=2):
+    """`bwa mem ... | stream_bam -@ threads -o bam_path` in one call: records leave as BAM. threads <= 0: this process's
+    share of the cores; level: zlib level, -1 = default (as stream_bam). Returns (return code, stats dict)."""
+    st = RunStats()
+    arr = _argv(argv)
+    rc = lib().bsb_mem_main_bam(index._h if index is not None else None, int(device), len(argv), arr, str(bam_path).encode(),
+                                int(threads), int(level), int(log_fd), C.byref(st))
+    return rc, st.as_dict()
+
+
+def stream_bam(in_fd, bam_path, threads=0, level=-1):
+    """SAM text on a file descriptor -> BAM file (host only). Returns the number of records."""
+    n = lib().bsb_stream_bam(int(in_fd), str(bam_path).encode(), int(threads), int(level))
+    if n < 0:
+        raise RuntimeError(last_error())
+    return n
 
 
 def align_batch(index, opt_argv, reads1, reads2=None, n_processed=0):

@@ -10,6 +10,8 @@
 #include <cuda_runtime_api.h>
 #include "bsb_cuda.h"
 #include "bsb_index_build.h"
+#include "host_bam.h"
+#include <thread>
 
 using namespace bsb;
 
@@ -81,10 +83,20 @@ static std::string make_pg(int argc, char **argv)
     return pg;
 }
 
-int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, int log_fd, bsb_run_stats_t *stats)
+static int host_thread_share()
+{
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) n /= std::max(1, atoi(e));
+    if (const char *e = getenv("BSB_HOST_THREADS")) n = atoi(e);
+    return std::max(1, std::min(n - 4, 64));
+}
+
+static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, const char *bam_path, int bam_threads, int bam_level,
+                         int log_fd, bsb_run_stats_t *stats)
 {
     FILE *out = nullptr, *log = nullptr;
     bsb_index_t *own = nullptr;
+    std::unique_ptr<BamWriter> bam;
     int ret = 1;
     try {
         MemArgs ma;
@@ -96,26 +108,52 @@ int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd
             if (!own) throw std::runtime_error(g_err);
             idx = own;
         }
-        int ofd = dup(out_fd), lfd = dup(log_fd);
-        if (!ma.out_path.empty()) { out = fopen(ma.out_path.c_str(), "wb"); if (ofd >= 0) close(ofd); }
-        else out = fdopen(ofd, "w");
+        int lfd = dup(log_fd);
         log = fdopen(lfd, "w");
-        if (!out || !log) throw std::runtime_error("[E::bsb_mem_main] cannot open the output streams");
-        setvbuf(out, nullptr, _IOFBF, 1 << 22);
+        if (bam_path) bam.reset(new BamWriter(bam_path, bam_threads > 0 ? bam_threads : host_thread_share(), bam_level));
+        else {
+            int ofd = dup(out_fd);
+            if (!ma.out_path.empty()) { out = fopen(ma.out_path.c_str(), "wb"); if (ofd >= 0) close(ofd); }
+            else out = fdopen(ofd, "w");
+            if (out) setvbuf(out, nullptr, _IOFBF, 1 << 22);
+        }
+        if ((!out && !bam) || !log) throw std::runtime_error("[E::bsb_mem_main] cannot open the output streams");
         if (ma.ignore_alt) throw std::runtime_error("[E::bsb_mem_main] -j needs an index loaded without ALT marks; not supported with a resident index");
         idx->aligner->verbose = ma.verbose;
         RunSummary sum;
-        ret = run_mem(ma, idx->host, *idx->aligner, out, log, &sum);
+        ret = run_mem(ma, idx->host, *idx->aligner, out, log, &sum, bam.get());
+        if (bam) { bam->close(); sum.sec_write += bam->sec_busy(); }
         fill_stats(stats, sum, idx->aligner.get());
     } catch (const std::exception &e) {
         g_err = e.what();
         if (log) fprintf(log, "%s\n", e.what());
         ret = 1;
     }
+    bam.reset();
     if (out) fclose(out);
     if (log) fclose(log);
     if (own) bsb_index_free(own);
     return ret;
+}
+
+int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, int log_fd, bsb_run_stats_t *stats)
+{
+    return mem_main_impl(idx, device, argc, argv, out_fd, nullptr, 0, -1, log_fd, stats);
+}
+
+int bsb_mem_main_bam(bsb_index_t *idx, int device, int argc, char **argv, const char *bam_path, int threads, int level, int log_fd,
+                     bsb_run_stats_t *stats)
+{
+    if (!bam_path) { g_err = "[E::bsb_mem_main_bam] bam_path is NULL"; return 1; }
+    return mem_main_impl(idx, device, argc, argv, -1, bam_path, threads, level, log_fd, stats);
+}
+
+int64_t bsb_stream_bam(int in_fd, const char *bam_path, int threads, int level)
+{
+    try {
+        if (!bam_path) throw std::runtime_error("[E::bsb_stream_bam] bam_path is NULL");
+        return (int64_t)stream_bam(in_fd, bam_path, threads > 0 ? threads : host_thread_share(), level);
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
 bsb_batch_t *bsb_batch_create(bsb_index_t *idx, int opt_argc, char **opt_argv, int n, const bsb_read_t *r1, const bsb_read_t *r2)

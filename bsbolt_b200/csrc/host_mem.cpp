@@ -1,5 +1,6 @@
 // host_mem.cpp -- see host_mem.h
 #include "host_mem.h"
+#include "host_bam.h"
 #include "bsb_hd.h"
 #include "bsb_sam.h"
 #include <ctype.h>
@@ -644,7 +645,7 @@ private:
 // Three overlapped stages, like the reference's kt_pipeline (fastmap.c:352) but with the GPU in the
 // middle: [read + convert-pattern bookkeeping] -> [device batch] -> [SAM text + arbiter + write].
 // Each stage handles batches strictly in input order, so output order and n_processed are unchanged.
-int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary)
+int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary, BamWriter *bam)
 {
     double t0 = now_sec();
     FastxReader r1(ma.fq1);
@@ -653,7 +654,16 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     std::string hdr = sam_header(idx, ma);
     const int shard_count = ma.shard_count > 1 ? ma.shard_count : 1, shard_index = ma.shard_index;
     size_t out_bytes = 0;
-    if (shard_index == 0) { fwrite(hdr.data(), 1, hdr.size(), out); out_bytes += hdr.size(); }
+    if (bam && shard_count > 1) throw std::runtime_error("[E::run_mem] BAM output of a sharded run is written after the merge");
+    // records leave as SAM text on `out` or, with a BamWriter, as BAM records (the `| stream_bam` half of the reference pipeline)
+    auto put_out = [&](const char *p, size_t n) {
+        if (bam) bam->records(p, n);
+        else if (fwrite(p, 1, n, out) != n) throw std::runtime_error("[E::run_mem] writing the SAM stream failed");
+    };
+    if (shard_index == 0) {
+        if (bam) bam->header(hdr); else put_out(hdr.data(), hdr.size());
+        out_bytes += hdr.size();
+    }
     FILE *parts = nullptr;
     if (shard_count > 1 && !ma.shard_parts.empty()) {
         parts = fopen(ma.shard_parts.c_str(), "w");
@@ -815,7 +825,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                     if (as_is) {
                         tw = now_sec();
                         total = R.text.size();
-                        fwrite(text, 1, total, out);
+                        put_out(text, total);
                     } else {
                         std::string all;
                         for (int i : emit) {
@@ -824,7 +834,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                         }
                         total = all.size();
                         tw = now_sec();
-                        fwrite(all.data(), 1, total, out);
+                        put_out(all.data(), total);
                     }
                 } else {
                 const int nt = std::max(1, std::min(host_threads, batch.n / 256 + 1));
@@ -845,7 +855,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 for (int k = 0; as_is && k < batch.n; ++k) as_is = emit[k] == k && !rewrite[k];
                 if (as_is) {
                     tw = now_sec();
-                    for (int t = 0; t < nt; ++t) { fwrite(pieces[t].buf.data(), 1, pieces[t].buf.size(), out); total += pieces[t].buf.size(); }
+                    for (int t = 0; t < nt; ++t) { put_out(pieces[t].buf.data(), pieces[t].buf.size()); total += pieces[t].buf.size(); }
                 } else {   // some entries dropped or rewritten by the arbiter: assemble the text entry by entry
                     tmp.clear();
                     auto span = [&](int i, const char *&p, size_t &l) {
@@ -860,7 +870,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                     }
                     total = all.size();
                     tw = now_sec();
-                    fwrite(all.data(), 1, total, out);
+                    put_out(all.data(), total);
                 }
                 }
                 if (parts) fprintf(parts, "%ld\t%zu\t%zu\n", j->batch_id, out_bytes, total);
@@ -895,7 +905,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (t_prefill.joinable()) t_prefill.join();
     for (auto &h : finished) aligner.unload(h->batch);
     finished.clear();
-    fflush(out);
+    if (out) fflush(out);
     if (parts) fclose(parts);
     sum.sec_read = std::max(sec_plan, sec_fill);   // the slower of the reader's two overlapped halves
     sum.sec_resident = resident ? t_res1 - t_res0 : 0;

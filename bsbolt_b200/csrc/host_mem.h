@@ -117,6 +117,8 @@ struct RunSummary {
 };
 
 // The whole `bwa mem` run. SAM goes to `out`, log/BSStat lines to `log`.
-int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary);
+class BamWriter;   // host_bam.h
+// SAM text goes to `out`, or -- when `bam` is given -- BAM records go to the BamWriter and `out` may be NULL
+int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary, BamWriter *bam = nullptr);
 
 } // namespace bsb

@@ -62,6 +62,17 @@ int bsb_index_n_contigs(const bsb_index_t *idx);  /* includes the hidden crick c
  * `device` and freed at the end). Returns 0 on success. */
 int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, int log_fd, bsb_run_stats_t *stats);
 
+/* replaces the reference's whole output pipeline `bwa mem ... | stream_bam -@ <threads> -o <bam_path>`
+ * (bsbolt/Align/AlignReads.py:52-60; bsbolt/External/HTSLIB/stream_bam.c): as bsb_mem_main, but the records are
+ * encoded as BAM (what htslib's sam_parse1 + bam_write1 make of the same SAM lines: the uncompressed BAM stream is
+ * byte-identical to the reference's) and BGZF-compressed by `threads` host threads (<= 0: this process's share of
+ * the cores) at zlib `level` (0..9, -1 = zlib default = what stream_bam uses). */
+int bsb_mem_main_bam(bsb_index_t *idx, int device, int argc, char **argv, const char *bam_path, int threads, int level,
+                     int log_fd, bsb_run_stats_t *stats);
+/* replaces stream_bam itself (HTSLIB/stream_bam.c main): SAM text on in_fd -> BAM file. Host only (needs no device).
+ * Returns the number of records written, -1 on error. */
+int64_t bsb_stream_bam(int in_fd, const char *bam_path, int threads, int level);
+
 /* replaces bseq_read (bwa.c:73-145) for reads already in host memory: builds the bseq entries of one
  * batch (conversion-pattern assessment, undirectional duplication). r2 may be NULL (single end).
  * opt_argc/opt_argv: `bwa mem` options only (argv[0] == "mem", no positional arguments). */

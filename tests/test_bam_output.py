@@ -1,0 +1,164 @@
+"""BAM output (`bsbolt Align -O`, the `| stream_bam` half of the reference pipeline): the uncompressed BAM stream of
+the native writer (bsbolt_b200/csrc/host_bam.cpp, through the C ABI) must be byte-identical to what the reference's
+htslib encoder makes of the same SAM text -- against committed digests of reference runs (tests/golden/bam_golden.json,
+made by tests/golden/make_bam_golden.py) and, where oracle/_ref/stream_bam exists, against a live run of it."""
+import gzip
+import hashlib
+import json
+import os
+import struct
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+STREAM_BAM = os.path.join(ROOT, 'oracle', '_ref', 'stream_bam')
+EOF_BLOCK = bytes.fromhex('1f8b08040000000000ff0600424302001b0003000000000000000000')
+
+
+def golden_streams():
+    return json.load(open(os.path.join(GOLDEN, 'bam_golden.json')))['streams']
+
+
+def sam_bytes(name):
+    p = os.path.join(GOLDEN, name)
+    return gzip.open(p, 'rb').read() if name.endswith('.gz') else open(p, 'rb').read()
+
+
+def bgzf_blocks(data):
+    """walks the BGZF framing; returns the uncompressed payloads"""
+    out, off = [], 0
+    while off < len(data):
+        assert data[off:off + 4] == b'\x1f\x8b\x08\x04' and data[off + 10:off + 16] == b'\x06\x00BC\x02\x00', f'bad BGZF header at {off}'
+        bsize, = struct.unpack('<H', data[off + 16:off + 18])
+        block = data[off:off + bsize + 1]
+        crc, isize = struct.unpack('<II', block[-8:])
+        import zlib
+        payload = zlib.decompress(block[18:-8], -15)
+        assert len(payload) == isize and isize <= 0xff00 and (zlib.crc32(payload) & 0xffffffff) == crc
+        out.append(payload)
+        off += bsize + 1
+    return out
+
+
+def walk_records(raw):
+    """(header text, reference names, list of record byte strings) of an uncompressed BAM stream"""
+    assert raw[:4] == b'BAM\x01'
+    l_text, = struct.unpack('<i', raw[4:8])
+    text = raw[8:8 + l_text]
+    off = 8 + l_text
+    n_ref, = struct.unpack('<i', raw[off:off + 4]); off += 4
+    names = []
+    for _ in range(n_ref):
+        l_name, = struct.unpack('<i', raw[off:off + 4]); off += 4
+        names.append(raw[off:off + l_name - 1].decode()); off += l_name + 4
+    recs = []
+    while off < len(raw):
+        bs, = struct.unpack('<i', raw[off:off + 4])
+        recs.append(raw[off:off + 4 + bs]); off += 4 + bs
+    assert off == len(raw)
+    return text, names, recs
+
+
+@pytest.mark.parametrize('name', sorted(json.load(open(os.path.join(GOLDEN, 'bam_golden.json')))['streams']))
+@pytest.mark.parametrize('threads', [1, 3])
+def test_stream_identical_to_reference_encoder(built, tmp_path, name, threads):
+    from bsbolt_b200 import _native
+    want = golden_streams()[name]
+    src = tmp_path / 'in.sam'
+    src.write_bytes(sam_bytes(name))
+    fd = os.open(src, os.O_RDONLY)
+    try:
+        n = _native.stream_bam(fd, tmp_path / 'out.bam', threads=threads, level=-1)
+    finally:
+        os.close(fd)
+    data = open(tmp_path / 'out.bam', 'rb').read()
+    assert data.endswith(EOF_BLOCK)
+    blocks = bgzf_blocks(data)
+    raw = b''.join(blocks)
+    assert len(raw) == want['raw_len'] and hashlib.sha256(raw).hexdigest() == want['raw_sha256']
+    assert gzip.open(tmp_path / 'out.bam', 'rb').read() == raw            # also readable as a plain multi-member gzip file
+    text, names, recs = walk_records(raw)
+    assert n == len(recs) == sum(1 for l in sam_bytes(name).split(b'\n') if l and not l.startswith(b'@'))
+    # like htslib, no record is split across blocks unless it is larger than a block
+    ends, pos = set(), 0
+    for b in blocks:
+        pos += len(b); ends.add(pos)
+    off = len(raw) - sum(len(r) for r in recs)
+    for r in recs:
+        if len(r) <= 0xff00:
+            inside = [e for e in ends if off < e < off + len(r)]
+            assert not inside, 'a record that fits a block was split'
+        off += len(r)
+    if os.path.exists(STREAM_BAM):   # the reference encoder itself, live
+        subprocess.run([STREAM_BAM, '-o', str(tmp_path / 'ref.bam')], stdin=open(src), check=True, stderr=subprocess.DEVNULL)
+        assert gzip.open(tmp_path / 'ref.bam', 'rb').read() == raw
+
+
+def test_levels_and_empty_input(built, tmp_path):
+    from bsbolt_b200 import _native
+    src = tmp_path / 'in.sam'
+    src.write_bytes(sam_bytes('se100.sam.gz'))
+    raws = []
+    for level in (0, 1, 9):
+        fd = os.open(src, os.O_RDONLY)
+        _native.stream_bam(fd, tmp_path / f'l{level}.bam', threads=2, level=level)
+        os.close(fd)
+        raws.append(b''.join(bgzf_blocks(open(tmp_path / f'l{level}.bam', 'rb').read())))
+    assert raws[0] == raws[1] == raws[2]
+    assert os.path.getsize(tmp_path / 'l9.bam') < os.path.getsize(tmp_path / 'l1.bam') < os.path.getsize(tmp_path / 'l0.bam')
+    # header only, and nothing at all
+    for body in (b'@SQ\tSN:c\tLN:5\n', b''):
+        src.write_bytes(body)
+        fd = os.open(src, os.O_RDONLY)
+        assert _native.stream_bam(fd, tmp_path / 'e.bam', threads=1) == 0
+        os.close(fd)
+        text, names, recs = walk_records(gzip.open(tmp_path / 'e.bam', 'rb').read())
+        assert text == body and recs == [] and names == (['c'] if body else [])
+
+
+def test_malformed_records_fail_loudly(built, tmp_path):
+    from bsbolt_b200 import _native
+    src = tmp_path / 'in.sam'
+    for bad in (b'r\t0\tc\t1\t0\t4M\t*\t0\t0\tACG\tIII\n',        # CIGAR/SEQ length mismatch
+                b'r\t0\tc\t1\t0\t3M\t*\t0\t0\tACG\tII\n',         # SEQ/QUAL length mismatch
+                b'r\t0\tc\t1\t0\t3Q\t*\t0\t0\tACG\tIII\n',        # unknown CIGAR operator
+                b'r\t0\tc\t1\n'):                                  # truncated
+        src.write_bytes(b'@SQ\tSN:c\tLN:50\n' + bad)
+        fd = os.open(src, os.O_RDONLY)
+        with pytest.raises(RuntimeError, match='bam_encode'):
+            _native.stream_bam(fd, tmp_path / 'x.bam', threads=1)
+        os.close(fd)
+
+
+@pytest.mark.gpu
+def test_aligner_writes_the_bam_the_reference_pipeline_would(built, golden, tmp_path):
+    """bsb_mem_main_bam == bsb_mem_main | stream_bam: same records as the golden SAM, identical uncompressed stream."""
+    from bsbolt_b200 import _native
+    from conftest import strip_pg
+    idx = _native.Index(golden.idxbase, 0)
+    try:
+        for case in ('pe150', 'se100_un'):
+            argv = golden.argv(case) + []
+            argv = argv[:-len(golden.cases[case]['fq']) - 1] + ['-K', '150000'] + argv[-len(golden.cases[case]['fq']) - 1:]
+            with open(tmp_path / 'log', 'w') as fl:
+                rc, st = _native.mem_main_bam(argv, tmp_path / f'{case}.bam', index=idx, threads=3, level=1, log_fd=fl.fileno())
+            assert rc == 0, _native.last_error()
+            with open(tmp_path / f'{case}.sam', 'w') as fo, open(tmp_path / 'log2', 'w') as fl:
+                rc, _ = _native.mem_main(argv, index=idx, out_fd=fo.fileno(), log_fd=fl.fileno())
+            assert rc == 0
+            assert open(tmp_path / 'log').read() == open(tmp_path / 'log2').read()      # same BSStat lines
+            sam = open(tmp_path / f'{case}.sam').read()
+            assert strip_pg(sam) == golden.sam(case)
+            raw = b''.join(bgzf_blocks(open(tmp_path / f'{case}.bam', 'rb').read()))
+            fd = os.open(tmp_path / f'{case}.sam', os.O_RDONLY)
+            _native.stream_bam(fd, tmp_path / 'via_sam.bam', threads=1)
+            os.close(fd)
+            assert gzip.open(tmp_path / 'via_sam.bam', 'rb').read() == raw
+            if os.path.exists(STREAM_BAM):
+                subprocess.run([STREAM_BAM, '-o', str(tmp_path / 'ref.bam')], stdin=open(tmp_path / f'{case}.sam'), check=True, stderr=subprocess.DEVNULL)
+                assert gzip.open(tmp_path / 'ref.bam', 'rb').read() == raw
+            assert len(walk_records(raw)[2]) == golden.cases[case]['n_records']
+    finally:
+        idx.close()

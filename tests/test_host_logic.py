@@ -53,11 +53,12 @@ def test_api_surface():
         BisulfiteAlignmentAndProcessing(['bwa', 'index'], output_to_stdout=True).align_reads()
 
 
-def test_bam_encoder_round_trip(golden, tmp_path):
-    from bsbolt_b200.Utils.BamOutput import sam_to_bam
+def test_bam_encoder_round_trip(built, golden, tmp_path):
+    from bsbolt_b200.Utils.BamOutput import sam_file_to_bam
     sam = golden.sam('pe150')
+    (tmp_path / 'x.sam').write_text(sam)
     out = tmp_path / 'x.bam'
-    sam_to_bam(io.StringIO(sam), str(out), threads=2)
+    assert sam_file_to_bam(str(tmp_path / 'x.sam'), str(out), threads=2) == golden.cases['pe150']['n_records']
     raw = gzip.open(out, 'rb').read()
     assert raw[:4] == b'BAM\x01'
     l_text, = struct.unpack('<i', raw[4:8])
