@@ -24,6 +24,18 @@ struct RefSeq {           // reference bases in the doubled coordinate space: st
 
 struct ExtResult { int score, qle, tle, gtle, gscore, max_off; };
 
+// Early end of the extension loop (both forms of sw_extend). ksw_extend2 keeps filling rows until the row maximum is 0,
+// z-drop fires or the target window ends -- for a query that has been consumed that is up to max_gap more full-width
+// rows whose only possible effects are a larger `max`, or a to-end score >= gscore. Once the band has reached the end of
+// the query (end == qlen: every cell a later row can read was written by this row, nothing stale) define
+//     phi = max_j ( H[j] > 0 ? H[j] + amax*(qlen-j) : 0 ,  E[j] > 0 ? E[j] + amax*(qlen-1-j) : 0 )
+// over the stored row (H[j] = H(i,j-1), the diagonal source of column j; E[j] = E(i+1,j); amax = largest matrix entry).
+// Every cell of every later row satisfies h(i',j') + amax*(qlen-1-j') <= phi: M gains at most amax per column, E and F
+// only lose, zero cells stay zero (M = H ? H + s : 0), and the first-column source h0 - o_del - e_del*(i'+1) only shrinks.
+// So when phi <= max and phi < gscore no later row can change max/max_i/max_j/max_off (they need m > max) or
+// gscore/max_ie (they need h1 >= gscore): the loop may stop with identical results.
+BSB_HD bool ext_rows_exhausted(int phi, int max, int gscore) { return phi <= max && phi < gscore; }
+
 // eh: scratch of 2*(qlen+1) ints
 template <class Q, class T>
 BSB_HD ExtResult sw_extend(int qlen, const Q &query, int tlen, const T &target, const int8_t *mat,
@@ -42,6 +54,7 @@ BSB_HD ExtResult sw_extend(int qlen, const Q &query, int tlen, const T &target, 
     max_del = (int)((double)(qlen * max + end_bonus - o_del) / e_del + 1.);
     max_del = max_del > 1 ? max_del : 1;
     w = w < max_del ? w : max_del;
+    const int amax = max;
     max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
     beg = 0; end = qlen;
     for (i = 0; i < tlen; ++i) {
@@ -84,6 +97,14 @@ BSB_HD ExtResult sw_extend(int qlen, const Q &query, int tlen, const T &target, 
             } else {
                 if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break;
             }
+        }
+        if (end == qlen) {
+            int phi = 0;
+            for (j = beg; j < end; ++j) {
+                t = H[j] > 0 ? H[j] + amax * (qlen - j) : 0; phi = phi > t ? phi : t;
+                t = E[j] > 0 ? E[j] + amax * (qlen - 1 - j) : 0; phi = phi > t ? phi : t;
+            }
+            if (ext_rows_exhausted(phi, max, gscore)) break;
         }
         for (j = beg; j < end && H[j] == 0 && E[j] == 0; ++j) {}
         beg = j;

@@ -52,6 +52,7 @@ __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, con
     max_del = (int)((double)(qlen * max + end_bonus - o_del) / e_del + 1.);
     max_del = max_del > 1 ? max_del : 1;
     w = w < max_del ? w : max_del;
+    const int amax = max;
     max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
     beg = 0; end = qlen;
     __syncwarp();
@@ -68,6 +69,8 @@ __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, con
         int carry_g = NEG_BIG, carry_h = h1;       // running F source, H(i, j-1) entering the chunk
         int best = -1;                              // (h << 12 | j) maximum of the row
         int first_nz = -1, last_nz = -1;            // non-zero cells of the updated row in [beg,end)
+        int phi = 0;                                // what any later row can still reach (ext_rows_exhausted, bsb_ksw.h)
+        const bool at_qend = end == qlen;
         for (int c0 = beg; c0 < end; c0 += 32) {
             const int j = c0 + lane;
             const bool act = j < end;
@@ -92,6 +95,11 @@ __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, con
             int hprev = __shfl_up_sync(FULLMASK, h, 1);
             if (lane == 0) hprev = carry_h;
             if (act) { H[j] = hprev; E[j] = e2; }
+            if (at_qend && act) {                   // per lane; reduced once per row below
+                int p1 = hprev > 0 ? hprev + amax * (qlen - j) : 0, p2 = e2 > 0 ? e2 + amax * (qlen - 1 - j) : 0;
+                p1 = p1 > p2 ? p1 : p2;
+                phi = phi > p1 ? phi : p1;
+            }
             int key = act ? (h << 12 | j) : -1;
             key = warp_max(key);
             best = best > key ? best : key;
@@ -124,6 +132,7 @@ __device__ ExtResult sw_extend_warp(int qlen, const QrySeq &query, int tlen, con
                 if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break;
             }
         }
+        if (at_qend && ext_rows_exhausted(warp_max(phi), max, gscore)) break;
         // next band: drop leading/trailing cells whose h and e are both zero
         int nb = first_nz >= 0 ? first_nz : end;
         int jl;
