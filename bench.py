@@ -74,11 +74,13 @@ def run_simulation(jobs, workers):
         return list(ex.map(_simulate_step, jobs))
 
 
-def concat(paths, dst):
+def concat(paths, dst, remove=False):
     with open(dst, 'wb') as o:
         for p in paths:
             with open(p, 'rb') as f:
                 shutil.copyfileobj(f, o, 1 << 24)
+            if remove:      # the per-step files are only needed once (keeps the scratch footprint of an 8-rank run down)
+                os.remove(p)
 
 
 class ClockSampler:
@@ -197,11 +199,18 @@ def main():
     warm = [p for (paths, n) in sims[:W] for p in paths]
     timed_pairs = sum(n for (_, n) in sims[W:])
     f1 = os.path.join(work, f'r{rank}_timed_1.fq'); f2 = os.path.join(work, f'r{rank}_timed_2.fq')
-    concat([paths[0] for (paths, n) in sims[W:]], f1)
-    concat([paths[1] for (paths, n) in sims[W:]], f2)
     w1 = os.path.join(work, f'r{rank}_warm_1.fq'); w2 = os.path.join(work, f'r{rank}_warm_2.fq')
-    if W:
-        concat(warm[0::2], w1); concat(warm[1::2], w2)
+    if a.impl != 'reference':             # (the reference arm samples every step's own file)
+        concat([paths[0] for (paths, n) in sims[W:]], f1, remove=True)
+        concat([paths[1] for (paths, n) in sims[W:]], f2, remove=True)
+        if W:
+            concat(warm[0::2], w1, remove=True); concat(warm[1::2], w2, remove=True)
+
+    def cleanup():
+        if not a.keep:
+            for f in [f1, f2, w1, w2] + [p for (paths, n) in sims for p in paths]:
+                if os.path.exists(f):
+                    os.remove(f)
     n_reads_timed = 2 * timed_pairs
 
     bwa = os.path.join(ROOT, 'oracle', '_ref', 'bwa')
@@ -241,6 +250,7 @@ def main():
                                  'sample': f'{sp} pairs per step of the same simulated reads, bwa mem -t {cores}, clock from first batch read to exit'},
                 'e2e': {'value': val, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
+        cleanup()
         return 0
 
     # ---------------- B200 arm ----------------
@@ -314,6 +324,7 @@ def main():
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         reads_all = float(c[0])
     if rank != 0:
+        cleanup()
         return 0
     n_batches = max(1, st['n_batches'])
     value = reads_all / (ms_resident / 1000)
@@ -375,8 +386,7 @@ def main():
             'setup_s': {'simulate': t_sim, 'index_build_or_wait': t_index}, 'index_hbm_bytes': idx.hbm_bytes}
     print(json.dumps(line))
     os.close(null)
-    if not a.keep:
-        pass
+    cleanup()
     return 0
 
 
