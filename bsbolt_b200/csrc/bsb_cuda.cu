@@ -536,19 +536,22 @@ __global__ void __launch_bounds__(128) k_sam_write(SamView v, int n, int is_pe, 
 // Index-load time: expands the reference's SA sample (every sa_intv-th rank) into the full suffix array in
 // HBM. SA values do not depend on the sampling rate, so lookups become one 4-byte load
 // instead of ~31 dependent 64-byte LF steps. One thread per sample walks LF until the next sampled rank.
-__global__ void k_dense_sa(IndexView ix, uint64_t n_sa, uint32_t *sa32)
+// sa_hi (optional): bits 32..39 of every entry, for texts of 2^32 symbols or more.
+__global__ void k_dense_sa(IndexView ix, uint64_t n_sa, uint32_t *sa32, uint8_t *sa_hi)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_sa) return;
     uint64_t k = j * (uint64_t)ix.sa_intv;
     uint64_t v = j == 0 ? ix.seq_len : ix.sa[j];
     sa32[k] = j == 0 ? 0xffffffffu : (uint32_t)v;
+    if (sa_hi) sa_hi[k] = j == 0 ? 0xff : (uint8_t)(v >> 32);
     const uint64_t mask = (uint64_t)ix.sa_intv - 1;
     for (;;) {
         k = fm_lf(ix, k);
         --v;
         if ((k & mask) == 0) break;
         sa32[k] = (uint32_t)v;
+        if (sa_hi) sa_hi[k] = (uint8_t)(v >> 32);
     }
 }
 
@@ -698,7 +701,7 @@ struct BatchCtx {
 struct CudaAligner::Impl {
     int device = 0, n_sm = 0;
     // resident index
-    DevBuf<uint32_t> d_bwt, d_sa32, d_occ32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac; DevBuf<Ann> d_anns;
+    DevBuf<uint32_t> d_bwt, d_sa32, d_occ32; DevBuf<uint64_t> d_sa; DevBuf<uint8_t> d_pac, d_opac, d_sa_hi; DevBuf<Ann> d_anns;
     IndexView ix;
     DevBuf<double> d_log;
     std::vector<double> log_tab;
@@ -731,7 +734,7 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     m.d_anns.ensure(idx.anns.size()); CK(cudaMemcpy(m.d_anns.p, idx.anns.data(), idx.anns.size() * sizeof(Ann), cudaMemcpyHostToDevice));
     m.ix = idx.host_view();
     m.ix.bwt = m.d_bwt.p; m.ix.sa = m.d_sa.p; m.ix.pac = m.d_pac.p; m.ix.opac = m.d_opac.p; m.ix.anns = m.d_anns.p;
-    m.ix.sa32 = nullptr; m.ix.sa32_intv = 0; m.ix.occ32 = nullptr;
+    m.ix.sa32 = nullptr; m.ix.sa32_intv = 0; m.ix.occ32 = nullptr; m.ix.sa_hi = nullptr;
     if (idx.seq_len + 1 < (1ull << 32) && !getenv("BSB_REF_BLOCKS")) {   // sector-sized occ blocks for seeding
         const uint64_t nb32 = (uint64_t)(idx.bwt.size() / 16) * 2;
         m.d_occ32.ensure(nb32 * 8);
@@ -741,12 +744,23 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
         m.ix.occ32 = m.d_occ32.p;
         ++m.launches;
     }
-    if (idx.seq_len + 1 < (1ull << 32) && !getenv("BSB_SAMPLED_SA")) { // full SA resident in HBM (4 B/rank)
+    // full SA resident in HBM: 4 B/rank below 2^32 symbols, else 5 B/rank (40-bit entries) when it fits beside the rest of
+    // the index with room left for the batches (a 12.4 G-symbol human-scale text: 62 GB of the 180 GB)
+    const bool wide_sa = idx.seq_len + 1 >= (1ull << 32) || getenv("BSB_DENSE_SA40");
+    bool dense_sa = !getenv("BSB_SAMPLED_SA");
+    if (dense_sa && wide_sa) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)(idx.seq_len + 1) * 5, reserve = (size_t)32 << 30;
+        if (idx.seq_len >= (1ull << 40) || (free_b < need + reserve && !getenv("BSB_DENSE_SA40"))) dense_sa = false;
+    }
+    if (dense_sa) {
         m.d_sa32.ensure(idx.seq_len + 1);
-        k_dense_sa<<<(unsigned)((idx.n_sa + 127) / 128), 128>>>(m.ix, idx.n_sa, m.d_sa32.p);
+        if (wide_sa) m.d_sa_hi.ensure(idx.seq_len + 1);
+        k_dense_sa<<<(unsigned)((idx.n_sa + 127) / 128), 128>>>(m.ix, idx.n_sa, m.d_sa32.p, wide_sa ? m.d_sa_hi.p : nullptr);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
-        m.ix.sa32 = m.d_sa32.p; m.ix.sa32_intv = 1;
+        m.ix.sa32 = m.d_sa32.p; m.ix.sa32_intv = 1; m.ix.sa_hi = wide_sa ? m.d_sa_hi.p : nullptr;
         ++m.launches;
     }
     {   // contig table of the SAM formatter
@@ -799,7 +813,7 @@ int CudaAligner::device() const { return im_->device; }
 size_t CudaAligner::index_bytes() const
 {
     const Impl &m = *im_;
-    return m.d_bwt.cap * 4 + m.d_occ32.cap * 4 + m.d_sa.cap * 8 + m.d_sa32.cap * 4 + m.d_pac.cap + m.d_opac.cap;
+    return m.d_bwt.cap * 4 + m.d_occ32.cap * 4 + m.d_sa.cap * 8 + m.d_sa32.cap * 4 + m.d_sa_hi.cap + m.d_pac.cap + m.d_opac.cap;
 }
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

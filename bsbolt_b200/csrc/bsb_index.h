@@ -21,8 +21,10 @@ struct IndexView {
     int64_t l_pac, crick_l;
     int32_t n_seqs, sa_intv;
     // optional result-preserving denser SA (values are independent of the sampling rate)
-    const uint32_t *sa32;   // when non-null: SA sampled every sa32_intv ranks, 32-bit entries (seq_len < 2^32)
+    const uint32_t *sa32;   // when non-null: SA sampled every sa32_intv ranks, low 32 bits of each entry
     int32_t sa32_intv, pad_;
+    const uint8_t *sa_hi;   // bits 32..39 of the sa32 entries (40-bit SA for texts of >= 2^32 symbols: 5 bytes per rank,
+                            // 62 GB for a human-scale 12.4 G-symbol text -- resident in 180 GB of HBM); null when < 2^32
     // optional sector-sized occ blocks (seq_len < 2^32): one 32-byte block per 64 BWT symbols = 4 x u32 cumulative
     // counts + 4 packed words, so that one rank query is ONE 32-byte sector and one 256-bit load (occ32_* below)
     const uint32_t *occ32;
@@ -290,6 +292,7 @@ BSB_HD uint64_t fm_sa(const IndexView &ix, uint64_t k)
         while (k & mask) { ++steps; k = fm_lf(ix, k); }
         uint64_t j = k / (uint64_t)ix.sa32_intv;
         uint64_t v = j == 0 ? (uint64_t)-1 : (uint64_t)ix.sa32[j];
+        if (ix.sa_hi && j != 0) v |= (uint64_t)ix.sa_hi[j] << 32;
         return steps + v;
     }
     uint64_t mask = (uint64_t)ix.sa_intv - 1;

@@ -150,7 +150,7 @@ IndexView HostIndex::host_view() const
     v.primary = primary; for (int i = 0; i < 5; ++i) v.L2[i] = L2[i];
     v.seq_len = seq_len; v.l_pac = l_pac; v.crick_l = crick_l;
     v.n_seqs = (int)anns.size(); v.sa_intv = sa_intv;
-    v.sa32 = nullptr; v.sa32_intv = 0; v.pad_ = 0; v.occ32 = nullptr;
+    v.sa32 = nullptr; v.sa32_intv = 0; v.pad_ = 0; v.occ32 = nullptr; v.sa_hi = nullptr;
     return v;
 }
 

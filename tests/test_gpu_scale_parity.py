@@ -78,6 +78,8 @@ def test_c2_sampled_suffix_array_layout(big, tmp_path):
     from bsbolt_b200 import simulate
     fqs, n = simulate.simulate_reads(big.names, big.contigs, str(tmp_path / 'pe'), 15000, seed=12, corrupt_frac=0.02)
     both(big, ['-K', '100000000', '-t', '16'], fqs, tmp_path, env={'BSB_SAMPLED_SA': '1', 'BSB_REF_BLOCKS': '1'})
+    # the same wide configuration with the 40-bit dense suffix array (5 bytes per rank) a human-scale index gets when it fits
+    both(big, ['-K', '100000000', '-t', '16'], fqs, tmp_path, env={'BSB_DENSE_SA40': '1', 'BSB_REF_BLOCKS': '1'})
 
 
 def test_c5_undirectional_pe150(big, tmp_path):

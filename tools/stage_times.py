@@ -27,21 +27,23 @@ def main():
     db = os.path.join(work, 'db', 'BSB_ref.fa')
     if not os.path.exists(db + '.sa'):
         index_db.build_database(fa, os.path.join(work, 'db'), device=0)
-    idx = _native.Index(db, 0)
     null = os.open(os.devnull, os.O_WRONLY)
     argv = ['mem'] + bench.LAUNCHER_ARGS + ['-t', '1', '-K', str(a.batch_pairs * 300), '-v', '1', db, f1, f2]
     names = ('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final')
-    _native.mem_main(argv, index=idx, out_fd=null, log_fd=null)   # warm-up
     for cfg in a.configs:
         kv = [x.split('=') for x in cfg.split(',') if x]
         for k, v in kv:
             os.environ[k] = v
+        idx = _native.Index(db, 0)        # some variables (index layout) are read when the index is loaded
+        _native.mem_main(argv, index=idx, out_fd=null, log_fd=null)   # warm-up
         rc, st = _native.mem_main(argv, index=idx, out_fd=null, log_fd=null)
+        hbm = idx.hbm_bytes
+        idx.close()
         for k, v in kv:
             del os.environ[k]
         nb = max(1, st['n_batches'])
         stages = ' '.join(f'{n}={v / nb:.2f}' for n, v in zip(names, st['ms_stage']))
-        print(f'[{cfg or "default"}] rc={rc} kernels={st["ms_kernels"] / nb:.2f} ms/batch | {stages} | select={st["ms_select"] / nb:.2f} tasks={st["ms_tasks"] / nb:.2f}', flush=True)
+        print(f'[{cfg or "default"}] rc={rc} kernels={st["ms_kernels"] / nb:.2f} ms/batch | {stages} | select={st["ms_select"] / nb:.2f} tasks={st["ms_tasks"] / nb:.2f} | index {hbm / 1e9:.2f} GB', flush=True)
 
 
 if __name__ == '__main__':
