@@ -367,13 +367,24 @@ __global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B,
     if (t < B.n) stage_chain(opt, ix, B, order ? order[t] : t);
 }
 
+// Warps of the warp-per-read kernels draw their reads from a global counter (reads differ by orders of magnitude in
+// seeds and chains; a fixed stride leaves most warps idle behind the few that met the heavy reads). ctr == nullptr:
+// fixed stride.
+__device__ __forceinline__ int warp_next_read(int *ctr, int cur, int stride)
+{
+    if (!ctr) return cur + stride;
+    int r = 0;
+    if ((threadIdx.x & 31) == 0) r = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, r, 0);
+}
+
 // K4, one warp per read (bsb_warp.cuh)
-__global__ void __launch_bounds__(128) k_chain_warp(Opt opt, IndexView ix, BatchDev B)
+__global__ void __launch_bounds__(128) k_chain_warp(Opt opt, IndexView ix, BatchDev B, int *ctr)
 {
     __shared__ ChainSmem sm[4];
     const int wib = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int r = gw; r < B.n; r += nw) stage_chain_warp(opt, ix, B, r, sm[wib]);
+    for (int r = warp_next_read(ctr, gw - nw, nw); r < B.n; r = warp_next_read(ctr, r, nw)) stage_chain_warp(opt, ix, B, r, sm[wib]);
 }
 
 
@@ -387,7 +398,8 @@ __global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B
 
 // K5, warp per read: rows of the banded extension across the lanes, (h,e) rows + query in shared memory
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp, const int32_t *order)
+__global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q, int smem_per_warp, const int32_t *order,
+                                                            int *ctr)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int wib = threadIdx.x >> 5;
@@ -396,7 +408,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix
     WarpDp S;
     S.H = (int32_t *)mine; S.E = S.H + (max_q + 1); S.qs = (uint8_t *)(S.E + (max_q + 1));
     DpScratch dp = {eh + (size_t)gw * 2 * (max_q + 1), nullptr, 0, max_q};
-    for (int t = gw; t < B.n; t += nw) stage_extend_warp(opt, ix, B, order ? order[t] : t, S, dp);
+    for (int t = warp_next_read(ctr, gw - nw, nw); t < B.n; t = warp_next_read(ctr, t, nw)) stage_extend_warp(opt, ix, B, order ? order[t] : t, S, dp);
 }
 
 __global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
@@ -679,7 +691,7 @@ struct BatchCtx {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         CK(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
-        d_used.ensure(1); d_misc.ensure(16); d_ntasks.ensure(1);
+        d_used.ensure(1); d_misc.ensure(32); d_ntasks.ensure(1);
         ready = true;
     }
     ~BatchCtx()
@@ -961,8 +973,10 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[4], st));
     // ---- K4 ----
+    const bool dyn_sched = getenv("BSB_STATIC_SCHED") == nullptr;
+    CK(cudaMemsetAsync(m.d_misc.p + 16, 0, 2 * 4, st));        // read counters of the chaining and the extension kernel
     if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, nullptr);
-    else k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B);
+    else k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr);
     ++m.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[5], st));
@@ -980,8 +994,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         const int32_t *ext_order = nullptr;
         const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)I.n_sm * ext_bps);
         m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
-        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
-        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order);
+        int *ext_ctr = dyn_sched ? m.d_misc.p + 17 : nullptr;
+        if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order, ext_ctr);
+        else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order, ext_ctr);
         ++m.launches;
     }
     CK(cudaGetLastError());

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+BSB_GPU_SLOTS=1 python tools/stage_times.py --batches 2 "$@" > gpurun_out/quick_stage.log 2>&1; grep "^\[" gpurun_out/quick_stage.log || tail -5 gpurun_out/quick_stage.log
