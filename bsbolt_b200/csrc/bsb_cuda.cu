@@ -378,6 +378,15 @@ __device__ __forceinline__ int warp_next_read(int *ctr, int cur, int stride)
     return __shfl_sync(0xffffffffu, r, 0);
 }
 
+// the same for kernels whose lanes each take one item: the warp draws 32 consecutive items at a time
+__device__ __forceinline__ unsigned warp_next_group(int *ctr, unsigned cur, unsigned stride)
+{
+    if (!ctr) return cur + stride;
+    unsigned r = 0;
+    if ((threadIdx.x & 31) == 0) r = (unsigned)atomicAdd(ctr, 32);
+    return __shfl_sync(0xffffffffu, r, 0);
+}
+
 // K4, one warp per read (bsb_warp.cuh)
 __global__ void __launch_bounds__(128) k_chain_warp(Opt opt, IndexView ix, BatchDev B, int *ctr)
 {
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(128) k_tasks(Opt opt, IndexView ix, BatchDev B
 
 // K6a: global alignments of the queued alignments that need one (about one in ten), warp-cooperative
 __global__ void __launch_bounds__(128) k_tasks_dp(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint8_t *zbuf, long z_cap, int max_q, int smem_per_warp,
-                                                  uint32_t *slots, int slot_cap, int32_t *n_cig)
+                                                  uint32_t *slots, int slot_cap, int32_t *n_cig, int *ctr)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(128) k_tasks_dp(Opt opt, IndexView ix, BatchDe
     S.H = (int32_t *)mine; S.E = S.H + (max_q + 1); S.qs = (uint8_t *)(S.E + (max_q + 1));
     S.cigar = nullptr; S.cigar_cap = 0; S.md = nullptr; S.md_cap = 0; S.xb = nullptr; S.xb_cap = 0;
     uint8_t *z = zbuf + (size_t)gw * z_cap;
-    for (unsigned int base = gw * 32; base < n_tasks; base += nw * 32) {
+    for (unsigned int base = warp_next_group(ctr, gw * 32 - nw * 32, nw * 32); base < n_tasks; base = warp_next_group(ctr, base, nw * 32)) {
         const unsigned int k = base + lane;
         bool dp = false;
         if (k < n_tasks) { const AlnTask t = B.tasks.a[k]; dp = !B.out[t.read].err && !task_is_trivial(opt, t); }
@@ -479,12 +488,14 @@ __global__ void __launch_bounds__(128) k_tasks_dp(Opt opt, IndexView ix, BatchDe
 
 // K6b + K8b: one thread per queued alignment
 __global__ void __launch_bounds__(128) k_tasks_finish(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint32_t *slots, int slot_cap, const int32_t *n_cig,
-                                                      char *text, int md_cap, int xb_cap)
+                                                      char *text, int md_cap, int xb_cap, int *ctr)
 {
-    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
     char *md = text + (size_t)w * (size_t)(md_cap + xb_cap);
-    for (unsigned int k = w; k < n_tasks; k += nw)
-        stage_task_finish(opt, ix, B, k, slots + (size_t)k * slot_cap, n_cig + k, md, md_cap, md + md_cap, xb_cap);
+    for (unsigned int base = warp_next_group(ctr, (w & ~31u) - nw, nw); base < n_tasks; base = warp_next_group(ctr, base, nw)) {
+        const unsigned int k = base + lane;
+        if (k < n_tasks) stage_task_finish(opt, ix, B, k, slots + (size_t)k * slot_cap, n_cig + k, md, md_cap, md + md_cap, xb_cap);
+    }
 }
 
 __global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch)
@@ -498,17 +509,22 @@ __global__ void __launch_bounds__(32) k_final_se(Opt opt, IndexView ix, BatchDev
 // K7 + K8a, thread per pair. Pairs that need mate-rescue Smith-Waterman are not finalised here: they are queued (heavy,
 // n_heavy) for the warp-cooperative kernel below, before anything has been written for them.
 template <int MINB>
-__global__ void __launch_bounds__(32, MINB) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, int32_t *heavy, int *n_heavy)
+__global__ void __launch_bounds__(32, MINB) k_final_pe(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, int32_t *heavy, int *n_heavy,
+                                                        int *ctr)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    const unsigned np = (unsigned)(B.n >> 1);
     FinalWS ws; AlnReg *wregs;
     make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
-    for (int p = w; p < (B.n >> 1); p += nw)
-        if (stage_final_pe(opt, ix, B, p, ws, wregs, heavy != nullptr)) heavy[atomicAdd(n_heavy, 1)] = p;
+    for (unsigned base = warp_next_group(ctr, (w & ~31u) - nw, nw); base < np; base = warp_next_group(ctr, base, nw)) {
+        const unsigned p = base + lane;
+        if (p < np && stage_final_pe(opt, ix, B, (int)p, ws, wregs, heavy != nullptr)) heavy[atomicAdd(n_heavy, 1)] = (int32_t)p;
+    }
 }
 
 // K7 for the queued pairs: one warp per pair, rescue Smith-Waterman across the lanes (bsb_warp.cuh)
-__global__ void __launch_bounds__(128) k_final_pe_heavy(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, const int32_t *heavy, const int *n_heavy)
+__global__ void __launch_bounds__(128) k_final_pe_heavy(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, const int32_t *heavy, const int *n_heavy,
+                                                        int *ctr)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int wib = threadIdx.x >> 5;
@@ -521,7 +537,7 @@ __global__ void __launch_bounds__(128) k_final_pe_heavy(Opt opt, IndexView ix, B
     sw.qs = reinterpret_cast<uint8_t *>(base + 4 * L.sw_cap); sw.cap = L.sw_cap;
     sw.b = ws.sw.b; sw.cap_b = ws.sw.cap_b;
     const int n = *n_heavy;
-    for (int k = gw; k < n; k += nw) stage_final_pe_heavy(opt, ix, B, heavy[k], ws, wregs, sw);
+    for (int k = warp_next_read(ctr, gw - nw, nw); k < n; k = warp_next_read(ctr, k, nw)) stage_final_pe_heavy(opt, ix, B, heavy[k], ws, wregs, sw);
 }
 
 // SAM text on the device (bsb_sam.h): sizes, then (after a scan) the bytes, one thread per entry
@@ -1087,6 +1103,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         unsigned long long init = 8; // offset 0 = "null"
         CK(cudaMemcpyAsync(m.d_used.p, &init, 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(m.d_ntasks.p, 0, 4, st));
+        CK(cudaMemsetAsync(m.d_misc.p + 18, 0, 4 * 4, st));   // work counters: selection, rescue, task DP, task finish
         B.arena.base = m.d_arena.p; B.arena.used = m.d_used.p; B.arena.cap = m.arena_cap;
         B.tasks.a = m.d_tasks.p; B.tasks.n = m.d_ntasks.p; B.tasks.cap = (unsigned int)m.task_cap;
         if (items) {
@@ -1095,12 +1112,13 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                 int32_t *heavy = coop ? m.d_heavy.p : nullptr;
                 int *n_heavy = m.d_misc.p + 12;
                 CK(cudaMemsetAsync(n_heavy, 0, 4, st));
-                if (fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
-                else if (fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
-                else k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
+                int *c_fin = dyn_sched ? m.d_misc.p + 18 : nullptr, *c_heavy = dyn_sched ? m.d_misc.p + 19 : nullptr;
+                if (fin_bps > 24) k_final_pe<32><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_fin);
+                else if (fin_bps > 16) k_final_pe<24><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_fin);
+                else k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_fin);
                 if (coop) {
                     const int hv_smem = 4 * (int)((4 * L.sw_cap + (L.sw_cap + 3) / 4) * 4);
-                    k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy);
+                    k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
                     ++m.launches;
                 }
             }
@@ -1124,8 +1142,9 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
             m.d_task_ncig.ensure(n_tasks);
             m.d_task_text.ensure((size_t)fin_threads * (md_cap + xb_cap));
             k_tasks_dp<<<tk_blocks, tk_wpb * 32, tk_wpb * dp_smem_per_warp, st>>>(opt, I.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, dp_smem_per_warp,
-                                                                                   m.d_task_cigar.p, slot_cap, m.d_task_ncig.p);
-            k_tasks_finish<<<fin_threads / 128, 128, 0, st>>>(opt, I.ix, B, n_tasks, m.d_task_cigar.p, slot_cap, m.d_task_ncig.p, m.d_task_text.p, md_cap, xb_cap);
+                                                                                   m.d_task_cigar.p, slot_cap, m.d_task_ncig.p, dyn_sched ? m.d_misc.p + 20 : nullptr);
+            k_tasks_finish<<<fin_threads / 128, 128, 0, st>>>(opt, I.ix, B, n_tasks, m.d_task_cigar.p, slot_cap, m.d_task_ncig.p, m.d_task_text.p, md_cap, xb_cap,
+                                                              dyn_sched ? m.d_misc.p + 21 : nullptr);
             m.launches += 2;
         }
         CK(cudaGetLastError());
