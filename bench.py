@@ -160,7 +160,7 @@ def compare_sam(ref_path, my_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=32)
+    ap.add_argument('--steps', type=int, default=48)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--genome-mb', type=int, default=250)
@@ -231,7 +231,8 @@ def main():
                 os.makedirs(os.path.join(work, 'db'), exist_ok=True)
                 shutil.copy(fa, db)
                 sh([bwa, 'index', '-a', 'bwtsw', db])
-        sp = min(a.cpu_sample_pairs, a.batch_pairs)
+        # bounded sample per step: about two minutes of host-core work over the whole --steps/--warmup run
+        sp = min(a.cpu_sample_pairs, a.batch_pairs, max(10000, 4000000 // (W + K)))
         rates, secs = [], []
         for s in range(W + K):
             paths = sims[s][0]

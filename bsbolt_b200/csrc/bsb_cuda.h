@@ -9,7 +9,7 @@ public:
     // uploads the index to HBM of `device`; throws if no CUDA device is usable
     CudaAligner(const HostIndex &idx, int device);
     ~CudaAligner() override;
-    static constexpr int kSlots = 2;   // batches that can be in flight on the device at once (one host thread each)
+    static constexpr int kSlots = 3;   // batches that can be in flight on the device at once (one host thread each)
     int slots() const override { return kSlots; }
     void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot = 0) override;
     void preload(ReadBatch &b) override;

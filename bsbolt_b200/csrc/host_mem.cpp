@@ -680,9 +680,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
-    int n_slots = aligner.slots();
-    if (const char *e = getenv("BSB_GPU_SLOTS")) n_slots = std::max(1, std::min(n_slots, atoi(e)));
-    Channel<std::unique_ptr<Job>> q_plan(2), q_read(2), q_free(16);
+    int n_slots = std::min(2, aligner.slots());   // two batches in flight; a third (BSB_GPU_SLOTS=3) measured no better end to end
+    if (const char *e = getenv("BSB_GPU_SLOTS")) n_slots = std::max(1, std::min(aligner.slots(), atoi(e)));
+    Channel<std::unique_ptr<Job>> q_plan(2), q_read((size_t)std::max(2, n_slots)), q_free(16);
     OrderedDone q_done;
     const int n_jobs = 5 + 2 * n_slots;
     std::thread t_prefill;   // page-locks the transfer buffers of the other jobs while the first batches run
