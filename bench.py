@@ -160,7 +160,7 @@ def compare_sam(ref_path, my_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=48)
+    ap.add_argument('--steps', type=int, default=32)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--genome-mb', type=int, default=250)
@@ -317,7 +317,12 @@ def main():
     ms_resident, ms_total_wall = st_res['sec_resident'] * 1000, wall * 1000
     ms_one = st_one['sec_resident'] * 1000
     reads_all = n_reads_timed
+    per_rank = None
     if dist:
+        mine = torch.tensor([ms_resident, ms_total_wall, ms_one], device=f'cuda:{device}', dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {'ms_resident': [round(float(x[0]), 1) for x in every], 'ms_e2e_wall': [round(float(x[1]), 1) for x in every]}
         t = torch.tensor([ms_resident, ms_total_wall, ms_one], device=f'cuda:{device}', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_resident, ms_total_wall, ms_one = float(t[0]), float(t[1]), float(t[2])
@@ -379,7 +384,7 @@ def main():
                          'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms,
                          'reads_per_launch': reads_per_launch, **layout},
-            'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info,
+            'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info, 'per_rank': per_rank, 'host_cores': cores,
             'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
             'final_split_ms_per_step': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},
             'stage_note': 'CUDA-event stage times of the run with ONE batch in flight (with two in flight the stages of different batches overlap)',
