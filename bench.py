@@ -8,7 +8,7 @@ with a fixed batch size -K. One "step" = one batch of --batch-pairs read pairs.
 
   value  reads/s with every timed batch already resident in HBM when the clock starts (BSB_RESIDENT_BENCH: all batches
          are parsed and uploaded first, then released to the device at once): reads / time until the last batch has
-         left the device, results copied back; two batches in flight per GPU, exactly as in the product run
+         left the device, results copied back; three batches in flight per GPU, exactly as in the product run
          (max over ranks)
   e2e    reads/s through the public API (bsb_mem_main: FASTQ files on the host -> SAM text to /dev/null),
          host parsing, H2D, kernels, D2H, SAM formatting all inside the timed region
@@ -378,7 +378,7 @@ def main():
             'dtype': 'int32', 'data': 'synthetic', 'config': config, 'clocks': clocks,
             'e2e': {'value': e2e, 'unit': 'reads/s', 'h2d_bytes_per_step': st['h2d_bytes'] // n_batches, 'd2h_bytes_per_step': st['d2h_bytes'] // n_batches,
                     'api': 'bsb_mem_main (FASTQ files on host -> SAM text to /dev/null)', 'wall_s': wall},
-            'gpu_launches': st['kernel_launches'] - launches0, 'batches_in_flight_per_gpu': 2,
+            'gpu_launches': st['kernel_launches'] - launches0, 'batches_in_flight_per_gpu': int(os.environ.get('BSB_GPU_SLOTS', '3')),
             'value_one_batch_in_flight': reads_all / (ms_one / 1000),
             'roofline': {'bound': 'hbm', 'kernel': 'k_seed3 (+ k_pack4, k_seed3_finish: SMEM seeding stage)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',

@@ -680,7 +680,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
-    int n_slots = std::min(2, aligner.slots());   // two batches in flight; a third (BSB_GPU_SLOTS=3) measured no better end to end
+    int n_slots = aligner.slots();   // three batches in flight: one slot's host round trips and copies are covered by the other two
     if (const char *e = getenv("BSB_GPU_SLOTS")) n_slots = std::max(1, std::min(aligner.slots(), atoi(e)));
     Channel<std::unique_ptr<Job>> q_plan(2), q_read((size_t)std::max(2, n_slots)), q_free(16);
     OrderedDone q_done;
