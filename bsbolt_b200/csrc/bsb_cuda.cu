@@ -55,12 +55,38 @@ __device__ __forceinline__ int owner_of(const uint32_t *off, int n, uint32_t g)
     return lo;
 }
 
+// K1: sixteen bases per thread (one 128-bit load, two 128-bit stores); the read that owns the first base is found once
+// and the walk steps into the next read(s) where the chunk crosses a boundary
 __global__ void k_convert(BatchDev B, uint32_t n_bases)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_bases) return;
-    int r = owner_of(B.seq_off, B.n, i);
-    stage_convert_base(B, r, i);
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16u;
+    if (i0 >= n_bases) return;
+    int r = owner_of(B.seq_off, B.n, i0);
+    uint32_t next = B.seq_off[r + 1];
+    int pat = B.pattern[r];
+    const uint32_t m = n_bases - i0 < 16u ? n_bases - i0 : 16u;
+    uint32_t in[4];
+    if (m == 16u) { const uint4 v = *reinterpret_cast<const uint4 *>(B.bases + i0); in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w; }
+    else { in[0] = in[1] = in[2] = in[3] = 0; for (uint32_t t = 0; t < m; ++t) in[t >> 2] |= (uint32_t)(uint8_t)B.bases[i0 + t] << ((t & 3) << 3); }
+    uint32_t so[4] = {0, 0, 0, 0}, oo[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (uint32_t t = 0; t < 16u; ++t) {
+        if (t < m) {
+            const uint32_t i = i0 + t;
+            while (i >= next) { ++r; next = B.seq_off[r + 1]; pat = B.pattern[r]; }
+            unsigned char c = (unsigned char)(in[t >> 2] >> ((t & 3) << 3));
+            oo[t >> 2] |= (uint32_t)nt4_code(c) << ((t & 3) << 3);
+            if (pat) { if (c == 'G') c = 'A'; }
+            else { if (c == 'C') c = 'T'; }
+            const uint8_t code = nt4_code(c);
+            so[t >> 2] |= (uint32_t)(code == 5 ? 4 : code) << ((t & 3) << 3);   // as stage_convert_base (bsb_stages.h)
+        }
+    }
+    if (m == 16u) {
+        *reinterpret_cast<uint4 *>(B.seq + i0) = make_uint4(so[0], so[1], so[2], so[3]);
+        *reinterpret_cast<uint4 *>(B.oseq + i0) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    } else
+        for (uint32_t t = 0; t < m; ++t) { B.seq[i0 + t] = (uint8_t)(so[t >> 2] >> ((t & 3) << 3)); B.oseq[i0 + t] = (uint8_t)(oo[t >> 2] >> ((t & 3) << 3)); }
 }
 
 __global__ void __launch_bounds__(64) k_seed(Opt opt, IndexView ix, BatchDev B, Intv *scratch)
@@ -903,7 +929,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     B.err = m.d_err.p;
 
     // ---- K1 ----
-    if (nb) { k_convert<<<cdiv(nb, 256), 256, 0, st>>>(B, (uint32_t)nb); ++m.launches; }
+    if (nb) { k_convert<<<cdiv(cdiv(nb, 16), 256), 256, 0, st>>>(B, (uint32_t)nb); ++m.launches; }
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[2], st));
 
