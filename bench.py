@@ -387,7 +387,7 @@ def main():
             'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info, 'per_rank': per_rank, 'host_cores': cores,
             'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
             'final_split_ms_per_step': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},
-            'stage_note': 'CUDA-event stage times of the run with ONE batch in flight (with two in flight the stages of different batches overlap)',
+            'stage_note': 'CUDA-event stage times of the run with ONE batch in flight (with several in flight the stages of different batches overlap)',
             'host_busy_s': {'read': st['sec_read'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_thread': st['sec_align']},
             'setup_s': {'simulate': t_sim, 'index_build_or_wait': t_index}, 'index_hbm_bytes': idx.hbm_bytes}
     print(json.dumps(line))
