@@ -1,0 +1,146 @@
+"""Edge cases of the alignment path, differential against a live run of the compiled reference (oracle/_ref/bwa travels to
+the GPU box): empty and ragged inputs, reads shorter than a seed, ambiguous and lower-case bases, FASTA and gzip input,
+and the options `bsbolt Align` can put on the `bwa mem` command line besides the defaults (-M -S -C -R -H -I -A ...).
+Bit-exact like the other parity tests: header (all but @PG) and every record."""
+import gzip
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import ROOT, first_diff, strip_pg
+
+pytestmark = pytest.mark.gpu
+BWA = os.path.join(ROOT, 'oracle', '_ref', 'bwa')
+COMP = str.maketrans('ACGTNacgtn', 'TGCANtgcan')
+
+
+@pytest.fixture(scope='module')
+def index(built, golden):
+    from bsbolt_b200 import _native
+    if not os.path.exists(BWA):
+        pytest.skip('oracle/_ref/bwa did not travel to this box')
+    ix = _native.Index(golden.idxbase, 0)
+    yield ix
+    ix.close()
+
+
+def genome(golden):
+    seqs, name = {}, None
+    for line in open(os.path.join(golden.dir, 'genome.fa')):
+        if line.startswith('>'):
+            name = line[1:].split()[0]; seqs[name] = []
+        else:
+            seqs[name].append(line.strip())
+    return {k: ''.join(v) for k, v in seqs.items()}
+
+
+def bisulfite(s, rnd, rate=0.9):
+    return ''.join('T' if c == 'C' and rnd.random() < rate else c for c in s)
+
+
+def ragged_reads(golden, seed, paired):
+    """reads of awkward lengths and contents; mates 350 bp apart where paired"""
+    rnd = random.Random(seed)
+    g = genome(golden)
+    names = sorted(g)
+    r1, r2 = [], []
+    lens = [1, 2, 5, 18, 19, 20, 21, 30, 31, 32, 33, 47, 48, 49, 64, 65, 99, 100, 149, 150, 151, 200, 250, 16, 17, 255, 256]
+    for k, L in enumerate(lens * 3):
+        c = names[k % len(names)]
+        L2 = lens[(k * 7 + 3) % len(lens)]
+        p = rnd.randrange(0, len(g[c]) - 700)
+        a = g[c][p:p + L]
+        b = g[c][p + 350:p + 350 + L2][::-1].translate(COMP) if True else ''
+        b = g[c][max(0, p + 350 - L2):p + 350][::-1].translate(COMP)
+        if k % 4 == 1:                      # crick-strand pair
+            a, b = b, a
+        a, b = bisulfite(a, rnd), b.replace('G', 'A') if k % 3 else b
+        kind = k % 11
+        if kind == 3: a = 'N' * len(a)
+        if kind == 4 and len(a) > 20: a = a[:len(a) // 2] + 'NNNN' + a[len(a) // 2 + 4:]
+        if kind == 5: a = a.lower()
+        if kind == 6: a = 'A' * len(a)
+        if kind == 7 and len(a) > 10: a = a[:5] + a[5:10].lower() + a[10:]
+        if kind == 8 and len(a) > 40:      # a few substitutions and a 2-base deletion
+            a = list(a)
+            for _ in range(3): a[rnd.randrange(len(a))] = rnd.choice('ACGT')
+            a = ''.join(a); a = a[:len(a) // 3] + a[len(a) // 3 + 2:]
+        q = lambda s: ''.join(chr(33 + rnd.randrange(2, 41)) for _ in s)
+        r1.append((f'e{k}', a, q(a)))
+        r2.append((f'e{k}', b, q(b)))
+    return (r1, r2) if paired else (r1, None)
+
+
+def write_fq(path, recs, fasta=False, comment=None, gz=False, suffix=''):
+    op = gzip.open if gz else open
+    with op(path, 'wt') as f:
+        for n, s, q in recs:
+            head = n + suffix + (' ' + comment if comment else '')
+            f.write(f'>{head}\n{s}\n' if fasta else f'@{head}\n{s}\n+\n{q}\n')
+    return str(path)
+
+
+def both(index, golden, extra, fqs, tmp_path, tag):
+    from bsbolt_b200 import _native
+    argv = ['mem'] + golden.manifest['launcher_args'] + extra + [golden.idxbase] + fqs
+    ref = subprocess.run([BWA] + argv, capture_output=True, text=True)
+    assert ref.returncode == 0, ref.stderr[-1500:]
+    out, log = tmp_path / f'{tag}.sam', tmp_path / f'{tag}.log'
+    with open(out, 'w') as fo, open(log, 'w') as fl:
+        rc, _ = _native.mem_main(argv, index=index, out_fd=fo.fileno(), log_fd=fl.fileno())
+    assert rc == 0, _native.last_error()
+    a, b = strip_pg(ref.stdout), strip_pg(open(out).read())
+    assert a == b, f'{tag} {extra}: ' + first_diff(a, b)
+    bs = lambda text: sorted(l for l in text.split('\n') if l.startswith('BSStat '))
+    assert bs(ref.stderr) == bs(open(log).read()), f'{tag}: BSStat lines differ'
+    return a
+
+
+def test_ragged_single_end(index, golden, tmp_path):
+    r1, _ = ragged_reads(golden, 5, False)
+    fq = write_fq(tmp_path / 'r.fq', r1)
+    for k, extra in enumerate((['-K', '3000'], ['-z', '-K', '100000'], ['-z', '-e', '0', '-K', '2500'], ['-L', '2,2', '-T', '0', '-K', '100000'])):
+        sam = both(index, golden, extra, [fq], tmp_path, f'se{k}')
+    assert sum(1 for l in sam.split('\n') if l and not l.startswith('@')) >= len(r1)
+
+
+def test_ragged_paired_end(index, golden, tmp_path):
+    r1, r2 = ragged_reads(golden, 6, True)
+    fqs = [write_fq(tmp_path / 'r1.fq', r1, suffix='/1'), write_fq(tmp_path / 'r2.fq', r2, suffix='/2')]
+    for k, extra in enumerate((['-K', '4000'], ['-z', '-K', '100000'], ['-S', '-K', '100000'], ['-I', '350,40', '-K', '5000'], ['-U', '3', '-K', '100000'])):
+        both(index, golden, extra, fqs, tmp_path, f'pe{k}')
+
+
+def test_empty_and_tiny_inputs(index, golden, tmp_path):
+    empty = tmp_path / 'empty.fq'
+    empty.write_text('')
+    both(index, golden, ['-K', '1000'], [str(empty)], tmp_path, 'empty_se')
+    both(index, golden, ['-K', '1000'], [str(empty), str(empty)], tmp_path, 'empty_pe')
+    g = genome(golden)
+    one = [('only', g['chr1'][1000:1100], 'I' * 100)]
+    both(index, golden, [], [write_fq(tmp_path / 'one.fq', one)], tmp_path, 'one')
+    mate = [('only', g['chr1'][1300:1400][::-1].translate(COMP), 'I' * 100)]
+    both(index, golden, [], [write_fq(tmp_path / 'o1.fq', one), write_fq(tmp_path / 'o2.fq', mate)], tmp_path, 'one_pair')
+
+
+def test_input_formats(index, golden, tmp_path):
+    r1, r2 = ragged_reads(golden, 7, True)
+    base = both(index, golden, ['-K', '100000'], [write_fq(tmp_path / 'a1.fq', r1), write_fq(tmp_path / 'a2.fq', r2)], tmp_path, 'plain')
+    gz = both(index, golden, ['-K', '100000'], [write_fq(tmp_path / 'g1.fq.gz', r1, gz=True), write_fq(tmp_path / 'g2.fq.gz', r2, gz=True)], tmp_path, 'gz')
+    assert gz == base
+    both(index, golden, ['-K', '100000'], [write_fq(tmp_path / 'f1.fa', r1, fasta=True), write_fq(tmp_path / 'f2.fa', r2, fasta=True)], tmp_path, 'fasta')
+
+
+def test_launcher_options(index, golden, tmp_path):
+    """every option bsbolt/Utils/Launcher.py:77-98 can add to the command line, away from its default"""
+    r1, r2 = ragged_reads(golden, 8, True)
+    fqs = [write_fq(tmp_path / 'c1.fq', r1, comment='BC:Z:ACGT'), write_fq(tmp_path / 'c2.fq', r2, comment='BC:Z:ACGT')]
+    hdr = tmp_path / 'hdr.txt'
+    hdr.write_text('@CO\tfirst extra line\n@CO\tsecond extra line\n')
+    for k, extra in enumerate((['-M'], ['-C'], ['-R', r'@RG\tID:grp1\tSM:sample'], ['-H', '@CO\textra header line'], ['-H', str(hdr)],
+                               ['-A', '2'], ['-A', '2', '-B', '6', '-O', '7,5', '-E', '2,1', '-L', '10,12'], ['-T', '40', '-h', '3,50'],
+                               ['-k', '12', '-r', '1.0', '-c', '30', '-D', '0.3', '-m', '10', '-W', '5', '-y', '5'],
+                               ['-d', '30', '-w', '20', '-Z', '0.5', '-z', '-l', '0.3', '-n', '2'])):
+        both(index, golden, extra + ['-K', '50000'], fqs, tmp_path, f'opt{k}')
