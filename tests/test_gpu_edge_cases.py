@@ -125,6 +125,27 @@ def test_empty_and_tiny_inputs(index, golden, tmp_path):
     both(index, golden, [], [write_fq(tmp_path / 'o1.fq', one), write_fq(tmp_path / 'o2.fq', mate)], tmp_path, 'one_pair')
 
 
+def test_zero_length_reads(index, golden, tmp_path):
+    g = genome(golden)
+    recs = [('z0', '', ''), ('ok', g['chr2'][500:600], 'I' * 100), ('z1', '', ''), ('z2', '', '')]
+    mates = [('z0', g['chr2'][800:900][::-1].translate(COMP), 'I' * 100), ('ok', '', ''), ('z1', '', ''), ('z2', 'ACGT', 'IIII')]
+    fq1, fq2 = write_fq(tmp_path / 'z1.fq', recs), write_fq(tmp_path / 'z2.fq', mates)
+    both(index, golden, [], [fq1], tmp_path, 'zero_se')
+    both(index, golden, ['-z'], [fq1], tmp_path, 'zero_se_un')
+    both(index, golden, [], [fq1, fq2], tmp_path, 'zero_pe')
+
+
+def test_reads_beyond_the_supported_length_fail_loudly(index, golden, tmp_path):
+    """mem_seed_sw (bwamem.c:575-619, reads of roughly 700 bp and more) is not implemented: refuse, never differ silently"""
+    from bsbolt_b200 import _native
+    g = genome(golden)
+    fq = write_fq(tmp_path / 'long.fq', [('long', g['chr1'][100:1000], 'I' * 900)])
+    argv = ['mem'] + golden.manifest['launcher_args'] + [golden.idxbase, fq]
+    with open(tmp_path / 'o.sam', 'w') as fo, open(tmp_path / 'o.log', 'w') as fl:
+        rc, _ = _native.mem_main(argv, index=index, out_fd=fo.fileno(), log_fd=fl.fileno())
+    assert rc != 0 and '700' in _native.last_error()
+
+
 def test_input_formats(index, golden, tmp_path):
     r1, r2 = ragged_reads(golden, 7, True)
     base = both(index, golden, ['-K', '100000'], [write_fq(tmp_path / 'a1.fq', r1), write_fq(tmp_path / 'a2.fq', r2)], tmp_path, 'plain')
