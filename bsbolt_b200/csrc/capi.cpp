@@ -118,7 +118,9 @@ static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, in
             if (out) setvbuf(out, nullptr, _IOFBF, 1 << 22);
         }
         if ((!out && !bam) || !log) throw std::runtime_error("[E::bsb_mem_main] cannot open the output streams");
-        if (ma.ignore_alt) throw std::runtime_error("[E::bsb_mem_main] -j needs an index loaded without ALT marks; not supported with a resident index");
+        // -j (fastmap.c: bns->anns[i].is_alt = 0 for every contig): a no-op unless the database carries an .alt file
+        if (ma.ignore_alt && idx->host.any_alt)
+            throw std::runtime_error("[E::bsb_mem_main] -j on a database with ALT contigs needs an index loaded without the ALT marks; not supported with a resident index");
         idx->aligner->verbose = ma.verbose;
         RunSummary sum;
         ret = run_mem(ma, idx->host, *idx->aligner, out, log, &sum, bam.get());

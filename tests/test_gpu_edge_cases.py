@@ -160,7 +160,7 @@ def test_launcher_options(index, golden, tmp_path):
     fqs = [write_fq(tmp_path / 'c1.fq', r1, comment='BC:Z:ACGT'), write_fq(tmp_path / 'c2.fq', r2, comment='BC:Z:ACGT')]
     hdr = tmp_path / 'hdr.txt'
     hdr.write_text('@CO\tfirst extra line\n@CO\tsecond extra line\n')
-    for k, extra in enumerate((['-M'], ['-C'], ['-R', r'@RG\tID:grp1\tSM:sample'], ['-H', '@CO\textra header line'], ['-H', str(hdr)],
+    for k, extra in enumerate((['-M'], ['-j'], ['-C'], ['-R', r'@RG\tID:grp1\tSM:sample'], ['-H', '@CO\textra header line'], ['-H', str(hdr)],
                                ['-A', '2'], ['-A', '2', '-B', '6', '-O', '7,5', '-E', '2,1', '-L', '10,12'], ['-T', '40', '-h', '3,50'],
                                ['-k', '12', '-r', '1.0', '-c', '30', '-D', '0.3', '-m', '10', '-W', '5', '-y', '5'],
                                ['-d', '30', '-w', '20', '-Z', '0.5', '-z', '-l', '0.3', '-n', '2'])):
