@@ -582,9 +582,10 @@ __global__ void __launch_bounds__(128) k_sam_write(SamView v, int n, int is_pe, 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SamWrite o = {text + off[i]};
+    SamWriteDev o = {text + off[i], 0, 0};
     SamStats st;
     sam_entry(o, v, i, is_pe != 0, st);
+    o.finish();
 }
 
 // Index-load time: expands the reference's SA sample (every sa_intv-th rank) into the full suffix array in

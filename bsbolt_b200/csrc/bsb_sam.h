@@ -71,7 +71,94 @@ struct SamWrite {
     BSB_HD void pa(double) {}   // "\tpa:f:%.3f" (ALT contigs) is only produced by the host sink
 };
 
+#if defined(__CUDACC__)
+// Device sink of k_sam_write. A thread's record is several hundred bytes; written and read a byte at a time every byte is
+// its own L1 transaction (ncu: the byte-wise kernel ran at 84 % of the L1 throughput peak with 10 % of the issue slots busy).
+// Here output bytes are collected in a 64-bit register and leave as aligned 8-byte stores (the first bytes up to the next
+// 8-byte boundary and the last few go out singly: the words they share belong to the neighbouring records), and the bulk
+// sources (qualities, read bases, MD/XB strings, names) are read with aligned 8-byte loads.
+struct SamWriteDev {
+    char *p; uint64_t acc; int fill;     // fill bytes of acc wait for the aligned word at p
+    __device__ __forceinline__ void ch(char c)
+    {
+        if (fill == 0 && (reinterpret_cast<uintptr_t>(p) & 7)) { *p++ = c; return; }
+        acc |= (uint64_t)(uint8_t)c << (fill << 3);
+        if (++fill == 8) { *reinterpret_cast<uint64_t *>(p) = acc; p += 8; acc = 0; fill = 0; }
+    }
+    __device__ __forceinline__ void put8(uint64_t w)      // eight bytes, first byte in the low bits
+    {
+        if (fill == 0 && (reinterpret_cast<uintptr_t>(p) & 7)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ch((char)(w >> (k << 3)));
+            return;
+        }
+        const int sh = fill << 3;
+        *reinterpret_cast<uint64_t *>(p) = fill ? (acc | w << sh) : w;
+        p += 8;
+        acc = fill ? w >> (64 - sh) : 0;
+    }
+    __device__ __forceinline__ void mem(const char *s, size_t l)
+    {
+        size_t i = 0;
+        while (i < l && (reinterpret_cast<uintptr_t>(s + i) & 7)) ch(s[i++]);
+        for (; i + 8 <= l; i += 8) put8(*reinterpret_cast<const uint64_t *>(s + i));
+        for (; i < l; ++i) ch(s[i]);
+    }
+    __device__ __forceinline__ void num(long v)
+    {
+        char buf[24]; int l = 0; unsigned long x = v < 0 ? (unsigned long)(-v) : (unsigned long)v;
+        do { buf[l++] = (char)('0' + x % 10); x /= 10; } while (x);
+        if (v < 0) buf[l++] = '-';
+        while (l) ch(buf[--l]);
+    }
+    __device__ __forceinline__ void pa(double) {}
+    __device__ __forceinline__ void finish() { for (int k = 0; k < fill; ++k) p[k] = (char)(acc >> (k << 3)); p += fill; fill = 0; acc = 0; }
+};
+#endif
+
 template <class S> BSB_HD void sam_lit(S &o, const char *s) { size_t l = 0; while (s[l]) ++l; o.mem(s, l); }
+
+// SEQ and QUAL columns (bwamem.c:936-966). tab: "ACGTN" for the forward strand, "TGCAN" for the reverse complement.
+template <class S> BSB_HD void sam_bases_fwd(S &o, const char *bases, int qb, int qe) { for (int i = qb; i < qe; ++i) o.ch("ACGTN"[sam_nt4((unsigned char)bases[i])]); }
+template <class S> BSB_HD void sam_bases_rc(S &o, const char *bases, int qb, int qe) { for (int i = qe - 1; i >= qb; --i) o.ch("TGCAN"[sam_nt4((unsigned char)bases[i])]); }
+template <class S> BSB_HD void sam_qual_rev(S &o, const char *qual, int qb, int qe) { for (int i = qe - 1; i >= qb; --i) o.ch(qual[i]); }
+#if defined(__CUDACC__)
+// the same columns with aligned 8-byte loads of the source
+__device__ __forceinline__ void sam_bases_fwd(SamWriteDev &o, const char *bases, int qb, int qe)
+{
+    int i = qb;
+    while (i < qe && (reinterpret_cast<uintptr_t>(bases + i) & 7)) { o.ch("ACGTN"[sam_nt4((unsigned char)bases[i])]); ++i; }
+    for (; i + 8 <= qe; i += 8) {
+        const uint64_t w = *reinterpret_cast<const uint64_t *>(bases + i);
+        uint64_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r |= (uint64_t)(uint8_t)"ACGTN"[sam_nt4((unsigned char)(w >> (k << 3)))] << (k << 3);
+        o.put8(r);
+    }
+    for (; i < qe; ++i) o.ch("ACGTN"[sam_nt4((unsigned char)bases[i])]);
+}
+__device__ __forceinline__ void sam_bases_rc(SamWriteDev &o, const char *bases, int qb, int qe)
+{
+    int i = qe;                                            // bases[qb, i) are still to be written, last one first
+    while (i > qb && (reinterpret_cast<uintptr_t>(bases + i) & 7)) { --i; o.ch("TGCAN"[sam_nt4((unsigned char)bases[i])]); }
+    for (; i - 8 >= qb; i -= 8) {
+        const uint64_t w = *reinterpret_cast<const uint64_t *>(bases + i - 8);
+        uint64_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r |= (uint64_t)(uint8_t)"TGCAN"[sam_nt4((unsigned char)(w >> ((7 - k) << 3)))] << (k << 3);
+        o.put8(r);
+    }
+    while (i > qb) { --i; o.ch("TGCAN"[sam_nt4((unsigned char)bases[i])]); }
+}
+__device__ __forceinline__ void sam_qual_rev(SamWriteDev &o, const char *qual, int qb, int qe)
+{
+    int i = qe;
+    while (i > qb && (reinterpret_cast<uintptr_t>(qual + i) & 7)) { --i; o.ch(qual[i]); }
+    for (; i - 8 >= qb; i -= 8) o.put8(__byte_perm((uint32_t)(*reinterpret_cast<const uint64_t *>(qual + i - 8) >> 32), 0, 0x0123)
+                                      | (uint64_t)__byte_perm((uint32_t)*reinterpret_cast<const uint64_t *>(qual + i - 8), 0, 0x0123) << 32);
+    while (i > qb) { --i; o.ch(qual[i]); }
+}
+#endif
 
 template <class S>
 BSB_HD void sam_cigar(S &o, int n, const uint32_t *cig, const char *ops, int clip_as)
@@ -210,14 +297,14 @@ BSB_HD void sam_record(S &o, const SamView &v, int ei, const AlnOut *list, int n
             }
         }
         if (!reverse) {
-            for (int i = qb; i < qe; ++i) o.ch("ACGTN"[sam_nt4((unsigned char)bases[i])]);   // '-' (code 5) prints the NUL, like the reference
+            sam_bases_fwd(o, bases, qb, qe);   // '-' (code 5) prints the NUL, like the reference
             o.ch('\t');
             if (has_qual) o.mem(qual + qb, (size_t)(qe > qb ? qe - qb : 0));
             else o.ch('*');
         } else {
-            for (int i = qe - 1; i >= qb; --i) o.ch("TGCAN"[sam_nt4((unsigned char)bases[i])]);
+            sam_bases_rc(o, bases, qb, qe);
             o.ch('\t');
-            if (has_qual) for (int i = qe - 1; i >= qb; --i) o.ch(qual[i]);
+            if (has_qual) sam_qual_rev(o, qual, qb, qe);
             else o.ch('*');
         }
     }
