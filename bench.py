@@ -329,6 +329,9 @@ def main():
         c = torch.tensor([n_reads_timed], device=f'cuda:{device}', dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         reads_all = float(c[0])
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         cleanup()
         return 0
