@@ -378,11 +378,27 @@ __global__ void __launch_bounds__(128) k_seed3_finish(Opt opt, BatchDev B, const
     if (lane == 0) { B.n_intv[r] = n; B.l_rep[r] = l_rep; B.n_seed[r] = cnt; }
 }
 
+// K3, one thread per seed. The read that owns the block's first seed is found once per block; the seeds of a block span a
+// handful of reads, so every thread finishes its own search inside a short window of seed_off kept in shared memory (and
+// falls back to the full search beyond it).
 __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, uint32_t n_seeds)
 {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int WIN = 64;
+    __shared__ uint32_t s_off[WIN + 1];
+    __shared__ int s_r0;
+    const uint32_t g0 = blockIdx.x * blockDim.x, g = g0 + threadIdx.x;
+    if (threadIdx.x == 0) s_r0 = owner_of(B.seed_off, B.n, g0);
+    __syncthreads();
+    const int r0 = s_r0;
+    if (threadIdx.x <= WIN) s_off[threadIdx.x] = r0 + (int)threadIdx.x <= B.n ? B.seed_off[r0 + threadIdx.x] : 0xffffffffu;
+    __syncthreads();
     if (g >= n_seeds) return;
-    int r = owner_of(B.seed_off, B.n, g);
+    int r;
+    if (s_off[WIN] > g) {            // largest k with s_off[k] <= g (s_off[0] <= g0 <= g)
+        int lo = 0, hi = WIN;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= g) lo = mid; else hi = mid; }
+        r = r0 + lo;
+    } else r = owner_of(B.seed_off, B.n, g);
     stage_sa(opt, ix, B, r, g);
 }
 

@@ -127,9 +127,12 @@ BSB_HD void stage_sa(const Opt &opt, const IndexView &ix, const BatchDev &B, int
     int n = B.n_intv[r];
     for (int i = 0; i < n; ++i) {
         const Intv &p = mem[i];
-        int64_t step = p.x2 > (uint64_t)opt.max_occ ? (int64_t)(p.x2 / opt.max_occ) : 1;
-        int64_t cnt = ((int64_t)p.x2 + step - 1) / step;
-        if (cnt > opt.max_occ) cnt = opt.max_occ;
+        int64_t step = 1, cnt = (int64_t)p.x2;      // bwamem.c:282-283; the 64-bit divisions only for repetitive intervals
+        if (p.x2 > (uint64_t)opt.max_occ) {
+            step = (int64_t)(p.x2 / opt.max_occ);
+            cnt = ((int64_t)p.x2 + step - 1) / step;
+            if (cnt > opt.max_occ) cnt = opt.max_occ;
+        }
         if (j < (uint32_t)cnt) {
             Seed s;
             int slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
