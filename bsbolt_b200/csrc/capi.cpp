@@ -88,7 +88,7 @@ static int host_thread_share()
     int n = (int)std::thread::hardware_concurrency();
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) n /= std::max(1, atoi(e));
     if (const char *e = getenv("BSB_HOST_THREADS")) n = atoi(e);
-    return std::max(1, std::min(n - 4, 64));
+    return std::max(1, std::min(n - 2, 64));   // the device threads sleep on events; leave two cores to the FASTQ reader
 }
 
 static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, const char *bam_path, int bam_threads, int bam_level,
