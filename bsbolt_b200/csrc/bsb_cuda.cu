@@ -429,13 +429,14 @@ __device__ __forceinline__ unsigned warp_next_group(int *ctr, unsigned cur, unsi
     return __shfl_sync(0xffffffffu, r, 0);
 }
 
-// K4, one warp per read (bsb_warp.cuh)
-__global__ void __launch_bounds__(128) k_chain_warp(Opt opt, IndexView ix, BatchDev B, int *ctr)
+// K4 (bsb_warp.cuh): a warp takes a group of 32 consecutive reads through the three phases
+__global__ void __launch_bounds__(128, 6) k_chain_warp(Opt opt, IndexView ix, BatchDev B, int *ctr, int32_t *aux)
 {
     __shared__ ChainSmem sm[4];
     const int wib = threadIdx.x >> 5;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp_next_read(ctr, gw - nw, nw); r < B.n; r = warp_next_read(ctr, r, nw)) stage_chain_warp(opt, ix, B, r, sm[wib]);
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned base = warp_next_group(ctr, gw * 32 - nw * 32, nw * 32); base < (unsigned)B.n; base = warp_next_group(ctr, base, nw * 32))
+        stage_chain_group(opt, ix, B, (int)base, sm[wib], aux);
 }
 
 
@@ -727,7 +728,7 @@ struct BatchCtx {
     DevBuf<int32_t> d_n_intv, d_l_rep, d_n_seed, d_n_chain, d_n_regs, d_err, d_misc;
     DevBuf<uint32_t> d_seed_off;
     DevBuf<uint8_t> d_cub;
-    DevBuf<Seed> d_seeds, d_cseeds; DevBuf<int32_t> d_next, d_tmp; DevBuf<Chain> d_pool, d_chains;
+    DevBuf<Seed> d_seeds, d_cseeds; DevBuf<int32_t> d_next, d_tmp, d_chain_aux; DevBuf<Chain> d_pool, d_chains;
     DevBuf<uint64_t> d_srt; DevBuf<AlnReg> d_regs; DevBuf<BtNode> d_nodes;
     DevBuf<int32_t> d_eh;
     DevBuf<int8_t> d_pe_dir; DevBuf<int64_t> d_pe_isize;
@@ -1035,7 +1036,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const bool dyn_sched = getenv("BSB_STATIC_SCHED") == nullptr;
     CK(cudaMemsetAsync(m.d_misc.p + 16, 0, 2 * 4, st));        // read counters of the chaining and the extension kernel
     if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, nullptr);
-    else k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr);
+    else { m.d_chain_aux.ensure(S + 1); k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr, m.d_chain_aux.p); }
     ++m.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[5], st));

@@ -228,9 +228,18 @@ __device__ __forceinline__ void lane_chain_emit(const BatchDev &B, uint32_t so, 
     B.chains[so + out_idx] = out;
 }
 
-// returns false when the read has to be redone by the serial form
-__device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainRec *rec, ChainRec *rec2, int32_t *cs_off,
-                                uint64_t *keys, Seed *stage)
+// K4 in three phases over a GROUP of 32 consecutive reads, so that the inherently serial parts run on 32 lanes at once
+// instead of on lane 0 of a warp that waits:
+//   phase 1 (warp per read, one read after the other): the seed loop above; every chain leaves a preliminary record in
+//            chain_pool[so + rank] (rank = order of the first positions = in-order traversal of the reference's tree),
+//            its query span in tmp[] and a (weight, rank) sort key in srt[];
+//   phase 2 (lane per read): the order-exact introsort of the keys and mem_chain_flt over the records, through the
+//            permutation held in the low halves of the keys; the surviving ranks are left in srt[0 .. n_out). Reads the
+//            warp form cannot take (duplicate tree key, more than CHAIN_MAX chains) run the serial form on their lane here;
+//   phase 3 (warp per read): offsets of the surviving chains in cseeds by a warp scan, every chain written out by one lane.
+
+// phase 1: returns the number of chains that entered the sort (>= 0) or -1 when the read needs the serial form
+__device__ int chain_phase1_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, Seed *stage)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t so = B.seed_off[r];
@@ -263,7 +272,7 @@ __device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const Batch
             else if (c1.valid && c1.pos == best) merged = lane_chain_merge(opt, l_pac, c1, s, si, next);
         }
         if (__any_sync(FULLMASK, merged)) continue;
-        if (best == s.rbeg || n_chains >= CHAIN_MAX) return false;     // duplicate key / too many chains: serial form
+        if (best == s.rbeg || n_chains >= CHAIN_MAX) return -1;        // duplicate key / too many chains: serial form
         const int ci = n_chains++;
         if (lane == (ci & 31)) {
             if (ci < 32) lane_chain_start(ix, c0, s, si, next);
@@ -283,97 +292,141 @@ __device__ bool chain_read_warp(const Opt &opt, const IndexView &ix, const Batch
         ++n_kept;
         rank0 += p < c0.pos; rank1 += p < c1.pos;
     }
-    if (keep0) { ChainRec t; t.w = w0; t.ci = lane; t.beg = c0.f_qbeg; t.end = c0.l_qbeg + c0.l_len; t.first = -1; t.kept = 0; t.is_alt = c0.is_alt; t.pad_ = 0; rec[rank0] = t; }
-    if (keep1) { ChainRec t; t.w = w1; t.ci = lane + 32; t.beg = c1.f_qbeg; t.end = c1.l_qbeg + c1.l_len; t.first = -1; t.kept = 0; t.is_alt = c1.is_alt; t.pad_ = 0; rec[rank1] = t; }
-    __syncwarp();
-    // mem_chain_flt on lane 0
-    int n_out = 0;
-    // the reference sorts the chain records themselves; the permutation depends only on the weights, so 8-byte
-    // (weight, rank) keys are sorted with the same algorithm and the records are moved once, by all lanes
-    for (int t = lane; t < n_kept; t += 32) keys[t] = (uint64_t)(uint32_t)rec[t].w << 32 | (uint32_t)t;
-    __syncwarp();
-    if (lane == 0 && n_kept > 0) introsort((long)n_kept, keys, LtKeyHiDesc());
-    __syncwarp();
-    for (int t = lane; t < n_kept; t += 32) rec2[t] = rec[(uint32_t)keys[t]];
-    __syncwarp();
-    if (lane == 0 && n_kept > 0) {
-        ChainRec *a = rec2;
-        int n_chn = n_kept, i, k;
-        int32_t *keptl = cs_off;     // scratch until the offsets are computed below
-        int nk = 0;
-        a[0].kept = 3;
-        keptl[nk++] = 0;
-        for (i = 1; i < n_chn; ++i) {
-            int large_ovlp = 0;
-            for (k = 0; k < nk; ++k) {
-                const int j = keptl[k];
-                const int b_max = a[j].beg > a[i].beg ? a[j].beg : a[i].beg;
-                const int e_min = a[j].end < a[i].end ? a[j].end : a[i].end;
-                if (e_min > b_max && (!a[j].is_alt || a[i].is_alt)) {
-                    const int li = a[i].end - a[i].beg, lj = a[j].end - a[j].beg;
-                    const int min_l = li < lj ? li : lj;
-                    if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
-                        large_ovlp = 1;
-                        if (a[j].first < 0) a[j].first = i;
-                        if (a[i].w < a[j].w * opt.drop_ratio && a[j].w - a[i].w >= opt.min_seed_len << 1) break;
-                    }
-                }
-            }
-            if (k == nk) {
-                keptl[nk++] = i;
-                a[i].kept = large_ovlp ? 2 : 3;
-            }
-        }
-        for (i = 0; i < nk; ++i) {
-            ChainRec &t = a[keptl[i]];
-            if (t.first >= 0) a[t.first].kept = 1;
-        }
-        for (i = k = 0; i < n_chn; ++i) {
-            if (a[i].kept == 0 || a[i].kept == 3) continue;
-            if (++k >= opt.max_chain_extend) break;
-        }
-        for (; i < n_chn; ++i)
-            if (a[i].kept < 3) a[i].kept = 0;
-        for (i = k = 0; i < n_chn; ++i)
-            if (a[i].kept != 0) a[k++] = a[i];
-        n_out = k;
+    Chain *pre = B.chain_pool + so;
+    if (keep0) {
+        Chain t; t.pos = c0.pos; t.n = c0.n; t.head = c0.head; t.tail = c0.tail; t.rid = c0.rid; t.first = -1; t.w = w0; t.kept = 0; t.is_alt = c0.is_alt; t.frac_rep = 0.f;
+        pre[rank0] = t;
+        B.tmp[so + rank0] = c0.f_qbeg | (c0.l_qbeg + c0.l_len) << 16;
+        B.srt[so + rank0] = (uint64_t)(uint32_t)w0 << 32 | (uint32_t)rank0;
     }
-    n_out = __shfl_sync(FULLMASK, n_out, 0);
-    __syncwarp();
-    // seed offsets of the surviving chains inside cseeds: exclusive sum of their seed counts, in output order
-    int run = 0;
-    for (int k = 0; k < n_out; ++k) {
-        const int ci = rec2[k].ci;
-        int n = ci < 32 ? c0.n : c1.n;
-        n = __shfl_sync(FULLMASK, n, ci & 31);
-        if (lane == 0) cs_off[k] = run;
-        run += n;
+    if (keep1) {
+        Chain t; t.pos = c1.pos; t.n = c1.n; t.head = c1.head; t.tail = c1.tail; t.rid = c1.rid; t.first = -1; t.w = w1; t.kept = 0; t.is_alt = c1.is_alt; t.frac_rep = 0.f;
+        pre[rank1] = t;
+        B.tmp[so + rank1] = c1.f_qbeg | (c1.l_qbeg + c1.l_len) << 16;
+        B.srt[so + rank1] = (uint64_t)(uint32_t)w1 << 32 | (uint32_t)rank1;
     }
     __syncwarp();
-    // every surviving chain is written out by the lane that owns it: record + its seeds in list order
-    const float frac_rep = (float)B.l_rep[r] / (float)(int)(B.seq_off[r + 1] - B.seq_off[r]);
-    for (int k = 0; k < n_out; ++k) {
-        const ChainRec t = rec2[k];
-        if (lane != (t.ci & 31)) continue;
-        if (t.ci < 32) lane_chain_emit(B, so, seeds, next, c0, t, cs_off[k], k, frac_rep);
-        else lane_chain_emit(B, so, seeds, next, c1, t, cs_off[k], k, frac_rep);
-    }
-    if (lane == 0) B.n_chain[r] = n_out;
-    __syncwarp();
-    return true;
+    return n_kept;
 }
 
-struct ChainSmem { ChainRec rec[CHAIN_MAX], rec2[CHAIN_MAX]; uint64_t keys[CHAIN_MAX]; int32_t off[CHAIN_MAX]; Seed stage[CHAIN_STAGE]; };
+// phase 2, one lane per read: introsort by weight + mem_chain_flt (bwamem.c:331-389). a[i] of the reference is
+// pre[(uint32_t)keys[i]]; keptl = this read's slice of `aux`. Returns the number of chains that survive.
+__device__ int chain_phase2_lane(const Opt &opt, const BatchDev &B, int r, int n_chn, int32_t *aux)
+{
+    const uint32_t so = B.seed_off[r];
+    uint64_t *keys = B.srt + so;
+    Chain *pre = B.chain_pool + so;
+    const int32_t *span = B.tmp + so;
+    int32_t *keptl = aux + so;
+    if (n_chn <= 0) return 0;
+    introsort((long)n_chn, keys, LtKeyHiDesc());
+#define BSB_A(i) pre[(uint32_t)keys[i]]
+    int nk = 0, i, k;
+    BSB_A(0).kept = 3;
+    keptl[nk++] = 0;
+    for (i = 1; i < n_chn; ++i) {
+        int large_ovlp = 0;
+        const uint32_t pi = (uint32_t)keys[i];
+        const int beg_i = span[pi] & 0xffff, end_i = span[pi] >> 16, w_i = pre[pi].w, alt_i = pre[pi].is_alt;
+        for (k = 0; k < nk; ++k) {
+            const int j = keptl[k];
+            const uint32_t pj = (uint32_t)keys[j];
+            const int beg_j = span[pj] & 0xffff, end_j = span[pj] >> 16;
+            const int b_max = beg_j > beg_i ? beg_j : beg_i;
+            const int e_min = end_j < end_i ? end_j : end_i;
+            if (e_min > b_max && (!pre[pj].is_alt || alt_i)) {
+                const int li = end_i - beg_i, lj = end_j - beg_j;
+                const int min_l = li < lj ? li : lj;
+                if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+                    large_ovlp = 1;
+                    if (pre[pj].first < 0) pre[pj].first = i;
+                    const int w_j = pre[pj].w;
+                    if (w_i < w_j * opt.drop_ratio && w_j - w_i >= opt.min_seed_len << 1) break;
+                }
+            }
+        }
+        if (k == nk) {
+            keptl[nk++] = i;
+            pre[pi].kept = large_ovlp ? 2 : 3;
+        }
+    }
+    for (i = 0; i < nk; ++i) {
+        const Chain &t = BSB_A(keptl[i]);
+        if (t.first >= 0) BSB_A(t.first).kept = 1;
+    }
+    for (i = k = 0; i < n_chn; ++i) {
+        if (BSB_A(i).kept == 0 || BSB_A(i).kept == 3) continue;
+        if (++k >= opt.max_chain_extend) break;
+    }
+    for (; i < n_chn; ++i)
+        if (BSB_A(i).kept < 3) BSB_A(i).kept = 0;
+    for (i = k = 0; i < n_chn; ++i)
+        if (BSB_A(i).kept != 0) keys[k++] = (uint32_t)keys[i];       // k <= i: the surviving ranks, in sorted order
+#undef BSB_A
+    return k;
+}
 
-__device__ void stage_chain_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, ChainSmem &S)
+// phase 3: the surviving chains of read r (ranks in srt[0 .. n_out)) go to chains[] / cseeds[], one chain per lane
+__device__ void chain_phase3_warp(const BatchDev &B, int r, int n_out)
 {
     const int lane = threadIdx.x & 31;
-    const int ns = (int)(B.seed_off[r + 1] - B.seed_off[r]);
-    if (ns == 0 || B.err[r]) { if (lane == 0) B.n_chain[r] = 0; return; }
-    if (!chain_read_warp(opt, ix, B, r, S.rec, S.rec2, S.off, S.keys, S.stage)) {
-        __syncwarp();
-        if (lane == 0) stage_chain(opt, ix, B, r);
-        __syncwarp();
+    const uint32_t so = B.seed_off[r];
+    const uint64_t *keys = B.srt + so;
+    const Chain *pre = B.chain_pool + so;
+    const Seed *seeds = B.seeds + so;
+    const int32_t *next = B.next + so;
+    const float frac_rep = (float)B.l_rep[r] / (float)(int)(B.seq_off[r + 1] - B.seq_off[r]);
+    int run = 0;
+    for (int k0 = 0; k0 < n_out; k0 += 32) {
+        const int k = k0 + lane;
+        Chain t;
+        t.n = 0;
+        if (k < n_out) t = pre[(uint32_t)keys[k]];
+        int incl = t.n;                                    // offsets: exclusive sum of the seed counts, in output order
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += v; }
+        const int head = run + incl - t.n;
+        run += __shfl_sync(FULLMASK, incl, 31);
+        if (k < n_out) {
+            Seed *cs = B.cseeds + so;
+            int o = head;
+            for (int j = t.head; j >= 0; j = next[j]) cs[o++] = seeds[j];
+            Chain out = t;
+            out.head = head; out.tail = o - 1; out.frac_rep = frac_rep;
+            B.chains[so + k] = out;
+        }
+    }
+    if (lane == 0) B.n_chain[r] = n_out;
+}
+
+struct ChainSmem { Seed stage[CHAIN_STAGE]; };
+
+// one group of up to 32 consecutive reads [base, base + 32)
+__device__ void stage_chain_group(const Opt &opt, const IndexView &ix, const BatchDev &B, int base, ChainSmem &S, int32_t *aux)
+{
+    const int lane = threadIdx.x & 31;
+    const int cnt = B.n - base < 32 ? B.n - base : 32;
+    int my_n = 0;                                          // lane q: chains of read base + q that enter the sort; -1: nothing to do
+    for (int q = 0; q < cnt; ++q) {
+        const int r = base + q;
+        const int ns = (int)(B.seed_off[r + 1] - B.seed_off[r]);
+        int n = -1;
+        if (ns == 0 || B.err[r]) { if (lane == 0) B.n_chain[r] = 0; }
+        else {
+            n = chain_phase1_warp(opt, ix, B, r, S.stage);
+            if (n < 0) n = -2;                             // the serial form, by this read's lane in phase 2
+            else if (n == 0) { if (lane == 0) B.n_chain[r] = 0; n = -1; }
+        }
+        if (lane == q) my_n = n;
+    }
+    __syncwarp();
+    int my_out = 0;
+    if (lane < cnt && my_n > 0) my_out = chain_phase2_lane(opt, B, base + lane, my_n, aux);
+    else if (lane < cnt && my_n == -2) stage_chain(opt, ix, B, base + lane);
+    __syncwarp();
+    for (int q = 0; q < cnt; ++q) {
+        const int n = __shfl_sync(FULLMASK, my_n, q), n_out = __shfl_sync(FULLMASK, my_out, q);
+        if (n > 0) chain_phase3_warp(B, base + q, n_out);
     }
 }
 
