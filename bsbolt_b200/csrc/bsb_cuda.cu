@@ -1036,7 +1036,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const bool dyn_sched = getenv("BSB_STATIC_SCHED") == nullptr;
     CK(cudaMemsetAsync(m.d_misc.p + 16, 0, 2 * 4, st));        // read counters of the chaining and the extension kernel
     if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, nullptr);
-    else { m.d_chain_aux.ensure(S + 1); k_chain_warp<<<I.n_sm * 12, 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr, m.d_chain_aux.p); }
+    else { m.d_chain_aux.ensure(S + 1); k_chain_warp<<<I.n_sm * env_int("BSB_CHAIN_BPS", 12), 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr, m.d_chain_aux.p); }
     ++m.launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m.ev[5], st));
