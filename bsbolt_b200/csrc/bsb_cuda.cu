@@ -459,8 +459,11 @@ __global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix
     uint8_t *mine = smem + (size_t)wib * smem_per_warp;
     WarpDp S;
     S.H = (int32_t *)mine; S.E = S.H + (max_q + 1); S.qs = (uint8_t *)(S.E + (max_q + 1));
-    DpScratch dp = {eh + (size_t)gw * 2 * (max_q + 1), nullptr, 0, max_q};
-    for (int t = warp_next_read(ctr, gw - nw, nw); t < B.n; t = warp_next_read(ctr, t, nw)) stage_extend_warp(opt, ix, B, order ? order[t] : t, S, dp);
+    DpScratch dp = {eh + (size_t)gw * 32 * 2 * (max_q + 1), nullptr, 0, max_q};
+    DpScratch dp_lane = {eh + ((size_t)gw * 32 + (threadIdx.x & 31)) * 2 * (max_q + 1), nullptr, 0, max_q};
+    for (unsigned base = warp_next_group(ctr, (unsigned)gw * 32 - (unsigned)nw * 32, (unsigned)nw * 32); base < (unsigned)B.n;
+         base = warp_next_group(ctr, base, (unsigned)nw * 32))
+        stage_extend_group(opt, ix, B, (int)base, min(32, B.n - (int)base), order, S, dp, dp_lane);
 }
 
 __global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
@@ -1053,7 +1056,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         const int ext_bps = env_int("BSB_EXT_BPS", 5);
         const int32_t *ext_order = nullptr;
         const int blocks = (int)std::min<size_t>((size_t)cdiv(n, wpb), (size_t)I.n_sm * ext_bps);
-        m.d_eh.ensure((size_t)blocks * wpb * 2 * (max_q + 1));
+        m.d_eh.ensure((size_t)blocks * wpb * 32 * 2 * (max_q + 1));   // one (h,e) row per lane for the per-lane tail
         int *ext_ctr = dyn_sched ? m.d_misc.p + 17 : nullptr;
         if (ext_bps > 5) k_extend_warp<8><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order, ext_ctr);
         else k_extend_warp<5><<<blocks, wpb * 32, wpb * smem_per_warp, st>>>(opt, I.ix, B, m.d_eh.p, max_q, smem_per_warp, ext_order, ext_ctr);

@@ -555,32 +555,47 @@ __device__ void chain_to_regions_warp(const Opt &opt, const IndexView &ix, int l
     }
 }
 
-// K5, one warp per read
-__device__ void stage_extend_warp(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const WarpDp &S, DpScratch &dp)
+// K5. A warp takes a group of up to 32 reads: the chains of each read are extended by the whole warp, one read after the
+// other (phase A); the tail of mem_align1_core -- mem_sort_dedup_patch with its introsorts and the occasional score-only
+// global alignment of mem_patch_reg, serial by nature -- then runs for all reads of the group at once, one read per lane,
+// each lane with its own DP scratch (phase B), instead of on lane 0 of a waiting warp after every read.
+__device__ void stage_extend_group(const Opt &opt, const IndexView &ix, const BatchDev &B, int base, int cnt, const int32_t *order,
+                                   const WarpDp &S, DpScratch &dp_warp, DpScratch &dp_lane)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t so = B.seed_off[r];
-    const int ns = (int)(B.seed_off[r + 1] - so);
-    if (ns == 0 || B.err[r]) { if (lane == 0) B.n_regs[r] = 0; return; }
-    const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
-    const uint8_t *seq = B.seq + B.seq_off[r];
-    RegList av = {B.regs + so, 0, ns};
-    int err = 0;
-    const int nc = B.n_chain[r];
-    for (int i = 0; i < nc; ++i) {
-        const Chain c = B.chains[so + i];
-        chain_to_regions_warp(opt, ix, len, seq, c, B.cseeds + so + c.head, B.srt + so, av, S, dp, &err);
-        if (err) break;
+    int my_n = -1, my_err = 0;                             // lane q: regions of read base + q before the tail (-1: nothing to do)
+    for (int q = 0; q < cnt; ++q) {
+        const int r = order ? order[base + q] : base + q;
+        const uint32_t so = B.seed_off[r];
+        const int ns = (int)(B.seed_off[r + 1] - so);
+        int n = -1, err = 0;
+        if (ns == 0 || B.err[r]) { if (lane == 0) B.n_regs[r] = 0; }
+        else {
+            const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+            const uint8_t *seq = B.seq + B.seq_off[r];
+            RegList av = {B.regs + so, 0, ns};
+            const int nc = B.n_chain[r];
+            for (int i = 0; i < nc; ++i) {
+                const Chain c = B.chains[so + i];
+                chain_to_regions_warp(opt, ix, len, seq, c, B.cseeds + so + c.head, B.srt + so, av, S, dp_warp, &err);
+                if (err) break;
+            }
+            n = av.n;
+        }
+        if (lane == q) { my_n = n; my_err = err; }
     }
     __syncwarp();
-    if (lane == 0) {
+    if (lane < cnt && my_n >= 0) {
+        const int r = order ? order[base + lane] : base + lane;
+        AlnReg *a = B.regs + B.seed_off[r];
+        int n = my_n, err = my_err;
         if (!err) {
-            av.n = sort_dedup_patch(opt, ix, seq, av.n, av.a, dp, &err);
-            for (int i = 0; i < av.n; ++i)
-                if (av.a[i].rid >= 0 && ix.anns[av.a[i].rid].is_alt) av.a[i].is_alt = 1;
+            n = sort_dedup_patch(opt, ix, B.seq + B.seq_off[r], n, a, dp_lane, &err);
+            for (int i = 0; i < n; ++i)
+                if (a[i].rid >= 0 && ix.anns[a[i].rid].is_alt) a[i].is_alt = 1;
         }
         if (err) { B.err[r] = err; B.n_regs[r] = 0; }
-        else B.n_regs[r] = av.n;
+        else B.n_regs[r] = n;
     }
     __syncwarp();
 }
