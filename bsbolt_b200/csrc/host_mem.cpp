@@ -262,7 +262,6 @@ int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err)
             opt.flag |= F_PE;
         }
     }
-    if (opt.flag & F_SMARTPE) { err = "[E::main_mem] smart pairing (-p) is not supported by the B200 aligner"; return 1; }
     if (const char *e = getenv("BSB_SHARD_COUNT")) ma.shard_count = atoi(e) > 1 ? atoi(e) : 1;
     if (const char *e = getenv("BSB_SHARD_INDEX")) ma.shard_index = atoi(e);
     if (const char *e = getenv("BSB_SHARD_PARTS")) ma.shard_parts = e;
@@ -642,6 +641,85 @@ private:
 };
 } // namespace
 
+// Smart pairing (-p): process() with MEM_F_SMARTPE (fastmap.c:38-57). The batch was cut from ONE interleaved file
+// (every read converted as a first mate); bseq_classify (bwa.c:147-165) splits it by read name into single-end
+// entries and pairs of consecutive equal names, the two classes are aligned as separate calls -- single-end at
+// n_processed, pairs at n_processed + n_single with their own insert-size statistics -- and only the SAM text
+// is copied back to the entries (the classes are struct copies in the reference), so the arbiter sees every
+// entry with alignment_score 0 / mapped 0. The result is handed on as device-style text (have_text).
+static void align_smart_pairs(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, const ReadBatch &b, int64_t n_processed,
+                              BatchResult &res, int slot, FILE *log, std::mutex &log_m)
+{
+    std::vector<int> sep[2];
+    auto same_name = [&](int x, int y) {   // strcmp: a name ends at its first NUL
+        const char *px = b.names.data() + b.name_off[x], *py = b.names.data() + b.name_off[y];
+        const size_t lx = strnlen(px, b.name_off[x + 1] - b.name_off[x]), ly = strnlen(py, b.name_off[y + 1] - b.name_off[y]);
+        return lx == ly && memcmp(px, py, lx) == 0;
+    };
+    bool has_last = true;
+    for (int i = 1; i < b.n; ++i) {
+        if (has_last) {
+            if (same_name(i, i - 1)) { sep[1].push_back(i - 1); sep[1].push_back(i); has_last = false; }
+            else sep[0].push_back(i - 1);
+        } else has_last = true;
+    }
+    if (has_last && b.n > 0) sep[0].push_back(b.n - 1);
+    if (ma.verbose >= 3) {
+        std::lock_guard<std::mutex> l(log_m);
+        fprintf(log, "[M::%s] %d single-end sequences; %d paired-end sequences\n", "process", (int)sep[0].size(), (int)sep[1].size());
+    }
+    std::vector<std::string> sam(b.n);
+    for (int k = 0; k < 2; ++k) {
+        if (sep[k].empty()) continue;
+        ReadBatch sub;
+        sub.clear();
+        FastxRecord r;
+        for (int i : sep[k]) {
+            r.name.assign(b.names.data() + b.name_off[i], b.name_off[i + 1] - b.name_off[i]);
+            r.comment.assign(b.comments.data() + b.cmt_off[i], b.cmt_off[i + 1] - b.cmt_off[i]);
+            r.seq.assign(b.bases.data() + b.seq_off[i], b.seq_off[i + 1] - b.seq_off[i]);
+            if (b.has_qual[i]) r.qual.assign(b.qual.data() + b.seq_off[i], b.seq_off[i + 1] - b.seq_off[i]); else r.qual.clear();
+            sub.add(r, ma.copy_comment, b.first[i], b.read_group[i], b.pattern[i]);
+        }
+        MemArgs mk = ma;
+        if (k) mk.opt.flag |= F_PE; else mk.opt.flag &= ~F_PE;
+        BatchResult rk;
+        rk.want_text = true; rk.rg_id = ma.rg_id;
+        const double ta = now_sec();
+        aligner.align(mk.opt, sub, n_processed + (k ? (int64_t)sep[0].size() : 0), k && ma.have_pes0 ? ma.pes0 : nullptr, rk, slot);
+        if (ma.verbose >= 3) {
+            std::lock_guard<std::mutex> l(log_m);
+            fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", sub.n, now_sec() - ta);
+        }
+        if (rk.have_text) {
+            const char *text = reinterpret_cast<const char *>(rk.text.data());
+            for (int q = 0; q < sub.n; ++q) sam[sep[k][q]].assign(text + rk.text_off[q], rk.text_off[q + 1] - rk.text_off[q]);
+        } else {
+            const SamView v = make_sam_view(mk, idx, sub, rk);
+            EntryStats st;
+            for (int q = 0; q < sub.n; ++q) format_entry_append(v, k != 0, q, sam[sep[k][q]], st);
+        }
+        res.ms_h2d += rk.ms_h2d; res.ms_kernels += rk.ms_kernels; res.ms_d2h += rk.ms_d2h;
+        for (int s = 0; s < 8; ++s) res.ms_stage[s] += rk.ms_stage[s];
+        res.n_seeds += rk.n_seeds; res.h2d_bytes += rk.h2d_bytes; res.d2h_bytes += rk.d2h_bytes;
+        if (k) memcpy(res.pes, rk.pes, sizeof res.pes);
+    }
+    size_t total = 0;
+    for (const std::string &s : sam) total += s.size();
+    res.text.resize_uninit(total);
+    res.text_off.resize(b.n + 1);
+    const SamStats zero = {0, 0, 0, 0, 0};
+    res.stats.assign(b.n, zero);
+    size_t o = 0;
+    for (int i = 0; i < b.n; ++i) {
+        res.text_off[i] = (uint32_t)o;
+        memcpy(res.text.data() + o, sam[i].data(), sam[i].size());
+        o += sam[i].size();
+    }
+    res.text_off[b.n] = (uint32_t)o;
+    res.have_text = true;
+}
+
 // Three overlapped stages, like the reference's kt_pipeline (fastmap.c:352) but with the GPU in the
 // middle: [read + convert-pattern bookkeeping] -> [device batch] -> [SAM text + arbiter + write].
 // Each stage handles batches strictly in input order, so output order and n_processed are unchanged.
@@ -764,10 +842,16 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 while (q_read.pop(j)) {
                     double ta = now_sec();
                     j->res.want_text = true; j->res.rg_id = ma.rg_id;   // SAM text from the device when the aligner can produce it
+                    const bool smart = (ma.opt.flag & F_SMARTPE) != 0;
+                    if (smart) {
+                        for (int k = 0; k < 8; ++k) j->res.ms_stage[k] = 0;
+                        j->res.ms_h2d = j->res.ms_kernels = j->res.ms_d2h = 0; j->res.n_seeds = j->res.h2d_bytes = j->res.d2h_bytes = 0;
+                        align_smart_pairs(ma, idx, aligner, j->batch, j->n_processed, j->res, slot, log, log_m);
+                    } else
                     aligner.align(ma.opt, j->batch, j->n_processed, ma.have_pes0 ? ma.pes0 : nullptr, j->res, slot);
                     j->sec_align = now_sec() - ta;
                     { std::lock_guard<std::mutex> l(res_m); t_res1 = std::max(t_res1, now_sec()); }
-                    if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", j->batch.n, j->sec_align); }
+                    if (ma.verbose >= 3 && !smart) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", j->batch.n, j->sec_align); }
                     q_done.push(std::move(j));
                 }
             } catch (const std::exception &e) {

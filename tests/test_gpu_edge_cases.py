@@ -165,3 +165,23 @@ def test_launcher_options(index, golden, tmp_path):
                                ['-k', '12', '-r', '1.0', '-c', '30', '-D', '0.3', '-m', '10', '-W', '5', '-y', '5'],
                                ['-d', '30', '-w', '20', '-Z', '0.5', '-z', '-l', '0.3', '-n', '2'])):
         both(index, golden, extra + ['-K', '50000'], fqs, tmp_path, f'opt{k}')
+
+
+def test_smart_pairing(index, golden, tmp_path):
+    """`-p`: interleaved ragged pairs with singletons and orphans mixed in, alone and with the options that change what the
+    two per-batch calls see (-I statistics for the paired call only, comments, read group, a second file that is ignored)"""
+    r1, r2 = ragged_reads(golden, 9, True)
+    inter = []
+    for k, (a, b) in enumerate(zip(r1, r2)):
+        if k % 5 == 2:
+            inter.append((f's{k}', a[1][::-1].translate(COMP), a[2]))   # a singleton between two pairs
+        inter.append(a)
+        if k % 6 != 4:
+            inter.append(b)                                             # else: orphaned first mate
+    fq = write_fq(tmp_path / 'inter.fq', inter, comment='BC:Z:ACGT')
+    for k, extra in enumerate((['-p', '-K', '3000'], ['-p', '-K', '100000'], ['-p', '-z', '-K', '2000'], ['-p', '-I', '350,40', '-K', '5000'],
+                               ['-p', '-C', '-R', r'@RG\tID:g\tSM:s', '-K', '4000'], ['-p', '-S', '-P', '-K', '100000'])):
+        both(index, golden, extra, [fq], tmp_path, f'smart{k}')
+    both(index, golden, ['-p', '-K', '100000'], [fq, fq], tmp_path, 'smart_two_files')
+    single = write_fq(tmp_path / 'single.fq', inter[:1])
+    both(index, golden, ['-p'], [single], tmp_path, 'smart_one_read')

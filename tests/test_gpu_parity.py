@@ -6,7 +6,8 @@ import subprocess
 
 import pytest
 
-from conftest import ROOT, first_diff, strip_pg
+from conftest import GOLDEN, ROOT, first_diff, strip_pg
+from smart_inter import SMART_CASES, write_interleaved
 
 pytestmark = pytest.mark.gpu
 CASES = ['se100', 'se100_un', 'se50_clip', 'pe150', 'pe150_un', 'pe150_un_sp0', 'pe150_opts']
@@ -42,6 +43,21 @@ def test_golden_sam_bit_exact(index, golden, tmp_path, case):
     assert mine == want, first_diff(want, mine)
     assert bs == golden.cases[case]['bsstat']
     assert stats['kernel_launches'] > 0 and stats['ms_kernels'] > 0
+
+
+@pytest.mark.parametrize('case', sorted(SMART_CASES))
+def test_smart_pairing_golden_sam_bit_exact(index, golden, tmp_path, case):
+    """`-p`: interleaved input split by read name into a single-end and a paired call per batch (fastmap.c:38-57)."""
+    import gzip
+    import json
+    man = json.load(open(os.path.join(GOLDEN, 'smart_golden.json')))[case]
+    fq = write_interleaved(golden.dir, tmp_path / 'smart_inter.fq')
+    argv = ['mem'] + golden.manifest['launcher_args'] + man['extra'] + [golden.idxbase, fq]
+    sam, bs, stats = run_mem(index, argv, tmp_path, case)
+    mine, want = strip_pg(sam), gzip.open(os.path.join(GOLDEN, case + '.sam.gz'), 'rt').read()
+    assert mine == want, first_diff(want, mine)
+    assert bs == man['bsstat']
+    assert stats['kernel_launches'] > 0
 
 
 def test_batch_api_matches_mem_main(index, golden, tmp_path):

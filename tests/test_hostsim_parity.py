@@ -6,7 +6,8 @@ import subprocess
 
 import pytest
 
-from conftest import ROOT, first_diff, strip_pg
+from conftest import GOLDEN, ROOT, first_diff, strip_pg
+from smart_inter import SMART_CASES, write_interleaved
 
 HOSTSIM = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
 CASES = ['se100', 'se100_un', 'se50_clip', 'pe150', 'pe150_un', 'pe150_un_sp0', 'pe150_opts']
@@ -29,6 +30,27 @@ def test_kernel_bodies_match_reference_sam(built, golden, case, seeding):
             k, v = l[7:].split(': ')
             stats[k] = stats.get(k, 0) + int(v)
     assert stats == golden.cases[case]['bsstat']
+
+
+@pytest.mark.parametrize('case', sorted(SMART_CASES))
+def test_smart_pairing_matches_reference_sam(built, golden, tmp_path, case):
+    """`-p` (fastmap.c:38-57, bseq_classify bwa.c:147-165): one interleaved file, single-end entries and name-matched
+    pairs aligned as two calls per batch, the arbiter fed with untouched statistics -- against the reference's SAM."""
+    import gzip
+    import json
+    man = json.load(open(os.path.join(GOLDEN, 'smart_golden.json')))[case]
+    fq = write_interleaved(golden.dir, tmp_path / 'smart_inter.fq')
+    argv = ['mem'] + golden.manifest['launcher_args'] + man['extra'] + [golden.idxbase, fq]
+    p = subprocess.run([HOSTSIM] + argv, capture_output=True, text=True, env=dict(os.environ, BSB_HOSTSIM_SEED_V3='1'))
+    assert p.returncode == 0, p.stderr[-2000:]
+    mine, want = strip_pg(p.stdout), gzip.open(os.path.join(GOLDEN, case + '.sam.gz'), 'rt').read()
+    assert mine == want, first_diff(want, mine)
+    stats = {}
+    for l in p.stderr.split('\n'):
+        if l.startswith('BSStat '):
+            k, v = l[7:].split(': ')
+            stats[k] = stats.get(k, 0) + int(v)
+    assert stats == man['bsstat']
 
 
 def test_reference_binary_reproduces_golden(built, golden):
