@@ -466,6 +466,33 @@ __global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix
         stage_extend_group(opt, ix, B, (int)base, min(32, B.n - (int)base), order, S, dp, dp_lane);
 }
 
+// K4b: mem_flt_chained_seeds (bwamem.c:602-619). Launched only when a read of the batch can qualify (reads of about
+// 720 bp and more, or -W): a warp takes a read, each lane one of its chains; the flanked 16-bit Smith-Waterman of a seed
+// covers fewer than 200 x 200 cells, its four rows live in the lane's local memory.
+__global__ void __launch_bounds__(128) k_seed_sw(Opt opt, IndexView ix, BatchDev B, const double *log_tab, int n_log)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = gw; r < B.n; r += nw) {
+        const int nc = B.n_chain[r];
+        const int had_err = B.err[r];
+        __syncwarp();
+        if (nc == 0 || had_err) continue;
+        const uint32_t so = B.seed_off[r];
+        const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+        int err = 0;
+        const int min_hsp = seed_sw_min_score(opt, len, log_tab, n_log, &err);
+        if (err) { if (lane == 0) B.err[r] = err; continue; }
+        if (min_hsp < 0) continue;
+        int32_t rows[4 * SEED_SW_CAP];
+        SwScratch ws = {rows, rows + SEED_SW_CAP, rows + 2 * SEED_SW_CAP, rows + 3 * SEED_SW_CAP, nullptr, SEED_SW_CAP, 0};
+        for (int i = lane; i < nc; i += 32) {
+            filter_chained_seeds(opt, ix, len, B.seq + B.seq_off[r], 1, B.chains + so + i, B.cseeds + so, min_hsp, ws, &err);
+            if (err) B.err[r] = err;
+        }
+    }
+}
+
 __global__ void k_pestat(Opt opt, IndexView ix, BatchDev B)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -893,6 +920,8 @@ size_t CudaAligner::index_bytes() const
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+static const int kMaxReadLen = 1200;
+
 void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot)
 {
     Impl &I = *im_;
@@ -908,7 +937,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const size_t nb = b.bases.size();
     int max_len = 0;
     for (int i = 0; i < n; ++i) max_len = std::max(max_len, b.len(i));
-    if (max_len > 700) throw std::runtime_error("[E::bsbolt_b200] reads longer than 700 bp need mem_seed_sw (bwamem.c:575-619), which this build does not implement");
+    // the warp kernels keep a DP row, the query and the CIGAR/MD scratch of a read in shared memory (36 bytes x length per block)
+    if (max_len > kMaxReadLen) throw std::runtime_error("[E::bsbolt_b200] reads longer than " + std::to_string(kMaxReadLen) + " bp do not fit the per-warp shared-memory tiles of this build");
     for (int k = 0; k < 8; ++k) out.ms_stage[k] = 0;
     const bool dbg = getenv("BSB_DEBUG_TIMELINE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -1042,6 +1072,13 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     else { m.d_chain_aux.ensure(S + 1); k_chain_warp<<<I.n_sm * env_int("BSB_CHAIN_BPS", 12), 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr, m.d_chain_aux.p); }
     ++m.launches;
     CK(cudaGetLastError());
+    // mem_flt_chained_seeds runs for reads with 5.5 ln(l) <= 0.05 l (l of about 720 and more; the kernel applies the exact
+    // per-read test) or, with -W, for reads of 22 W bases and more
+    const bool chained_seed_sw = opt.min_chain_weight ? !((double)(1.1f * (float)opt.min_chain_weight) > (double)(0.05f * (float)max_len)) : max_len >= 700;
+    if (chained_seed_sw && S) {
+        k_seed_sw<<<I.n_sm * 8, 128, 0, st>>>(opt, I.ix, B, I.d_log.p, (int)I.log_tab.size()); ++m.launches;
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(m.ev[5], st));
     // ---- K5 ----
     const int max_q = max_len + 8;

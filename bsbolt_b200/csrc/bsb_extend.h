@@ -81,6 +81,68 @@ BSB_HD void alnreg_clear(AlnReg &a)
 struct RegList { AlnReg *a; int n, cap; };
 
 // Extends the seeds of one chain (longest first) and appends the regions to av.
+// mem_flt_chained_seeds' threshold (bwamem.c:604-606): the minimum seed score, or -1 when the filter does not run for this
+// read length (5.5 ln(l) > 0.05 l, i.e. every read shorter than about 720 bp unless -W is given). Float/double mix as in C:
+// MEM_HSP_COEF * int and MEM_SEEDSW_COEF * int are float products; log_tab[i] = glibc log(i).
+BSB_HD int seed_sw_min_score(const Opt &opt, int l_query, const double *log_tab, int n_log, int *err)
+{
+    double min_l;
+    if (opt.min_chain_weight) min_l = (double)(1.1f * (float)opt.min_chain_weight);
+    else {
+        if (l_query >= n_log) { *err = ERR_SCRATCH_OVERFLOW; return -1; }
+        min_l = (double)5.5f * log_tab[l_query];
+    }
+    if (min_l > (double)(0.05f * (float)l_query)) return -1;
+    return (int)(opt.a * min_l + .499);
+}
+
+// mem_seed_sw (bwamem.c:575-600): local alignment score of the seed with 50 bp of flank on either side, -1 when the seed
+// (or its window) is 200 bp or longer. ksw_align2 without KSW_XBYTE runs the 16-bit kernel; only the score is used.
+BSB_HD int seed_sw(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query, const Seed &s, SwScratch &ws, int *err)
+{
+    const int64_t l_pac = ix.l_pac;
+    if (s.len >= 200) return -1;
+    int qb = s.qbeg, qe = s.qbeg + s.len;
+    int64_t rb = s.rbeg, re = s.rbeg + s.len;
+    const int64_t mid = (rb + re) >> 1;
+    qb -= 50; qb = qb > 0 ? qb : 0;
+    qe += 50; qe = qe < l_query ? qe : l_query;
+    rb -= 50; rb = rb > 0 ? rb : 0;
+    re += 50; re = re < l_pac << 1 ? re : l_pac << 1;
+    if (rb < l_pac && l_pac < re) {
+        if (mid < l_pac) re = l_pac;
+        else rb = l_pac;
+    }
+    if (qe - qb >= 200 || re - rb >= 200) return -1;
+    fetch_window(ix, &rb, mid, &re);
+    QrySeq q = {query + qb, 1};
+    RefSeq t = {ix.pac, l_pac, rb, 1};
+    SwResult x = sw_striped(2, qe - qb, q, (int)(re - rb), t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, SW_XSTART, ws, err);
+    return x.score;
+}
+
+// mem_flt_chained_seeds (bwamem.c:602-619) over the compacted chains of one read: seeds whose flanked local score is below
+// the threshold leave their chain, the others carry that score into the extension order (chain_to_regions sorts by it).
+BSB_HD void filter_chained_seeds(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query, int n_chn, Chain *chains,
+                                 Seed *cseeds, int min_hsp, SwScratch &ws, int *err)
+{
+    for (int i = 0; i < n_chn; ++i) {
+        Chain &c = chains[i];
+        Seed *cs = cseeds + c.head;
+        int k = 0;
+        for (int j = 0; j < c.n; ++j) {
+            Seed s = cs[j];
+            int sc = seed_sw(opt, ix, l_query, query, s, ws, err);
+            if (*err) return;
+            if (sc < 0 || sc >= min_hsp) {
+                s.score = sc < 0 ? s.len * opt.a : sc;
+                cs[k++] = s;
+            }
+        }
+        c.n = k;
+    }
+}
+
 // cs: the chain's seeds (contiguous); srt: scratch u64[c.n]
 BSB_HD void chain_to_regions(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query,
                              const Chain &c, const Seed *cs, uint64_t *srt, RegList &av, DpScratch &dp, int *err)

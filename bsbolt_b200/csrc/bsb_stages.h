@@ -176,6 +176,25 @@ BSB_HD void stage_chain(const Opt &opt, const IndexView &ix, const BatchDev &B, 
     B.n_chain[r] = n;
 }
 
+// K4b: mem_flt_chained_seeds for read r (only reads of about 720 bp and more, or any read when -W is set). Scratch: four
+// rows of SEED_SW_CAP cells (the flanked window is shorter than 200 bases, padded to a multiple of 8).
+enum { SEED_SW_CAP = 208 };
+BSB_HD void stage_seed_sw(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const double *log_tab, int n_log)
+{
+    const uint32_t so = B.seed_off[r];
+    const int nc = B.n_chain[r];
+    if (nc == 0 || B.err[r]) return;
+    const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
+    int err = 0;
+    const int min_hsp = seed_sw_min_score(opt, len, log_tab, n_log, &err);
+    if (err) { B.err[r] = err; return; }
+    if (min_hsp < 0) return;
+    int32_t rows[4 * SEED_SW_CAP];
+    SwScratch ws = {rows, rows + SEED_SW_CAP, rows + 2 * SEED_SW_CAP, rows + 3 * SEED_SW_CAP, nullptr, SEED_SW_CAP, 0};
+    filter_chained_seeds(opt, ix, len, B.seq + B.seq_off[r], nc, B.chains + so, B.cseeds + so, min_hsp, ws, &err);
+    if (err) B.err[r] = err;
+}
+
 // K5: banded extension of every kept chain of read r + region de-duplication
 BSB_HD void stage_extend(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, DpScratch &dp)
 {

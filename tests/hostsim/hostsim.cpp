@@ -74,6 +74,7 @@ public:
         for (int r = 0; r < n; ++r)
             for (uint32_t g = seed_off[r]; g < seed_off[r + 1]; ++g) stage_sa(opt, ix_, B, r, g);
         for (int r = 0; r < n; ++r) stage_chain(opt, ix_, B, r);
+        for (int r = 0; r < n; ++r) stage_seed_sw(opt, ix_, B, r, log_tab_.data(), (int)log_tab_.size());
         // DP scratch
         const int max_q = max_len + 8;
         std::vector<int32_t> eh(2 * (size_t)(max_q + 1));

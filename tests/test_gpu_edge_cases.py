@@ -136,14 +136,59 @@ def test_zero_length_reads(index, golden, tmp_path):
 
 
 def test_reads_beyond_the_supported_length_fail_loudly(index, golden, tmp_path):
-    """mem_seed_sw (bwamem.c:575-619, reads of roughly 700 bp and more) is not implemented: refuse, never differ silently"""
+    """reads longer than the per-warp shared-memory tiles (1200 bp): refuse, never differ silently"""
     from bsbolt_b200 import _native
     g = genome(golden)
-    fq = write_fq(tmp_path / 'long.fq', [('long', g['chr1'][100:1000], 'I' * 900)])
+    fq = write_fq(tmp_path / 'long.fq', [('long', g['chr1'][100:1400], 'I' * 1300)])
     argv = ['mem'] + golden.manifest['launcher_args'] + [golden.idxbase, fq]
     with open(tmp_path / 'o.sam', 'w') as fo, open(tmp_path / 'o.log', 'w') as fl:
         rc, _ = _native.mem_main(argv, index=index, out_fd=fo.fileno(), log_fd=fl.fileno())
-    assert rc != 0 and '700' in _native.last_error()
+    assert rc != 0 and '1200' in _native.last_error()
+
+
+def long_reads(golden, seed, n=120):
+    """pairs of 650-1200 bp with substitutions and indels: short seeds around the errors, so mem_seed_sw has work"""
+    rnd = random.Random(seed)
+    g = genome(golden)
+    names = sorted(k for k in g if len(g[k]) > 6000)
+
+    def mut(s, sub, indel):
+        out = []
+        for c in s:
+            r = rnd.random()
+            if r < sub: out.append(rnd.choice('ACGT'))
+            elif r < sub + indel: continue
+            elif r < sub + 2 * indel: out.append(c + rnd.choice('ACGT'))
+            else: out.append(c)
+        return ''.join(out)[:1200]
+    r1, r2 = [], []
+    for k in range(n):
+        c = names[k % len(names)]
+        L = rnd.choice([650, 700, 719, 720, 721, 760, 850, 1000, 1190])
+        p = rnd.randrange(0, len(g[c]) - 2 * L - 400)
+        a, b = g[c][p:p + L].upper(), g[c][p + L + 150:p + 2 * L + 150].upper()[::-1].translate(COMP)
+        sub, ind = rnd.choice([0.0, 0.02, 0.05, 0.09]), rnd.choice([0, 0.003, 0.01])
+        a, b = mut(bisulfite(a, rnd), sub, ind), mut(b.replace('G', 'A'), sub, ind)
+        if k % 13 == 0:
+            a = a[:len(a) // 2] + ''.join(rnd.choice('ACGT') for _ in range(len(a) // 2))
+        r1.append((f'l{k}', a, 'I' * len(a)))
+        r2.append((f'l{k}', b, 'F' * len(b)))
+    return r1, r2
+
+
+def test_long_reads_chained_seed_filter(index, golden, tmp_path):
+    """mem_flt_chained_seeds (bwamem.c:602-619) on reads around and above its ~720 bp threshold, single and paired, and switched
+    on for short reads by -W (min_l = 1.1 W instead of 5.5 ln l)"""
+    r1, r2 = long_reads(golden, 10)
+    fqs = [write_fq(tmp_path / 'l1.fq', r1), write_fq(tmp_path / 'l2.fq', r2)]
+    both(index, golden, ['-K', '30000'], fqs[:1], tmp_path, 'long_se')
+    both(index, golden, ['-z', '-K', '100000'], fqs[:1], tmp_path, 'long_se_un')
+    both(index, golden, ['-K', '50000'], fqs, tmp_path, 'long_pe')
+    both(index, golden, ['-W', '25', '-K', '50000'], fqs, tmp_path, 'long_pe_w25')
+    s1, s2 = ragged_reads(golden, 11, True)
+    sq = [write_fq(tmp_path / 's1.fq', s1), write_fq(tmp_path / 's2.fq', s2)]
+    both(index, golden, ['-W', '1', '-k', '12', '-K', '50000'], sq, tmp_path, 'short_w1')
+    both(index, golden, ['-W', '4', '-K', '50000'], sq, tmp_path, 'short_w4')
 
 
 def test_input_formats(index, golden, tmp_path):

@@ -60,6 +60,19 @@ def test_smart_pairing_golden_sam_bit_exact(index, golden, tmp_path, case):
     assert stats['kernel_launches'] > 0
 
 
+@pytest.mark.parametrize('case', ['long_se', 'long_se_w30'])
+def test_long_reads_golden_sam_bit_exact(index, golden, tmp_path, case):
+    """reads of 690-1200 bp: mem_flt_chained_seeds / mem_seed_sw (k_seed_sw) between chaining and extension"""
+    import gzip
+    import json
+    man = json.load(open(os.path.join(GOLDEN, 'long_golden.json')))[case]
+    argv = ['mem'] + golden.manifest['launcher_args'] + man['extra'] + [golden.idxbase] + [os.path.join(golden.dir, f) for f in man['fq']]
+    sam, bs, stats = run_mem(index, argv, tmp_path, case)
+    mine, want = strip_pg(sam), gzip.open(os.path.join(GOLDEN, case + '.sam.gz'), 'rt').read()
+    assert mine == want, first_diff(want, mine)
+    assert bs == man['bsstat']
+
+
 def test_batch_api_matches_mem_main(index, golden, tmp_path):
     """bsb_batch_create/align/sam (host buffers in, SAM text out) == the file-based run"""
     from bsbolt_b200 import _native

@@ -53,6 +53,20 @@ def test_smart_pairing_matches_reference_sam(built, golden, tmp_path, case):
     assert stats == man['bsstat']
 
 
+@pytest.mark.parametrize('case', ['long_se', 'long_se_w30'])
+def test_chained_seed_filter_matches_reference_sam(built, golden, case):
+    """mem_flt_chained_seeds / mem_seed_sw (bwamem.c:575-619): reads of 690-1200 bp (the filter starts at about 720 bp), and
+    the same reads with -W 30, which switches it on for every length"""
+    import gzip
+    import json
+    man = json.load(open(os.path.join(GOLDEN, 'long_golden.json')))[case]
+    argv = ['mem'] + golden.manifest['launcher_args'] + man['extra'] + [golden.idxbase] + [os.path.join(golden.dir, f) for f in man['fq']]
+    p = subprocess.run([HOSTSIM] + argv, capture_output=True, text=True, env=dict(os.environ, BSB_HOSTSIM_SEED_V3='1'))
+    assert p.returncode == 0, p.stderr[-2000:]
+    mine, want = strip_pg(p.stdout), gzip.open(os.path.join(GOLDEN, case + '.sam.gz'), 'rt').read()
+    assert mine == want, first_diff(want, mine)
+
+
 def test_reference_binary_reproduces_golden(built, golden):
     """Pins oracle/_ref (the compiled reference) to the committed vectors."""
     bwa = os.path.join(ROOT, 'oracle', '_ref', 'bwa')
