@@ -1202,6 +1202,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                 else k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_fin);
                 if (coop) {
                     const int hv_smem = 4 * (int)((4 * L.sw_cap + (L.sw_cap + 3) / 4) * 4);
+                    if (hv_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_final_pe_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, hv_smem));
                     k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
                     ++m.launches;
                 }
