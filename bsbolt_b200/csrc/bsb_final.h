@@ -144,6 +144,29 @@ BSB_HD int mark_primary(const Opt &opt, int n, AlnReg *a, int64_t id, int32_t *z
     return n_pri;
 }
 
+// mem_reorder_primary5 (bwamem.c:1085-1108), `bwa mem -5`: the primary with the smallest query start becomes entry 0
+BSB_HD void reorder_primary5(int T, int n, AlnReg *a)
+{
+    int k, n_pri = 0, left_st = 0x7fffffff, left_k = -1;
+    for (k = 0; k < n; ++k)
+        if (a[k].secondary < 0 && !a[k].is_alt && a[k].score >= T) ++n_pri;
+    if (n_pri <= 1) return;
+    for (k = 0; k < n; ++k) {
+        const AlnReg &p = a[k];
+        if (p.secondary >= 0 || p.is_alt || p.score < T) continue;
+        if (p.qb < left_st) { left_st = p.qb; left_k = k; }
+    }
+    if (left_k == 0) return;
+    AlnReg t = a[0]; a[0] = a[left_k]; a[left_k] = t;
+    for (k = 1; k < n; ++k) {
+        AlnReg &p = a[k];
+        if (p.secondary == 0) p.secondary = left_k;
+        else if (p.secondary == left_k) p.secondary = 0;
+        if (p.secondary_all == 0) p.secondary_all = left_k;
+        else if (p.secondary_all == left_k) p.secondary_all = 0;
+    }
+}
+
 // ---- mapping quality -------------------------------------------------------------------------
 
 BSB_HD double tab_log(const MathTab &mt, int x, int *err)
@@ -775,6 +798,7 @@ BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt
     }
     n_pri[0] = mark_primary(opt, a[0]->n, a[0]->a, (int64_t)(id << 1 | 0), ws.z);
     n_pri[1] = mark_primary(opt, a[1]->n, a[1]->a, (int64_t)(id << 1 | 1), ws.z);
+    if (opt.flag & F_PRIMARY5) { reorder_primary5(opt.T, a[0]->n, a[0]->a); reorder_primary5(opt.T, a[1]->n, a[1]->a); }
     ReadCtx rc[2];
     for (i = 0; i < 2; ++i) { rc[i].read = first + i; rc[i].l_seq = ls[i]; rc[i].regs = a[i]->a; rc[i].n_regs = a[i]->n; }
 

@@ -248,6 +248,7 @@ BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int
     const AlnReg *src = B.regs + B.seed_off[r];
     for (int j = 0; j < n; ++j) wregs[j] = src[j];
     mark_primary(opt, n, wregs, B.n_processed + r, ws.z);
+    if (opt.flag & F_PRIMARY5) reorder_primary5(opt.T, n, wregs);
     ReadCtx rc;
     rc.read = r;
     rc.l_seq = (int)(B.seq_off[r + 1] - B.seq_off[r]);

@@ -230,3 +230,22 @@ def test_smart_pairing(index, golden, tmp_path):
     both(index, golden, ['-p', '-K', '100000'], [fq, fq], tmp_path, 'smart_two_files')
     single = write_fq(tmp_path / 'single.fq', inter[:1])
     both(index, golden, ['-p'], [single], tmp_path, 'smart_one_read')
+
+
+def test_bwa_mem_options_beyond_the_launcher(index, golden, tmp_path):
+    """`bsb_mem_main` takes a full `bwa mem` command line: the options `bsbolt Align` never sets (fastmap.c:113-190) behave like
+    the reference's too -- -5 (mem_reorder_primary5), -a, -q, -u, -V, -P, -s/-G/-N/-X/-Q and the -x presets"""
+    r1, r2 = ragged_reads(golden, 12, True)
+    fqs = [write_fq(tmp_path / 'b1.fq', r1), write_fq(tmp_path / 'b2.fq', r2)]
+    pe = [os.path.join(golden.dir, 'pe150uc_1.fq'), os.path.join(golden.dir, 'pe150uc_2.fq')]
+    se = [os.path.join(golden.dir, 'se100c.fq')]
+    for k, extra in enumerate((['-5'], ['-5', '-z'], ['-a'], ['-q'], ['-u'], ['-V'], ['-P'], ['-S', '-P'], ['-s', '3', '-G', '50', '-N', '2'],
+                               ['-X', '0.2'], ['-Q', '20'], ['-Q', '0'])):
+        both(index, golden, extra + ['-K', '50000'], fqs, tmp_path, f'bwa{k}')
+    both(index, golden, ['-5', '-K', '150000'], pe, tmp_path, 'bwa_5_pe')
+    both(index, golden, ['-5', '-M', '-K', '100000'], se, tmp_path, 'bwa_5_se')
+    both(index, golden, ['-a', '-M', '-u', '-K', '100000'], se, tmp_path, 'bwa_amu_se')
+    both(index, golden, ['-x', 'pacbio', '-K', '100000'], se, tmp_path, 'bwa_pacbio')
+    long_fq = [os.path.join(golden.dir, 'long_se.fq')]
+    both(index, golden, ['-x', 'ont2d', '-K', '100000'], long_fq, tmp_path, 'bwa_ont2d')
+    both(index, golden, ['-x', 'intractg', '-5', '-K', '100000'], long_fq, tmp_path, 'bwa_intractg')
