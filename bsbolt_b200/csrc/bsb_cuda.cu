@@ -1133,7 +1133,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
             CK(cudaMemcpyAsync(dir.data(), m.d_pe_dir.p, np, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(isz.data(), m.d_pe_isize.p, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
             m.wait();
-            estimate_pestat(opt, dir, isz, B.pes, verbose);
+            estimate_pestat(opt, dir, isz, B.pes, verbose, &out.log_text);
         }
         memcpy(out.pes, B.pes, sizeof B.pes);
     }

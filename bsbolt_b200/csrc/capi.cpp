@@ -110,6 +110,7 @@ static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, in
         }
         int lfd = dup(log_fd);
         log = fdopen(lfd, "w");
+        if (log) setvbuf(log, nullptr, _IOLBF, 1 << 16);   // whole lines: the descriptor may be shared with other writers (stderr)
         if (bam_path) bam.reset(new BamWriter(bam_path, bam_threads > 0 ? bam_threads : host_thread_share(), bam_level));
         else {
             int ofd = dup(out_fd);
@@ -206,6 +207,7 @@ int bsb_batch_align(bsb_batch_t *b, int64_t n_processed, bsb_run_stats_t *stats)
         if (!b) throw std::runtime_error("[E::bsb_batch_align] batch is NULL");
         b->idx->aligner->verbose = 0;
         b->idx->aligner->align(b->ma.opt, b->reads, n_processed, b->ma.have_pes0 ? b->ma.pes0 : nullptr, b->res);
+        if (!b->res.log_text.empty()) { fputs(b->res.log_text.c_str(), stderr); b->res.log_text.clear(); }   // [M::mem_pestat] lines, like the reference
         b->aligned = true;
         if (stats) {
             RunSummary sum;

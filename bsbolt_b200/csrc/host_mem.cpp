@@ -1,5 +1,6 @@
 // host_mem.cpp -- see host_mem.h
 #include "host_mem.h"
+#include <stdarg.h>
 #include "host_bam.h"
 #include "bsb_hd.h"
 #include "bsb_sam.h"
@@ -454,15 +455,27 @@ void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vect
 // ------------------------------------------------------------------------------------------------
 // insert size statistics + math tables
 // ------------------------------------------------------------------------------------------------
-void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::vector<int64_t> &isz, PeStat pes[4], int verbose)
+void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::vector<int64_t> &isz, PeStat pes[4], int verbose, std::string *log_text)
 {
+    // the messages of one batch leave as ONE block (through the caller's log under its lock, or stderr): device slots run
+    // concurrently and a line must never land inside another thread's line
+    std::string text;
+    auto say = [&](const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        text += buf;
+    };
+    struct Flush { std::string &t; std::string *sink; ~Flush() { if (sink) *sink += t; else if (!t.empty()) fputs(t.c_str(), stderr); } } flush = {text, log_text};
     (void)opt;
     std::vector<uint64_t> isize[4];
     memset(pes, 0, 4 * sizeof(PeStat));
     for (size_t i = 0; i < dir.size(); ++i)
         if (dir[i] >= 0) isize[dir[i]].push_back((uint64_t)isz[i]);
     if (verbose >= 3)
-        fprintf(stderr, "[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", "mem_pestat",
+        say("[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", "mem_pestat",
                 (long)isize[0].size(), (long)isize[1].size(), (long)isize[2].size(), (long)isize[3].size());
     for (int d = 0; d < 4; ++d) {
         PeStat *r = &pes[d];
@@ -470,10 +483,10 @@ void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::
         int p25, p50, p75, x;
         size_t n = q.size(), i;
         if (n < 10) {
-            if (verbose >= 3) fprintf(stderr, "[M::%s] skip orientation %c%c as there are not enough pairs\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
+            if (verbose >= 3) say("[M::%s] skip orientation %c%c as there are not enough pairs\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
             r->failed = 1;
             continue;
-        } else if (verbose >= 3) fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
+        } else if (verbose >= 3) say("[M::%s] analyzing insert size distribution for orientation %c%c...\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
         { // insert sizes are bounded by max_ins: counting sort when the range is small, else a comparison sort
             uint64_t mx = 0;
             for (uint64_t v : q) mx = v > mx ? v : mx;
@@ -491,8 +504,8 @@ void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::
         if (r->low < 1) r->low = 1;
         r->high = (int)(p75 + 2.0 * (p75 - p25) + .499);
         if (verbose >= 3) {
-            fprintf(stderr, "[M::%s] (25, 50, 75) percentile: (%d, %d, %d)\n", "mem_pestat", p25, p50, p75);
-            fprintf(stderr, "[M::%s] low and high boundaries for computing mean and std.dev: (%d, %d)\n", "mem_pestat", r->low, r->high);
+            say("[M::%s] (25, 50, 75) percentile: (%d, %d, %d)\n", "mem_pestat", p25, p50, p75);
+            say("[M::%s] low and high boundaries for computing mean and std.dev: (%d, %d)\n", "mem_pestat", r->low, r->high);
         }
         for (i = 0, x = 0, r->avg = 0; i < n; ++i)
             if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) r->avg += q[i], ++x;
@@ -500,20 +513,20 @@ void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::
         for (i = 0, r->std = 0; i < n; ++i)
             if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) r->std += (q[i] - r->avg) * (q[i] - r->avg);
         r->std = sqrt(r->std / x);
-        if (verbose >= 3) fprintf(stderr, "[M::%s] mean and std.dev: (%.2f, %.2f)\n", "mem_pestat", r->avg, r->std);
+        if (verbose >= 3) say("[M::%s] mean and std.dev: (%.2f, %.2f)\n", "mem_pestat", r->avg, r->std);
         r->low = (int)(p25 - 3.0 * (p75 - p25) + .499);
         r->high = (int)(p75 + 3.0 * (p75 - p25) + .499);
         if (r->low > r->avg - 4.0 * r->std) r->low = (int)(r->avg - 4.0 * r->std + .499);
         if (r->high < r->avg + 4.0 * r->std) r->high = (int)(r->avg + 4.0 * r->std + .499);
         if (r->low < 1) r->low = 1;
-        if (verbose >= 3) fprintf(stderr, "[M::%s] low and high boundaries for proper pairs: (%d, %d)\n", "mem_pestat", r->low, r->high);
+        if (verbose >= 3) say("[M::%s] low and high boundaries for proper pairs: (%d, %d)\n", "mem_pestat", r->low, r->high);
     }
     size_t max = 0;
     for (int d = 0; d < 4; ++d) max = max > isize[d].size() ? max : isize[d].size();
     for (int d = 0; d < 4; ++d)
         if (pes[d].failed == 0 && isize[d].size() < max * 0.05) {
             pes[d].failed = 1;
-            if (verbose >= 3) fprintf(stderr, "[M::%s] skip orientation %c%c\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
+            if (verbose >= 3) say("[M::%s] skip orientation %c%c\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
         }
 }
 
@@ -689,6 +702,7 @@ static void align_smart_pairs(const MemArgs &ma, const HostIndex &idx, BatchAlig
         aligner.align(mk.opt, sub, n_processed + (k ? (int64_t)sep[0].size() : 0), k && ma.have_pes0 ? ma.pes0 : nullptr, rk, slot);
         if (ma.verbose >= 3) {
             std::lock_guard<std::mutex> l(log_m);
+            fputs(rk.log_text.c_str(), log);
             fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", sub.n, now_sec() - ta);
         }
         if (rk.have_text) {
@@ -850,6 +864,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                     } else
                     aligner.align(ma.opt, j->batch, j->n_processed, ma.have_pes0 ? ma.pes0 : nullptr, j->res, slot);
                     j->sec_align = now_sec() - ta;
+                    if (!j->res.log_text.empty()) { std::lock_guard<std::mutex> l(log_m); fputs(j->res.log_text.c_str(), log); j->res.log_text.clear(); }
                     { std::lock_guard<std::mutex> l(res_m); t_res1 = std::max(t_res1, now_sec()); }
                     if (ma.verbose >= 3 && !smart) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] Processed %d reads in %.3f real sec\n", "mem_process_seqs", j->batch.n, j->sec_align); }
                     q_done.push(std::move(j));

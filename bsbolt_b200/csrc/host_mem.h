@@ -58,6 +58,7 @@ struct BatchResult {
     std::string rg_id;
     RawBuf text; PinArray<uint32_t> text_off; PinArray<SamStats> stats;
     double ms_text = 0;
+    std::string log_text;        // log lines of this batch (mem_pestat), printed by the pipeline as one block
 };
 
 class BatchAligner {
@@ -94,7 +95,8 @@ void sam_sort_batch(const ReadBatch &b, std::vector<std::string> &sam, std::vect
                     std::string &out, MapStats &stats);
 
 // Insert-size distribution from the per-pair candidates (dir in [0,4) or -1, insert size).
-void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::vector<int64_t> &isize, PeStat pes[4], int verbose);
+// The [M::mem_pestat] lines are appended to *log_text when given (the caller prints them under its log lock), else written to stderr.
+void estimate_pestat(const Opt &opt, const std::vector<int8_t> &dir, const std::vector<int64_t> &isize, PeStat pes[4], int verbose, std::string *log_text = nullptr);
 
 // glibc-evaluated tables shipped to the device (see MathTab in bsb_final.h)
 void build_log_table(std::vector<double> &t, int n);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Development aid (CPU only): differential fuzzing of the kernel bodies (tests/hostsim) against the compiled reference
+"""Development aid: differential fuzzing of the kernel bodies (tests/hostsim, CPU) or, with --gpu, of the product on the device against the compiled reference
 (oracle/_ref/bwa) on adversarial reads cut from the golden genome -- chimeras, repeats, overlapping and mis-oriented mates,
 heavy mutation, homopolymers, N runs -- under random option sets. Prints one line per run; exits 1 at the first difference.
 
@@ -15,6 +15,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--runs', type=int, default=20); ap.add_argument('--seed', type=int, default=1)
     ap.add_argument('--work', default='/tmp/bsb_fuzz'); ap.add_argument('--reads', type=int, default=600)
+    ap.add_argument('--first', type=int, default=0, help='first run to execute (a run is determined by seed and run number)')
+    ap.add_argument('--keep', action='store_true', help='keep ref.sam / mine.sam / logs of a differing run under --work')
+    ap.add_argument('--gpu', action='store_true', help='run the product (bsbolt_b200/bwa, the bwa-compatible binary over the C ABI) on cuda:0 instead of the CPU harness')
     a = ap.parse_args()
     os.makedirs(a.work + '/db', exist_ok=True)
     for f in os.listdir(G + '/db'):
@@ -27,7 +30,7 @@ def main():
     g = {k: ''.join(v) for k, v in g.items()}
     names = sorted(g)
     base = json.load(open(G + '/golden.json'))['launcher_args']
-    for run in range(a.runs):
+    for run in range(a.first, a.runs):
         rnd = random.Random(a.seed * 1000 + run)
 
         def locus(L):
@@ -100,7 +103,7 @@ def main():
                 extra += [opt] if vals == [None] else [opt, rnd.choice(vals)]
         argv = ['mem'] + base + extra + [a.work + '/db/BSB_ref.fa'] + fqs
         ref = subprocess.run([ROOT + '/oracle/_ref/bwa'] + argv, capture_output=True, text=True, errors='backslashreplace')
-        me = subprocess.run([ROOT + '/tests/hostsim/hostsim'] + argv, capture_output=True, text=True, errors='backslashreplace', env=dict(os.environ, BSB_HOSTSIM_SEED_V3='1'))
+        me = subprocess.run([ROOT + ('/bsbolt_b200/bwa' if a.gpu else '/tests/hostsim/hostsim')] + argv, capture_output=True, text=True, errors='backslashreplace', env=dict(os.environ, BSB_HOSTSIM_SEED_V3='1'))
         # records at the strand boundary (NM:i:4194303): the reference prints MD from memory it never wrote, i.e. arbitrary
         # bytes up to the first NUL; this build prints an empty MD. The field is masked for the comparison.
         def strip(t):
@@ -118,7 +121,11 @@ def main():
         ok = ref.returncode == 0 and me.returncode == 0 and x == y and bs(ref.stderr) == bs(me.stderr)
         print(f'run {run}: {"PE" if paired else "SE"} {len(x)} records {" ".join(extra)} -> {"identical" if ok else "DIFFERENT"}', flush=True)
         if not ok:
-            print('ref rc', ref.returncode, 'mine rc', me.returncode, me.stderr[-600:])
+            print('ref rc', ref.returncode, 'mine rc', me.returncode, 'records', len(x), len(y), 'bsstat equal', bs(ref.stderr) == bs(me.stderr), me.stderr[-300:])
+            if a.keep:
+                for nm, t in (('ref.sam', ref.stdout), ('mine.sam', me.stdout), ('ref.log', ref.stderr), ('mine.log', me.stderr)):
+                    open(f'{a.work}/{nm}', 'w').write(t)
+                print('argv:', ' '.join(argv))
             for u, v in zip(x, y):
                 if u != v:
                     print('ref :', u[:400]); print('mine:', v[:400]); break
