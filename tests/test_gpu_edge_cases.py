@@ -249,3 +249,14 @@ def test_bwa_mem_options_beyond_the_launcher(index, golden, tmp_path):
     long_fq = [os.path.join(golden.dir, 'long_se.fq')]
     both(index, golden, ['-x', 'ont2d', '-K', '100000'], long_fq, tmp_path, 'bwa_ont2d')
     both(index, golden, ['-x', 'intractg', '-5', '-K', '100000'], long_fq, tmp_path, 'bwa_intractg')
+
+
+def test_differential_fuzz_on_the_device(index, golden, tmp_path):
+    """tools/fuzz_hostsim.py --gpu: adversarial reads (chimeras, repeats, mis-oriented and overlapping mates, homopolymers, N runs)
+    under random option sets, the product binary (bsbolt_b200/bwa over the C ABI) against the compiled reference, record by
+    record and BSStat line by line. 70 runs of the same generator are logged in profiles/r01_fuzz_gpu_70_runs.log."""
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_hostsim.py'), '--gpu', '--runs', '8', '--reads', '400', '--seed', '5',
+                        '--work', str(tmp_path / 'fz')], capture_output=True, text=True, errors='backslashreplace')
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-1000:]
+    assert p.stdout.count('-> identical') == 8
