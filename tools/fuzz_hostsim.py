@@ -17,6 +17,7 @@ def main():
     ap.add_argument('--work', default='/tmp/bsb_fuzz'); ap.add_argument('--reads', type=int, default=600)
     ap.add_argument('--first', type=int, default=0, help='first run to execute (a run is determined by seed and run number)')
     ap.add_argument('--keep', action='store_true', help='keep ref.sam / mine.sam / logs of a differing run under --work')
+    ap.add_argument('--long', action='store_true', help='mix in reads of 700-1200 bp (mem_flt_chained_seeds territory) and smart pairing (-p)')
     ap.add_argument('--gpu', action='store_true', help='run the product (bsbolt_b200/bwa, the bwa-compatible binary over the C ABI) on cuda:0 instead of the CPU harness')
     a = ap.parse_args()
     os.makedirs(a.work + '/db', exist_ok=True)
@@ -30,6 +31,7 @@ def main():
     g = {k: ''.join(v) for k, v in g.items()}
     names = sorted(g)
     base = json.load(open(G + '/golden.json'))['launcher_args']
+    CAP = 1200 if a.long else 650
     for run in range(a.first, a.runs):
         rnd = random.Random(a.seed * 1000 + run)
 
@@ -67,11 +69,12 @@ def main():
             if rnd.random() < .5: s = s[::-1].translate(COMP)
             s = mutate(convert(s, rnd.randrange(2)))
             if rnd.random() < .05 and len(s) > 30: s = s[:10] + 'N' * rnd.randint(1, 12) + s[20:]
-            return s[:650] or 'A'
+            return s[:CAP] or 'A'
         paired = rnd.random() < .6
         r1, r2 = [], []
         for k in range(a.reads):
             L = rnd.choice([20, 25, 36, 50, 75, 100, 101, 125, 150, 150, 150, 200, 250, 300, 400])
+            if a.long and rnd.random() < .3: L = rnd.choice([700, 719, 720, 760, 900, 1100, 1200])
             if paired:
                 c, p, s = locus(L * 2 + rnd.choice([-L, 0, 50, 200, 400, 700]) if L * 3 < 60000 else L * 2)
                 m1, m2 = s[:L], s[-L:][::-1].translate(COMP)
@@ -81,7 +84,7 @@ def main():
                 elif o < .25: m2 = one(L)                           # unrelated mate
                 if rnd.random() < .5: m1, m2 = mutate(convert(m1, 0)), mutate(convert(m2, 1))
                 else: m1, m2 = mutate(convert(m2, 0)), mutate(convert(m1, 1))
-                m1, m2 = m1[:650] or 'A', m2[:650] or 'A'
+                m1, m2 = m1[:CAP] or 'A', m2[:CAP] or 'A'
                 r1.append((f'f{k}', m1)); r2.append((f'f{k}', m2))
             else:
                 r1.append((f'f{k}', one(L)))
@@ -94,6 +97,14 @@ def main():
                         f.write(f'@{n}\n{s}\n+\n{"".join(chr(33 + rnd.randrange(2, 41)) for _ in s)}\n')
                 fqs.append(path)
         extra = ['-K', str(rnd.choice([3000, 20000, 100000, 10000000]))]
+        if a.long and paired and rnd.random() < .3:   # smart pairing: one interleaved file, some mates dropped
+            with open(f'{a.work}/inter.fq', 'w') as f:
+                r1l, r2l = open(fqs[0]).read().split('\n'), open(fqs[1]).read().split('\n')
+                for k in range(0, len(r1l) - 3, 4):
+                    f.write('\n'.join(r1l[k:k + 4]) + '\n')
+                    if rnd.random() > .1: f.write('\n'.join(r2l[k:k + 4]) + '\n')
+            fqs = [f'{a.work}/inter.fq']
+            extra.append('-p')
         for opt, vals in (('-z', [None]), ('-M', [None]), ('-S', [None]), ('-P', [None]), ('-5', [None]), ('-a', [None]),
                           ('-k', ['10', '14', '25']), ('-c', ['5', '50']), ('-T', ['0', '30']), ('-L', ['0,0', '5,9']), ('-U', ['0', '40']),
                           ('-w', ['5', '30']), ('-d', ['20']), ('-r', ['0.8', '3']), ('-y', ['3', '0']), ('-A', ['2']), ('-B', ['2', '9']),
