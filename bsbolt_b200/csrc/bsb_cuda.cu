@@ -14,6 +14,7 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -922,6 +923,22 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 
 static const int kMaxReadLen = 1200;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one value per kernel and device, shared by the device slots that launch
+// concurrently with different batch shapes: it is only ever raised, under a lock, so that a slot with a smaller batch cannot
+// lower it between another slot's request and launch.
+template <class K>
+static void raise_dynamic_smem(K kernel, int bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, int> cur;
+    if (bytes <= 48 * 1024) return;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> l(mu);
+    int &c = cur[std::make_pair(dev, (const void *)kernel)];
+    if (bytes > c) { CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); c = bytes; }
+}
+
 void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot)
 {
     Impl &I = *im_;
@@ -1175,8 +1192,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const long z_cap = (long)max_q * (long)(max_q + 2 * (4 * opt.w) + 64);
     const int tk_smem_per_warp = (2 * (max_q + 1) * 4 + (2 * max_q + 16) * 4 + (8 * max_q + 64) + (4 * max_q + 64) + max_q + 31) & ~15;
     m.d_zbuf.ensure((size_t)tk_blocks * tk_wpb * z_cap);
-    if (tk_wpb * tk_smem_per_warp > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, tk_wpb * tk_smem_per_warp));
+    raise_dynamic_smem(k_tasks, tk_wpb * tk_smem_per_warp);
     unsigned long long used = 0;
     unsigned int n_tasks = 0;
     out.reads.resize(n);
@@ -1202,7 +1218,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                 else k_final_pe<16><<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_fin);
                 if (coop) {
                     const int hv_smem = 4 * (int)((4 * L.sw_cap + (L.sw_cap + 3) / 4) * 4);
-                    if (hv_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_final_pe_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, hv_smem));
+                    raise_dynamic_smem(k_final_pe_heavy, hv_smem);
                     k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
                     ++m.launches;
                 }

@@ -115,7 +115,9 @@ int parse_mem_args(int argc, char **argv, MemArgs &ma, std::string &err)
     std::string rg_line;
     const char *mode = nullptr;
     int c;
-    optind = 1; opterr = 0;
+    // optind = 0 makes glibc re-initialise its scanner completely: with optind = 1 it keeps a pointer into the PREVIOUS call's
+    // argv (freed by now when the caller is the Python layer), and whatever lies there is parsed as clustered option letters
+    optind = 0; opterr = 0;
     while ((c = getopt(argc, argv, "51qpaMCSPVYjuzk:c:v:s:r:t:R:A:B:O:E:U:w:L:d:T:Q:D:m:I:N:o:f:W:x:G:h:Z:y:K:X:H:l:n:e:")) >= 0) {
         if (c == 'k') opt.min_seed_len = atoi(optarg), opt0.min_seed_len = 1;
         else if (c == '1') ma.no_mt_io = true;
