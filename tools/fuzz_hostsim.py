@@ -128,7 +128,7 @@ def main():
                 if '\tNM:i:4194303\t' in l:
                     f = l.split('\t')
                     k0 = next(i for i, x in enumerate(f) if x.startswith('NM:i:'))   # the undefined bytes may hold tabs: drop
-                    k1 = next(i for i, x in enumerate(f) if x.startswith('XC:i:'))   # everything between NM and XC
+                    k1 = next(i for i, x in enumerate(f) if i > k0 and x.startswith(('XC:i:', 'AS:i:')))   # everything between NM and XC/AS
                     l = '\t'.join(f[:k0 + 1] + f[k1:])
                 out.append(l)
             return out
