@@ -196,3 +196,58 @@ def simulate_reads(names, contigs, out_prefix, n_pairs, read_len=150, paired=Tru
     for f in files:
         f.close()
     return paths, rid - first_id
+
+
+def simulate_rrbs_reads(names, contigs, out_path, n_reads, read_len=50, seed=7, lower_bound=30, upper_bound=500,
+                        site=b'CCGG', cut_offset=1, mut_rate=0.005, seq_err=0.001, cpg_meth=0.8, ch_meth=0.02, undirectional=False):
+    """Single-end reads of a reduced-representation library (BASELINE config C3): every read starts at the 5' end of
+    one strand of a restriction fragment (MspI, C^CGG) whose length lies in the size window of `bsbolt Index -rrbs`
+    (bsbolt/Index/RRBSIndex.py:103-139), so the reads pile up on a small set of start positions -- the high-duplicate,
+    short-read regime -- and fall inside the unmasked part of an RRBS database. Directional library: both strands
+    are read 5'->3' with unmethylated C -> T; `undirectional` also emits the reverse complements."""
+    rng = np.random.default_rng(seed)
+    L = read_len
+    starts = []          # (contig, forward-strand start of the read window, is_bottom_strand)
+    pat = np.frombuffer(site, dtype=np.uint8)
+    for ci, s in enumerate(contigs):
+        hit = np.ones(len(s) - len(pat) + 1, dtype=bool)
+        for k, c in enumerate(pat):
+            hit &= s[k:len(s) - len(pat) + 1 + k] == c
+        cuts = np.nonzero(hit)[0] + cut_offset
+        frag = np.diff(cuts)
+        ok = np.nonzero((frag >= max(lower_bound, L)) & (frag <= upper_bound))[0]
+        for k in ok:
+            starts.append((ci, int(cuts[k]), 0))                                   # top strand, left end of the fragment
+            starts.append((ci, int(cuts[k + 1]) + len(site) - 2 * cut_offset - L, 1))   # bottom strand, right end
+    starts = np.array(starts, dtype=np.int64)
+    pick = starts[rng.integers(0, len(starts), size=n_reads)]
+    acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    idx = np.arange(L, dtype=np.int64)
+    qual = b'?' * (L - 1) + b'>'
+    with open(out_path, 'wb') as f:
+        for ci in range(len(contigs)):
+            rows = pick[pick[:, 0] == ci]
+            if not len(rows):
+                continue
+            s = contigs[ci]
+            pos = np.clip(rows[:, 1], 0, len(s) - L)
+            m = s[pos[:, None] + idx[None, :]].copy()
+            nxt = s[np.minimum(pos[:, None] + idx[None, :] + 1, len(s) - 1)]
+            prv = s[np.maximum(pos[:, None] + idx[None, :] - 1, 0)]
+            sub = rng.random(m.shape) < (mut_rate + seq_err)
+            m[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
+            bottom = rows[:, 2] == 1
+            r = rng.random(m.shape)
+            for is_top in (True, False):
+                sel = ~bottom if is_top else bottom
+                base, conv = (ord('C'), ord('T')) if is_top else (ord('G'), ord('A'))
+                cpg = (nxt == ord('G')) if is_top else (prv == ord('C'))
+                keep = np.where(cpg, r < cpg_meth, r < ch_meth)
+                m[(m == base) & sel[:, None] & ~keep] = conv
+            m = np.where(bottom[:, None], _COMP[m[:, ::-1]], m)
+            if undirectional:
+                flip = rng.random(len(m)) < 0.5
+                m = np.where(flip[:, None], _COMP[m[:, ::-1]], m)
+            for j in range(len(m)):
+                f.write(b'@rrbs%d_%s_%d_%d\n' % (ci, names[ci].encode(), int(pos[j]), j) + m[j].tobytes() + b'\n+\n' + qual + b'\n')
+    return out_path, n_reads

@@ -64,6 +64,23 @@ def both(big, extra, fqs, tmp_path, env=None):
     return n, st
 
 
+def test_48mb_index_identical_to_bwa_index(big, tmp_path):
+    """The out-of-cache index every test of this module (and, at 250 Mb, the benchmark) aligns against is built by the
+    product's GPU builder; here the REFERENCE indexer (`oracle/_ref/bwa index -a bwtsw`, bwtindex.c:256-321) builds the
+    same database FASTA on the host and all six files must be byte-identical -- so a fault of the builder that both
+    aligners would digest the same way (N-run lrand48 fill, long contigs, SA sampling) cannot hide behind matching SAM."""
+    import hashlib
+    import shutil
+    live = str(tmp_path / 'BSB_ref.fa')
+    shutil.copy(big.db, live)
+    p = subprocess.run([BWA, 'index', '-a', 'bwtsw', live], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    for ext in ('amb', 'ann', 'pac', 'opac', 'bwt', 'sa'):
+        a = hashlib.md5(open(f'{big.db}.{ext}', 'rb').read()).hexdigest()
+        b = hashlib.md5(open(f'{live}.{ext}', 'rb').read()).hexdigest()
+        assert a == b, f'.{ext} of the GPU-built 48 Mb index differs from bwa index'
+
+
 def test_c2_pe150_directional_with_rescue(big, tmp_path):
     from bsbolt_b200 import simulate
     fqs, n = simulate.simulate_reads(big.names, big.contigs, str(tmp_path / 'pe'), 40000, seed=11, corrupt_frac=0.05)

@@ -125,3 +125,47 @@ def test_reader_variants_give_identical_batches(built, golden, tmp_path):
     assert want.count('\n') > 1000
     for name, got in outs.items():
         assert got == want, name
+
+
+def test_database_fasta_writers_match_bsbolt_index(tmp_path):
+    """`bsbolt Index` front half (whole genome, -MR bed mask, -rrbs MspI mask) on the reference's own test genome: the
+    FASTA handed to the indexer and mappable_regions.bed must be byte-identical to what the reference wrote
+    (md5s recorded by tests/golden/make_c1c3_golden.py from bsbolt/Index/{WholeGenomeIndex,RRBSIndex}.py)."""
+    import gzip
+    import hashlib
+    import json
+    import shutil
+    from bsbolt_b200 import index_db
+    g = os.path.join(ROOT, 'tests', 'golden')
+    man = json.load(open(os.path.join(g, 'c1c3.json')))
+    fa = str(tmp_path / 'BSB_test.fa')
+    with gzip.open(os.path.join(g, 'c1', 'BSB_test.fa.gz'), 'rb') as i, open(fa, 'wb') as o:
+        shutil.copyfileobj(i, o)
+    md5 = lambda p: hashlib.md5(open(p, 'rb').read()).hexdigest()
+    assert md5(index_db.write_database_fasta(fa, str(tmp_path / 'w'))) == man['db']['wgbs']['BSB_ref.fa']
+    assert md5(index_db.write_database_fasta(fa, str(tmp_path / 'm'), mappable_regions=os.path.join(g, 'c1', 'test_wgbs_masking.bed'))) == man['db']['masked']['BSB_ref.fa']
+    assert md5(index_db.write_rrbs_database_fasta(fa, str(tmp_path / 'r'))) == man['db']['rrbs']['BSB_ref.fa']
+    assert hashlib.md5(gzip.open(tmp_path / 'r' / 'mappable_regions.bed.gz', 'rb').read()).hexdigest() == man['db']['rrbs']['mappable_regions.bed']
+    # restriction-site table: IUPAC expansion and cut offsets (RRBSCutSites.py)
+    assert index_db.restriction_sites('C-CGG') == {'CCGG': 1}
+    assert index_db.restriction_sites('T-CGA,GR-CGYC') == {'TCGA': 1, 'GACGCC': 4, 'GGCGTC': 2, 'GGCGCC': 2, 'GACGTC': 2}   # values of ProcessCutSites
+    assert index_db.restriction_sites('CCWGG') == {'CCAGG': 0, 'CCTGG': 0}
+    # the one-step-per-position region walk of the reference's masking loop, on nested / out-of-order regions
+    def ref_mask(seq, regions):
+        it = iter(regions)
+        start, end = next(it)
+        out = []
+        for pos, bp in enumerate(seq):
+            if pos > end:
+                try:
+                    start, end = next(it)
+                except StopIteration:
+                    pass
+            out.append(bp if start <= pos <= end else '-')
+        return ''.join(out)
+    import random
+    rnd = random.Random(5)
+    seq = ''.join(rnd.choice('ACGT') for _ in range(300))
+    for _ in range(200):
+        regs = sorted(((rnd.randrange(-5, 300), rnd.randrange(-5, 320)) for _ in range(rnd.randrange(1, 12))), key=lambda r: r[0])
+        assert index_db.mask_outside(seq, regs) == ref_mask(seq, regs)
