@@ -16,7 +16,14 @@ with a fixed batch size -K. One "step" = one batch of --batch-pairs read pairs.
   cpu_baseline / --impl reference   the reference's own multithreaded CPU aligner (oracle/_ref/bwa, built
          from /root/reference by oracle/Makefile) on a bounded sample of the same reads, same argv
 
-python bench.py --gpus N --steps K --warmup W [--impl reference]
+Multi-GPU (--gpus N, or N ranks under torchrun): the timed run is the PRODUCT's own N-GPU run -- ONE process (rank 0),
+one FASTQ pair holding N x steps batches, read and cut into batches once, batch b aligned on device b mod N against that
+device's resident copy of the index, ONE SAM stream in input order (bsb_mem_main_multi). No collective is on the data path;
+the other torchrun ranks only join the NCCL barriers that fence the timed regions (they wait on the rendezvous store, not
+on a spinning stream, so that their cores stay free for rank 0's reader). A step = one batch per GPU; per-GPU work is fixed
+as N grows (weak scaling). The N-GPU output of a bounded sample is compared byte for byte with the one-GPU output.
+
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c5]
 """
 import argparse
 import json
@@ -51,22 +58,10 @@ def _simulate_step(args):
     return paths, n
 
 
-def prepare_workload(work, genome_mb, n_steps, batch_pairs, rank, seed0=1000, dist=None):
-    """Genome + per-step FASTQ pairs (rank-specific reads, shared genome written by rank 0 only)."""
-    from bsbolt_b200 import simulate
+def prepare_workload(work, fa, n_batches, batch_pairs, seed0=1000):
+    """one simulation job (one FASTQ pair) per batch"""
     os.makedirs(work, exist_ok=True)
-    fa = os.path.join(work, 'genome.fa')
-    if rank == 0 and not os.path.exists(fa + '.done'):
-        n_ctg = 10
-        simulate.make_genome(fa, [genome_mb * 1000000 // n_ctg] * n_ctg, seed=20240517)
-        open(fa + '.done', 'w').write('ok')
-    if dist:
-        dist.barrier()
-    jobs = []
-    for s in range(n_steps):
-        prefix = os.path.join(work, f'r{rank}_s{s}')
-        jobs.append((fa, prefix, batch_pairs, seed0 + 7919 * rank + s, s * batch_pairs * 2))
-    return fa, jobs
+    return [(fa, os.path.join(work, f'b{s}'), batch_pairs, seed0 + s, s * batch_pairs * 2) for s in range(n_batches)]
 
 
 def run_simulation(jobs, workers):
@@ -81,6 +76,28 @@ def concat(paths, dst, remove=False):
                 shutil.copyfileobj(f, o, 1 << 24)
             if remove:      # the per-step files are only needed once (keeps the scratch footprint of an 8-rank run down)
                 os.remove(p)
+
+
+def md5_file(path):
+    import hashlib
+    h = hashlib.md5()
+    with open(path, 'rb') as f:
+        for blk in iter(lambda: f.read(1 << 24), b''):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def check_index_md5(fa, db, genome_mb):
+    """The benchmark index is written by the product's GPU builder; tests/golden/bench_index_md5.json holds the md5 of
+    what the REFERENCE indexer (`bwa index -a bwtsw`) wrote for the same (seeded) genome in the build container."""
+    try:
+        want = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'bench_index_md5.json')))
+    except Exception:
+        return 'no golden md5 file'
+    if want.get('genome_mb') != genome_mb or md5_file(fa) != want['genome_fa_md5']:
+        return 'not applicable (different genome)'
+    bad = [e for e, h in want['index_md5'].items() if md5_file(f'{db}.{e}') != h]
+    return 'identical to bwa index (6 files)' if not bad else 'DIFFERS from bwa index: ' + ','.join(bad)
 
 
 class ClockSampler:
@@ -157,14 +174,66 @@ def compare_sam(ref_path, my_path):
     return {'sam_records': n, 'identical': same, 'identical_frac': same / n if n else None, 'header_identical': hdr_same}
 
 
+def sam_digest(path):
+    """(blake2 digest, bytes, records) of a SAM file without its @PG line"""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    n = recs = 0
+    with open(path, 'rb') as f:
+        for line in f:
+            if line.startswith(b'@PG'):
+                continue
+            h.update(line); n += len(line); recs += line[:1] != b'@'
+    return h.hexdigest(), n, recs
+
+
+class Ranks:
+    """torchrun ranks around a one-process multi-GPU run: rank 0 works, the others only meet it at the fences. A waiting rank
+    blocks on the rendezvous store (a socket), then joins the NCCL barrier -- no core spins while rank 0's host pipeline runs."""
+
+    def __init__(self, rank, world, local_rank):
+        self.rank, self.world, self.dist, self.n = rank, world, None, 0
+        if world > 1:
+            import datetime
+            import torch
+            import torch.distributed as dist
+            backend = os.environ.get('BSB_BENCH_BACKEND', 'nccl')   # gloo: the CPU test of this class (tests/test_sharding_gloo.py)
+            if backend == 'nccl':
+                torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, timeout=datetime.timedelta(hours=2))
+            self.dist = dist
+            self.store = dist.distributed_c10d._get_default_store()
+
+    def fence(self):
+        if not self.dist:
+            return
+        key = f'bsb_fence_{self.n}'
+        self.n += 1
+        if self.rank == 0:
+            self.store.set(key, '1')
+        else:
+            import datetime
+            self.store.wait([key], datetime.timedelta(hours=2))
+        self.dist.barrier()
+
+    def close(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+N_FENCES = 8   # fences rank 0 passes in the B200 arm (b200_arm: 2 x 3 timed regions + 2); the waiting ranks pass the same number
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=32)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='c2', choices=['c2', 'c5'], help='c2: directional PE150 (headline); c5: undirectional library, 5 %% corrupted mates (mate rescue)')
     ap.add_argument('--genome-mb', type=int, default=250)
-    ap.add_argument('--batch-pairs', type=int, default=266666, help='read pairs per step (= -K 80 Mbp)')
+    ap.add_argument('--batch-pairs', type=int, default=266666, help='read pairs per batch (= -K 80 Mbp)')
     ap.add_argument('--cpu-sample-pairs', type=int, default=100000)
     ap.add_argument('--work', default=os.environ.get('BSB_BENCH_WORK', '/tmp/bsb_bench'))
     ap.add_argument('--keep', action='store_true')
@@ -173,135 +242,198 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     W, K = max(a.warmup, 0), max(a.steps, 1)
-    dist = None
-    if world > 1 and a.impl == 'b200':
-        import torch
-        import torch.distributed as dist_
-        torch.cuda.set_device(local_rank)
-        dist_.init_process_group('nccl')
-        dist = dist_
     if a.impl == 'reference' and rank != 0:
         return 0
+    n_dev = world if world > 1 else max(1, a.gpus)
     cores = os.cpu_count() or 1
-    work = os.path.join(a.work, f'g{a.genome_mb}')
+    c5 = a.config == 'c5'
+    if c5:
+        os.environ['BSB_SIM_UNDIRECTIONAL'] = '1'
+        os.environ.setdefault('BSB_SIM_CORRUPT', '0.05')
+    work = os.path.join(a.work, f'g{a.genome_mb}{a.config}')
     K_bases = a.batch_pairs * 300
-    config = {'workload': f'WGBS PE150 directional, {a.genome_mb} Mb synthetic genome (10 contigs), seeded simulator; '
-                          f'{a.batch_pairs} pairs per step (-K {K_bases}); index + batch working set >> 126 MB L2 (no flush needed)',
-              'genome_mb': a.genome_mb, 'read_len': 150, 'paired': True, 'batch_pairs': a.batch_pairs,
-              'align_args': ' '.join(LAUNCHER_ARGS + ['-K', str(K_bases)])}
-
-    # ---------------- workload ----------------
-    t0 = time.time()
-    fa, jobs = prepare_workload(work, a.genome_mb, W + K, a.batch_pairs, rank, dist=dist)
-    sim_workers = max(1, min(len(jobs), cores // max(world, 1), 8))
-    sims = run_simulation(jobs, sim_workers)
-    t_sim = time.time() - t0
-    warm = [p for (paths, n) in sims[:W] for p in paths]
-    timed_pairs = sum(n for (_, n) in sims[W:])
-    f1 = os.path.join(work, f'r{rank}_timed_1.fq'); f2 = os.path.join(work, f'r{rank}_timed_2.fq')
-    w1 = os.path.join(work, f'r{rank}_warm_1.fq'); w2 = os.path.join(work, f'r{rank}_warm_2.fq')
-    if a.impl != 'reference':             # (the reference arm samples every step's own file)
-        concat([paths[0] for (paths, n) in sims[W:]], f1, remove=True)
-        concat([paths[1] for (paths, n) in sims[W:]], f2, remove=True)
-        if W:
-            concat(warm[0::2], w1, remove=True); concat(warm[1::2], w2, remove=True)
-
-    def cleanup():
-        if not a.keep:
-            for f in [f1, f2, w1, w2] + [p for (paths, n) in sims for p in paths]:
-                if os.path.exists(f):
-                    os.remove(f)
-    n_reads_timed = 2 * timed_pairs
-
+    extra_args = ['-z'] if c5 else []
+    lib = 'undirectional (-UN), 5 % of the second mates corrupted (mate rescue)' if c5 else 'directional'
+    config = {'workload': f'WGBS PE150 {lib}, {a.genome_mb} Mb synthetic genome (10 contigs), seeded simulator; '
+                          f'{a.batch_pairs} pairs per batch (-K {K_bases}), one batch per GPU per step; index + batch working set >> 126 MB L2 (no flush needed)',
+              'name': a.config, 'genome_mb': a.genome_mb, 'read_len': 150, 'paired': True, 'batch_pairs': a.batch_pairs,
+              'align_args': ' '.join(LAUNCHER_ARGS + extra_args + ['-K', str(K_bases)])}
     bwa = os.path.join(ROOT, 'oracle', '_ref', 'bwa')
-    db = os.path.join(work, 'db', 'BSB_ref.fa')
+    db = os.path.join(a.work, f'g{a.genome_mb}', 'db', 'BSB_ref.fa')   # the index does not depend on the read library
 
     if a.impl == 'reference':
-        # the reference arm: the reference's own CPU implementation on all host threads, bounded sample per step
-        if not os.path.exists(bwa):
-            print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/bwa is not built (no /root/reference here and no prebuilt copy)'}))
-            return 0
-        if not os.path.exists(db + '.bwt'):
-            # the reference needs an index; it is built by the product's GPU builder when a device exists,
-            # otherwise by the reference indexer itself
-            try:
-                from bsbolt_b200 import index_db
-                index_db.build_database(fa, os.path.join(work, 'db'))
-            except Exception:
-                os.makedirs(os.path.join(work, 'db'), exist_ok=True)
-                shutil.copy(fa, db)
-                sh([bwa, 'index', '-a', 'bwtsw', db])
-        # bounded sample per step: about two minutes of host-core work over the whole --steps/--warmup run
-        sp = min(a.cpu_sample_pairs, a.batch_pairs, max(10000, 4000000 // (W + K)))
-        rates, secs = [], []
-        for s in range(W + K):
-            paths = sims[s][0]
-            s1 = os.path.join(work, 'ref_s1.fq'); s2 = os.path.join(work, 'ref_s2.fq')
-            for src, dst in zip(paths, (s1, s2)):
-                head_records(src, dst, sp)
-            r, sec = reference_cpu_run(bwa, ['-K', str(K_bases), db, s1, s2], 2 * sp, cores)
-            if s >= W:
-                rates.append(r); secs.append(sec)
-        total_reads = 2 * sp * K
-        val = total_reads / sum(secs)
-        line = {'metric': 'paired-end 150bp WGBS reads aligned/sec', 'value': val, 'unit': 'reads/s', 'n_gpus': a.gpus, 'steps': K,
-                'warmup': W, 'ms_per_step': 1000 * sum(secs) / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'int32', 'data': 'synthetic', 'impl': 'reference', 'config': config,
-                'cpu_baseline': {'value': val, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference',
-                                 'sample': f'{sp} pairs per step of the same simulated reads, bwa mem -t {cores}, clock from first batch read to exit'},
-                'e2e': {'value': val, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
-        cleanup()
-        return 0
+        return reference_arm(a, W, K, work, db, bwa, cores, config, K_bases, extra_args)
 
-    # ---------------- B200 arm ----------------
+    ranks = Ranks(rank, world, local_rank)
+    if rank != 0:           # rank 0 drives every GPU; this rank's cores stay free for its reader
+        for _ in range(N_FENCES):
+            ranks.fence()
+        ranks.close()
+        return 0
+    if world > 1:
+        os.environ['BSB_ALL_CORES'] = '1'   # the native pipeline would otherwise take 1/LOCAL_WORLD_SIZE of the cores
+    try:
+        return b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, ranks)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)         # the launcher ends the waiting ranks
+
+
+def ensure_genome(work, db_dir, genome_mb):
+    from bsbolt_b200 import simulate
+    os.makedirs(db_dir, exist_ok=True)
+    fa = os.path.join(os.path.dirname(db_dir), 'genome.fa')
+    if not os.path.exists(fa + '.done'):
+        n_ctg = 10
+        simulate.make_genome(fa, [genome_mb * 1000000 // n_ctg] * n_ctg, seed=20240517)
+        open(fa + '.done', 'w').write('ok')
+    return fa
+
+
+def reference_arm(a, W, K, work, db, bwa, cores, config, K_bases, extra_args):
+    """The reference's own CPU implementation (oracle/_ref/bwa mem, all host threads) on a bounded sample of every step."""
+    if not os.path.exists(bwa):
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/bwa is not built (no /root/reference here and no prebuilt copy)'}))
+        return 0
+    fa = ensure_genome(work, os.path.dirname(db), a.genome_mb)
+    jobs = prepare_workload(work, fa, W + K, a.batch_pairs)
+    # bounded sample per step: about a minute of host-core work over the whole --steps/--warmup run
+    sp = min(a.cpu_sample_pairs, a.batch_pairs, max(10000, 4000000 // (W + K)))
+    jobs = [(f, pre, sp, seed, first) for (f, pre, n, seed, first) in jobs]     # the first sp pairs of each step's reads
+    sims = run_simulation(jobs, max(1, min(len(jobs), cores - 1, 16)))
+    index_note = None
+    if not os.path.exists(db + '.sa'):
+        # The reference needs an index. `bwa index` takes 10.5 min on this genome, so the files come from the GPU builder --
+        # run as a separate executable (bsbolt_b200/bwa index), nothing of the product is loaded into this process -- and are
+        # accepted only if their md5 equals what the reference indexer wrote for the same genome (tests/golden/bench_index_md5.json)
+        from bsbolt_b200 import index_db
+        index_db.write_database_fasta(fa, os.path.dirname(db))
+        p = sh([os.path.join(ROOT, 'bsbolt_b200', 'bwa'), 'index', '-a', 'bwtsw', db])
+        if p.returncode != 0:
+            sh([bwa, 'index', '-a', 'bwtsw', db])
+            index_note = 'built by the reference indexer (no GPU builder available)'
+    index_note = index_note or check_index_md5(fa, db, a.genome_mb)
+
+    def cat(steps, dst):
+        for k in (0, 1):
+            concat([sims[s][0][k] for s in steps], f'{dst}_{k + 1}.fq')
+        return [f'{dst}_1.fq', f'{dst}_2.fq']
+    tail = extra_args + ['-K', str(K_bases), db]
+    if W:   # warm-up steps: page cache, index in memory
+        reference_cpu_run(bwa, tail + cat(range(W), os.path.join(work, 'ref_warm')), 2 * sp * W, cores)
+    # the K timed steps as ONE run, so that the reference's own pipeline (read || align || write, fastmap.c:352) overlaps as it does in production
+    val, sec = reference_cpu_run(bwa, tail + cat(range(W, W + K), os.path.join(work, 'ref_timed')), 2 * sp * K, cores)
+    line = {'metric': 'paired-end 150bp WGBS reads aligned/sec', 'value': val, 'unit': 'reads/s', 'n_gpus': a.gpus, 'steps': K,
+            'warmup': W, 'ms_per_step': 1000 * sec / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'int32', 'data': 'synthetic', 'impl': 'reference', 'config': config,
+            'cpu_baseline': {'value': val, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference',
+                             'sample': f'{sp} pairs per step of the same simulated reads, {K} steps in one run of oracle/_ref/bwa mem -t {cores}, '
+                                       f'{sec:.1f} s, clock from first batch read to exit'},
+            'e2e': {'value': val, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'index': index_note}
+    print(json.dumps(line))
+    if not a.keep:
+        for f in [p for (paths, n) in sims for p in paths] + [os.path.join(work, f'ref_{w}_{k}.fq') for w in ('warm', 'timed') for k in (1, 2)]:
+            if os.path.exists(f):
+                os.remove(f)
+    return 0
+
+
+def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, ranks):
     from bsbolt_b200 import _native, index_db
-    device = local_rank if world > 1 else 0
+    devices = list(range(n_dev))
+    # ---------------- workload: ONE input of n_dev x (W + K) batches ----------------
     t0 = time.time()
-    if rank == 0 and not os.path.exists(db + '.sa'):
-        index_db.build_database(fa, os.path.join(work, 'db'), device=device)
-    if dist:
-        dist.barrier()
+    fa = ensure_genome(work, os.path.dirname(db), a.genome_mb)
+    jobs = prepare_workload(work, fa, n_dev * (W + K), a.batch_pairs)
+    sims = run_simulation(jobs, max(1, min(len(jobs), cores - 2, 28)))
+    t_sim = time.time() - t0
+    nw = n_dev * W
+    timed_pairs = sum(n for (_, n) in sims[nw:])
+    f1 = os.path.join(work, 'timed_1.fq'); f2 = os.path.join(work, 'timed_2.fq')
+    w1 = os.path.join(work, 'warm_1.fq'); w2 = os.path.join(work, 'warm_2.fq')
+    concat([paths[0] for (paths, n) in sims[nw:]], f1, remove=True)
+    concat([paths[1] for (paths, n) in sims[nw:]], f2, remove=True)
+    if W:
+        concat([paths[0] for (paths, n) in sims[:nw]], w1, remove=True); concat([paths[1] for (paths, n) in sims[:nw]], w2, remove=True)
+    scratch = [f1, f2, w1, w2]
+    n_reads_timed = 2 * timed_pairs
+
+    t0 = time.time()
+    if not os.path.exists(db + '.sa'):
+        index_db.build_database(fa, os.path.dirname(db), device=0)
     t_index = time.time() - t0
-    idx = _native.Index(db, device)
-    argv_common = ['mem'] + LAUNCHER_ARGS + ['-t', '1', '-K', str(K_bases), '-v', '1']
+    index_note = check_index_md5(fa, db, a.genome_mb)
+    idx = _native.MultiIndex(db, devices) if n_dev > 1 else _native.Index(db, 0)
+    argv_common = ['mem'] + LAUNCHER_ARGS + extra_args + ['-t', '1', '-K', str(K_bases), '-v', '1']
     null = os.open(os.devnull, os.O_WRONLY)
+
+    def mem(argv, out_fd):
+        if n_dev > 1:
+            return _native.mem_main_multi(argv, idx, out_fd=out_fd, log_fd=null)
+        return _native.mem_main(argv, index=idx, out_fd=out_fd, log_fd=null)
 
     def run(fq1, fq2, env=None):
         for k, v in (env or {}).items():
             os.environ[k] = v
         try:
             t = time.time()
-            rc, st = _native.mem_main(argv_common + [db, fq1, fq2], index=idx, out_fd=null, log_fd=null)
+            rc, st = mem(argv_common + [db, fq1, fq2], null)
         finally:
             for k in (env or {}):
                 del os.environ[k]
         if rc:
             raise RuntimeError(_native.last_error())
         return time.time() - t, st
-    launches0 = 0
     if W:
-        launches0 = run(w1, w2)[1]['kernel_launches']
-    import torch  # only for the device synchronisation / rank reduction the bench contract asks for
+        run(w1, w2)
+    import torch  # only for the device synchronisation the bench contract asks for (and the NCCL fences under torchrun)
+
+    def sync():
+        for d in devices:
+            torch.cuda.synchronize(d)
 
     def fenced(fn):
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize(device)
+        ranks.fence(); sync()
         r = fn()
-        torch.cuda.synchronize(device)
-        if dist:
-            dist.barrier()
+        sync(); ranks.fence()
         return r
-    sampler = ClockSampler(device)
+    sampler = ClockSampler(devices)
     sampler.start()
     wall, st = fenced(lambda: run(f1, f2))                                                  # e2e: host files -> SAM
     _, st_res = fenced(lambda: run(f1, f2, {'BSB_RESIDENT_BENCH': '1'}))                     # value: inputs resident
     clocks = sampler.stop()
     _, st_one = fenced(lambda: run(f1, f2, {'BSB_RESIDENT_BENCH': '1', 'BSB_GPU_SLOTS': '1'}))  # clean per-kernel times
-    # the reference's default output (`-O prefix`: bwa mem | stream_bam): FASTQ files -> BAM file, on the first 4 steps' reads
+    ranks.fence()
+    # ---- the N-GPU output against the one-GPU output of the same input (bounded sample, smaller batches) ----
+    multi_identity = None
+    if n_dev > 1:
+        sp = 40000
+        nb = 2 * n_dev
+        m1 = os.path.join(work, 'mg_1.fq'); m2 = os.path.join(work, 'mg_2.fq')
+        head_records(f1, m1, sp * nb); head_records(f2, m2, sp * nb)
+        argv = ['mem'] + LAUNCHER_ARGS + extra_args + ['-t', '1', '-K', str(sp * 300), '-v', '1', db, m1, m2]
+        outs = []
+        for tag in ('one', 'multi'):
+            path = os.path.join(work, f'mg_{tag}.sam')
+            fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            if tag == 'one':
+                rc, st_m = _native.mem_main(argv, index=idx.parts[0], out_fd=fd, log_fd=null)
+            else:
+                rc, st_m = _native.mem_main_multi(argv, idx, out_fd=fd, log_fd=null)
+            os.close(fd)
+            if rc:
+                raise RuntimeError(_native.last_error())
+            outs.append(sam_digest(path) + (st_m['n_batches'],))
+            scratch.append(path)
+        scratch += [m1, m2]
+        multi_identity = {'batches': outs[1][3], 'sam_bytes': outs[1][1], 'records': outs[1][2],
+                          'identical_to_one_gpu_output': outs[0][:3] == outs[1][:3]}
+    # the reference's default output (`-O prefix`: bwa mem | stream_bam): FASTQ files -> BAM file, on the first 4 batches' reads
     bam_info = None
-    if world == 1:
+    if n_dev == 1:
         nb = min(4, K) * a.batch_pairs
         b1 = os.path.join(work, 'bam_1.fq'); b2 = os.path.join(work, 'bam_2.fq'); bam_path = os.path.join(work, 'bench_out.bam')
         head_records(f1, b1, nb); head_records(f2, b2, nb)
@@ -313,31 +445,13 @@ def main():
                 raise RuntimeError(_native.last_error())
             bam_info = bam_info or {'api': 'bsb_mem_main_bam (FASTQ files on host -> BGZF/BAM file)', 'reads': 2 * nb, 'unit': 'reads/s'}
             bam_info['zlib_default' if level < 0 else f'zlib_level_{level}'] = {'value': 2 * nb / dt, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path)}
-        os.remove(bam_path)
+        scratch += [b1, b2, bam_path]
     ms_resident, ms_total_wall = st_res['sec_resident'] * 1000, wall * 1000
     ms_one = st_one['sec_resident'] * 1000
-    reads_all = n_reads_timed
-    per_rank = None
-    if dist:
-        mine = torch.tensor([ms_resident, ms_total_wall, ms_one], device=f'cuda:{device}', dtype=torch.float64)
-        every = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(every, mine)
-        per_rank = {'ms_resident': [round(float(x[0]), 1) for x in every], 'ms_e2e_wall': [round(float(x[1]), 1) for x in every]}
-        t = torch.tensor([ms_resident, ms_total_wall, ms_one], device=f'cuda:{device}', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_resident, ms_total_wall, ms_one = float(t[0]), float(t[1]), float(t[2])
-        c = torch.tensor([n_reads_timed], device=f'cuda:{device}', dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        reads_all = float(c[0])
-    if dist:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        cleanup()
-        return 0
     n_batches = max(1, st['n_batches'])
-    value = reads_all / (ms_resident / 1000)
-    e2e = reads_all / (ms_total_wall / 1000)
+    steps = n_batches / n_dev
+    value = n_reads_timed / (ms_resident / 1000)
+    e2e = n_reads_timed / (ms_total_wall / 1000)
     seed_ms = st_one['ms_stage'][2] / n_batches
     reads_per_launch = n_reads_timed / n_batches
     peaks = {}
@@ -358,44 +472,52 @@ def main():
         pass
     cpu = None
     parity = None
-    if os.path.exists(bwa) and world == 1:
+    if os.path.exists(bwa) and n_dev == 1:
         sp = min(a.cpu_sample_pairs, a.batch_pairs)
         s1 = os.path.join(work, 'cpu_s1.fq'); s2 = os.path.join(work, 'cpu_s2.fq')
         ref_sam = os.path.join(work, 'cpu_ref.sam'); my_sam = os.path.join(work, 'cpu_mine.sam')
+        scratch += [s1, s2, ref_sam, my_sam]
         for src, dst in ((f1, s1), (f2, s2)):
             head_records(src, dst, sp)
         try:
-            r, sec = reference_cpu_run(bwa, ['-K', str(K_bases), db, s1, s2], 2 * sp, cores, sam_out=ref_sam)
+            r, sec = reference_cpu_run(bwa, extra_args + ['-K', str(K_bases), db, s1, s2], 2 * sp, cores, sam_out=ref_sam)
             cpu = {'value': r, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference',
                    'sample': f'first {sp} pairs of the timed reads, oracle/_ref/bwa mem -t {cores}, {sec:.1f} s, clock from first batch read to exit'}
             # the same sample through the product (untimed): record-level identity with the reference's SAM
             fd = os.open(my_sam, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
-            rc, _ = _native.mem_main(argv_common + [db, s1, s2], index=idx, out_fd=fd, log_fd=null)
+            rc, _ = mem(argv_common + [db, s1, s2], fd)
             os.close(fd)
             if rc == 0:
                 parity = compare_sam(ref_sam, my_sam)
         except Exception as e:  # noqa
             cpu = cpu or {'value': None, 'unit': 'reads/s', 'cores': cores, 'kind': 'reference', 'sample': f'failed: {e}'}
-    line = {'metric': 'paired-end 150bp WGBS reads aligned/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': a.gpus, 'steps': n_batches,
-            'warmup': W, 'ms_per_step': ms_resident / n_batches, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+    ranks.fence()
+    ranks.close()
+    line = {'metric': 'paired-end 150bp WGBS reads aligned/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': n_dev, 'steps': steps,
+            'warmup': W, 'ms_per_step': ms_resident / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'int32', 'data': 'synthetic', 'config': config, 'clocks': clocks,
-            'e2e': {'value': e2e, 'unit': 'reads/s', 'h2d_bytes_per_step': st['h2d_bytes'] // n_batches, 'd2h_bytes_per_step': st['d2h_bytes'] // n_batches,
-                    'api': 'bsb_mem_main (FASTQ files on host -> SAM text to /dev/null)', 'wall_s': wall},
-            'gpu_launches': st['kernel_launches'] - launches0, 'batches_in_flight_per_gpu': int(os.environ.get('BSB_GPU_SLOTS', '3')),
-            'value_one_batch_in_flight': reads_all / (ms_one / 1000),
+            'e2e': {'value': e2e, 'unit': 'reads/s', 'h2d_bytes_per_step': int(st['h2d_bytes'] / steps), 'd2h_bytes_per_step': int(st['d2h_bytes'] / steps),
+                    'api': ('bsb_mem_main_multi' if n_dev > 1 else 'bsb_mem_main') + ' (one FASTQ pair on the host -> one SAM stream to /dev/null)', 'wall_s': wall},
+            'gpu_launches': st['kernel_launches'], 'batches_in_flight_per_gpu': int(os.environ.get('BSB_GPU_SLOTS', '3')),
+            'multi_gpu': {'processes': 1, 'readers': 1, 'devices': n_dev, 'batches': n_batches, 'assignment': 'batch b -> device b mod N', 'collectives_on_data_path': 0,
+                          'identity': multi_identity} if n_dev > 1 else None,
+            'value_one_batch_in_flight': n_reads_timed / (ms_one / 1000),
             'roofline': {'bound': 'hbm', 'kernel': 'k_seed3 (+ k_pack4, k_seed3_finish: SMEM seeding stage)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                          'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms,
                          'reads_per_launch': reads_per_launch, **layout},
-            'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info, 'per_rank': per_rank, 'host_cores': cores,
-            'stage_ms_per_step': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
-            'final_split_ms_per_step': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},
-            'stage_note': 'CUDA-event stage times of the run with ONE batch in flight (with several in flight the stages of different batches overlap)',
-            'host_busy_s': {'read': st['sec_read'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_thread': st['sec_align']},
-            'setup_s': {'simulate': t_sim, 'index_build_or_wait': t_index}, 'index_hbm_bytes': idx.hbm_bytes}
+            'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info, 'host_cores': cores, 'index': index_note,
+            'stage_ms_per_batch': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
+            'final_split_ms_per_batch': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},
+            'stage_note': 'CUDA-event stage times of the run with ONE batch in flight per GPU (with several in flight the stages of different batches overlap)',
+            'host_busy_s': {'read': st['sec_read'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_threads': st['sec_align']},
+            'setup_s': {'simulate': t_sim, 'index_build': t_index}, 'index_hbm_bytes_per_gpu': idx.hbm_bytes}
     print(json.dumps(line))
     os.close(null)
-    cleanup()
+    if not a.keep:
+        for f in scratch:
+            if os.path.exists(f):
+                os.remove(f)
     return 0
 
 

@@ -7,7 +7,7 @@ their formats, so anything that consumed the reference's streams keeps working.
 """
 import os
 import sys
-import tempfile
+import threading
 from typing import List
 
 from bsbolt_b200 import _native
@@ -59,61 +59,59 @@ class BisulfiteAlignmentAndProcessing:
         if not argv or argv[0] != 'mem':
             raise BisulfiteAlignmentError('alignment_commands must be [bwa, "mem", ...]')
         sys.stdout.flush()
-        if isinstance(self.device, (list, tuple)) and len(self.device) > 1:
-            return self._align_multi_gpu(argv)
-        if isinstance(self.device, (list, tuple)):
-            self.device = self.device[0]
-        with tempfile.TemporaryFile(mode='w+') as log:
+        devices = list(self.device) if isinstance(self.device, (list, tuple)) else [self.device]
+        multi = None
+        if len(devices) > 1:
+            # several GPUs, ONE process: the input is read and cut into batches once, batch b runs on device b mod G against
+            # that device's resident copy of the index, records leave in input order (bsb_mem_main_multi); no temp files
+            multi = self.index if isinstance(self.index, _native.MultiIndex) else _native.MultiIndex(self._idxbase(argv), devices)
+        # the aligner's log is consumed line by line while it runs, like the reference reads bwa's stderr
+        # (AlignReads.py:61-78): progress and per-batch BSStat counters appear as the batches finish
+        rd, wr = os.pipe()
+        reader = threading.Thread(target=self._consume_log, args=(os.fdopen(rd, 'r', errors='replace'),), daemon=True)
+        reader.start()
+        try:
             if self.output_to_stdout:
-                rc, stats = _native.mem_main(argv, index=self.index, device=self.device, out_fd=1, log_fd=log.fileno())
+                if multi is not None:
+                    rc, stats = _native.mem_main_multi(argv, multi, out_fd=1, log_fd=wr)
+                else:
+                    rc, stats = _native.mem_main(argv, index=self.index, device=devices[0], out_fd=1, log_fd=wr)
             else:
                 from bsbolt_b200.Utils.BamOutput import sam_stream_to_bam
-                rc, stats = sam_stream_to_bam(argv, f'{self.output}.bam', self.output_threads, log.fileno(),
-                                              index=self.index, device=self.device)
-            log.seek(0)
-            for alignment_info in log:
+                rc, stats = sam_stream_to_bam(argv, f'{self.output}.bam', self.output_threads, wr,
+                                              index=multi if multi is not None else self.index, device=devices[0])
+        finally:
+            os.close(wr)
+            reader.join()
+            if multi is not None and multi is not self.index:
+                multi.close()
+        self.run_statistics = stats
+        if rc:
+            print(rc, file=sys.stderr)
+            raise BisulfiteAlignmentError(_native.last_error())
+
+    @staticmethod
+    def _idxbase(argv):
+        """the index prefix in a `bwa mem` argv: the first positional argument (options as in fastmap.c:113-190)"""
+        flags = set('51qpaMCSPVYjuz')   # the options of `bwa mem` that take no value (getopt string of main_mem)
+        i = 1
+        while i < len(argv):
+            a = argv[i]
+            if a.startswith('-') and len(a) > 1:
+                k = 1
+                while k < len(a) and a[k] in flags:   # bundled flags, e.g. -MY
+                    k += 1
+                i += 1 if (k == len(a) or k + 1 < len(a)) else 2   # a value glued to its option (-k19) or the next word
+            else:
+                return a
+        raise BisulfiteAlignmentError('no index in the alignment command')
+
+    def _consume_log(self, lines):
+        with lines:
+            for alignment_info in lines:
                 if alignment_info[0:7] == 'BSStat ':
                     category, count = alignment_info.replace('BSStat ', '').split(': ')
                     self.mapping_statistics[category] += int(count)
                     print(alignment_info.replace('BSStat ', '').strip(), file=sys.stderr)
                 else:
                     print(alignment_info.strip(), file=sys.stderr)
-        self.run_statistics = stats
-        if rc:
-            print(rc, file=sys.stderr)
-            raise BisulfiteAlignmentError(_native.last_error())
-
-    def _consume_log(self, lines):
-        for alignment_info in lines:
-            if alignment_info[0:7] == 'BSStat ':
-                category, count = alignment_info.replace('BSStat ', '').split(': ')
-                self.mapping_statistics[category] += int(count)
-                print(alignment_info.replace('BSStat ', '').strip(), file=sys.stderr)
-            else:
-                print(alignment_info.strip(), file=sys.stderr)
-
-    def _align_multi_gpu(self, argv):
-        """One worker process per GPU; batch b is aligned on GPU b mod G; parts merged in input order."""
-        import subprocess
-        from bsbolt_b200.shard import merge_shards
-        devices = list(self.device)
-        with tempfile.TemporaryDirectory() as d:
-            procs = []
-            for i, dev in enumerate(devices):
-                cmd = [sys.executable, '-m', 'bsbolt_b200._shard_worker', str(dev), str(i), str(len(devices)),
-                       f'{d}/p{i}.sam', f'{d}/p{i}.idx', f'{d}/p{i}.log', '--'] + argv
-                procs.append(subprocess.Popen(cmd))
-            rcs = [p.wait() for p in procs]
-            for i in range(len(devices)):
-                self._consume_log(open(f'{d}/p{i}.log'))
-            if any(rcs):
-                raise BisulfiteAlignmentError(f'shard worker failed: {rcs}')
-            sams, parts = [f'{d}/p{i}.sam' for i in range(len(devices))], [f'{d}/p{i}.idx' for i in range(len(devices))]
-            if self.output_to_stdout:
-                merge_shards(sams, parts, sys.stdout.buffer)
-                sys.stdout.buffer.flush()
-            else:
-                from bsbolt_b200.Utils.BamOutput import sam_file_to_bam
-                with open(f'{d}/merged.sam', 'wb') as o:
-                    merge_shards(sams, parts, o)
-                sam_file_to_bam(f'{d}/merged.sam', f'{self.output}.bam', self.output_threads)

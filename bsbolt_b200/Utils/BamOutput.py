@@ -34,4 +34,6 @@ def sam_file_to_bam(sam_path, bam_path, threads=1):
 
 def sam_stream_to_bam(argv, bam_path, threads, log_fd, index=None, device=0):
     """Run the aligner with its records written as BAM (no SAM text leaves the library)."""
+    if isinstance(index, _native.MultiIndex):
+        return _native.mem_main_multi_bam(argv, bam_path, index, threads=_threads(threads), level=_level(), log_fd=log_fd)
     return _native.mem_main_bam(argv, bam_path, index=index, device=device, threads=_threads(threads), level=_level(), log_fd=log_fd)

@@ -34,7 +34,7 @@ class Read(C.Structure):
 EXPORTS = ('bsb_version', 'bsb_last_error', 'bsb_device_count', 'bsb_index_load', 'bsb_index_free',
            'bsb_index_hbm_bytes', 'bsb_index_n_contigs', 'bsb_mem_main', 'bsb_batch_create', 'bsb_batch_align',
            'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header', 'bsb_index_build',
-           'bsb_mem_main_bam', 'bsb_stream_bam')
+           'bsb_mem_main_bam', 'bsb_stream_bam', 'bsb_index_clone', 'bsb_mem_main_multi', 'bsb_mem_main_multi_bam')
 
 
 def lib():
@@ -52,6 +52,11 @@ def lib():
     L.bsb_index_load.restype = C.c_void_p
     L.bsb_index_load.argtypes = [C.c_char_p, C.c_int]
     L.bsb_index_free.argtypes = [C.c_void_p]
+    L.bsb_index_clone.restype = C.c_void_p
+    L.bsb_index_clone.argtypes = [C.c_void_p, C.c_int]
+    L.bsb_mem_main_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(RunStats)]
+    L.bsb_mem_main_multi_bam.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(RunStats)]
     L.bsb_index_hbm_bytes.restype = C.c_int64
     L.bsb_index_hbm_bytes.argtypes = [C.c_void_p]
     L.bsb_index_n_contigs.argtypes = [C.c_void_p]
@@ -84,11 +89,18 @@ def _argv(args):
 class Index:
     """Index of `bsbolt Index` resident in one GPU's HBM."""
 
-    def __init__(self, idxbase, device=0):
-        self._h = lib().bsb_index_load(str(idxbase).encode(), int(device))
+    def __init__(self, idxbase, device=0, _handle=None):
+        self._h = _handle if _handle is not None else lib().bsb_index_load(str(idxbase).encode(), int(device))
         if not self._h:
             raise RuntimeError(last_error())
         self.device = device
+
+    def clone(self, device):
+        """One more resident copy of this index, on another device (host-side tables shared)."""
+        h = lib().bsb_index_clone(self._h, int(device))
+        if not h:
+            raise RuntimeError(last_error())
+        return Index(None, device, _handle=h)
 
     @property
     def hbm_bytes(self):
@@ -129,6 +141,45 @@ def mem_main_bam(argv, bam_path, index=None, device=0, threads=0, level=-1, log_
     arr = _argv(argv)
     rc = lib().bsb_mem_main_bam(index._h if index is not None else None, int(device), len(argv), arr, str(bam_path).encode(),
                                 int(threads), int(level), int(log_fd), C.byref(st))
+    return rc, st.as_dict()
+
+
+class MultiIndex:
+    """The same index resident on several GPUs of one box: reads shard by batch, the index is replicated, no collective."""
+
+    def __init__(self, idxbase, devices):
+        devices = [int(d) for d in devices]
+        if not devices:
+            raise ValueError('MultiIndex needs at least one device')
+        self.parts = [Index(idxbase, devices[0])]
+        for d in devices[1:]:
+            self.parts.append(self.parts[0].clone(d))
+        self.devices = devices
+
+    @property
+    def hbm_bytes(self):
+        return self.parts[0].hbm_bytes
+
+    def handles(self):
+        return (C.c_void_p * len(self.parts))(*[p._h for p in self.parts])
+
+    def close(self):
+        for p in reversed(self.parts):
+            p.close()
+        self.parts = []
+
+
+def mem_main_multi(argv, multi_index, out_fd=1, log_fd=2):
+    """`bwa mem` over several GPUs: one reader, batch b on device b mod G, output in input order (bsb_mem_main_multi)."""
+    st = RunStats()
+    rc = lib().bsb_mem_main_multi(multi_index.handles(), len(multi_index.parts), len(argv), _argv(argv), int(out_fd), int(log_fd), C.byref(st))
+    return rc, st.as_dict()
+
+
+def mem_main_multi_bam(argv, bam_path, multi_index, threads=0, level=-1, log_fd=2):
+    st = RunStats()
+    rc = lib().bsb_mem_main_multi_bam(multi_index.handles(), len(multi_index.parts), len(argv), _argv(argv), str(bam_path).encode(),
+                                      int(threads), int(level), int(log_fd), C.byref(st))
     return rc, st.as_dict()
 
 

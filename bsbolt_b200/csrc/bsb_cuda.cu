@@ -886,7 +886,7 @@ CudaAligner::~CudaAligner()
 
 struct DeviceInput { DevBuf<char> bases; DevBuf<uint32_t> seq_off; DevBuf<uint8_t> pattern; };
 
-void CudaAligner::preload(ReadBatch &b)
+void CudaAligner::preload(ReadBatch &b, int)
 {
     CK(cudaSetDevice(im_->device));
     DeviceInput *d = new DeviceInput;

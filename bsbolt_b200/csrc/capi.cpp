@@ -19,7 +19,7 @@ static thread_local std::string g_err;
 static thread_local std::string g_hdr;
 
 struct bsb_index {
-    HostIndex host;
+    std::shared_ptr<HostIndex> host;   // shared by the copies of one index on several devices (bsb_index_clone)
     std::unique_ptr<CudaAligner> aligner;
     int device = 0;
 };
@@ -33,7 +33,7 @@ struct bsb_batch {
     std::string sam;
 };
 
-static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAligner *al)
+static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAligner *al, long launches = -1)
 {
     if (!s) return;
     s->total_reads = sum.stats.reads; s->total_alignments = sum.stats.alignments;
@@ -43,7 +43,7 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     s->ms_h2d = sum.ms_h2d; s->ms_kernels = sum.ms_kernels; s->ms_d2h = sum.ms_d2h;
     for (int k = 0; k < 8; ++k) s->ms_stage[k] = sum.ms_stage[k];
     s->n_seeds = (int64_t)sum.n_seeds; s->h2d_bytes = (int64_t)sum.h2d_bytes; s->d2h_bytes = (int64_t)sum.d2h_bytes;
-    s->kernel_launches = al ? al->kernel_launches() : 0;
+    s->kernel_launches = launches >= 0 ? launches : al ? al->kernel_launches() : 0;
     s->sec_read = sum.sec_read; s->sec_format = sum.sec_format; s->sec_write = sum.sec_write;
     s->ms_select = sum.ms_select; s->ms_tasks = sum.ms_tasks; s->n_tasks = (int64_t)sum.n_tasks;
     s->sec_resident = sum.sec_resident;
@@ -66,15 +66,28 @@ bsb_index_t *bsb_index_load(const char *idxbase, int device)
     try {
         std::unique_ptr<bsb_index> ix(new bsb_index);
         ix->device = device;
-        ix->host.load(idxbase);
-        ix->aligner.reset(new CudaAligner(ix->host, device));
+        ix->host.reset(new HostIndex);
+        ix->host->load(idxbase);
+        ix->aligner.reset(new CudaAligner(*ix->host, device));
+        return ix.release();
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
+bsb_index_t *bsb_index_clone(const bsb_index_t *src, int device)
+{
+    try {
+        if (!src) throw std::runtime_error("[E::bsb_index_clone] index is NULL");
+        std::unique_ptr<bsb_index> ix(new bsb_index);
+        ix->device = device;
+        ix->host = src->host;
+        ix->aligner.reset(new CudaAligner(*ix->host, device));
         return ix.release();
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 
 void bsb_index_free(bsb_index_t *idx) { delete idx; }
 int64_t bsb_index_hbm_bytes(const bsb_index_t *idx) { return idx ? (int64_t)idx->aligner->index_bytes() : 0; }
-int bsb_index_n_contigs(const bsb_index_t *idx) { return idx ? (int)idx->host.contigs.size() : 0; }
+int bsb_index_n_contigs(const bsb_index_t *idx) { return idx ? (int)idx->host->contigs.size() : 0; }
 
 static std::string make_pg(int argc, char **argv)
 {
@@ -85,14 +98,12 @@ static std::string make_pg(int argc, char **argv)
 
 static int host_thread_share()
 {
-    int n = (int)std::thread::hardware_concurrency();
-    if (const char *e = getenv("LOCAL_WORLD_SIZE")) n /= std::max(1, atoi(e));
-    if (const char *e = getenv("BSB_HOST_THREADS")) n = atoi(e);
+    const int n = host_core_share();
     return std::max(1, std::min(n - 2, 64));   // the device threads sleep on events; leave two cores to the FASTQ reader
 }
 
 static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, int out_fd, const char *bam_path, int bam_threads, int bam_level,
-                         int log_fd, bsb_run_stats_t *stats)
+                         int log_fd, bsb_run_stats_t *stats, bsb_index_t *const *more = nullptr, int n_more = 0)
 {
     FILE *out = nullptr, *log = nullptr;
     bsb_index_t *own = nullptr;
@@ -120,13 +131,28 @@ static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, in
         }
         if ((!out && !bam) || !log) throw std::runtime_error("[E::bsb_mem_main] cannot open the output streams");
         // -j (fastmap.c: bns->anns[i].is_alt = 0 for every contig): a no-op unless the database carries an .alt file
-        if (ma.ignore_alt && idx->host.any_alt)
+        if (ma.ignore_alt && idx->host->any_alt)
             throw std::runtime_error("[E::bsb_mem_main] -j on a database with ALT contigs needs an index loaded without the ALT marks; not supported with a resident index");
         idx->aligner->verbose = ma.verbose;
         RunSummary sum;
-        ret = run_mem(ma, idx->host, *idx->aligner, out, log, &sum, bam.get());
+        if (n_more > 0) {   // several devices: one reader, batches dealt round-robin, output in input order
+            std::vector<CudaAligner *> per_device(1, idx->aligner.get());
+            for (int k = 0; k < n_more; ++k) {
+                if (!more[k] || more[k]->host.get() != idx->host.get())
+                    throw std::runtime_error("[E::bsb_mem_main_multi] every index must be a bsb_index_clone of the first");
+                per_device.push_back(more[k]->aligner.get());
+            }
+            MultiAligner multi(per_device);
+            multi.set_verbose(ma.verbose);
+            const long launches0 = multi.kernel_launches();
+            ret = run_mem(ma, *idx->host, multi, out, log, &sum, bam.get());
+            if (bam) { bam->close(); sum.sec_write += bam->sec_busy(); }
+            fill_stats(stats, sum, nullptr, multi.kernel_launches() - launches0);
+        } else {
+        ret = run_mem(ma, *idx->host, *idx->aligner, out, log, &sum, bam.get());
         if (bam) { bam->close(); sum.sec_write += bam->sec_busy(); }
         fill_stats(stats, sum, idx->aligner.get());
+        }
     } catch (const std::exception &e) {
         g_err = e.what();
         if (log) fprintf(log, "%s\n", e.what());
@@ -149,6 +175,20 @@ int bsb_mem_main_bam(bsb_index_t *idx, int device, int argc, char **argv, const 
 {
     if (!bam_path) { g_err = "[E::bsb_mem_main_bam] bam_path is NULL"; return 1; }
     return mem_main_impl(idx, device, argc, argv, -1, bam_path, threads, level, log_fd, stats);
+}
+
+int bsb_mem_main_multi(bsb_index_t *const *idx, int n_idx, int argc, char **argv, int out_fd, int log_fd, bsb_run_stats_t *stats)
+{
+    if (!idx || n_idx < 1 || !idx[0]) { g_err = "[E::bsb_mem_main_multi] no index"; return 1; }
+    return mem_main_impl(idx[0], idx[0]->device, argc, argv, out_fd, nullptr, 0, -1, log_fd, stats, idx + 1, n_idx - 1);
+}
+
+int bsb_mem_main_multi_bam(bsb_index_t *const *idx, int n_idx, int argc, char **argv, const char *bam_path, int threads, int level, int log_fd,
+                           bsb_run_stats_t *stats)
+{
+    if (!idx || n_idx < 1 || !idx[0]) { g_err = "[E::bsb_mem_main_multi_bam] no index"; return 1; }
+    if (!bam_path) { g_err = "[E::bsb_mem_main_multi_bam] bam_path is NULL"; return 1; }
+    return mem_main_impl(idx[0], idx[0]->device, argc, argv, -1, bam_path, threads, level, log_fd, stats, idx + 1, n_idx - 1);
 }
 
 int64_t bsb_stream_bam(int in_fd, const char *bam_path, int threads, int level)
@@ -225,7 +265,7 @@ int bsb_batch_sam(bsb_batch_t *b, const char **sam, size_t *len, bsb_run_stats_t
         if (!b || !b->aligned) throw std::runtime_error("[E::bsb_batch_sam] batch has not been aligned");
         std::vector<std::string> lines(b->reads.n);
         std::vector<EntryStats> st(b->reads.n);
-        for (int i = 0; i < b->reads.n; ++i) format_entry(b->ma, b->idx->host, b->reads, i, b->res, lines[i], st[i]);
+        for (int i = 0; i < b->reads.n; ++i) format_entry(b->ma, *b->idx->host, b->reads, i, b->res, lines[i], st[i]);
         b->sam.clear();
         MapStats ms;
         sam_sort_batch(b->reads, lines, st, b->sam, ms);
@@ -252,7 +292,7 @@ const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv)
         std::string err;
         if (parse_mem_args(argc, argv, ma, err)) throw std::runtime_error(err);
         ma.pg_line = make_pg(argc, argv);
-        g_hdr = sam_header(idx->host, ma);
+        g_hdr = sam_header(*idx->host, ma);
         return g_hdr.c_str();
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }

@@ -742,9 +742,11 @@ static void align_smart_pairs(const MemArgs &ma, const HostIndex &idx, BatchAlig
 int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE *out, FILE *log, RunSummary *summary, BamWriter *bam)
 {
     double t0 = now_sec();
-    FastxReader r1(ma.fq1);
+    const int n_dev = std::max(1, aligner.devices());
+    const int parse_threads = host_parse_threads(n_dev);
+    FastxReader r1(ma.fq1, parse_threads);
     std::unique_ptr<FastxReader> r2;
-    if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2));
+    if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2, parse_threads));
     std::string hdr = sam_header(idx, ma);
     const int shard_count = ma.shard_count > 1 ? ma.shard_count : 1, shard_index = ma.shard_index;
     size_t out_bytes = 0;
@@ -767,16 +769,20 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     RunSummary sum;
     // formatter threads: this process's share of the cores (one process per GPU under torchrun / the shard launcher),
     // minus the reader, the parser threads and the device threads, which must never wait for a core
-    int host_threads = (int)std::thread::hardware_concurrency();
-    if (const char *e = getenv("LOCAL_WORLD_SIZE")) host_threads /= std::max(1, atoi(e));
-    else if (ma.shard_count > 1) host_threads /= ma.shard_count;
+    int host_threads = host_core_share();
+    if (ma.shard_count > 1 && !getenv("LOCAL_WORLD_SIZE")) host_threads /= ma.shard_count;
     host_threads -= 5;
     if (const char *e = getenv("BSB_HOST_THREADS")) host_threads = atoi(e);
     if (host_threads < 1) host_threads = 1;
     if (host_threads > 32) host_threads = 32;
-    int n_slots = aligner.slots();   // three batches in flight: one slot's host round trips and copies are covered by the other two
-    if (const char *e = getenv("BSB_GPU_SLOTS")) n_slots = std::max(1, std::min(aligner.slots(), atoi(e)));
-    Channel<std::unique_ptr<Job>> q_plan(2), q_read((size_t)std::max(2, n_slots)), q_free(16);
+    // three batches in flight per device: one slot's host round trips and copies are covered by the other two
+    int slots_per_dev = aligner.slots() / n_dev;
+    if (const char *e = getenv("BSB_GPU_SLOTS")) slots_per_dev = std::max(1, std::min(slots_per_dev, atoi(e)));
+    const int slot_stride = aligner.slots() / n_dev;   // slot index of device d's first context
+    const int n_slots = slots_per_dev * n_dev;
+    Channel<std::unique_ptr<Job>> q_plan(2), q_free(64);
+    std::vector<std::unique_ptr<Channel<std::unique_ptr<Job>>>> q_read;   // one per device: batch b goes to device b mod G
+    for (int d = 0; d < n_dev; ++d) q_read.emplace_back(new Channel<std::unique_ptr<Job>>((size_t)std::max(2, slots_per_dev)));
     OrderedDone q_done;
     const int n_jobs = 5 + 2 * n_slots;
     std::thread t_prefill;   // page-locks the transfer buffers of the other jobs while the first batches run
@@ -820,7 +826,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     // reader, second half: copy the batch into its flat (page-locked) arrays while the next one is being cut
     std::thread t_fill([&] {
         try {
-            const int nt = host_fill_threads();
+            const int nt = host_fill_threads(n_dev);
             std::unique_ptr<Job> j;
             while (q_plan.pop(j)) {
                 if (j->seq < 0) {
@@ -833,29 +839,37 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 fill_batch(j->plan, &r1, r2.get(), ma.copy_comment, nt, j->batch);
                 sec_fill += now_sec() - tr;
                 if (ma.verbose >= 3) { std::lock_guard<std::mutex> l(log_m); fprintf(log, "[M::%s] read %d sequences (%ld bp)...\n", "process", j->batch.n, (long)j->batch.n_bases); }
-                if (resident) { aligner.preload(j->batch); held.push_back(std::move(j)); continue; }
-                q_read.push(std::move(j));
+                const int dev = (int)(j->seq % n_dev);
+                if (resident) { aligner.preload(j->batch, dev * slot_stride); held.push_back(std::move(j)); continue; }
+                q_read[dev]->push(std::move(j));
             }
-            if (resident) {
-                t_res0 = now_sec();
-                for (auto &h : held) q_read.push(std::move(h));
+            if (resident) {   // every batch is in HBM: release them all at once, each device's in its own order
+                std::vector<std::vector<std::unique_ptr<Job>>> per_dev(n_dev);
+                for (auto &h : held) { const int d = (int)(h->seq % n_dev); per_dev[d].push_back(std::move(h)); }
                 held.clear();
+                std::vector<std::thread> rel;
+                t_res0 = now_sec();
+                for (int d = 0; d < n_dev; ++d)
+                    rel.emplace_back([&, d] { for (auto &h : per_dev[d]) q_read[d]->push(std::move(h)); });
+                for (auto &t : rel) t.join();
             }
         } catch (const std::exception &e) {
             set_fail(e.what());
             std::unique_ptr<Job> j;
             while (q_plan.pop(j)) {}
         }
-        q_read.close();
+        for (auto &q : q_read) q->close();
     });
     // one host thread per device slot: batches are taken in input order and may finish out of order
     std::vector<std::thread> t_gpu;
     for (int slot = 0; slot < n_slots; ++slot) q_done.add_producer();
-    for (int slot = 0; slot < n_slots; ++slot)
-        t_gpu.emplace_back([&, slot] {
+    for (int k = 0; k < n_slots; ++k)
+        t_gpu.emplace_back([&, k] {
+            const int dev = k / slots_per_dev, slot = dev * slot_stride + k % slots_per_dev;
+            Channel<std::unique_ptr<Job>> &mine = *q_read[dev];
             try {
                 std::unique_ptr<Job> j;
-                while (q_read.pop(j)) {
+                while (mine.pop(j)) {
                     double ta = now_sec();
                     j->res.want_text = true; j->res.rg_id = ma.rg_id;   // SAM text from the device when the aligner can produce it
                     const bool smart = (ma.opt.flag & F_SMARTPE) != 0;
@@ -875,7 +889,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 set_fail(e.what());
                 q_done.abort();
                 std::unique_ptr<Job> j;
-                while (q_read.pop(j)) {} // drain so that the reader can finish
+                while (mine.pop(j)) {} // drain so that the reader can finish
             }
             q_done.producer_done();
         });

@@ -70,9 +70,13 @@ public:
     // concurrently from different host threads.
     virtual void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot = 0) = 0;
     virtual int slots() const { return 1; }
-    // Measurement aid: uploads the inputs of `b` ahead of time (b.dev_input) so that a following align() starts with
-    // its batch already resident in device memory; unload() frees them.
-    virtual void preload(ReadBatch &) {}
+    // An aligner may drive several GPUs (index replicated, reads sharded by batch, no collective): slots
+    // [d * slots() / devices(), (d + 1) * slots() / devices()) belong to device d. The pipeline hands batch b to device
+    // b mod devices() and collects the results in input order.
+    virtual int devices() const { return 1; }
+    // Measurement aid: uploads the inputs of `b` ahead of time (b.dev_input) to the device that owns `slot`, so that a
+    // following align() on a slot of that device starts with its batch already resident in HBM; unload() frees them.
+    virtual void preload(ReadBatch &, int /*slot*/ = 0) {}
     virtual void unload(ReadBatch &) {}
 };
 

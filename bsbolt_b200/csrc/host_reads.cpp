@@ -10,8 +10,12 @@
 #include <mutex>
 #include <stdexcept>
 #include <thread>
+#include <map>
+#include <atomic>
 
 #include <stdlib.h>
+#include <unistd.h>
+#include <sys/stat.h>
 
 namespace bsb {
 
@@ -39,9 +43,67 @@ struct FastxReader::Prefetch {
     int pos = 0;
     bool done = false, stop = false;
     std::thread th;
+    // parallel fast path: pieces [k * piece, (k + 1) * piece) of the file, parsed out of order, chained in order
+    struct Piece {
+        std::unique_ptr<Block> blk;
+        int64_t first_off = -1, end_off = -1;   // file offsets of the first record's '@' / just past the last record
+        bool give_up = false;                   // the record at end_off is not strict four-line FASTQ (or has no final newline)
+        bool unsynced = false;                  // no record boundary could be recognised in this piece
+    };
+    size_t piece = kPiece;
+    std::map<int64_t, Piece> parsed;            // finished pieces waiting for their turn
+    int64_t next_claim = 0, next_deliver = 0, n_pieces = 0;
+    bool par_stop = false;
+    std::unique_ptr<Block> take_spare()
+    {
+        std::unique_ptr<Block> b;
+        std::lock_guard<std::mutex> l(m);
+        if (!spare.empty()) { b = std::move(spare.front()); spare.pop_front(); }
+        return b;
+    }
 };
 
-FastxReader::FastxReader(const std::string &path) : buf_(kBuf)
+// what the batcher needs of every record, computed where the parsing is parallel: the read as the reference sees it
+// (strlen), its C and G counts (conversion-pattern assessment of undirectional libraries) and the name without "/1" "/2"
+static inline void finish_view(RecView &v)
+{
+    const uint32_t l = (uint32_t)strnlen(v.seq, v.seq_l);
+    uint32_t c = 0, g = 0;
+    for (uint32_t i = 0; i < l; ++i) { c += v.seq[i] == 'C'; g += v.seq[i] == 'G'; }
+    v.len = l; v.n_c = c; v.n_g = g;
+    const size_t n = v.name_l;
+    if (n > 2 && v.name[n - 2] == '/' && isdigit((unsigned char)v.name[n - 1])) v.name_l = (uint32_t)(n - 2);
+}
+
+// Cuts strict four-line FASTQ records out of [p, end) while the record's header starts before `limit`. Stops at an
+// incomplete record (returns with *p on its header). give_up: the record at *p is something else -- anything but
+// "@name[ comment]\nSEQ\n+...\nQUAL\n" with |SEQ| == |QUAL| > 0 and no carriage returns.
+static void cut_records(const char *&p, const char *end, const char *limit, std::vector<RecView> &view, bool &give_up)
+{
+    while (p < limit) {
+        const char *l0 = p, *e0, *e1, *e2, *e3;
+        if (!(e0 = (const char *)memchr(l0, '\n', end - l0))) break;
+        if (!(e1 = (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)))) break;
+        if (!(e2 = (const char *)memchr(e1 + 1, '\n', end - (e1 + 1)))) break;
+        if (!(e3 = (const char *)memchr(e2 + 1, '\n', end - (e2 + 1)))) break;
+        const char *seq = e0 + 1, *qual = e2 + 1;
+        const size_t sl = (size_t)(e1 - seq), ql = (size_t)(e3 - qual);
+        if (*l0 != '@' || e0 == l0 + 1 || e1[1] != '+' || sl == 0 || sl != ql || seq[0] == '+' || seq[0] == '>' || seq[0] == '@' ||
+            e0[-1] == '\r' || e1[-1] == '\r' || e3[-1] == '\r') { give_up = true; break; }
+        const char *nm = l0 + 1, *q = nm;
+        while (q < e0 && !isspace((unsigned char)*q)) ++q;
+        if (q == nm) { give_up = true; break; }
+        RecView v;
+        v.name = nm; v.name_l = (uint32_t)(q - nm);
+        v.cmt = q < e0 ? q + 1 : e0; v.cmt_l = (uint32_t)(e0 - v.cmt);
+        v.seq = seq; v.seq_l = (uint32_t)sl; v.qual = qual; v.qual_l = (uint32_t)ql;
+        finish_view(v);
+        view.push_back(v);
+        p = e3 + 1;
+    }
+}
+
+FastxReader::FastxReader(const std::string &path, int n_threads) : buf_(kBuf), n_threads_(n_threads)
 {
     fp_ = path == "-" ? gzdopen(0, "r") : gzopen(path.c_str(), "r");
     if (!fp_) throw std::runtime_error("[E::main_mem] fail to open file `" + path + "'.");
@@ -49,9 +111,10 @@ FastxReader::FastxReader(const std::string &path) : buf_(kBuf)
     if (path != "-" && gzdirect(fp_) && !getenv("BSB_SLOW_READER")) {   // not compressed: try the fast parser
         raw_ = fopen(path.c_str(), "rb");
         if (raw_ && fseeko(raw_, 0, SEEK_END) != 0) { fclose(raw_); raw_ = nullptr; }   // pipes and the like
-        if (raw_) { rewind(raw_); setvbuf(raw_, nullptr, _IONBF, 0); }
+        if (raw_) { file_size_ = (int64_t)ftello(raw_); rewind(raw_); setvbuf(raw_, nullptr, _IONBF, 0); }
     }
     pf_ = new Prefetch;
+    if (const char *e = getenv("BSB_READ_PIECE")) pf_->piece = (size_t)std::max(64, atoi(e));   // tests: many pieces in a small file
     pf_->th = std::thread([this] { pump(); });
 }
 
@@ -67,9 +130,170 @@ FastxReader::~FastxReader()
     if (raw_) fclose(raw_);
 }
 
+void FastxReader::deliver(void *block)
+{
+    Prefetch &P = *pf_;
+    std::unique_ptr<Prefetch::Block> b(static_cast<Prefetch::Block *>(block));
+    const bool last = b->status < 0;
+    {
+        std::lock_guard<std::mutex> l(P.m);
+        P.ready.push_back(std::move(b));
+        if (last) P.done = true;
+    }
+    P.cv.notify_all();
+}
+
+// One piece of the file, on any thread: finds the first record header at or after the piece's first byte by its
+// signature (a line starting with '@' whose next-but-one line starts with '+': in strict four-line FASTQ, where no
+// sequence starts with '@' or '+', only a header line matches), then cuts records until one starts in the next piece.
+void FastxReader::parse_piece(void *piece, int64_t k)
+{
+    Prefetch &P = *pf_;
+    Prefetch::Piece &pc = *static_cast<Prefetch::Piece *>(piece);
+    pc.blk = P.take_spare();
+    if (!pc.blk) pc.blk.reset(new Prefetch::Block);
+    Prefetch::Block &b = *pc.blk;
+    b.n = 0; b.status = 0; b.view.clear();
+    const int64_t lo = k * (int64_t)P.piece, hi = std::min<int64_t>(lo + (int64_t)P.piece, file_size_);
+    const int64_t from = lo > 0 ? lo - 1 : 0;                 // one byte back: is `lo` the start of a line?
+    size_t slack = 1 << 16;
+    const int fd = fileno(raw_);
+    for (;;) {
+        const int64_t want_end = std::min<int64_t>(hi + (int64_t)slack, file_size_);
+        b.raw.resize((size_t)(want_end - from));
+        size_t got = 0;
+        while (got < b.raw.size()) {
+            const ssize_t r = pread(fd, b.raw.data() + got, b.raw.size() - got, from + (int64_t)got);
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got < b.raw.size()) { pc.unsynced = true; return; }   // the file shrank under us: let the serial parser report it
+        const char *base = b.raw.data(), *end = base + got, *limit = base + (hi - from);
+        const char *p = base;
+        if (lo > 0) {
+            if (base[0] == '\n') p = base + 1;                 // first line start at or after lo
+            else { const char *nl = (const char *)memchr(base + 1, '\n', end - (base + 1)); p = nl ? nl + 1 : end; }
+            bool found = false, short_of_data = false;
+            for (int tries = 0; tries < 6 && p < limit; ++tries) {
+                const char *e0 = (const char *)memchr(p, '\n', end - p);
+                const char *e1 = e0 ? (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)) : nullptr;
+                if (!e1 || e1 + 1 >= end) { short_of_data = true; break; }
+                if (*p == '@' && e1[1] == '+') { found = true; break; }
+                p = e0 + 1;
+            }
+            if (!found && short_of_data && want_end < file_size_) {       // longer lines than the slack: read further
+                if (slack >= (64u << 20)) { pc.unsynced = true; return; }
+                slack *= 8;
+                continue;
+            }
+            if (!found && p < limit && !short_of_data) { pc.unsynced = true; return; }
+            // no complete record starts in this piece (or, at the end of the file, only a truncated one: the chain check
+            // of the consumer then sends the serial parser there)
+            if (!found) { pc.first_off = pc.end_off = -1; return; }
+        }
+        const char *first = p;
+        bool give_up = false;
+        b.view.clear();
+        cut_records(p, end, limit, b.view, give_up);
+        if (!give_up && p < limit && want_end < file_size_) {              // a record runs past the slack: read further and cut again
+            if (slack >= (1u << 30)) { pc.unsynced = true; return; }
+            slack *= 8;
+            continue;
+        }
+        pc.first_off = from + (first - base);
+        pc.end_off = from + (p - base);
+        pc.give_up = give_up || (p < limit);                               // at end of file: a tail without its final newline
+        b.n = (int)b.view.size();
+        return;
+    }
+}
+
+bool FastxReader::pump_parallel()
+{
+    Prefetch &P = *pf_;
+    P.n_pieces = (file_size_ + (int64_t)P.piece - 1) / (int64_t)P.piece;
+    const int window = 2 * n_threads_ + 2;                     // pieces parsed ahead of the one being handed out
+    std::vector<std::thread> workers;
+    for (int t = 0; t < n_threads_; ++t)
+        workers.emplace_back([&] {
+            for (;;) {
+                int64_t k;
+                {
+                    std::unique_lock<std::mutex> l(P.m);
+                    P.cv.wait(l, [&] { return P.stop || P.par_stop || P.next_claim >= P.n_pieces || P.next_claim < P.next_deliver + window; });
+                    if (P.stop || P.par_stop || P.next_claim >= P.n_pieces) return;
+                    k = P.next_claim++;
+                }
+                Prefetch::Piece pc;
+                parse_piece(&pc, k);
+                {
+                    std::lock_guard<std::mutex> l(P.m);
+                    P.parsed[k] = std::move(pc);
+                }
+                P.cv.notify_all();
+            }
+        });
+    int64_t expect = 0;                                        // file offset the next record must start at
+    bool whole = true, sent_last = false;
+    for (int64_t k = 0; k < P.n_pieces; ++k) {
+        Prefetch::Piece pc;
+        {
+            std::unique_lock<std::mutex> l(P.m);
+            P.cv.wait(l, [&] { return P.stop || P.parsed.count(k); });
+            if (P.stop) { whole = true; break; }
+            pc = std::move(P.parsed[k]);
+            P.parsed.erase(k);
+            P.cv.wait(l, [&] { return P.stop || P.ready.size() < 24; });
+            if (P.stop) break;
+            P.next_deliver = k + 1;
+        }
+        P.cv.notify_all();
+        const int64_t lo = k * (int64_t)P.piece, hi = std::min<int64_t>(lo + (int64_t)P.piece, file_size_);
+        if (pc.first_off < 0 && !pc.unsynced) {                // nothing starts in this piece: the previous record must cover it
+            if (expect < hi) { whole = false; break; }
+            { std::lock_guard<std::mutex> l(P.m); P.spare.push_back(std::move(pc.blk)); }
+            continue;
+        }
+        if (pc.unsynced || pc.first_off != expect) { whole = false; break; }
+        expect = pc.end_off;
+        const bool last = k + 1 == P.n_pieces;
+        if (pc.give_up) {                                      // hand out what was cut, the general parser continues at `expect`
+            if (pc.blk->n) deliver(pc.blk.release());
+            whole = false;
+            break;
+        }
+        if (last) { pc.blk->status = -1; sent_last = true; }
+        if (pc.blk->n || last) deliver(pc.blk.release());
+        else { std::lock_guard<std::mutex> l(P.m); P.spare.push_back(std::move(pc.blk)); }
+    }
+    {
+        std::lock_guard<std::mutex> l(P.m);
+        P.par_stop = true;
+    }
+    P.cv.notify_all();
+    for (auto &w : workers) w.join();
+    {
+        std::lock_guard<std::mutex> l(P.m);
+        for (auto &kv : P.parsed) if (kv.second.blk) P.spare.push_back(std::move(kv.second.blk));
+        P.parsed.clear();
+    }
+    if (getenv("BSB_DEBUG_READER"))
+        fprintf(stderr, "[D::reader] %d threads, %ld pieces of %zu bytes: %s at offset %ld of %ld\n", n_threads_, (long)P.n_pieces, P.piece,
+                whole ? "whole file cut in parallel" : "serial parser takes over", (long)expect, (long)file_size_);
+    if (whole) {
+        if (!sent_last) { std::unique_ptr<Prefetch::Block> b(new Prefetch::Block); b->status = -1; deliver(b.release()); }
+        fclose(raw_); raw_ = nullptr; gzseek(fp_, 0, SEEK_END); begin_ = end_ = 0; is_eof_ = true;
+        return true;
+    }
+    raw_off_ = expect;
+    fseeko(raw_, (off_t)expect, SEEK_SET);
+    return false;
+}
+
 void FastxReader::pump()
 {
     Prefetch &P = *pf_;
+    if (raw_ && n_threads_ > 1 && file_size_ >= 2 * (int64_t)P.piece && pump_parallel()) return;
     for (;;) {
         std::unique_ptr<Prefetch::Block> b;
         {
@@ -90,6 +314,7 @@ void FastxReader::pump()
                 RecView &v = b->view[b->n];
                 v.name = k.name.data(); v.name_l = (uint32_t)k.name.size(); v.cmt = k.comment.data(); v.cmt_l = (uint32_t)k.comment.size();
                 v.seq = k.seq.data(); v.seq_l = (uint32_t)k.seq.size(); v.qual = k.qual.data(); v.qual_l = (uint32_t)k.qual.size();
+                finish_view(v);
                 ++b->n;
             }
         }
@@ -120,27 +345,7 @@ bool FastxReader::pump_fast_block(void *block)
     const char *base = raw.data(), *end = base + len;
     const char *p = base;
     bool give_up = false;
-    while (p < end) {
-        const char *l0 = p, *e0, *e1, *e2, *e3;
-        if (!(e0 = (const char *)memchr(l0, '\n', end - l0))) break;
-        if (!(e1 = (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)))) break;
-        if (!(e2 = (const char *)memchr(e1 + 1, '\n', end - (e1 + 1)))) break;
-        if (!(e3 = (const char *)memchr(e2 + 1, '\n', end - (e2 + 1)))) break;
-        const char *seq = e0 + 1, *qual = e2 + 1;
-        const size_t sl = (size_t)(e1 - seq), ql = (size_t)(e3 - qual);
-        // anything but "@name[ comment]\nSEQ\n+...\nQUAL\n" with |SEQ| == |QUAL| > 0 and no carriage returns
-        if (*l0 != '@' || e0 == l0 + 1 || e1[1] != '+' || sl == 0 || sl != ql || seq[0] == '+' || seq[0] == '>' || seq[0] == '@' ||
-            e0[-1] == '\r' || e1[-1] == '\r' || e3[-1] == '\r') { give_up = true; break; }
-        const char *nm = l0 + 1, *q = nm;
-        while (q < e0 && !isspace((unsigned char)*q)) ++q;
-        if (q == nm) { give_up = true; break; }
-        RecView v;
-        v.name = nm; v.name_l = (uint32_t)(q - nm);
-        v.cmt = q < e0 ? q + 1 : e0; v.cmt_l = (uint32_t)(e0 - v.cmt);
-        v.seq = seq; v.seq_l = (uint32_t)sl; v.qual = qual; v.qual_l = (uint32_t)ql;
-        b.view.push_back(v);
-        p = e3 + 1;
-    }
+    cut_records(p, end, end, b.view, give_up);
     const size_t used = (size_t)(p - base);
     raw_off_ += (int64_t)used;
     if (!give_up && !at_eof) carry_.assign(p, end);          // an incomplete record: finish it with the next piece
@@ -153,27 +358,6 @@ bool FastxReader::pump_fast_block(void *block)
     b.n = (int)b.view.size();
     if (at_eof && !give_up && p >= end) { b.status = -1; fclose(raw_); raw_ = nullptr; gzseek(fp_, 0, SEEK_END); begin_ = end_ = 0; is_eof_ = true; }
     return true;
-}
-
-int FastxReader::next(FastxRecord &r)
-{
-    Prefetch &P = *pf_;
-    for (;;) {
-        if (P.cur && P.pos < P.cur->n) {
-            const RecView &s = P.cur->view[P.pos++];
-            r.name.assign(s.name, s.name_l); r.comment.assign(s.cmt, s.cmt_l); r.seq.assign(s.seq, s.seq_l); r.qual.assign(s.qual, s.qual_l);
-            return (int)r.seq.size();
-        }
-        if (P.cur && P.cur->status < 0) return P.cur->status;
-        std::unique_lock<std::mutex> l(P.m);
-        if (P.cur) { P.spare.push_back(std::move(P.cur)); P.cv.notify_all(); }
-        P.cv.wait(l, [&] { return !P.ready.empty() || P.done; });
-        if (P.ready.empty()) return -1;
-        P.cur = std::move(P.ready.front());
-        P.ready.pop_front();
-        P.pos = 0;
-        P.cv.notify_all();
-    }
 }
 
 RecView *FastxReader::next_ptr()
@@ -348,10 +532,23 @@ int assess_conversion(const char *s1, size_t l1, const char *s2, size_t l2, int 
     else return 1;
 }
 
-static void trim_readno(RecView &v)
+// assessConversion (bs_helpers.cpp:41-62) in the reference's float arithmetic, from the parser's counts
+int assess_conversion_counts(const RecView &k1, const RecView *k2, float substitution_proportion)
 {
-    size_t l = v.name_l;
-    if (l > 2 && v.name[l - 2] == '/' && isdigit((unsigned char)v.name[l - 1])) v.name_l = (uint32_t)(l - 2);
+    float observed = (float)k1.len, c_count = (float)(int)(float)k1.n_c, g_count = (float)(int)(float)k1.n_g;
+    if (k2) {
+        observed += (float)k2->len;
+        g_count += (float)(int)(float)k2->n_c;
+        c_count += (float)(int)(float)k2->n_g;
+    }
+    const float c_prop = c_count / observed, g_prop = g_count / observed;
+    float diff = c_prop - g_prop;
+    if (diff < 0) diff = (float)(diff * -1.0);
+    if (c_prop > substitution_proportion && g_prop > substitution_proportion) return 2;
+    else if (c_prop == g_prop) return 2;
+    else if (diff < 0.02) return 2;
+    else if (c_prop < g_prop) return 0;
+    else return 1;
 }
 
 void ReadBatch::fill(const std::vector<Entry> &e, bool keep_comment, int n_threads)
@@ -401,9 +598,8 @@ bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undire
     ents.clear();
     int64_t size = 0;
     auto push = [&](RecView *k, int first, int rg, int pattern) {
-        uint32_t l = (uint32_t)strnlen(k->seq, k->seq_l);
-        ents.push_back(ReadBatch::Entry{k, l, (uint8_t)first, (uint8_t)rg, (uint8_t)pattern});
-        size += l;
+        ents.push_back(ReadBatch::Entry{k, k->len, (uint8_t)first, (uint8_t)rg, (uint8_t)pattern});
+        size += k->len;
     };
     RecView *k1, *k2 = nullptr;
     while ((k1 = r1->next_ptr()) != nullptr) {
@@ -411,16 +607,14 @@ bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undire
             fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", "bseq_read");
             break;
         }
-        trim_readno(*k1);
         int pattern = 0, compare_reads = 0;
         if (undirectional) {
-            int un_type = r2 ? assess_conversion(k1->seq, k1->seq_l, k2->seq, k2->seq_l, 1, substitution_proportion)
-                             : assess_conversion(k1->seq, k1->seq_l, k1->seq, k1->seq_l, 0, substitution_proportion);
+            const int un_type = assess_conversion_counts(*k1, r2 ? k2 : nullptr, substitution_proportion);
             if (un_type == 2) compare_reads = 1;
             else pattern = un_type;
         }
         push(k1, 0, 0, pattern);
-        if (r2) { trim_readno(*k2); push(k2, 1, 0, pattern ? 0 : 1); }
+        if (r2) push(k2, 1, 0, pattern ? 0 : 1);
         if (compare_reads) {
             push(k1, 0, 1, 1);
             if (r2) push(k2, 1, 1, 0);
@@ -443,12 +637,27 @@ void fill_batch(const BatchPlan &plan, FastxReader *r1, FastxReader *r2, bool ke
     if (r2) r2->release_until(plan.mark2);
 }
 
-static int fill_threads()
+int host_core_share()
 {
-    int nt = (int)std::thread::hardware_concurrency() / 2;
-    if (const char *e = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(e));
-    if (const char *e = getenv("BSB_HOST_THREADS")) nt = atoi(e) / 2;
-    return nt < 1 ? 1 : nt > 8 ? 8 : nt;
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("BSB_HOST_THREADS")) n = atoi(e);
+    else if (const char *e = getenv("LOCAL_WORLD_SIZE")) { if (!getenv("BSB_ALL_CORES")) n /= std::max(1, atoi(e)); }
+    return n < 1 ? 1 : n;
+}
+
+static int fill_threads(int n_devices = 1)
+{
+    const int nt = host_core_share() / 2, cap = n_devices > 2 ? 12 : 8;
+    return nt < 1 ? 1 : nt > cap ? cap : nt;
+}
+
+// parser threads per input file: one keeps a GPU fed (about 18 M records/s); more devices, more pieces in flight
+int host_parse_threads(int n_devices)
+{
+    if (const char *e = getenv("BSB_PARSE_THREADS")) return std::max(1, atoi(e));
+    const int share = host_core_share() / 6;
+    const int want = n_devices > 1 ? n_devices / 2 + 1 : 2;
+    return std::max(1, std::min(want, std::max(share, 1)));
 }
 
 bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,
@@ -460,6 +669,6 @@ bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_
     return any && b.n > 0;
 }
 
-int host_fill_threads() { return fill_threads(); }
+int host_fill_threads(int n_devices) { return fill_threads(n_devices); }
 
 } // namespace bsb

@@ -94,7 +94,9 @@ struct FastxRecord { std::string name, comment, seq, qual; };
 // One parsed record as the batcher sees it: spans into the parser's block (text of the file itself on the fast path)
 struct RecView {
     const char *name, *cmt, *seq, *qual;
-    uint32_t name_l, cmt_l, seq_l, qual_l;   // qual_l == 0: no quality string
+    uint32_t name_l, cmt_l, seq_l, qual_l;   // qual_l == 0: no quality string; name_l: "/1" "/2" already trimmed (bwa.c:28-32)
+    uint32_t len;                            // strlen(seq): what the reference takes as the read (bwa.c:44-57)
+    uint32_t n_c, n_g;                       // 'C's and 'G's among those `len` bases (countBase, bs_helpers.cpp:31-39)
 };
 
 // Two parsers behind one interface, each on its own thread, handing blocks of records to the batcher:
@@ -104,10 +106,11 @@ struct RecView {
 //    hands over to it at the byte offset of the first record it does not recognise, so results never differ.
 class FastxReader {
 public:
-    explicit FastxReader(const std::string &path);
+    // n_threads > 1: a plain four-line FASTQ file is cut by that many threads at once (pieces of the file parsed
+    // speculatively from a record boundary found by its "@...\n...\n+" signature, then chained in file order: a piece
+    // is only handed out when it starts exactly where its predecessor ended, else the serial parser takes over there)
+    explicit FastxReader(const std::string &path, int n_threads = 1);
     ~FastxReader();
-    // >=0 sequence length, -1 end of file, -2 truncated quality
-    int next(FastxRecord &r);
     // zero-copy form for the batcher: the next record inside the parser's block (nullptr at end of input). The
     // pointer stays valid until release_held().
     RecView *next_ptr();
@@ -120,6 +123,9 @@ private:
     int next_raw(FastxRecord &r);
     void pump();               // parser thread body
     bool pump_fast_block(void *block);
+    bool pump_parallel();      // true: the whole file was handed out; false: continue serially at raw_off_
+    void parse_piece(void *piece, int64_t k);
+    void deliver(void *block);
     struct Prefetch;           // blocks of parsed records handed over from the parser thread
     Prefetch *pf_ = nullptr;
     int getc_();
@@ -134,6 +140,8 @@ private:
     FILE *raw_ = nullptr;      // non-null while the fast parser is active
     int64_t raw_off_ = 0;      // file offset of the first byte not yet handed out as a record
     std::vector<char> carry_;  // incomplete record at the end of the previous piece
+    int n_threads_ = 1;
+    int64_t file_size_ = 0;
 };
 
 // One batch of bseq entries (a read aligned under both conversion patterns appears twice).
@@ -150,6 +158,7 @@ struct ReadBatch {
     std::vector<uint8_t> first, read_group, pattern;
     int64_t n_bases = 0;
     void *dev_input = nullptr;       // set by BatchAligner::preload(): the batch's inputs are already resident on the device
+    void *dev_owner = nullptr;       // ... of this aligner (multi-GPU runs)
 
     void clear();
     void reserve_like(const ReadBatch &o);   // pre-size for a batch about as large as o
@@ -161,6 +170,8 @@ struct ReadBatch {
 };
 
 int assess_conversion(const char *s1, size_t l1, const char *s2, size_t l2, int paired_end, float substitution_proportion);
+// the same decision from the parser's per-record counts (RecView::len, n_c, n_g)
+int assess_conversion_counts(const RecView &k1, const RecView *k2, float substitution_proportion);
 
 // The two halves of read_batch(), so that cutting batch i+1 can overlap with copying batch i: plan_batch() applies the
 // reference's batching rule and records which parser records make up the batch; fill_batch() copies them into the flat
@@ -169,7 +180,9 @@ struct BatchPlan { std::vector<ReadBatch::Entry> ents; uint64_t mark1 = 0, mark2
 bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undirectional, float substitution_proportion, BatchPlan &plan);
 void fill_batch(const BatchPlan &plan, FastxReader *r1, FastxReader *r2, bool keep_comment, int n_threads, ReadBatch &b);
 
-int host_fill_threads();   // copy threads for fill_batch(): this process's share of the cores, at most 8
+int host_core_share();                       // cores this process may use (all of them, or its share under a one-process-per-GPU launcher)
+int host_fill_threads(int n_devices = 1);    // copy threads for fill_batch(): this process's share of the cores
+int host_parse_threads(int n_devices = 1);   // FASTQ parser threads per input file
 
 // Fills `b` with the next batch. Returns false when no read could be read (end of input).
 bool read_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, bool keep_comment, int undirectional,

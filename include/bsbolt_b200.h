@@ -52,6 +52,10 @@ int bsb_device_count(void);                       /* number of CUDA devices, 0 i
 /* replaces bwa_idx_load(hint, BWA_IDX_ALL) (bwa.c:407-443): reads <idxbase>.bwt .sa .ann .amb .pac .opac
  * and uploads them to HBM of `device` */
 bsb_index_t *bsb_index_load(const char *idxbase, int device);
+/* one more resident copy of a loaded index, on another device; the host-side tables are shared. The reference's
+ * multi-threaded run shares one bwaidx_t between its worker threads (fastmap.c:319-352); on GPUs the index is replicated
+ * per device and the batches are dealt out. */
+bsb_index_t *bsb_index_clone(const bsb_index_t *src, int device);
 void bsb_index_free(bsb_index_t *idx);
 int64_t bsb_index_hbm_bytes(const bsb_index_t *idx);
 int bsb_index_n_contigs(const bsb_index_t *idx);  /* includes the hidden crick copies */
@@ -69,6 +73,15 @@ int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd
  * the cores) at zlib `level` (0..9, -1 = zlib default = what stream_bam uses). */
 int bsb_mem_main_bam(bsb_index_t *idx, int device, int argc, char **argv, const char *bam_path, int threads, int level,
                      int log_fd, bsb_run_stats_t *stats);
+/* The same two entry points over several GPUs of one box: idx[0] from bsb_index_load, idx[1..] its bsb_index_clone on the
+ * other devices. The input is read and cut into the reference's batches ONCE (kt_pipeline step 0, fastmap.c:10-36), batch b
+ * is aligned on idx[b mod n_idx] (the role of kt_for's worker threads, kthread.c:119-147 / bwamem.c:1319-1348: reads are
+ * independent, nothing is exchanged between devices), and the records leave in input order (step 2, fastmap.c:61-73):
+ * output and BSStat lines are byte-identical to the single-device run. */
+int bsb_mem_main_multi(bsb_index_t *const *idx, int n_idx, int argc, char **argv, int out_fd, int log_fd, bsb_run_stats_t *stats);
+int bsb_mem_main_multi_bam(bsb_index_t *const *idx, int n_idx, int argc, char **argv, const char *bam_path, int threads, int level,
+                           int log_fd, bsb_run_stats_t *stats);
+
 /* replaces stream_bam itself (HTSLIB/stream_bam.c main): SAM text on in_fd -> BAM file. Host only (needs no device).
  * Returns the number of records written, -1 on error. */
 int64_t bsb_stream_bam(int in_fd, const char *bam_path, int threads, int level);

@@ -11,6 +11,7 @@
 #include <memory>
 #include <stdexcept>
 #include <vector>
+#include <mutex>
 #include "../../bsbolt_b200/csrc/bsb_stages.h"
 #include "../../bsbolt_b200/csrc/host_mem.h"
 
@@ -156,8 +157,56 @@ private:
     std::vector<uint32_t> occ32_;
 };
 
+// HOSTSIM_DEVICES=n: the pipeline's multi-device path (batch b -> device b mod n, one slot per device, results collected in
+// input order) over n CPU "devices" -- the host-side logic of bsb_mem_main_multi without a GPU
+class FakeDevices : public BatchAligner {
+public:
+    FakeDevices(BatchAligner &one, int n) : one_(one), n_(n), used_(n, 0) {}
+    int devices() const override { return n_; }
+    int slots() const override { return n_; }
+    void align(const Opt &opt, const ReadBatch &b, int64_t n_processed, const PeStat *pes0, BatchResult &out, int slot = 0) override
+    {
+        { std::lock_guard<std::mutex> l(m_); ++used_[slot]; }
+        one_.align(opt, b, n_processed, pes0, out, 0);
+    }
+    void report() { for (int d = 0; d < n_; ++d) fprintf(stderr, "[D::hostsim] device %d aligned %ld batches\n", d, used_[d]); }
+private:
+    BatchAligner &one_; int n_; std::vector<long> used_; std::mutex m_;
+};
+
+// hostsim readbench <chunk bases> <parse threads> <fill threads> <undirectional 0|1> <in1.fq> [in2.fq]: the reader alone (cut + batch + copy)
+static int readbench(int argc, char **argv)
+{
+    if (argc < 7) { fprintf(stderr, "usage: hostsim readbench <chunk> <parse threads> <fill threads> <undirectional> <in1.fq> [in2.fq]\n"); return 1; }
+    const int64_t chunk = atoll(argv[2]);
+    const int pt = atoi(argv[3]), ft = atoi(argv[4]), un = atoi(argv[5]);
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    FastxReader r1(argv[6], pt);
+    std::unique_ptr<FastxReader> r2;
+    if (argc > 7) r2.reset(new FastxReader(argv[7], pt));
+    BatchPlan plan;
+    ReadBatch batch;
+    long n = 0, nb = 0;
+    double t_plan = 0, t_fill = 0;
+    auto now = [] { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
+    for (;;) {
+        double t0 = now();
+        if (!plan_batch(chunk, &r1, r2.get(), un, 0.1f, plan)) break;
+        double t1 = now();
+        fill_batch(plan, &r1, r2.get(), false, ft, batch);
+        t_plan += t1 - t0; t_fill += now() - t1;
+        n += batch.n; ++nb;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    const double s = (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+    printf("%ld entries in %ld batches, %.3f s: %.1f M entries/s (plan %.3f s, fill %.3f s, serialised here)\n", n, nb, s, n / s / 1e6, t_plan, t_fill);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc >= 2 && strcmp(argv[1], "readbench") == 0) return readbench(argc, argv);
     if (argc < 2 || strcmp(argv[1], "mem") != 0) { fprintf(stderr, "usage: hostsim mem [options] <idxbase> <in1.fq> [in2.fq]\n"); return 1; }
     try {
         MemArgs ma;
@@ -169,6 +218,12 @@ int main(int argc, char **argv)
         if (ma.ignore_alt) for (auto &a : idx.anns) a.is_alt = 0;
         HostSimAligner al(idx);
         RunSummary sum;
+        if (const char *e = getenv("HOSTSIM_DEVICES")) {
+            FakeDevices multi(al, std::max(1, atoi(e)));
+            const int rc = run_mem(ma, idx, multi, stdout, stderr, &sum);
+            multi.report();
+            return rc;
+        }
         return run_mem(ma, idx, al, stdout, stderr, &sum);
     } catch (const std::exception &e) {
         fprintf(stderr, "%s\n", e.what());

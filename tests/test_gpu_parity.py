@@ -202,9 +202,47 @@ def test_index_build_byte_identical(built, golden, tmp_path):
     assert ms > 0
 
 
-def test_cli_drop_in_single_and_two_shards(built, golden, tmp_path):
-    """`python -m bsbolt_b200 Align ... -OS` (the reference's CLI surface) on one device and as two batch shards
-    (-GPU 0,0: two worker processes on the same device) -- both must print the reference's SAM."""
+def test_multi_device_run_identical(index, golden, tmp_path):
+    """bsb_mem_main_multi (one reader, batch b on device b mod G, output in input order) over every visible GPU -- or two
+    resident copies of the index on GPU 0 when the box has one -- prints the single-device SAM and BSStat lines; SAM and
+    BAM output; every device gets its share of the batches."""
+    from bsbolt_b200 import _native
+    n = _native.lib().bsb_device_count()
+    devices = list(range(n)) if n > 1 else [0, 0]
+    multi = _native.MultiIndex(golden.idxbase, devices)
+    try:
+        for case in ('pe150', 'pe150_un', 'se100'):
+            out, log = tmp_path / f'{case}.sam', tmp_path / f'{case}.log'
+            with open(out, 'w') as fo, open(log, 'w') as fl:
+                rc, st = _native.mem_main_multi(golden.argv(case), multi, out_fd=fo.fileno(), log_fd=fl.fileno())
+            assert rc == 0, _native.last_error()
+            got = strip_pg(open(out).read())
+            assert got == golden.sam(case), first_diff(golden.sam(case), got)
+            bs = {}
+            for l in open(log):
+                if l.startswith('BSStat '):
+                    k, v = l[7:].split(': ')
+                    bs[k] = bs.get(k, 0) + int(v)
+            assert bs == golden.cases[case]['bsstat']
+            assert st['n_batches'] >= len(devices) and st['kernel_launches'] > 0
+        import gzip
+        bam = tmp_path / 'multi.bam'
+        with open(tmp_path / 'bam.log', 'w') as fl:
+            rc, st = _native.mem_main_multi_bam(golden.argv('pe150'), str(bam), multi, threads=2, log_fd=fl.fileno())
+        assert rc == 0, _native.last_error()
+        one = tmp_path / 'one.bam'
+        with open(tmp_path / 'bam1.log', 'w') as fl:
+            rc, _ = _native.mem_main_bam(golden.argv('pe150'), str(one), index=multi.parts[0], threads=2, log_fd=fl.fileno())
+        assert rc == 0
+        a, b = gzip.open(bam, 'rb').read(), gzip.open(one, 'rb').read()
+        assert a[:4] == b'BAM\x01' and len(a) == len(b)
+    finally:
+        multi.close()
+
+
+def test_cli_drop_in_single_and_two_devices(built, golden, tmp_path):
+    """`python -m bsbolt_b200 Align ... -OS` (the reference's CLI surface) on one device and over two (-GPU 0,0: two resident
+    copies of the index driven by ONE process, batches dealt round-robin) -- both must print the reference's SAM."""
     import sys
     db = os.path.dirname(golden.idxbase)
     c = golden.cases['pe150']

@@ -96,13 +96,13 @@ def test_reader_variants_give_identical_batches(built, golden, tmp_path):
     import subprocess
     hostsim = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
     src = open(os.path.join(golden.dir, golden.cases['se100']['fq'][0])).read().split('\n')
-    recs = [src[i:i + 4] for i in range(0, 4 * 3000, 4)]
+    recs = [r for r in (src[i:i + 4] for i in range(0, 4 * 3000, 4)) if len(r) == 4 and r[0]]
     plain = ''.join('\n'.join(r) + '\n' for r in recs)
     variants = {'plain.fq': plain.encode(), 'nonl.fq': plain[:-1].encode(), 'crlf.fq': plain.replace('\n', '\r\n').encode()}
-    # record 1500 with its sequence and quality folded over two lines each: only the general parser reads that
+    # the middle record with its sequence and quality folded over two lines each: only the general parser reads that
     folded = []
     for k, r in enumerate(recs):
-        if k == 1500:
+        if k == len(recs) // 2:
             h = len(r[1]) // 2
             folded.append('\n'.join([r[0], r[1][:h], r[1][h:], r[2], r[3][:h], r[3][h:]]) + '\n')
         else:
@@ -125,6 +125,28 @@ def test_reader_variants_give_identical_batches(built, golden, tmp_path):
     assert want.count('\n') > 1000
     for name, got in outs.items():
         assert got == want, name
+    # the multi-threaded cutter (pieces of the file parsed speculatively, chained in file order): tiny pieces so that this
+    # small file spans hundreds of them, piece boundaries on every kind of line; qualities that begin with '@' or '+' (a
+    # quality line must never be taken for a header), and the variants above, where the serial / general parser takes over
+    adv = ''.join('\n'.join([r[0], r[1], r[2], ('@' if k % 3 == 0 else '+' if k % 3 == 1 else 'I') + r[3][1:]]) + '\n' for k, r in enumerate(recs) if len(r) == 4 and r[0])
+    (tmp_path / 'adv.fq').write_text(adv)
+    p = subprocess.run([hostsim, 'mem'] + golden.manifest['launcher_args'] + ['-K', '70000', golden.idxbase, str(tmp_path / 'adv.fq')], capture_output=True, text=True, env=env)
+    want_adv = ''.join(l + '\n' for l in p.stdout.split('\n') if l and not l.startswith('@PG'))
+    assert want_adv.count('\n') > 1000 and want_adv != want
+    for piece, threads in (('97', '3'), ('1000', '2'), ('4099', '5'), ('100000', '4')):
+        penv = dict(os.environ, BSB_READ_PIECE=piece, BSB_PARSE_THREADS=threads, BSB_DEBUG_READER='1')
+        for name, expect in [(n, want) for n in variants] + [('adv.fq', want_adv)]:
+            p = subprocess.run([hostsim, 'mem'] + golden.manifest['launcher_args'] + ['-K', '70000', golden.idxbase, str(tmp_path / name)],
+                               capture_output=True, text=True, env=penv)
+            assert p.returncode == 0, p.stderr[-1500:]
+            got = ''.join(l + '\n' for l in p.stdout.split('\n') if l and not l.startswith('@PG'))
+            assert got == expect, (name, piece, threads)
+            note = [l for l in p.stderr.split('\n') if l.startswith('[D::reader]')]
+            assert note, 'the multi-threaded cutter did not run'
+            if name in ('plain.fq', 'adv.fq'):
+                assert 'whole file cut in parallel' in note[0], note
+            else:
+                assert 'serial parser takes over' in note[0], note
 
 
 def test_database_fasta_writers_match_bsbolt_index(tmp_path):
@@ -169,3 +191,24 @@ def test_database_fasta_writers_match_bsbolt_index(tmp_path):
     for _ in range(200):
         regs = sorted(((rnd.randrange(-5, 300), rnd.randrange(-5, 320)) for _ in range(rnd.randrange(1, 12))), key=lambda r: r[0])
         assert index_db.mask_outside(seq, regs) == ref_mask(seq, regs)
+
+
+@pytest.mark.parametrize('case,n_dev', [('pe150', 2), ('pe150_un', 3), ('se100', 2)])
+def test_multi_device_pipeline_equals_single_run(built, golden, case, n_dev):
+    """bsb_mem_main_multi's host logic on CPU "devices" (tests/hostsim, HOSTSIM_DEVICES): one reader, batch b on device
+    b mod G, several batches in flight, results in input order -- SAM and BSStat lines identical to the reference."""
+    import subprocess
+    hostsim = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
+    env = dict(os.environ, HOSTSIM_DEVICES=str(n_dev))
+    p = subprocess.run([hostsim] + golden.argv(case), capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    got = ''.join(l + '\n' for l in p.stdout.split('\n') if l and not l.startswith('@PG'))
+    assert got == golden.sam(case)
+    used = [int(l.split()[4]) for l in p.stderr.split('\n') if l.startswith('[D::hostsim] device')]
+    assert len(used) == n_dev and all(u >= 1 for u in used) and max(used) - min(used) <= 1
+    bs = {}
+    for l in p.stderr.split('\n'):
+        if l.startswith('BSStat '):
+            k, v = l[7:].split(': ')
+            bs[k] = bs.get(k, 0) + int(v)
+    assert bs == golden.cases[case]['bsstat']

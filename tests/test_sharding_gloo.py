@@ -49,3 +49,40 @@ def test_two_rank_sharded_run_equals_single_run(built, golden, tmp_path, case):
     # both ranks really had work (the cases are cut into several batches by their -K)
     n0 = sum(1 for _ in open(tmp_path / 'part0.idx')); n1 = sum(1 for _ in open(tmp_path / 'part1.idx'))
     assert n0 >= 2 and n1 >= 1
+
+
+FENCE_WORKER = r'''
+import os, sys, time
+sys.path.insert(0, os.environ['BSB_ROOT'])
+os.environ['BSB_BENCH_BACKEND'] = 'gloo'
+import bench
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+r = bench.Ranks(rank, world, int(os.environ['LOCAL_RANK']))
+out = open(os.path.join(sys.argv[1], f'fence{rank}.log'), 'w')
+for k in range(4):
+    if rank == 0:
+        time.sleep(0.4)                      # rank 0's "work" between two fences
+        out.write(f'{k} {time.time()}\n')    # ... finished before it enters fence k
+    r.fence()
+    if rank != 0:
+        out.write(f'{k} {time.time()}\n')    # a waiting rank leaves fence k
+out.close()
+r.close()
+'''
+
+
+def test_bench_ranks_wait_for_rank0_at_every_fence(tmp_path):
+    """bench.py under torchrun: rank 0 drives every GPU through the product's one-process path, the other ranks only meet
+    it at the fences around the timed regions (gloo here, NCCL on the GPU box). A waiting rank must never leave fence k
+    before rank 0 has reached it."""
+    worker = tmp_path / 'fence_worker.py'
+    worker.write_text(FENCE_WORKER)
+    env = dict(os.environ, BSB_ROOT=ROOT)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29519', str(worker), str(tmp_path)]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    t0 = [float(l.split()[1]) for l in open(tmp_path / 'fence0.log')]
+    t1 = [float(l.split()[1]) for l in open(tmp_path / 'fence1.log')]
+    assert len(t0) == len(t1) == 4
+    assert all(b >= a for a, b in zip(t0, t1))
