@@ -21,6 +21,7 @@
 #include <vector>
 #include "bsb_stages.h"
 #include "bsb_warp.cuh"
+#include "bsb_extlane.h"
 #include "bsb_cuda.h"
 
 namespace bsb {
@@ -467,6 +468,78 @@ __global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix
         stage_extend_group(opt, ix, B, (int)base, min(32, B.n - (int)base), order, S, dp, dp_lane);
 }
 
+// K5, lane per read (bsb_extlane.h): every lane runs the extension machine of one read; the warp draws reads 32 at a time from
+// a global counter and hands them to its lanes as they finish; between two DP rows a lane runs its own (divergent, short)
+// control flow, then all lanes that have a row to fill meet in row(). The (h,e) rows live in shared memory, word
+// j * 32 + lane of the warp's tile. Finished reads carry their regions before mem_sort_dedup_patch; k_extend_tail ends them.
+constexpr int XL_WARPS = 2;
+__global__ void __launch_bounds__(XL_WARPS * 32) k_extend_lanes(Opt opt, IndexView ix, BatchDev B, int max_q, int row_cap, int *ctr, int chunk, int ctl_mask, int ctl_lanes)
+{
+    extern __shared__ uint32_t xl_rows[];
+    typedef ExtLane<PackedRow<32>> Machine;
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
+    Machine L;
+    L.state = Machine::IDLE;
+    L.H.p = xl_rows + (size_t)wib * 32 * (size_t)row_cap + lane;
+    L.row_cap = row_cap;
+    {   // per-query-length tables behind the row tiles: max_gap, band limits of the left / right extension
+        int *tab = reinterpret_cast<int *>(xl_rows + (size_t)XL_WARPS * 32 * (size_t)row_cap);
+        const int nt = max_q + 2, amax = ext_amax(opt);
+        for (int q = threadIdx.x; q < nt; q += blockDim.x) ext_tables_fill(opt, amax, q, tab, tab + nt, tab + 2 * nt);
+        L.T.gap = tab; L.T.wl = tab + nt; L.T.wr = tab + 2 * nt; L.T.n = nt; L.T.amax = amax;
+        __syncthreads();
+    }
+    int pool_next = 0, pool_end = 0;   // the warp's drawn reads [pool_next, pool_end): same values in all lanes
+    bool dry = false;
+    for (unsigned iter = 0;; ++iter) {
+        unsigned rows = __ballot_sync(0xffffffffu, L.state == Machine::ROW);
+        const bool more_reads = !(dry && pool_next == pool_end);
+        // lanes a control phase would move: those between two rows, and idle ones while reads remain. The phase is divergent,
+        // so it waits until several lanes need it (or nothing else can run, or every fourth step at the latest)
+        const unsigned can = __ballot_sync(0xffffffffu, L.state != Machine::ROW && (L.state != Machine::IDLE || more_reads));
+        if (can && (!rows || __popc(can) >= ctl_lanes || (iter & ctl_mask) == 0)) {
+            for (;;) {                   // idle lanes take reads (a read without seeds leaves its lane idle: it draws again)
+                const unsigned want = __ballot_sync(0xffffffffu, L.state == Machine::IDLE);
+                if (!want) break;
+                if (pool_next == pool_end) {
+                    if (dry) break;
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(ctr, 32);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    pool_next = min(base, B.n); pool_end = min(base + 32, B.n);
+                    if (pool_next == pool_end) { dry = true; break; }
+                }
+                const int rank = __popc(want & lt_mask);
+                const bool take = L.state == Machine::IDLE && pool_next + rank < pool_end;
+                if (take) L.begin_read(B, pool_next + rank);
+                pool_next += __popc(__ballot_sync(0xffffffffu, take));
+            }
+            if (L.state != Machine::IDLE && L.state != Machine::ROW) L.advance(opt, ix, B, max_q);
+            __syncwarp();
+            while (__ballot_sync(0xffffffffu, L.in_init())) {   // the lanes that have just set up an extension fill its initial row together
+                if (L.in_init()) L.init_step(opt, 32);
+                __syncwarp();
+            }
+            rows = __ballot_sync(0xffffffffu, L.state == Machine::ROW);
+        }
+        if (!rows) {
+            if (dry && pool_next == pool_end && !__ballot_sync(0xffffffffu, L.state != Machine::IDLE)) break;
+            continue;
+        }
+        if (L.state == Machine::ROW) L.step(opt, ix, chunk);
+        __syncwarp();
+    }
+}
+
+// mem_sort_dedup_patch + ALT marks, one thread per read (serial by nature: two introsorts, the redundancy scan, now and then a
+// score-only global alignment in the thread's own DP scratch)
+__global__ void __launch_bounds__(128) k_extend_tail(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
+    DpScratch dp = {eh + (size_t)w * 2 * (max_q + 1), nullptr, 0, max_q};
+    for (int r = w; r < B.n; r += nw) extend_tail(opt, ix, B, r, dp);
+}
+
 // K4b: mem_flt_chained_seeds (bwamem.c:602-619). Launched only when a read of the batch can qualify (reads of about
 // 720 bp and more, or -W): a warp takes a read, each lane one of its chains; the flanked 16-bit Smith-Waterman of a seed
 // covers fewer than 200 x 200 cells, its four rows live in the lane's local memory.
@@ -656,6 +729,12 @@ __global__ void k_dense_sa(IndexView ix, uint64_t n_sa, uint32_t *sa32, uint8_t 
         sa32[k] = (uint32_t)v;
         if (sa_hi) sa_hi[k] = (uint8_t)(v >> 32);
     }
+}
+
+__global__ void k_clear_code(int32_t *a, int n, int32_t code)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] == code) a[i] = 0;
 }
 
 __global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
@@ -1099,7 +1178,34 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaEventRecord(m.ev[5], st));
     // ---- K5 ----
     const int max_q = max_len + 8;
-    if (getenv("BSB_EXTEND_V1")) {
+    // the lane-per-read machine needs every score in 14 bits, the scoring matrix of bwa_fill_scmat (always the case for
+    // matrices built from -A/-B) and a shared-memory row tile per warp; longer reads take the warp-per-read kernel
+    bool scmat_std = true;
+    for (int i = 0; i < 5 && scmat_std; ++i)
+        for (int j = 0; j < 5; ++j) {
+            const int want = (i == 4 || j == 4) ? -1 : (i == j ? opt.a : -opt.b);
+            if (opt.mat[i * 5 + j] != want) { scmat_std = false; break; }
+        }
+    // a seed is min_seed_len bases or longer, so no flank (the query of one extension) is longer than the read without it
+    const int xl_row_cap = std::max(8, max_len - std::max(opt.min_seed_len, 0) + 3);
+    const size_t xl_smem = (size_t)XL_WARPS * 32 * (size_t)xl_row_cap * 4 + 3 * (size_t)(max_q + 2) * 4;
+    const long xl_max_score = 2L * max_len * (long)std::max(opt.a, 1) + std::max(opt.pen_clip5, opt.pen_clip3) + 64;
+    const bool ext_lanes = !getenv("BSB_EXTEND_WARP") && !getenv("BSB_EXTEND_V1") && scmat_std && xl_max_score < (1 << XL_BITS) - 1 && max_q < 4000 && xl_smem <= 100 * 1024 &&
+                           opt.a > 0 && opt.b >= 0 && opt.e_ins > 0 && opt.e_del > 0;
+    bool use_lanes = ext_lanes;
+    int32_t h_misc[2] = {0, 0};
+    for (;;) {
+    if (use_lanes) {
+        raise_dynamic_smem(k_extend_lanes, (int)xl_smem);
+        const int xl_bps = std::max(1, std::min(16, (int)((225 * 1024) / (xl_smem + 1024))));
+        const int blocks = (int)std::min<size_t>((size_t)cdiv(n, XL_WARPS * 32), (size_t)I.n_sm * xl_bps);
+        k_extend_lanes<<<blocks, XL_WARPS * 32, xl_smem, st>>>(opt, I.ix, B, max_q, xl_row_cap, m.d_misc.p + 17, env_int("BSB_XL_CHUNK", 24), env_int("BSB_XL_CTLMASK", 15),
+                                                                env_int("BSB_XL_CTLLANES", 10));
+        const int tail_blocks = (int)std::min<size_t>((size_t)cdiv(n, 128), (size_t)I.n_sm * 8);
+        m.d_eh.ensure((size_t)tail_blocks * 128 * 2 * (max_q + 1));
+        k_extend_tail<<<tail_blocks, 128, 0, st>>>(opt, I.ix, B, m.d_eh.p, max_q);
+        m.launches += 2;
+    } else if (getenv("BSB_EXTEND_V1")) {
         const int ext_block = 64;
         const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)I.n_sm * 16 * ext_block);
         m.d_eh.ensure((size_t)ext_workers * 2 * (max_q + 1));
@@ -1120,11 +1226,18 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
     k_max_i32<<<I.n_sm, 256, 0, st>>>(m.d_n_regs.p, n, m.d_misc.p); ++m.launches;
     k_max_i32<<<I.n_sm, 256, 0, st>>>(m.d_err.p, n, m.d_misc.p + 1); ++m.launches;
-    int32_t h_misc[2] = {0, 0};
     CK(cudaMemcpyAsync(h_misc, m.d_misc.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(m.ev[6], st));
     m.wait();
     T("extend_done");
+    if (use_lanes && h_misc[1] == ERR_ROW_TILE) {   // a flank longer than the row tile (a seed shorter than -k): warp-per-read form
+        k_clear_code<<<cdiv(n, 256), 256, 0, st>>>(m.d_err.p, n, ERR_ROW_TILE); ++m.launches;
+        CK(cudaMemsetAsync(m.d_misc.p + 17, 0, 4, st));
+        use_lanes = false;
+        continue;
+    }
+    break;
+    }
     if (h_misc[1]) throw std::runtime_error("[E::bsbolt_b200] chaining/extension failed with error code " + std::to_string(h_misc[1]));
     const int max_regs = h_misc[0];
     if (getenv("BSB_DEBUG_STATS")) {

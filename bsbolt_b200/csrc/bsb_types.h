@@ -126,7 +126,8 @@ struct Ann {
 
 enum : int {
     ERR_NONE = 0, ERR_INTV_OVERFLOW = 1, ERR_ARENA_OVERFLOW = 2, ERR_SCRATCH_OVERFLOW = 3,
-    ERR_CIGAR_OVERFLOW = 4, ERR_NO_MD = 5
+    ERR_CIGAR_OVERFLOW = 4, ERR_NO_MD = 5,
+    ERR_ROW_TILE = 6      // lane-per-read extension: a flank longer than the shared-memory row tile (the stage is re-run warp-per-read)
 };
 
 } // namespace bsb

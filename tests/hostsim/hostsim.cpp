@@ -13,6 +13,7 @@
 #include <vector>
 #include <mutex>
 #include "../../bsbolt_b200/csrc/bsb_stages.h"
+#include "../../bsbolt_b200/csrc/bsb_extlane.h"
 #include "../../bsbolt_b200/csrc/host_mem.h"
 
 using namespace bsb;
@@ -82,6 +83,36 @@ public:
         const long z_cap = (long)(max_q) * (long)(max_q + 2 * (4 * opt.w) + 64);
         std::vector<uint8_t> z(z_cap);
         DpScratch dp = {eh.data(), z.data(), z_cap, max_q};
+        if (getenv("HOSTSIM_EXT_LANES")) {
+            // the per-read extension machine of k_extend_lanes (bsb_extlane.h), LANES reads interleaved row by row like the
+            // lanes of a warp: control flow up to the next DP row, then one row each; then the tail, read by read
+            const int LANES = std::max(1, atoi(getenv("HOSTSIM_EXT_LANES")));
+            const int chunk = getenv("HOSTSIM_EXT_CHUNK") ? std::max(1, atoi(getenv("HOSTSIM_EXT_CHUNK"))) : 16;
+            std::vector<std::vector<uint32_t>> rows(LANES, std::vector<uint32_t>(max_q + 2));
+            std::vector<ExtLane<PackedRow<1>>> L(LANES);
+            std::vector<int> tg(max_q + 2), twl(max_q + 2), twr(max_q + 2);
+            const int amax = ext_amax(opt);
+            for (int q = 0; q < max_q + 2; ++q) ext_tables_fill(opt, amax, q, tg.data(), twl.data(), twr.data());
+            const ExtTables tabs = {tg.data(), twl.data(), twr.data(), getenv("HOSTSIM_EXT_NOTAB") ? 0 : max_q + 2, amax};
+            for (int l = 0; l < LANES; ++l) { L[l].state = ExtLane<PackedRow<1>>::IDLE; L[l].H.p = rows[l].data(); L[l].row_cap = max_q + 2; L[l].T = tabs; }
+            int next = 0;
+            for (;;) {
+                bool any = false;
+                for (int l = 0; l < LANES; ++l) {
+                    ExtLane<PackedRow<1>> &m = L[l];
+                    while (m.state == ExtLane<PackedRow<1>>::IDLE && next < n) { m.begin_read(B, next++); m.advance(opt, ix_, B, max_q); }
+                    if (m.state != ExtLane<PackedRow<1>>::IDLE && m.state != ExtLane<PackedRow<1>>::ROW) m.advance(opt, ix_, B, max_q);
+                    while (m.state == ExtLane<PackedRow<1>>::IDLE && next < n) { m.begin_read(B, next++); m.advance(opt, ix_, B, max_q); }
+                    if (m.state == ExtLane<PackedRow<1>>::ROW) { m.step(opt, ix_, chunk); any = true; }
+                }
+                if (!any && next >= n) {
+                    bool busy = false;
+                    for (int l = 0; l < LANES; ++l) busy = busy || L[l].state != ExtLane<PackedRow<1>>::IDLE;
+                    if (!busy) break;
+                }
+            }
+            for (int r = 0; r < n; ++r) extend_tail(opt, ix_, B, r, dp);
+        } else
         for (int r = 0; r < n; ++r) stage_extend(opt, ix_, B, r, dp);
         int max_regs = 0;
         for (int r = 0; r < n; ++r) max_regs = std::max(max_regs, n_regs[r]);

@@ -20,11 +20,12 @@ def main():
     a = ap.parse_args()
     from bsbolt_b200 import _native, index_db
     work = os.path.join('/tmp/bsb_bench', f'g{a.genome_mb}')
-    fa, jobs = bench.prepare_workload(work, a.genome_mb, a.batches, a.batch_pairs, 0)
+    db = os.path.join(work, 'db', 'BSB_ref.fa')
+    fa = bench.ensure_genome(work, os.path.dirname(db), a.genome_mb)
+    jobs = bench.prepare_workload(work, fa, a.batches, a.batch_pairs)
     sims = bench.run_simulation(jobs, min(8, len(jobs)))
     f1 = os.path.join(work, 'st_1.fq'); f2 = os.path.join(work, 'st_2.fq')
     bench.concat([p[0] for p, n in sims], f1); bench.concat([p[1] for p, n in sims], f2)
-    db = os.path.join(work, 'db', 'BSB_ref.fa')
     if not os.path.exists(db + '.sa'):
         index_db.build_database(fa, os.path.join(work, 'db'), device=0)
     null = os.open(os.devnull, os.O_WRONLY)
