@@ -744,9 +744,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     double t0 = now_sec();
     const int n_dev = std::max(1, aligner.devices());
     const int parse_threads = host_parse_threads(n_dev);
-    FastxReader r1(ma.fq1, parse_threads);
+    FastxReader r1(ma.fq1, parse_threads, ma.opt.undirectional != 0);
     std::unique_ptr<FastxReader> r2;
-    if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2, parse_threads));
+    if (!ma.fq2.empty()) r2.reset(new FastxReader(ma.fq2, parse_threads, ma.opt.undirectional != 0));
     std::string hdr = sam_header(idx, ma);
     const int shard_count = ma.shard_count > 1 ? ma.shard_count : 1, shard_index = ma.shard_index;
     size_t out_bytes = 0;
@@ -811,7 +811,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 double tr = now_sec();
                 if (!plan_batch(ma.actual_chunk_size(), &r1, r2.get(), ma.opt.undirectional, ma.opt.substitution_proportion, j->plan)) break;
                 sec_plan += now_sec() - tr;
-                const int n = (int)j->plan.ents.size();
+                const int n = (int)j->plan.n_entries;
                 j->n_processed = n_processed;
                 j->batch_id = batch_id++;
                 n_processed += n;

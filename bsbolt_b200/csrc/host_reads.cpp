@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <unistd.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 
 namespace bsb {
 
@@ -30,7 +31,14 @@ struct FastxReader::Prefetch {
         std::vector<FastxRecord> rec;   // general parser: the records themselves
         std::vector<char> raw;          // fast parser: one piece of the file
         std::vector<RecView> view;      // what the batcher reads, either way
+        std::vector<uint32_t> cum, cumn, cumc;   // running sums of read / name / comment lengths (view.size() + 1 each)
         int n = 0; int status = 0;
+        void begin() { view.clear(); cum.assign(1, 0); cumn.assign(1, 0); cumc.assign(1, 0); n = 0; status = 0; }
+        void add(const RecView &v)
+        {
+            view.push_back(v);
+            cum.push_back(cum.back() + v.len); cumn.push_back(cumn.back() + v.name_l); cumc.push_back(cumc.back() + v.cmt_l);
+        }
     };
     static const int kBlock = 4096;
     static const size_t kPiece = 8u << 20;
@@ -65,11 +73,26 @@ struct FastxReader::Prefetch {
 
 // what the batcher needs of every record, computed where the parsing is parallel: the read as the reference sees it
 // (strlen), its C and G counts (conversion-pattern assessment of undirectional libraries) and the name without "/1" "/2"
-static inline void finish_view(RecView &v)
+// bytes of `w` equal to the byte replicated in `pat`, counted eight at a time (exact zero-byte test, no carries between bytes)
+static inline uint32_t count_eq8(uint64_t w, uint64_t pat)
+{
+    const uint64_t x = w ^ pat, m = 0x7f7f7f7f7f7f7f7full;
+    return (uint32_t)__builtin_popcountll(~(((x & m) + m) | x | m));
+}
+
+static inline void finish_view(RecView &v, bool count_cg)
 {
     const uint32_t l = (uint32_t)strnlen(v.seq, v.seq_l);
     uint32_t c = 0, g = 0;
-    for (uint32_t i = 0; i < l; ++i) { c += v.seq[i] == 'C'; g += v.seq[i] == 'G'; }
+    if (count_cg) {   // only undirectional libraries look at the base composition (assessConversion)
+        uint32_t i = 0;
+        for (; i + 8 <= l; i += 8) {
+            uint64_t w;
+            memcpy(&w, v.seq + i, 8);
+            c += count_eq8(w, 0x4343434343434343ull); g += count_eq8(w, 0x4747474747474747ull);
+        }
+        for (; i < l; ++i) { c += v.seq[i] == 'C'; g += v.seq[i] == 'G'; }
+    }
     v.len = l; v.n_c = c; v.n_g = g;
     const size_t n = v.name_l;
     if (n > 2 && v.name[n - 2] == '/' && isdigit((unsigned char)v.name[n - 1])) v.name_l = (uint32_t)(n - 2);
@@ -78,7 +101,10 @@ static inline void finish_view(RecView &v)
 // Cuts strict four-line FASTQ records out of [p, end) while the record's header starts before `limit`. Stops at an
 // incomplete record (returns with *p on its header). give_up: the record at *p is something else -- anything but
 // "@name[ comment]\nSEQ\n+...\nQUAL\n" with |SEQ| == |QUAL| > 0 and no carriage returns.
-static void cut_records(const char *&p, const char *end, const char *limit, std::vector<RecView> &view, bool &give_up)
+static inline bool is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }   // isspace() in the C locale
+
+template <class Blk>
+static void cut_records(const char *&p, const char *end, const char *limit, Blk &blk, bool &give_up, bool count_cg)
 {
     while (p < limit) {
         const char *l0 = p, *e0, *e1, *e2, *e3;
@@ -91,19 +117,19 @@ static void cut_records(const char *&p, const char *end, const char *limit, std:
         if (*l0 != '@' || e0 == l0 + 1 || e1[1] != '+' || sl == 0 || sl != ql || seq[0] == '+' || seq[0] == '>' || seq[0] == '@' ||
             e0[-1] == '\r' || e1[-1] == '\r' || e3[-1] == '\r') { give_up = true; break; }
         const char *nm = l0 + 1, *q = nm;
-        while (q < e0 && !isspace((unsigned char)*q)) ++q;
+        while (q < e0 && !is_space((unsigned char)*q)) ++q;
         if (q == nm) { give_up = true; break; }
         RecView v;
         v.name = nm; v.name_l = (uint32_t)(q - nm);
         v.cmt = q < e0 ? q + 1 : e0; v.cmt_l = (uint32_t)(e0 - v.cmt);
         v.seq = seq; v.seq_l = (uint32_t)sl; v.qual = qual; v.qual_l = (uint32_t)ql;
-        finish_view(v);
-        view.push_back(v);
+        finish_view(v, count_cg);
+        blk.add(v);
         p = e3 + 1;
     }
 }
 
-FastxReader::FastxReader(const std::string &path, int n_threads) : buf_(kBuf), n_threads_(n_threads)
+FastxReader::FastxReader(const std::string &path, int n_threads, bool count_cg) : buf_(kBuf), n_threads_(n_threads), count_cg_(count_cg)
 {
     fp_ = path == "-" ? gzdopen(0, "r") : gzopen(path.c_str(), "r");
     if (!fp_) throw std::runtime_error("[E::main_mem] fail to open file `" + path + "'.");
@@ -128,6 +154,7 @@ FastxReader::~FastxReader()
     }
     if (fp_) gzclose(fp_);
     if (raw_) fclose(raw_);
+    if (map_) munmap(const_cast<char *>(map_), (size_t)file_size_);   // after the parser threads: records point into the mapping
 }
 
 void FastxReader::deliver(void *block)
@@ -153,64 +180,43 @@ void FastxReader::parse_piece(void *piece, int64_t k)
     pc.blk = P.take_spare();
     if (!pc.blk) pc.blk.reset(new Prefetch::Block);
     Prefetch::Block &b = *pc.blk;
-    b.n = 0; b.status = 0; b.view.clear();
+    b.begin();
     const int64_t lo = k * (int64_t)P.piece, hi = std::min<int64_t>(lo + (int64_t)P.piece, file_size_);
-    const int64_t from = lo > 0 ? lo - 1 : 0;                 // one byte back: is `lo` the start of a line?
-    size_t slack = 1 << 16;
-    const int fd = fileno(raw_);
-    for (;;) {
-        const int64_t want_end = std::min<int64_t>(hi + (int64_t)slack, file_size_);
-        b.raw.resize((size_t)(want_end - from));
-        size_t got = 0;
-        while (got < b.raw.size()) {
-            const ssize_t r = pread(fd, b.raw.data() + got, b.raw.size() - got, from + (int64_t)got);
-            if (r <= 0) break;
-            got += (size_t)r;
+    // the file is mapped: records are cut where they lie in the page cache (a record that starts in this piece may run on into
+    // the next), nothing is copied until the batch is filled
+    const char *base = map_, *end = map_ + file_size_, *limit = map_ + hi;
+    const char *p = map_ + lo;
+    if (lo > 0) {
+        if (p[-1] != '\n') { const char *nl = (const char *)memchr(p, '\n', end - p); p = nl ? nl + 1 : end; }   // first line start at or after lo
+        bool found = false, short_of_data = false;
+        for (int tries = 0; tries < 6 && p < limit; ++tries) {
+            const char *e0 = (const char *)memchr(p, '\n', end - p);
+            const char *e1 = e0 ? (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)) : nullptr;
+            if (!e1 || e1 + 1 >= end) { short_of_data = true; break; }
+            if (*p == '@' && e1[1] == '+') { found = true; break; }
+            p = e0 + 1;
         }
-        if (got < b.raw.size()) { pc.unsynced = true; return; }   // the file shrank under us: let the serial parser report it
-        const char *base = b.raw.data(), *end = base + got, *limit = base + (hi - from);
-        const char *p = base;
-        if (lo > 0) {
-            if (base[0] == '\n') p = base + 1;                 // first line start at or after lo
-            else { const char *nl = (const char *)memchr(base + 1, '\n', end - (base + 1)); p = nl ? nl + 1 : end; }
-            bool found = false, short_of_data = false;
-            for (int tries = 0; tries < 6 && p < limit; ++tries) {
-                const char *e0 = (const char *)memchr(p, '\n', end - p);
-                const char *e1 = e0 ? (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)) : nullptr;
-                if (!e1 || e1 + 1 >= end) { short_of_data = true; break; }
-                if (*p == '@' && e1[1] == '+') { found = true; break; }
-                p = e0 + 1;
-            }
-            if (!found && short_of_data && want_end < file_size_) {       // longer lines than the slack: read further
-                if (slack >= (64u << 20)) { pc.unsynced = true; return; }
-                slack *= 8;
-                continue;
-            }
-            if (!found && p < limit && !short_of_data) { pc.unsynced = true; return; }
-            // no complete record starts in this piece (or, at the end of the file, only a truncated one: the chain check
-            // of the consumer then sends the serial parser there)
-            if (!found) { pc.first_off = pc.end_off = -1; return; }
-        }
-        const char *first = p;
-        bool give_up = false;
-        b.view.clear();
-        cut_records(p, end, limit, b.view, give_up);
-        if (!give_up && p < limit && want_end < file_size_) {              // a record runs past the slack: read further and cut again
-            if (slack >= (1u << 30)) { pc.unsynced = true; return; }
-            slack *= 8;
-            continue;
-        }
-        pc.first_off = from + (first - base);
-        pc.end_off = from + (p - base);
-        pc.give_up = give_up || (p < limit);                               // at end of file: a tail without its final newline
-        b.n = (int)b.view.size();
-        return;
+        if (!found && p < limit && !short_of_data) { pc.unsynced = true; return; }
+        // no complete record starts in this piece (or, at the end of the file, only a truncated one: the chain check of the
+        // consumer then sends the serial parser there)
+        if (!found) { pc.first_off = pc.end_off = -1; return; }
     }
+    const char *first = p;
+    bool give_up = false;
+    cut_records(p, end, limit, b, give_up, count_cg_);
+    pc.first_off = first - base;
+    pc.end_off = p - base;
+    pc.give_up = give_up || (p < limit);           // at the end of the file: a tail without its final newline
+    b.n = (int)b.view.size();
 }
 
 bool FastxReader::pump_parallel()
 {
     Prefetch &P = *pf_;
+    void *mp = mmap(nullptr, (size_t)file_size_, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fileno(raw_), 0);
+    if (mp == MAP_FAILED) return false;            // the serial parser reads the file from its start
+    map_ = static_cast<const char *>(mp);
+    madvise(mp, (size_t)file_size_, MADV_SEQUENTIAL);
     P.n_pieces = (file_size_ + (int64_t)P.piece - 1) / (int64_t)P.piece;
     const int window = 2 * n_threads_ + 2;                     // pieces parsed ahead of the one being handed out
     std::vector<std::thread> workers;
@@ -293,7 +299,7 @@ bool FastxReader::pump_parallel()
 void FastxReader::pump()
 {
     Prefetch &P = *pf_;
-    if (raw_ && n_threads_ > 1 && file_size_ >= 2 * (int64_t)P.piece && pump_parallel()) return;
+    if (raw_ && file_size_ > 0 && pump_parallel()) return;
     for (;;) {
         std::unique_ptr<Prefetch::Block> b;
         {
@@ -306,15 +312,16 @@ void FastxReader::pump()
         b->n = 0; b->status = 0;
         if (!raw_ || !pump_fast_block(b.get())) {
             if (b->rec.size() < (size_t)Prefetch::kBlock) b->rec.resize(Prefetch::kBlock);
-            b->view.resize(Prefetch::kBlock);
+            b->begin();
             while (b->n < Prefetch::kBlock) {
                 FastxRecord &k = b->rec[b->n];
                 int r = next_raw(k);
                 if (r < 0) { b->status = r; break; }
-                RecView &v = b->view[b->n];
+                RecView v;
                 v.name = k.name.data(); v.name_l = (uint32_t)k.name.size(); v.cmt = k.comment.data(); v.cmt_l = (uint32_t)k.comment.size();
                 v.seq = k.seq.data(); v.seq_l = (uint32_t)k.seq.size(); v.qual = k.qual.data(); v.qual_l = (uint32_t)k.qual.size();
-                finish_view(v);
+                finish_view(v, count_cg_);
+                b->add(v);
                 ++b->n;
             }
         }
@@ -341,11 +348,11 @@ bool FastxReader::pump_fast_block(void *block)
     const size_t len = carry_.size() + got;
     const bool at_eof = got < Prefetch::kPiece;
     carry_.clear();
-    b.view.clear();
+    b.begin();
     const char *base = raw.data(), *end = base + len;
     const char *p = base;
     bool give_up = false;
-    cut_records(p, end, end, b.view, give_up);
+    cut_records(p, end, end, b, give_up, count_cg_);
     const size_t used = (size_t)(p - base);
     raw_off_ += (int64_t)used;
     if (!give_up && !at_eof) carry_.assign(p, end);          // an incomplete record: finish it with the next piece
@@ -376,6 +383,30 @@ RecView *FastxReader::next_ptr()
         P.cv.notify_all();
     }
 }
+
+bool FastxReader::run(RecRun &r)
+{
+    Prefetch &P = *pf_;
+    for (;;) {
+        if (P.cur && P.pos < P.cur->n) {
+            const Prefetch::Block &b = *P.cur;
+            r.v = b.view.data() + P.pos; r.cum = b.cum.data() + P.pos; r.cumn = b.cumn.data() + P.pos; r.cumc = b.cumc.data() + P.pos;
+            r.n = b.n - P.pos;
+            return true;
+        }
+        if (P.cur && P.cur->status < 0) return false;
+        std::unique_lock<std::mutex> l(P.m);
+        if (P.cur) { P.held.push_back(std::move(P.cur)); ++P.n_retired; }
+        P.cv.wait(l, [&] { return !P.ready.empty() || P.done; });
+        if (P.ready.empty()) return false;
+        P.cur = std::move(P.ready.front());
+        P.ready.pop_front();
+        P.pos = 0;
+        P.cv.notify_all();
+    }
+}
+
+void FastxReader::consume(int k) { pf_->pos += k; }
 
 uint64_t FastxReader::hold_mark()
 {
@@ -591,8 +622,122 @@ void ReadBatch::fill(const std::vector<Entry> &e, bool keep_comment, int n_threa
     for (auto &x : th) x.join();
 }
 
+// Directional libraries: every record is exactly one entry with conversion pattern 0 (first mates / single end) or 1
+// (second mates), so the batch is cut through the blocks' running sums -- whole runs of records per step, a binary search in
+// the run where the reference's rule (bwa.c:73-145: stop after the pair that brings the batch to chunk_size bases, on an even
+// number of entries) fires -- and the entries themselves are only spelled out by fill_segments(), in parallel.
+static bool plan_batch_segments(int64_t chunk_size, FastxReader *r1, FastxReader *r2, BatchPlan &plan)
+{
+    plan.segs.clear(); plan.ents.clear();
+    plan.by_segments = true; plan.paired = r2 != nullptr;
+    int64_t size = 0, n_ent = 0;
+    RecRun a, b;
+    for (;;) {
+        if (!r1->run(a)) break;
+        if (r2 && !r2->run(b)) {
+            fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", "bseq_read");
+            r1->consume(1);                        // the reference has read this record and drops it
+            break;
+        }
+        const int run = r2 ? (a.n < b.n ? a.n : b.n) : a.n;
+        auto bases = [&](int k) { return (int64_t)(a.cum[k] - a.cum[0]) + (r2 ? (int64_t)(b.cum[k] - b.cum[0]) : 0); };
+        int take = run;
+        if (size + bases(run) >= chunk_size) {     // the rule fires inside this run: first k with size + bases(k) >= chunk_size
+            int lo = 1, hi = run;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (size + bases(mid) >= chunk_size) hi = mid; else lo = mid + 1; }
+            take = lo;
+            if (!r2 && ((n_ent + take) & 1) && take < run) ++take;   // single end: the entry count must be even as well
+        }
+        ReadBatch::Seg sg; sg.a = a; sg.b = b; sg.n = take;
+        plan.segs.push_back(sg);
+        size += bases(take); n_ent += r2 ? 2 * (int64_t)take : take;
+        r1->consume(take);
+        if (r2) r2->consume(take);
+        if (size >= chunk_size && (n_ent & 1) == 0) break;
+    }
+    if (size == 0 && plan.segs.empty()) {
+        RecRun t;
+        if (r2 && !r1->run(t) && r2->run(t)) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", "bseq_read");
+    }
+    plan.mark1 = r1->hold_mark();
+    plan.mark2 = r2 ? r2->hold_mark() : 0;
+    plan.n_entries = n_ent;
+    return !plan.segs.empty();
+}
+
+void ReadBatch::fill_segments(const std::vector<Seg> &segs, bool paired, bool keep_comment, int n_threads)
+{
+    clear();
+    // where each segment starts in the flat arrays (serial over the handful of segments)
+    struct Start { size_t rec, seq, name, cmt; };
+    std::vector<Start> st(segs.size() + 1);
+    Start cur = {0, 0, 0, 0};
+    for (size_t k = 0; k < segs.size(); ++k) {
+        st[k] = cur;
+        const Seg &g = segs[k];
+        cur.rec += (size_t)g.n;
+        cur.seq += g.a.cum[g.n] - g.a.cum[0]; cur.name += g.a.cumn[g.n] - g.a.cumn[0];
+        if (keep_comment) cur.cmt += g.a.cumc[g.n] - g.a.cumc[0];
+        if (paired) {
+            cur.seq += g.b.cum[g.n] - g.b.cum[0]; cur.name += g.b.cumn[g.n] - g.b.cumn[0];
+            if (keep_comment) cur.cmt += g.b.cumc[g.n] - g.b.cumc[0];
+        }
+    }
+    st[segs.size()] = cur;
+    const size_t n_rec = cur.rec, m = paired ? 2 * n_rec : n_rec;
+    if (cur.seq > 0xfffffff0ull || cur.name > 0xfffffff0ull) throw std::runtime_error("[E::bseq_read] a batch of 4 GiB of bases or more: lower -K");
+    seq_off.resize(m + 1); name_off.resize(m + 1); cmt_off.resize(m + 1);
+    has_qual.resize(m); first.resize(m); read_group.resize(m); pattern.resize(m);
+    seq_off[m] = (uint32_t)cur.seq; name_off[m] = (uint32_t)cur.name; cmt_off[m] = (uint32_t)cur.cmt;
+    bases.resize(cur.seq); qual.resize(cur.seq); names.resize(cur.name); comments.resize(cur.cmt);
+    n = (int)m; n_bases = (int64_t)cur.seq;
+    auto put = [&](size_t e, const RecView &r, uint32_t so, uint32_t no, uint32_t co, int fst) {
+        seq_off[e] = so; name_off[e] = no; cmt_off[e] = co;
+        memcpy(bases.data() + so, r.seq, r.len);
+        const bool hq = r.qual_l != 0;
+        if (hq) memcpy(qual.data() + so, r.qual, r.len);
+        else memset(qual.data() + so, '*', r.len);
+        has_qual[e] = hq;
+        memcpy(names.data() + no, r.name, r.name_l);
+        if (keep_comment) memcpy(comments.data() + co, r.cmt, r.cmt_l);
+        first[e] = (uint8_t)fst; read_group[e] = 0; pattern[e] = (uint8_t)fst;   // first mates C->T (0), second mates G->A (1)
+    };
+    auto work = [&](size_t lo, size_t hi) {                // records [lo, hi) of the batch
+        size_t k = 0;
+        while (k + 1 < segs.size() && st[k + 1].rec <= lo) ++k;
+        for (size_t rec = lo; rec < hi;) {
+            const Seg &g = segs[k];
+            const size_t p0 = rec - st[k].rec, p1 = std::min<size_t>((size_t)g.n, hi - st[k].rec);
+            for (size_t p = p0; p < p1; ++p) {
+                uint32_t so = (uint32_t)(st[k].seq + (g.a.cum[p] - g.a.cum[0])), no = (uint32_t)(st[k].name + (g.a.cumn[p] - g.a.cumn[0]));
+                uint32_t co = (uint32_t)(st[k].cmt + (keep_comment ? g.a.cumc[p] - g.a.cumc[0] : 0));
+                if (paired) {
+                    so += g.b.cum[p] - g.b.cum[0]; no += g.b.cumn[p] - g.b.cumn[0];
+                    if (keep_comment) co += g.b.cumc[p] - g.b.cumc[0];
+                    const size_t e = 2 * (st[k].rec + p);
+                    put(e, g.a.v[p], so, no, co, 0);
+                    put(e + 1, g.b.v[p], so + g.a.v[p].len, no + g.a.v[p].name_l, co + (keep_comment ? g.a.v[p].cmt_l : 0), 1);
+                } else put(st[k].rec + p, g.a.v[p], so, no, co, 0);
+            }
+            rec = st[k].rec + p1;
+            ++k;
+        }
+    };
+    if (n_threads <= 1 || n_rec < 4096) { work(0, n_rec); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n_rec + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const size_t lo = t * chunk, hi = lo + chunk < n_rec ? lo + chunk : n_rec;
+        if (lo >= hi) break;
+        th.emplace_back(work, lo, hi);
+    }
+    for (auto &x : th) x.join();
+}
+
 bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undirectional, float substitution_proportion, BatchPlan &plan)
 {
+    if (!undirectional && !getenv("BSB_PLAN_ENTRIES")) return plan_batch_segments(chunk_size, r1, r2, plan);
+    plan.by_segments = false; plan.segs.clear();
     // serial, no copying: walk the parsers' record blocks, apply the reference's batching rule (bwa.c:73-145)
     std::vector<ReadBatch::Entry> &ents = plan.ents;
     ents.clear();
@@ -627,12 +772,14 @@ bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undire
     // the block each parser is standing in may also hold records of the next batch: it is not part of this mark
     plan.mark1 = r1->hold_mark();
     plan.mark2 = r2 ? r2->hold_mark() : 0;
+    plan.n_entries = (int64_t)ents.size();
     return !ents.empty();
 }
 
 void fill_batch(const BatchPlan &plan, FastxReader *r1, FastxReader *r2, bool keep_comment, int n_threads, ReadBatch &b)
 {
-    b.fill(plan.ents, keep_comment, n_threads);
+    if (plan.by_segments) b.fill_segments(plan.segs, plan.paired, keep_comment, n_threads);
+    else b.fill(plan.ents, keep_comment, n_threads);
     r1->release_until(plan.mark1);
     if (r2) r2->release_until(plan.mark2);
 }
@@ -655,8 +802,8 @@ static int fill_threads(int n_devices = 1)
 int host_parse_threads(int n_devices)
 {
     if (const char *e = getenv("BSB_PARSE_THREADS")) return std::max(1, atoi(e));
-    const int share = host_core_share() / 6;
-    const int want = n_devices > 1 ? n_devices / 2 + 1 : 2;
+    const int share = host_core_share() / 4;
+    const int want = n_devices + 1;   // a thread cuts about 8 M records/s out of the mapped file; a GPU takes 5-6 M per file
     return std::max(1, std::min(want, std::max(share, 1)));
 }
 

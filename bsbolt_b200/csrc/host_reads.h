@@ -99,6 +99,15 @@ struct RecView {
     uint32_t n_c, n_g;                       // 'C's and 'G's among those `len` bases (countBase, bs_helpers.cpp:31-39)
 };
 
+// A run of parsed records inside one parser block, with running sums over the records (cum*[k] = sum over the first k records
+// of the run's block prefix; only differences are meaningful): read length, name length, comment length. The batcher cuts and
+// addresses a batch through these sums without touching the records one by one.
+struct RecRun {
+    const RecView *v = nullptr;
+    const uint32_t *cum = nullptr, *cumn = nullptr, *cumc = nullptr;
+    int n = 0;
+};
+
 // Two parsers behind one interface, each on its own thread, handing blocks of records to the batcher:
 //  * fast: plain (uncompressed, seekable) files made of strict four-line FASTQ records are read in multi-megabyte
 //    pieces and cut with memchr; records are spans into the piece, nothing is copied until the batch is filled;
@@ -109,11 +118,16 @@ public:
     // n_threads > 1: a plain four-line FASTQ file is cut by that many threads at once (pieces of the file parsed
     // speculatively from a record boundary found by its "@...\n...\n+" signature, then chained in file order: a piece
     // is only handed out when it starts exactly where its predecessor ended, else the serial parser takes over there)
-    explicit FastxReader(const std::string &path, int n_threads = 1);
+    // count_cg: fill RecView::n_c / n_g (only undirectional libraries need them)
+    explicit FastxReader(const std::string &path, int n_threads = 1, bool count_cg = true);
     ~FastxReader();
     // zero-copy form for the batcher: the next record inside the parser's block (nullptr at end of input). The
     // pointer stays valid until release_held().
     RecView *next_ptr();
+    // block-wise form: the records of the current block that have not been consumed yet (false at the end of the input);
+    // consume(k) takes the first k of them. Pointers stay valid until release_held() like those of next_ptr().
+    bool run(RecRun &r);
+    void consume(int k);
     // Blocks the batcher has walked past stay alive until released. hold_mark() names the blocks fully consumed so
     // far; release_until(mark) recycles them (callable from another thread than next_ptr()'s).
     uint64_t hold_mark();
@@ -141,7 +155,9 @@ private:
     int64_t raw_off_ = 0;      // file offset of the first byte not yet handed out as a record
     std::vector<char> carry_;  // incomplete record at the end of the previous piece
     int n_threads_ = 1;
+    bool count_cg_ = true;
     int64_t file_size_ = 0;
+    const char *map_ = nullptr;   // the plain-FASTQ file, mapped (multi-threaded cutter)
 };
 
 // One batch of bseq entries (a read aligned under both conversion patterns appears twice).
@@ -164,6 +180,9 @@ struct ReadBatch {
     void reserve_like(const ReadBatch &o);   // pre-size for a batch about as large as o
     struct Entry { const RecView *rec; uint32_t len; uint8_t first, read_group, pattern; };
     void fill(const std::vector<Entry> &e, bool keep_comment, int n_threads);   // bulk, multi-threaded add()
+    // n consecutive records of file 1 (a) and, when paired, their mates in file 2 (b): one directional-library entry each
+    struct Seg { RecRun a, b; int n; };
+    void fill_segments(const std::vector<Seg> &segs, bool paired, bool keep_comment, int n_threads);
     void add(const FastxRecord &r, bool keep_comment, int first, int read_group, int pattern);
     int len(int i) const { return (int)(seq_off[i + 1] - seq_off[i]); }
     std::string name(int i) const { return std::string(names.data() + name_off[i], name_off[i + 1] - name_off[i]); }
@@ -176,7 +195,13 @@ int assess_conversion_counts(const RecView &k1, const RecView *k2, float substit
 // The two halves of read_batch(), so that cutting batch i+1 can overlap with copying batch i: plan_batch() applies the
 // reference's batching rule and records which parser records make up the batch; fill_batch() copies them into the flat
 // arrays (multi-threaded) and lets the parsers recycle the blocks.
-struct BatchPlan { std::vector<ReadBatch::Entry> ents; uint64_t mark1 = 0, mark2 = 0; };
+struct BatchPlan {
+    std::vector<ReadBatch::Entry> ents;    // undirectional libraries: the entries one by one (a read may appear twice)
+    std::vector<ReadBatch::Seg> segs;      // directional libraries: runs of records, cut and addressed through their running sums
+    bool by_segments = false, paired = false;
+    int64_t n_entries = 0;                 // bseq entries of the batch, either way
+    uint64_t mark1 = 0, mark2 = 0;
+};
 bool plan_batch(int64_t chunk_size, FastxReader *r1, FastxReader *r2, int undirectional, float substitution_proportion, BatchPlan &plan);
 void fill_batch(const BatchPlan &plan, FastxReader *r1, FastxReader *r2, bool keep_comment, int n_threads, ReadBatch &b);
 

@@ -213,9 +213,9 @@ static int readbench(int argc, char **argv)
     const int pt = atoi(argv[3]), ft = atoi(argv[4]), un = atoi(argv[5]);
     struct timespec a, b;
     clock_gettime(CLOCK_MONOTONIC, &a);
-    FastxReader r1(argv[6], pt);
+    FastxReader r1(argv[6], pt, un != 0);
     std::unique_ptr<FastxReader> r2;
-    if (argc > 7) r2.reset(new FastxReader(argv[7], pt));
+    if (argc > 7) r2.reset(new FastxReader(argv[7], pt, un != 0));
     BatchPlan plan;
     ReadBatch batch;
     long n = 0, nb = 0;
