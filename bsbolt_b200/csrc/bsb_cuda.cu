@@ -753,6 +753,7 @@ __global__ void k_max_i32(const int32_t *a, int n, int32_t *out)
 struct PinnedPool {
     std::mutex m;
     std::vector<std::pair<uint8_t *, size_t>> free_blocks;   // (block incl. 64-byte header, payload capacity)
+    std::map<size_t, int> created;                            // page-locked blocks that exist per size class, handed out or not
 };
 static PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool; return *p; }
 
@@ -781,8 +782,15 @@ static void *pinned_alloc(size_t n)
     }
     // 64-byte header: how the block was obtained + its capacity
     void *p = nullptr;
-    if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) == cudaSuccess && p) {
+    static const bool dbg_pin = getenv("BSB_DEBUG_PINNED") != nullptr;
+    const auto t_pin = std::chrono::steady_clock::now();
+    const cudaError_t pin_rc = cudaHostAlloc(&p, n + 64, cudaHostAllocPortable);
+    if (dbg_pin) fprintf(stderr, "[D::pinned] cudaHostAlloc %zu MB on demand: %.1f ms\n", n >> 20, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pin).count());
+    if (pin_rc == cudaSuccess && p) {
         ((uint64_t *)p)[0] = 0x50494e4e45445f5full; ((uint64_t *)p)[1] = n;
+        PinnedPool &P = pinned_pool();
+        std::lock_guard<std::mutex> l(P.m);
+        ++P.created[n];
         return (uint8_t *)p + 64;
     }
     cudaGetLastError();
@@ -802,21 +810,30 @@ static void pinned_release(void *q)
 }
 // Page-locks `count` blocks of the class of `bytes` ahead of need (called off the critical path once the first batch
 // has shown what sizes a run uses), so that later batches never wait ~30 ms for cudaHostAlloc.
-static void pinned_prefill(size_t bytes, int count)
+static void pinned_prefill_class(size_t n, int count);
+static void pinned_prefill(const size_t *bytes, const int *count, int n_req)
 {
-    const size_t n = pinned_class(bytes);
+    std::map<size_t, int> want;
+    for (int i = 0; i < n_req; ++i) want[pinned_class(bytes[i])] += count[i];
+    for (const auto &kv : want) pinned_prefill_class(kv.first, kv.second);
+}
+static void pinned_prefill_class(size_t n, int count)
+{
     PinnedPool &P = pinned_pool();
+    // blocks of this class that exist already, whether in the pool or handed out to the batches in flight (a later run of
+    // the same process finds the blocks of the first: nothing is page-locked again)
     int have = 0;
     {
         std::lock_guard<std::mutex> l(P.m);
-        for (auto &b : P.free_blocks) if (b.second >= n && b.second <= 2 * n + (1 << 20)) ++have;
+        have = P.created[n];
     }
     for (; have < count; ++have) {
         void *p = nullptr;
-        if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) != cudaSuccess || !p) { cudaGetLastError(); return; }
+        if (cudaHostAlloc(&p, n + 64, cudaHostAllocPortable) != cudaSuccess || !p) { cudaGetLastError(); return; }   // portable: every device of a multi-GPU run copies from it
         ((uint64_t *)p)[0] = 0x50494e4e45445f5full; ((uint64_t *)p)[1] = n;
         std::lock_guard<std::mutex> l(P.m);
         P.free_blocks.emplace_back((uint8_t *)p, n);
+        ++P.created[n];
     }
 }
 struct InstallPinnedHooks { InstallPinnedHooks() { g_host_alloc.alloc = pinned_alloc; g_host_alloc.release = pinned_release; g_host_alloc.prefill = pinned_prefill; } };

@@ -912,11 +912,11 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                     const size_t s_arena = j->res.have_text ? j->res.text.size() : j->res.arena.size();
                     const size_t s_off = j->res.text_off.size() * 4, s_stats = j->res.stats.size() * sizeof(SamStats);
                     t_prefill = std::thread([=] {
-                        g_host_alloc.prefill(s_bases, 2 * (n_jobs - 1));     // bases and qualities
-                        g_host_alloc.prefill(s_names, n_jobs - 1);
-                        g_host_alloc.prefill(s_arena + s_arena / 4 + 4096, n_jobs - 1);
-                        g_host_alloc.prefill(s_reads + s_reads / 4 + 4096, n_jobs - 1);
-                        if (s_off) { g_host_alloc.prefill(s_off + s_off / 4 + 4096, n_jobs - 1); g_host_alloc.prefill(s_stats + s_stats / 4 + 4096, n_jobs - 1); }
+                        // every job in flight holds: bases, qualities, names; result text (or arena), per-read records, offsets, statistics
+                        const size_t bytes[7] = {s_bases, s_bases, s_names, s_arena + s_arena / 4 + 4096, s_reads + s_reads / 4 + 4096,
+                                                 s_off + s_off / 4 + 4096, s_stats + s_stats / 4 + 4096};
+                        const int count[7] = {n_jobs, n_jobs, n_jobs, n_jobs, n_jobs, s_off ? n_jobs : 0, s_off ? n_jobs : 0};
+                        g_host_alloc.prefill(bytes, count, 7);
                     });
                 }
                 sum.sec_align += j->sec_align;

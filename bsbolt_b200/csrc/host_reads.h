@@ -17,7 +17,9 @@ namespace bsb {
 // once the CUDA library installs its allocator (bsb_cuda.cu). Set once, before any buffer exists.
 struct HostAllocHooks {
     void *(*alloc)(size_t); void (*release)(void *);
-    void (*prefill)(size_t bytes, int count);   // optional: make sure `count` released blocks of that size are on hand
+    // optional: make sure that, for every i, count[i] blocks able to hold bytes[i] exist (in use or on hand); requests
+    // that fall into the same size class add up
+    void (*prefill)(const size_t *bytes, const int *count, int n);
 };
 extern HostAllocHooks g_host_alloc;
 
@@ -157,7 +159,6 @@ private:
     int n_threads_ = 1;
     bool count_cg_ = true;
     int64_t file_size_ = 0;
-    const char *map_ = nullptr;   // the plain-FASTQ file, mapped (multi-threaded cutter)
 };
 
 // One batch of bseq entries (a read aligned under both conversion patterns appears twice).
