@@ -388,7 +388,10 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
             raise RuntimeError(_native.last_error())
         return time.time() - t, st
     if W:
-        run(w1, w2)
+        # W untimed warm-up steps -- repeated until every batch context of every device (three per GPU) has seen two batches, so
+        # that no device buffer is sized and no host buffer page-locked inside the timed region whatever W the caller chose
+        for _ in range(max(1, -(-6 // W))):
+            run(w1, w2)
     import torch  # only for the device synchronisation the bench contract asks for (and the NCCL fences under torchrun)
 
     def sync():

@@ -393,11 +393,48 @@ static void set_unmapped(const ReadBatch &b, int i, const EntryStats &st, std::s
 
 // Decision pass of the arbiter: which entries are printed (in input order), with BS-ambiguous groups rewritten
 // as unmapped. Serial and cheap -- no SAM text is copied here.
+static void sam_sort_range(const ReadBatch &b, std::vector<EntryStats> &st, int lo, int hi, std::vector<int> &emit, std::vector<uint8_t> &rewrite, MapStats &ms);
+
 static void sam_sort_plan(const ReadBatch &b, std::vector<EntryStats> &st, std::vector<int> &emit, std::vector<uint8_t> &rewrite, MapStats &ms)
 {
     emit.clear();
     rewrite.assign(b.n, 0);
     if (b.n == 0) return;
+    sam_sort_range(b, st, 0, b.n, emit, rewrite, ms);
+}
+
+// The same over several threads: the entries are cut where a new read name starts (a group never straddles two ranges), every
+// range is arbitrated on its own, the results are joined in input order.
+static void sam_sort_plan_parallel(const ReadBatch &b, std::vector<EntryStats> &st, std::vector<int> &emit, std::vector<uint8_t> &rewrite, MapStats &ms,
+                                   int n_threads)
+{
+    if (n_threads <= 1 || b.n < 4096) { sam_sort_plan(b, st, emit, rewrite, ms); return; }
+    auto same_name = [&](int i, int j) {
+        uint32_t li = b.name_off[i + 1] - b.name_off[i], lj = b.name_off[j + 1] - b.name_off[j];
+        return li == lj && memcmp(b.names.data() + b.name_off[i], b.names.data() + b.name_off[j], li) == 0;
+    };
+    std::vector<int> cut(n_threads + 1, b.n);
+    cut[0] = 0;
+    for (int t = 1; t < n_threads; ++t) {
+        int c = (int)((int64_t)b.n * t / n_threads);
+        if (c < cut[t - 1]) c = cut[t - 1];
+        while (c > 0 && c < b.n && same_name(c, c - 1)) ++c;   // forward to the first entry of the next name group
+        cut[t] = c;
+    }
+    rewrite.assign(b.n, 0);
+    std::vector<std::vector<int>> part(n_threads);
+    std::vector<MapStats> pms(n_threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] { if (cut[t] < cut[t + 1]) sam_sort_range(b, st, cut[t], cut[t + 1], part[t], rewrite, pms[t]); });
+    for (auto &x : th) x.join();
+    emit.clear();
+    for (int t = 0; t < n_threads; ++t) { emit.insert(emit.end(), part[t].begin(), part[t].end()); ms.add(pms[t]); }
+}
+
+static void sam_sort_range(const ReadBatch &b, std::vector<EntryStats> &st, int lo, int hi, std::vector<int> &emit, std::vector<uint8_t> &rewrite, MapStats &ms)
+{
+    emit.clear();
     std::vector<int> g[2];
     long score[2] = {0, 0};
     auto same_name = [&](int i, int j) {
@@ -434,9 +471,9 @@ static void sam_sort_plan(const ReadBatch &b, std::vector<EntryStats> &st, std::
         g[0].clear(); g[1].clear(); score[0] = score[1] = 0;
     };
     auto bank = [&](int i) { int k = b.read_group[i] ? 1 : 0; score[k] += st[i].alignment_score; g[k].push_back(i); };
-    int cur = 0;
-    bank(0);
-    for (int i = 1; i < b.n; ++i) {
+    int cur = lo;
+    bank(lo);
+    for (int i = lo + 1; i < hi; ++i) {
         if (same_name(i, cur)) bank(i);
         else { flush(); cur = i; bank(i); }
     }
@@ -933,7 +970,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                         const SamStats &x = R.stats[i];
                         st[i].alignment_score = x.alignment_score; st[i].mapped = x.mapped; st[i].bs_conflict = x.bs_conflict; st[i].crick = x.crick; st[i].paired = x.paired;
                     });
-                    sam_sort_plan(batch, st, emit, rewrite, ms);
+                    sam_sort_plan_parallel(batch, st, emit, rewrite, ms, std::min(host_threads, 8));
                     bool as_is = (int)emit.size() == batch.n;
                     for (int k = 0; as_is && k < batch.n; ++k) as_is = emit[k] == k && !rewrite[k];
                     const char *text = reinterpret_cast<const char *>(R.text.data());
@@ -965,7 +1002,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                         pc.end[i - pc.lo] = pc.buf.size();
                     }
                 }, 1);
-                sam_sort_plan(batch, st, emit, rewrite, ms);
+                sam_sort_plan_parallel(batch, st, emit, rewrite, ms, std::min(host_threads, 8));
                 bool as_is = (int)emit.size() == batch.n;
                 for (int k = 0; as_is && k < batch.n; ++k) as_is = emit[k] == k && !rewrite[k];
                 if (as_is) {

@@ -15,6 +15,7 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batches', type=int, default=12)
+    ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--warm-batches', type=int, default=0, help='warm-up on the first N batches only (0: all)')
     ap.add_argument('configs', nargs='*', default=[''])
     a = ap.parse_args()
@@ -30,19 +31,20 @@ def main():
         index_db.build_database(fa, os.path.join(work, 'db'), device=0)
     null = os.open(os.devnull, os.O_WRONLY)
     argv = ['mem'] + bench.LAUNCHER_ARGS + ['-t', '1', '-K', str(266666 * 300), '-v', '1', db, f1, f2]
-    idx = _native.Index(db, 0)
+    idx = _native.MultiIndex(db, list(range(a.gpus))) if a.gpus > 1 else _native.Index(db, 0)
+    mem = (lambda av: _native.mem_main_multi(av, idx, out_fd=null, log_fd=null)) if a.gpus > 1 else (lambda av: _native.mem_main(av, index=idx, out_fd=null, log_fd=null))
     if a.warm_batches:
         w1 = os.path.join(work, 'stw_1.fq'); w2 = os.path.join(work, 'stw_2.fq')
         bench.head_records(f1, w1, a.warm_batches * 266666); bench.head_records(f2, w2, a.warm_batches * 266666)
-        _native.mem_main(argv[:-2] + [w1, w2], index=idx, out_fd=null, log_fd=null)
+        mem(argv[:-2] + [w1, w2])
     else:
-        _native.mem_main(argv, index=idx, out_fd=null, log_fd=null)   # warm-up
+        mem(argv)   # warm-up
     for cfg in a.configs:
         kv = [x.split('=') for x in cfg.split(',') if x]
         for k, v in kv:
             os.environ[k] = v
         t = time.time()
-        rc, st = _native.mem_main(argv, index=idx, out_fd=null, log_fd=null)
+        rc, st = mem(argv)
         dt = time.time() - t
         for k, v in kv:
             del os.environ[k]
