@@ -810,14 +810,14 @@ static void pinned_release(void *q)
 }
 // Page-locks `count` blocks of the class of `bytes` ahead of need (called off the critical path once the first batch
 // has shown what sizes a run uses), so that later batches never wait ~30 ms for cudaHostAlloc.
-static void pinned_prefill_class(size_t n, int count);
-static void pinned_prefill(const size_t *bytes, const int *count, int n_req)
+static void pinned_prefill_class(size_t n, int count, bool free_only);
+static void pinned_prefill(const size_t *bytes, const int *count, int n_req, bool free_only)
 {
     std::map<size_t, int> want;
     for (int i = 0; i < n_req; ++i) want[pinned_class(bytes[i])] += count[i];
-    for (const auto &kv : want) pinned_prefill_class(kv.first, kv.second);
+    for (const auto &kv : want) pinned_prefill_class(kv.first, kv.second, free_only);
 }
-static void pinned_prefill_class(size_t n, int count)
+static void pinned_prefill_class(size_t n, int count, bool free_only)
 {
     PinnedPool &P = pinned_pool();
     // blocks of this class that exist already, whether in the pool or handed out to the batches in flight (a later run of
@@ -825,7 +825,8 @@ static void pinned_prefill_class(size_t n, int count)
     int have = 0;
     {
         std::lock_guard<std::mutex> l(P.m);
-        have = P.created[n];
+        if (free_only) { for (auto &b : P.free_blocks) if (b.second == n) ++have; }
+        else have = P.created[n];
     }
     for (; have < count; ++have) {
         void *p = nullptr;

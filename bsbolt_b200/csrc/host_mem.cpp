@@ -814,6 +814,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (host_threads > 32) host_threads = 32;
     // three batches in flight per device: one slot's host round trips and copies are covered by the other two
     int slots_per_dev = aligner.slots() / n_dev;
+    if (n_dev >= 4) slots_per_dev = std::min(slots_per_dev, 2);   // measured at 8 GPUs: 24 device threads in one process cost more than the third slot hides
     if (const char *e = getenv("BSB_GPU_SLOTS")) slots_per_dev = std::max(1, std::min(slots_per_dev, atoi(e)));
     const int slot_stride = aligner.slots() / n_dev;   // slot index of device d's first context
     const int n_slots = slots_per_dev * n_dev;
@@ -881,6 +882,15 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 q_read[dev]->push(std::move(j));
             }
             if (resident) {   // every batch is in HBM: release them all at once, each device's in its own order
+                if (!held.empty() && g_host_alloc.prefill) {
+                    // the held batches have taken the pool's blocks: page-lock the result buffers of the batches that will be
+                    // in flight now, not inside the timed region (text: about 500 bytes per entry; the rest is exact)
+                    const ReadBatch &b0 = held[0]->batch;
+                    const size_t n0 = (size_t)b0.n, s_reads = n0 * sizeof(ReadOut), s_off = (n0 + 1) * 4, s_stats = n0 * sizeof(SamStats), s_text = n0 * 520;
+                    const size_t bytes[4] = {s_reads + s_reads / 4 + 4096, s_off + s_off / 4 + 4096, s_stats + s_stats / 4 + 4096, s_text + s_text / 4 + 4096};
+                    const int want = 2 * n_slots + 2, count[4] = {want, want, want, want};
+                    g_host_alloc.prefill(bytes, count, 4, true);
+                }
                 std::vector<std::vector<std::unique_ptr<Job>>> per_dev(n_dev);
                 for (auto &h : held) { const int d = (int)(h->seq % n_dev); per_dev[d].push_back(std::move(h)); }
                 held.clear();
@@ -953,7 +963,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                         const size_t bytes[7] = {s_bases, s_bases, s_names, s_arena + s_arena / 4 + 4096, s_reads + s_reads / 4 + 4096,
                                                  s_off + s_off / 4 + 4096, s_stats + s_stats / 4 + 4096};
                         const int count[7] = {n_jobs, n_jobs, n_jobs, n_jobs, n_jobs, s_off ? n_jobs : 0, s_off ? n_jobs : 0};
-                        g_host_alloc.prefill(bytes, count, 7);
+                        g_host_alloc.prefill(bytes, count, 7, false);
                     });
                 }
                 sum.sec_align += j->sec_align;

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <unistd.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 
 namespace bsb {
 
@@ -153,6 +154,7 @@ FastxReader::~FastxReader()
     }
     if (fp_) gzclose(fp_);
     if (raw_) fclose(raw_);
+    if (map_) munmap(const_cast<char *>(map_), (size_t)file_size_);   // after the parser threads: records point into the mapping
 }
 
 void FastxReader::deliver(void *block)
@@ -180,65 +182,42 @@ void FastxReader::parse_piece(void *piece, int64_t k)
     Prefetch::Block &b = *pc.blk;
     b.begin();
     const int64_t lo = k * (int64_t)P.piece, hi = std::min<int64_t>(lo + (int64_t)P.piece, file_size_);
-    // The piece is read into the block's own buffer (pread: any thread, any offset). Mapping the file instead saves this copy
-    // but was measured 3x slower end to end: the page faults of six cutter threads queue behind the address-space lock that
-    // cudaHostAlloc / cudaMalloc of the device threads hold for milliseconds at a time.
-    const int64_t from = lo > 0 ? lo - 1 : 0;                 // one byte back: is `lo` the start of a line?
-    size_t slack = 1 << 16;
-    const int fd = fileno(raw_);
-    for (;;) {
-        const int64_t want_end = std::min<int64_t>(hi + (int64_t)slack, file_size_);
-        b.raw.resize((size_t)(want_end - from));
-        size_t got = 0;
-        while (got < b.raw.size()) {
-            const ssize_t r = pread(fd, b.raw.data() + got, b.raw.size() - got, from + (int64_t)got);
-            if (r <= 0) break;
-            got += (size_t)r;
+    // the file is mapped: records are cut where they lie in the page cache (a record that starts in this piece may run on into
+    // the next), nothing is copied until the batch is filled -- at eight GPUs the host's memory bandwidth is what the reader
+    // runs out of, and every copy of the input that is not made counts
+    const char *base = map_, *end = map_ + file_size_, *limit = map_ + hi;
+    const char *p = map_ + lo;
+    if (lo > 0) {
+        if (p[-1] != '\n') { const char *nl = (const char *)memchr(p, '\n', end - p); p = nl ? nl + 1 : end; }   // first line start at or after lo
+        bool found = false, short_of_data = false;
+        for (int tries = 0; tries < 6 && p < limit; ++tries) {
+            const char *e0 = (const char *)memchr(p, '\n', end - p);
+            const char *e1 = e0 ? (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)) : nullptr;
+            if (!e1 || e1 + 1 >= end) { short_of_data = true; break; }
+            if (*p == '@' && e1[1] == '+') { found = true; break; }
+            p = e0 + 1;
         }
-        if (got < b.raw.size()) { pc.unsynced = true; return; }   // the file shrank under us: let the serial parser report it
-        const char *base = b.raw.data(), *end = base + got, *limit = base + (hi - from);
-        const char *p = base;
-        if (lo > 0) {
-            if (base[0] == '\n') p = base + 1;                 // first line start at or after lo
-            else { const char *nl = (const char *)memchr(base + 1, '\n', end - (base + 1)); p = nl ? nl + 1 : end; }
-            bool found = false, short_of_data = false;
-            for (int tries = 0; tries < 6 && p < limit; ++tries) {
-                const char *e0 = (const char *)memchr(p, '\n', end - p);
-                const char *e1 = e0 ? (const char *)memchr(e0 + 1, '\n', end - (e0 + 1)) : nullptr;
-                if (!e1 || e1 + 1 >= end) { short_of_data = true; break; }
-                if (*p == '@' && e1[1] == '+') { found = true; break; }
-                p = e0 + 1;
-            }
-            if (!found && short_of_data && want_end < file_size_) {       // longer lines than the slack: read further
-                if (slack >= (64u << 20)) { pc.unsynced = true; return; }
-                slack *= 8;
-                continue;
-            }
-            if (!found && p < limit && !short_of_data) { pc.unsynced = true; return; }
-            // no complete record starts in this piece (or, at the end of the file, only a truncated one: the chain check
-            // of the consumer then sends the serial parser there)
-            if (!found) { pc.first_off = pc.end_off = -1; return; }
-        }
-        const char *first = p;
-        bool give_up = false;
-        b.begin();
-        cut_records(p, end, limit, b, give_up, count_cg_);
-        if (!give_up && p < limit && want_end < file_size_) {              // a record runs past the slack: read further and cut again
-            if (slack >= (1u << 30)) { pc.unsynced = true; return; }
-            slack *= 8;
-            continue;
-        }
-        pc.first_off = from + (first - base);
-        pc.end_off = from + (p - base);
-        pc.give_up = give_up || (p < limit);                               // at end of file: a tail without its final newline
-        b.n = (int)b.view.size();
-        return;
+        if (!found && p < limit && !short_of_data) { pc.unsynced = true; return; }
+        // no complete record starts in this piece (or, at the end of the file, only a truncated one: the chain check of the
+        // consumer then sends the serial parser there)
+        if (!found) { pc.first_off = pc.end_off = -1; return; }
     }
+    const char *first = p;
+    bool give_up = false;
+    cut_records(p, end, limit, b, give_up, count_cg_);
+    pc.first_off = first - base;
+    pc.end_off = p - base;
+    pc.give_up = give_up || (p < limit);           // at the end of the file: a tail without its final newline
+    b.n = (int)b.view.size();
 }
 
 bool FastxReader::pump_parallel()
 {
     Prefetch &P = *pf_;
+    void *mp = mmap(nullptr, (size_t)file_size_, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fileno(raw_), 0);
+    if (mp == MAP_FAILED) return false;            // the serial parser reads the file from its start
+    map_ = static_cast<const char *>(mp);
+    madvise(mp, (size_t)file_size_, MADV_SEQUENTIAL);
 
     P.n_pieces = (file_size_ + (int64_t)P.piece - 1) / (int64_t)P.piece;
     const int window = 2 * n_threads_ + 2;                     // pieces parsed ahead of the one being handed out
@@ -826,7 +805,7 @@ int host_parse_threads(int n_devices)
 {
     if (const char *e = getenv("BSB_PARSE_THREADS")) return std::max(1, atoi(e));
     const int share = host_core_share() / 4;
-    const int want = n_devices + 1;   // a thread cuts about 8 M records/s out of the mapped file; a GPU takes 5-6 M per file
+    const int want = n_devices + 1 < 5 ? n_devices + 1 : 5;   // a thread cuts about 8 M records/s out of the mapped file; a GPU takes 6 M per file
     return std::max(1, std::min(want, std::max(share, 1)));
 }
 

@@ -19,7 +19,8 @@ struct HostAllocHooks {
     void *(*alloc)(size_t); void (*release)(void *);
     // optional: make sure that, for every i, count[i] blocks able to hold bytes[i] exist (in use or on hand); requests
     // that fall into the same size class add up
-    void (*prefill)(const size_t *bytes, const int *count, int n);
+    // free_only: count[i] blocks must be on hand (not counting those handed out)
+    void (*prefill)(const size_t *bytes, const int *count, int n, bool free_only);
 };
 extern HostAllocHooks g_host_alloc;
 
@@ -159,6 +160,7 @@ private:
     int n_threads_ = 1;
     bool count_cg_ = true;
     int64_t file_size_ = 0;
+    const char *map_ = nullptr;   // the plain-FASTQ file, mapped (multi-threaded cutter)
 };
 
 // One batch of bseq entries (a read aligned under both conversion patterns appears twice).

@@ -24,7 +24,7 @@ def main():
     db = os.path.join(work, 'db', 'BSB_ref.fa')
     fa = bench.ensure_genome(work, os.path.dirname(db), 250)
     jobs = bench.prepare_workload(work, fa, a.batches, 266666)
-    sims = bench.run_simulation(jobs, min(8, len(jobs)))
+    sims = bench.run_simulation(jobs, min(max(8, (os.cpu_count() or 8) - 4), len(jobs)))
     f1 = os.path.join(work, 'st_1.fq'); f2 = os.path.join(work, 'st_2.fq')
     bench.concat([p[0] for p, n in sims], f1); bench.concat([p[1] for p, n in sims], f2)
     if not os.path.exists(db + '.sa'):
@@ -48,6 +48,8 @@ def main():
         dt = time.time() - t
         for k, v in kv:
             del os.environ[k]
+        if st['sec_resident'] > 0:
+            print(f'[{cfg}] resident: {st["sec_resident"]:.3f} s = {2 * 266666 * a.batches / st["sec_resident"] / 1e6:.2f} M reads/s', flush=True)
         print(f'[{cfg or "default"}] rc={rc} wall {dt:.3f} s = {2 * 266666 * a.batches / dt / 1e6:.2f} M reads/s | read {st["sec_read"]:.3f} format {st["sec_format"]:.3f} '
               f'gpu threads {st["sec_align"]:.3f} | kernels {st["ms_kernels"] / max(1, st["n_batches"]):.1f} ms/batch h2d {st["ms_h2d"] / max(1, st["n_batches"]):.1f} d2h {st["ms_d2h"] / max(1, st["n_batches"]):.1f}', flush=True)
 
