@@ -463,16 +463,37 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
     except Exception:
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
-    achieved = SEED_BYTES_PER_READ * reads_per_launch / (seed_ms / 1000) / 1e9
-    traffic, layout = None, {}
-    try:   # one ncu --set full capture of the same kernel on the same workload (profiles/r01_ncu_final.md)
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'r01_seed_traffic.json')))
+    # ---- seeding roofline: bytes COUNTED by the kernel in this run (every FM extension reads one occ block per rank: one
+    # block when both ranks fall into the same block, else two), over the CUDA-event time of the seeding stage
+    fm_ext = st_one['fm_extensions'] / n_batches
+    blk = st_one['fm_block_bytes'] or 32
+    bytes_layout = blk * (fm_ext + st_one['fm_two_block'] / n_batches)            # minimal sectors of the layout the kernel reads
+    bytes_ref = 64 * (fm_ext + st_one['fm_two_block_ref'] / n_batches)           # the same extensions over the reference's 64-byte blocks
+    achieved = bytes_layout / (seed_ms / 1000) / 1e9
+    rnd = None
+    traffic = None
+    try:   # one ncu --set full capture of the same kernel on the same workload
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r02_seed_traffic.json')))
         traffic = t['dram_bytes_read'] + t['dram_bytes_write']
-        layout = {'counted_extensions_per_launch': t['extensions_per_launch'],
-                  'counted_bytes_reference_layout': 64 * (t['extensions_per_launch'] + t['two_block_64B']),
-                  'counted_bytes_this_layout': 32 * (t['extensions_per_launch'] + t['two_block_32B'])}
     except Exception:
         pass
+    if n_dev == 1:
+        try:
+            ind, chase = _native.random_sector_peak(0)
+            rnd = {'independent_loads_gbs': ind, 'dependent_chain_per_thread_gbs': chase,
+                   'how': 'bsb_random_sector_peak: random 32-byte sectors of a 4 GiB buffer, 2048 threads per SM, 256 loads per thread, best of 3'}
+        except Exception as e:  # noqa
+            rnd = {'error': str(e)}
+    ext_ms = st_one['ms_stage'][5] / n_batches
+    cells = st_one['dp_cells_extend'] / n_batches
+    sm_mhz = float(peaks.get('sm_max_mhz', 1965.0))
+    lane_ops = 148 * 128 * sm_mhz * 1e6                     # integer lane-operations per second of the whole chip
+    dp = {'kernel': 'k_extend_lanes + k_extend_tail (banded extension, ksw_extend2 semantics)', 'cells_per_launch': cells, 'cells_per_read': cells / reads_per_launch,
+          'stage_ms_per_launch': ext_ms, 'gcups': cells / (ext_ms / 1000) / 1e9 if ext_ms else None,
+          'int_lane_ops_per_s': lane_ops, 'ops_per_cell_floor': 20,
+          'gcups_peak_at_floor': lane_ops / 20 / 1e9, 'frac_of_int_peak': (cells / (ext_ms / 1000)) / (lane_ops / 20) if ext_ms else None,
+          'note': 'cells counted by the kernel in this run; floor = the 20 integer operations of one cell of the affine-gap recurrence with band/maximum tracking '
+                  '(DESIGN.md); ncu thread-instructions per cell of the shipped kernel: profiles/r02_ncu_k_extend_lanes.md'}
     cpu = None
     parity = None
     if os.path.exists(bwa) and n_dev == 1:
@@ -507,8 +528,15 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
             'value_one_batch_in_flight': n_reads_timed / (ms_one / 1000),
             'roofline': {'bound': 'hbm', 'kernel': 'k_seed3 (+ k_pack4, k_seed3_finish: SMEM seeding stage)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
-                         'algorithmic_bytes_per_read': SEED_BYTES_PER_READ, 'kernel_ms_per_launch': seed_ms,
-                         'reads_per_launch': reads_per_launch, **layout},
+                         'algorithmic_bytes_per_launch': bytes_layout, 'algorithmic_bytes_per_read': bytes_layout / reads_per_launch,
+                         'bytes_counted': f'in this run: {blk}-byte occ blocks x (FM extensions + extensions whose two ranks lie in different blocks)',
+                         'fm_extensions_per_launch': fm_ext, 'fm_extensions_per_read': fm_ext / reads_per_launch,
+                         'reference_layout': {'bytes_per_launch': bytes_ref, 'bytes_per_read': bytes_ref / reads_per_launch, 'gbs': bytes_ref / (seed_ms / 1000) / 1e9,
+                                              'frac_of_copy_peak': bytes_ref / (seed_ms / 1000) / 1e9 / peak, 'survey_figure_bytes_per_read': SEED_BYTES_PER_READ},
+                         'random_sector_peak': rnd,
+                         'frac_of_random_sector_chain_peak': (achieved / rnd['dependent_chain_per_thread_gbs']) if rnd and rnd.get('dependent_chain_per_thread_gbs') else None,
+                         'kernel_ms_per_launch': seed_ms, 'reads_per_launch': reads_per_launch},
+            'roofline_dp': dp,
             'cpu_baseline': cpu, 'parity_vs_reference': parity, 'e2e_bam': bam_info, 'host_cores': cores, 'index': index_note,
             'stage_ms_per_batch': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
             'final_split_ms_per_batch': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},

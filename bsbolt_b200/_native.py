@@ -17,7 +17,8 @@ class RunStats(C.Structure):
                 ('ms_h2d', C.c_double), ('ms_kernels', C.c_double), ('ms_d2h', C.c_double),
                 ('ms_stage', C.c_double * 8)] + \
                [(n, C.c_int64) for n in ('n_seeds', 'h2d_bytes', 'd2h_bytes', 'kernel_launches')] + \
-               [(n, C.c_double) for n in ('sec_read', 'sec_format', 'sec_write', 'ms_select', 'ms_tasks')] + [('n_tasks', C.c_int64), ('sec_resident', C.c_double)]
+               [(n, C.c_double) for n in ('sec_read', 'sec_format', 'sec_write', 'ms_select', 'ms_tasks')] + [('n_tasks', C.c_int64), ('sec_resident', C.c_double)] + \
+               [(n, C.c_int64) for n in ('fm_extensions', 'fm_two_block', 'fm_block_bytes', 'dp_cells_extend', 'fm_two_block_ref')]
 
     def as_dict(self):
         d = {}
@@ -34,7 +35,7 @@ class Read(C.Structure):
 EXPORTS = ('bsb_version', 'bsb_last_error', 'bsb_device_count', 'bsb_index_load', 'bsb_index_free',
            'bsb_index_hbm_bytes', 'bsb_index_n_contigs', 'bsb_mem_main', 'bsb_batch_create', 'bsb_batch_align',
            'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header', 'bsb_index_build',
-           'bsb_mem_main_bam', 'bsb_stream_bam', 'bsb_index_clone', 'bsb_mem_main_multi', 'bsb_mem_main_multi_bam')
+           'bsb_mem_main_bam', 'bsb_stream_bam', 'bsb_index_clone', 'bsb_mem_main_multi', 'bsb_mem_main_multi_bam', 'bsb_random_sector_peak')
 
 
 def lib():
@@ -73,6 +74,7 @@ def lib():
     L.bsb_sam_header.restype = C.c_char_p
     L.bsb_sam_header.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
     L.bsb_index_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+    L.bsb_random_sector_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -124,6 +126,14 @@ def index_build(fasta, prefix, device=0):
     if lib().bsb_index_build(str(fasta).encode(), str(prefix).encode(), int(device), C.byref(ms)):
         raise RuntimeError(last_error())
     return ms.value
+
+
+def random_sector_peak(device=0):
+    """GB/s of random 32-byte sector reads: (independent loads, one dependent load per thread). Measurement aid."""
+    a, b = C.c_double(), C.c_double()
+    if lib().bsb_random_sector_peak(int(device), C.byref(a), C.byref(b)):
+        raise RuntimeError(last_error())
+    return a.value, b.value
 
 
 def mem_main(argv, index=None, device=0, out_fd=1, log_fd=2):

@@ -242,9 +242,10 @@ template <> struct SeedCoord<true> { typedef uint32_t type; };
 // single extension site. COMPACT: sector-sized occ blocks and 32-bit coordinates (index < 2^32 symbols).
 template <int SCAP, int MINB, bool COMPACT>
 __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView ix, BatchDev B, const uint64_t *seq4, uint4 *spill, int ltotal,
-                                                              int *next_item, int32_t *cnt_a, int32_t *cnt_b)
+                                                              int *next_item, int32_t *cnt_a, int32_t *cnt_b, unsigned long long *work)
 {
     extern __shared__ uint32_t sm_list[];
+    uint32_t n_ext = 0, n_two = 0, n_two_ref = 0;  // FM extensions of this lane; those whose two ranks lie in different occ blocks (this layout / the reference's 128-symbol blocks)
     typedef typename SeedCoord<COMPACT>::type U;
     typedef Seeder3<BasesPacked, ListRing<SCAP>, U> Machine;
     Machine sm;
@@ -299,11 +300,17 @@ __global__ void __launch_bounds__(SEED3_BLOCK, MINB) k_seed3(Opt opt, IndexView 
         if (need) {
             U xa, xb, s, na, nb, sz;
             sm.request(xa, xb, s);
+            ++n_ext;
+            n_two += COMPACT ? ((uint32_t)(xa - 1) >> 6) != ((uint32_t)(xa - 1 + s) >> 6) : ((uint64_t)(xa - 1) >> 7) != ((uint64_t)(xa - 1 + s) >> 7);
+            n_two_ref += ((uint64_t)(xa - 1) >> 7) != ((uint64_t)(xa - 1 + s) >> 7);
             fm_extend_any(ix, xa, xb, s, sm.c, na, nb, sz);
             need = sm.step(opt, ix, na, nb, sz);
         }
         __syncwarp();
     }
+    // algorithmic work of the launch, counted: extensions and occ-block sectors (measurement; two adds per extension)
+    n_ext = __reduce_add_sync(0xffffffffu, n_ext); n_two = __reduce_add_sync(0xffffffffu, n_two); n_two_ref = __reduce_add_sync(0xffffffffu, n_two_ref);
+    if (lane == 0 && work) { atomicAdd(work, (unsigned long long)n_ext); atomicAdd(work + 1, (unsigned long long)n_two); atomicAdd(work + 3, (unsigned long long)n_two_ref); }
 }
 
 // index-load time: the sector-sized occ blocks (bsb_index.h) from the reference-layout BWT
@@ -473,13 +480,15 @@ __global__ void __launch_bounds__(128, MINB) k_extend_warp(Opt opt, IndexView ix
 // control flow, then all lanes that have a row to fill meet in row(). The (h,e) rows live in shared memory, word
 // j * 32 + lane of the warp's tile. Finished reads carry their regions before mem_sort_dedup_patch; k_extend_tail ends them.
 constexpr int XL_WARPS = 2;
-__global__ void __launch_bounds__(XL_WARPS * 32) k_extend_lanes(Opt opt, IndexView ix, BatchDev B, int max_q, int row_cap, int *ctr, int chunk, int ctl_mask, int ctl_lanes)
+__global__ void __launch_bounds__(XL_WARPS * 32) k_extend_lanes(Opt opt, IndexView ix, BatchDev B, int max_q, int row_cap, int *ctr, int chunk, int ctl_mask, int ctl_lanes,
+                                                                 unsigned long long *work)
 {
     extern __shared__ uint32_t xl_rows[];
     typedef ExtLane<PackedRow<32>> Machine;
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
     Machine L;
     L.state = Machine::IDLE;
+    L.n_cells = 0;
     L.H.p = xl_rows + (size_t)wib * 32 * (size_t)row_cap + lane;
     L.row_cap = row_cap;
     {   // per-query-length tables behind the row tiles: max_gap, band limits of the left / right extension
@@ -529,6 +538,8 @@ __global__ void __launch_bounds__(XL_WARPS * 32) k_extend_lanes(Opt opt, IndexVi
         if (L.state == Machine::ROW) L.step(opt, ix, chunk);
         __syncwarp();
     }
+    const unsigned cells = __reduce_add_sync(0xffffffffu, L.n_cells);   // (a warp fills far fewer than 2^32 cells)
+    if (lane == 0 && work) atomicAdd(work + 2, (unsigned long long)cells);
 }
 
 // mem_sort_dedup_patch + ALT marks, one thread per read (serial by nature: two introsorts, the redundancy scan, now and then a
@@ -868,7 +879,7 @@ struct BatchCtx {
     // device-side SAM text
     DevBuf<char> d_names, d_qual, d_text, d_rg; DevBuf<uint32_t> d_name_off, d_text_len, d_text_off; DevBuf<uint8_t> d_has_qual; DevBuf<SamStats> d_stats;
     size_t task_cap = 0;
-    DevBuf<unsigned long long> d_used;
+    DevBuf<unsigned long long> d_used, d_work;   // d_work: counted work of the batch (FM extensions, two-block extensions, extension DP cells)
     size_t arena_cap = 0;
     int intv_cap_hint = 0;
     long launches = 0;
@@ -879,7 +890,7 @@ struct BatchCtx {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         CK(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
-        d_used.ensure(1); d_misc.ensure(32); d_ntasks.ensure(1);
+        d_used.ensure(1); d_misc.ensure(32); d_ntasks.ensure(1); d_work.ensure(4);
         ready = true;
     }
     ~BatchCtx()
@@ -1093,6 +1104,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     B.n_intv = m.d_n_intv.p; B.l_rep = m.d_l_rep.p; B.n_seed = m.d_n_seed.p; B.n_chain = m.d_n_chain.p; B.n_regs = m.d_n_regs.p;
     B.err = m.d_err.p;
 
+    CK(cudaMemsetAsync(m.d_work.p, 0, 4 * sizeof(unsigned long long), st));
     // ---- K1 ----
     if (nb) { k_convert<<<cdiv(cdiv(nb, 16), 256), 256, 0, st>>>(B, (uint32_t)nb); ++m.launches; }
     CK(cudaGetLastError());
@@ -1128,7 +1140,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         } else if (n) {
             CK(cudaMemsetAsync(m.d_cnt_ab.p, 0, 2 * (size_t)n * 4, st));
             const size_t s3_smem = (size_t)SEED3_BLOCK * s3_scap * 12;
-#define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, I.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n)
+#define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, I.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n, m.d_work.p)
             if (!I.ix.occ32) BSB_S3_LAUNCH(16, 10, false);       // >= 2^32-symbol index: reference block layout
             else if (s3_bps > 12) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 16, true); else BSB_S3_LAUNCH(16, 16, true); }
             else if (s3_bps > 10) { if (s3_scap == 8) BSB_S3_LAUNCH(8, 12, true); else if (s3_scap == 32) BSB_S3_LAUNCH(32, 12, true); else BSB_S3_LAUNCH(16, 12, true); }
@@ -1218,7 +1230,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         const int xl_bps = std::max(1, std::min(16, (int)((225 * 1024) / (xl_smem + 1024))));
         const int blocks = (int)std::min<size_t>((size_t)cdiv(n, XL_WARPS * 32), (size_t)I.n_sm * xl_bps);
         k_extend_lanes<<<blocks, XL_WARPS * 32, xl_smem, st>>>(opt, I.ix, B, max_q, xl_row_cap, m.d_misc.p + 17, env_int("BSB_XL_CHUNK", 24), env_int("BSB_XL_CTLMASK", 15),
-                                                                env_int("BSB_XL_CTLLANES", 10));
+                                                                env_int("BSB_XL_CTLLANES", 10), m.d_work.p);
         const int tail_blocks = (int)std::min<size_t>((size_t)cdiv(n, 128), (size_t)I.n_sm * 8);
         m.d_eh.ensure((size_t)tail_blocks * 128 * 2 * (max_q + 1));
         k_extend_tail<<<tail_blocks, 128, 0, st>>>(opt, I.ix, B, m.d_eh.p, max_q);
@@ -1443,12 +1455,97 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     CK(cudaEventElapsedTime(&ms, m.ev[1], m.ev[8]));
     out.ms_kernels = ms;
     out.n_seeds = S;
+    {
+        unsigned long long w[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(w, m.d_work.p, sizeof w, cudaMemcpyDeviceToHost, st));
+        m.wait();
+        out.n_fm_ext = w[0]; out.n_fm_two_block = w[1]; out.n_ext_cells = w[2]; out.n_fm_two_block_ref = w[3];
+        out.fm_block_bytes = I.ix.occ32 ? 32 : 64;
+    }
     out.h2d_bytes = nb + (size_t)(n + 1) * 4 + (size_t)n;
     out.d2h_bytes = (out.have_text ? text_bytes + (size_t)(n + 1) * 4 + (size_t)n * sizeof(SamStats) : (size_t)used) + (size_t)n * sizeof(ReadOut);
     if (out.have_text) {
         CK(cudaEventElapsedTime(&ms, m.ev[8], m.ev[11])); out.ms_text = ms;
         out.h2d_bytes += b.names.size() + (size_t)(n + 1) * 4 + nb + (size_t)n;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement: random 32-byte sectors (the denominator of the seeding roofline)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_random(uint4 *buf, uint64_t n16)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        buf[i] = make_uint4((uint32_t)x, (uint32_t)(x >> 32), (uint32_t)(x * 3), (uint32_t)(x >> 17));
+    }
+}
+
+// CHASE: the next sector index is a hash of the sector just read (a true dependency, like the rank that feeds the next
+// bwt_extend); otherwise the indices follow a per-thread generator and UNROLL loads are in flight per thread.
+template <bool CHASE>
+__global__ void __launch_bounds__(256) k_random_sectors(const uint32_t *buf, uint64_t sector_mask, int steps, unsigned long long *sink)
+{
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+    uint32_t acc = 0;
+    if (CHASE) {
+        for (int s = 0; s < steps; ++s) {
+            const uint32_t *p = buf + ((x >> 11) & sector_mask) * 8;
+            uint32_t v[8];
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+            acc += v[0] ^ v[7];
+            x = (x ^ ((uint64_t)v[3] << 32 | v[5])) * 0xBF58476D1CE4E5B9ull + s;
+        }
+    } else {
+        for (int s = 0; s < steps; s += 4) {
+            uint32_t v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x = x * 6364136223846793005ull + 1442695040888963407ull;
+                const uint32_t *p = buf + ((x >> 24) & sector_mask) * 8;
+                asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]), "=r"(v[u][4]), "=r"(v[u][5]), "=r"(v[u][6]), "=r"(v[u][7]) : "l"(p));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += v[u][0] ^ v[u][7];
+        }
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+void random_sector_peak(int device, double *gbs_independent, double *gbs_chase)
+{
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const uint64_t bytes = 4ull << 30, n_sectors = bytes / 32;           // far beyond the 126 MB L2
+    DevBuf<uint4> buf; buf.ensure(bytes / 16);
+    DevBuf<unsigned long long> sink; sink.ensure(1);
+    k_fill_random<<<prop.multiProcessorCount * 8, 256>>>(buf.p, bytes / 16);
+    CK(cudaGetLastError());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, steps = 256;        // 2048 threads per SM
+    double out[2] = {0, 0};
+    for (int mode = 0; mode < 2; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {                              // first pass warms up; best of the next three
+            CK(cudaEventRecord(e0));
+            if (mode == 0) k_random_sectors<false><<<blocks, 256>>>(reinterpret_cast<const uint32_t *>(buf.p), n_sectors - 1, steps, sink.p);
+            else k_random_sectors<true><<<blocks, 256>>>(reinterpret_cast<const uint32_t *>(buf.p), n_sectors - 1, steps, sink.p);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < best) best = ms;
+        }
+        out[mode] = (double)blocks * 256 * steps * 32 / (best * 1e-3) / 1e9;
+    }
+    CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+    if (gbs_independent) *gbs_independent = out[0];
+    if (gbs_chase) *gbs_chase = out[1];
 }
 
 } // namespace bsb

@@ -109,6 +109,7 @@ struct ExtLane {
     int i, beg, end, max, max_i, max_j, max_ie, gscore, max_off;
     // row in progress: next column (-1: not opened), target base, H(i, j-1), F, row maximum key, first / last nonzero cell, potential
     int jc, rt, rh1, rf, rkey, rfirst, rlast, rphi;
+    uint32_t n_cells;                            // DP cells this lane has filled (measurement: GCUPS of the launch)
     uint32_t tcache; int tc0, tcs;               // sixteen target bases (two bits each, first at the top) and how row i indexes them
     Row H; int row_cap;                          // words of this lane's row tile
     ExtTables T;
@@ -353,6 +354,7 @@ struct ExtLane {
             const bool at_qend = end == qlen;
             int j = jc, h1 = rh1, f = rf, key = rkey, first_nz = rfirst, last_nz = rlast, phi = rphi;
             const int stop_at = j + C < end ? j + C : end;
+            n_cells += (uint32_t)(stop_at - j);
             uint32_t *hp = H.at(j);
             int A = at_qend ? amax * (qlen - j) : 0;
             const int dA = at_qend ? amax : 0;         // away from the query end the potential is not needed: phi stays 0

@@ -47,6 +47,8 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     s->sec_read = sum.sec_read; s->sec_format = sum.sec_format; s->sec_write = sum.sec_write;
     s->ms_select = sum.ms_select; s->ms_tasks = sum.ms_tasks; s->n_tasks = (int64_t)sum.n_tasks;
     s->sec_resident = sum.sec_resident;
+    s->fm_extensions = (int64_t)sum.n_fm_ext; s->fm_two_block = (int64_t)sum.n_fm_two_block; s->fm_block_bytes = sum.fm_block_bytes;
+    s->dp_cells_extend = (int64_t)sum.n_ext_cells; s->fm_two_block_ref = (int64_t)sum.n_fm_two_block_ref;
 }
 
 extern "C" {
@@ -283,6 +285,17 @@ int bsb_batch_sam(bsb_batch_t *b, const char **sam, size_t *len, bsb_run_stats_t
 
 int bsb_batch_n_entries(const bsb_batch_t *b) { return b ? b->reads.n : 0; }
 void bsb_batch_free(bsb_batch_t *b) { delete b; }
+
+int bsb_random_sector_peak(int device, double *gbs_independent, double *gbs_chase)
+{
+    try {
+        double a = 0, b = 0;
+        random_sector_peak(device, &a, &b);
+        if (gbs_independent) *gbs_independent = a;
+        if (gbs_chase) *gbs_chase = b;
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return 1; }
+}
 
 const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv)
 {

@@ -51,6 +51,9 @@ struct BatchResult {
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0;
     double ms_select = 0, ms_tasks = 0; uint64_t n_tasks = 0;   // split of stage 7: record selection / alignment tasks
+    // counted work of the batch: FM-index extensions of the seeding kernel, how many of them read two occ blocks, bytes per
+    // occ block of the layout in use; DP cells filled by the extension kernel (0 where the warp-per-read form ran)
+    uint64_t n_fm_ext = 0, n_fm_two_block = 0, n_fm_two_block_ref = 0, n_ext_cells = 0; int fm_block_bytes = 0;
     // SAM text formatted on the device (bsb_sam.h): requested by the caller with want_text (+ the read-group id, if any);
     // when have_text comes back true, `text` holds the records of all entries back to back (entry i = bytes
     // [text_off[i], text_off[i+1])), `stats` the per-entry statistics the arbiter needs, and `arena` was not copied back.
@@ -112,6 +115,7 @@ struct RunSummary {
     double sec_resident = 0;  // BSB_RESIDENT_BENCH: wall time from "all batches resident on the device" to "last batch aligned"
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0, n_tasks = 0;
+    uint64_t n_fm_ext = 0, n_fm_two_block = 0, n_fm_two_block_ref = 0, n_ext_cells = 0; int fm_block_bytes = 0;
     double ms_select = 0, ms_tasks = 0;
     void add_timing(const BatchResult &r)
     {
@@ -119,6 +123,7 @@ struct RunSummary {
         ms_h2d += r.ms_h2d; ms_kernels += r.ms_kernels; ms_d2h += r.ms_d2h;
         for (int k = 0; k < 8; ++k) ms_stage[k] += r.ms_stage[k];
         n_seeds += r.n_seeds; h2d_bytes += r.h2d_bytes; d2h_bytes += r.d2h_bytes;
+        n_fm_ext += r.n_fm_ext; n_fm_two_block += r.n_fm_two_block; n_fm_two_block_ref += r.n_fm_two_block_ref; n_ext_cells += r.n_ext_cells; if (r.fm_block_bytes) fm_block_bytes = r.fm_block_bytes;
     }
 };
 

@@ -36,6 +36,11 @@ typedef struct {
     int64_t n_tasks;                        /* global alignments queued (records + XA entries) */
     double sec_resident;                    /* BSB_RESIDENT_BENCH=1 only (measurement): wall time from "every batch's input
                                                resident in HBM" to "last batch left the device"; 0 otherwise */
+    /* algorithmic work counted on the device during the run (roofline numerators): FM-index extensions of the seeding kernel
+       (bwt_extend calls of the reference, bwt.c:262-275), how many of them touch two occ blocks, bytes of one occ block in the
+       layout used; cells of the banded extension DP (ksw_extend2 inner loop, ksw.c:439-454) */
+    int64_t fm_extensions, fm_two_block, fm_block_bytes, dp_cells_extend;
+    int64_t fm_two_block_ref;              /* ... of them that touch two of the reference's 64-byte occ blocks (bwt.h:72-78) */
 } bsb_run_stats_t;
 
 typedef struct {
@@ -104,6 +109,12 @@ void bsb_batch_free(bsb_batch_t *b);
  * reference for references below 2^31 bases; the suffix array is built on the GPU. device_ms (optional)
  * receives the device time. */
 int bsb_index_build(const char *fasta, const char *prefix, int device, double *device_ms);
+
+/* Measurement aid for the seeding roofline: bandwidth of random 32-byte sector reads on `device` -- `independent`:
+ * every thread issues unrelated loads (what the memory system can deliver); `chase`: every thread's next address depends on
+ * the sector it has just read, one load in flight per thread at full occupancy (the access pattern of backward search, the
+ * honest ceiling for bwt_extend chains). GB/s; returns 0 on success. */
+int bsb_random_sector_peak(int device, double *gbs_independent, double *gbs_chase);
 
 /* SAM header as printed by bwa_print_sam_hdr (bwa.c:530-553); buffer valid until the next call on this thread */
 const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv);

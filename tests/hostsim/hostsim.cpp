@@ -94,7 +94,7 @@ public:
             const int amax = ext_amax(opt);
             for (int q = 0; q < max_q + 2; ++q) ext_tables_fill(opt, amax, q, tg.data(), twl.data(), twr.data());
             const ExtTables tabs = {tg.data(), twl.data(), twr.data(), getenv("HOSTSIM_EXT_NOTAB") ? 0 : max_q + 2, amax};
-            for (int l = 0; l < LANES; ++l) { L[l].state = ExtLane<PackedRow<1>>::IDLE; L[l].H.p = rows[l].data(); L[l].row_cap = max_q + 2; L[l].T = tabs; }
+            for (int l = 0; l < LANES; ++l) { L[l].state = ExtLane<PackedRow<1>>::IDLE; L[l].H.p = rows[l].data(); L[l].row_cap = max_q + 2; L[l].T = tabs; L[l].n_cells = 0; }
             int next = 0;
             for (;;) {
                 bool any = false;
