@@ -101,36 +101,53 @@ def check_index_md5(fa, db, genome_mb):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons of every GPU of the run during the timed region (B200_PROFILING.md recipe), read
+    through NVML every 50 ms on a thread (nvidia-smi -lms buffers its pipe output for seconds)."""
 
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.p = gpu, [], None
+    def __init__(self, gpus):
+        self.gpus, self.rows, self.stop_flag, self.th = list(gpus), [], False, None
 
     def start(self):
-        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100'],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(g) for g in self.gpus]
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+        self.th = threading.Thread(target=self._poll, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            for g, h in zip(self.gpus, self.handles):
+                try:
+                    self.rows.append((g, nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                      nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                except Exception:
+                    pass
+            time.sleep(0.05)
 
     def stop(self):
-        if self.p:
-            self.p.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
-        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()] or [0])
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+        self.stop_flag = True
+        if self.th:
+            self.th.join()
+        if not self.nv:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'note': 'NVML not available'}
+        nv = self.nv
+        per = {}
+        for g, mhz, _, _ in self.rows:
+            per.setdefault(g, []).append(mhz)
+        med = {str(g): sorted(v)[len(v) // 2] for g, v in per.items()}
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8), 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), 'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+        reasons = sorted({n for _, _, _, r in self.rows for n, bit in names.items() if r & bit})
+        out = {'sm_mhz': min(med.values()) if med else None, 'sm_max_mhz': max([m for _, _, m, _ in self.rows] or [0]) or None, 'reasons': reasons, 'samples': len(self.rows)}
+        if len(med) > 1:
+            out['sm_mhz_per_gpu'] = med
+        return out
 
 
 def head_records(src, dst, n):
@@ -479,9 +496,12 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
         pass
     if n_dev == 1:
         try:
-            ind, chase = _native.random_sector_peak(0)
-            rnd = {'independent_loads_gbs': ind, 'dependent_chain_per_thread_gbs': chase,
-                   'how': 'bsb_random_sector_peak: random 32-byte sectors of a 4 GiB buffer, 2048 threads per SM, 256 loads per thread, best of 3'}
+            occ_bytes = a.genome_mb * 1000000 * 4 // 2          # the occ-block array the seeding kernel walks: 4 x genome symbols, 2 symbols per byte
+            ind, chase = _native.random_sector_peak(0, occ_bytes)
+            ind4, chase4 = _native.random_sector_peak(0, 4 << 30)
+            rnd = {'independent_loads_gbs': ind, 'dependent_chain_per_thread_gbs': chase, 'footprint_bytes': occ_bytes,
+                   'over_4GiB': {'independent_loads_gbs': ind4, 'dependent_chain_per_thread_gbs': chase4},
+                   'how': 'bsb_random_sector_peak: random 32-byte sectors of a buffer the size of the occ-block array (power of two below), 2048 threads per SM, 256 loads per thread, best of 3'}
         except Exception as e:  # noqa
             rnd = {'error': str(e)}
     ext_ms = st_one['ms_stage'][5] / n_batches

@@ -74,7 +74,7 @@ def lib():
     L.bsb_sam_header.restype = C.c_char_p
     L.bsb_sam_header.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
     L.bsb_index_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
-    L.bsb_random_sector_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bsb_random_sector_peak.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -128,10 +128,10 @@ def index_build(fasta, prefix, device=0):
     return ms.value
 
 
-def random_sector_peak(device=0):
-    """GB/s of random 32-byte sector reads: (independent loads, one dependent load per thread). Measurement aid."""
+def random_sector_peak(device=0, footprint_bytes=1 << 29):
+    """GB/s of random 32-byte sector reads over about footprint_bytes: (independent loads, one dependent load per thread)."""
     a, b = C.c_double(), C.c_double()
-    if lib().bsb_random_sector_peak(int(device), C.byref(a), C.byref(b)):
+    if lib().bsb_random_sector_peak(int(device), int(footprint_bytes), C.byref(a), C.byref(b)):
         raise RuntimeError(last_error())
     return a.value, b.value
 

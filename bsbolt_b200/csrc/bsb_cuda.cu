@@ -1515,12 +1515,14 @@ __global__ void __launch_bounds__(256) k_random_sectors(const uint32_t *buf, uin
     if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
-void random_sector_peak(int device, double *gbs_independent, double *gbs_chase)
+void random_sector_peak(int device, size_t footprint_bytes, double *gbs_independent, double *gbs_chase)
 {
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    const uint64_t bytes = 4ull << 30, n_sectors = bytes / 32;           // far beyond the 126 MB L2
+    uint64_t bytes = 1ull << 26;                                         // power of two at or below the footprint asked for (64 MiB .. 16 GiB)
+    while (bytes * 2 <= (uint64_t)footprint_bytes && bytes < (16ull << 30)) bytes *= 2;
+    const uint64_t n_sectors = bytes / 32;
     DevBuf<uint4> buf; buf.ensure(bytes / 16);
     DevBuf<unsigned long long> sink; sink.ensure(1);
     k_fill_random<<<prop.multiProcessorCount * 8, 256>>>(buf.p, bytes / 16);

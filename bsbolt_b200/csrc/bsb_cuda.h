@@ -24,8 +24,8 @@ private:
     Impl *im_;
 };
 
-// random 32-byte sector reads over a 4 GiB buffer: GB/s with independent loads and with one dependent load per thread
-void random_sector_peak(int device, double *gbs_independent, double *gbs_chase);
+// random 32-byte sector reads over a buffer of about footprint_bytes: GB/s with independent loads and with one dependent load per thread
+void random_sector_peak(int device, size_t footprint_bytes, double *gbs_independent, double *gbs_chase);
 
 // Several GPUs behind one BatchAligner: one CudaAligner (one resident copy of the index) per device, kSlots batch
 // contexts each. Nothing is exchanged between the devices -- reads are independent given the index, the options, the

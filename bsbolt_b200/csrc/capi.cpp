@@ -286,11 +286,11 @@ int bsb_batch_sam(bsb_batch_t *b, const char **sam, size_t *len, bsb_run_stats_t
 int bsb_batch_n_entries(const bsb_batch_t *b) { return b ? b->reads.n : 0; }
 void bsb_batch_free(bsb_batch_t *b) { delete b; }
 
-int bsb_random_sector_peak(int device, double *gbs_independent, double *gbs_chase)
+int bsb_random_sector_peak(int device, size_t footprint_bytes, double *gbs_independent, double *gbs_chase)
 {
     try {
         double a = 0, b = 0;
-        random_sector_peak(device, &a, &b);
+        random_sector_peak(device, footprint_bytes, &a, &b);
         if (gbs_independent) *gbs_independent = a;
         if (gbs_chase) *gbs_chase = b;
         return 0;

@@ -110,11 +110,12 @@ void bsb_batch_free(bsb_batch_t *b);
  * receives the device time. */
 int bsb_index_build(const char *fasta, const char *prefix, int device, double *device_ms);
 
-/* Measurement aid for the seeding roofline: bandwidth of random 32-byte sector reads on `device` -- `independent`:
+/* Measurement aid for the seeding roofline: bandwidth of random 32-byte sector reads on `device` over a buffer of about
+ * footprint_bytes (rounded down to a power of two; give the size of the occ-block array the kernel walks) -- `independent`:
  * every thread issues unrelated loads (what the memory system can deliver); `chase`: every thread's next address depends on
  * the sector it has just read, one load in flight per thread at full occupancy (the access pattern of backward search, the
  * honest ceiling for bwt_extend chains). GB/s; returns 0 on success. */
-int bsb_random_sector_peak(int device, double *gbs_independent, double *gbs_chase);
+int bsb_random_sector_peak(int device, size_t footprint_bytes, double *gbs_independent, double *gbs_chase);
 
 /* SAM header as printed by bwa_print_sam_hdr (bwa.c:530-553); buffer valid until the next call on this thread */
 const char *bsb_sam_header(bsb_index_t *idx, int argc, char **argv);
