@@ -22,6 +22,7 @@
 #include "bsb_stages.h"
 #include "bsb_warp.cuh"
 #include "bsb_extlane.h"
+#include "bsb_rescue.h"
 #include "bsb_cuda.h"
 
 namespace bsb {
@@ -698,6 +699,126 @@ __global__ void __launch_bounds__(128) k_final_pe_heavy(Opt opt, IndexView ix, B
     for (int k = warp_next_read(ctr, gw - nw, nw); k < n; k = warp_next_read(ctr, k, nw)) stage_final_pe_heavy(opt, ix, B, heavy[k], ws, wregs, sw);
 }
 
+// ---- mate rescue by jobs (bsb_final.h: RescueJob; bsb_rescue.h: the Smith-Waterman machine) --------------------------------
+// 1. k_rescue_enum, thread per queued pair, twice: every Smith-Waterman the pair can need is counted, then (after a scan
+//    over the counts) written into the pair's own block of the job list;
+// 2. k_rescue_sw, lane per job: the jobs are drawn from a counter, each lane fills its own tile of shared memory;
+// 3. k_rescue_replay, thread per queued pair: mem_sam_pe with the rescue results looked up instead of computed. A pair with
+//    a job the lane kernel could not take (saturated score, overlong sub-optimal list) goes on to the warp-per-pair kernel.
+__global__ void __launch_bounds__(32, 16) k_rescue_enum(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, const int32_t *heavy, int n_heavy,
+                                                        RescueJob *jobs, const uint32_t *job_off, uint32_t *job_cnt, int *ctr)
+{
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    FinalWS ws; AlnReg *wregs;
+    make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
+    for (unsigned base = warp_next_group(ctr, (w & ~31u) - nw, nw); base < (unsigned)n_heavy; base = warp_next_group(ctr, base, nw)) {
+        const unsigned k = base + lane;
+        if (k >= (unsigned)n_heavy) continue;
+        unsigned int cnt = 0;
+        RescueSink sink = {jobs ? jobs + job_off[k] : nullptr, &cnt, jobs ? job_off[k + 1] - job_off[k] : 0u, (int32_t)k, 0};
+        stage_final_pe(opt, ix, B, heavy[k], ws, wregs, false, &sink, nullptr);
+        if (!jobs) job_cnt[k] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_rescue_sw(Opt opt, IndexView ix, BatchDev B, const RescueJob *jobs, SwResult *res, int n_jobs, int cap_cells,
+                                                  uint64_t *blist, int cap_b, int *ctr, int chunk)
+{
+    extern __shared__ uint32_t rs_tile[];
+    typedef SwLane<PackedRow<32>> Machine;
+    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    Machine L;
+    L.state = Machine::IDLE;
+    L.W.p = rs_tile + lane; L.cap_cells = cap_cells;
+    L.b = blist + ((size_t)blockIdx.x * 32 + lane) * (size_t)cap_b; L.cap_b = cap_b;
+    int mine = -1, pool_next = 0, pool_end = 0;
+    bool dry = false;
+    for (;;) {
+        for (;;) {                       // idle lanes take jobs
+            const unsigned want = __ballot_sync(0xffffffffu, L.state == Machine::IDLE);
+            if (!want) break;
+            if (pool_next == pool_end) {
+                if (dry) break;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(ctr, 32);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                pool_next = min(base, n_jobs); pool_end = min(base + 32, n_jobs);
+                if (pool_next == pool_end) { dry = true; break; }
+            }
+            const int rank = __popc(want & lt_mask);
+            const bool take = L.state == Machine::IDLE && pool_next + rank < pool_end;
+            if (take) {
+                mine = pool_next + rank;
+                const RescueJob jb = jobs[mine];
+                L.begin(opt, ix, jb, B.seq + B.seq_off[jb.mate_read]);
+            }
+            pool_next += __popc(__ballot_sync(0xffffffffu, take));
+        }
+        if (!__ballot_sync(0xffffffffu, L.state != Machine::IDLE)) break;      // nothing in flight and nothing left to draw
+        if (L.state == Machine::PASS_END && L.end_pass()) {
+            SwResult r = L.out;
+            if (L.err) r.score = -0x7fffffff;                                   // not this kernel's case: the pair takes the warp path
+            res[mine] = r;
+        }
+        __syncwarp();
+        if (L.state == Machine::INIT) L.init_step(64);
+        __syncwarp();
+        if (L.state == Machine::ROWS) L.step(opt, chunk);
+        __syncwarp();
+    }
+}
+
+// SMEM_LISTS: the pairs that reach this kernel are the ones with long region lists (a read of a two-letter alphabet under the
+// wrong conversion pattern has a hundred regions and as many rescue calls), and mem_matesw re-sorts the mate's list after
+// every call (mem_sort_dedup_patch, two unstable sorts whose permutations are result-visible): a serial chain of 88-byte
+// swaps. With the two lists of the pair in shared memory that chain runs at shared-memory latency: one pair per block of
+// one warp, lane 0 alone working (the lists of a pair take tens of KB: three pairs per SM either way).
+template <bool SMEM_LISTS>
+__global__ void __launch_bounds__(32, 16) k_rescue_replay(Opt opt, IndexView ix, BatchDev B, FinalLayout L, uint8_t *scratch, const int32_t *heavy, int n_heavy,
+                                                          const RescueJob *jobs, const SwResult *res, const uint32_t *job_off, int32_t *heavy2, int *n_heavy2, int *ctr,
+                                                          unsigned long long *slowest)
+{
+    extern __shared__ __align__(16) uint8_t rr_lists[];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned w = SMEM_LISTS ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x, nw = SMEM_LISTS ? gridDim.x : gridDim.x * blockDim.x;
+    FinalWS ws; AlnReg *wregs;
+    make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
+    if (SMEM_LISTS) {
+        wregs = reinterpret_cast<AlnReg *>(rr_lists);
+        if (lane) return;
+        for (;;) {
+            const unsigned k = (unsigned)atomicAdd(ctr, 1);
+            if (k >= (unsigned)n_heavy) return;
+            const RescuePre pre = {jobs + job_off[k], res + job_off[k], (int)(job_off[k + 1] - job_off[k])};
+            bool lane_ok = true;
+            for (int q = 0; q < pre.n; ++q) lane_ok = lane_ok && pre.res[q].score != -0x7fffffff;
+            if (!lane_ok) { heavy2[atomicAdd(n_heavy2, 1)] = heavy[k]; continue; }
+            const long long t0 = slowest ? clock64() : 0;
+            stage_final_pe(opt, ix, B, heavy[k], ws, wregs, false, nullptr, &pre);
+            if (slowest) {
+                const unsigned long long dt = (unsigned long long)(clock64() - t0);
+                atomicMax(slowest, (dt >> 10) << 32 | (unsigned long long)k);
+                atomicAdd(slowest + 1, dt >> 10);
+            }
+        }
+    }
+    for (unsigned base = warp_next_group(ctr, (w & ~31u) - nw, nw); base < (unsigned)n_heavy; base = warp_next_group(ctr, base, nw)) {
+        const unsigned k = base + lane;
+        if (k >= (unsigned)n_heavy) continue;
+        const RescuePre pre = {jobs + job_off[k], res + job_off[k], (int)(job_off[k + 1] - job_off[k])};
+        bool lane_ok = true;
+        for (int q = 0; q < pre.n; ++q) lane_ok = lane_ok && pre.res[q].score != -0x7fffffff;
+        if (!lane_ok) { heavy2[atomicAdd(n_heavy2, 1)] = heavy[k]; continue; }
+        const long long t0 = slowest ? clock64() : 0;
+        stage_final_pe(opt, ix, B, heavy[k], ws, wregs, false, nullptr, &pre);
+        if (slowest) {   // diagnostics (BSB_DEBUG_STATS): the slowest pair of the launch, and the cycles of all pairs together
+            const unsigned long long dt = (unsigned long long)(clock64() - t0);
+            atomicMax(slowest, (dt >> 10) << 32 | (unsigned long long)k);
+            atomicAdd(slowest + 1, dt >> 10);
+        }
+    }
+}
+
 // SAM text on the device (bsb_sam.h): sizes, then (after a scan) the bytes, one thread per entry
 __global__ void __launch_bounds__(128) k_sam_count(SamView v, int n, int is_pe, uint32_t *len, SamStats *stats)
 {
@@ -875,7 +996,7 @@ struct BatchCtx {
     DevBuf<ReadOut> d_out; DevBuf<uint8_t> d_arena, d_final_scratch, d_zbuf;
     DevBuf<AlnTask> d_tasks; DevBuf<unsigned int> d_ntasks;
     DevBuf<uint32_t> d_task_cigar; DevBuf<int32_t> d_task_ncig; DevBuf<char> d_task_text;
-    DevBuf<int32_t> d_heavy;
+    DevBuf<int32_t> d_heavy, d_heavy2; DevBuf<uint32_t> d_job_cnt, d_job_off; DevBuf<RescueJob> d_jobs; DevBuf<SwResult> d_job_res; DevBuf<uint64_t> d_blist;
     // device-side SAM text
     DevBuf<char> d_names, d_qual, d_text, d_rg; DevBuf<uint32_t> d_name_off, d_text_len, d_text_off; DevBuf<uint8_t> d_has_qual; DevBuf<SamStats> d_stats;
     size_t task_cap = 0;
@@ -890,7 +1011,7 @@ struct BatchCtx {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         CK(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
-        d_used.ensure(1); d_misc.ensure(32); d_ntasks.ensure(1); d_work.ensure(4);
+        d_used.ensure(1); d_misc.ensure(32); d_ntasks.ensure(1); d_work.ensure(8);
         ready = true;
     }
     ~BatchCtx()
@@ -1362,8 +1483,76 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                 if (coop) {
                     const int hv_smem = 4 * (int)((4 * L.sw_cap + (L.sw_cap + 3) / 4) * 4);
                     raise_dynamic_smem(k_final_pe_heavy, hv_smem);
-                    k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
-                    ++m.launches;
+                    // rescue by jobs: the 8-bit Smith-Waterman (reads below 250 / a bases) with a tile per lane that fits shared memory
+                    const int rs_cells = ((max_len + 15) / 16) * 16, rs_words = rs_cells + rs_cells / 8;
+                    const size_t rs_smem = (size_t)32 * rs_words * 4;
+                    const bool by_jobs = !getenv("BSB_RESCUE_WARP") && (long)max_len * opt.a < 250 && rs_smem <= 96 * 1024;
+                    if (by_jobs) {
+                        int h_heavy = 0;
+                        CK(cudaMemcpyAsync(&h_heavy, n_heavy, 4, cudaMemcpyDeviceToHost, st));
+                        m.wait();
+                        CK(cudaMemsetAsync(m.d_misc.p + 13, 0, 4, st));            // pairs left to the warp kernel
+                        if (h_heavy > 0) {
+                            m.d_heavy2.ensure((size_t)h_heavy + 1);
+                            m.d_job_cnt.ensure((size_t)h_heavy + 2); m.d_job_off.ensure((size_t)h_heavy + 2);
+                            CK(cudaMemsetAsync(m.d_misc.p + 22, 0, 4 * 4, st));    // work counters of the four launches below
+                            CK(cudaMemsetAsync(m.d_job_cnt.p + h_heavy, 0, 4, st));
+                            const int en_blocks = (int)std::min<size_t>(cdiv(h_heavy, fin_block), (size_t)fin_workers / fin_block);
+                            k_rescue_enum<<<en_blocks, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, h_heavy, nullptr, nullptr, m.d_job_cnt.p, m.d_misc.p + 22);
+                            size_t sb = 0;
+                            cub::DeviceScan::ExclusiveSum(nullptr, sb, m.d_job_cnt.p, m.d_job_off.p, h_heavy + 1, st);
+                            m.d_cub.ensure(sb + 16);
+                            cub::DeviceScan::ExclusiveSum(m.d_cub.p, sb, m.d_job_cnt.p, m.d_job_off.p, h_heavy + 1, st);
+                            uint32_t n_jobs = 0;
+                            CK(cudaMemcpyAsync(&n_jobs, m.d_job_off.p + h_heavy, 4, cudaMemcpyDeviceToHost, st));
+                            m.wait();
+                            m.d_jobs.ensure((size_t)n_jobs + 1); m.d_job_res.ensure((size_t)n_jobs + 1);
+                            k_rescue_enum<<<en_blocks, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, h_heavy, m.d_jobs.p, m.d_job_off.p, nullptr, m.d_misc.p + 23);
+                            if (n_jobs) {
+                                raise_dynamic_smem(k_rescue_sw, (int)rs_smem);
+                                const int rs_bps = std::max(1, std::min(24, (int)((225 * 1024) / (rs_smem + 1024))));
+                                const int rs_blocks = (int)std::min<size_t>(cdiv(n_jobs, 32), (size_t)I.n_sm * rs_bps);
+                                const int cap_b = 128;
+                                m.d_blist.ensure((size_t)rs_blocks * 32 * cap_b);
+                                k_rescue_sw<<<rs_blocks, 32, rs_smem, st>>>(opt, I.ix, B, m.d_jobs.p, m.d_job_res.p, (int)n_jobs, rs_cells, m.d_blist.p, cap_b, m.d_misc.p + 24,
+                                                                            env_int("BSB_RS_CHUNK", 32) & ~7);
+                                ++m.launches;
+                            }
+                            const bool dbg_stats = getenv("BSB_DEBUG_STATS") != nullptr;
+                            if (dbg_stats) CK(cudaMemsetAsync(m.d_work.p + 4, 0, 16, st));
+                            const size_t rr_smem = (size_t)2 * L.wreg_stride * sizeof(AlnReg);
+                            if (rr_smem <= 72 * 1024 && !getenv("BSB_REPLAY_GLOBAL")) {
+                                raise_dynamic_smem(k_rescue_replay<true>, (int)rr_smem);
+                                const int rr_blocks = (int)std::min<size_t>((size_t)h_heavy, std::min<size_t>((size_t)fin_workers, (size_t)I.n_sm * std::max<size_t>(1, (220 * 1024) / (rr_smem + 1024))));
+                                k_rescue_replay<true><<<rr_blocks, 32, rr_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, h_heavy, m.d_jobs.p, m.d_job_res.p, m.d_job_off.p,
+                                                                                      m.d_heavy2.p, m.d_misc.p + 13, m.d_misc.p + 25, dbg_stats ? m.d_work.p + 4 : nullptr);
+                            } else
+                            k_rescue_replay<false><<<en_blocks, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, h_heavy, m.d_jobs.p, m.d_job_res.p, m.d_job_off.p,
+                                                                             m.d_heavy2.p, m.d_misc.p + 13, m.d_misc.p + 25, dbg_stats ? m.d_work.p + 4 : nullptr);
+                            if (dbg_stats) {
+                                unsigned long long sl[2] = {0, 0};
+                                std::vector<uint32_t> cnt(h_heavy);
+                                CK(cudaMemcpyAsync(sl, m.d_work.p + 4, 16, cudaMemcpyDeviceToHost, st));
+                                CK(cudaMemcpyAsync(cnt.data(), m.d_job_cnt.p, (size_t)h_heavy * 4, cudaMemcpyDeviceToHost, st));
+                                m.wait();
+                                std::vector<int32_t> hv(h_heavy), nr(n);
+                                CK(cudaMemcpy(hv.data(), heavy, (size_t)h_heavy * 4, cudaMemcpyDeviceToHost));
+                                CK(cudaMemcpy(nr.data(), m.d_n_regs.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+                                const uint32_t k_slow = (uint32_t)sl[0];
+                                const int p_slow = hv[k_slow];
+                                fprintf(stderr, "[D::rescue] %d of %d pairs queued, %u Smith-Waterman jobs (max %u per pair); replay: slowest pair %d took %.2f M cycles of %.2f M in all "
+                                        "(its jobs: %u, regions %d + %d)\n", h_heavy, n >> 1, n_jobs, *std::max_element(cnt.begin(), cnt.end()), p_slow, (double)(sl[0] >> 32) * 1024 / 1e6,
+                                        (double)sl[1] * 1024 / 1e6, cnt[k_slow], nr[2 * p_slow], nr[2 * p_slow + 1]);
+                            }
+                            m.launches += 5;
+                            k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, m.d_heavy2.p, m.d_misc.p + 13, c_heavy);
+                            ++m.launches;
+                            out.n_rescue_jobs += n_jobs; out.n_rescue_pairs += (uint64_t)h_heavy;
+                        }
+                    } else {
+                        k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
+                        ++m.launches;
+                    }
                 }
             }
             else k_final_se<<<fin_workers / fin_block, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p);

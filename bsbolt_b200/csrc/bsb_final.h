@@ -628,15 +628,72 @@ BSB_HD int pestat_candidate(const Opt &opt, int64_t l_pac, const AlnReg *r0, int
     return -1;
 }
 
+// The rescue Smith-Waterman of mem_matesw depends only on the region `a`, the orientation r, the insert-size statistics and
+// the mate's sequence -- not on the mate's region list, which only decides whether the orientation is skipped and where the
+// result is inserted. So every Smith-Waterman a pair can need is known before the first one runs: they are enumerated as
+// RescueJobs, computed side by side (k_rescue_sw, bsb_rescue.h), and the sequential logic is then replayed over the results.
+struct RescueJob {
+    int64_t rb;          // window start (doubled coordinates); the window is tlen bases long
+    int32_t tlen, qlen;  // qlen = length of the mate
+    int32_t key;         // side << 16 | j << 2 | r : mem_matesw call (side, j), orientation r
+    int32_t mate_read;   // bseq entry of the mate (the query)
+    int32_t is_rev;      // the query is the reverse complement of the mate
+    int32_t pair;        // position of the pair in the heavy list
+};
+struct RescueSink {      // enumeration: where the jobs go (jobs == nullptr: they are only counted)
+    RescueJob *jobs; unsigned int *n; unsigned int cap;
+    int32_t pair, mate_read;
+};
+struct RescuePre { const RescueJob *jobs; const SwResult *res; int n; };   // replay: the jobs of this pair and their results
+
+// window of orientation r around region a (bwamem_pair.c:129-147); false: no Smith-Waterman for this orientation
+BSB_HD bool rescue_window(const Opt &opt, const IndexView &ix, const PeStat pes[4], const AlnReg &a, int l_ms, int r, int64_t *rb_, int64_t *re_, int *is_rev_)
+{
+    const int64_t l_pac = ix.l_pac;
+    const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+    int64_t rb, re;
+    if (!is_rev) {
+        rb = is_larger ? a.rb + pes[r].low : a.rb - pes[r].high;
+        re = (is_larger ? a.rb + pes[r].high : a.rb - pes[r].low) + l_ms;
+    } else {
+        rb = (is_larger ? a.rb + pes[r].low : a.rb - pes[r].high) - l_ms;
+        re = is_larger ? a.rb + pes[r].high : a.rb - pes[r].low;
+    }
+    if (rb < 0) rb = 0;
+    if (re > l_pac << 1) re = l_pac << 1;
+    int rid = -1;
+    bool have_ref = false;
+    if (rb < re) { rid = fetch_window(ix, &rb, (rb + re) >> 1, &re); have_ref = true; }
+    *rb_ = rb; *re_ = re; *is_rev_ = is_rev;
+    return have_ref && a.rid == rid && re - rb >= opt.min_seed_len;
+}
+
 // mem_matesw: Smith-Waterman of the mate inside the window implied by region `a` and the
 // insert-size distribution. `ma` is the mate's region list (grows in place).
 // `defer` (optional): instead of running the Smith-Waterman, report that one is needed and return before anything has
-// been modified -- the pair is then finalised by the warp-cooperative kernel (k_final_pe_heavy).
+// been modified -- the pair is then finalised by the rescue kernels.
+// `sink` (optional): enumeration only -- every Smith-Waterman this call can need becomes a RescueJob, nothing is modified.
+// `pre` (optional): replay -- the Smith-Waterman results are taken from the jobs computed before.
 BSB_HD int mate_rescue(const Opt &opt, const IndexView &ix, const PeStat pes[4], const AlnReg &a, int l_ms, const uint8_t *ms,
-                       RegList &ma, FinalWS &ws, int *err, int *defer = nullptr)
+                       RegList &ma, FinalWS &ws, int *err, int *defer = nullptr, int call_key = 0, RescueSink *sink = nullptr,
+                       const RescuePre *pre = nullptr)
 {
     const int64_t l_pac = ix.l_pac;
     int i, r, skip[4], n = 0;
+    if (sink) {
+        for (r = 0; r < 4; ++r) {
+            int64_t rb, re; int is_rev;
+            if (pes[r].failed || !rescue_window(opt, ix, pes, a, l_ms, r, &rb, &re, &is_rev)) continue;
+            const unsigned int k = (*sink->n)++;     // the counter belongs to the enumerating thread
+            if (sink->jobs && k < sink->cap) {
+                RescueJob jb;
+                jb.rb = rb; jb.tlen = (int32_t)(re - rb); jb.qlen = l_ms; jb.key = call_key | r; jb.mate_read = sink->mate_read;
+                jb.is_rev = is_rev; jb.pair = sink->pair;
+                sink->jobs[k] = jb;
+            }
+        }
+        return 0;
+    }
     for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
     for (i = 0; i < ma.n; ++i) {
         int64_t dist;
@@ -645,33 +702,28 @@ BSB_HD int mate_rescue(const Opt &opt, const IndexView &ix, const PeStat pes[4],
     }
     if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
     for (r = 0; r < 4; ++r) {
-        int is_rev, is_larger, rid = -1;
+        int is_rev;
         int64_t rb, re;
         if (skip[r]) continue;
-        is_rev = (r >> 1 != (r & 1));
-        is_larger = !(r >> 1);
-        const uint8_t *seq = ms;
-        if (is_rev) {
-            for (i = 0; i < l_ms; ++i) ws.rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
-            seq = ws.rev;
-        }
-        if (!is_rev) {
-            rb = is_larger ? a.rb + pes[r].low : a.rb - pes[r].high;
-            re = (is_larger ? a.rb + pes[r].high : a.rb - pes[r].low) + l_ms;
-        } else {
-            rb = (is_larger ? a.rb + pes[r].low : a.rb - pes[r].high) - l_ms;
-            re = is_larger ? a.rb + pes[r].high : a.rb - pes[r].low;
-        }
-        if (rb < 0) rb = 0;
-        if (re > l_pac << 1) re = l_pac << 1;
-        bool have_ref = false;
-        if (rb < re) { rid = fetch_window(ix, &rb, (rb + re) >> 1, &re); have_ref = true; }
-        if (have_ref && a.rid == rid && re - rb >= opt.min_seed_len) {
+        if (rescue_window(opt, ix, pes, a, l_ms, r, &rb, &re, &is_rev)) {
             if (defer) { *defer = 1; return n; }
-            int xtra = SW_XSUBO | SW_XSTART | (l_ms * opt.a < 250 ? SW_XBYTE : 0) | (opt.min_seed_len * opt.a);
-            QrySeq q = {seq, 1};
-            RefSeq t = {ix.pac, l_pac, rb, 1};
-            SwResult aln = sw_local(l_ms, q, (int)(re - rb), t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, ws.sw, err);
+            SwResult aln;
+            if (pre) {
+                int k = 0;
+                while (k < pre->n && pre->jobs[k].key != (call_key | r)) ++k;
+                if (k == pre->n) { *err = ERR_SCRATCH_OVERFLOW; return n; }   // cannot happen: the enumeration saw the same windows
+                aln = pre->res[k];
+            } else {
+                const uint8_t *seq = ms;
+                if (is_rev) {
+                    for (i = 0; i < l_ms; ++i) ws.rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
+                    seq = ws.rev;
+                }
+                int xtra = SW_XSUBO | SW_XSTART | (l_ms * opt.a < 250 ? SW_XBYTE : 0) | (opt.min_seed_len * opt.a);
+                QrySeq q = {seq, 1};
+                RefSeq t = {ix.pac, l_pac, rb, 1};
+                aln = sw_local(l_ms, q, (int)(re - rb), t, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, ws.sw, err);
+            }
             if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
                 AlnReg b;
                 alnreg_clear(b);
@@ -768,7 +820,8 @@ BSB_HD int pair_hits(const Opt &opt, const IndexView &ix, const MathTab &mt, con
 // `first` is the bseq index of read 1 of the pair (read 2 is first+1); alignments are queued in `tl`.
 BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt, const PeStat pes[4], uint64_t id, int first,
                           int l0, const uint8_t *seq0, RegList &r0, int l1, const uint8_t *seq1, RegList &r1,
-                          FinalWS &ws, Arena &ar, TaskList &tl, ReadOut *reads, int *err, int *defer = nullptr)
+                          FinalWS &ws, Arena &ar, TaskList &tl, ReadOut *reads, int *err, int *defer = nullptr,
+                          RescueSink *sink = nullptr, const RescuePre *pre = nullptr)
 {
     RegList *a[2] = {&r0, &r1};
     const int ls[2] = {l0, l1};
@@ -792,9 +845,11 @@ BSB_HD void finalize_pair(const Opt &opt, const IndexView &ix, const MathTab &mt
         }
         for (i = 0; i < 2; ++i)
             for (j = 0; j < nb[i]; ++j) {
-                mate_rescue(opt, ix, pes, bcopy[i][j], ls[!i], seqs[!i], *a[!i], ws, err, defer);
+                if (sink) sink->mate_read = first + !i;
+                mate_rescue(opt, ix, pes, bcopy[i][j], ls[!i], seqs[!i], *a[!i], ws, err, defer, i << 16 | j << 2, sink, pre);
                 if (defer && *defer) return;
             }
+        if (sink) return;   // enumeration: the jobs are out, nothing else is touched
     }
     n_pri[0] = mark_primary(opt, a[0]->n, a[0]->a, (int64_t)(id << 1 | 0), ws.z);
     n_pri[1] = mark_primary(opt, a[1]->n, a[1]->a, (int64_t)(id << 1 | 1), ws.z);

@@ -260,11 +260,13 @@ BSB_HD void stage_final_se(const Opt &opt, const IndexView &ix, BatchDev &B, int
 // K7 + K8a (paired-end): mate rescue, pairing, record selection. wregs: per-worker scratch of
 // 2*(reg_cap + max_matesw) regions
 // `defer` (optional): returns true, with nothing written, when the pair needs rescue Smith-Waterman (see mate_rescue)
-BSB_HD bool stage_final_pe(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs, bool defer = false)
+// `sink`: only enumerates the rescue Smith-Waterman jobs of the pair; `pre`: finalises the pair with their results (bsb_final.h)
+BSB_HD bool stage_final_pe(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs, bool defer = false,
+                           RescueSink *sink = nullptr, const RescuePre *pre = nullptr)
 {
     const int r0 = p << 1, r1 = r0 | 1;
     const int e0 = B.err[r0] ? B.err[r0] : B.err[r1];
-    readout_init(B.out[r0], e0); readout_init(B.out[r1], e0);
+    if (!sink) { readout_init(B.out[r0], e0); readout_init(B.out[r1], e0); }
     if (e0) return false;
     const int stride = ws.reg_cap + opt.max_matesw;
     RegList rl[2];
@@ -279,8 +281,9 @@ BSB_HD bool stage_final_pe(const Opt &opt, const IndexView &ix, BatchDev &B, int
     finalize_pair(opt, ix, B.mt, B.pes, (uint64_t)((B.n_processed >> 1) + p), r0,
                   (int)(B.seq_off[r0 + 1] - B.seq_off[r0]), B.seq + B.seq_off[r0], rl[0],
                   (int)(B.seq_off[r1 + 1] - B.seq_off[r1]), B.seq + B.seq_off[r1], rl[1],
-                  ws, B.arena, B.tasks, B.out, &err, defer ? &deferred : nullptr);
+                  ws, B.arena, B.tasks, B.out, &err, defer ? &deferred : nullptr, sink, pre);
     if (deferred) return true;
+    if (sink) return false;
     if (err) B.out[r0].err = B.out[r1].err = err;
     return false;
 }

@@ -989,14 +989,21 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                         total = R.text.size();
                         put_out(text, total);
                     } else {
-                        std::string all;
-                        for (int i : emit) {
-                            if (rewrite[i]) { set_unmapped(batch, i, st[i], tmp); all += tmp; }
-                            else all.append(text + R.text_off[i], R.text_off[i + 1] - R.text_off[i]);
-                        }
-                        total = all.size();
+                        // entries were dropped or rewritten (undirectional libraries): the text leaves in runs of consecutive
+                        // entries straight from the device's buffer -- nothing is assembled, only the rewritten records are made here
                         tw = now_sec();
-                        put_out(all.data(), total);
+                        size_t k = 0;
+                        const size_t m = emit.size();
+                        while (k < m) {
+                            const int i = emit[k];
+                            if (rewrite[i]) { set_unmapped(batch, i, st[i], tmp); put_out(tmp.data(), tmp.size()); total += tmp.size(); ++k; continue; }
+                            size_t k2 = k;
+                            while (k2 + 1 < m && emit[k2 + 1] == emit[k2] + 1 && !rewrite[emit[k2 + 1]]) ++k2;
+                            const size_t len = R.text_off[emit[k2] + 1] - R.text_off[i];
+                            put_out(text + R.text_off[i], len);
+                            total += len;
+                            k = k2 + 1;
+                        }
                     }
                 } else {
                 const int nt = std::max(1, std::min(host_threads, batch.n / 256 + 1));

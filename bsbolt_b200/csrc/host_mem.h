@@ -54,6 +54,7 @@ struct BatchResult {
     // counted work of the batch: FM-index extensions of the seeding kernel, how many of them read two occ blocks, bytes per
     // occ block of the layout in use; DP cells filled by the extension kernel (0 where the warp-per-read form ran)
     uint64_t n_fm_ext = 0, n_fm_two_block = 0, n_fm_two_block_ref = 0, n_ext_cells = 0; int fm_block_bytes = 0;
+    uint64_t n_rescue_pairs = 0, n_rescue_jobs = 0;   // pairs that needed mate-rescue Smith-Waterman; Smith-Waterman jobs computed for them
     // SAM text formatted on the device (bsb_sam.h): requested by the caller with want_text (+ the read-group id, if any);
     // when have_text comes back true, `text` holds the records of all entries back to back (entry i = bytes
     // [text_off[i], text_off[i+1])), `stats` the per-entry statistics the arbiter needs, and `arena` was not copied back.

@@ -14,6 +14,7 @@
 #include <mutex>
 #include "../../bsbolt_b200/csrc/bsb_stages.h"
 #include "../../bsbolt_b200/csrc/bsb_extlane.h"
+#include "../../bsbolt_b200/csrc/bsb_rescue.h"
 #include "../../bsbolt_b200/csrc/host_mem.h"
 
 using namespace bsb;
@@ -169,6 +170,48 @@ public:
             B.out = out.reads.data();
             B.arena.base = out.arena.data(); B.arena.used = &used; B.arena.cap = arena_cap;
             B.tasks.a = tasks.data(); B.tasks.n = &n_tasks; B.tasks.cap = (unsigned int)task_cap;
+            if (pe && getenv("HOSTSIM_RESCUE_JOBS") && (long)max_len * opt.a < 250) {   // (the device takes this path for the 8-bit kernel only)
+                // the rescue path of the device: pairs that need a rescue Smith-Waterman are set aside, all their jobs are
+                // enumerated, computed by the lane machine (bsb_rescue.h) and the pairs are finalised over the results
+                const int chunk = std::max(8, atoi(getenv("HOSTSIM_RESCUE_JOBS")) & ~7);
+                std::vector<int> heavy;
+                for (int p = 0; p < n / 2; ++p) if (stage_final_pe(opt, ix_, B, p, ws, wregs.data(), true)) heavy.push_back(p);
+                std::vector<RescueJob> jobs(heavy.size() * 8 * (size_t)opt.max_matesw + 8);
+                unsigned int n_jobs = 0;
+                for (size_t h = 0; h < heavy.size(); ++h) {       // (the device counts first, scans, then writes each pair's block)
+                    unsigned int cnt = 0;
+                    RescueSink sink = {jobs.data() + n_jobs, &cnt, (unsigned int)(jobs.size() - n_jobs), (int32_t)h, 0};
+                    stage_final_pe(opt, ix_, B, heavy[h], ws, wregs.data(), false, &sink, nullptr);
+                    n_jobs += cnt;
+                }
+                if (n_jobs > jobs.size()) throw std::runtime_error("hostsim: rescue job list too small");
+                std::vector<SwResult> res(n_jobs);
+                const int cap_cells = ((max_len + 15) / 16) * 16;
+                std::vector<uint32_t> tile(cap_cells + cap_cells / 8 + 8);
+                std::vector<uint64_t> blist(256);
+                for (unsigned int k = 0; k < n_jobs; ++k) {
+                    SwLane<PackedRow<1>> L;
+                    L.W.p = tile.data(); L.cap_cells = cap_cells; L.b = blist.data(); L.cap_b = (int)blist.size();
+                    const RescueJob &jb = jobs[k];
+                    L.begin(opt, ix_, jb, B.seq + B.seq_off[jb.mate_read]);
+                    for (;;) {
+                        if (L.state == SwLane<PackedRow<1>>::INIT) L.init_step(chunk);
+                        else if (L.state == SwLane<PackedRow<1>>::ROWS) L.step(opt, chunk);
+                        else if (L.state == SwLane<PackedRow<1>>::PASS_END) { if (L.end_pass()) break; }
+                        else break;
+                    }
+                    if (L.err) throw std::runtime_error("hostsim: rescue Smith-Waterman failed");
+                    res[k] = L.out;
+                }
+                size_t k0 = 0;
+                for (size_t h = 0; h < heavy.size(); ++h) {       // jobs of a pair are contiguous here (serial enumeration)
+                    size_t k1 = k0;
+                    while (k1 < n_jobs && jobs[k1].pair == (int32_t)h) ++k1;
+                    const RescuePre pre = {jobs.data() + k0, res.data() + k0, (int)(k1 - k0)};
+                    stage_final_pe(opt, ix_, B, heavy[h], ws, wregs.data(), false, nullptr, &pre);
+                    k0 = k1;
+                }
+            } else
             if (pe) for (int p = 0; p < n / 2; ++p) stage_final_pe(opt, ix_, B, p, ws, wregs.data());
             else for (int r = 0; r < n; ++r) stage_final_se(opt, ix_, B, r, ws, wregs.data());
             if (n_tasks <= task_cap) for (unsigned int k = 0; k < n_tasks; ++k) stage_task(opt, ix_, B, k, ws);
