@@ -1003,6 +1003,7 @@ struct BatchCtx {
     DevBuf<unsigned long long> d_used, d_work;   // d_work: counted work of the batch (FM extensions, two-block extensions, extension DP cells)
     size_t arena_cap = 0;
     int intv_cap_hint = 0;
+    int fin_scale = 1;          // growth of the finalisation scratch (see make_layout in align())
     long launches = 0;
     bool ready = false;
     void init()
@@ -1184,6 +1185,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     int max_len = 0;
     for (int i = 0; i < n; ++i) max_len = std::max(max_len, b.len(i));
     // the warp kernels keep a DP row, the query and the CIGAR/MD scratch of a read in shared memory (36 bytes x length per block)
+    // offsets into the batch's bases and into its SAM text (3 to 4 bytes of text per base) are 32-bit on the device
+    if (nb > 900000000ull) throw std::runtime_error("[E::bsbolt_b200] a batch of " + std::to_string(nb) + " bases: batches above 900 Mbp are not supported (lower -K, or -t when -K is not given)");
     if (max_len > kMaxReadLen) throw std::runtime_error("[E::bsbolt_b200] reads longer than " + std::to_string(kMaxReadLen) + " bp do not fit the per-warp shared-memory tiles of this build");
     for (int k = 0; k < 8; ++k) out.ms_stage[k] = 0;
     const bool dbg = getenv("BSB_DEBUG_TIMELINE") != nullptr;
@@ -1426,19 +1429,26 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     T("pestat_done");
 
     // ---- K6/K7/K8 ----
-    FinalLayout L;
-    memset(&L, 0, sizeof L);
-    L.max_q = max_q;
-    L.reg_cap = max_regs + 4 * opt.max_matesw + 8;
-    L.pair_cap = 4096; L.sw_cap = max_q + 32; L.sw_b = 1 << 14; L.wreg_stride = L.reg_cap + opt.max_matesw;
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    L.eh = take((size_t)2 * (max_q + 1) * 4);
-    L.cnt = take((size_t)L.reg_cap * 4); L.has_alt = take(L.reg_cap);
-    L.zz = take((size_t)L.reg_cap * 4); L.pv = take((size_t)L.pair_cap * 16); L.pu = take((size_t)L.pair_cap * 16);
-    L.sw = take((size_t)4 * L.sw_cap * 4); L.swb = take((size_t)L.sw_b * 8); L.rev = take(max_q);
-    L.wregs = take((size_t)2 * L.wreg_stride * sizeof(AlnReg));
-    L.total = o;
+    // per-worker scratch of the selection / pairing kernels. The pairing arrays and the sub-optimal list of the rescue
+    // Smith-Waterman are sized for ordinary reads; a read that overflows them (ERR_SCRATCH_OVERFLOW: hundreds of candidate
+    // pairs in a repeat) makes the stage run again with four times the room -- the reference's kvecs grow the same way
+    auto make_layout = [&](int scale) {
+        FinalLayout L;
+        memset(&L, 0, sizeof L);
+        L.max_q = max_q;
+        L.reg_cap = max_regs + 4 * opt.max_matesw + 8 + (scale > 1 ? 64 * scale : 0);
+        L.pair_cap = 512 * scale; L.sw_cap = max_q + 32; L.sw_b = 1024 * scale; L.wreg_stride = L.reg_cap + opt.max_matesw;
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+        L.eh = take((size_t)2 * (max_q + 1) * 4);
+        L.cnt = take((size_t)L.reg_cap * 4); L.has_alt = take(L.reg_cap);
+        L.zz = take((size_t)L.reg_cap * 4); L.pv = take((size_t)L.pair_cap * 16); L.pu = take((size_t)L.pair_cap * 16);
+        L.sw = take((size_t)4 * L.sw_cap * 4); L.swb = take((size_t)L.sw_b * 8); L.rev = take(max_q);
+        L.wregs = take((size_t)2 * L.wreg_stride * sizeof(AlnReg));
+        L.total = o;
+        return L;
+    };
+    FinalLayout L = make_layout(m.fin_scale);
     const int fin_block = 32;
     const int items = pe ? n >> 1 : n;
     const int fin_bps = env_int("BSB_FIN_BPS", 16);
@@ -1586,6 +1596,17 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemcpyAsync(out.reads.data(), m.d_out.p, (size_t)n * sizeof(ReadOut), cudaMemcpyDeviceToHost, st));
         m.wait();
         T("tasks_done");
+        if (m.fin_scale < 64) {   // a data-dependent scratch limit was hit: more room, same stage again
+            bool grow = false;
+            for (int r = 0; r < n && !grow; ++r) grow = out.reads[r].err == ERR_SCRATCH_OVERFLOW;
+            if (grow) {
+                m.fin_scale *= 4;
+                L = make_layout(m.fin_scale);
+                m.d_final_scratch.ensure((size_t)std::max(fin_workers, heavy_blocks * 4) * L.total);
+                if (used > m.arena_cap) m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20);
+                continue;
+            }
+        }
         if (used <= m.arena_cap) break;
         m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
     }

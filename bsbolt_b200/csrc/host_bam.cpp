@@ -185,7 +185,7 @@ void BamWriter::header(const std::string &text)
     }
     w.flush_raw();
     raw_bytes_ += w.n_raw; w.n_raw = 0;
-    fwrite(w.comp.data(), 1, w.comp.size(), f_);
+    if (fwrite(w.comp.data(), 1, w.comp.size(), f_) != w.comp.size()) throw std::runtime_error("[E::bam] writing the BAM header failed");
     file_bytes_ += w.comp.size();
     w.comp.clear();
 }
@@ -388,11 +388,11 @@ void BamWriter::close()
     if (closed_ || !f_) return;
     closed_ = true;
     if (!have_header_) header("");
-    fwrite(BGZF_EOF, 1, sizeof BGZF_EOF, f_);
+    const bool short_write = fwrite(BGZF_EOF, 1, sizeof BGZF_EOF, f_) != sizeof BGZF_EOF || fflush(f_) != 0 || ferror(f_);
     file_bytes_ += sizeof BGZF_EOF;
     const int rc = fclose(f_);
     f_ = nullptr;
-    if (rc) throw std::runtime_error("[E::bam] closing the BAM file failed");
+    if (short_write || rc) throw std::runtime_error("[E::bam] writing the end of the BAM file failed (disk full?)");
 }
 
 uint64_t stream_bam(int in_fd, const std::string &bam_path, int threads, int level)

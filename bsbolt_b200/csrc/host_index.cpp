@@ -63,6 +63,7 @@ void HostIndex::load(const std::string &hint)
         xread(sa.data() + 1, 8, n_sa - 1, fp, fn);
         fclose(fp);
     }
+    std::vector<std::string> raw_names;   // as in the .ann file (the crick copies carry their _crick_bs suffix): what .alt is matched against
     { // .ann
         std::string fn = prefix + ".ann";
         FILE *fp = xopen_rb(fn, "r");
@@ -76,6 +77,7 @@ void HostIndex::load(const std::string &hint)
             HostContig &p = contigs[i];
             if (fscanf(fp, "%u%8191s", &p.gi, str.data()) != 2) { fclose(fp); throw std::runtime_error("[E::bsb_index_load] parse error reading " + fn); }
             p.name = str.data();
+            raw_names.push_back(p.name);
             p.is_crick = strstr(p.name.c_str(), "_crick_bs") != nullptr; // checkRname (bs_helpers.cpp:65-72)
             if (p.is_crick) p.name.resize(p.name.size() - 9);             // formatCrickRname (bs_helpers.cpp:74-76)
             std::string rest;
@@ -99,7 +101,8 @@ void HostIndex::load(const std::string &hint)
                 if (line[0] == '@') continue;
                 size_t l = strcspn(line, "\t\r\n");
                 std::string nm(line, l);
-                for (auto &c : contigs) if (c.name == nm) c.is_alt = 1;
+                for (size_t k = contigs.size(); k-- > 0;)   // bns_restore hashes the untrimmed names; of equal names the last one wins
+                    if (raw_names[k] == nm) { contigs[k].is_alt = 1; break; }
             }
             fclose(fp);
         }
