@@ -10,6 +10,8 @@
 // the traversal order feeds an unstable sort -- so the tree itself is restated here: same order
 // t=5 (KB_DEFAULT_SIZE 512 with a 40-byte key), same lower-bound search inside a node, same
 // split-on-the-way-down insertion. Nodes hold chain indices and live in per-read scratch in HBM.
+// Attribution: restates klib's kbtree.h (MIT, Attractive Chaos) and BWA-MEM's mem_chain / mem_chain_flt (bwamem.c, GPLv3,
+// Heng Li): tree shape and unstable-sort order are result-visible. See NOTICE.md.
 #pragma once
 #include "bsb_index.h"
 

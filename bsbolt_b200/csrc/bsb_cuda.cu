@@ -92,64 +92,6 @@ __global__ void k_convert(BatchDev B, uint32_t n_bases)
         for (uint32_t t = 0; t < m; ++t) { B.seq[i0 + t] = (uint8_t)(so[t >> 2] >> ((t & 3) << 3)); B.oseq[i0 + t] = (uint8_t)(oo[t >> 2] >> ((t & 3) << 3)); }
 }
 
-__global__ void __launch_bounds__(64) k_seed(Opt opt, IndexView ix, BatchDev B, Intv *scratch)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
-    Intv *base = scratch + (size_t)w * 3 * B.intv_cap;
-    SeedScratch sc = {base, base + B.intv_cap, base + 2 * (size_t)B.intv_cap};
-    for (int r = w; r < B.n; r += nw) stage_seed(opt, ix, B, r, sc);
-}
-
-// K2, state-machine form: lane = read, the warp reconverges at the single FM-index extension site
-__global__ void __launch_bounds__(64) k_seed_sm(Opt opt, IndexView ix, BatchDev B, Intv *scratch)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
-    Intv *base = scratch + (size_t)w * 3 * B.intv_cap;
-    SeedScratch sc = {base, base + B.intv_cap, base + 2 * (size_t)B.intv_cap};
-    const int first = w & ~31;
-    for (int r0 = first; r0 < B.n; r0 += nw) {   // all 32 lanes of a warp iterate together
-        const int r = r0 + (w & 31);
-        stage_seed(opt, ix, B, r, sc, true, r < B.n);
-    }
-}
-
-// K2, dynamic form: every lane runs the seeding state machine of one read and, the moment that read is done,
-// pulls the next read from a global counter -- the warp never waits for its slowest read (the static form had
-// 9 of 32 lanes at the extension site on average, profiles/r01_ncu_seed_sm.md)
-__global__ void __launch_bounds__(64, 16) k_seed_dyn(Opt opt, IndexView ix, BatchDev B, Intv *scratch, int *next_read)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    Intv *base = scratch + (size_t)w * 3 * B.intv_cap;
-    SeedMachine sm;
-    sm.sub = SeedMachine::FINISHED; sm.err = 0; sm.mem_n = 0; sm.mem_a = nullptr;
-    int r = -1;
-    bool exhausted = false;
-    for (;;) {
-        bool need = false;
-        while (!need && !exhausted) {
-            if (sm.sub == SeedMachine::FINISHED) {
-                if (r >= 0) { // close the read that just finished
-                    if (!sm.err) introsort((long)sm.mem_n, sm.mem_a, LtIntvInfo());
-                    seed_finish(opt, B, r, sm.mem_a, sm.mem_n, sm.err);
-                }
-                r = atomicAdd(next_read, 1);
-                if (r >= B.n) { exhausted = true; r = -1; break; }
-                const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
-                B.n_intv[r] = 0; B.l_rep[r] = 0; B.n_seed[r] = 0;
-                if (len < opt.min_seed_len) { r = -1; continue; }
-                sm.init(opt, len, B.seq + B.seq_off[r], B.intv + (size_t)r * B.intv_cap, base, base + B.intv_cap, base + 2 * (size_t)B.intv_cap, B.intv_cap);
-            }
-            need = sm.advance(ix);
-        }
-        __syncwarp();
-        if (!__any_sync(0xffffffffu, need)) break;
-        if (need) {
-            const Intv o = fm_extend_sel(ix, sm.req, sm.req_c, sm.req_back);
-            sm.consume(o);
-        }
-    }
-}
-
 // ---- K2, two-item form (bsb_seed3.h) ---------------------------------------------------------
 // 4-bit packed copy of the converted reads, 16 bases per 64-bit word; read r starts at word (seq_off[r] >> 4) + r
 // (a closed form that never overlaps: ceil(len/16) <= (len >> 4) + 1). A lane keeps one word in registers.
@@ -412,13 +354,6 @@ __global__ void __launch_bounds__(128) k_sa(Opt opt, IndexView ix, BatchDev B, u
     stage_sa(opt, ix, B, r, g);
 }
 
-// K4, thread-per-read form (kept for comparison; `order` optionally permutes the reads)
-__global__ void __launch_bounds__(64) k_chain(Opt opt, IndexView ix, BatchDev B, const int32_t *order)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < B.n) stage_chain(opt, ix, B, order ? order[t] : t);
-}
-
 // Warps of the warp-per-read kernels draw their reads from a global counter (reads differ by orders of magnitude in
 // seeds and chains; a fixed stride leaves most warps idle behind the few that met the heavy reads). ctr == nullptr:
 // fixed stride.
@@ -450,13 +385,6 @@ __global__ void __launch_bounds__(128, 6) k_chain_warp(Opt opt, IndexView ix, Ba
 }
 
 
-
-__global__ void __launch_bounds__(64) k_extend(Opt opt, IndexView ix, BatchDev B, int32_t *eh, int max_q)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x, nw = gridDim.x * blockDim.x;
-    DpScratch dp = {eh + (size_t)w * 2 * (max_q + 1), nullptr, 0, max_q};
-    for (int r = w; r < B.n; r += nw) stage_extend(opt, ix, B, r, dp);
-}
 
 // K5, warp per read: rows of the banded extension across the lanes, (h,e) rows + query in shared memory
 template <int MINB>
@@ -601,23 +529,6 @@ __device__ __forceinline__ void make_ws(const FinalLayout &L, uint8_t *blk, Fina
     ws.sw.b = (uint64_t *)(blk + L.swb); ws.sw.cap = L.sw_cap; ws.sw.cap_b = L.sw_b;
     ws.rev = blk + L.rev;
     wregs = (AlnReg *)(blk + L.wregs);
-}
-
-// K6 + K8b, single-kernel form (one warp per queued alignment; lane 0 finishes the record)
-__global__ void __launch_bounds__(128) k_tasks(Opt opt, IndexView ix, BatchDev B, unsigned int n_tasks, uint8_t *zbuf, long z_cap, int max_q, int smem_per_warp)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int wib = threadIdx.x >> 5;
-    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    uint8_t *mine = smem + (size_t)wib * smem_per_warp;
-    WarpTask S;
-    S.H = (int32_t *)mine; S.E = S.H + (max_q + 1);
-    S.cigar = (uint32_t *)(S.E + (max_q + 1)); S.cigar_cap = 2 * max_q + 16;
-    S.md = (char *)(S.cigar + S.cigar_cap); S.md_cap = 8 * max_q + 64;
-    S.xb = S.md + S.md_cap; S.xb_cap = 4 * max_q + 64;
-    S.qs = (uint8_t *)(S.xb + S.xb_cap);
-    uint8_t *z = zbuf + (size_t)gw * z_cap;
-    for (unsigned int k = gw; k < n_tasks; k += nw) stage_task_warp(opt, ix, B, k, S, z, z_cap, max_q);
 }
 
 // K6a: global alignments of the queued alignments that need one (about one in ten), warp-cooperative
@@ -983,7 +894,7 @@ struct BatchCtx {
     cudaEvent_t ev[12];   // 0..9 stage boundaries, 10 = selection kernel done
     cudaEvent_t ev_wait = nullptr;   // blocking-sync event: the host thread sleeps instead of spinning on a core
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
-    DevBuf<Intv> d_intv, d_seed_scratch;
+    DevBuf<Intv> d_intv;
     DevBuf<uint64_t> d_seq4; DevBuf<uint4> d_spill; DevBuf<int32_t> d_cnt_ab;
     DevBuf<int32_t> d_n_intv, d_l_rep, d_n_seed, d_n_chain, d_n_regs, d_err, d_misc;
     DevBuf<uint32_t> d_seed_off;
@@ -1236,13 +1147,10 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
 
     // ---- K2 (retry with a larger interval capacity on overflow) ----
     B.intv_cap = std::max(std::max(256, 2 * max_len), m.intv_cap_hint);
-    const int seed_block = 64;
-    const int seed_workers = (int)std::min<size_t>((size_t)cdiv(n, seed_block) * seed_block, (size_t)I.n_sm * 16 * seed_block);
-    const bool seed_old = getenv("BSB_SEED_V1") || getenv("BSB_SEED_V2") || getenv("BSB_SEED_DYN");
     auto env_int = [](const char *k, int d) { const char *v = getenv(k); return v ? atoi(v) : d; };
     const int s3_scap = I.ix.occ32 ? env_int("BSB_S3_SCAP", 16) : 16, s3_total = max_len + 1, s3_bps = env_int("BSB_S3_BPS", I.ix.occ32 ? 12 : 10), s3_blocks = I.n_sm * s3_bps;
     const uint32_t n_words = (uint32_t)(nb >> 4) + (uint32_t)n + 1;
-    if (!seed_old && n) {
+    if (n) {
         m.d_seq4.ensure(n_words + 1);
         m.d_spill.ensure((size_t)s3_blocks * SEED3_BLOCK * (size_t)s3_total + 1);
         m.d_cnt_ab.ensure(2 * (size_t)n + 2);
@@ -1255,13 +1163,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaMemsetAsync(m.d_err.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_n_seed.p, 0, (size_t)(n + 1) * 4, st));
         CK(cudaMemsetAsync(m.d_misc.p, 0, 16 * 4, st));
-        if (seed_old) {
-            m.d_seed_scratch.ensure((size_t)seed_workers * 3 * B.intv_cap);
-            if (getenv("BSB_SEED_V1")) k_seed<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, I.ix, B, m.d_seed_scratch.p);
-            else if (getenv("BSB_SEED_V2")) k_seed_sm<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, I.ix, B, m.d_seed_scratch.p);
-            else k_seed_dyn<<<seed_workers / seed_block, seed_block, 0, st>>>(opt, I.ix, B, m.d_seed_scratch.p, m.d_misc.p + 8);
-            ++m.launches;
-        } else if (n) {
+        if (n) {
             CK(cudaMemsetAsync(m.d_cnt_ab.p, 0, 2 * (size_t)n * 4, st));
             const size_t s3_smem = (size_t)SEED3_BLOCK * s3_scap * 12;
 #define BSB_S3_LAUNCH(SC, MB, CP) k_seed3<SC, MB, CP><<<s3_blocks, SEED3_BLOCK, s3_smem, st>>>(opt, I.ix, B, m.d_seq4.p, m.d_spill.p, s3_total, m.d_misc.p + 8, m.d_cnt_ab.p, m.d_cnt_ab.p + n, m.d_work.p)
@@ -1318,8 +1220,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     // ---- K4 ----
     const bool dyn_sched = getenv("BSB_STATIC_SCHED") == nullptr;
     CK(cudaMemsetAsync(m.d_misc.p + 16, 0, 2 * 4, st));        // read counters of the chaining and the extension kernel
-    if (getenv("BSB_CHAIN_V1")) k_chain<<<cdiv(n, 64), 64, 0, st>>>(opt, I.ix, B, nullptr);
-    else { m.d_chain_aux.ensure(S + 1); k_chain_warp<<<I.n_sm * env_int("BSB_CHAIN_BPS", 12), 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr, m.d_chain_aux.p); }
+    m.d_chain_aux.ensure(S + 1);
+    k_chain_warp<<<I.n_sm * env_int("BSB_CHAIN_BPS", 12), 128, 0, st>>>(opt, I.ix, B, dyn_sched ? m.d_misc.p + 16 : nullptr, m.d_chain_aux.p);
     ++m.launches;
     CK(cudaGetLastError());
     // mem_flt_chained_seeds runs for reads with 5.5 ln(l) <= 0.05 l (l of about 720 and more; the kernel applies the exact
@@ -1344,7 +1246,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const int xl_row_cap = std::max(8, max_len - std::max(opt.min_seed_len, 0) + 3);
     const size_t xl_smem = (size_t)XL_WARPS * 32 * (size_t)xl_row_cap * 4 + 3 * (size_t)(max_q + 2) * 4;
     const long xl_max_score = 2L * max_len * (long)std::max(opt.a, 1) + std::max(opt.pen_clip5, opt.pen_clip3) + 64;
-    const bool ext_lanes = !getenv("BSB_EXTEND_WARP") && !getenv("BSB_EXTEND_V1") && scmat_std && xl_max_score < (1 << XL_BITS) - 1 && max_q < 4000 && xl_smem <= 100 * 1024 &&
+    const bool ext_lanes = !getenv("BSB_EXTEND_WARP") && scmat_std && xl_max_score < (1 << XL_BITS) - 1 && max_q < 4000 && xl_smem <= 100 * 1024 &&
                            opt.a > 0 && opt.b >= 0 && opt.e_ins > 0 && opt.e_del > 0;
     bool use_lanes = ext_lanes;
     int32_t h_misc[2] = {0, 0};
@@ -1359,11 +1261,6 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         m.d_eh.ensure((size_t)tail_blocks * 128 * 2 * (max_q + 1));
         k_extend_tail<<<tail_blocks, 128, 0, st>>>(opt, I.ix, B, m.d_eh.p, max_q);
         m.launches += 2;
-    } else if (getenv("BSB_EXTEND_V1")) {
-        const int ext_block = 64;
-        const int ext_workers = (int)std::min<size_t>((size_t)cdiv(n, ext_block) * ext_block, (size_t)I.n_sm * 16 * ext_block);
-        m.d_eh.ensure((size_t)ext_workers * 2 * (max_q + 1));
-        k_extend<<<ext_workers / ext_block, ext_block, 0, st>>>(opt, I.ix, B, m.d_eh.p, max_q); ++m.launches;
     } else {
         const int wpb = 4;
         const int smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 15) & ~15;
@@ -1464,9 +1361,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     const int tk_wpb = 4;
     const int tk_blocks = I.n_sm * 8;
     const long z_cap = (long)max_q * (long)(max_q + 2 * (4 * opt.w) + 64);
-    const int tk_smem_per_warp = (2 * (max_q + 1) * 4 + (2 * max_q + 16) * 4 + (8 * max_q + 64) + (4 * max_q + 64) + max_q + 31) & ~15;
     m.d_zbuf.ensure((size_t)tk_blocks * tk_wpb * z_cap);
-    raise_dynamic_smem(k_tasks, tk_wpb * tk_smem_per_warp);
     unsigned long long used = 0;
     unsigned int n_tasks = 0;
     out.reads.resize(n);
@@ -1482,8 +1377,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         B.tasks.a = m.d_tasks.p; B.tasks.n = m.d_ntasks.p; B.tasks.cap = (unsigned int)m.task_cap;
         if (items) {
             if (pe) {
-                const bool coop = !getenv("BSB_RESCUE_V1");
-                int32_t *heavy = coop ? m.d_heavy.p : nullptr;
+                const bool coop = true;    // pairs that need rescue Smith-Waterman are queued for the rescue kernels
+                int32_t *heavy = m.d_heavy.p;
                 int *n_heavy = m.d_misc.p + 12;
                 CK(cudaMemsetAsync(n_heavy, 0, 4, st));
                 int *c_fin = dyn_sched ? m.d_misc.p + 18 : nullptr, *c_heavy = dyn_sched ? m.d_misc.p + 19 : nullptr;
@@ -1574,10 +1469,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         m.wait();
         T("select_done");
         if (n_tasks > m.task_cap) { m.task_cap = (size_t)n_tasks + (size_t)n_tasks / 4 + 4096; continue; }
-        if (n_tasks && getenv("BSB_TASKS_V1")) {
-            k_tasks<<<tk_blocks, tk_wpb * 32, tk_wpb * tk_smem_per_warp, st>>>(opt, I.ix, B, n_tasks, m.d_zbuf.p, z_cap, max_q, tk_smem_per_warp);
-            ++m.launches;
-        } else if (n_tasks) {
+        if (n_tasks) {
             const int slot_cap = 2 * max_q + 16, md_cap = 8 * max_q + 64, xb_cap = 4 * max_q + 64;
             const int dp_smem_per_warp = (2 * (max_q + 1) * 4 + max_q + 31) & ~15;
             const int fin_threads = I.n_sm * 8 * 128;

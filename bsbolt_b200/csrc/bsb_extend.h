@@ -1,9 +1,12 @@
 // bsb_extend.h -- chain -> alignment regions for one read (north_star stage 5).
 //
 //   global_core()        <- bwa_gen_cigar2 part 1       (bwa.c:199-249)  score (and CIGAR) between fixed end points
-//   chain_to_regions()   <- mem_chain2aln               (bwamem.c:636-790)
+//   (mem_chain2aln, bwamem.c:636-790: the lane machine of bsb_extlane.h and chain_to_regions_warp of bsb_warp.cuh; a plain
+//    scalar form for the CPU harness lives in tests/hostsim/scalar_stages.h)
 //   patch_regions()      <- mem_patch_reg               (bwamem.c:410-439)
 //   sort_dedup_patch()   <- mem_sort_dedup_patch        (bwamem.c:441-493)
+// Attribution: restates BWA-MEM's mem_sort_dedup_patch, mem_patch_reg (bwamem.c) and bwa_gen_cigar2 (bwa.c); GPLv3, Heng Li.
+// See NOTICE.md.
 #pragma once
 #include "bsb_ksw.h"
 #include "bsb_chain.h"
@@ -143,122 +146,6 @@ BSB_HD void filter_chained_seeds(const Opt &opt, const IndexView &ix, int l_quer
     }
 }
 
-// cs: the chain's seeds (contiguous); srt: scratch u64[c.n]
-BSB_HD void chain_to_regions(const Opt &opt, const IndexView &ix, int l_query, const uint8_t *query,
-                             const Chain &c, const Seed *cs, uint64_t *srt, RegList &av, DpScratch &dp, int *err)
-{
-    int i, k, max_off[2], aw[2];
-    const int64_t l_pac = ix.l_pac;
-    int64_t rmax[2], tmp, max = 0;
-    if (c.n == 0) return;
-    rmax[0] = l_pac << 1; rmax[1] = 0;
-    for (i = 0; i < c.n; ++i) {
-        const Seed &t = cs[i];
-        int64_t b = t.rbeg - (t.qbeg + cal_max_gap(opt, t.qbeg));
-        int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + cal_max_gap(opt, l_query - t.qbeg - t.len));
-        rmax[0] = rmax[0] < b ? rmax[0] : b;
-        rmax[1] = rmax[1] > e ? rmax[1] : e;
-        if (t.len > max) max = t.len;
-    }
-    rmax[0] = rmax[0] > 0 ? rmax[0] : 0;
-    rmax[1] = rmax[1] < l_pac << 1 ? rmax[1] : l_pac << 1;
-    if (rmax[0] < l_pac && l_pac < rmax[1]) {
-        if (cs[0].rbeg < l_pac) rmax[1] = l_pac;
-        else rmax[0] = l_pac;
-    }
-    fetch_window(ix, &rmax[0], cs[0].rbeg, &rmax[1]);
-    if (l_query > dp.max_q) { *err = ERR_SCRATCH_OVERFLOW; return; }
-
-    for (i = 0; i < c.n; ++i) srt[i] = (uint64_t)cs[i].score << 32 | (uint32_t)i;
-    introsort((long)c.n, srt, LtU64());
-
-    for (k = c.n - 1; k >= 0; --k) {
-        const Seed &s = cs[(uint32_t)srt[k]];
-        for (i = 0; i < av.n; ++i) { // already covered by an earlier extension?
-            const AlnReg &p = av.a[i];
-            int64_t rd;
-            int qd, w, max_gap;
-            if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
-            if (s.len - p.seedlen0 > .1 * l_query) continue;
-            qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
-            max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
-            w = max_gap < p.w ? max_gap : p.w;
-            if (qd - rd < w && rd - qd < w) break;
-            qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
-            max_gap = cal_max_gap(opt, qd < rd ? qd : (int)rd);
-            w = max_gap < p.w ? max_gap : p.w;
-            if (qd - rd < w && rd - qd < w) break;
-        }
-        if (i < av.n) {
-            for (i = k + 1; i < c.n; ++i) { // an overlapping, non-colinear longer seed forces an extension
-                if (srt[i] == 0) continue;
-                const Seed &t = cs[(uint32_t)srt[i]];
-                if (t.len < s.len * .95) continue;
-                if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
-                if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
-            }
-            if (i == c.n) { srt[k] = 0; continue; }
-        }
-        if (av.n >= av.cap) { *err = ERR_SCRATCH_OVERFLOW; return; }
-        AlnReg &a = av.a[av.n++];
-        alnreg_clear(a);
-        a.w = aw[0] = aw[1] = opt.w;
-        a.score = a.truesc = -1;
-        a.rid = c.rid;
-
-        if (s.qbeg) { // left extension over the reversed prefix
-            QrySeq qs = {query + (s.qbeg - 1), -1};
-            RefSeq rs = {ix.pac, l_pac, s.rbeg - 1, -1};
-            tmp = s.rbeg - rmax[0];
-            ExtResult x = {0, 0, 0, 0, 0, 0};
-            for (i = 0; i < 2; ++i) {
-                int prev = a.score;
-                aw[0] = opt.w << i;
-                x = sw_extend(s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0], opt.pen_clip5, opt.zdrop, s.len * opt.a, dp.eh);
-                a.score = x.score; max_off[0] = x.max_off;
-                if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
-            }
-            if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip5) {
-                a.qb = s.qbeg - x.qle; a.rb = s.rbeg - x.tle;
-                a.truesc = a.score;
-            } else {
-                a.qb = 0; a.rb = s.rbeg - x.gtle;
-                a.truesc = x.gscore;
-            }
-        } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
-
-        if (s.qbeg + s.len != l_query) { // right extension
-            int qe = s.qbeg + s.len, sc0 = a.score;
-            int64_t re = s.rbeg + s.len - rmax[0];
-            QrySeq qs = {query + qe, 1};
-            RefSeq rs = {ix.pac, l_pac, rmax[0] + re, 1};
-            ExtResult x = {0, 0, 0, 0, 0, 0};
-            for (i = 0; i < 2; ++i) {
-                int prev = a.score;
-                aw[1] = opt.w << i;
-                x = sw_extend(l_query - qe, qs, (int)(rmax[1] - rmax[0] - re), rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, dp.eh);
-                a.score = x.score; max_off[1] = x.max_off;
-                if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
-            }
-            if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip3) {
-                a.qe = qe + x.qle; a.re = rmax[0] + re + x.tle;
-                a.truesc += a.score - sc0;
-            } else {
-                a.qe = l_query; a.re = rmax[0] + re + x.gtle;
-                a.truesc += x.gscore - sc0;
-            }
-        } else { a.qe = l_query; a.re = s.rbeg + s.len; }
-
-        a.seedcov = 0;
-        for (i = 0; i < c.n; ++i) {
-            const Seed &t = cs[i];
-            if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
-        }
-        a.w = aw[0] > aw[1] ? aw[0] : aw[1];
-        a.seedlen0 = s.len;
-        a.frac_rep = c.frac_rep;
-    }
-}
 
 // Can regions a (left) and b (right) be one alignment? Returns the merged score or 0.
 BSB_HD int patch_regions(const Opt &opt, const IndexView &ix, const uint8_t *query, const AlnReg &a, const AlnReg &b, int *_w, DpScratch &dp, int *err)

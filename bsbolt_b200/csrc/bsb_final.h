@@ -15,6 +15,8 @@
 // (log in MAPQ, log/erfc in pairing) is tabulated by the HOST with glibc for the integer arguments
 // that can occur and shipped to HBM (MathTab); the device only does IEEE add/mul/div on them
 // (kernels are compiled with -fmad=false so no contraction changes a rounding).
+// Attribution: restates BWA-MEM's record selection, MAPQ, pairing and mate rescue (bwamem.c, bwamem_pair.c, bwamem_extra.c;
+// GPLv3, Heng Li) and BSBolt's bisulfite tags (bs_helpers.cpp; MIT, Colin P. Farrell). See NOTICE.md.
 #pragma once
 #include "bsb_extend.h"
 

@@ -3,6 +3,8 @@
 // Device functions are written once and compiled by nvcc for sm_100a (the product) and by g++
 // for the CPU-side unit tests under tests/hostsim (test infrastructure only; the product library
 // contains no CPU execution path for them).
+// Attribution: introsort/comb_sort restate klib's ksort.h (ks_introsort, ks_combsort; MIT, Attractive Chaos) move for move --
+// the order they leave equal keys in is visible in the reference's output. See NOTICE.md.
 #pragma once
 #include <stdint.h>
 #include "bsb_types.h"

@@ -1,6 +1,7 @@
 // bsb_ksw.h -- integer dynamic-programming primitives, one sequence pair per call (scalar form).
 //
-//   sw_extend()  <- ksw_extend2  (ksw.c:380-479)  banded affine extension with z-drop
+//   (ksw_extend2, ksw.c:380-479: ExtLane::step of bsb_extlane.h and sw_extend_warp of bsb_warp.cuh; the plain scalar form of
+//    the CPU harness is tests/hostsim/scalar_stages.h)
 //   nw_global()  <- ksw_global2  (ksw.c:504-606)  banded global alignment + traceback -> CIGAR
 //   sw_local()   <- ksw_u8 / ksw_i16 / ksw_align2 (ksw.c:111-365) local alignment used by mate rescue
 //
@@ -8,6 +9,7 @@
 // (h,e) row state of the reference is kept, because score, end points and max_off feed decisions
 // downstream. Sequences are read through small accessor functors so that reference bases come
 // straight from the 2-bit pac in HBM (no per-call materialisation).
+// Attribution: restates klib's ksw.c (ksw_global2, ksw_u8, ksw_i16, ksw_align2; MIT, Attractive Chaos) cell for cell. See NOTICE.md.
 #pragma once
 #include "bsb_index.h"
 
@@ -35,87 +37,6 @@ struct ExtResult { int score, qle, tle, gtle, gscore, max_off; };
 // So when phi <= max and phi < gscore no later row can change max/max_i/max_j/max_off (they need m > max) or
 // gscore/max_ie (they need h1 >= gscore): the loop may stop with identical results.
 BSB_HD bool ext_rows_exhausted(int phi, int max, int gscore) { return phi <= max && phi < gscore; }
-
-// eh: scratch of 2*(qlen+1) ints
-template <class Q, class T>
-BSB_HD ExtResult sw_extend(int qlen, const Q &query, int tlen, const T &target, const int8_t *mat,
-                           int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
-                           int32_t *eh)
-{
-    int i, j, k, oe_del = o_del + e_del, oe_ins = o_ins + e_ins, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
-    int32_t *H = eh, *E = eh + (qlen + 1);
-    for (j = 0; j <= qlen; ++j) H[j] = E[j] = 0;
-    H[0] = h0; H[1] = h0 > oe_ins ? h0 - oe_ins : 0;
-    for (j = 2; j <= qlen && H[j - 1] > e_ins; ++j) H[j] = H[j - 1] - e_ins;
-    for (i = 0, max = 0; i < 25; ++i) max = max > mat[i] ? max : mat[i];
-    max_ins = (int)((double)(qlen * max + end_bonus - o_ins) / e_ins + 1.);
-    max_ins = max_ins > 1 ? max_ins : 1;
-    w = w < max_ins ? w : max_ins;
-    max_del = (int)((double)(qlen * max + end_bonus - o_del) / e_del + 1.);
-    max_del = max_del > 1 ? max_del : 1;
-    w = w < max_del ? w : max_del;
-    const int amax = max;
-    max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
-    beg = 0; end = qlen;
-    for (i = 0; i < tlen; ++i) {
-        int t, f = 0, h1, m = 0, mj = -1;
-        const int8_t *row = mat + target(i) * 5;
-        if (beg < i - w) beg = i - w;
-        if (end > i + w + 1) end = i + w + 1;
-        if (end > qlen) end = qlen;
-        if (beg == 0) {
-            h1 = h0 - (o_del + e_del * (i + 1));
-            if (h1 < 0) h1 = 0;
-        } else h1 = 0;
-        for (j = beg; j < end; ++j) {
-            int h, M = H[j], e = E[j];
-            H[j] = h1;
-            M = M ? M + row[query(j)] : 0;
-            h = M > e ? M : e;
-            h = h > f ? h : f;
-            h1 = h;
-            mj = m > h ? mj : j;
-            m = m > h ? m : h;
-            t = M - oe_del; t = t > 0 ? t : 0;
-            e -= e_del; e = e > t ? e : t;
-            E[j] = e;
-            t = M - oe_ins; t = t > 0 ? t : 0;
-            f -= e_ins; f = f > t ? f : t;
-        }
-        H[end] = h1; E[end] = 0;
-        if (j == qlen) {
-            max_ie = gscore > h1 ? max_ie : i;
-            gscore = gscore > h1 ? gscore : h1;
-        }
-        if (m == 0) break;
-        if (m > max) {
-            max = m; max_i = i; max_j = mj;
-            max_off = max_off > iabs(mj - i) ? max_off : iabs(mj - i);
-        } else if (zdrop > 0) {
-            if (i - max_i > mj - max_j) {
-                if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break;
-            } else {
-                if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break;
-            }
-        }
-        if (end == qlen) {
-            int phi = 0;
-            for (j = beg; j < end; ++j) {
-                t = H[j] > 0 ? H[j] + amax * (qlen - j) : 0; phi = phi > t ? phi : t;
-                t = E[j] > 0 ? E[j] + amax * (qlen - 1 - j) : 0; phi = phi > t ? phi : t;
-            }
-            if (ext_rows_exhausted(phi, max, gscore)) break;
-        }
-        for (j = beg; j < end && H[j] == 0 && E[j] == 0; ++j) {}
-        beg = j;
-        for (j = end; j >= beg && H[j] == 0 && E[j] == 0; --j) {}
-        end = j + 2 < qlen ? j + 2 : qlen;
-    }
-    (void)k;
-    ExtResult r;
-    r.score = max; r.qle = max_j + 1; r.tle = max_i + 1; r.gtle = max_ie + 1; r.gscore = gscore; r.max_off = max_off;
-    return r;
-}
 
 #define BSB_MINUS_INF (-0x40000000)
 

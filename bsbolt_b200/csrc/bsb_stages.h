@@ -9,8 +9,6 @@
 //   per seed  : seeds, next, chain pool, chains, tmp, cseeds, srt, regs  (all indexed seed_off[r] + j)
 //   per worker: scratch blocks (interval lists, DP rows, traceback, strings)
 #pragma once
-#include "bsb_smem.h"
-#include "bsb_smem_sm.h"
 #include "bsb_seed3.h"
 #include "bsb_chain.h"
 #include "bsb_extend.h"
@@ -51,7 +49,6 @@ struct BatchDev {
     TaskList tasks;
 };
 
-struct SeedScratch { Intv *mem1, *t0, *t1; };
 
 BSB_HD uint8_t nt4_code(unsigned char c)
 {   // nst_nt4_table (bntseq.c:48-65)
@@ -93,30 +90,6 @@ BSB_HD void seed_finish(const Opt &opt, const BatchDev &B, int r, const Intv *me
     }
     l_rep += e - b;
     B.n_intv[r] = n; B.l_rep[r] = l_rep; B.n_seed[r] = total;
-}
-
-// K2: SMEM seeding for read r. use_sm selects the converged state-machine form (all lanes of a warp call
-// together, `active` false for lanes without a read); both forms produce the same interval list.
-BSB_HD void stage_seed(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, const SeedScratch &sc, bool use_sm = false, bool active = true, bool use_v3 = false)
-{
-    const int len = active ? (int)(B.seq_off[r + 1] - B.seq_off[r]) : 0;
-    const uint8_t *seq = active ? B.seq + B.seq_off[r] : nullptr;
-    IntvList mem = {active ? B.intv + (size_t)r * B.intv_cap : nullptr, 0, B.intv_cap};
-    IntvList mem1 = {sc.mem1, 0, B.intv_cap}, t0 = {sc.t0, 0, B.intv_cap}, t1 = {sc.t1, 0, B.intv_cap};
-    int err = 0;
-    if (active) { B.n_intv[r] = 0; B.l_rep[r] = 0; B.n_seed[r] = 0; }
-    const bool work = active && len >= opt.min_seed_len;
-    if (use_v3) {   // the product's seeding form (k_seed3), driven sequentially: list storage borrowed from the scratch lists
-        if (work) {
-            ListPlain L = {(uint64_t *)sc.t0, (uint64_t *)sc.t1, (int *)sc.mem1, B.intv_cap};
-            BasesBytes q = {seq};
-            mem.n = ix.occ32 ? collect_intv_v3<uint32_t>(opt, ix, len, q, L, mem.a, mem.cap, &err)
-                             : collect_intv_v3<uint64_t>(opt, ix, len, q, L, mem.a, mem.cap, &err);
-        }
-    } else if (use_sm) collect_intv_sm(opt, ix, len, seq, mem, mem1, t0, t1, &err, work);
-    else if (work) collect_intv(opt, ix, len, seq, mem, mem1, t0, t1, &err);
-    if (!work) return;
-    seed_finish(opt, B, r, mem.a, mem.n, err);
 }
 
 // K3: one suffix-array lookup. g = global seed slot, r = owning read (seed_off[r] <= g < seed_off[r+1])
@@ -193,30 +166,6 @@ BSB_HD void stage_seed_sw(const Opt &opt, const IndexView &ix, const BatchDev &B
     SwScratch ws = {rows, rows + SEED_SW_CAP, rows + 2 * SEED_SW_CAP, rows + 3 * SEED_SW_CAP, nullptr, SEED_SW_CAP, 0};
     filter_chained_seeds(opt, ix, len, B.seq + B.seq_off[r], nc, B.chains + so, B.cseeds + so, min_hsp, ws, &err);
     if (err) B.err[r] = err;
-}
-
-// K5: banded extension of every kept chain of read r + region de-duplication
-BSB_HD void stage_extend(const Opt &opt, const IndexView &ix, const BatchDev &B, int r, DpScratch &dp)
-{
-    const uint32_t so = B.seed_off[r];
-    const int ns = (int)(B.seed_off[r + 1] - so);
-    B.n_regs[r] = 0;
-    if (ns == 0 || B.err[r]) return;
-    const int len = (int)(B.seq_off[r + 1] - B.seq_off[r]);
-    const uint8_t *seq = B.seq + B.seq_off[r];
-    RegList av = {B.regs + so, 0, ns};
-    int err = 0;
-    const int nc = B.n_chain[r];
-    for (int i = 0; i < nc; ++i) {
-        const Chain &c = B.chains[so + i];
-        chain_to_regions(opt, ix, len, seq, c, B.cseeds + so + c.head, B.srt + so, av, dp, &err);
-        if (err) { B.err[r] = err; return; }
-    }
-    av.n = sort_dedup_patch(opt, ix, seq, av.n, av.a, dp, &err);
-    for (int i = 0; i < av.n; ++i)
-        if (av.a[i].rid >= 0 && ix.anns[av.a[i].rid].is_alt) av.a[i].is_alt = 1;
-    if (err) { B.err[r] = err; return; }
-    B.n_regs[r] = av.n;
 }
 
 // PE: insert-size candidate of pair p

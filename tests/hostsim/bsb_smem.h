@@ -7,7 +7,7 @@
 // Interval lists live in caller-provided scratch (HBM on the device); `cap` bounds every list and
 // an overflow is reported, never truncated silently.
 #pragma once
-#include "bsb_index.h"
+#include "../../bsbolt_b200/csrc/bsb_index.h"
 
 namespace bsb {
 

@@ -13,6 +13,7 @@
 #include <vector>
 #include <mutex>
 #include "../../bsbolt_b200/csrc/bsb_stages.h"
+#include "scalar_stages.h"
 #include "../../bsbolt_b200/csrc/bsb_extlane.h"
 #include "../../bsbolt_b200/csrc/bsb_rescue.h"
 #include "../../bsbolt_b200/csrc/host_mem.h"
