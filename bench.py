@@ -561,7 +561,8 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
             'stage_ms_per_batch': {k: v / n_batches for k, v in zip(('h2d', 'convert', 'seed', 'scan_sa', 'chain', 'extend', 'pestat', 'final'), st_one['ms_stage'])},
             'final_split_ms_per_batch': {'select': st_one['ms_select'] / n_batches, 'tasks': st_one['ms_tasks'] / n_batches, 'n_tasks': st_one['n_tasks'] // n_batches},
             'stage_note': 'CUDA-event stage times of the run with ONE batch in flight per GPU (with several in flight the stages of different batches overlap)',
-            'host_busy_s': {'read': st['sec_read'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_threads': st['sec_align']},
+            'host_busy_s': {'read': st['sec_read'], 'read_plan': st['sec_plan'], 'read_fill': st['sec_fill'], 'format': st['sec_format'], 'write': st['sec_write'], 'gpu_threads': st['sec_align']},
+            'rescue': {'pairs_per_batch': st_one['rescue_pairs'] / n_batches, 'sw_jobs_per_batch': st_one['rescue_jobs'] / n_batches},
             'setup_s': {'simulate': t_sim, 'index_build': t_index}, 'index_hbm_bytes_per_gpu': idx.hbm_bytes}
     print(json.dumps(line))
     os.close(null)

@@ -1100,6 +1100,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
     if (nb > 900000000ull) throw std::runtime_error("[E::bsbolt_b200] a batch of " + std::to_string(nb) + " bases: batches above 900 Mbp are not supported (lower -K, or -t when -K is not given)");
     if (max_len > kMaxReadLen) throw std::runtime_error("[E::bsbolt_b200] reads longer than " + std::to_string(kMaxReadLen) + " bp do not fit the per-warp shared-memory tiles of this build");
     for (int k = 0; k < 8; ++k) out.ms_stage[k] = 0;
+    out.n_rescue_jobs = out.n_rescue_pairs = 0;
     const bool dbg = getenv("BSB_DEBUG_TIMELINE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     static const auto t_epoch = std::chrono::steady_clock::now();
@@ -1452,7 +1453,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                             m.launches += 5;
                             k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, m.d_heavy2.p, m.d_misc.p + 13, c_heavy);
                             ++m.launches;
-                            out.n_rescue_jobs += n_jobs; out.n_rescue_pairs += (uint64_t)h_heavy;
+                            out.n_rescue_jobs = n_jobs; out.n_rescue_pairs = (uint64_t)h_heavy;
                         }
                     } else {
                         k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);

@@ -49,6 +49,7 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     s->sec_resident = sum.sec_resident;
     s->fm_extensions = (int64_t)sum.n_fm_ext; s->fm_two_block = (int64_t)sum.n_fm_two_block; s->fm_block_bytes = sum.fm_block_bytes;
     s->dp_cells_extend = (int64_t)sum.n_ext_cells; s->fm_two_block_ref = (int64_t)sum.n_fm_two_block_ref;
+    s->sec_plan = sum.sec_plan; s->sec_fill = sum.sec_fill; s->rescue_pairs = (int64_t)sum.n_rescue_pairs; s->rescue_jobs = (int64_t)sum.n_rescue_jobs;
 }
 
 extern "C" {

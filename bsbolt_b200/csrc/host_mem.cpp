@@ -1077,6 +1077,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     if (out) fflush(out);
     if (parts) fclose(parts);
     sum.sec_read = std::max(sec_plan, sec_fill);   // the slower of the reader's two overlapped halves
+    sum.sec_plan = sec_plan; sum.sec_fill = sec_fill;
     sum.sec_resident = resident ? t_res1 - t_res0 : 0;
     sum.sec_total = now_sec() - t0;
     if (summary) *summary = sum;

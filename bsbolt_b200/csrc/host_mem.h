@@ -113,10 +113,12 @@ void build_pair_table(const Opt &opt, const PeStat pes[4], std::vector<double> &
 struct RunSummary {
     MapStats stats; long n_batches = 0; long n_entries = 0; double sec_total = 0, sec_align = 0;
     double sec_read = 0, sec_format = 0, sec_write = 0; // busy time of the reader / formatter / output stages
+    double sec_plan = 0, sec_fill = 0;                  // the reader's two overlapped halves: cutting batches (incl. waiting for the parsers) / copying them
     double sec_resident = 0;  // BSB_RESIDENT_BENCH: wall time from "all batches resident on the device" to "last batch aligned"
     double ms_h2d = 0, ms_kernels = 0, ms_d2h = 0, ms_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t n_seeds = 0, h2d_bytes = 0, d2h_bytes = 0, n_tasks = 0;
     uint64_t n_fm_ext = 0, n_fm_two_block = 0, n_fm_two_block_ref = 0, n_ext_cells = 0; int fm_block_bytes = 0;
+    uint64_t n_rescue_pairs = 0, n_rescue_jobs = 0;
     double ms_select = 0, ms_tasks = 0;
     void add_timing(const BatchResult &r)
     {
@@ -125,6 +127,7 @@ struct RunSummary {
         for (int k = 0; k < 8; ++k) ms_stage[k] += r.ms_stage[k];
         n_seeds += r.n_seeds; h2d_bytes += r.h2d_bytes; d2h_bytes += r.d2h_bytes;
         n_fm_ext += r.n_fm_ext; n_fm_two_block += r.n_fm_two_block; n_fm_two_block_ref += r.n_fm_two_block_ref; n_ext_cells += r.n_ext_cells; if (r.fm_block_bytes) fm_block_bytes = r.fm_block_bytes;
+        n_rescue_pairs += r.n_rescue_pairs; n_rescue_jobs += r.n_rescue_jobs;
     }
 };
 

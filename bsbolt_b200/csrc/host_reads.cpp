@@ -796,7 +796,8 @@ int host_core_share()
 
 static int fill_threads(int n_devices = 1)
 {
-    const int nt = host_core_share() / 2, cap = n_devices > 2 ? 12 : 8;
+    if (const char *e = getenv("BSB_FILL_THREADS")) return std::max(1, atoi(e));
+    const int nt = host_core_share() / 2, cap = n_devices > 2 ? 16 : 8;
     return nt < 1 ? 1 : nt > cap ? cap : nt;
 }
 

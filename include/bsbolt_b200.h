@@ -41,6 +41,8 @@ typedef struct {
        layout used; cells of the banded extension DP (ksw_extend2 inner loop, ksw.c:439-454) */
     int64_t fm_extensions, fm_two_block, fm_block_bytes, dp_cells_extend;
     int64_t fm_two_block_ref;              /* ... of them that touch two of the reference's 64-byte occ blocks (bwt.h:72-78) */
+    double sec_plan, sec_fill;             /* sec_read split: cutting the batches (incl. waiting for the parser threads) / copying them */
+    int64_t rescue_pairs, rescue_jobs;     /* pairs that needed mate-rescue Smith-Waterman (mem_matesw) and the Smith-Waterman jobs run for them */
 } bsb_run_stats_t;
 
 typedef struct {
