@@ -691,22 +691,23 @@ __global__ void __launch_bounds__(32, 16) k_rescue_replay(Opt opt, IndexView ix,
 {
     extern __shared__ __align__(16) uint8_t rr_lists[];
     const unsigned lane = threadIdx.x & 31;
-    const unsigned w = SMEM_LISTS ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x, nw = SMEM_LISTS ? gridDim.x : gridDim.x * blockDim.x;
+    const unsigned w = SMEM_LISTS ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x, nw = SMEM_LISTS ? gridDim.x : gridDim.x * blockDim.x;   // scratch block of this worker
     FinalWS ws; AlnReg *wregs;
     make_ws(L, scratch + (size_t)w * L.total, ws, wregs);
     if (SMEM_LISTS) {
-        wregs = reinterpret_cast<AlnReg *>(rr_lists);
-        if (lane) return;
+        AlnReg *lists = reinterpret_cast<AlnReg *>(rr_lists);
         for (;;) {
-            const unsigned k = (unsigned)atomicAdd(ctr, 1);
+            unsigned k = 0;
+            if (lane == 0) k = (unsigned)atomicAdd(ctr, 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
             if (k >= (unsigned)n_heavy) return;
             const RescuePre pre = {jobs + job_off[k], res + job_off[k], (int)(job_off[k + 1] - job_off[k])};
             bool lane_ok = true;
-            for (int q = 0; q < pre.n; ++q) lane_ok = lane_ok && pre.res[q].score != -0x7fffffff;
-            if (!lane_ok) { heavy2[atomicAdd(n_heavy2, 1)] = heavy[k]; continue; }
+            for (int q = lane; q < pre.n; q += 32) lane_ok = lane_ok && pre.res[q].score != -0x7fffffff;
+            if (!__all_sync(0xffffffffu, lane_ok)) { if (lane == 0) heavy2[atomicAdd(n_heavy2, 1)] = heavy[k]; continue; }
             const long long t0 = slowest ? clock64() : 0;
-            stage_final_pe(opt, ix, B, heavy[k], ws, wregs, false, nullptr, &pre);
-            if (slowest) {
+            stage_final_pe_replay_warp(opt, ix, B, heavy[k], ws, lists, pre);
+            if (slowest && lane == 0) {
                 const unsigned long long dt = (unsigned long long)(clock64() - t0);
                 atomicMax(slowest, (dt >> 10) << 32 | (unsigned long long)k);
                 atomicAdd(slowest + 1, dt >> 10);
@@ -1426,8 +1427,8 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                             }
                             const bool dbg_stats = getenv("BSB_DEBUG_STATS") != nullptr;
                             if (dbg_stats) CK(cudaMemsetAsync(m.d_work.p + 4, 0, 16, st));
-                            const size_t rr_smem = (size_t)2 * L.wreg_stride * sizeof(AlnReg);
-                            if (rr_smem <= 72 * 1024 && !getenv("BSB_REPLAY_GLOBAL")) {
+                            const size_t rr_smem = ((size_t)2 * L.wreg_stride + L.reg_cap) * sizeof(AlnReg);   // the two lists of a pair + the sort's second buffer
+                            if (rr_smem <= 220 * 1024 && !getenv("BSB_REPLAY_GLOBAL")) {
                                 raise_dynamic_smem(k_rescue_replay<true>, (int)rr_smem);
                                 const int rr_blocks = (int)std::min<size_t>((size_t)h_heavy, std::min<size_t>((size_t)fin_workers, (size_t)I.n_sm * std::max<size_t>(1, (220 * 1024) / (rr_smem + 1024))));
                                 k_rescue_replay<true><<<rr_blocks, 32, rr_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, h_heavy, m.d_jobs.p, m.d_job_res.p, m.d_job_off.p,

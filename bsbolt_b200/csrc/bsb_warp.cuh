@@ -1103,6 +1103,201 @@ __device__ int mate_rescue_warp(const Opt &opt, const IndexView &ix, const PeSta
     return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Replay of the rescue calls over precomputed Smith-Waterman results (bsb_final.h: RescueJob / RescuePre), one warp per
+// pair with the pair's region lists in shared memory. What is left of mem_matesw once the alignments are known is
+// mem_sort_dedup_patch after every call -- two sorts of a list that has a hundred entries for the pairs that get here. The
+// reference's sorts are unstable introsorts, so the order of EQUAL keys is result-visible; with all keys distinct any sort
+// gives the same array. The warp therefore ranks the entries by counting (every lane a few entries against all others),
+// notices equal keys while it counts, and only then lets lane 0 run the order-exact introsort instead.
+// ---------------------------------------------------------------------------------------------
+template <class Less>
+__device__ void warp_sort_regs(int n, AlnReg *a, AlnReg *tmp, Less lt)
+{
+    const int lane = threadIdx.x & 31;
+    bool dup = false;
+    for (int e = lane; e < n; e += 32) {
+        const AlnReg x = a[e];
+        int rank = 0;
+        for (int f = 0; f < n; ++f) {
+            const bool less = lt(a[f], x);
+            rank += less;
+            dup = dup || (f != e && !less && !lt(x, a[f]));
+        }
+        tmp[rank] = x;
+    }
+    dup = __any_sync(FULLMASK, dup);
+    __syncwarp();
+    if (dup) { if (lane == 0) introsort((long)n, a, lt); }
+    else {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tmp);
+        const int words = n * (int)(sizeof(AlnReg) / 4);
+        for (int k = lane; k < words; k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+}
+
+// mem_sort_dedup_patch (bwamem.c:441-493) without a query, i.e. as mem_matesw calls it (bwamem_pair.c:175): no patching
+__device__ int sort_dedup_warp(const Opt &opt, int n, AlnReg *a, AlnReg *tmp)
+{
+    const int lane = threadIdx.x & 31;
+    if (n <= 1) return n;
+    warp_sort_regs(n, a, tmp, LtRegRe());
+    int m = 0;
+    if (lane == 0) {
+        int i, j;
+        for (i = 0; i < n; ++i) a[i].n_comp = 1;
+        for (i = 1; i < n; ++i) {
+            AlnReg &p = a[i];
+            if (p.rid != a[i - 1].rid || p.rb >= a[i - 1].re + opt.max_chain_gap) continue;
+            for (j = i - 1; j >= 0 && p.rid == a[j].rid && p.rb < a[j].re + opt.max_chain_gap; --j) {
+                AlnReg &q = a[j];
+                if (q.qe == q.qb) continue;
+                const int64_t orr = q.re - p.rb;
+                const int64_t oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+                const int64_t mr = q.re - q.rb < p.re - p.rb ? q.re - q.rb : p.re - p.rb;
+                const int64_t mq = q.qe - q.qb < p.qe - p.qb ? q.qe - q.qb : p.qe - p.qb;
+                if (orr > opt.mask_level_redun * mr && oq > opt.mask_level_redun * mq) {
+                    if (p.score < q.score) { p.qe = p.qb; break; }
+                    else q.qe = q.qb;
+                }
+            }
+        }
+        for (i = 0, m = 0; i < n; ++i)
+            if (a[i].qe > a[i].qb) {
+                if (m != i) a[m++] = a[i];
+                else ++m;
+            }
+    }
+    n = __shfl_sync(FULLMASK, m, 0);
+    __syncwarp();
+    warp_sort_regs(n, a, tmp, LtRegScore());
+    if (lane == 0) {
+        int i;
+        for (i = 1; i < n; ++i)
+            if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+        for (i = 1, m = 1; i < n; ++i)
+            if (a[i].qe > a[i].qb) {
+                if (m != i) a[m++] = a[i];
+                else ++m;
+            }
+    }
+    m = __shfl_sync(FULLMASK, m, 0);
+    __syncwarp();
+    return m;
+}
+
+// mem_matesw with the Smith-Waterman results at hand; warp-uniform (every lane the same control flow on the same values)
+__device__ int mate_rescue_warp_pre(const Opt &opt, const IndexView &ix, const PeStat pes[4], const AlnReg &a, int l_ms, RegList &ma, AlnReg *tmp,
+                                    int call_key, const RescuePre &pre, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t l_pac = ix.l_pac;
+    int i, r, skip[4], n = 0;
+    for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+    for (i = 0; i < ma.n; ++i) {
+        int64_t dist;
+        r = infer_dir(l_pac, a.rb, ma.a[i].rb, &dist);
+        if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+    }
+    if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
+    for (r = 0; r < 4; ++r) {
+        int is_rev;
+        int64_t rb, re;
+        if (skip[r]) continue;
+        if (rescue_window(opt, ix, pes, a, l_ms, r, &rb, &re, &is_rev)) {
+            int k = 0;
+            while (k < pre.n && pre.jobs[k].key != (call_key | r)) ++k;
+            if (k == pre.n) { *err = ERR_SCRATCH_OVERFLOW; return n; }
+            const SwResult aln = pre.res[k];
+            if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
+                AlnReg b;
+                alnreg_clear(b);
+                b.rid = a.rid;
+                b.is_alt = a.is_alt;
+                b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+                b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+                b.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
+                b.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
+                b.score = aln.score;
+                b.csub = aln.score2;
+                b.secondary = -1;
+                b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+                if (ma.n >= ma.cap) { *err = ERR_SCRATCH_OVERFLOW; return n; }
+                ++ma.n;
+                __syncwarp();
+                if (lane == 0) {
+                    for (i = 0; i < ma.n - 1; ++i)
+                        if (ma.a[i].score < b.score) break;
+                    const int at = i;
+                    for (i = ma.n - 1; i > at; --i) ma.a[i] = ma.a[i - 1];
+                    ma.a[i] = b;
+                }
+                __syncwarp();
+            }
+            ++n;
+        }
+        if (n) ma.n = sort_dedup_warp(opt, ma.n, ma.a, tmp);
+    }
+    return n;
+}
+
+// One queued pair on one warp: the rescue block of mem_sam_pe (bwamem_pair.c:262-277) replayed over the results, then the rest
+// of the pair's finalisation on lane 0. lists: 2 * (ws.reg_cap + max_matesw) regions for the two ends + ws.reg_cap for the sort.
+__device__ void stage_final_pe_replay_warp(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *lists, const RescuePre &pre)
+{
+    const int lane = threadIdx.x & 31;
+    const int r0 = p << 1, r1 = r0 | 1;
+    const int stride = ws.reg_cap + opt.max_matesw;
+    AlnReg *tmp = lists + (size_t)2 * stride;
+    const int e0 = B.err[r0] ? B.err[r0] : B.err[r1];
+    if (lane == 0) { readout_init(B.out[r0], e0); readout_init(B.out[r1], e0); }
+    __syncwarp();
+    if (e0) return;
+    RegList rl[2];
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 | i, n = B.n_regs[r];
+        rl[i].a = lists + (size_t)i * stride; rl[i].cap = ws.reg_cap; rl[i].n = n;
+        if (n > ws.reg_cap) { if (lane == 0) B.out[r0].err = B.out[r1].err = ERR_SCRATCH_OVERFLOW; return; }
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(B.regs + B.seed_off[r]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(rl[i].a);
+        for (int k = lane; k < n * (int)(sizeof(AlnReg) / 4); k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+    int err = 0;
+    const int ls[2] = {(int)(B.seq_off[r0 + 1] - B.seq_off[r0]), (int)(B.seq_off[r1 + 1] - B.seq_off[r1])};
+    const uint8_t *seqs[2] = {B.seq + B.seq_off[r0], B.seq + B.seq_off[r1]};
+    AlnReg *bcopy[2]; int nb[2];
+    for (int i = 0; i < 2; ++i) {
+        nb[i] = 0;
+        bcopy[i] = rl[i].a + rl[i].cap;
+        for (int j = 0; j < rl[i].n; ++j)
+            if (rl[i].a[j].score >= rl[i].a[0].score - opt.pen_unpaired) {
+                if (nb[i] < opt.max_matesw && lane == 0) bcopy[i][nb[i]] = rl[i].a[j];
+                ++nb[i];
+            }
+        if (nb[i] > opt.max_matesw) nb[i] = opt.max_matesw;
+    }
+    __syncwarp();
+    for (int i = 0; i < 2 && !err; ++i)
+        for (int j = 0; j < nb[i] && !err; ++j) {
+            const AlnReg a = bcopy[i][j];
+            mate_rescue_warp_pre(opt, ix, B.pes, a, ls[!i], rl[!i], tmp, i << 16 | j << 2, pre, &err);
+        }
+    __syncwarp();
+    if (lane == 0) {
+        if (!err) {
+            Opt o2 = opt;
+            o2.flag |= F_NO_RESCUE;
+            finalize_pair(o2, ix, B.mt, B.pes, (uint64_t)((B.n_processed >> 1) + p), r0, ls[0], seqs[0], rl[0], ls[1], seqs[1], rl[1],
+                          ws, B.arena, B.tasks, B.out, &err);
+        }
+        if (err) B.out[r0].err = B.out[r1].err = err;
+    }
+    __syncwarp();
+}
+
 // One pair that needs rescue Smith-Waterman, on one warp: the rescue block of mem_sam_pe (bwamem_pair.c:262-277) with
 // the lanes together, then the rest of the pair's finalisation on lane 0 with the rescue already done.
 __device__ void stage_final_pe_heavy(const Opt &opt, const IndexView &ix, BatchDev &B, int p, FinalWS &ws, AlnReg *wregs, const WarpSw &sw)
