@@ -93,4 +93,18 @@ def launch_alignment(arguments):
     return align_bisulfite(bwa_cmd, arguments.O, arguments.OT, arguments.OS, device=getattr(arguments, 'GPU', [0]))
 
 
-bsb_launch = {'Align': launch_alignment}
+def launch_index(arguments):
+    """`bsbolt Index` (reference: Launcher.py:18-38): same messages, same database directory; the index files come from the GPU builder"""
+    from bsbolt_b200 import index_db
+    if arguments.rrbs:
+        print(f'Generating RRBS Database at {arguments.DB}: '
+              f'lower bound {arguments.rrbs_lower}, upper bound {arguments.rrbs_upper}: '
+              f'Cut Format {arguments.rrbs_cut_format}')
+        print(index_db.restriction_sites(arguments.rrbs_cut_format))
+        return index_db.build_rrbs_database(arguments.G, arguments.DB, device=arguments.GPU, lower_bound=arguments.rrbs_lower,
+                                            upper_bound=arguments.rrbs_upper, cut_format=arguments.rrbs_cut_format, ignore_alt=arguments.IA)
+    print(f'Generating WGBS Database at {arguments.DB}')
+    return index_db.build_database(arguments.G, arguments.DB, device=arguments.GPU, ignore_alt=arguments.IA, mappable_regions=arguments.MR)
+
+
+bsb_launch = {'Align': launch_alignment, 'Index': launch_index}

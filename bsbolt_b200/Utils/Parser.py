@@ -1,7 +1,7 @@
-"""`bsbolt Align` command line, flag for flag (reference: bsbolt/Utils/Parser.py:31-115).
+"""`bsbolt Align` and `bsbolt Index` command lines, flag for flag (reference: bsbolt/Utils/Parser.py:31-115, 118-140).
 
-Only the Align module is provided: the other bsbolt modules (Index, Simulate, CallMethylation, ...) are
-outside the GPU hot path and keep running from the reference package.
+Align is the GPU hot path; Index produces its input (the suffix array is built on the GPU, the files are byte-identical to
+`bwa index`). The other bsbolt modules (Simulate, CallMethylation, ...) keep running from the reference package.
 """
 import argparse
 
@@ -61,9 +61,25 @@ EXTRA_FLAGS = [
                   help='CUDA device(s) to align on, comma separated; with several devices batch b runs on device b mod G [0]')),
 ]
 
-parser = argparse.ArgumentParser(description='bsbolt_b200: GPU drop-in for the bsbolt Align module',
-                                 usage='python -m bsbolt_b200 Align -F1 <fq> [-F2 <fq>] -DB <db> (-O <prefix> | -OS) [options]')
-subparsers = parser.add_subparsers(description='module', metavar='Align', dest='subparser_name')
+parser = argparse.ArgumentParser(description='bsbolt_b200: GPU drop-in for the bsbolt Align (and Index) modules', prog='python -m bsbolt_b200')
+subparsers = parser.add_subparsers(description='module', metavar='Align | Index', dest='subparser_name')
 align_parser = subparsers.add_parser('Align', help='Alignment', add_help=True)
 for _flag, _kw in ALIGN_FLAGS + EXTRA_FLAGS:
     align_parser.add_argument(_flag, **_kw)
+
+# `bsbolt Index` (reference flags and defaults); -B is accepted and ignored: it sizes the blocks of the CPU bwtsw algorithm
+INDEX_FLAGS = [
+    ('-G', dict(type=str, required=True, help='Path to reference genome fasta file, fasta file should contain all contigs')),
+    ('-DB', dict(type=str, required=True, help='Path to index directory, will create directory if folder does not exist')),
+    ('-B', dict(type=int, default=10000000, help='Block size for the bwtsw algorithm of the reference (ignored: the suffix array is built on the GPU)')),
+    ('-MR', dict(type=str, default=None, help='Path to bed file of mappable regions. Index will be built using masked contig sequence')),
+    ('-IA', dict(action='store_true', default=False, help='ignore alt contigs during index construction')),
+    ('-rrbs', dict(action='store_true', default=False, help='Generate a Reduced Representative Bisulfite Sequencing (RRBS) index')),
+    ('-rrbs-cut-format', dict(default='C-CGG', help='Cut format for the RRBS database, default= C-CGG (MSPI); several enzymes comma separated')),
+    ('-rrbs-lower', dict(type=int, default=40, help='Lower bound fragment size to consider for the RRBS index, default = 40')),
+    ('-rrbs-upper', dict(type=int, default=500, help='Upper bound fragment size to consider for the RRBS index, default = 500')),
+]
+index_parser = subparsers.add_parser('Index', help='Index Generation', add_help=True)
+for _flag, _kw in INDEX_FLAGS:
+    index_parser.add_argument(_flag, **_kw)
+index_parser.add_argument('-GPU', type=int, default=0, help='CUDA device that builds the suffix array [0]')

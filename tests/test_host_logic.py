@@ -28,6 +28,19 @@ def test_align_flags_match_reference_parser():
     assert (a.t, a.k, a.T, a.L, a.XA, a.DR, a.INDEL, a.U) == (1, 19, 10, '30,30', '100,200', 0.95, '6,6', 17)
 
 
+def test_index_flags_match_reference_parser():
+    from bsbolt_b200.Utils.Parser import INDEX_FLAGS, parser
+    flags = [f for f, _ in INDEX_FLAGS]
+    expected = ['-G', '-DB', '-B', '-MR', '-IA', '-rrbs', '-rrbs-cut-format', '-rrbs-lower', '-rrbs-upper']
+    assert flags == expected
+    if os.path.exists(os.path.join(REF, 'bsbolt', 'Utils', 'Parser.py')):
+        src = open(os.path.join(REF, 'bsbolt', 'Utils', 'Parser.py')).read()
+        import re
+        assert re.findall(r"index_parser\.add_argument\('(-[\w-]+)'", src) == expected
+    a = parser.parse_args(['Index', '-G', 'g.fa', '-DB', 'db', '-rrbs'])
+    assert (a.rrbs, a.rrbs_cut_format, a.rrbs_lower, a.rrbs_upper, a.MR, a.IA, a.B) == (True, 'C-CGG', 40, 500, None, False, 10000000)
+
+
 def test_argv_equals_reference_launcher(tmp_path):
     """build_alignment_command() produces the argv the reference's launch_alignment() would exec."""
     from bsbolt_b200.Utils.Launcher import build_alignment_command
