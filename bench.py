@@ -499,9 +499,9 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
             occ_bytes = a.genome_mb * 1000000 * 4 // 2          # the occ-block array the seeding kernel walks: 4 x genome symbols, 2 symbols per byte
             ind, chase = _native.random_sector_peak(0, occ_bytes)
             ind4, chase4 = _native.random_sector_peak(0, 4 << 30)
-            rnd = {'independent_loads_gbs': ind, 'dependent_chain_per_thread_gbs': chase, 'footprint_bytes': occ_bytes,
+            rnd = {'independent_loads_gbs': ind, 'dependent_chain_per_thread_gbs': chase, 'footprint_bytes': occ_bytes, 'buffer_bytes': 1 << round(__import__('math').log2(occ_bytes)),
                    'over_4GiB': {'independent_loads_gbs': ind4, 'dependent_chain_per_thread_gbs': chase4},
-                   'how': 'bsb_random_sector_peak: random 32-byte sectors of a buffer the size of the occ-block array (power of two below), 2048 threads per SM, 256 loads per thread, best of 3'}
+                   'how': 'bsb_random_sector_peak: random 32-byte sectors of a buffer the size of the occ-block array (nearest power of two), 2048 threads per SM, 256 loads per thread, best of 3'}
         except Exception as e:  # noqa
             rnd = {'error': str(e)}
     ext_ms = st_one['ms_stage'][5] / n_batches

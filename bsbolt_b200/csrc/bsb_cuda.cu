@@ -916,6 +916,7 @@ struct BatchCtx {
     size_t arena_cap = 0;
     int intv_cap_hint = 0;
     int fin_scale = 1;          // growth of the finalisation scratch (see make_layout in align())
+    int last_heavy = -1, last_pairs = 0;   // pairs queued for rescue by this context's previous batch, of how many: picks the rescue path without a host round trip
     long launches = 0;
     bool ready = false;
     void init()
@@ -1335,7 +1336,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         FinalLayout L;
         memset(&L, 0, sizeof L);
         L.max_q = max_q;
-        L.reg_cap = max_regs + 4 * opt.max_matesw + 8 + (scale > 1 ? 64 * scale : 0);
+        L.reg_cap = max_regs + 4 * opt.max_matesw + 8 + (scale > 16 ? 16 * scale : 0);   // (rescue adds at most 4 regions per call: only the last resort grows this)
         L.pair_cap = 512 * scale; L.sw_cap = max_q + 32; L.sw_b = 1024 * scale; L.wreg_stride = L.reg_cap + opt.max_matesw;
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
@@ -1394,10 +1395,20 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                     const int rs_cells = ((max_len + 15) / 16) * 16, rs_words = rs_cells + rs_cells / 8;
                     const size_t rs_smem = (size_t)32 * rs_words * 4;
                     const bool by_jobs = !getenv("BSB_RESCUE_WARP") && (long)max_len * opt.a < 250 && rs_smem <= 96 * 1024;
-                    if (by_jobs) {
+                    // The job path needs the number of queued pairs on the host. Libraries differ by orders of magnitude in that
+                    // number but hardly from batch to batch, so the previous batch of this context decides: few pairs -> the
+                    // warp-per-pair kernel straight away (device-side count, no round trip), many -> count, enumerate, run by jobs.
+                    const double heavy_expected = m.last_heavy < 0 ? 1e9 : (double)m.last_heavy / std::max(m.last_pairs, 1) * (n >> 1);   // first batch: find out
+                    m.last_pairs = n >> 1;
+                    if (by_jobs && heavy_expected < env_int("BSB_RESCUE_PAIRS_MIN", 256)) {
+                        k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
+                        ++m.launches;
+                        CK(cudaMemcpyAsync(&m.last_heavy, n_heavy, 4, cudaMemcpyDeviceToHost, st));   // read at the next wait of this stream
+                    } else if (by_jobs) {
                         int h_heavy = 0;
                         CK(cudaMemcpyAsync(&h_heavy, n_heavy, 4, cudaMemcpyDeviceToHost, st));
                         m.wait();
+                        m.last_heavy = h_heavy;
                         CK(cudaMemsetAsync(m.d_misc.p + 13, 0, 4, st));            // pairs left to the warp kernel
                         if (h_heavy > 0) {
                             m.d_heavy2.ensure((size_t)h_heavy + 1);
@@ -1413,6 +1424,13 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                             uint32_t n_jobs = 0;
                             CK(cudaMemcpyAsync(&n_jobs, m.d_job_off.p + h_heavy, 4, cudaMemcpyDeviceToHost, st));
                             m.wait();
+                            // a lane runs a whole job on its own (~5 ms of dependent rows): with only a few thousand jobs the warp-per-pair
+                            // kernel, which spreads every Smith-Waterman over 32 lanes, is back sooner (measured on clean C2 pairs: 1 vs 5 ms)
+                            if ((int)n_jobs < env_int("BSB_RESCUE_JOBS_MIN", 3000)) {
+                                k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
+                                m.launches += 3;
+                                out.n_rescue_pairs = (uint64_t)h_heavy;
+                            } else {
                             m.d_jobs.ensure((size_t)n_jobs + 1); m.d_job_res.ensure((size_t)n_jobs + 1);
                             k_rescue_enum<<<en_blocks, fin_block, 0, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, h_heavy, m.d_jobs.p, m.d_job_off.p, nullptr, m.d_misc.p + 23);
                             if (n_jobs) {
@@ -1455,6 +1473,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                             k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, m.d_heavy2.p, m.d_misc.p + 13, c_heavy);
                             ++m.launches;
                             out.n_rescue_jobs = n_jobs; out.n_rescue_pairs = (uint64_t)h_heavy;
+                            }
                         }
                     } else {
                         k_final_pe_heavy<<<heavy_blocks, 128, hv_smem, st>>>(opt, I.ix, B, L, m.d_final_scratch.p, heavy, n_heavy, c_heavy);
@@ -1624,8 +1643,8 @@ void random_sector_peak(int device, size_t footprint_bytes, double *gbs_independ
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    uint64_t bytes = 1ull << 26;                                         // power of two at or below the footprint asked for (64 MiB .. 16 GiB)
-    while (bytes * 2 <= (uint64_t)footprint_bytes && bytes < (16ull << 30)) bytes *= 2;
+    uint64_t bytes = 1ull << 26;                                         // the power of two nearest to the footprint asked for (64 MiB .. 16 GiB)
+    while ((double)bytes * 1.4142 < (double)footprint_bytes && bytes < (16ull << 30)) bytes *= 2;
     const uint64_t n_sectors = bytes / 32;
     DevBuf<uint4> buf; buf.ensure(bytes / 16);
     DevBuf<unsigned long long> sink; sink.ensure(1);

@@ -113,7 +113,7 @@ void bsb_batch_free(bsb_batch_t *b);
 int bsb_index_build(const char *fasta, const char *prefix, int device, double *device_ms);
 
 /* Measurement aid for the seeding roofline: bandwidth of random 32-byte sector reads on `device` over a buffer of about
- * footprint_bytes (rounded down to a power of two; give the size of the occ-block array the kernel walks) -- `independent`:
+ * footprint_bytes (rounded to the nearest power of two; give the size of the occ-block array the kernel walks) -- `independent`:
  * every thread issues unrelated loads (what the memory system can deliver); `chase`: every thread's next address depends on
  * the sector it has just read, one load in flight per thread at full occupancy (the access pattern of backward search, the
  * honest ceiling for bwt_extend chains). GB/s; returns 0 on success. */
