@@ -26,6 +26,7 @@ as N grows (weak scaling). The N-GPU output of a bounded sample is compared byte
 python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c5]
 """
 import argparse
+import hashlib
 import json
 import os
 import shutil
@@ -457,14 +458,25 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
         nb = min(4, K) * a.batch_pairs
         b1 = os.path.join(work, 'bam_1.fq'); b2 = os.path.join(work, 'bam_2.fq'); bam_path = os.path.join(work, 'bench_out.bam')
         head_records(f1, b1, nb); head_records(f2, b2, nb)
-        for level in (-1, 1):
+        # level -1 (the default, what `bsbolt Align -O` uses): records, arbiter and BGZF deflate on the device, the host appends
+        # the blocks to the file; an explicit zlib level: SAM text to the host, encoded and deflated by the host cores
+        for name, level in (('device_deflate', -1), ('device_deflate_again', -1), ('host_zlib_level_1', 1), ('host_zlib_level_6', 6)):
             t = time.time()
             rc, st_b = _native.mem_main_bam(argv_common + [db, b1, b2], bam_path, index=idx, threads=0, level=level, log_fd=null)
             dt = time.time() - t
             if rc:
                 raise RuntimeError(_native.last_error())
             bam_info = bam_info or {'api': 'bsb_mem_main_bam (FASTQ files on host -> BGZF/BAM file)', 'reads': 2 * nb, 'unit': 'reads/s'}
-            bam_info['zlib_default' if level < 0 else f'zlib_level_{level}'] = {'value': 2 * nb / dt, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path)}
+            bam_info[name] = {'value': 2 * nb / dt, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path), 'd2h_bytes': st_b['d2h_bytes']}
+            if name in ('device_deflate', 'host_zlib_level_1'):   # both files inflate (zlib, here) to the same BAM stream
+                import gzip
+                h = hashlib.sha256()
+                with gzip.open(bam_path, 'rb') as f:
+                    for chunk in iter(lambda: f.read(1 << 24), b''):
+                        h.update(chunk)
+                bam_info[name]['raw_sha256'] = h.hexdigest()
+        bam_info['value'] = bam_info['device_deflate_again']['value']
+        bam_info['device_stream_identical_to_host_stream'] = bam_info['device_deflate']['raw_sha256'] == bam_info['host_zlib_level_1']['raw_sha256']
         scratch += [b1, b2, bam_path]
     ms_resident, ms_total_wall = st_res['sec_resident'] * 1000, wall * 1000
     ms_one = st_one['sec_resident'] * 1000

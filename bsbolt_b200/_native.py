@@ -19,7 +19,8 @@ class RunStats(C.Structure):
                [(n, C.c_int64) for n in ('n_seeds', 'h2d_bytes', 'd2h_bytes', 'kernel_launches')] + \
                [(n, C.c_double) for n in ('sec_read', 'sec_format', 'sec_write', 'ms_select', 'ms_tasks')] + [('n_tasks', C.c_int64), ('sec_resident', C.c_double)] + \
                [(n, C.c_int64) for n in ('fm_extensions', 'fm_two_block', 'fm_block_bytes', 'dp_cells_extend', 'fm_two_block_ref')] + \
-               [('sec_plan', C.c_double), ('sec_fill', C.c_double), ('rescue_pairs', C.c_int64), ('rescue_jobs', C.c_int64)]
+               [('sec_plan', C.c_double), ('sec_fill', C.c_double), ('rescue_pairs', C.c_int64), ('rescue_jobs', C.c_int64)] + \
+               [('ms_text', C.c_double), ('ms_bam', C.c_double), ('bam_raw_bytes', C.c_int64), ('bam_bgzf_bytes', C.c_int64), ('bam_blocks', C.c_int64)]
 
     def as_dict(self):
         d = {}

@@ -23,6 +23,8 @@
 #include "bsb_warp.cuh"
 #include "bsb_extlane.h"
 #include "bsb_rescue.h"
+#include "bsb_bam.h"
+#include "bsb_deflate.h"
 #include "bsb_cuda.h"
 
 namespace bsb {
@@ -753,6 +755,129 @@ __global__ void __launch_bounds__(128) k_sam_write(SamView v, int n, int is_pe, 
     o.finish();
 }
 
+// ------------------------------------------------------------------------------------------------
+// BAM on the device: the arbiter, the records (bsb_bam.h), the BGZF blocks (bsb_deflate.h)
+// ------------------------------------------------------------------------------------------------
+// counters of a batch: [0, 8) MapCounters, 8 = first defect ((entry << 8 | code) + 1), 9 = largest entry in bytes, 10 = records
+__global__ void __launch_bounds__(128) k_bam_arbiter(ArbiterView a, uint8_t *code, unsigned long long *ctr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    MapCounters c;
+    memset(&c, 0, sizeof c);
+    if (i < a.n && a.is_head(i)) bam_arbitrate(a, i, code, c);     // one thread per read-name group (its first entry)
+    const unsigned long long *f = reinterpret_cast<const unsigned long long *>(&c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, (unsigned)f[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ctr + k, (unsigned long long)v);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_bam_count(BamView v, uint32_t *len, unsigned long long *ctr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bytes = 0, nr = 0;
+    if (i < v.a.n) {
+        SamCount c;
+        int r = 0;
+        const int rc = bam_entry(c, v, i, false, &r);
+        bytes = (unsigned)c.n; nr = (unsigned)r;
+        len[i] = bytes;
+        if (rc) atomicCAS(ctr + 8, 0ull, ((unsigned long long)i << 8 | (unsigned)rc) + 1);
+    }
+    const unsigned mx = __reduce_max_sync(0xffffffffu, bytes), sum = __reduce_add_sync(0xffffffffu, nr);
+    if ((threadIdx.x & 31) == 0) { atomicMax(ctr + 9, (unsigned long long)mx); if (sum) atomicAdd(ctr + 10, (unsigned long long)sum); }
+}
+
+__global__ void __launch_bounds__(128) k_bam_write(BamView v, const uint32_t *off, char *raw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.a.n || off[i + 1] == off[i]) return;
+    SamWriteDev o = {raw + off[i], 0, 0};
+    bam_entry(o, v, i, true);                                       // (defects were reported by the sizing pass)
+    o.finish();
+}
+
+__global__ void k_bam_cuts(const uint32_t *off, int n, uint32_t quantum, int fixed, int nblk, uint32_t *cut)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nblk) return;
+    const uint64_t target = (uint64_t)k * quantum;
+    cut[k] = fixed ? (uint32_t)(target < off[n] ? target : off[n]) : bam_block_cut(off, n, target);
+}
+
+struct XDev {   // bsb_deflate.h's execution policy on the device: one phase = a strided loop over the block + a barrier
+    template <class F> __host__ __device__ __forceinline__ void par(int n, F f)
+    {
+#if defined(__CUDA_ARCH__)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) f(i);
+        __syncthreads();
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_or(uint32_t *p, uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        atomicOr(p, v);
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_xor(uint32_t *p, uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        atomicXor(p, v);
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_add(uint32_t *p, uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(p, v);
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_max(int32_t *p, int32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        atomicMax(p, v);
+#endif
+    }
+};
+
+// One thread block per BGZF block, persistent over the batch's blocks. tok: BGZF_MAX_IN + 8 words of scratch per thread block.
+__global__ void __launch_bounds__(DF_CH) k_bgzf_deflate(const uint8_t *raw, const uint32_t *cut, int nblk, uint8_t *slots, uint32_t *len, uint32_t *tok)
+{
+    extern __shared__ __align__(16) unsigned char df_smem[];       // sizeof(DeflateShared): the input block, the hash table, the code tables
+    DeflateShared &S = *reinterpret_cast<DeflateShared *>(df_smem);
+    XDev x;
+    uint32_t *my_tok = tok + (size_t)blockIdx.x * (BGZF_MAX_IN + 8);
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int n = (int)(cut[blk + 1] - cut[blk]);
+        uint32_t total = 0;
+        if (n > 0 && n <= BGZF_MAX_IN) total = bgzf_block(x, S, raw + cut[blk], n, slots + (size_t)blk * BGZF_SLOT, my_tok);
+        if (threadIdx.x == 0) len[blk] = n > BGZF_MAX_IN ? 0xffffffffu : total;   // (a cut larger than a block cannot happen; it would be reported)
+    }
+}
+
+// the finished blocks, back to back
+__global__ void __launch_bounds__(256) k_bgzf_gather(const uint8_t *slots, const uint32_t *len, const uint32_t *off, int nblk, uint8_t *dense)
+{
+    const int blk = blockIdx.x;
+    const uint8_t *src = slots + (size_t)blk * BGZF_SLOT;
+    uint8_t *dst = dense + off[blk];
+    const uint32_t n = len[blk];
+    uint32_t i = threadIdx.x;
+    const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);   // bytes up to the first 16-byte aligned destination
+    if (n >= 64) {
+        if (i < head) dst[i] = src[i];
+        const uint32_t n16 = (n - head) >> 4;
+        for (uint32_t k = i; k < n16; k += blockDim.x) {
+            const uint8_t *s = src + head + (k << 4);
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = df_load32(s + 4 * q);
+            *reinterpret_cast<uint4 *>(dst + head + (k << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        for (uint32_t k = head + (n16 << 4) + i; k < n; k += blockDim.x) dst[k] = src[k];
+    } else for (; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
 // Index-load time: expands the reference's SA sample (every sa_intv-th rank) into the full suffix array in
 // HBM. SA values do not depend on the sampling rate, so lookups become one 4-byte load
 // instead of ~31 dependent 64-byte LF steps. One thread per sample walks LF until the next sampled rank.
@@ -892,7 +1017,7 @@ static InstallPinnedHooks g_install_pinned_hooks;
 // host round trips of the other.
 struct BatchCtx {
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[12];   // 0..9 stage boundaries, 10 = selection kernel done
+    cudaEvent_t ev[13];   // 0..9 stage boundaries, 10 = selection kernel done, 11 = SAM text written, 12 = BGZF blocks gathered
     cudaEvent_t ev_wait = nullptr;   // blocking-sync event: the host thread sleeps instead of spinning on a core
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off; DevBuf<uint8_t> d_pattern, d_seq, d_oseq;
     DevBuf<Intv> d_intv;
@@ -911,6 +1036,10 @@ struct BatchCtx {
     DevBuf<int32_t> d_heavy, d_heavy2; DevBuf<uint32_t> d_job_cnt, d_job_off; DevBuf<RescueJob> d_jobs; DevBuf<SwResult> d_job_res; DevBuf<uint64_t> d_blist;
     // device-side SAM text
     DevBuf<char> d_names, d_qual, d_text, d_rg; DevBuf<uint32_t> d_name_off, d_text_len, d_text_off; DevBuf<uint8_t> d_has_qual; DevBuf<SamStats> d_stats;
+    // device-side BAM: arbiter decisions, record bytes, BGZF blocks
+    DevBuf<uint8_t> d_first, d_rgrp, d_bam_code, d_bam_raw, d_bgzf_slots, d_bgzf_dense;
+    DevBuf<uint32_t> d_bam_len, d_bam_off, d_bam_cut, d_bgzf_len, d_bgzf_off, d_bam_tok;
+    DevBuf<unsigned long long> d_bam_ctr;
     size_t task_cap = 0;
     DevBuf<unsigned long long> d_used, d_work;   // d_work: counted work of the batch (FM extensions, two-block extensions, extension DP cells)
     size_t arena_cap = 0;
@@ -952,6 +1081,7 @@ struct CudaAligner::Impl {
     DevBuf<double> d_log;
     std::vector<double> log_tab;
     DevBuf<char> d_ctg_text; DevBuf<uint32_t> d_ctg_name_off, d_ctg_anno_off; DevBuf<uint8_t> d_ctg_is_crick, d_ctg_sign;   // SAM formatter's contig table
+    DevBuf<int32_t> d_ctg_sorted; int n_ctg = 0, df_per_sm = 0;                                                                          // + the BAM encoder's name lookup
     bool any_alt = false;
     long launches = 0;        // index-load kernels
     BatchCtx ctx[CudaAligner::kSlots];
@@ -1012,7 +1142,8 @@ CudaAligner::CudaAligner(const HostIndex &idx, int device) : im_(new Impl)
     {   // contig table of the SAM formatter
         auto up = [](auto &dst, const auto &src) { dst.ensure(src.size() + 1); if (!src.empty()) CK(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(src[0]), cudaMemcpyHostToDevice)); };
         up(m.d_ctg_text, idx.ctg_text); up(m.d_ctg_name_off, idx.ctg_name_off); up(m.d_ctg_anno_off, idx.ctg_anno_off);
-        up(m.d_ctg_is_crick, idx.ctg_is_crick); up(m.d_ctg_sign, idx.ctg_sign);
+        up(m.d_ctg_is_crick, idx.ctg_is_crick); up(m.d_ctg_sign, idx.ctg_sign); up(m.d_ctg_sorted, idx.ctg_sorted);
+        m.n_ctg = (int)idx.ctg_sorted.size();
         m.any_alt = idx.any_alt;
     }
     build_log_table(m.log_tab, 65536);
@@ -1524,7 +1655,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         m.arena_cap = (size_t)used + (size_t)used / 4 + (1 << 20); // the counter keeps counting past the cap: exact retry size
     }
     // ---- SAM text on the device, D2H ----
-    out.have_text = false;
+    out.have_text = false; out.have_bam = false;
     size_t text_bytes = 0;
     if (dev_text && n) {
         SamView v;
@@ -1554,11 +1685,82 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         m.launches += 3;
         CK(cudaGetLastError());
         CK(cudaEventRecord(m.ev[11], st));
+        if (out.want_bam) {
+            // ---- BAM: the arbiter, the records and their BGZF blocks are made here; only compressed blocks cross PCIe ----
+            m.d_first.ensure(n + 1); m.d_rgrp.ensure(n + 1); m.d_bam_code.ensure(n + 1); m.d_bam_len.ensure(n + 2); m.d_bam_off.ensure(n + 2); m.d_bam_ctr.ensure(16);
+            CK(cudaMemcpyAsync(m.d_first.p, b.first.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(m.d_rgrp.p, b.read_group.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(m.d_bam_ctr.p, 0, 16 * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(m.d_bam_len.p + n, 0, 4, st));
+            BamView bv;
+            bv.a.names = m.d_names.p; bv.a.name_off = m.d_name_off.p; bv.a.first = m.d_first.p; bv.a.read_group = m.d_rgrp.p; bv.a.stats = m.d_stats.p; bv.a.n = n;
+            bv.text = m.d_text.p; bv.text_off = m.d_text_off.p; bv.code = m.d_bam_code.p;
+            bv.ctg.text = I.d_ctg_text.p; bv.ctg.name_off = I.d_ctg_name_off.p; bv.ctg.sorted = I.d_ctg_sorted.p; bv.ctg.n = I.n_ctg;
+            bv.bases = B.bases; bv.qual = m.d_qual.p; bv.seq_off = B.seq_off; bv.has_qual = m.d_has_qual.p;
+            k_bam_arbiter<<<cdiv(n, 128), 128, 0, st>>>(bv.a, m.d_bam_code.p, m.d_bam_ctr.p);
+            k_bam_count<<<cdiv(n, 128), 128, 0, st>>>(bv, m.d_bam_len.p, m.d_bam_ctr.p);
+            cub::DeviceScan::ExclusiveSum(nullptr, sb, m.d_bam_len.p, m.d_bam_off.p, n + 1, st);
+            m.d_cub.ensure(sb + 16);
+            cub::DeviceScan::ExclusiveSum(m.d_cub.p, sb, m.d_bam_len.p, m.d_bam_off.p, n + 1, st);
+            unsigned long long hc[16];
+            uint32_t raw_total = 0;
+            CK(cudaMemcpyAsync(hc, m.d_bam_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&raw_total, m.d_bam_off.p + n, 4, cudaMemcpyDeviceToHost, st));
+            m.wait();
+            if (hc[8]) {
+                const unsigned long long e = hc[8] - 1;
+                throw std::runtime_error(std::string("[E::bam_encode] ") + bam_strerror((int)(e & 0xff)) + ": read '" + b.name((int)(e >> 8)) + "'");
+            }
+            const uint32_t max_entry = (uint32_t)hc[9];
+            const int fixed = max_entry > 0xff00u / 2;
+            const uint32_t quantum = bam_block_quantum(max_entry);
+            const int nblk = raw_total ? (int)cdiv((size_t)raw_total, (size_t)quantum) + 1 : 0;
+            uint32_t bgzf_total = 0;
+            if (nblk) {
+                m.d_bam_raw.ensure((size_t)raw_total + 64);
+                k_bam_write<<<cdiv(n, 128), 128, 0, st>>>(bv, m.d_bam_off.p, reinterpret_cast<char *>(m.d_bam_raw.p));
+                int df_per_sm;
+                {   // (function attributes belong to the device: set once per aligner)
+                    std::lock_guard<std::mutex> l(I.init_m);
+                    if (!I.df_per_sm) {
+                        CK(cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateShared)));
+                        int nb = 1;
+                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_bgzf_deflate, DF_CH, sizeof(DeflateShared)));
+                        I.df_per_sm = std::max(1, nb);
+                    }
+                    df_per_sm = I.df_per_sm;
+                }
+                const int grid = std::min(nblk, I.n_sm * df_per_sm);
+                m.d_bam_cut.ensure(nblk + 2); m.d_bgzf_len.ensure(nblk + 2); m.d_bgzf_off.ensure(nblk + 2);
+                m.d_bgzf_slots.ensure((size_t)nblk * BGZF_SLOT); m.d_bam_tok.ensure((size_t)grid * (BGZF_MAX_IN + 8));
+                k_bam_cuts<<<cdiv(nblk + 1, 128), 128, 0, st>>>(m.d_bam_off.p, n, quantum, fixed, nblk, m.d_bam_cut.p);
+                CK(cudaMemsetAsync(m.d_bgzf_len.p + nblk, 0, 4, st));
+                k_bgzf_deflate<<<grid, DF_CH, sizeof(DeflateShared), st>>>(m.d_bam_raw.p, m.d_bam_cut.p, nblk, m.d_bgzf_slots.p, m.d_bgzf_len.p, m.d_bam_tok.p);
+                cub::DeviceScan::ExclusiveSum(nullptr, sb, m.d_bgzf_len.p, m.d_bgzf_off.p, nblk + 1, st);
+                m.d_cub.ensure(sb + 16);
+                cub::DeviceScan::ExclusiveSum(m.d_cub.p, sb, m.d_bgzf_len.p, m.d_bgzf_off.p, nblk + 1, st);
+                CK(cudaMemcpyAsync(&bgzf_total, m.d_bgzf_off.p + nblk, 4, cudaMemcpyDeviceToHost, st));
+                m.wait();
+                if (bgzf_total > (uint64_t)nblk * BGZF_SLOT) throw std::runtime_error("[E::bsbolt_b200] the BGZF stage produced an impossible size");
+                m.d_bgzf_dense.ensure((size_t)bgzf_total + 64);
+                k_bgzf_gather<<<nblk, 256, 0, st>>>(m.d_bgzf_slots.p, m.d_bgzf_len.p, m.d_bgzf_off.p, nblk, m.d_bgzf_dense.p);
+                m.launches += 8;
+                CK(cudaGetLastError());
+            } else m.launches += 3;
+            CK(cudaEventRecord(m.ev[12], st));
+            out.bam.resize_uninit(bgzf_total);
+            if (bgzf_total) CK(cudaMemcpyAsync(out.bam.data(), m.d_bgzf_dense.p, bgzf_total, cudaMemcpyDeviceToHost, st));
+            for (int k = 0; k < 8; ++k) out.bam_counts[k] = hc[k];
+            out.bam_raw_bytes = raw_total; out.bam_records = hc[10]; out.bam_blocks = (uint64_t)nblk;
+            out.have_bam = true;
+            text_bytes = bgzf_total;       // what crosses PCIe for this batch
+        } else {
         out.text.resize_uninit(text_bytes); out.text_off.resize(n + 1); out.stats.resize(n);
         CK(cudaMemcpyAsync(out.text.data(), m.d_text.p, text_bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out.text_off.data(), m.d_text_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out.stats.data(), m.d_stats.p, (size_t)n * sizeof(SamStats), cudaMemcpyDeviceToHost, st));
-        out.have_text = true;
+        }
+        out.have_text = !out.have_bam;
     } else {
         out.arena.resize_uninit((size_t)used);
         CK(cudaMemcpyAsync(out.arena.data(), m.d_arena.p, (size_t)used, cudaMemcpyDeviceToHost, st));
@@ -1586,8 +1788,10 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         out.fm_block_bytes = I.ix.occ32 ? 32 : 64;
     }
     out.h2d_bytes = nb + (size_t)(n + 1) * 4 + (size_t)n;
-    out.d2h_bytes = (out.have_text ? text_bytes + (size_t)(n + 1) * 4 + (size_t)n * sizeof(SamStats) : (size_t)used) + (size_t)n * sizeof(ReadOut);
-    if (out.have_text) {
+    out.d2h_bytes = (out.have_bam ? text_bytes + 16 * sizeof(unsigned long long)
+                     : out.have_text ? text_bytes + (size_t)(n + 1) * 4 + (size_t)n * sizeof(SamStats) : (size_t)used) + (size_t)n * sizeof(ReadOut);
+    if (out.have_bam) { CK(cudaEventElapsedTime(&ms, m.ev[11], m.ev[12])); out.ms_bam = ms; }
+    if (out.have_text || out.have_bam) {
         CK(cudaEventElapsedTime(&ms, m.ev[8], m.ev[11])); out.ms_text = ms;
         out.h2d_bytes += b.names.size() + (size_t)(n + 1) * 4 + nb + (size_t)n;
     }

@@ -1,0 +1,457 @@
+// bsb_deflate.h -- one BGZF block (RFC 1951 deflate, dynamic Huffman codes, inside the gzip member htslib's bgzf.c writes)
+// produced by ONE thread block from up to 0xff00 bytes of BAM records.
+//
+// Replaces the compression half of `stream_bam` (bsbolt/External/HTSLIB/stream_bam.c -> bgzf_write -> deflate, zlib on the
+// host cores): with the records already in HBM (k_bam_write) the compressed blocks are what crosses PCIe and the host only
+// copies them to the file. Only the *uncompressed* stream is comparable with the reference (tests: inflate and compare);
+// the compressed bytes are this file's own.
+//
+// Shape (everything data-parallel over the block's threads, nothing is a per-thread zlib):
+//   1. Matches. The block is taken in chunks of CH positions, one per thread. Every position hashes its next 4 bytes and
+//      looks up the most recent earlier-chunk position with that hash (an atomic-max table in shared memory, so the table
+//      and hence the output do not depend on thread timing) plus the distance-1 candidate (runs); the longer match wins.
+//   2. Parse. Greedy: from the position where the previous token ended, take the match there (or one literal) and jump
+//      behind it. The positions visited are found by pointer doubling over the chunk's jump table -- 8 rounds for 256
+//      positions, each marking the next 2^k hops -- instead of a serial walk; marked positions are compacted into tokens
+//      (ballot-style prefix over the mark words) and counted into the literal/length and distance histograms.
+//   3. Codes. Symbols are rank-sorted by frequency in parallel; one thread per tree runs the two-queue Huffman merge,
+//      limits the depth (Kraft repair) and assigns canonical codes; one thread run-length-codes the code lengths and
+//      writes the block header.
+//   4. Bits. Every thread sizes a contiguous run of tokens, a scan gives its first bit, it packs its run in a 64-bit
+//      register and ORs whole words into the (zeroed) output; CRC-32 of the input is computed per slice and combined
+//      with x^n mod P multiplications.
+// A block that does not shrink is stored (BTYPE 00).
+//
+// The functions take an execution policy X: X::par(n, f) runs f(i) for i in [0, n) across the block and ends with a barrier;
+// X::atomic_* are the shared/global atomics. XDev (bsb_cuda.cu) maps them to threadIdx/__syncthreads/atomicOr; XHost
+// (tests/hostsim/bamsim.cpp) runs the same phases as plain loops, which is how this file is tested on the CPU against zlib's
+// inflate and crc32 -- a phase therefore never reads what the same phase writes, except through the atomics.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "bsb_hd.h"
+
+namespace bsb {
+
+constexpr int BGZF_MAX_IN = 0xff00;          // htslib BGZF_BLOCK_SIZE
+constexpr int BGZF_SLOT = 0x10000;           // room for one block in the worst case: 18 + 5 + 0xff00 + 8
+constexpr int DF_CH = 256;                   // positions per chunk = threads per block
+constexpr int DF_HASH_BITS = 13;
+constexpr int DF_MIN_MATCH = 4, DF_MAX_MATCH = 258, DF_MAX_DIST = 32768;
+constexpr int DF_NLL = 286, DF_ND = 30, DF_NCL = 19;
+
+struct DeflateShared {
+    uint32_t in32[BGZF_MAX_IN / 4 + 4];      // the block's input: every later access (hashing, match compares, literals, CRC) is a shared-memory access
+    int32_t head[1 << DF_HASH_BITS];         // hash -> latest position of an earlier chunk (-1: none)
+    uint16_t mlen[DF_CH], mdist[DF_CH], hash[DF_CH];
+    uint16_t jump[2][DF_CH];
+    uint32_t markw[DF_CH / 32];
+    uint32_t hist[320];                      // [0, 286): literal/length, [288, 318): distance
+    uint32_t sorted[320];                    // (freq << 9 | symbol) ascending, per tree at the same bases
+    uint32_t wi[320];                        // two-queue merge: weights of the internal nodes
+    uint16_t par_leaf[320], par_int[320], depth_int[320];
+    uint8_t len[320];                        // code lengths
+    uint16_t code[320];                      // codes, bit-reversed (deflate sends Huffman codes MSB first in an LSB-first stream)
+    uint16_t rle[320];                       // run-length coded code lengths: symbol | extra << 8
+    uint32_t hdr[80];                        // the block header's bits
+    uint32_t part[DF_CH + 1];
+    uint32_t crc_tab[256], x2n[32];
+    uint32_t crc;
+    int n_used[2], n_rle, hdr_bits, stored;
+    uint32_t total_bits;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+BSB_HD uint32_t df_load32(const uint8_t *p)                       // four bytes at any address, little-endian
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) << 3;
+    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+#else
+    return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+#endif
+}
+BSB_HD int df_ctz(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+BSB_HD int df_hibit(uint32_t x)                                   // position of the highest set bit, x > 0
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+BSB_HD int df_popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// bytes in[a ..] and in[b ..] agree for how long (at most lim)
+BSB_HD int df_match_len(const uint8_t *in, int a, int b, int lim)
+{
+    int k = 0;
+    for (; k + 4 <= lim; k += 4) {
+        const uint32_t x = df_load32(in + a + k) ^ df_load32(in + b + k);
+        if (x) return k + (df_ctz(x) >> 3);
+    }
+    while (k < lim && in[a + k] == in[b + k]) ++k;
+    return k;
+}
+
+// length 3..258 -> literal/length symbol, number and value of the extra bits (RFC 1951 3.2.5)
+BSB_HD void df_len_code(int l, int &sym, int &nx, int &xv)
+{
+    if (l == 258) { sym = 285; nx = 0; xv = 0; return; }
+    const int m = l - 3;
+    if (m < 8) { sym = 257 + m; nx = 0; xv = 0; return; }
+    const int hb = df_hibit((uint32_t)m);
+    sym = 257 + 4 * (hb - 1) + ((m >> (hb - 2)) & 3);
+    nx = hb - 2; xv = m & ((1 << nx) - 1);
+}
+// distance 1..32768 -> distance symbol, extra bits
+BSB_HD void df_dist_code(int d, int &sym, int &nx, int &xv)
+{
+    if (d <= 4) { sym = d - 1; nx = 0; xv = 0; return; }
+    const int m = d - 1, hb = df_hibit((uint32_t)m);
+    sym = 2 * hb + ((m >> (hb - 1)) & 1);
+    nx = hb - 1; xv = m & ((1 << nx) - 1);
+}
+
+BSB_HD uint32_t df_rev(uint32_t c, int n) { uint32_t r = 0; for (int k = 0; k < n; ++k) { r = r << 1 | (c & 1); c >>= 1; } return r; }
+
+// CRC-32 arithmetic over GF(2), reflected polynomial 0xedb88320: a(x) * b(x) mod P(x)
+BSB_HD uint32_t df_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (uint32_t m = 0x80000000u; m; m >>= 1) {
+        if (a & m) p ^= b;
+        b = (b & 1) ? (b >> 1) ^ 0xedb88320u : b >> 1;
+    }
+    return p;
+}
+// x^(8 n) mod P from the table of x^(2^k) mod P
+BSB_HD uint32_t df_x8n(const uint32_t *x2n, uint32_t n)
+{
+    uint32_t p = 0x80000000u;                 // x^0
+    for (int k = 3; n; n >>= 1, ++k)
+        if (n & 1) p = df_mulmod(x2n[k & 31], p);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Code lengths of one tree. sorted[0, m): (freq << 9 | symbol) ascending; m >= 1. Serial (one thread per tree).
+BSB_HD void df_tree(const uint32_t *sorted, int m, int limit, uint8_t *len, uint16_t *code, int n_sym,
+                    uint32_t *wi, uint16_t *par_leaf, uint16_t *par_int, uint16_t *depth_int)
+{
+    for (int s = 0; s < n_sym; ++s) { len[s] = 0; code[s] = 0; }
+    int bl[16];
+    for (int d = 0; d < 16; ++d) bl[d] = 0;
+    if (m == 1) { len[sorted[0] & 511] = 1; bl[1] = 1; }
+    else {
+        // two queues: the leaves in ascending weight, the internal nodes in the order they are made (ascending too);
+        // on a tie the leaf goes first, which keeps the tree shallow
+        int a = 0, b = 0;
+        for (int j = 0; j < m - 1; ++j) {
+            uint32_t w = 0;
+            for (int k = 0; k < 2; ++k) {
+                if (a < m && (b >= j || (sorted[a] >> 9) <= wi[b])) { w += sorted[a] >> 9; par_leaf[a++] = (uint16_t)j; }
+                else { w += wi[b]; par_int[b++] = (uint16_t)j; }
+            }
+            wi[j] = w;
+        }
+        depth_int[m - 2] = 0;
+        for (int j = m - 3; j >= 0; --j) depth_int[j] = (uint16_t)(depth_int[par_int[j]] + 1);
+        for (int i = 0; i < m; ++i) { int d = depth_int[par_leaf[i]] + 1; if (d > limit) d = limit; ++bl[d]; }
+        // depth limit: the clamped lengths over-subscribe the code space; every step gives one unit of it back
+        // (one code leaves the last level, one code one level up takes a sibling with it)
+        uint32_t total = 0;
+        for (int d = 1; d <= limit; ++d) total += (uint32_t)bl[d] << (limit - d);
+        while (total > (1u << limit)) {
+            --bl[limit];
+            for (int d = limit - 1; d > 0; --d)
+                if (bl[d]) { --bl[d]; bl[d + 1] += 2; break; }
+            --total;
+        }
+        int i = 0;                             // the rarest symbols take the longest codes
+        for (int d = limit; d >= 1; --d)
+            for (int c = 0; c < bl[d]; ++c) len[sorted[i++] & 511] = (uint8_t)d;
+    }
+    uint32_t next[17], c = 0;                  // canonical codes (RFC 1951 3.2.2)
+    next[0] = 0;
+    for (int d = 1; d <= 15; ++d) { c = (c + (d <= limit + 0 ? (uint32_t)bl[d - 1] : 0u)) << 1; next[d] = c; }
+    for (int s = 0; s < n_sym; ++s)
+        if (len[s]) code[s] = (uint16_t)df_rev(next[len[s]]++, len[s]);
+}
+
+struct DfBits {                                // the header's bit writer (one thread)
+    uint32_t *w; int n;
+    BSB_HD void put(uint32_t v, int nb)
+    {
+        if (!nb) return;
+        const int at = n >> 5, sh = n & 31;
+        w[at] |= v << sh;
+        if (sh + nb > 32) w[at + 1] |= v >> (32 - sh);
+        n += nb;
+    }
+};
+
+// token: literal byte, or 1 << 31 | (length - 3) << 16 | (distance - 1)
+BSB_HD int df_token_bits(const DeflateShared &S, uint32_t tk)
+{
+    if (!(tk >> 31)) return S.len[tk];
+    int sym, nx, xv, ds, dnx, dxv;
+    df_len_code((int)((tk >> 16) & 0xff) + 3, sym, nx, xv);
+    df_dist_code((int)(tk & 0xffff) + 1, ds, dnx, dxv);
+    return S.len[sym] + nx + S.len[288 + ds] + dnx;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One BGZF block. in[0, n), 1 <= n <= BGZF_MAX_IN, at any address and readable up to in[n + 7]; out: a 4-byte aligned slot of
+// BGZF_SLOT bytes; tok: BGZF_MAX_IN + 8 words of scratch private to the block. Returns (through S.part[0] after the last
+// barrier, and as the function's value in every thread) the number of bytes of the finished block.
+template <class X>
+BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uint8_t *out, uint32_t *tok)
+{
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out + 16);   // the deflate stream starts at bit 16 of this word array
+    const uint8_t *gin = in;
+    in = reinterpret_cast<const uint8_t *>(S.in32);
+    // ---- 0. input and tables ----
+    x.par(BGZF_MAX_IN / 4 + 4, [&](int w) { S.in32[w] = 4 * w < n ? df_load32(gin + 4 * w) : 0u; });
+    x.par(1 << DF_HASH_BITS, [&](int i) { S.head[i] = -1; });
+    x.par(320, [&](int i) {
+        S.hist[i] = 0;
+        if (i < 256) { uint32_t c = (uint32_t)i; for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0xedb88320u : c >> 1; S.crc_tab[i] = c; }
+        if (i == 256) {
+            uint32_t p = 0x40000000u;          // x^1
+            S.x2n[0] = p;
+            for (int k = 1; k < 32; ++k) S.x2n[k] = p = df_mulmod(p, p);
+            S.crc = 0; S.stored = 0;
+        }
+    });
+    // ---- 1 + 2. matches and the greedy parse, chunk by chunk ----
+    int n_tok = 0, carry = 0;                  // (the same in every thread: computed from shared memory behind a barrier)
+    for (int base = 0; base < n; base += DF_CH) {
+        const int L = n - base < DF_CH ? n - base : DF_CH;
+        const int s0 = carry - base;           // the first position of this chunk that starts a token
+        x.par(DF_CH, [&](int t) {
+            const int i = base + t;
+            int best = 0, dist = 0;
+            S.hash[t] = 0xffff;
+            if (t < L) {
+                const int lim = n - i < DF_MAX_MATCH ? n - i : DF_MAX_MATCH;
+                if (lim >= DF_MIN_MATCH) {
+                    const uint32_t h = (df_load32(in + i) * 2654435761u) >> (32 - DF_HASH_BITS);
+                    S.hash[t] = (uint16_t)h;
+                    const int c = S.head[h];
+                    if (c >= 0 && i - c <= DF_MAX_DIST) { const int l = df_match_len(in, c, i, lim); if (l >= DF_MIN_MATCH) { best = l; dist = i - c; } }
+                    if (i > 0) { const int l = df_match_len(in, i - 1, i, lim); if (l >= DF_MIN_MATCH && l > best) { best = l; dist = 1; } }
+                }
+            }
+            S.mlen[t] = (uint16_t)best; S.mdist[t] = (uint16_t)dist;
+            S.jump[0][t] = (uint16_t)(t < L ? t + (best ? best : 1) : t);
+            if (t < DF_CH / 32) S.markw[t] = (s0 < L && (s0 >> 5) == t) ? 1u << (s0 & 31) : 0u;
+        });
+        for (int k = 0; k < 8; ++k) {
+            const uint16_t *J = S.jump[k & 1];
+            uint16_t *Jn = S.jump[(k & 1) ^ 1];
+            x.par(DF_CH, [&](int t) {
+                if (k == 0 && S.hash[t] != 0xffff) x.atomic_max(&S.head[S.hash[t]], base + t);   // this chunk enters the table
+                const int u = J[t];
+                if (((S.markw[t >> 5] >> (t & 31)) & 1) && u < L) x.atomic_or(&S.markw[u >> 5], 1u << (u & 31));
+                Jn[t] = (uint16_t)(u < L ? J[u] : u);
+            });
+        }
+        uint32_t pre[DF_CH / 32 + 1];
+        pre[0] = 0;
+        for (int w = 0; w < DF_CH / 32; ++w) pre[w + 1] = pre[w] + (uint32_t)df_popc(S.markw[w]);
+        if (s0 < L) carry = base + S.jump[0][s0];                // after 8 doublings jump[0] holds 256 hops: the way out of the chunk
+        x.par(DF_CH, [&](int t) {
+            if (!((S.markw[t >> 5] >> (t & 31)) & 1)) return;
+            const uint32_t at = (uint32_t)n_tok + pre[t >> 5] + (uint32_t)df_popc(S.markw[t >> 5] & ((1u << (t & 31)) - 1));
+            if (S.mlen[t]) {
+                tok[at] = 1u << 31 | (uint32_t)(S.mlen[t] - 3) << 16 | (uint32_t)(S.mdist[t] - 1);
+                int sym, nx, xv;
+                df_len_code(S.mlen[t], sym, nx, xv);
+                x.atomic_add(&S.hist[sym], 1u);
+                df_dist_code(S.mdist[t], sym, nx, xv);
+                x.atomic_add(&S.hist[288 + sym], 1u);
+            } else {
+                const uint32_t b = in[base + t];
+                tok[at] = b;
+                x.atomic_add(&S.hist[b], 1u);
+            }
+        });
+        n_tok += (int)pre[DF_CH / 32];
+    }
+    // ---- 3. codes ----
+    x.par(1, [&](int) {
+        S.hist[256] += 1;                                        // end of block
+        // at least two codes per tree, so that both are complete prefix codes (what every inflater accepts)
+        int nd = 0;
+        for (int s = 0; s < DF_ND; ++s) nd += S.hist[288 + s] != 0;
+        for (int s = 0; nd < 2 && s < DF_ND; ++s) if (!S.hist[288 + s]) { S.hist[288 + s] = 1; ++nd; }
+        int nl = 0;
+        for (int s = 0; s < DF_NLL; ++s) nl += S.hist[s] != 0;
+        for (int s = 0; nl < 2 && s < DF_NLL; ++s) if (!S.hist[s]) { S.hist[s] = 1; ++nl; }
+        S.n_used[0] = nl; S.n_used[1] = nd;
+    });
+    x.par(320, [&](int t) {                                      // rank sort: keys are distinct (the symbol is part of the key)
+        const int lo = t < 288 ? 0 : 288, hi = t < 288 ? DF_NLL : 288 + DF_ND;
+        if (t >= hi || !S.hist[t]) return;
+        const uint32_t key = S.hist[t] << 9 | (uint32_t)(t - lo);
+        int r = 0;
+        for (int u = lo; u < hi; ++u) r += S.hist[u] && (S.hist[u] << 9 | (uint32_t)(u - lo)) < key;
+        S.sorted[lo + r] = key;
+    });
+    x.par(64, [&](int t) {
+        if (t & 31) return;
+        const int w = t >> 5, o = w ? 288 : 0;
+        df_tree(S.sorted + o, S.n_used[w], 15, S.len + o, S.code + o, w ? DF_ND : DF_NLL, S.wi + o, S.par_leaf + o, S.par_int + o, S.depth_int + o);
+    });
+    x.par(1, [&](int) {
+        // code lengths of both trees, run-length coded with the symbols 16 (repeat previous 3-6), 17 (zeros 3-10), 18 (zeros 11-138)
+        int hlit = DF_NLL, hdist = DF_ND;
+        while (hlit > 257 && !S.len[hlit - 1]) --hlit;
+        while (hdist > 1 && !S.len[288 + hdist - 1]) --hdist;
+        uint8_t seq[DF_NLL + DF_ND];
+        int ns = 0;
+        for (int s = 0; s < hlit; ++s) seq[ns++] = S.len[s];
+        for (int s = 0; s < hdist; ++s) seq[ns++] = S.len[288 + s];
+        uint32_t clf[DF_NCL];
+        for (int s = 0; s < DF_NCL; ++s) clf[s] = 0;
+        int nr = 0;
+        for (int i = 0; i < ns;) {
+            const int v = seq[i];
+            int c = 1;
+            while (i + c < ns && seq[i + c] == v) ++c;
+            i += c;
+            if (v == 0) {
+                while (c >= 11) { const int r = c < 138 ? c : 138; S.rle[nr++] = (uint16_t)(18 | (r - 11) << 8); ++clf[18]; c -= r; }
+                if (c >= 3) { S.rle[nr++] = (uint16_t)(17 | (c - 3) << 8); ++clf[17]; c = 0; }
+                for (; c > 0; --c) { S.rle[nr++] = 0; ++clf[0]; }
+            } else {
+                S.rle[nr++] = (uint16_t)v; ++clf[v]; --c;
+                while (c >= 3) { const int r = c < 6 ? c : 6; S.rle[nr++] = (uint16_t)(16 | (r - 3) << 8); ++clf[16]; c -= r; }
+                for (; c > 0; --c) { S.rle[nr++] = (uint16_t)v; ++clf[v]; }
+            }
+        }
+        S.n_rle = nr;
+        // the code of the code lengths: at most 7 bits, 19 symbols -- sorted by insertion
+        uint32_t srt[DF_NCL]; int m = 0;
+        for (int s = 0; s < DF_NCL; ++s) {
+            if (!clf[s]) continue;
+            const uint32_t key = clf[s] << 9 | (uint32_t)s;
+            int k = m++;
+            while (k > 0 && srt[k - 1] > key) { srt[k] = srt[k - 1]; --k; }
+            srt[k] = key;
+        }
+        uint8_t cl_len[DF_NCL]; uint16_t cl_code[DF_NCL];
+        uint32_t wi[DF_NCL]; uint16_t pl[DF_NCL], pi[DF_NCL], di[DF_NCL];
+        df_tree(srt, m, 7, cl_len, cl_code, DF_NCL, wi, pl, pi, di);
+        const uint8_t order[DF_NCL] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        int hclen = DF_NCL;
+        while (hclen > 4 && !cl_len[order[hclen - 1]]) --hclen;
+        for (int w = 0; w < 80; ++w) S.hdr[w] = 0;
+        DfBits B = {S.hdr, 0};
+        B.put(1, 1); B.put(2, 2);                                // BFINAL, BTYPE = dynamic
+        B.put((uint32_t)(hlit - 257), 5); B.put((uint32_t)(hdist - 1), 5); B.put((uint32_t)(hclen - 4), 4);
+        for (int k = 0; k < hclen; ++k) B.put(cl_len[order[k]], 3);
+        for (int k = 0; k < nr; ++k) {
+            const int s = S.rle[k] & 0xff, xv = S.rle[k] >> 8;
+            B.put(cl_code[s], cl_len[s]);
+            if (s == 16) B.put((uint32_t)xv, 2); else if (s == 17) B.put((uint32_t)xv, 3); else if (s == 18) B.put((uint32_t)xv, 7);
+        }
+        S.hdr_bits = B.n;
+    });
+    // ---- 4. bits ----
+    const int per = (n_tok + DF_CH - 1) / DF_CH;
+    x.par(DF_CH, [&](int t) {
+        uint32_t b = 0;
+        const int lo = t * per, hi = lo + per < n_tok ? lo + per : n_tok;
+        for (int k = lo; k < hi; ++k) b += (uint32_t)df_token_bits(S, tok[k]);
+        S.part[t] = b;
+    });
+    x.par(1, [&](int) {
+        uint32_t c = 16 + (uint32_t)S.hdr_bits;                  // bit 16 of out32: where the deflate stream starts
+        for (int t = 0; t < DF_CH; ++t) { const uint32_t b = S.part[t]; S.part[t] = c; c += b; }
+        S.part[DF_CH] = c;
+        S.total_bits = c + S.len[256] - 16;
+        S.stored = (S.total_bits + 7) / 8 >= (uint32_t)n + 5;
+    });
+    uint32_t clen;
+    if (!S.stored) {
+        clen = (S.total_bits + 7) / 8;
+        const int n_words = (int)((16 + S.total_bits + 31) / 32);
+        x.par(n_words, [&](int w) { out32[w] = 0; });
+        const int hdr_words = (S.hdr_bits + 31) / 32;
+        x.par(hdr_words > DF_CH ? hdr_words : DF_CH, [&](int t) {
+            if (t < hdr_words) {                                 // the header, shifted by the 16 bits
+                x.atomic_or(&out32[t], S.hdr[t] << 16);
+                if (S.hdr[t] >> 16) x.atomic_or(&out32[t + 1], S.hdr[t] >> 16);
+            }
+            if (t >= DF_CH) return;
+            const int lo = t * per, hi = lo + per < n_tok ? lo + per : n_tok;
+            uint32_t bit = S.part[t];
+            uint32_t word = bit >> 5;
+            int fill = (int)(bit & 31);
+            uint64_t acc = 0;
+            auto put = [&](uint32_t v, int nb) {
+                acc |= (uint64_t)v << fill; fill += nb;
+                if (fill >= 32) { x.atomic_or(&out32[word++], (uint32_t)acc); acc >>= 32; fill -= 32; }
+            };
+            for (int k = lo; k < hi; ++k) {
+                const uint32_t tk = tok[k];
+                if (!(tk >> 31)) { put(S.code[tk], S.len[tk]); continue; }
+                int sym, nx, xv;
+                df_len_code((int)((tk >> 16) & 0xff) + 3, sym, nx, xv);
+                put(S.code[sym] | (uint32_t)xv << S.len[sym], S.len[sym] + nx);
+                df_dist_code((int)(tk & 0xffff) + 1, sym, nx, xv);
+                put(S.code[288 + sym] | (uint32_t)xv << S.len[288 + sym], S.len[288 + sym] + nx);
+            }
+            if (t == DF_CH - 1) put(S.code[256], S.len[256]);    // end of block (the last thread's run ends the stream)
+            if (fill) x.atomic_or(&out32[word], (uint32_t)acc);
+        });
+    } else {
+        clen = (uint32_t)n + 5;
+        x.par(n, [&](int i) { out[18 + 5 + i] = in[i]; });
+        x.par(1, [&](int) {
+            uint8_t *d = out + 18;
+            d[0] = 1; d[1] = (uint8_t)n; d[2] = (uint8_t)(n >> 8); d[3] = (uint8_t)~d[1]; d[4] = (uint8_t)~d[2];
+        });
+    }
+    // CRC-32 of the input: every thread its slice, then crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
+    const int slice = (n + DF_CH - 1) / DF_CH;
+    x.par(DF_CH, [&](int t) {
+        const int lo = t * slice, hi = lo + slice < n ? lo + slice : n;
+        if (lo >= hi) return;
+        uint32_t c = 0xffffffffu;
+        for (int k = lo; k < hi; ++k) c = S.crc_tab[(c ^ in[k]) & 0xff] ^ (c >> 8);
+        c ^= 0xffffffffu;
+        if (hi < n) c = df_mulmod(df_x8n(S.x2n, (uint32_t)(n - hi)), c);
+        x.atomic_xor(&S.crc, c);
+    });
+    const uint32_t total = 18 + clen + 8;
+    x.par(1, [&](int) {
+        const uint8_t H[16] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0};
+        for (int k = 0; k < 16; ++k) out[k] = H[k];
+        out[16] = (uint8_t)(total - 1); out[17] = (uint8_t)((total - 1) >> 8);
+        uint8_t *tl = out + 18 + clen;
+        const uint32_t c = S.crc, l = (uint32_t)n;
+        tl[0] = (uint8_t)c; tl[1] = (uint8_t)(c >> 8); tl[2] = (uint8_t)(c >> 16); tl[3] = (uint8_t)(c >> 24);
+        tl[4] = (uint8_t)l; tl[5] = (uint8_t)(l >> 8); tl[6] = (uint8_t)(l >> 16); tl[7] = (uint8_t)(l >> 24);
+    });
+    return total;
+}
+
+} // namespace bsb

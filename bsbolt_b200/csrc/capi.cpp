@@ -50,6 +50,7 @@ static void fill_stats(bsb_run_stats_t *s, const RunSummary &sum, const CudaAlig
     s->fm_extensions = (int64_t)sum.n_fm_ext; s->fm_two_block = (int64_t)sum.n_fm_two_block; s->fm_block_bytes = sum.fm_block_bytes;
     s->dp_cells_extend = (int64_t)sum.n_ext_cells; s->fm_two_block_ref = (int64_t)sum.n_fm_two_block_ref;
     s->sec_plan = sum.sec_plan; s->sec_fill = sum.sec_fill; s->rescue_pairs = (int64_t)sum.n_rescue_pairs; s->rescue_jobs = (int64_t)sum.n_rescue_jobs;
+    s->ms_text = sum.ms_text; s->ms_bam = sum.ms_bam; s->bam_raw_bytes = (int64_t)sum.bam_raw_bytes; s->bam_bgzf_bytes = (int64_t)sum.bam_bgzf_bytes; s->bam_blocks = (int64_t)sum.bam_blocks;
 }
 
 extern "C" {
@@ -126,6 +127,7 @@ static int mem_main_impl(bsb_index_t *idx, int device, int argc, char **argv, in
         log = fdopen(lfd, "w");
         if (log) setvbuf(log, nullptr, _IOLBF, 1 << 16);   // whole lines: the descriptor may be shared with other writers (stderr)
         if (bam_path) bam.reset(new BamWriter(bam_path, bam_threads > 0 ? bam_threads : host_thread_share(), bam_level));
+        if (bam) bam->accept_device_blocks(bam_level < 0 && !getenv("BSB_BAM_HOST"));   // default level: compressed on the device (bsb_deflate.h)
         else {
             int ofd = dup(out_fd);
             if (!ma.out_path.empty()) { out = fopen(ma.out_path.c_str(), "wb"); if (ofd >= 0) close(ofd); }

@@ -1,5 +1,6 @@
 // host_bam.cpp -- see host_bam.h
 #include "host_bam.h"
+#include "bsb_bam.h"
 #include <errno.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,37 +20,6 @@ const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06,
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// seq_nt16_table (hts.c:73-91): "=ACMGRSVTWYHKDBN", anything else 15
-struct Nt16 {
-    uint8_t t[256];
-    Nt16()
-    {
-        memset(t, 15, sizeof t);
-        const char *s = "=ACMGRSVTWYHKDBN";
-        for (int i = 0; i < 16; ++i) { t[(uint8_t)s[i]] = (uint8_t)i; if (s[i] >= 'A') t[(uint8_t)(s[i] + 32)] = (uint8_t)i; }
-        t[(uint8_t)'0'] = 1; t[(uint8_t)'1'] = 2; t[(uint8_t)'2'] = 4; t[(uint8_t)'3'] = 8;
-    }
-};
-const Nt16 g_nt16;
-
-inline int cigar_op(char c)
-{
-    switch (c) {
-    case 'M': return 0; case 'I': return 1; case 'D': return 2; case 'N': return 3; case 'S': return 4;
-    case 'H': return 5; case 'P': return 6; case '=': return 7; case 'X': return 8; case 'B': return 9;
-    }
-    return -1;
-}
-
-// hts_reg2bin(beg, end, 14, 5) (htslib/hts.h:1322-1328)
-inline int reg2bin(int64_t beg, int64_t end)
-{
-    int l, s = 14, t = ((1 << 15) - 1) / 7;
-    for (--end, l = 5; l > 0; --l, s += 3, t -= 1 << ((l << 1) + l))
-        if (beg >> s == end >> s) return t + (int)(beg >> s);
-    return 0;
-}
-
 inline void put32(std::vector<uint8_t> &o, uint32_t v) { uint8_t b[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)}; o.insert(o.end(), b, b + 4); }
 inline void set32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 
@@ -58,20 +28,6 @@ inline void set32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(
     throw std::runtime_error(std::string("[E::bam_encode] ") + what + ": " + std::string(p, std::min<size_t>(e - p, 80)));
 }
 
-inline uint64_t parse_uint(const char *&p, const char *e)
-{
-    uint64_t v = 0;
-    if (p < e && *p == '+') ++p;
-    while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (uint64_t)(*p++ - '0');
-    return v;
-}
-inline int64_t parse_int(const char *&p, const char *e)
-{
-    bool neg = false;
-    if (p < e && (*p == '-' || *p == '+')) neg = *p++ == '-';
-    const uint64_t v = parse_uint(p, e);
-    return neg ? -(int64_t)v : (int64_t)v;
-}
 } // namespace
 
 struct BamWriter::Worker {
@@ -190,140 +146,29 @@ void BamWriter::header(const std::string &text)
     w.comp.clear();
 }
 
-// sam_parse1 (sam.c:1924-2160) followed by bam_write1 (sam.c:661-735), little-endian host
+// sam_parse1 (sam.c:1924-2160) followed by bam_write1 (sam.c:661-735): bam_record (bsb_bam.h), the statements the device runs too
 void BamWriter::encode_record(const char *p, const char *e, std::vector<uint8_t> &o) const
 {
-    const char *line = p;
-    auto field = [&](const char *&b, size_t &n) {   // next tab-separated field; p moves behind its tab
-        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
-        if (!t) bad("truncated record", line, e);
-        b = p; n = (size_t)(t - p); p = t + 1;
-    };
-    const char *qn, *s; size_t l_qn, n;
-    field(qn, l_qn);
-    if (l_qn + 1 > 255) bad("query name too long", line, e);
-    uint32_t flag = (uint32_t)parse_uint(p, e);
-    if (p >= e || *p++ != '\t') bad("malformed FLAG", line, e);
-    field(s, n);
-    int32_t tid = (n == 1 && *s == '*') ? -1 : tid_of(s, n);
-    int64_t pos = (int64_t)parse_uint(p, e) - 1;
-    if (p >= e || *p++ != '\t') bad("malformed POS", line, e);
-    if (pos < 0 && tid >= 0) tid = -1;
-    if (tid < 0) flag |= 4;
-    const uint32_t mapq = (uint32_t)parse_uint(p, e) & 0xff;
-    if (p >= e || *p++ != '\t') bad("malformed MAPQ", line, e);
-
+    auto tid = [this](const char *s, size_t n) { return tid_of(s, n); };
+    SamCount c;
+    BamCore core;
+    int rc = bam_record(c, tid, p, e, nullptr, &core);
+    if (rc != BAM_OK) bad(bam_strerror(rc), p, e);
     const size_t at = o.size();
-    o.resize(at + 36 + l_qn + 1);
-    memcpy(o.data() + at + 36, qn, l_qn);
-    o[at + 36 + l_qn] = 0;
+    o.resize(at + c.n);
+    SamWrite w = {reinterpret_cast<char *>(o.data() + at)};
+    rc = bam_record(w, tid, p, e, &core, nullptr);
+    if (rc != BAM_OK || (size_t)(w.p - reinterpret_cast<char *>(o.data() + at)) != c.n) bad("record changed between sizing and writing", p, e);
+}
 
-    uint32_t n_cigar = 0;
-    int64_t cigreflen = 1, qlen_cigar = 0;
-    if (*p != '*') {
-        int64_t rlen = 0;
-        while (p < e && *p != '\t') {
-            const uint64_t len = parse_uint(p, e);
-            const int op = p < e ? cigar_op(*p) : -1;
-            if (op < 0) bad("unrecognized CIGAR operator", line, e);
-            ++p;
-            put32(o, (uint32_t)(len << 4) | (uint32_t)op);
-            ++n_cigar;
-            if ((0x3C1A7 >> (op << 1)) & 2) rlen += (int64_t)len;
-            if ((0x3C1A7 >> (op << 1)) & 1) qlen_cigar += (int64_t)len;
-        }
-        if (p >= e || *p++ != '\t') bad("truncated record", line, e);
-        if (n_cigar == 0) bad("no CIGAR operations", line, e);
-        if (n_cigar > 0xffff) bad("more than 65535 CIGAR operations", line, e);
-        cigreflen = !(flag & 4) ? rlen : 1;
-    } else {
-        flag |= 4;
-        field(s, n);
-    }
-    const int bin = reg2bin(pos, pos + cigreflen);
-    field(s, n);
-    int32_t mtid;
-    if (n == 1 && *s == '=') mtid = tid;
-    else if (n == 1 && *s == '*') mtid = -1;
-    else mtid = tid_of(s, n);
-    int64_t mpos = (int64_t)parse_uint(p, e) - 1;
-    if (p >= e || *p++ != '\t') bad("malformed PNEXT", line, e);
-    if (mpos < 0 && mtid >= 0) mtid = -1;
-    const int64_t isize = parse_int(p, e);
-    if (p >= e || *p++ != '\t') bad("malformed TLEN", line, e);
-    field(s, n);
-    uint32_t l_seq = 0;
-    if (!(n == 1 && *s == '*')) {
-        l_seq = (uint32_t)n;
-        if (n_cigar && qlen_cigar != (int64_t)l_seq) bad("CIGAR and query sequence are of different length", line, e);
-        const size_t a = o.size();
-        o.resize(a + (l_seq + 1) / 2);
-        uint8_t *t = o.data() + a;
-        uint32_t i = 0;
-        for (; i + 1 < l_seq; i += 2) t[i >> 1] = (uint8_t)(g_nt16.t[(uint8_t)s[i]] << 4 | g_nt16.t[(uint8_t)s[i + 1]]);
-        if (i < l_seq) t[i >> 1] = (uint8_t)(g_nt16.t[(uint8_t)s[i]] << 4);
-    }
-    {   // QUAL: the last mandatory field, ends at a tab or at the end of the line
-        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
-        const char *qe = t ? t : e;
-        const size_t a = o.size();
-        o.resize(a + l_seq);
-        if (qe - p == 1 && *p == '*') memset(o.data() + a, 0xff, l_seq);
-        else {
-            if ((size_t)(qe - p) != l_seq) bad("SEQ and QUAL are of different length", line, e);
-            for (uint32_t i = 0; i < l_seq; ++i) {
-                const int v = (uint8_t)p[i] - 33;
-                if (v < 0 || v > 127) bad("invalid QUAL character", line, e);
-                o[a + i] = (uint8_t)v;
-            }
-        }
-        p = t ? t + 1 : e;
-    }
-    while (p < e) {   // optional fields TAG:TYPE:VALUE
-        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
-        const char *fe = t ? t : e;
-        if (fe - p < 5 || p[2] != ':' || p[4] != ':') bad("incomplete aux field", line, e);
-        const char type = p[3];
-        const char *v = p + 5;
-        o.push_back((uint8_t)p[0]); o.push_back((uint8_t)p[1]);
-        if (type == 'A' || type == 'a' || type == 'c' || type == 'C') {
-            if (v >= fe) bad("incomplete aux field", line, e);
-            o.push_back('A'); o.push_back((uint8_t)*v);
-        } else if (type == 'i' || type == 'I') {
-            if (v >= fe) bad("incomplete aux field", line, e);
-            if (*v == '-') {
-                const int64_t x = parse_int(v, fe);
-                if (x >= -128) { o.push_back('c'); o.push_back((uint8_t)(int8_t)x); }
-                else if (x >= -32768) { o.push_back('s'); o.push_back((uint8_t)x); o.push_back((uint8_t)(x >> 8)); }
-                else { o.push_back('i'); put32(o, (uint32_t)(int32_t)x); }
-            } else {
-                const uint64_t x = parse_uint(v, fe);
-                if (x <= 255) { o.push_back('C'); o.push_back((uint8_t)x); }
-                else if (x <= 65535) { o.push_back('S'); o.push_back((uint8_t)x); o.push_back((uint8_t)(x >> 8)); }
-                else { o.push_back('I'); put32(o, (uint32_t)x); }
-            }
-        } else if (type == 'f') {
-            std::string tmp(v, fe);
-            const float f = (float)strtod(tmp.c_str(), nullptr);
-            uint32_t u; memcpy(&u, &f, 4);
-            o.push_back('f'); put32(o, u);
-        } else if (type == 'Z' || type == 'H') {
-            o.push_back((uint8_t)type);
-            o.insert(o.end(), v, fe);
-            o.push_back(0);
-        } else bad("unsupported aux type", p, fe);
-        p = t ? t + 1 : e;
-    }
-    uint8_t *h = o.data() + at;
-    set32(h, (uint32_t)(o.size() - at - 4));
-    set32(h + 4, (uint32_t)tid);
-    set32(h + 8, (uint32_t)(int32_t)pos);
-    set32(h + 12, (uint32_t)bin << 16 | mapq << 8 | (uint32_t)(l_qn + 1));
-    set32(h + 16, flag << 16 | (n_cigar & 0xffff));
-    set32(h + 20, l_seq);
-    set32(h + 24, (uint32_t)mtid);
-    set32(h + 28, (uint32_t)(int32_t)mpos);
-    set32(h + 32, (uint32_t)(int32_t)isize);
+// BGZF blocks made elsewhere (the device's deflate, bsb_deflate.h): they only have to reach the file, in order
+void BamWriter::blocks(const uint8_t *bgzf, size_t n, uint64_t raw_bytes, uint64_t n_records)
+{
+    if (!have_header_) throw std::runtime_error("[E::bam] records before the header");
+    const double t0 = now_s();
+    if (n && fwrite(bgzf, 1, n, f_) != n) throw std::runtime_error("[E::bam] write failed");
+    file_bytes_ += n; raw_bytes_ += raw_bytes; n_records_ += n_records;
+    sec_busy_ += now_s() - t0;
 }
 
 void BamWriter::records(const char *text, size_t n)

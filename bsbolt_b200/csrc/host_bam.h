@@ -20,6 +20,11 @@ public:
     ~BamWriter();
     void header(const std::string &sam_header_text);     // magic, header text, reference table from the @SQ lines
     void records(const char *text, size_t n);            // whole SAM record lines, '\n'-terminated
+    void blocks(const uint8_t *bgzf, size_t n, uint64_t raw_bytes, uint64_t n_records);   // finished BGZF blocks (compressed on the device), appended as they are
+    // the pipeline asks the aligner for finished blocks (BatchResult::want_bam) when this is set: the default compression level
+    // (the caller did not ask for a zlib level) and no BSB_BAM_HOST in the environment
+    void accept_device_blocks(bool yes) { device_blocks_ = yes; }
+    bool device_blocks() const { return device_blocks_; }
     void close();                                        // flush + BGZF EOF block
     uint64_t n_records() const { return n_records_; }
     uint64_t raw_bytes() const { return raw_bytes_; }    // uncompressed BAM bytes written so far
@@ -32,7 +37,7 @@ private:
     struct Worker;
     FILE *f_ = nullptr;
     int threads_, level_;
-    bool have_header_ = false, closed_ = false;
+    bool have_header_ = false, closed_ = false, device_blocks_ = false;
     std::unordered_map<std::string, int> ref_ids_;
     std::vector<Worker *> workers_;
     uint64_t n_records_ = 0, raw_bytes_ = 0, file_bytes_ = 0;

@@ -1,5 +1,6 @@
 // host_index.cpp -- see host_index.h
 #include "host_index.h"
+#include <algorithm>
 #include <stdio.h>
 #include <string.h>
 #include <stdexcept>
@@ -144,6 +145,9 @@ void HostIndex::build_sam_table()
         ctg_text.insert(ctg_text.end(), contigs[i].anno.begin(), contigs[i].anno.end());
     }
     ctg_anno_off[n] = (uint32_t)ctg_text.size();
+    ctg_sorted.resize(n);
+    for (size_t i = 0; i < n; ++i) ctg_sorted[i] = (int32_t)i;
+    std::stable_sort(ctg_sorted.begin(), ctg_sorted.end(), [&](int32_t a, int32_t b) { return contigs[a].name < contigs[b].name; });
 }
 
 IndexView HostIndex::host_view() const

@@ -28,6 +28,7 @@ struct HostIndex {
     std::string prefix;
     // contig table flattened for the SAM formatter (bsb_sam.h): names back to back, then annotations
     std::vector<char> ctg_text; std::vector<uint32_t> ctg_name_off, ctg_anno_off; std::vector<uint8_t> ctg_is_crick, ctg_sign;
+    std::vector<int32_t> ctg_sorted;   // contig ids ordered by name, then id: the BAM encoder's name -> tid lookup (BamContigs, bsb_bam.h)
     bool any_alt = false;
     void build_sam_table();
 

@@ -788,6 +788,9 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
     const int shard_count = ma.shard_count > 1 ? ma.shard_count : 1, shard_index = ma.shard_index;
     size_t out_bytes = 0;
     if (bam && shard_count > 1) throw std::runtime_error("[E::run_mem] BAM output of a sharded run is written after the merge");
+    // BGZF blocks straight from the device: not when the user supplied @SQ lines (the device resolves contig names through the index's
+    // own table) or asked for the FASTQ comments (free text the device formatter does not carry)
+    const bool dev_bam = bam && bam->device_blocks() && !ma.copy_comment && !(ma.have_hdr && ma.hdr_line.find("@SQ") != std::string::npos);
     // records leave as SAM text on `out` or, with a BamWriter, as BAM records (the `| stream_bam` half of the reference pipeline)
     auto put_out = [&](const char *p, size_t n) {
         if (bam) bam->records(p, n);
@@ -920,6 +923,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                     double ta = now_sec();
                     j->res.want_text = true; j->res.rg_id = ma.rg_id;   // SAM text from the device when the aligner can produce it
                     const bool smart = (ma.opt.flag & F_SMARTPE) != 0;
+                    j->res.want_bam = dev_bam && !smart;               // ... or, for a BAM file, the finished BGZF blocks
                     if (smart) {
                         for (int k = 0; k < 8; ++k) j->res.ms_stage[k] = 0;
                         j->res.ms_h2d = j->res.ms_kernels = j->res.ms_d2h = 0; j->res.n_seeds = j->res.h2d_bytes = j->res.d2h_bytes = 0;
@@ -956,7 +960,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 const ReadBatch &batch = j->batch;
                 if (sum.n_batches == 0 && g_host_alloc.prefill && !resident && !t_prefill.joinable()) {
                     const size_t s_bases = batch.bases.capacity(), s_names = batch.names.capacity(), s_reads = j->res.reads.size() * sizeof(ReadOut);
-                    const size_t s_arena = j->res.have_text ? j->res.text.size() : j->res.arena.size();
+                    const size_t s_arena = j->res.have_bam ? j->res.bam.size() : j->res.have_text ? j->res.text.size() : j->res.arena.size();
                     const size_t s_off = j->res.text_off.size() * 4, s_stats = j->res.stats.size() * sizeof(SamStats);
                     t_prefill = std::thread([=] {
                         // every job in flight holds: bases, qualities, names; result text (or arena), per-read records, offsets, statistics
@@ -973,6 +977,15 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 MapStats ms;
                 size_t total = 0;
                 double tw;
+                if (j->res.have_bam) {
+                    // records, arbiter and compression ran on the device: the blocks go to the file as they are
+                    const BatchResult &R = j->res;
+                    ms.reads = (long)R.bam_counts[0]; ms.alignments = (long)R.bam_counts[1]; ms.wc2t = (long)R.bam_counts[2]; ms.wg2a = (long)R.bam_counts[3];
+                    ms.cc2t = (long)R.bam_counts[4]; ms.cg2a = (long)R.bam_counts[5]; ms.unaligned = (long)R.bam_counts[6]; ms.bs_ambiguous = (long)R.bam_counts[7];
+                    tw = now_sec();
+                    total = R.bam.size();
+                    bam->blocks(R.bam.data(), total, R.bam_raw_bytes, R.bam_records);
+                } else
                 if (j->res.have_text) {
                     // the records were formatted on the device: only the arbiter runs here
                     const BatchResult &R = j->res;
@@ -1061,7 +1074,7 @@ int run_mem(const MemArgs &ma, const HostIndex &idx, BatchAligner &aligner, FILE
                 sum.n_entries += batch.n;
             } catch (const std::exception &e) { set_fail(e.what()); }
             if (resident) {   // the page-locked host buffers go back to the pool now, for the batches still to come
-                j->res.arena.reset(); j->res.reads.reset(); j->res.text.reset(); j->res.text_off.reset(); j->res.stats.reset(); j->batch.bases.reset();
+                j->res.arena.reset(); j->res.reads.reset(); j->res.text.reset(); j->res.bam.reset(); j->res.text_off.reset(); j->res.stats.reset(); j->batch.bases.reset();
                 finished.push_back(std::move(j));
             }   // (device inputs are freed after the run: cudaFree synchronises the device)
             else q_free.push(std::move(j));

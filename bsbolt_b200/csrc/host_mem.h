@@ -62,6 +62,14 @@ struct BatchResult {
     std::string rg_id;
     RawBuf text; PinArray<uint32_t> text_off; PinArray<SamStats> stats;
     double ms_text = 0;
+    // BAM on the device (bsb_bam.h, bsb_deflate.h): requested with want_bam (the caller writes a BAM file and no comments are
+    // appended). When have_bam comes back true the arbiter ran on the device, `bam` holds the finished BGZF blocks of the batch's
+    // records in input order -- the host only appends them to the file -- and neither text nor arena were copied back.
+    bool want_bam = false, have_bam = false;
+    RawBuf bam;
+    uint64_t bam_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // reads, alignments, W_C2T, W_G2A, C_C2T, C_G2A, unaligned, BS-ambiguous (the BSStat lines)
+    uint64_t bam_raw_bytes = 0, bam_records = 0, bam_blocks = 0;
+    double ms_bam = 0;
     std::string log_text;        // log lines of this batch (mem_pestat), printed by the pipeline as one block
 };
 
@@ -120,8 +128,11 @@ struct RunSummary {
     uint64_t n_fm_ext = 0, n_fm_two_block = 0, n_fm_two_block_ref = 0, n_ext_cells = 0; int fm_block_bytes = 0;
     uint64_t n_rescue_pairs = 0, n_rescue_jobs = 0;
     double ms_select = 0, ms_tasks = 0;
+    double ms_text = 0, ms_bam = 0; uint64_t bam_raw_bytes = 0, bam_bgzf_bytes = 0, bam_blocks = 0;
     void add_timing(const BatchResult &r)
     {
+        ms_text += r.ms_text; ms_bam += r.ms_bam;
+        if (r.have_bam) { bam_raw_bytes += r.bam_raw_bytes; bam_bgzf_bytes += r.bam.size(); bam_blocks += r.bam_blocks; }
         ms_select += r.ms_select; ms_tasks += r.ms_tasks; n_tasks += r.n_tasks;
         ms_h2d += r.ms_h2d; ms_kernels += r.ms_kernels; ms_d2h += r.ms_d2h;
         for (int k = 0; k < 8; ++k) ms_stage[k] += r.ms_stage[k];

@@ -43,6 +43,10 @@ typedef struct {
     int64_t fm_two_block_ref;              /* ... of them that touch two of the reference's 64-byte occ blocks (bwt.h:72-78) */
     double sec_plan, sec_fill;             /* sec_read split: cutting the batches (incl. waiting for the parser threads) / copying them */
     int64_t rescue_pairs, rescue_jobs;     /* pairs that needed mate-rescue Smith-Waterman (mem_matesw) and the Smith-Waterman jobs run for them */
+    /* output stages on the device, CUDA-event sums in ms: SAM text of the records; for a BAM file at the default level the
+       arbiter + BAM records + BGZF deflate that follow it (bsb_mem_main_bam), with the uncompressed and compressed sizes */
+    double ms_text, ms_bam;
+    int64_t bam_raw_bytes, bam_bgzf_bytes, bam_blocks;
 } bsb_run_stats_t;
 
 typedef struct {

@@ -17,6 +17,8 @@
 #include "../../bsbolt_b200/csrc/bsb_extlane.h"
 #include "../../bsbolt_b200/csrc/bsb_rescue.h"
 #include "../../bsbolt_b200/csrc/host_mem.h"
+#include "../../bsbolt_b200/csrc/host_bam.h"
+#include "bam_emulation.h"
 
 using namespace bsb;
 
@@ -224,6 +226,36 @@ public:
         }
         for (int r = 0; r < n; ++r)
             if (out.reads[r].err) throw std::runtime_error("hostsim: read " + b.name(r) + " failed with error code " + std::to_string(out.reads[r].err));
+        out.have_bam = false;
+        if (out.want_bam && !idx_.any_alt && b.comments.empty() && n) {
+            // the device's BAM stage, emulated (bam_emulation.h): SAM text of every entry as the device formatter leaves it, then the
+            // arbiter, the records and the BGZF blocks through the functions the kernels run
+            MemArgs ma;
+            ma.opt = opt; ma.rg_id = out.rg_id;
+            std::string text, one;
+            std::vector<uint32_t> text_off(n + 1, 0);
+            std::vector<SamStats> stats(n);
+            for (int i = 0; i < n; ++i) {
+                EntryStats st;
+                format_entry(ma, idx_, b, i, out, one, st);
+                text += one;
+                text_off[i + 1] = (uint32_t)text.size();
+                stats[i].alignment_score = st.alignment_score; stats[i].mapped = st.mapped; stats[i].bs_conflict = st.bs_conflict; stats[i].crick = st.crick; stats[i].paired = st.paired;
+            }
+            BamBatchIn in;
+            in.names = b.names.data(); in.name_off = b.name_off.data(); in.first = b.first.data(); in.read_group = b.read_group.data();
+            in.bases = b.bases.data(); in.qual = b.qual.data(); in.seq_off = b.seq_off.data(); in.has_qual = b.has_qual.data();
+            in.text = text.data(); in.text_off = text_off.data(); in.stats = stats.data(); in.n = n;
+            in.ctg_text = idx_.ctg_text.data(); in.ctg_name_off = idx_.ctg_name_off.data(); in.ctg_sorted = idx_.ctg_sorted.data(); in.n_ctg = (int)idx_.ctg_sorted.size();
+            std::vector<uint8_t> bgzf;
+            MapCounters ctr;
+            bam_batch_emulated(in, bgzf, ctr, out.bam_raw_bytes, out.bam_records);
+            out.bam.resize_uninit(bgzf.size());
+            if (!bgzf.empty()) memcpy(out.bam.data(), bgzf.data(), bgzf.size());
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(&ctr);
+            for (int k = 0; k < 8; ++k) out.bam_counts[k] = f[k];
+            out.have_bam = true;
+        }
     }
 private:
     const HostIndex &idx_;
@@ -293,6 +325,13 @@ int main(int argc, char **argv)
         if (ma.ignore_alt) for (auto &a : idx.anns) a.is_alt = 0;
         HostSimAligner al(idx);
         RunSummary sum;
+        if (const char *e = getenv("HOSTSIM_BAM")) {   // HOSTSIM_BAM=<path>: the run's BAM file; HOSTSIM_BAM_HOST=1: through the host encoder (zlib)
+            BamWriter bw(e, 2, -1);
+            bw.accept_device_blocks(!getenv("HOSTSIM_BAM_HOST"));
+            const int rc = run_mem(ma, idx, al, nullptr, stderr, &sum, &bw);
+            bw.close();
+            return rc;
+        }
         if (const char *e = getenv("HOSTSIM_DEVICES")) {
             FakeDevices multi(al, std::max(1, atoi(e)));
             const int rc = run_mem(ma, idx, multi, stdout, stderr, &sum);

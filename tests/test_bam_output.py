@@ -163,3 +163,127 @@ def test_aligner_writes_the_bam_the_reference_pipeline_would(built, golden, tmp_
             assert len(walk_records(raw)[2]) == golden.cases[case]['n_records']
     finally:
         idx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BAM made on the device (bsb_bam.h records + arbiter, bsb_deflate.h BGZF blocks)
+# ----------------------------------------------------------------------------------------------------------------------
+BAMSIM = os.path.join(ROOT, 'tests', 'hostsim', 'bamsim')
+HOSTSIM = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim')
+
+
+@pytest.mark.parametrize('order', ['', 'reverse', 'shuffle'])
+def test_device_deflate_blocks_inflate_to_the_input(built, tmp_path, order):
+    """bgzf_block (the body of k_bgzf_deflate) phase by phase on the CPU: every block is valid deflate for zlib, carries
+    zlib's CRC-32, and the bytes do not depend on the order the block's threads run in"""
+    import random
+    random.seed(7)
+    cases = {
+        'empty': b'', 'one': b'x', 'three': b'abc', 'four': b'abcd', 'zeros': bytes(200000), 'noise': random.randbytes(150000),
+        'runs': b''.join(bytes([random.randrange(4)]) * random.randrange(1, 600) for _ in range(1500)),
+        'records': b''.join(b'read_%d\tNM:i:%d\tMD:Z:%d\tYS:Z:W_C2T\t%s\n' % (i, i % 7, i % 150, bytes(random.choices(b'FFFFFF:,#', k=40))) for i in range(20000)),
+        'block': bytes(range(256)) * 255, 'block+1': bytes(range(256)) * 255 + b'z',
+        'skewed': bytes(random.choices(range(256), weights=[2 ** (-(i / 4)) for i in range(256)], k=200000)),
+    }
+    env = dict(os.environ)
+    if order:
+        env['BSB_PAR_ORDER'] = order
+    sizes = {}
+    for name, data in cases.items():
+        (tmp_path / 'in').write_bytes(data)
+        p = subprocess.run([BAMSIM, 'deflate', str(tmp_path / 'in'), str(tmp_path / 'out')], env=env, capture_output=True, text=True)
+        assert p.returncode == 0, (name, p.stderr)
+        out = (tmp_path / 'out').read_bytes()
+        assert out.endswith(EOF_BLOCK)
+        assert b''.join(bgzf_blocks(out)) == data, name
+        sizes[name] = hashlib.sha256(out).hexdigest()
+        if name in ('zeros', 'runs', 'records', 'block'):
+            assert len(out) < len(data) / (3 if name == 'records' else 20), name   # the matches are found
+        if name == 'noise':
+            assert len(out) <= len(data) + 40 * (len(data) // 0xff00 + 2)   # stored blocks
+    ref = tmp_path.parent / 'deflate_digests.json'                 # shared by the three parametrisations of this session
+    if ref.exists():
+        assert json.load(open(ref)) == sizes, 'the compressed bytes depend on the thread order'
+    else:
+        json.dump(sizes, open(ref, 'w'))
+
+
+@pytest.mark.parametrize('name', sorted(json.load(open(os.path.join(GOLDEN, 'bam_golden.json')))['streams']))
+def test_device_record_encoder_identical_to_reference_encoder(built, tmp_path, name):
+    """bam_entry with the sorted-contig lookup (the body of k_bam_count / k_bam_write) + bgzf_block on the reference's SAM:
+    the uncompressed stream equals the reference encoder's, and no record that fits a block is split"""
+    want = golden_streams()[name]
+    src = tmp_path / 'in.sam'
+    src.write_bytes(sam_bytes(name))
+    p = subprocess.run([BAMSIM, 'sam2bam', str(src), str(tmp_path / 'out.bam')], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    data = open(tmp_path / 'out.bam', 'rb').read()
+    blocks = bgzf_blocks(data)
+    raw = b''.join(blocks)
+    assert len(raw) == want['raw_len'] and hashlib.sha256(raw).hexdigest() == want['raw_sha256']
+    text, names, recs = walk_records(raw)
+    ends, pos = set(), 0
+    for b in blocks:
+        pos += len(b); ends.add(pos)
+    off = len(raw) - sum(len(r) for r in recs)
+    for r in recs:
+        if len(r) <= 0xff00 // 2:
+            assert not [e for e in ends if off < e < off + len(r)], 'a record that fits a block was split'
+        off += len(r)
+
+
+@pytest.mark.parametrize('case', ['pe150', 'pe150_un', 'pe150_un_sp0', 'se100_un', 'se50_clip'])
+def test_device_bam_stage_equals_host_writer(built, golden, tmp_path, case):
+    """The whole stage on the CPU (tests/hostsim, HOSTSIM_BAM): arbiter on "device", records, blocks -- against the host
+    path (SAM text -> arbiter -> BamWriter) of the same run: identical uncompressed stream, identical BSStat lines. The
+    undirectional cases drop the losing conversion group and rewrite BS-ambiguous reads as unmapped records."""
+    outs, stats = [], []
+    for host in (False, True):
+        env = dict(os.environ, BSB_HOSTSIM_SEED_V3='1', HOSTSIM_BAM=str(tmp_path / f'o{int(host)}.bam'))
+        if host:
+            env['HOSTSIM_BAM_HOST'] = '1'
+        argv = golden.argv(case)
+        nfq = len(golden.cases[case]['fq'])
+        argv = argv[:-nfq - 1] + ['-K', '60000'] + argv[-nfq - 1:]
+        p = subprocess.run([HOSTSIM] + argv, capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(b''.join(bgzf_blocks(open(tmp_path / f'o{int(host)}.bam', 'rb').read())))
+        stats.append([l for l in p.stderr.split('\n') if l.startswith('BSStat ')])
+    assert outs[0] == outs[1]
+    assert stats[0] == stats[1] and len(stats[0]) >= 8
+    assert len(walk_records(outs[0])[2]) == golden.cases[case]['n_records']
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['pe150', 'pe150_un', 'se100_un', 'se50_clip'])
+def test_bam_made_on_the_device_equals_the_host_writer(built, golden, tmp_path, case):
+    """bsb_mem_main_bam at the default level: arbiter (k_bam_arbiter), records (k_bam_count / k_bam_write) and BGZF blocks
+    (k_bgzf_deflate) on the GPU -- against the same run through SAM text and the host encoder: identical uncompressed
+    stream (which the other tests pin to the reference's stream_bam), identical BSStat lines, every block valid for zlib."""
+    from bsbolt_b200 import _native
+    idx = _native.Index(golden.idxbase, 0)
+    try:
+        argv = golden.argv(case)
+        nfq = len(golden.cases[case]['fq'])
+        argv = argv[:-nfq - 1] + ['-K', '60000'] + argv[-nfq - 1:]
+        raws, logs, stats = [], [], []
+        for level in (-1, 1):
+            with open(tmp_path / f'log{level}', 'w') as fl:
+                rc, st = _native.mem_main_bam(argv, tmp_path / f'l{level}.bam', index=idx, threads=2, level=level, log_fd=fl.fileno())
+            assert rc == 0, _native.last_error()
+            data = open(tmp_path / f'l{level}.bam', 'rb').read()
+            assert data.endswith(EOF_BLOCK)
+            raws.append(b''.join(bgzf_blocks(data)))
+            logs.append([l for l in open(tmp_path / f'log{level}') if l.startswith('BSStat ')])
+            stats.append(st)
+        assert raws[0] == raws[1]
+        assert logs[0] == logs[1] and len(logs[0]) >= 8
+        assert stats[0]['d2h_bytes'] < stats[1]['d2h_bytes']           # compressed blocks crossed PCIe, not text
+        assert len(walk_records(raws[0])[2]) == golden.cases[case]['n_records']
+        if os.path.exists(STREAM_BAM):
+            with open(tmp_path / 'x.sam', 'w') as fo, open(tmp_path / 'log2', 'w') as fl:
+                rc, _ = _native.mem_main(argv, index=idx, out_fd=fo.fileno(), log_fd=fl.fileno())
+            subprocess.run([STREAM_BAM, '-o', str(tmp_path / 'ref.bam')], stdin=open(tmp_path / 'x.sam'), check=True, stderr=subprocess.DEVNULL)
+            assert gzip.open(tmp_path / 'ref.bam', 'rb').read() == raws[0]
+    finally:
+        idx.close()
