@@ -807,10 +807,37 @@ __global__ void k_bam_cuts(const uint32_t *off, int n, uint32_t quantum, int fix
 }
 
 struct XDev {   // bsb_deflate.h's execution policy on the device: one phase = a strided loop over the block + a barrier
+    unsigned long long *prof; long long last;      // BSB_DF_PROFILE: cycles per phase, summed over the thread blocks (thread 0's clock)
+    __host__ __device__ __forceinline__ void tick(int k)
+    {
+#if defined(__CUDA_ARCH__)
+        if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(prof + k, (unsigned long long)(now - last)); last = now; }
+#endif
+    }
     template <class F> __host__ __device__ __forceinline__ void par(int n, F f)
     {
 #if defined(__CUDA_ARCH__)
         for (int i = threadIdx.x; i < n; i += blockDim.x) f(i);
+        __syncthreads();
+#endif
+    }
+    template <class F> __host__ __device__ __forceinline__ void par1(F f)     // one item per thread (blockDim.x == DF_CH)
+    {
+#if defined(__CUDA_ARCH__)
+        f((int)threadIdx.x);
+        __syncthreads();
+#endif
+    }
+    template <class F> __host__ __device__ __forceinline__ void wpar1(F f)    // ... with a warp barrier only
+    {
+#if defined(__CUDA_ARCH__)
+        f((int)threadIdx.x);
+        __syncwarp();
+#endif
+    }
+    __host__ __device__ __forceinline__ void sync()
+    {
+#if defined(__CUDA_ARCH__)
         __syncthreads();
 #endif
     }
@@ -832,20 +859,28 @@ struct XDev {   // bsb_deflate.h's execution policy on the device: one phase = a
         atomicAdd(p, v);
 #endif
     }
-    __host__ __device__ __forceinline__ void atomic_max(int32_t *p, int32_t v)
+    __host__ __device__ __forceinline__ void atomic_max16(uint32_t *w, uint32_t idx, uint32_t v)   // 16-bit entry idx of a word array
     {
 #if defined(__CUDA_ARCH__)
-        atomicMax(p, v);
+        uint32_t *p = w + (idx >> 1);
+        const int sh = (int)(idx & 1) << 4;
+        uint32_t old = *p;
+        while (v > (old >> sh & 0xffffu)) {
+            const uint32_t seen = atomicCAS(p, old, (old & ~(0xffffu << sh)) | v << sh);
+            if (seen == old) break;
+            old = seen;
+        }
 #endif
     }
 };
 
 // One thread block per BGZF block, persistent over the batch's blocks. tok: BGZF_MAX_IN + 8 words of scratch per thread block.
-__global__ void __launch_bounds__(DF_CH) k_bgzf_deflate(const uint8_t *raw, const uint32_t *cut, int nblk, uint8_t *slots, uint32_t *len, uint32_t *tok)
+__global__ void __launch_bounds__(DF_CH, 2) k_bgzf_deflate(const uint8_t *raw, const uint32_t *cut, int nblk, uint8_t *slots, uint32_t *len, uint32_t *tok, unsigned long long *prof)
 {
     extern __shared__ __align__(16) unsigned char df_smem[];       // sizeof(DeflateShared): the input block, the hash table, the code tables
     DeflateShared &S = *reinterpret_cast<DeflateShared *>(df_smem);
     XDev x;
+    x.prof = prof; x.last = clock64();
     uint32_t *my_tok = tok + (size_t)blockIdx.x * (BGZF_MAX_IN + 8);
     for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const int n = (int)(cut[blk + 1] - cut[blk]);
@@ -1687,7 +1722,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
         CK(cudaEventRecord(m.ev[11], st));
         if (out.want_bam) {
             // ---- BAM: the arbiter, the records and their BGZF blocks are made here; only compressed blocks cross PCIe ----
-            m.d_first.ensure(n + 1); m.d_rgrp.ensure(n + 1); m.d_bam_code.ensure(n + 1); m.d_bam_len.ensure(n + 2); m.d_bam_off.ensure(n + 2); m.d_bam_ctr.ensure(16);
+            m.d_first.ensure(n + 1); m.d_rgrp.ensure(n + 1); m.d_bam_code.ensure(n + 1); m.d_bam_len.ensure(n + 2); m.d_bam_off.ensure(n + 2); m.d_bam_ctr.ensure(32);
             CK(cudaMemcpyAsync(m.d_first.p, b.first.data(), (size_t)n, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(m.d_rgrp.p, b.read_group.data(), (size_t)n, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(m.d_bam_ctr.p, 0, 16 * sizeof(unsigned long long), st));
@@ -1735,7 +1770,20 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                 m.d_bgzf_slots.ensure((size_t)nblk * BGZF_SLOT); m.d_bam_tok.ensure((size_t)grid * (BGZF_MAX_IN + 8));
                 k_bam_cuts<<<cdiv(nblk + 1, 128), 128, 0, st>>>(m.d_bam_off.p, n, quantum, fixed, nblk, m.d_bam_cut.p);
                 CK(cudaMemsetAsync(m.d_bgzf_len.p + nblk, 0, 4, st));
-                k_bgzf_deflate<<<grid, DF_CH, sizeof(DeflateShared), st>>>(m.d_bam_raw.p, m.d_bam_cut.p, nblk, m.d_bgzf_slots.p, m.d_bgzf_len.p, m.d_bam_tok.p);
+                static const bool df_profile = getenv("BSB_DF_PROFILE") != nullptr;
+                if (df_profile) CK(cudaMemsetAsync(m.d_bam_ctr.p + 16, 0, 16 * sizeof(unsigned long long), st));
+                k_bgzf_deflate<<<grid, DF_CH, sizeof(DeflateShared), st>>>(m.d_bam_raw.p, m.d_bam_cut.p, nblk, m.d_bgzf_slots.p, m.d_bgzf_len.p, m.d_bam_tok.p,
+                                                                         df_profile ? m.d_bam_ctr.p + 16 : nullptr);
+                if (df_profile) {
+                    unsigned long long pc[16];
+                    CK(cudaMemcpyAsync(pc, m.d_bam_ctr.p + 16, sizeof pc, cudaMemcpyDeviceToHost, st));
+                    m.wait();
+                    unsigned long long tot = 0;
+                    for (int k = 0; k < 12; ++k) tot += pc[k];
+                    fprintf(stderr, "[D::deflate] %d blocks on %d thread blocks; cycles per phase (%%):", nblk, grid);
+                    for (int k = 0; k < 12; ++k) fprintf(stderr, " %d:%.1f", k, 100.0 * (double)pc[k] / (double)(tot ? tot : 1));
+                    fprintf(stderr, " | %.0f cycles per block\n", (double)tot / nblk);
+                }
                 cub::DeviceScan::ExclusiveSum(nullptr, sb, m.d_bgzf_len.p, m.d_bgzf_off.p, nblk + 1, st);
                 m.d_cub.ensure(sb + 16);
                 cub::DeviceScan::ExclusiveSum(m.d_cub.p, sb, m.d_bgzf_len.p, m.d_bgzf_off.p, nblk + 1, st);

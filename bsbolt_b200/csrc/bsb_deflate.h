@@ -22,7 +22,10 @@
 //      with x^n mod P multiplications.
 // A block that does not shrink is stored (BTYPE 00).
 //
-// The functions take an execution policy X: X::par(n, f) runs f(i) for i in [0, n) across the block and ends with a barrier;
+// The functions take an execution policy X: X::par(n, f) runs f(i) for i in [0, n) across the block and ends with a barrier
+// (X::par1(f): n = DF_CH, one item per thread; X::wpar1(f): the same with a WARP barrier, for phases in which a thread only
+// reads what its own warp's 32 threads wrote since the last block barrier; X::sync(): a block barrier; X::tick(k): a
+// measurement hook, cycles since the previous tick are charged to phase k);
 // X::atomic_* are the shared/global atomics. XDev (bsb_cuda.cu) maps them to threadIdx/__syncthreads/atomicOr; XHost
 // (tests/hostsim/bamsim.cpp) runs the same phases as plain loops, which is how this file is tested on the CPU against zlib's
 // inflate and crc32 -- a phase therefore never reads what the same phase writes, except through the atomics.
@@ -35,16 +38,18 @@ namespace bsb {
 
 constexpr int BGZF_MAX_IN = 0xff00;          // htslib BGZF_BLOCK_SIZE
 constexpr int BGZF_SLOT = 0x10000;           // room for one block in the worst case: 18 + 5 + 0xff00 + 8
-constexpr int DF_CH = 256;                   // positions per chunk = threads per block
+constexpr int DF_CH = 512;                   // positions per chunk = threads per block
 constexpr int DF_HASH_BITS = 13;
-constexpr int DF_MIN_MATCH = 4, DF_MAX_MATCH = 258, DF_MAX_DIST = 32768;
+constexpr int DF_MIN_MATCH = 4, DF_MAX_MATCH = 258, DF_MAX_DIST = 32768, DF_GOOD_RUN = 32;
+constexpr int DF_MAX_HASH_MATCH = 128;         // a match found through the hash table is compared this far (runs go to 258 through the eq bits): bounds the slowest thread
 constexpr int DF_NLL = 286, DF_ND = 30, DF_NCL = 19;
 
 struct DeflateShared {
     uint32_t in32[BGZF_MAX_IN / 4 + 4];      // the block's input: every later access (hashing, match compares, literals, CRC) is a shared-memory access
-    int32_t head[1 << DF_HASH_BITS];         // hash -> latest position of an earlier chunk (-1: none)
+    uint32_t head[(1 << DF_HASH_BITS) / 2];  // hash -> 1 + the latest position of an earlier chunk (0: none), two 16-bit entries per word
+    uint32_t eq[BGZF_MAX_IN / 32 + 12];       // bit p: in[p] == in[p - 1] -- a run's length is a count of one bits, not a byte compare
     uint16_t mlen[DF_CH], mdist[DF_CH], hash[DF_CH];
-    uint16_t jump[2][DF_CH];
+    uint16_t jl[6][DF_CH];                    // jl[k][t]: where 2^k hops from t lead, hops that stay inside t's 32-position segment
     uint32_t markw[DF_CH / 32];
     uint32_t hist[320];                      // [0, 286): literal/length, [288, 318): distance
     uint32_t sorted[320];                    // (freq << 9 | symbol) ascending, per tree at the same bases
@@ -72,6 +77,18 @@ BSB_HD uint32_t df_load32(const uint8_t *p)                       // four bytes 
     return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
 #endif
 }
+// the same out of an array of little-endian words (the staged input): byte offset `at`
+BSB_HD uint32_t df_word(const uint32_t *w, int at)
+{
+    const uint32_t lo = w[at >> 2], hi = w[(at >> 2) + 1];
+    const uint32_t sh = (uint32_t)(at & 3) << 3;
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? lo >> sh | hi << (32 - sh) : lo;
+#endif
+}
+BSB_HD uint32_t df_byte(const uint32_t *w, int at) { return w[at >> 2] >> ((at & 3) << 3) & 0xffu; }
 BSB_HD int df_ctz(uint32_t x)
 {
 #if defined(__CUDA_ARCH__)
@@ -97,16 +114,45 @@ BSB_HD int df_popc(uint32_t x)
 #endif
 }
 
-// bytes in[a ..] and in[b ..] agree for how long (at most lim)
-BSB_HD int df_match_len(const uint8_t *in, int a, int b, int lim)
+BSB_HD uint32_t df_funnel(uint32_t lo, uint32_t hi, uint32_t sh)     // bits [sh, sh + 32) of hi:lo, sh in {0, 8, 16, 24}
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? lo >> sh | hi << (32 - sh) : lo;
+#endif
+}
+// bytes at offsets a.. and b.. of the staged input agree for how long (at most lim). Eight bytes a step, all six loads of a
+// step issued together: the loop is a chain of shared-memory latencies and the slowest thread of the block sets the pace.
+BSB_HD int df_match_len(const uint32_t *w, int a, int b, int lim)
 {
     int k = 0;
+    const uint32_t sa = (uint32_t)(a & 3) << 3, sb = (uint32_t)(b & 3) << 3;
+    for (; k + 8 <= lim; k += 8) {
+        const int ia = (a + k) >> 2, ib = (b + k) >> 2;
+        const uint32_t a0 = w[ia], a1 = w[ia + 1], a2 = w[ia + 2], b0 = w[ib], b1 = w[ib + 1], b2 = w[ib + 2];
+        const uint32_t x0 = df_funnel(a0, a1, sa) ^ df_funnel(b0, b1, sb), x1 = df_funnel(a1, a2, sa) ^ df_funnel(b1, b2, sb);
+        if (x0) return k + (df_ctz(x0) >> 3);
+        if (x1) return k + 4 + (df_ctz(x1) >> 3);
+    }
     for (; k + 4 <= lim; k += 4) {
-        const uint32_t x = df_load32(in + a + k) ^ df_load32(in + b + k);
+        const uint32_t x = df_word(w, a + k) ^ df_word(w, b + k);
         if (x) return k + (df_ctz(x) >> 3);
     }
-    while (k < lim && in[a + k] == in[b + k]) ++k;
+    while (k < lim && df_byte(w, a + k) == df_byte(w, b + k)) ++k;
     return k;
+}
+// the distance-1 match at i: how many one bits follow from bit i of eq[] (at most lim; eq[] is zero behind the input)
+BSB_HD int df_run_len(const uint32_t *eq, int i, int lim)
+{
+    int w = i >> 5, got = 0, avail = 32 - (i & 31);
+    uint32_t z = ~eq[w] >> (i & 31);            // bit k set: eq bit i + k is zero; only the low `avail` bits are this word's
+    for (;;) {
+        if (z) { const int f = df_ctz(z); return got + f < lim ? got + f : lim; }
+        got += avail;
+        if (got >= lim) return lim;
+        z = ~eq[++w]; avail = 32;
+    }
 }
 
 // length 3..258 -> literal/length symbol, number and value of the extra bits (RFC 1951 3.2.5)
@@ -128,7 +174,14 @@ BSB_HD void df_dist_code(int d, int &sym, int &nx, int &xv)
     nx = hb - 1; xv = m & ((1 << nx) - 1);
 }
 
-BSB_HD uint32_t df_rev(uint32_t c, int n) { uint32_t r = 0; for (int k = 0; k < n; ++k) { r = r << 1 | (c & 1); c >>= 1; } return r; }
+BSB_HD uint32_t df_rev(uint32_t c, int n)
+{
+#if defined(__CUDA_ARCH__)
+    return n ? __brev(c) >> (32 - n) : 0u;
+#else
+    uint32_t r = 0; for (int k = 0; k < n; ++k) { r = r << 1 | (c & 1); c >>= 1; } return r;
+#endif
+}
 
 // CRC-32 arithmetic over GF(2), reflected polynomial 0xedb88320: a(x) * b(x) mod P(x)
 BSB_HD uint32_t df_mulmod(uint32_t a, uint32_t b)
@@ -224,11 +277,25 @@ template <class X>
 BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uint8_t *out, uint32_t *tok)
 {
     uint32_t *out32 = reinterpret_cast<uint32_t *>(out + 16);   // the deflate stream starts at bit 16 of this word array
-    const uint8_t *gin = in;
-    in = reinterpret_cast<const uint8_t *>(S.in32);
+    const uint32_t *w32 = S.in32;
     // ---- 0. input and tables ----
-    x.par(BGZF_MAX_IN / 4 + 4, [&](int w) { S.in32[w] = 4 * w < n ? df_load32(gin + 4 * w) : 0u; });
-    x.par(1 << DF_HASH_BITS, [&](int i) { S.head[i] = -1; });
+    x.par(BGZF_MAX_IN / 4 + 4, [&](int w) { S.in32[w] = 4 * w < n ? df_load32(in + 4 * w) : 0u; });
+    x.par(BGZF_MAX_IN / 32 + 12, [&](int w) {                    // eq bits: 32 positions per thread and step
+        uint32_t bits = 0;
+        const int p0 = 32 * w;
+        if (p0 < n) {
+            for (int g = 0; g < 8; ++g) {
+                const int q = p0 + 4 * g;
+                const uint32_t a = w32[q >> 2];
+                const uint32_t prev = q ? df_byte(w32, q - 1) : (~a & 0xffu);   // (nothing in front of the first byte)
+                const uint32_t d = a ^ (a << 8 | prev);              // byte k is zero where in[q + k] == in[q + k - 1]
+                bits |= ((d & 0xffu ? 0u : 1u) | (d & 0xff00u ? 0u : 2u) | (d & 0xff0000u ? 0u : 4u) | (d & 0xff000000u ? 0u : 8u)) << (4 * g);
+            }
+            if (n - p0 < 32) bits &= (1u << (n - p0)) - 1;
+        }
+        S.eq[w] = bits;
+    });
+    x.par((1 << DF_HASH_BITS) / 2, [&](int i) { S.head[i] = 0; });
     x.par(320, [&](int i) {
         S.hist[i] = 0;
         if (i < 256) { uint32_t c = (uint32_t)i; for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0xedb88320u : c >> 1; S.crc_tab[i] = c; }
@@ -239,46 +306,76 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
             S.crc = 0; S.stored = 0;
         }
     });
+    x.tick(0);
     // ---- 1 + 2. matches and the greedy parse, chunk by chunk ----
+    // Per chunk: (A) every position's best match and its jump; (B) five doubling rounds INSIDE each 32-position segment --
+    // a segment belongs to one warp, so these rounds need a warp barrier only -- leave in jl[5][t] the position at which
+    // the chain starting at t leaves t's segment; (C) the entry of each segment follows from the chunk's entry by eight
+    // table look-ups; (D) five more warp-local rounds mark the chain inside each segment; (E) marked positions become tokens.
     int n_tok = 0, carry = 0;                  // (the same in every thread: computed from shared memory behind a barrier)
     for (int base = 0; base < n; base += DF_CH) {
         const int L = n - base < DF_CH ? n - base : DF_CH;
-        const int s0 = carry - base;           // the first position of this chunk that starts a token
-        x.par(DF_CH, [&](int t) {
+        x.par1([&](int t) {                                                                         // (A)
             const int i = base + t;
             int best = 0, dist = 0;
-            S.hash[t] = 0xffff;
+            uint32_t hh = 0xffff;
             if (t < L) {
                 const int lim = n - i < DF_MAX_MATCH ? n - i : DF_MAX_MATCH;
                 if (lim >= DF_MIN_MATCH) {
-                    const uint32_t h = (df_load32(in + i) * 2654435761u) >> (32 - DF_HASH_BITS);
-                    S.hash[t] = (uint16_t)h;
-                    const int c = S.head[h];
-                    if (c >= 0 && i - c <= DF_MAX_DIST) { const int l = df_match_len(in, c, i, lim); if (l >= DF_MIN_MATCH) { best = l; dist = i - c; } }
-                    if (i > 0) { const int l = df_match_len(in, i - 1, i, lim); if (l >= DF_MIN_MATCH && l > best) { best = l; dist = 1; } }
+                    const uint32_t h = (df_word(w32, i) * 2654435761u) >> (32 - DF_HASH_BITS);
+                    hh = h;
+                    if (i > 0) { const int l = df_run_len(S.eq, i, lim); if (l >= DF_MIN_MATCH) { best = l; dist = 1; } }
+                    const int c = (int)(S.head[h >> 1] >> ((h & 1) << 4) & 0xffffu) - 1;
+                    if (best < DF_GOOD_RUN && best < lim && c >= 0 && i - c <= DF_MAX_DIST) {   /* (a long run is taken as it is) */ const int l = df_match_len(w32, c, i, lim < DF_MAX_HASH_MATCH ? lim : DF_MAX_HASH_MATCH); if (l >= DF_MIN_MATCH && l > best) { best = l; dist = i - c; } }
                 }
             }
+            S.hash[t] = (uint16_t)hh;
             S.mlen[t] = (uint16_t)best; S.mdist[t] = (uint16_t)dist;
-            S.jump[0][t] = (uint16_t)(t < L ? t + (best ? best : 1) : t);
-            if (t < DF_CH / 32) S.markw[t] = (s0 < L && (s0 >> 5) == t) ? 1u << (s0 & 31) : 0u;
+            S.jl[0][t] = (uint16_t)(t + (best ? best : 1));
         });
-        for (int k = 0; k < 8; ++k) {
-            const uint16_t *J = S.jump[k & 1];
-            uint16_t *Jn = S.jump[(k & 1) ^ 1];
-            x.par(DF_CH, [&](int t) {
-                if (k == 0 && S.hash[t] != 0xffff) x.atomic_max(&S.head[S.hash[t]], base + t);   // this chunk enters the table
-                const int u = J[t];
-                if (((S.markw[t >> 5] >> (t & 31)) & 1) && u < L) x.atomic_or(&S.markw[u >> 5], 1u << (u & 31));
-                Jn[t] = (uint16_t)(u < L ? J[u] : u);
+        x.tick(1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 5; ++k)
+            x.wpar1([&](int t) {                                                                    // (B)
+                // this chunk enters the table; where the next position has the same hash (inside a run) it is the one that counts
+                if (k == 0 && S.hash[t] != 0xffff && (t == DF_CH - 1 || S.hash[t + 1] != S.hash[t])) x.atomic_max16(S.head, S.hash[t], (uint32_t)(base + t + 1));
+                const int end = (t | 31) + 1 < L ? (t | 31) + 1 : L;     // the end of t's segment (or of the input)
+                const int u = S.jl[k][t];
+                S.jl[k + 1][t] = u < end ? S.jl[k][u] : (uint16_t)u;
             });
+        x.sync();
+        x.tick(2);
+        int entry[DF_CH / 32 + 1];                                                                  // (C)
+        entry[0] = carry - base;
+        for (int g = 0; g < DF_CH / 32; ++g) {
+            const int end = 32 * (g + 1) < L ? 32 * (g + 1) : L, e = entry[g];
+            entry[g + 1] = e >= 32 * g && e < end ? S.jl[5][e] : e;
         }
+        if (entry[0] < L) carry = base + entry[DF_CH / 32];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 6; ++k)
+            x.wpar1([&](int t) {                                                                    // (D)
+                const int g = t >> 5, end = 32 * (g + 1) < L ? 32 * (g + 1) : L;
+                if (k == 0) {
+                    if ((t & 31) == 0) { const int e = entry[g]; S.markw[g] = e >= 32 * g && e < end ? 1u << (e & 31) : 0u; }
+                    return;
+                }
+                const int u = S.jl[k - 1][t];
+                if (((S.markw[g] >> (t & 31)) & 1) && u < end) x.atomic_or(&S.markw[g], 1u << (u & 31));
+            });
+        x.sync();
+        x.tick(3);
         uint32_t pre[DF_CH / 32 + 1];
         pre[0] = 0;
         for (int w = 0; w < DF_CH / 32; ++w) pre[w + 1] = pre[w] + (uint32_t)df_popc(S.markw[w]);
-        if (s0 < L) carry = base + S.jump[0][s0];                // after 8 doublings jump[0] holds 256 hops: the way out of the chunk
-        x.par(DF_CH, [&](int t) {
-            if (!((S.markw[t >> 5] >> (t & 31)) & 1)) return;
-            const uint32_t at = (uint32_t)n_tok + pre[t >> 5] + (uint32_t)df_popc(S.markw[t >> 5] & ((1u << (t & 31)) - 1));
+        x.par1([&](int t) {                                                                         // (E)
+            const uint32_t mw = S.markw[t >> 5];
+            if (!((mw >> (t & 31)) & 1)) return;
+            const uint32_t at = (uint32_t)n_tok + pre[t >> 5] + (uint32_t)df_popc(mw & ((1u << (t & 31)) - 1));
             if (S.mlen[t]) {
                 tok[at] = 1u << 31 | (uint32_t)(S.mlen[t] - 3) << 16 | (uint32_t)(S.mdist[t] - 1);
                 int sym, nx, xv;
@@ -287,12 +384,13 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
                 df_dist_code(S.mdist[t], sym, nx, xv);
                 x.atomic_add(&S.hist[288 + sym], 1u);
             } else {
-                const uint32_t b = in[base + t];
+                const uint32_t b = df_byte(w32, base + t);
                 tok[at] = b;
                 x.atomic_add(&S.hist[b], 1u);
             }
         });
         n_tok += (int)pre[DF_CH / 32];
+        x.tick(4);
     }
     // ---- 3. codes ----
     x.par(1, [&](int) {
@@ -314,11 +412,13 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         for (int u = lo; u < hi; ++u) r += S.hist[u] && (S.hist[u] << 9 | (uint32_t)(u - lo)) < key;
         S.sorted[lo + r] = key;
     });
+    x.tick(5);
     x.par(64, [&](int t) {
         if (t & 31) return;
         const int w = t >> 5, o = w ? 288 : 0;
         df_tree(S.sorted + o, S.n_used[w], 15, S.len + o, S.code + o, w ? DF_ND : DF_NLL, S.wi + o, S.par_leaf + o, S.par_int + o, S.depth_int + o);
     });
+    x.tick(6);
     x.par(1, [&](int) {
         // code lengths of both trees, run-length coded with the symbols 16 (repeat previous 3-6), 17 (zeros 3-10), 18 (zeros 11-138)
         int hlit = DF_NLL, hdist = DF_ND;
@@ -374,6 +474,7 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         }
         S.hdr_bits = B.n;
     });
+    x.tick(7);
     // ---- 4. bits ----
     const int per = (n_tok + DF_CH - 1) / DF_CH;
     x.par(DF_CH, [&](int t) {
@@ -389,6 +490,7 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         S.total_bits = c + S.len[256] - 16;
         S.stored = (S.total_bits + 7) / 8 >= (uint32_t)n + 5;
     });
+    x.tick(8);
     uint32_t clen;
     if (!S.stored) {
         clen = (S.total_bits + 7) / 8;
@@ -424,23 +526,25 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         });
     } else {
         clen = (uint32_t)n + 5;
-        x.par(n, [&](int i) { out[18 + 5 + i] = in[i]; });
+        x.par(n, [&](int i) { out[18 + 5 + i] = (uint8_t)df_byte(w32, i); });
         x.par(1, [&](int) {
             uint8_t *d = out + 18;
             d[0] = 1; d[1] = (uint8_t)n; d[2] = (uint8_t)(n >> 8); d[3] = (uint8_t)~d[1]; d[4] = (uint8_t)~d[2];
         });
     }
+    x.tick(9);
     // CRC-32 of the input: every thread its slice, then crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
     const int slice = (n + DF_CH - 1) / DF_CH;
     x.par(DF_CH, [&](int t) {
         const int lo = t * slice, hi = lo + slice < n ? lo + slice : n;
         if (lo >= hi) return;
         uint32_t c = 0xffffffffu;
-        for (int k = lo; k < hi; ++k) c = S.crc_tab[(c ^ in[k]) & 0xff] ^ (c >> 8);
+        for (int k = lo; k < hi; ++k) c = S.crc_tab[(c ^ df_byte(w32, k)) & 0xff] ^ (c >> 8);
         c ^= 0xffffffffu;
         if (hi < n) c = df_mulmod(df_x8n(S.x2n, (uint32_t)(n - hi)), c);
         x.atomic_xor(&S.crc, c);
     });
+    x.tick(10);
     const uint32_t total = 18 + clen + 8;
     x.par(1, [&](int) {
         const uint8_t H[16] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0};
@@ -451,6 +555,7 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         tl[0] = (uint8_t)c; tl[1] = (uint8_t)(c >> 8); tl[2] = (uint8_t)(c >> 16); tl[3] = (uint8_t)(c >> 24);
         tl[4] = (uint8_t)l; tl[5] = (uint8_t)(l >> 8); tl[6] = (uint8_t)(l >> 16); tl[7] = (uint8_t)(l >> 24);
     });
+    x.tick(11);
     return total;
 }
 

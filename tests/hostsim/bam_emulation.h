@@ -35,10 +35,18 @@ struct XHost {
         for (int i = n - 1; i > 0; --i) { seed = seed * 1103515245u + 12345u; std::swap(perm[i], perm[(seed >> 8) % (unsigned)(i + 1)]); }
         for (int i = 0; i < n; ++i) f(perm[i]);
     }
+    template <class F> void par1(F f) { par(DF_CH, f); }
+    template <class F> void wpar1(F f) { par(DF_CH, f); }
+    void sync() {}
+    void tick(int) {}
     void atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
     void atomic_xor(uint32_t *p, uint32_t v) { *p ^= v; }
     void atomic_add(uint32_t *p, uint32_t v) { *p += v; }
-    void atomic_max(int32_t *p, int32_t v) { if (v > *p) *p = v; }
+    void atomic_max16(uint32_t *w, uint32_t idx, uint32_t v)   // 16-bit entry idx of a word array
+    {
+        const int sh = (int)(idx & 1) << 4;
+        if (v > (w[idx >> 1] >> sh & 0xffffu)) w[idx >> 1] = (w[idx >> 1] & ~(0xffffu << sh)) | v << sh;
+    }
 };
 
 // raw bytes -> BGZF blocks. cuts: block k = raw[cuts[k], cuts[k + 1]); empty blocks are skipped (k_bgzf_deflate does the same)
