@@ -240,7 +240,7 @@ class Ranks:
             self.dist.destroy_process_group()
 
 
-N_FENCES = 8   # fences rank 0 passes in the B200 arm (b200_arm: 2 x 3 timed regions + 2); the waiting ranks pass the same number
+N_FENCES = 10  # fences rank 0 passes in the B200 arm (b200_arm: 2 x 4 timed regions + 2); the waiting ranks pass the same number
 
 
 def main():
@@ -452,32 +452,62 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
         scratch += [m1, m2]
         multi_identity = {'batches': outs[1][3], 'sam_bytes': outs[1][1], 'records': outs[1][2],
                           'identical_to_one_gpu_output': outs[0][:3] == outs[1][:3]}
-    # the reference's default output (`-O prefix`: bwa mem | stream_bam): FASTQ files -> BAM file, on the first 4 batches' reads
-    bam_info = None
-    if n_dev == 1:
+    # the reference's default output (`-O prefix`: bwa mem | stream_bam): FASTQ files -> BAM file.
+    # Default level (what `bsbolt Align -O` uses): arbiter, BAM records and BGZF deflate on the device (bsb_bam.h, bsb_deflate.h), the
+    # host appends the blocks to the file -- timed on the SAME input as `e2e`, fenced the same way. An explicit zlib level keeps the
+    # round-1 path (SAM text to the host, encoded and deflated by the host cores): timed on the first 4 batches, where the two
+    # files are also inflated (zlib, here) and their BAM streams compared.
+    bam_path = os.path.join(work, 'bench_out.bam')
+
+    def mem_bam(fq1, fq2, level):
+        t = time.time()
+        if n_dev > 1:
+            rc, st_b = _native.mem_main_multi_bam(argv_common + [db, fq1, fq2], bam_path, idx, threads=0, level=level, log_fd=null)
+        else:
+            rc, st_b = _native.mem_main_bam(argv_common + [db, fq1, fq2], bam_path, index=idx, threads=0, level=level, log_fd=null)
+        if rc:
+            raise RuntimeError(_native.last_error())
+        return time.time() - t, st_b
+
+    def bam_timed():
+        try:
+            return mem_bam(f1, f2, -1)
+        except Exception as e:  # noqa  (the SAM line above stands on its own; a failure here is reported, not fatal)
+            return None, str(e)
+    try:
+        mem_bam(w1 if W else f1, w2 if W else f2, -1)                                     # (sizes the BAM stage's buffers)
+    except Exception:  # noqa
+        pass
+    dt, st_b = fenced(bam_timed)
+    if dt is None:
+        bam_info = {'error': st_b}
+    else:
+        nbt = max(1, st_b['n_batches'])
+        bam_info = {'api': 'bsb_mem_main_bam%s (one FASTQ pair on the host -> one BGZF/BAM file), default level: compressed on the device' % ('_multi' if n_dev > 1 else ''),
+                    'unit': 'reads/s', 'value': n_reads_timed / dt, 'reads': n_reads_timed, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path),
+                    'd2h_bytes_per_step': st_b['d2h_bytes'] / nbt * n_dev, 'bam_bytes_per_step': st_b['bam_raw_bytes'] / nbt * n_dev,
+                    'bgzf_bytes_per_step': st_b['bam_bgzf_bytes'] / nbt * n_dev,
+                    'device_ms_per_batch': {'sam_text': st_b['ms_text'] / nbt, 'arbiter_records_deflate': st_b['ms_bam'] / nbt}}
+    if n_dev == 1 and dt is not None:
+        import gzip
         nb = min(4, K) * a.batch_pairs
-        b1 = os.path.join(work, 'bam_1.fq'); b2 = os.path.join(work, 'bam_2.fq'); bam_path = os.path.join(work, 'bench_out.bam')
+        b1 = os.path.join(work, 'bam_1.fq'); b2 = os.path.join(work, 'bam_2.fq')
         head_records(f1, b1, nb); head_records(f2, b2, nb)
-        # level -1 (the default, what `bsbolt Align -O` uses): records, arbiter and BGZF deflate on the device, the host appends
-        # the blocks to the file; an explicit zlib level: SAM text to the host, encoded and deflated by the host cores
-        for name, level in (('device_deflate', -1), ('device_deflate_again', -1), ('host_zlib_level_1', 1), ('host_zlib_level_6', 6)):
-            t = time.time()
-            rc, st_b = _native.mem_main_bam(argv_common + [db, b1, b2], bam_path, index=idx, threads=0, level=level, log_fd=null)
-            dt = time.time() - t
-            if rc:
-                raise RuntimeError(_native.last_error())
-            bam_info = bam_info or {'api': 'bsb_mem_main_bam (FASTQ files on host -> BGZF/BAM file)', 'reads': 2 * nb, 'unit': 'reads/s'}
-            bam_info[name] = {'value': 2 * nb / dt, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path), 'd2h_bytes': st_b['d2h_bytes']}
-            if name in ('device_deflate', 'host_zlib_level_1'):   # both files inflate (zlib, here) to the same BAM stream
-                import gzip
+        sub = {}
+        for name, level in (('device_deflate', -1), ('host_zlib_level_1', 1), ('host_zlib_level_6', 6)):
+            dt, st_b = mem_bam(b1, b2, level)
+            sub[name] = {'value': 2 * nb / dt, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path)}
+            if level < 6:
                 h = hashlib.sha256()
                 with gzip.open(bam_path, 'rb') as f:
                     for chunk in iter(lambda: f.read(1 << 24), b''):
                         h.update(chunk)
-                bam_info[name]['raw_sha256'] = h.hexdigest()
-        bam_info['value'] = bam_info['device_deflate_again']['value']
-        bam_info['device_stream_identical_to_host_stream'] = bam_info['device_deflate']['raw_sha256'] == bam_info['host_zlib_level_1']['raw_sha256']
-        scratch += [b1, b2, bam_path]
+                sub[name]['raw_sha256'] = h.hexdigest()
+        sub['reads'] = 2 * nb
+        sub['device_stream_identical_to_host_stream'] = sub['device_deflate']['raw_sha256'] == sub['host_zlib_level_1']['raw_sha256']
+        bam_info['first_4_batches'] = sub
+        scratch += [b1, b2]
+    scratch.append(bam_path)
     ms_resident, ms_total_wall = st_res['sec_resident'] * 1000, wall * 1000
     ms_one = st_one['sec_resident'] * 1000
     n_batches = max(1, st['n_batches'])

@@ -4,6 +4,8 @@
 // (bsbolt/Align/AlignReads.py:52-60, bsbolt/External/HTSLIB/stream_bam.c): what htslib's sam_parse1 (sam.c:1924-2160)
 // + bam_write1 (sam.c:661-735) + bam_hdr_write make of a SAM stream, i.e. the *uncompressed* BAM byte stream is
 // identical to the reference's; the BGZF framing differs (blocks are cut per worker and never split a record).
+// At the default level the pipeline does not come through records() at all: the aligner hands over BGZF blocks it compressed on
+// the device (BatchResult::bam; bsb_bam.h, bsb_deflate.h) and blocks() appends them.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>

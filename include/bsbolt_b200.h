@@ -80,8 +80,12 @@ int bsb_mem_main(bsb_index_t *idx, int device, int argc, char **argv, int out_fd
 /* replaces the reference's whole output pipeline `bwa mem ... | stream_bam -@ <threads> -o <bam_path>`
  * (bsbolt/Align/AlignReads.py:52-60; bsbolt/External/HTSLIB/stream_bam.c): as bsb_mem_main, but the records are
  * encoded as BAM (what htslib's sam_parse1 + bam_write1 make of the same SAM lines: the uncompressed BAM stream is
- * byte-identical to the reference's) and BGZF-compressed by `threads` host threads (<= 0: this process's share of
- * the cores) at zlib `level` (0..9, -1 = zlib default = what stream_bam uses). */
+ * byte-identical to the reference's) and BGZF-compressed:
+ *   level -1 (default)  on the GPU: the read-group arbiter (samSorter, bs_sorter.cpp:84-170), the records and one dynamic-Huffman
+ *                       deflate block per <= 0xff00 bytes (RFC 1951; BGZF framing of htslib's bgzf.c) are made by kernels and only
+ *                       finished blocks cross PCIe; the host appends them to the file.
+ *   level 0..9          by `threads` host threads (<= 0: this process's share of the cores) with zlib at that level; also the path
+ *                       of runs whose records the device formatter does not make (-C comments, ALT contigs, -p, @SQ lines in -H). */
 int bsb_mem_main_bam(bsb_index_t *idx, int device, int argc, char **argv, const char *bam_path, int threads, int level,
                      int log_fd, bsb_run_stats_t *stats);
 /* The same two entry points over several GPUs of one box: idx[0] from bsb_index_load, idx[1..] its bsb_index_clone on the
