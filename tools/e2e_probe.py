@@ -35,7 +35,7 @@ def main():
     idx = _native.MultiIndex(db, list(range(a.gpus))) if a.gpus > 1 else _native.Index(db, 0)
     mem = (lambda av: _native.mem_main_multi(av, idx, out_fd=null, log_fd=null)) if a.gpus > 1 else (lambda av: _native.mem_main(av, index=idx, out_fd=null, log_fd=null))
     if a.bam:
-        bam_path = os.path.join(work, 'probe.bam')
+        bam_path = os.environ.get('BSB_PROBE_BAM_PATH', os.path.join(work, 'probe.bam'))
         mem = (lambda av: _native.mem_main_multi_bam(av, bam_path, idx, log_fd=null)) if a.gpus > 1 else (lambda av: _native.mem_main_bam(av, bam_path, index=idx, log_fd=null))
     if a.warm_batches:
         w1 = os.path.join(work, 'stw_1.fq'); w2 = os.path.join(work, 'stw_2.fq')
