@@ -1761,7 +1761,7 @@ void CudaAligner::align(const Opt &opt_in, const ReadBatch &b, int64_t n_process
                         CK(cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateShared)));
                         int nb = 1;
                         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_bgzf_deflate, DF_CH, sizeof(DeflateShared)));
-                        I.df_per_sm = std::max(1, nb);
+                        I.df_per_sm = std::max(1, std::min(nb, env_int("BSB_DF_PER_SM", nb)));   // fewer thread blocks per SM leave room for the other batches' kernels
                     }
                     df_per_sm = I.df_per_sm;
                 }

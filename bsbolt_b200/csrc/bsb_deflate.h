@@ -60,6 +60,11 @@ struct DeflateShared {
     uint16_t rle[320];                       // run-length coded code lengths: symbol | extra << 8
     uint32_t hdr[80];                        // the block header's bits
     uint32_t part[DF_CH + 1];
+    // what one thread's serial passes index dynamically lives here, not in local memory (with ~200 KB of the SM's L1 carved out
+    // as shared memory, a local-memory access is an L2 round trip)
+    int32_t entry[DF_CH / 32 + 1]; uint32_t pre[DF_CH / 32 + 1];
+    uint32_t tscr[3][36];                     // df_tree: code counts per length, next code per length (literal/length, distance, code-length tree)
+    uint32_t clf[DF_NCL], cl_sorted[DF_NCL]; uint8_t cl_len[DF_NCL + 1], order[DF_NCL + 1]; uint16_t cl_code[DF_NCL + 1];
     uint32_t crc_tab[256], x2n[32];
     uint32_t crc;
     int n_used[2], n_rle, hdr_bits, stored;
@@ -205,10 +210,10 @@ BSB_HD uint32_t df_x8n(const uint32_t *x2n, uint32_t n)
 // ---------------------------------------------------------------------------------------------------------------------
 // Code lengths of one tree. sorted[0, m): (freq << 9 | symbol) ascending; m >= 1. Serial (one thread per tree).
 BSB_HD void df_tree(const uint32_t *sorted, int m, int limit, uint8_t *len, uint16_t *code, int n_sym,
-                    uint32_t *wi, uint16_t *par_leaf, uint16_t *par_int, uint16_t *depth_int)
+                    uint32_t *wi, uint16_t *par_leaf, uint16_t *par_int, uint16_t *depth_int, uint32_t *scr)
 {
     for (int s = 0; s < n_sym; ++s) { len[s] = 0; code[s] = 0; }
-    int bl[16];
+    uint32_t *bl = scr, *next = scr + 16;      // [16] codes per length, [17] next code per length
     for (int d = 0; d < 16; ++d) bl[d] = 0;
     if (m == 1) { len[sorted[0] & 511] = 1; bl[1] = 1; }
     else {
@@ -229,7 +234,7 @@ BSB_HD void df_tree(const uint32_t *sorted, int m, int limit, uint8_t *len, uint
         // depth limit: the clamped lengths over-subscribe the code space; every step gives one unit of it back
         // (one code leaves the last level, one code one level up takes a sibling with it)
         uint32_t total = 0;
-        for (int d = 1; d <= limit; ++d) total += (uint32_t)bl[d] << (limit - d);
+        for (int d = 1; d <= limit; ++d) total += bl[d] << (limit - d);
         while (total > (1u << limit)) {
             --bl[limit];
             for (int d = limit - 1; d > 0; --d)
@@ -238,25 +243,23 @@ BSB_HD void df_tree(const uint32_t *sorted, int m, int limit, uint8_t *len, uint
         }
         int i = 0;                             // the rarest symbols take the longest codes
         for (int d = limit; d >= 1; --d)
-            for (int c = 0; c < bl[d]; ++c) len[sorted[i++] & 511] = (uint8_t)d;
+            for (uint32_t c2 = 0; c2 < bl[d]; ++c2) len[sorted[i++] & 511] = (uint8_t)d;
     }
-    uint32_t next[17], c = 0;                  // canonical codes (RFC 1951 3.2.2)
+    uint32_t c = 0;                            // canonical codes (RFC 1951 3.2.2)
     next[0] = 0;
-    for (int d = 1; d <= 15; ++d) { c = (c + (d <= limit + 0 ? (uint32_t)bl[d - 1] : 0u)) << 1; next[d] = c; }
+    for (int d = 1; d <= 15; ++d) { c = (c + bl[d - 1]) << 1; next[d] = c; }
     for (int s = 0; s < n_sym; ++s)
         if (len[s]) code[s] = (uint16_t)df_rev(next[len[s]]++, len[s]);
 }
 
-struct DfBits {                                // the header's bit writer (one thread)
-    uint32_t *w; int n;
+struct DfBits {                                // the header's bit writer (one thread): bits collect in a register, whole words leave
+    uint32_t *w; int n; uint64_t acc; int fill;
     BSB_HD void put(uint32_t v, int nb)
     {
-        if (!nb) return;
-        const int at = n >> 5, sh = n & 31;
-        w[at] |= v << sh;
-        if (sh + nb > 32) w[at + 1] |= v >> (32 - sh);
-        n += nb;
+        acc |= (uint64_t)v << fill; fill += nb; n += nb;
+        if (fill >= 32) { *w++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
     }
+    BSB_HD void finish() { if (fill) *w++ = (uint32_t)acc; }
 };
 
 // token: literal byte, or 1 << 31 | (length - 3) << 16 | (distance - 1)
@@ -305,6 +308,10 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
             for (int k = 1; k < 32; ++k) S.x2n[k] = p = df_mulmod(p, p);
             S.crc = 0; S.stored = 0;
         }
+        if (i == 257) {
+            const uint8_t order[DF_NCL] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            for (int k = 0; k < DF_NCL; ++k) S.order[k] = order[k];   // (constant indices: no local copy)
+        }
     });
     x.tick(0);
     // ---- 1 + 2. matches and the greedy parse, chunk by chunk ----
@@ -347,13 +354,16 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
             });
         x.sync();
         x.tick(2);
-        int entry[DF_CH / 32 + 1];                                                                  // (C)
-        entry[0] = carry - base;
-        for (int g = 0; g < DF_CH / 32; ++g) {
-            const int end = 32 * (g + 1) < L ? 32 * (g + 1) : L, e = entry[g];
-            entry[g + 1] = e >= 32 * g && e < end ? S.jl[5][e] : e;
+        {                                                                                           // (C) every thread the same values
+            int e = carry - base;
+            const int e0 = e;
+            for (int g = 0; g < DF_CH / 32; ++g) {
+                const int end = 32 * (g + 1) < L ? 32 * (g + 1) : L;
+                S.entry[g] = e;
+                if (e >= 32 * g && e < end) e = S.jl[5][e];
+            }
+            if (e0 < L) carry = base + e;
         }
-        if (entry[0] < L) carry = base + entry[DF_CH / 32];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -361,7 +371,7 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
             x.wpar1([&](int t) {                                                                    // (D)
                 const int g = t >> 5, end = 32 * (g + 1) < L ? 32 * (g + 1) : L;
                 if (k == 0) {
-                    if ((t & 31) == 0) { const int e = entry[g]; S.markw[g] = e >= 32 * g && e < end ? 1u << (e & 31) : 0u; }
+                    if ((t & 31) == 0) { const int e = S.entry[g]; S.markw[g] = e >= 32 * g && e < end ? 1u << (e & 31) : 0u; }
                     return;
                 }
                 const int u = S.jl[k - 1][t];
@@ -369,13 +379,12 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
             });
         x.sync();
         x.tick(3);
-        uint32_t pre[DF_CH / 32 + 1];
-        pre[0] = 0;
-        for (int w = 0; w < DF_CH / 32; ++w) pre[w + 1] = pre[w] + (uint32_t)df_popc(S.markw[w]);
+        uint32_t n_chunk = 0;
+        for (int w = 0; w < DF_CH / 32; ++w) { S.pre[w] = n_chunk; n_chunk += (uint32_t)df_popc(S.markw[w]); }
         x.par1([&](int t) {                                                                         // (E)
             const uint32_t mw = S.markw[t >> 5];
             if (!((mw >> (t & 31)) & 1)) return;
-            const uint32_t at = (uint32_t)n_tok + pre[t >> 5] + (uint32_t)df_popc(mw & ((1u << (t & 31)) - 1));
+            const uint32_t at = (uint32_t)n_tok + S.pre[t >> 5] + (uint32_t)df_popc(mw & ((1u << (t & 31)) - 1));
             if (S.mlen[t]) {
                 tok[at] = 1u << 31 | (uint32_t)(S.mlen[t] - 3) << 16 | (uint32_t)(S.mdist[t] - 1);
                 int sym, nx, xv;
@@ -389,7 +398,7 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
                 x.atomic_add(&S.hist[b], 1u);
             }
         });
-        n_tok += (int)pre[DF_CH / 32];
+        n_tok += (int)n_chunk;
         x.tick(4);
     }
     // ---- 3. codes ----
@@ -416,7 +425,7 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
     x.par(64, [&](int t) {
         if (t & 31) return;
         const int w = t >> 5, o = w ? 288 : 0;
-        df_tree(S.sorted + o, S.n_used[w], 15, S.len + o, S.code + o, w ? DF_ND : DF_NLL, S.wi + o, S.par_leaf + o, S.par_int + o, S.depth_int + o);
+        df_tree(S.sorted + o, S.n_used[w], 15, S.len + o, S.code + o, w ? DF_ND : DF_NLL, S.wi + o, S.par_leaf + o, S.par_int + o, S.depth_int + o, S.tscr[w]);
     });
     x.tick(6);
     x.par(1, [&](int) {
@@ -424,54 +433,49 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         int hlit = DF_NLL, hdist = DF_ND;
         while (hlit > 257 && !S.len[hlit - 1]) --hlit;
         while (hdist > 1 && !S.len[288 + hdist - 1]) --hdist;
-        uint8_t seq[DF_NLL + DF_ND];
-        int ns = 0;
-        for (int s = 0; s < hlit; ++s) seq[ns++] = S.len[s];
-        for (int s = 0; s < hdist; ++s) seq[ns++] = S.len[288 + s];
-        uint32_t clf[DF_NCL];
-        for (int s = 0; s < DF_NCL; ++s) clf[s] = 0;
+        const int ns = hlit + hdist;
+        auto seq = [&](int p) { return (int)S.len[p < hlit ? p : 288 + p - hlit]; };   // the two length tables back to back
+        for (int k = 0; k < DF_NCL; ++k) S.clf[k] = 0;
         int nr = 0;
         for (int i = 0; i < ns;) {
-            const int v = seq[i];
+            const int v = seq(i);
             int c = 1;
-            while (i + c < ns && seq[i + c] == v) ++c;
+            while (i + c < ns && seq(i + c) == v) ++c;
             i += c;
             if (v == 0) {
-                while (c >= 11) { const int r = c < 138 ? c : 138; S.rle[nr++] = (uint16_t)(18 | (r - 11) << 8); ++clf[18]; c -= r; }
-                if (c >= 3) { S.rle[nr++] = (uint16_t)(17 | (c - 3) << 8); ++clf[17]; c = 0; }
-                for (; c > 0; --c) { S.rle[nr++] = 0; ++clf[0]; }
+                while (c >= 11) { const int r = c < 138 ? c : 138; S.rle[nr++] = (uint16_t)(18 | (r - 11) << 8); ++S.clf[18]; c -= r; }
+                if (c >= 3) { S.rle[nr++] = (uint16_t)(17 | (c - 3) << 8); ++S.clf[17]; c = 0; }
+                for (; c > 0; --c) { S.rle[nr++] = 0; ++S.clf[0]; }
             } else {
-                S.rle[nr++] = (uint16_t)v; ++clf[v]; --c;
-                while (c >= 3) { const int r = c < 6 ? c : 6; S.rle[nr++] = (uint16_t)(16 | (r - 3) << 8); ++clf[16]; c -= r; }
-                for (; c > 0; --c) { S.rle[nr++] = (uint16_t)v; ++clf[v]; }
+                S.rle[nr++] = (uint16_t)v; ++S.clf[v]; --c;
+                while (c >= 3) { const int r = c < 6 ? c : 6; S.rle[nr++] = (uint16_t)(16 | (r - 3) << 8); ++S.clf[16]; c -= r; }
+                for (; c > 0; --c) { S.rle[nr++] = (uint16_t)v; ++S.clf[v]; }
             }
         }
         S.n_rle = nr;
-        // the code of the code lengths: at most 7 bits, 19 symbols -- sorted by insertion
-        uint32_t srt[DF_NCL]; int m = 0;
-        for (int s = 0; s < DF_NCL; ++s) {
-            if (!clf[s]) continue;
-            const uint32_t key = clf[s] << 9 | (uint32_t)s;
-            int k = m++;
-            while (k > 0 && srt[k - 1] > key) { srt[k] = srt[k - 1]; --k; }
-            srt[k] = key;
+        // the code of the code lengths: at most 7 bits, 19 symbols -- sorted by insertion (the big trees' scratch is free again)
+        int m = 0;
+        for (int k = 0; k < DF_NCL; ++k) {
+            if (!S.clf[k]) continue;
+            const uint32_t key = S.clf[k] << 9 | (uint32_t)k;
+            int q = m++;
+            while (q > 0 && S.cl_sorted[q - 1] > key) { S.cl_sorted[q] = S.cl_sorted[q - 1]; --q; }
+            S.cl_sorted[q] = key;
         }
-        uint8_t cl_len[DF_NCL]; uint16_t cl_code[DF_NCL];
-        uint32_t wi[DF_NCL]; uint16_t pl[DF_NCL], pi[DF_NCL], di[DF_NCL];
-        df_tree(srt, m, 7, cl_len, cl_code, DF_NCL, wi, pl, pi, di);
-        const uint8_t order[DF_NCL] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        df_tree(S.cl_sorted, m, 7, S.cl_len, S.cl_code, DF_NCL, S.wi, S.par_leaf, S.par_int, S.depth_int, S.tscr[2]);
         int hclen = DF_NCL;
-        while (hclen > 4 && !cl_len[order[hclen - 1]]) --hclen;
-        for (int w = 0; w < 80; ++w) S.hdr[w] = 0;
-        DfBits B = {S.hdr, 0};
+        while (hclen > 4 && !S.cl_len[S.order[hclen - 1]]) --hclen;
+        DfBits B = {S.hdr, 0, 0, 0};
         B.put(1, 1); B.put(2, 2);                                // BFINAL, BTYPE = dynamic
         B.put((uint32_t)(hlit - 257), 5); B.put((uint32_t)(hdist - 1), 5); B.put((uint32_t)(hclen - 4), 4);
-        for (int k = 0; k < hclen; ++k) B.put(cl_len[order[k]], 3);
+        for (int k = 0; k < hclen; ++k) B.put(S.cl_len[S.order[k]], 3);
         for (int k = 0; k < nr; ++k) {
-            const int s = S.rle[k] & 0xff, xv = S.rle[k] >> 8;
-            B.put(cl_code[s], cl_len[s]);
-            if (s == 16) B.put((uint32_t)xv, 2); else if (s == 17) B.put((uint32_t)xv, 3); else if (s == 18) B.put((uint32_t)xv, 7);
+            const int sy = S.rle[k] & 0xff, xv = S.rle[k] >> 8;
+            // the code and its extra bits in one go (at most 7 + 7 bits)
+            const int xb = sy == 16 ? 2 : sy == 17 ? 3 : sy == 18 ? 7 : 0;
+            B.put(S.cl_code[sy] | (uint32_t)xv << S.cl_len[sy], S.cl_len[sy] + xb);
         }
+        B.finish();
         S.hdr_bits = B.n;
     });
     x.tick(7);
