@@ -63,7 +63,7 @@ struct DeflateShared {
     // what one thread's serial passes index dynamically lives here, not in local memory (with ~200 KB of the SM's L1 carved out
     // as shared memory, a local-memory access is an L2 round trip)
     int32_t entry[DF_CH / 32 + 1]; uint32_t pre[DF_CH / 32 + 1];
-    uint32_t tscr[3][36];                     // df_tree: code counts per length, next code per length (literal/length, distance, code-length tree)
+    uint32_t tscr[3][52];                     // df_tree: code counts per length, next code per length (literal/length, distance, code-length tree)
     uint32_t clf[DF_NCL], cl_sorted[DF_NCL]; uint8_t cl_len[DF_NCL + 1], order[DF_NCL + 1]; uint16_t cl_code[DF_NCL + 1];
     uint32_t crc_tab[256], x2n[32];
     uint32_t crc;
@@ -208,48 +208,81 @@ BSB_HD uint32_t df_x8n(const uint32_t *x2n, uint32_t n)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Code lengths of one tree. sorted[0, m): (freq << 9 | symbol) ascending; m >= 1. Serial (one thread per tree).
+// Code lengths of one tree, in pieces so that the block can run the data-parallel ones across its threads.
+// sorted[0, m): (freq << 9 | symbol) ascending. scr: 52 words -- [0, 16) codes per length, [16, 33) next canonical code per
+// length, [33, 50) rank in `sorted` at which each length starts.
+//
+// (1) serial, m >= 2: the Huffman merge with two queues -- the leaves in ascending weight, the internal nodes in the order
+// they are made (ascending too); on a tie the leaf goes first, which keeps the tree shallow -- and the depth of every internal node
+BSB_HD void df_tree_merge(const uint32_t *sorted, int m, uint32_t *wi, uint16_t *par_leaf, uint16_t *par_int, uint16_t *depth_int)
+{
+    int a = 0, b = 0;
+    for (int j = 0; j < m - 1; ++j) {
+        uint32_t w = 0;
+        for (int k = 0; k < 2; ++k) {
+            if (a < m && (b >= j || (sorted[a] >> 9) <= wi[b])) { w += sorted[a] >> 9; par_leaf[a++] = (uint16_t)j; }
+            else { w += wi[b]; par_int[b++] = (uint16_t)j; }
+        }
+        wi[j] = w;
+    }
+    depth_int[m - 2] = 0;
+    for (int j = m - 3; j >= 0; --j) depth_int[j] = (uint16_t)(depth_int[par_int[j]] + 1);
+}
+// (2) per leaf: its code length, clamped to the limit
+BSB_HD int df_tree_leaf_len(int m, int i, int limit, const uint16_t *par_leaf, const uint16_t *depth_int)
+{
+    if (m == 1) return 1;
+    const int d = depth_int[par_leaf[i]] + 1;
+    return d < limit ? d : limit;
+}
+// (3) serial, short: the clamped lengths over-subscribe the code space; every step gives one unit of it back (one code leaves
+// the last level, one code one level up takes a sibling with it). Then where each length starts among the sorted symbols (the
+// rarest take the longest codes) and the first canonical code of each length (RFC 1951 3.2.2)
+BSB_HD void df_tree_limit(uint32_t *scr, int limit)
+{
+    uint32_t *bl = scr, *next = scr + 16, *start = scr + 33;
+    uint32_t total = 0;
+    for (int d = 1; d <= limit; ++d) total += bl[d] << (limit - d);
+    while (total > (1u << limit)) {
+        --bl[limit];
+        for (int d = limit - 1; d > 0; --d)
+            if (bl[d]) { --bl[d]; bl[d + 1] += 2; break; }
+        --total;
+    }
+    uint32_t at = 0;
+    for (int d = 15; d >= 1; --d) { start[d] = at; at += d <= limit ? bl[d] : 0u; }
+    uint32_t c = 0;
+    next[0] = 0;
+    for (int d = 1; d <= 15; ++d) { c = (c + bl[d - 1]) << 1; next[d] = c; }
+}
+// (4) the length of the i-th sorted symbol
+BSB_HD int df_tree_len_of_rank(const uint32_t *scr, int limit, uint32_t i)
+{
+    const uint32_t *bl = scr, *start = scr + 33;
+    for (int d = limit; d >= 1; --d)
+        if (i < start[d] + bl[d]) return d;
+    return 0;
+}
+// (5) the canonical code of symbol s: the first code of its length + the number of smaller symbols with that length, bit-reversed
+BSB_HD uint32_t df_tree_code(const uint32_t *scr, const uint8_t *len, int s)
+{
+    const int l = len[s];
+    if (!l) return 0;
+    uint32_t r = 0;
+    for (int u = 0; u < s; ++u) r += len[u] == l;
+    return df_rev(scr[16 + l] + r, l);
+}
+// all of it by one thread (the small tree of the code lengths)
 BSB_HD void df_tree(const uint32_t *sorted, int m, int limit, uint8_t *len, uint16_t *code, int n_sym,
                     uint32_t *wi, uint16_t *par_leaf, uint16_t *par_int, uint16_t *depth_int, uint32_t *scr)
 {
     for (int s = 0; s < n_sym; ++s) { len[s] = 0; code[s] = 0; }
-    uint32_t *bl = scr, *next = scr + 16;      // [16] codes per length, [17] next code per length
-    for (int d = 0; d < 16; ++d) bl[d] = 0;
-    if (m == 1) { len[sorted[0] & 511] = 1; bl[1] = 1; }
-    else {
-        // two queues: the leaves in ascending weight, the internal nodes in the order they are made (ascending too);
-        // on a tie the leaf goes first, which keeps the tree shallow
-        int a = 0, b = 0;
-        for (int j = 0; j < m - 1; ++j) {
-            uint32_t w = 0;
-            for (int k = 0; k < 2; ++k) {
-                if (a < m && (b >= j || (sorted[a] >> 9) <= wi[b])) { w += sorted[a] >> 9; par_leaf[a++] = (uint16_t)j; }
-                else { w += wi[b]; par_int[b++] = (uint16_t)j; }
-            }
-            wi[j] = w;
-        }
-        depth_int[m - 2] = 0;
-        for (int j = m - 3; j >= 0; --j) depth_int[j] = (uint16_t)(depth_int[par_int[j]] + 1);
-        for (int i = 0; i < m; ++i) { int d = depth_int[par_leaf[i]] + 1; if (d > limit) d = limit; ++bl[d]; }
-        // depth limit: the clamped lengths over-subscribe the code space; every step gives one unit of it back
-        // (one code leaves the last level, one code one level up takes a sibling with it)
-        uint32_t total = 0;
-        for (int d = 1; d <= limit; ++d) total += bl[d] << (limit - d);
-        while (total > (1u << limit)) {
-            --bl[limit];
-            for (int d = limit - 1; d > 0; --d)
-                if (bl[d]) { --bl[d]; bl[d + 1] += 2; break; }
-            --total;
-        }
-        int i = 0;                             // the rarest symbols take the longest codes
-        for (int d = limit; d >= 1; --d)
-            for (uint32_t c2 = 0; c2 < bl[d]; ++c2) len[sorted[i++] & 511] = (uint8_t)d;
-    }
-    uint32_t c = 0;                            // canonical codes (RFC 1951 3.2.2)
-    next[0] = 0;
-    for (int d = 1; d <= 15; ++d) { c = (c + bl[d - 1]) << 1; next[d] = c; }
-    for (int s = 0; s < n_sym; ++s)
-        if (len[s]) code[s] = (uint16_t)df_rev(next[len[s]]++, len[s]);
+    for (int d = 0; d < 16; ++d) scr[d] = 0;
+    if (m >= 2) df_tree_merge(sorted, m, wi, par_leaf, par_int, depth_int);
+    for (int i = 0; i < m; ++i) ++scr[df_tree_leaf_len(m, i, limit, par_leaf, depth_int)];
+    df_tree_limit(scr, limit);
+    for (int i = 0; i < m; ++i) len[sorted[i] & 511] = (uint8_t)df_tree_len_of_rank(scr, limit, (uint32_t)i);
+    for (int s = 0; s < n_sym; ++s) code[s] = (uint16_t)df_tree_code(scr, len, s);
 }
 
 struct DfBits {                                // the header's bit writer (one thread): bits collect in a register, whole words leave
@@ -422,10 +455,28 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         S.sorted[lo + r] = key;
     });
     x.tick(5);
+    // the two big trees: the merge by one thread each, everything around it across the block
+    x.par(320, [&](int t) {
+        S.len[t] = 0; S.code[t] = 0;
+        if (t < 32) { S.tscr[0][t] = 0; S.tscr[1][t] = 0; }
+    });
     x.par(64, [&](int t) {
         if (t & 31) return;
         const int w = t >> 5, o = w ? 288 : 0;
-        df_tree(S.sorted + o, S.n_used[w], 15, S.len + o, S.code + o, w ? DF_ND : DF_NLL, S.wi + o, S.par_leaf + o, S.par_int + o, S.depth_int + o, S.tscr[w]);
+        if (S.n_used[w] >= 2) df_tree_merge(S.sorted + o, S.n_used[w], S.wi + o, S.par_leaf + o, S.par_int + o, S.depth_int + o);
+    });
+    x.par(320, [&](int t) {
+        const int w = t >= 288, o = w ? 288 : 0;
+        if (t - o < S.n_used[w]) x.atomic_add(&S.tscr[w][df_tree_leaf_len(S.n_used[w], t - o, 15, S.par_leaf + o, S.depth_int + o)], 1u);
+    });
+    x.par(64, [&](int t) { if (!(t & 31)) df_tree_limit(S.tscr[t >> 5], 15); });
+    x.par(320, [&](int t) {
+        const int w = t >= 288, o = w ? 288 : 0;
+        if (t - o < S.n_used[w]) S.len[o + (S.sorted[t] & 511)] = (uint8_t)df_tree_len_of_rank(S.tscr[w], 15, (uint32_t)(t - o));
+    });
+    x.par(320, [&](int t) {
+        const int w = t >= 288, o = w ? 288 : 0;
+        if (t - o < (w ? DF_ND : DF_NLL)) S.code[t] = (uint16_t)df_tree_code(S.tscr[w], S.len + o, t - o);
     });
     x.tick(6);
     x.par(1, [&](int) {
