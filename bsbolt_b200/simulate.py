@@ -2,7 +2,9 @@
 
 Follows the conventions of the reference generator (`bsbolt Simulate`: bsbolt/Simulate/SimulateMethylatedReads.py
 + External/WGSIM/src/wgsim.cpp) -- read names `@<id>_<contig>/1|2`, truth on the `+` line as
-`contig:start:end:cigar:{W|C}{C2T|G2A}`, directional reads C->T on read 1 / G->A on read 2, optional
+`contig:start:end:cigar:{W|C}{C2T|G2A}` (start/end: the mate's own forward-strand window, 0-based, end exclusive; the cigar is
+`<L>M` here where the reference prints one letter per base), checked against reads of the reference generator in
+tests/test_simulator_conventions.py, directional reads C->T on read 1 / G->A on read 2, optional
 undirectional swap, SNP/indel/sequencing-error rates with the same defaults -- but is reproducible from its
 seed (the reference mixes std::random_device into wgsim and unseeded Python `random`) and fast enough to
 produce millions of pairs inside a benchmark run. It is NOT on the alignment path.
@@ -187,10 +189,15 @@ def simulate_reads(names, contigs, out_prefix, n_pairs, read_len=150, paired=Tru
                 c = names[ci[j]]
                 tag1 = ('W' if watson[j] else 'C') + ('G2A' if swap[j] else 'C2T')
                 s0, e0 = int(start[j]), int(start[j] + frag[j])
-                files[0].write(b'@%d_%s/1\n' % (rid, c.encode()) + r1[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), s0, e0, L, tag1.encode()) + qual + b'\n')
+                # like the reference generator (SimulateMethylatedReads.output_sim_reads), every mate carries the forward-strand
+                # window it was read from: the C2T mate of a Watson fragment and the G2A mate of a Crick fragment the left one
+                left_w, right_w = (s0, s0 + L), (e0 - L, e0)
+                w1 = left_w if bool(watson[j]) != bool(swap[j]) else right_w
+                files[0].write(b'@%d_%s/1\n' % (rid, c.encode()) + r1[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), w1[0], w1[1], L, tag1.encode()) + qual + b'\n')
                 if paired:
                     tag2 = ('W' if watson[j] else 'C') + ('C2T' if swap[j] else 'G2A')
-                    files[1].write(b'@%d_%s/2\n' % (rid, c.encode()) + r2[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), s0, e0, L, tag2.encode()) + qual + b'\n')
+                    w2 = right_w if w1 is left_w else left_w
+                    files[1].write(b'@%d_%s/2\n' % (rid, c.encode()) + r2[j].tobytes() + b'\n+%s:%d:%d:%dM:%s\n' % (c.encode(), w2[0], w2[1], L, tag2.encode()) + qual + b'\n')
                 rid += 1
         done += len(good)
     for f in files:
