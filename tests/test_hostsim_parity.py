@@ -80,11 +80,12 @@ def test_reference_binary_reproduces_golden(built, golden):
 
 def test_differential_fuzz_of_the_kernel_bodies(built, tmp_path):
     """tools/fuzz_hostsim.py: adversarial reads under random option sets, kernel bodies on the CPU against the compiled
-    reference (skipped where oracle/_ref/bwa is absent)"""
+    reference (skipped where oracle/_ref/bwa is absent); with --bam every run is also written as BAM through the emulated device
+    stage (arbiter, record encoder, deflate) and through the host encoder, and the inflated streams must be identical"""
     import sys
     if not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'bwa')):
         pytest.skip('oracle/_ref/bwa not built')
-    p = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_hostsim.py'), '--runs', '5', '--reads', '300', '--seed', '3',
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_hostsim.py'), '--runs', '5', '--reads', '300', '--seed', '3', '--bam',
                         '--work', str(tmp_path / 'fz')], capture_output=True, text=True, errors='backslashreplace')
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-1000:]
-    assert p.stdout.count('-> identical') == 5
+    assert p.stdout.count('-> identical') == 5 and p.stdout.count('BAM stream identical') == 5

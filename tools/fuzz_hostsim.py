@@ -18,6 +18,7 @@ def main():
     ap.add_argument('--first', type=int, default=0, help='first run to execute (a run is determined by seed and run number)')
     ap.add_argument('--keep', action='store_true', help='keep ref.sam / mine.sam / logs of a differing run under --work')
     ap.add_argument('--long', action='store_true', help='mix in reads of 700-1200 bp (mem_flt_chained_seeds territory) and smart pairing (-p)')
+    ap.add_argument('--bam', action='store_true', help='also write the run as BAM twice on the CPU harness -- through the emulated device stage (arbiter, bam_record, bgzf_block) and through the host encoder -- and compare the inflated streams')
     ap.add_argument('--gpu', action='store_true', help='run the product (bsbolt_b200/bwa, the bwa-compatible binary over the C ABI) on cuda:0 instead of the CPU harness')
     a = ap.parse_args()
     os.makedirs(a.work + '/db', exist_ok=True)
@@ -135,7 +136,19 @@ def main():
         x, y = strip(ref.stdout), strip(me.stdout)
         bs = lambda t: sorted(l for l in t.split('\n') if l.startswith('BSStat'))
         ok = ref.returncode == 0 and me.returncode == 0 and x == y and bs(ref.stderr) == bs(me.stderr)
-        print(f'run {run}: {"PE" if paired else "SE"} {len(x)} records {" ".join(extra)} -> {"identical" if ok else "DIFFERENT"}', flush=True)
+        bam_note = ''
+        if ok and a.bam and not a.gpu:
+            raws, logs = [], []
+            for host in (False, True):
+                env = dict(os.environ, BSB_HOSTSIM_SEED_V3='1', HOSTSIM_BAM=f'{a.work}/fuzz_{int(host)}.bam')
+                if host: env['HOSTSIM_BAM_HOST'] = '1'
+                r = subprocess.run([ROOT + '/tests/hostsim/hostsim'] + argv, capture_output=True, text=True, errors='backslashreplace', env=env)
+                if r.returncode: print('BAM run failed:', r.stderr[-400:]); sys.exit(1)
+                raws.append(gzip.open(f'{a.work}/fuzz_{int(host)}.bam', 'rb').read()); logs.append(bs(r.stderr))
+            if raws[0] != raws[1] or logs[0] != logs[1] or logs[0] != bs(me.stderr):
+                print(f'run {run}: BAM streams differ (device stage {len(raws[0])} bytes, host encoder {len(raws[1])} bytes), BSStat equal {logs[0] == logs[1]}'); print('argv:', ' '.join(argv)); sys.exit(1)
+            bam_note = f', BAM stream identical ({len(raws[0])} bytes)'
+        print(f'run {run}: {"PE" if paired else "SE"} {len(x)} records {" ".join(extra)} -> {"identical" if ok else "DIFFERENT"}{bam_note}', flush=True)
         if not ok:
             print('ref rc', ref.returncode, 'mine rc', me.returncode, 'records', len(x), len(y), 'bsstat equal', bs(ref.stderr) == bs(me.stderr), me.stderr[-300:])
             if a.keep:
