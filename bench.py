@@ -472,13 +472,17 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
             raise RuntimeError(_native.last_error())
         return time.time() - t, st_b
 
+    # from four GPUs on the timed input makes a BAM file of 10 GB and more: the blocks are discarded there (like `e2e` discards its
+    # text) rather than risking the box's scratch space
+    bam_sink = os.devnull if n_dev >= 4 else None
+
     def bam_timed():
         try:
-            return mem_bam(f1, f2, -1)
+            return mem_bam(f1, f2, -1, bam_sink)
         except Exception as e:  # noqa  (the SAM line above stands on its own; a failure here is reported, not fatal)
             return None, str(e)
     try:
-        mem_bam(w1 if W else f1, w2 if W else f2, -1)                                     # (sizes the BAM stage's buffers)
+        mem_bam(w1 if W else f1, w2 if W else f2, -1, bam_sink)                           # (sizes the BAM stage's buffers)
     except Exception:  # noqa
         pass
     dt, st_b = fenced(bam_timed)
@@ -487,11 +491,12 @@ def b200_arm(a, W, K, n_dev, work, db, bwa, cores, config, K_bases, extra_args, 
     else:
         nbt = max(1, st_b['n_batches'])
         bam_info = {'api': 'bsb_mem_main_bam%s (one FASTQ pair on the host -> one BGZF/BAM file), default level: compressed on the device' % ('_multi' if n_dev > 1 else ''),
-                    'unit': 'reads/s', 'value': n_reads_timed / dt, 'reads': n_reads_timed, 'wall_s': dt, 'file_bytes': os.path.getsize(bam_path),
+                    'unit': 'reads/s', 'value': n_reads_timed / dt, 'reads': n_reads_timed, 'wall_s': dt, 'sink': 'file' if bam_sink is None else '/dev/null',
+                    'file_bytes': os.path.getsize(bam_path) if bam_sink is None else None,
                     'd2h_bytes_per_step': st_b['d2h_bytes'] / nbt * n_dev, 'bam_bytes_per_step': st_b['bam_raw_bytes'] / nbt * n_dev,
                     'bgzf_bytes_per_step': st_b['bam_bgzf_bytes'] / nbt * n_dev,
                     'device_ms_per_batch': {'sam_text': st_b['ms_text'] / nbt, 'arbiter_records_deflate': st_b['ms_bam'] / nbt}}
-    if dt is not None:
+    if dt is not None and bam_sink is None:
         try:   # the same run with the blocks discarded, like `e2e` discards its SAM text: what the file system costs above
             dt0, _ = mem_bam(f1, f2, -1, os.devnull)
             bam_info['to_dev_null'] = {'value': n_reads_timed / dt0, 'wall_s': dt0}
