@@ -362,11 +362,12 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
             if (t < L) {
                 const int lim = n - i < DF_MAX_MATCH ? n - i : DF_MAX_MATCH;
                 if (lim >= DF_MIN_MATCH) {
-                    const uint32_t h = (df_word(w32, i) * 2654435761u) >> (32 - DF_HASH_BITS);
+                    const uint32_t four = df_word(w32, i);
+                    const uint32_t h = (four * 2654435761u) >> (32 - DF_HASH_BITS);
                     hh = h;
                     if (i > 0) { const int l = df_run_len(S.eq, i, lim); if (l >= DF_MIN_MATCH) { best = l; dist = 1; } }
                     const int c = (int)(S.head[h >> 1] >> ((h & 1) << 4) & 0xffffu) - 1;
-                    if (best < DF_GOOD_RUN && best < lim && c >= 0 && i - c <= DF_MAX_DIST) {   /* (a long run is taken as it is) */ const int l = df_match_len(w32, c, i, lim < DF_MAX_HASH_MATCH ? lim : DF_MAX_HASH_MATCH); if (l >= DF_MIN_MATCH && l > best) { best = l; dist = i - c; } }
+                    if (best < DF_GOOD_RUN && best < lim && c >= 0 && i - c <= DF_MAX_DIST && df_word(w32, c) == four) {   /* (a long run is taken as it is; most table hits are other 4-grams) */ const int l = df_match_len(w32, c, i, lim < DF_MAX_HASH_MATCH ? lim : DF_MAX_HASH_MATCH); if (l >= DF_MIN_MATCH && l > best) { best = l; dist = i - c; } }
                 }
             }
             S.hash[t] = (uint16_t)hh;
