@@ -34,7 +34,7 @@ class Read(C.Structure):
     _fields_ = [('name', C.c_char_p), ('comment', C.c_char_p), ('seq', C.c_char_p), ('qual', C.c_char_p)]
 
 
-EXPORTS = ('bsb_version', 'bsb_last_error', 'bsb_device_count', 'bsb_index_load', 'bsb_index_free',
+EXPORTS = ('bsb_version', 'bsb_last_error', 'bsb_device_count', 'bsb_run_stats_size', 'bsb_index_load', 'bsb_index_free',
            'bsb_index_hbm_bytes', 'bsb_index_n_contigs', 'bsb_mem_main', 'bsb_batch_create', 'bsb_batch_align',
            'bsb_batch_sam', 'bsb_batch_n_entries', 'bsb_batch_free', 'bsb_sam_header', 'bsb_index_build',
            'bsb_mem_main_bam', 'bsb_stream_bam', 'bsb_index_clone', 'bsb_mem_main_multi', 'bsb_mem_main_multi_bam', 'bsb_random_sector_peak')
@@ -52,6 +52,10 @@ def lib():
     L.bsb_version.restype = C.c_char_p
     L.bsb_last_error.restype = C.c_char_p
     L.bsb_device_count.restype = C.c_int
+    L.bsb_run_stats_size.restype = C.c_size_t
+    if L.bsb_run_stats_size() != C.sizeof(RunStats):   # a stale library next to a newer binding (or the reverse) would scribble over memory
+        raise NativeLibraryMissing(f'{_LIB_PATH} was built from another include/bsbolt_b200.h (bsb_run_stats_t is '
+                                   f'{L.bsb_run_stats_size()} bytes there, {C.sizeof(RunStats)} here): rebuild with `make -C bsbolt_b200/csrc`')
     L.bsb_index_load.restype = C.c_void_p
     L.bsb_index_load.argtypes = [C.c_char_p, C.c_int]
     L.bsb_index_free.argtypes = [C.c_void_p]

@@ -58,6 +58,8 @@ extern "C" {
 const char *bsb_version(void) { return "bsbolt_b200 0.1 (BSB-1.2.1-BWA-fork-0.7.17 semantics, sm_100a)"; }
 const char *bsb_last_error(void) { return g_err.c_str(); }
 
+size_t bsb_run_stats_size(void) { return sizeof(bsb_run_stats_t); }
+
 int bsb_device_count(void)
 {
     int n = 0;

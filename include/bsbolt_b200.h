@@ -59,6 +59,7 @@ typedef struct {
 const char *bsb_version(void);
 const char *bsb_last_error(void);
 int bsb_device_count(void);                       /* number of CUDA devices, 0 if none */
+size_t bsb_run_stats_size(void);                  /* sizeof(bsb_run_stats_t) of the library: a binding checks its own layout against it */
 
 /* replaces bwa_idx_load(hint, BWA_IDX_ALL) (bwa.c:407-443): reads <idxbase>.bwt .sa .ann .amb .pac .opac
  * and uploads them to HBM of `device` */
