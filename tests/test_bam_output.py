@@ -185,6 +185,22 @@ def test_device_deflate_blocks_inflate_to_the_input(built, tmp_path, order):
         'block': bytes(range(256)) * 255, 'block+1': bytes(range(256)) * 255 + b'z',
         'skewed': bytes(random.choices(range(256), weights=[2 ** (-(i / 4)) for i in range(256)], k=200000)),
     }
+    # seeded mixtures: literals, runs, near and far repeats (up to the 32 KB window and beyond), lengths around the block and chunk edges
+    for k in range(24):
+        parts, total = [], random.choice([5, 511, 512, 513, 4097, 65279, 65280, 65281, 130560, random.randrange(1, 200000)])
+        while sum(map(len, parts)) < total:
+            kind = random.random()
+            if kind < 0.3 or not parts:
+                parts.append(random.randbytes(random.randrange(1, 300)))
+            elif kind < 0.5:
+                parts.append(bytes([random.randrange(256)]) * random.randrange(1, 700))
+            else:
+                flat = b''.join(parts)
+                a = random.randrange(len(flat)); l = random.randrange(3, 400)
+                if random.random() < 0.3:
+                    a = max(0, len(flat) - random.randrange(1, 70000))
+                parts.append(flat[a:a + l])
+        cases[f'mix{k}'] = b''.join(parts)[:total]
     env = dict(os.environ)
     if order:
         env['BSB_PAR_ORDER'] = order
