@@ -67,7 +67,8 @@ struct DeflateShared {
     uint32_t clf[DF_NCL], cl_sorted[DF_NCL]; uint8_t cl_len[DF_NCL + 1], order[DF_NCL + 1]; uint16_t cl_code[DF_NCL + 1];
     uint32_t crc_tab[256], x2n[32];
     uint32_t crc;
-    int n_used[2], n_rle, hdr_bits, stored;
+    int n_used[2], hdr_bits, stored, hlit, hdist;
+    uint16_t rcnt[320], roff[320]; uint32_t rgrp[11];   // the header's run-length symbols: counts / bit sizes, their prefix sums
     uint32_t total_bits;
 };
 
@@ -480,31 +481,59 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         if (t - o < (w ? DF_ND : DF_NLL)) S.code[t] = (uint16_t)df_tree_code(S.tscr[w], S.len + o, t - o);
     });
     x.tick(6);
-    x.par(1, [&](int) {
-        // code lengths of both trees, run-length coded with the symbols 16 (repeat previous 3-6), 17 (zeros 3-10), 18 (zeros 11-138)
-        int hlit = DF_NLL, hdist = DF_ND;
-        while (hlit > 257 && !S.len[hlit - 1]) --hlit;
-        while (hdist > 1 && !S.len[288 + hdist - 1]) --hdist;
-        const int ns = hlit + hdist;
-        auto seq = [&](int p) { return (int)S.len[p < hlit ? p : 288 + p - hlit]; };   // the two length tables back to back
-        for (int k = 0; k < DF_NCL; ++k) S.clf[k] = 0;
-        int nr = 0;
-        for (int i = 0; i < ns;) {
-            const int v = seq(i);
-            int c = 1;
-            while (i + c < ns && seq(i + c) == v) ++c;
-            i += c;
-            if (v == 0) {
-                while (c >= 11) { const int r = c < 138 ? c : 138; S.rle[nr++] = (uint16_t)(18 | (r - 11) << 8); ++S.clf[18]; c -= r; }
-                if (c >= 3) { S.rle[nr++] = (uint16_t)(17 | (c - 3) << 8); ++S.clf[17]; c = 0; }
-                for (; c > 0; --c) { S.rle[nr++] = 0; ++S.clf[0]; }
-            } else {
-                S.rle[nr++] = (uint16_t)v; ++S.clf[v]; --c;
-                while (c >= 3) { const int r = c < 6 ? c : 6; S.rle[nr++] = (uint16_t)(16 | (r - 3) << 8); ++S.clf[16]; c -= r; }
-                for (; c > 0; --c) { S.rle[nr++] = (uint16_t)v; ++S.clf[v]; }
+    // The block header. The code lengths of both trees, back to back, are run-length coded with the symbols 16 (repeat the
+    // previous length 3-6 times), 17 (3-10 zeros), 18 (11-138 zeros): one thread per RUN of equal lengths emits that run's
+    // symbols (count, scan, write -- like the tokens), one thread builds the 19-symbol code of those symbols, then every symbol is
+    // sized, a scan places it and its bits are ORed into the header words.
+    x.par(320, [&](int t) {
+        if (t == 0) { int h = DF_NLL; while (h > 257 && !S.len[h - 1]) --h; S.hlit = h; }
+        if (t == 32) { int h = DF_ND; while (h > 1 && !S.len[288 + h - 1]) --h; S.hdist = h; }
+        if (t >= 64 && t < 64 + DF_NCL) S.clf[t - 64] = 0;
+        if (t >= 96 && t < 96 + 80) S.hdr[t - 96] = 0;
+    });
+    const int hlit = S.hlit, hdist = S.hdist, ns = hlit + hdist;
+    auto seq = [&](int p) { return (int)S.len[p < hlit ? p : 288 + p - hlit]; };   // the two length tables back to back
+    // the symbols of one run of c equal lengths v, in order, through emit(symbol | extra << 8)
+    auto run_symbols = [&](int v, int c, auto emit) {
+        if (v == 0) {
+            while (c >= 11) { const int r = c < 138 ? c : 138; emit((uint32_t)(18 | (r - 11) << 8)); c -= r; }
+            if (c >= 3) { emit((uint32_t)(17 | (c - 3) << 8)); c = 0; }
+            for (; c > 0; --c) emit(0u);
+        } else {
+            emit((uint32_t)v); --c;
+            while (c >= 3) { const int r = c < 6 ? c : 6; emit((uint32_t)(16 | (r - 3) << 8)); c -= r; }
+            for (; c > 0; --c) emit((uint32_t)v);
+        }
+    };
+    // exclusive prefix sums of S.rcnt[0, 320) into S.roff, S.rgrp[10] = the total (two levels of 32)
+    auto scan320 = [&]() {
+        x.par(10, [&](int g) { uint32_t sum = 0; for (int k = 32 * g; k < 32 * g + 32; ++k) sum += S.rcnt[k]; S.rgrp[g] = sum; });
+        x.par(1, [&](int) { uint32_t c = 0; for (int g = 0; g <= 10; ++g) { const uint32_t v = g < 10 ? S.rgrp[g] : 0u; S.rgrp[g] = c; c += v; } });
+        x.par(320, [&](int p) { uint32_t o = S.rgrp[p >> 5]; for (int k = p & ~31; k < p; ++k) o += S.rcnt[k]; S.roff[p] = (uint16_t)o; });
+    };
+    x.par(320, [&](int p) {
+        uint32_t cnt = 0;
+        if (p < ns) {
+            const int v = seq(p);
+            if (p == 0 || seq(p - 1) != v) {
+                int c = 1;
+                while (p + c < ns && seq(p + c) == v) ++c;
+                run_symbols(v, c, [&](uint32_t) { ++cnt; });
             }
         }
-        S.n_rle = nr;
+        S.rcnt[p] = (uint16_t)cnt;
+    });
+    scan320();
+    x.par(320, [&](int p) {
+        if (p >= ns || !S.rcnt[p]) return;
+        const int v = seq(p);
+        int c = 1;
+        while (p + c < ns && seq(p + c) == v) ++c;
+        uint32_t at = S.roff[p];
+        run_symbols(v, c, [&](uint32_t sy) { S.rle[at++] = (uint16_t)sy; x.atomic_add(&S.clf[sy & 0xff], 1u); });
+    });
+    const int nr = (int)S.rgrp[10];
+    x.par(1, [&](int) {
         // the code of the code lengths: at most 7 bits, 19 symbols -- sorted by insertion (the big trees' scratch is free again)
         int m = 0;
         for (int k = 0; k < DF_NCL; ++k) {
@@ -521,15 +550,25 @@ BSB_HD uint32_t bgzf_block(X &x, DeflateShared &S, const uint8_t *in, int n, uin
         B.put(1, 1); B.put(2, 2);                                // BFINAL, BTYPE = dynamic
         B.put((uint32_t)(hlit - 257), 5); B.put((uint32_t)(hdist - 1), 5); B.put((uint32_t)(hclen - 4), 4);
         for (int k = 0; k < hclen; ++k) B.put(S.cl_len[S.order[k]], 3);
-        for (int k = 0; k < nr; ++k) {
-            const int sy = S.rle[k] & 0xff, xv = S.rle[k] >> 8;
-            // the code and its extra bits in one go (at most 7 + 7 bits)
-            const int xb = sy == 16 ? 2 : sy == 17 ? 3 : sy == 18 ? 7 : 0;
-            B.put(S.cl_code[sy] | (uint32_t)xv << S.cl_len[sy], S.cl_len[sy] + xb);
-        }
-        B.finish();
+        B.finish();                                              // (at most 74 bits: the words behind them are still zero)
         S.hdr_bits = B.n;
     });
+    x.par(320, [&](int k) {
+        uint32_t nb = 0;
+        if (k < nr) { const int sy = S.rle[k] & 0xff; nb = (uint32_t)S.cl_len[sy] + (sy == 16 ? 2u : sy == 17 ? 3u : sy == 18 ? 7u : 0u); }
+        S.rcnt[k] = (uint16_t)nb;
+    });
+    scan320();
+    const int fixed_bits = S.hdr_bits;
+    x.par(320, [&](int k) {
+        if (k >= nr) return;
+        const int sy = S.rle[k] & 0xff, xv = S.rle[k] >> 8;
+        const uint32_t v = S.cl_code[sy] | (uint32_t)xv << S.cl_len[sy];     // the code and its extra bits: at most 7 + 7 bits
+        const uint32_t at = (uint32_t)fixed_bits + S.roff[k];
+        x.atomic_or(&S.hdr[at >> 5], v << (at & 31));
+        if ((at & 31) + S.rcnt[k] > 32) x.atomic_or(&S.hdr[(at >> 5) + 1], v >> (32 - (at & 31)));
+    });
+    x.par(1, [&](int) { S.hdr_bits = fixed_bits + (int)S.rgrp[10]; });
     x.tick(7);
     // ---- 4. bits ----
     const int per = (n_tok + DF_CH - 1) / DF_CH;
