@@ -217,14 +217,19 @@ BSB_HD uint32_t df_x8n(const uint32_t *x2n, uint32_t n)
 // they are made (ascending too); on a tie the leaf goes first, which keeps the tree shallow -- and the depth of every internal node
 BSB_HD void df_tree_merge(const uint32_t *sorted, int m, uint32_t *wi, uint16_t *par_leaf, uint16_t *par_int, uint16_t *depth_int)
 {
+    // the weights at the heads of the two queues wait in registers (the loop is one thread's chain of shared-memory latencies);
+    // NONE: that queue is empty -- for the internal nodes also "the next one is being made in this step"
+    const uint32_t NONE = 0xffffffffu;
     int a = 0, b = 0;
+    uint32_t lw = sorted[0] >> 9, iw = NONE;
     for (int j = 0; j < m - 1; ++j) {
         uint32_t w = 0;
         for (int k = 0; k < 2; ++k) {
-            if (a < m && (b >= j || (sorted[a] >> 9) <= wi[b])) { w += sorted[a] >> 9; par_leaf[a++] = (uint16_t)j; }
-            else { w += wi[b]; par_int[b++] = (uint16_t)j; }
+            if (lw != NONE && lw <= iw) { w += lw; par_leaf[a++] = (uint16_t)j; lw = a < m ? sorted[a] >> 9 : NONE; }
+            else { w += iw; par_int[b++] = (uint16_t)j; iw = b < j ? wi[b] : NONE; }
         }
         wi[j] = w;
+        if (b == j) iw = w;
     }
     depth_int[m - 2] = 0;
     for (int j = m - 3; j >= 0; --j) depth_int[j] = (uint16_t)(depth_int[par_int[j]] + 1);
