@@ -6,17 +6,23 @@
 // copies them to the file. Only the *uncompressed* stream is comparable with the reference (tests: inflate and compare);
 // the compressed bytes are this file's own.
 //
-// Shape (everything data-parallel over the block's threads, nothing is a per-thread zlib):
-//   1. Matches. The block is taken in chunks of CH positions, one per thread. Every position hashes its next 4 bytes and
-//      looks up the most recent earlier-chunk position with that hash (an atomic-max table in shared memory, so the table
-//      and hence the output do not depend on thread timing) plus the distance-1 candidate (runs); the longer match wins.
+// Shape (everything data-parallel over the block's threads, nothing is a per-thread zlib; the input block is staged in
+// shared memory first, and nothing a thread indexes dynamically lives in local memory -- with ~200 KB of the SM's L1 carved
+// out as shared memory a local access is an L2 round trip):
+//   1. Matches. The block is taken in chunks of DF_CH = 512 positions, one per thread. Every position hashes its next 4
+//      bytes and looks up the most recent earlier-chunk position with that hash (a 16-bit atomic-max table in shared memory,
+//      so the table and hence the output do not depend on thread timing; of neighbours with the same hash -- a run -- only the
+//      last one inserts) and compares 8 bytes a step, at most DF_MAX_HASH_MATCH bytes. The distance-1 candidate (runs) costs
+//      no compare: one bit per position says in[p] == in[p-1] and a run's length is a count of one bits. The longer wins.
 //   2. Parse. Greedy: from the position where the previous token ended, take the match there (or one literal) and jump
-//      behind it. The positions visited are found by pointer doubling over the chunk's jump table -- 8 rounds for 256
-//      positions, each marking the next 2^k hops -- instead of a serial walk; marked positions are compacted into tokens
-//      (ballot-style prefix over the mark words) and counted into the literal/length and distance histograms.
-//   3. Codes. Symbols are rank-sorted by frequency in parallel; one thread per tree runs the two-queue Huffman merge,
-//      limits the depth (Kraft repair) and assigns canonical codes; one thread run-length-codes the code lengths and
-//      writes the block header.
+//      behind it. The positions visited are found by pointer doubling over the chunk's jump table instead of a serial walk:
+//      five rounds INSIDE each warp's 32 positions (warp barriers only) give every position's way out of its segment,
+//      16 look-ups chain the segments, five more warp-local rounds mark the next 2^k hops; marked positions are compacted
+//      into tokens (prefix over the mark words) and counted into the literal/length and distance histograms.
+//   3. Codes. Symbols are rank-sorted by frequency in parallel; one thread per tree runs the two-queue Huffman merge (the
+//      only serial pass left); depths, the Kraft repair of the depth limit, the assignment of lengths and the canonical codes
+//      run across the block. The header: one thread per RUN of equal code lengths emits its run-length symbols (count, scan,
+//      write), one thread builds the 19-symbol code, then every symbol is sized, placed by a scan and ORed into the header.
 //   4. Bits. Every thread sizes a contiguous run of tokens, a scan gives its first bit, it packs its run in a 64-bit
 //      register and ORs whole words into the (zeroed) output; CRC-32 of the input is computed per slice and combined
 //      with x^n mod P multiplications.
