@@ -177,6 +177,24 @@ def reference_cpu_run(bwa, argv_tail, n_reads, threads, sam_out=os.devnull):
     return n_reads / (t_end - t_first), t_end - t_first
 
 
+def reference_cpu_bam_run(bwa, stream_bam, argv_tail, n_reads, threads, bam_out):
+    """The reference's default output pipeline, `bwa mem ... | stream_bam -@ T -o out.bam` (bsbolt/Align/AlignReads.py:51-56), timed like
+    reference_cpu_run; the clock stops when the BAM file is closed."""
+    cmd = [bwa, 'mem'] + LAUNCHER_ARGS + ['-t', str(threads)] + argv_tail
+    t_first = None
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=False)
+    q = subprocess.Popen([stream_bam, '-@', str(threads), '-o', bam_out], stdin=p.stdout, stderr=subprocess.DEVNULL)
+    p.stdout.close()
+    for line in p.stderr:
+        if t_first is None and line.startswith(b'[M::process] read'):
+            t_first = time.time()
+    p.wait(); q.wait()
+    t_end = time.time()
+    if p.returncode != 0 or q.returncode != 0 or t_first is None:
+        raise RuntimeError('reference aligner | stream_bam failed')
+    return n_reads / (t_end - t_first), t_end - t_first
+
+
 def compare_sam(ref_path, my_path):
     """record-by-record identity of two SAM files (headers: all but @PG, whose CL differs by construction)"""
     n = same = 0
@@ -351,6 +369,18 @@ def reference_arm(a, W, K, work, db, bwa, cores, config, K_bases, extra_args):
                                        f'{sec:.1f} s, clock from first batch read to exit'},
             'e2e': {'value': val, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'index': index_note}
+    # the reference's DEFAULT output (`-O prefix`): the same timed reads through `| stream_bam` into a BAM file -- the counterpart of
+    # the B200 arm's `e2e_bam`
+    stream_bam = os.path.join(os.path.dirname(bwa), 'stream_bam')
+    if os.path.exists(stream_bam):
+        try:
+            bam_out = os.path.join(work, 'ref_out.bam')
+            vb, sb = reference_cpu_bam_run(bwa, stream_bam, tail + [os.path.join(work, 'ref_timed_1.fq'), os.path.join(work, 'ref_timed_2.fq')], 2 * sp * K, cores, bam_out)
+            line['e2e_bam'] = {'value': vb, 'unit': 'reads/s', 'wall_s': sb, 'file_bytes': os.path.getsize(bam_out),
+                               'pipeline': f'oracle/_ref/bwa mem -t {cores} | oracle/_ref/stream_bam -@ {cores} -o file (bsbolt/Align/AlignReads.py:51-56)'}
+            os.remove(bam_out)
+        except Exception as e:  # noqa
+            line['e2e_bam'] = {'error': str(e)}
     print(json.dumps(line))
     if not a.keep:
         for f in [p for (paths, n) in sims for p in paths] + [os.path.join(work, f'ref_{w}_{k}.fq') for w in ('warm', 'timed') for k in (1, 2)]:
